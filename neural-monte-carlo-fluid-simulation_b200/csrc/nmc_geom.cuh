@@ -1,0 +1,491 @@
+// csrc/nmc_geom.cuh -- boundary acceleration structure (flattened BVH with normal cones, "SNCH")
+// and the geometric queries of the walk, as device functions over a SceneView.
+//
+// Replaces, for this path, FCPW's Sbvh traversal (deps/fcpw/include/fcpw/aggregates/sbvh.inl:538-1255),
+// its primitives (geometry/{line_segments,triangles,vertex_silhouettes,edge_silhouettes}.inl),
+// core/bounding_volumes.h and zombie's query adapters (include/zombie/utils/fcpw_scene_loader.h:292-652).
+//
+// Layout (all 16-byte records so that a node / primitive is fetched with vectorised loads and the
+// whole structure can be staged in shared memory when it is small):
+//   nodes  4 x float4 per node : (lo.xyz, nRefs) (hi.xyz, secondChildOffset) (coneAxis.xyz, halfAngle)
+//                                (refOffset, silOffset, nSilRefs, -)            [ints stored bit-cast]
+//   prims  2D 1 x float4 per segment (pa.xy, pb.xy); 3D 3 x float4 per triangle (pa, pb, pc)
+//   primN  1 x float4 per primitive: unit face normal, w = primitive index in the input mesh
+//   nrmV   pseudo-normals for signed distance: 2D 2 x float4 (vertex a, b); 3D 6 x float4
+//          (vertex a, b, c, edge 0, 1, 2)
+//   sils   silhouette references in node order: 2D 2 x float4 (p.xy, flags, id)(n0.xy, n1.xy);
+//          3D 4 x float4 (pa, flags)(pb, id)(n0, dihedral)(n1, -); flags bit0/bit1 = has face 0/1
+// Traversal order, tie-breaking and arithmetic association follow the reference so that the
+// deterministic mode returns the same primitive, point and distance.
+#pragma once
+#include "nmc_math.cuh"
+
+#if !defined(__CUDACC__)
+struct float4 { float x, y, z, w; };
+#endif
+
+namespace nmc {
+
+struct SceneView {
+	int dim, nNodes, nPrims, nSilRefs;
+	const float4* nodes;
+	const float4* prims;
+	const float4* primN;
+	const float4* nrmV;
+	const float4* sils;
+	float bboxLo[3], bboxHi[3];
+	const float* src; int n0, n1, n2;
+	float absorption; int watertight, doubleSided;
+};
+
+struct Box { V3 lo, hi; };
+struct Hit { float d; V3 p, n; float u, v; int ref; };
+
+#define NMC_STACK 64 // FCPW_SBVH_MAX_DEPTH (aggregates/sbvh.h:5)
+
+NMC_HD V3 xyz(const float4& q) { return mk(q.x, q.y, q.z); }
+
+// BoundingBox::computeSquaredDistance (bounding_volumes.h:62-67)
+NMC_HD void boxSqDist(V3 lo, V3 hi, V3 p, float& d2Min, float& d2Max) {
+	float ux = lo.x - p.x, vx = p.x - hi.x, uy = lo.y - p.y, vy = p.y - hi.y, uz = lo.z - p.z, vz = p.z - hi.z;
+	V3 a = mk(maxS(maxS(ux, vx), 0.0f), maxS(maxS(uy, vy), 0.0f), maxS(maxS(uz, vz), 0.0f));
+	V3 c = mk(minS(ux, vx), minS(uy, vy), minS(uz, vz));
+	d2Min = dot(a, a); d2Max = dot(c, c);
+}
+// BoundingBox::intersect(ray) (bounding_volumes.h:99-114)
+NMC_HD bool boxRay(V3 lo, V3 hi, V3 o, V3 invD, float rtMax, float& tMin, float& tMax) {
+	float t0 = (lo.x - o.x)*invD.x, t1 = (hi.x - o.x)*invD.x;
+	float nx = minS(t0, t1), fx = maxS(t0, t1);
+	t0 = (lo.y - o.y)*invD.y; t1 = (hi.y - o.y)*invD.y;
+	float ny = minS(t0, t1), fy = maxS(t0, t1);
+	t0 = (lo.z - o.z)*invD.z; t1 = (hi.z - o.z)*invD.z;
+	float nz = minS(t0, t1), fz = maxS(t0, t1);
+	float tNearMax = maxS(0.0f, maxS(nx, maxS(ny, nz)));
+	float tFarMin = minS(rtMax, minS(fx, minS(fy, fz)));
+	if (tNearMax > tFarMin) return false;
+	tMin = tNearMax; tMax = tFarMin;
+	return true;
+}
+NMC_HD bool inRange(float val, float low, float high) { return val >= low && val <= high; }
+// projectToPlane<3> + computeOrthonormalBasis (bounding_volumes.h:175-209)
+NMC_HD float projectToPlane(V3 n, V3 e) {
+	float sign = copysignf(1.0f, n.z);
+	const float a = -1.0f/(sign + n.z);
+	const float b = n.x*n.y*a;
+	V3 b1 = mk(fabsf(1.0f + sign*n.x*n.x*a), fabsf(sign*b), fabsf(-sign*n.x));
+	V3 b2 = mk(fabsf(b), fabsf(sign + n.y*n.y*a), fabsf(-n.y));
+	float r1 = dot(e, b1), r2 = dot(e, b2);
+	return sqrtf(r1*r1 + r2*r2);
+}
+// BoundingCone::overlap (bounding_volumes.h:225-271)
+template <class M>
+NMC_HD bool coneOverlap(V3 axis, float halfAngle, V3 o, V3 lo, V3 hi, float distToBox) {
+	if (halfAngle >= kPi2 || distToBox < kEps) return true;
+	V3 c = (lo + hi)*0.5f;
+	V3 vca = c - o;
+	float l = norm(vca);
+	vca = vca/l;
+	float dAxisAngle = M::acos_(maxS(-1.0f, minS(1.0f, dot(axis, vca))));
+	if (inRange((float)kPi2, dAxisAngle - halfAngle, dAxisAngle + halfAngle)) return true;
+	V3 e = hi - c;
+	float r2 = dot(e, e);
+	if (l*l > r2) {
+		float r = sqrtf(r2);
+		float vha = M::asin_(r/l);
+		float sum = halfAngle + vha;
+		return sum >= kPi2 ? true : inRange((float)kPi2, dAxisAngle - sum, dAxisAngle + sum);
+	}
+	float d = dot(e, mk(fabsf(vca.x), fabsf(vca.y), fabsf(vca.z)));
+	float s = l - d;
+	if (s <= 0.0f) return true;
+	d = projectToPlane(vca, e);
+	float vha = M::atan2_(d, s);
+	float sum = halfAngle + vha;
+	return sum >= kPi2 ? true : inRange((float)kPi2, dAxisAngle - sum, dAxisAngle + sum);
+}
+
+// findClosestPointLineSegment (line_segments.inl:184-209)
+NMC_HD float closestOnSegment(V3 pa, V3 pb, V3 x, V3& pt, float& t) {
+	V3 u = pb - pa, v = x - pa;
+	float c1 = dot(u, v);
+	if (c1 <= 0.0f) { pt = pa; t = 0.0f; return norm(x - pt); }
+	float c2 = dot(u, u);
+	if (c2 <= c1) { pt = pb; t = 1.0f; return norm(x - pt); }
+	t = c1/c2;
+	pt = pa + u*t;
+	return norm(x - pt);
+}
+// findClosestPointTriangle (triangles.inl:258-341)
+NMC_HD float closestOnTriangle(V3 pa, V3 pb, V3 pc, V3 x, V3& pt, float& t0, float& t1) {
+	V3 ab = pb - pa, ac = pc - pa, ax = x - pa;
+	float d1 = dot(ab, ax), d2 = dot(ac, ax);
+	if (d1 <= 0.0f && d2 <= 0.0f) { t0 = 1.0f; t1 = 0.0f; pt = pa; return norm(x - pt); }
+	V3 bx = x - pb;
+	float d3 = dot(ab, bx), d4 = dot(ac, bx);
+	if (d3 >= 0.0f && d4 <= d3) { t0 = 0.0f; t1 = 1.0f; pt = pb; return norm(x - pt); }
+	V3 cx = x - pc;
+	float d5 = dot(ab, cx), d6 = dot(ac, cx);
+	if (d6 >= 0.0f && d5 <= d6) { t0 = 0.0f; t1 = 0.0f; pt = pc; return norm(x - pt); }
+	float vc = d1*d4 - d3*d2;
+	if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+		float v = d1/(d1 - d3);
+		t0 = 1.0f - v; t1 = v; pt = pa + ab*v; return norm(x - pt);
+	}
+	float vb = d5*d2 - d1*d6;
+	if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+		float w = d2/(d2 - d6);
+		t0 = 1.0f - w; t1 = 0.0f; pt = pa + ac*w; return norm(x - pt);
+	}
+	float va = d3*d6 - d5*d4;
+	if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+		float w = (d4 - d3)/((d4 - d3) + (d5 - d6));
+		t0 = 0.0f; t1 = 1.0f - w; pt = pb + (pc - pb)*w; return norm(x - pt);
+	}
+	float denom = 1.0f/(va + vb + vc);
+	float v = vb*denom, w = vc*denom;
+	t0 = 1.0f - v - w; t1 = v;
+	pt = (pa + ab*v) + ac*w;
+	return norm(x - pt);
+}
+
+struct Trav { int node; float dist; };
+
+// closest point on the boundary mesh: Sbvh::findClosestPointFromNode (sbvh.inl:948-1074).
+// Returns false when nothing lies within sqrt(r2).  wantNormal: pseudo-normal as in
+// LineSegment/Triangle::normal(uv) with soup normals present (line_segments.inl:60-77, triangles.inl:62-90).
+template <int DIM>
+NMC_HD bool closestPoint(const SceneView& S, V3 x, float r2, bool wantNormal, Hit& out) {
+	if (S.nNodes == 0) return false;
+	Trav stack[NMC_STACK];
+	float b0, b1, b2, b3;
+	bool found = false;
+	{
+		float4 a = S.nodes[0], b = S.nodes[1];
+		boxSqDist(xyz(a), xyz(b), x, b0, b1);
+	}
+	if (!(b0 <= r2)) return false;
+	r2 = minS(r2, b1);
+	stack[0].node = 0; stack[0].dist = b0;
+	int sp = 0;
+	out.d = kMaxF; out.ref = -1; out.u = 0.0f; out.v = 0.0f;
+	while (sp >= 0) {
+		int ni = stack[sp].node; float cd = stack[sp].dist; sp--;
+		if (cd > r2) continue;
+		float4 na = S.nodes[4*ni], nb = S.nodes[4*ni + 1];
+		int nRefs = asInt(na.w);
+		if (nRefs > 0) {
+			int refOffset = asInt(S.nodes[4*ni + 3].x);
+			for (int p = 0; p < nRefs; p++) {
+				int ri = refOffset + p;
+				V3 pt; float u = 0.0f, v = 0.0f, d;
+				if (DIM == 2) {
+					float4 q = S.prims[ri];
+					d = closestOnSegment(mk(q.x, q.y, 0.0f), mk(q.z, q.w, 0.0f), x, pt, u); v = -1.0f;
+				} else {
+					d = closestOnTriangle(xyz(S.prims[3*ri]), xyz(S.prims[3*ri + 1]), xyz(S.prims[3*ri + 2]), x, pt, u, v);
+				}
+				if (d*d <= r2) {
+					found = true;
+					r2 = minS(r2, d*d);
+					out.d = d; out.p = pt; out.u = u; out.v = v; out.ref = ri;
+				}
+			}
+		} else {
+			int c0 = ni + 1, c1 = ni + asInt(nb.w);
+			boxSqDist(xyz(S.nodes[4*c0]), xyz(S.nodes[4*c0 + 1]), x, b0, b1); bool hit0 = b0 <= r2;
+			r2 = minS(r2, b1);
+			boxSqDist(xyz(S.nodes[4*c1]), xyz(S.nodes[4*c1 + 1]), x, b2, b3); bool hit1 = b2 <= r2;
+			r2 = minS(r2, b3);
+			if (hit0 && hit1) {
+				int closer = c0, other = c1;
+				if (b0 == 0.0f && b2 == 0.0f) {
+					if (b3 < b1) { closer = c1; other = c0; }
+				} else if (b2 < b0) {
+					float t = b0; b0 = b2; b2 = t;
+					closer = c1; other = c0;
+				}
+				sp++; stack[sp].node = other; stack[sp].dist = b2;
+				sp++; stack[sp].node = closer; stack[sp].dist = b0;
+			} else if (hit0) { sp++; stack[sp].node = c0; stack[sp].dist = b0; }
+			else if (hit1) { sp++; stack[sp].node = c1; stack[sp].dist = b2; }
+		}
+	}
+	if (found && wantNormal) {
+		int ri = out.ref;
+		if (DIM == 2) {
+			int vi = -1;
+			if (out.u <= kEps) vi = 0; else if (out.u >= 1.0f - kEps) vi = 1;
+			out.n = vi >= 0 ? xyz(S.nrmV[2*ri + vi]) : xyz(S.primN[ri]);
+		} else {
+			const float ome = 1.0f - kEps;
+			int vi = -1;
+			if (out.u >= ome && out.v <= kEps) vi = 0;
+			else if (out.u <= kEps && out.v >= ome) vi = 1;
+			else if (out.u <= kEps && out.v <= kEps) vi = 2;
+			int ei = -1;
+			if (vi == -1) {
+				if (out.u <= kEps) ei = 1;
+				else if (out.v <= kEps) ei = 2;
+				else if (out.u + out.v >= ome) ei = 0;
+			}
+			out.n = vi >= 0 ? xyz(S.nrmV[6*ri + vi]) : (ei >= 0 ? xyz(S.nrmV[6*ri + 3 + ei]) : xyz(S.primN[ri]));
+		}
+	}
+	return found;
+}
+
+// LineSegment::intersect(ray) (line_segments.inl:146-182) / Triangle::intersect(ray) (triangles.inl:219-256)
+template <int DIM>
+NMC_HD bool primRay(const SceneView& S, int ri, V3 o, V3 dir, float tMax, bool occl, Hit& h) {
+	if (DIM == 2) {
+		float4 q = S.prims[ri];
+		V3 pa = mk(q.x, q.y, 0.0f), pb = mk(q.z, q.w, 0.0f);
+		V3 u = pa - o, v = pb - pa;
+		float dv = dir.x*v.y - dir.y*v.x;
+		if (fabsf(dv) <= kEps) return false;
+		float ud = u.x*dir.y - u.y*dir.x;
+		float s = ud/dv;
+		if (s >= 0.0f && s <= 1.0f) {
+			float uv = u.x*v.y - u.y*v.x;
+			float t = uv/dv;
+			if (t >= 0.0f && t <= tMax) {
+				if (occl) return true;
+				h.d = t; h.p = pa + s*v; h.n = xyz(S.primN[ri]); h.u = s; h.v = -1.0f; h.ref = ri;
+				return true;
+			}
+		}
+		return false;
+	}
+	V3 pa = xyz(S.prims[3*ri]), pb = xyz(S.prims[3*ri + 1]), pc = xyz(S.prims[3*ri + 2]);
+	V3 v1 = pb - pa, v2 = pc - pa;
+	V3 p = cross(dir, v2);
+	float det = dot(v1, p);
+	if (fabsf(det) <= kEps) return false;
+	float invDet = 1.0f/det;
+	V3 s = o - pa;
+	float v = dot(s, p)*invDet;
+	if (v < 0 || v > 1) return false;
+	V3 q = cross(s, v1);
+	float w = dot(dir, q)*invDet;
+	if (w < 0 || v + w > 1) return false;
+	float t = dot(v2, q)*invDet;
+	if (t >= 0.0f && t <= tMax) {
+		if (occl) return true;
+		h.d = t; h.p = (pa + v1*v) + v2*w; h.n = xyz(S.primN[ri]); h.u = 1.0f - v - w; h.v = v; h.ref = ri;
+		return true;
+	}
+	return false;
+}
+// closest-hit / any-hit ray: Sbvh::intersectFromNode + processSubtreeForIntersection (sbvh.inl:538-683)
+template <int DIM>
+NMC_HD bool rayIntersect(const SceneView& S, V3 o, V3 dir, float tMax, bool occl, Hit& out) {
+	if (S.nNodes == 0) return false;
+	V3 invD = mk(1.0f/dir.x, 1.0f/dir.y, 1.0f/dir.z);
+	Trav stack[NMC_STACK];
+	float b0, b1, b2, b3;
+	int hits = 0;
+	if (!boxRay(xyz(S.nodes[0]), xyz(S.nodes[1]), o, invD, tMax, b0, b1)) return false;
+	stack[0].node = 0; stack[0].dist = b0;
+	int sp = 0;
+	while (sp >= 0) {
+		int ni = stack[sp].node; float cd = stack[sp].dist; sp--;
+		if (cd > tMax) continue;
+		float4 na = S.nodes[4*ni];
+		int nRefs = asInt(na.w);
+		if (nRefs > 0) {
+			int refOffset = asInt(S.nodes[4*ni + 3].x);
+			for (int p = 0; p < nRefs; p++) {
+				Hit h;
+				if (primRay<DIM>(S, refOffset + p, o, dir, tMax, occl, h)) {
+					if (occl) return true;
+					hits++;
+					tMax = minS(tMax, h.d);
+					out = h;
+				}
+			}
+		} else {
+			int c0 = ni + 1, c1 = ni + asInt(S.nodes[4*ni + 1].w);
+			bool hit0 = boxRay(xyz(S.nodes[4*c0]), xyz(S.nodes[4*c0 + 1]), o, invD, tMax, b0, b1);
+			bool hit1 = boxRay(xyz(S.nodes[4*c1]), xyz(S.nodes[4*c1 + 1]), o, invD, tMax, b2, b3);
+			if (hit0 && hit1) {
+				int closer = c0, other = c1;
+				if (b2 < b0) { float t = b0; b0 = b2; b2 = t; closer = c1; other = c0; }
+				sp++; stack[sp].node = other; stack[sp].dist = b2;
+				sp++; stack[sp].node = closer; stack[sp].dist = b0;
+			} else if (hit0) { sp++; stack[sp].node = c0; stack[sp].dist = b0; }
+			else if (hit1) { sp++; stack[sp].node = c1; stack[sp].dist = b2; }
+		}
+	}
+	return hits > 0;
+}
+
+// isSilhouetteVertex (vertex_silhouettes.inl:62-87) / isSilhouetteEdge (edge_silhouettes.inl:83-110)
+NMC_HD bool isSilhouette(float concavity, V3 n0, V3 n1, V3 viewDir, float d, bool flip, float precision) {
+	float sign = flip ? 1.0f : -1.0f;
+	if (d <= precision) return sign*concavity > precision;
+	V3 vu = viewDir/d;
+	float dot0 = dot(vu, n0), dot1 = dot(vu, n1);
+	if (fabsf(dot0) <= precision) return sign*dot1 > precision;
+	if (fabsf(dot1) <= precision) return sign*dot0 > precision;
+	return dot0*dot1 < 0.0f;
+}
+// closest silhouette point: Sbvh::findClosestSilhouettePointFromNode (sbvh.inl:1093-1255) with
+// SilhouetteVertex/Edge::findClosestSilhouettePoint (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143)
+template <int DIM, class M>
+NMC_HD bool closestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
+	if (S.nNodes == 0) return false;
+	if (sqMinR >= r2) return false;
+	Trav stack[NMC_STACK];
+	float b0, b1, tmp;
+	bool found = false; int lastId = -1;
+	boxSqDist(xyz(S.nodes[0]), xyz(S.nodes[1]), x, b0, tmp);
+	if (!(b0 <= r2)) return false;
+	stack[0].node = 0; stack[0].dist = b0;
+	int sp = 0;
+	while (sp >= 0) {
+		int ni = stack[sp].node; float cd = stack[sp].dist; sp--;
+		if (cd > r2) continue;
+		int nRefs = asInt(S.nodes[4*ni].w);
+		if (nRefs > 0) {
+			float4 nd = S.nodes[4*ni + 3];
+			int silOffset = asInt(nd.y), nSil = asInt(nd.z);
+			for (int p = 0; p < nSil; p++) {
+				int ri = silOffset + p;
+				V3 viewDir, n0, n1; float d, concavity; int flags, id;
+				if (DIM == 2) {
+					float4 s0 = S.sils[2*ri], s1 = S.sils[2*ri + 1];
+					flags = asInt(s0.z); id = asInt(s0.w);
+					if (id == lastId) continue;
+					if (sqMinR >= r2) continue;
+					viewDir = x - mk(s0.x, s0.y, 0.0f);
+					d = norm(viewDir);
+					n0 = mk(s1.x, s1.y, 0.0f); n1 = mk(s1.z, s1.w, 0.0f);
+					concavity = n0.x*n1.y - n1.x*n0.y;
+				} else {
+					float4 s0 = S.sils[4*ri], s1 = S.sils[4*ri + 1];
+					flags = asInt(s0.w); id = asInt(s1.w);
+					if (id == lastId) continue;
+					if (sqMinR >= r2) continue;
+					V3 pt; float t;
+					d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
+					viewDir = x - pt;
+					float4 s2 = S.sils[4*ri + 2];
+					n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.sils[4*ri + 3]);
+				}
+				if (d*d > r2) continue;
+				bool isSil = (flags & 3) != 3;
+				if (!isSil) isSil = isSilhouette(concavity, n0, n1, viewDir, d, flip, precision);
+				if (isSil && d*d <= r2) {
+					found = true;
+					r2 = minS(r2, d*d);
+					dOut = d; lastId = id;
+					if (sqMinR >= r2) break;
+				}
+			}
+		} else {
+			int c0 = ni + 1, c1 = ni + asInt(S.nodes[4*ni + 1].w);
+			bool hit0 = false, hit1 = false;
+			float4 k0 = S.nodes[4*c0 + 2];
+			if (k0.w >= 0.0f) {
+				V3 lo = xyz(S.nodes[4*c0]), hi = xyz(S.nodes[4*c0 + 1]);
+				boxSqDist(lo, hi, x, b0, tmp);
+				hit0 = b0 <= r2 && coneOverlap<M>(xyz(k0), k0.w, x, lo, hi, b0);
+			}
+			float4 k1 = S.nodes[4*c1 + 2];
+			if (k1.w >= 0.0f) {
+				V3 lo = xyz(S.nodes[4*c1]), hi = xyz(S.nodes[4*c1 + 1]);
+				boxSqDist(lo, hi, x, b1, tmp);
+				hit1 = b1 <= r2 && coneOverlap<M>(xyz(k1), k1.w, x, lo, hi, b1);
+			}
+			if (hit0 && hit1) {
+				int closer = c0, other = c1;
+				if (b1 < b0) { float t = b0; b0 = b1; b1 = t; closer = c1; other = c0; }
+				sp++; stack[sp].node = other; stack[sp].dist = b1;
+				sp++; stack[sp].node = closer; stack[sp].dist = b0;
+			} else if (hit0) { sp++; stack[sp].node = c0; stack[sp].dist = b0; }
+			else if (hit1) { sp++; stack[sp].node = c1; stack[sp].dist = b1; }
+		}
+	}
+	return found;
+}
+
+// ---- zombie's query adapters (fcpw_scene_loader.h:292-652) --------------------------------------
+// computeDistToDirichlet with no Dirichlet geometry: sqrt(d2Max) to the scene box (:299-315)
+template <int DIM>
+NMC_HD float distDirichlet(const SceneView& S, V3 x) {
+	float cx = minS(S.bboxLo[0] - x.x, x.x - S.bboxHi[0]);
+	float cy = minS(S.bboxLo[1] - x.y, x.y - S.bboxHi[1]);
+	if (DIM == 2) return sqrtf(cx*cx + cy*cy);
+	float cz = minS(S.bboxLo[2] - x.z, x.z - S.bboxHi[2]);
+	return sqrtf(cx*cx + (cy*cy + cz*cz));
+}
+// computeDistToNeumann (:316-330) + Interaction::signedDistance (core/interaction.h:32-34)
+template <int DIM>
+NMC_HD float distNeumann(const SceneView& S, V3 x, bool sgn) {
+	if (S.nPrims == 0) return kMaxF;
+	Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
+	closestPoint<DIM>(S, x, kMaxF, sgn, h);
+	if (!sgn) return h.d;
+	return (dot(x - h.p, h.n) > 0.0f ? 1.0f : -1.0f)*h.d;
+}
+template <int DIM>
+NMC_HD bool insideDomain(const SceneView& S, V3 x) { // :642-648
+	if (!S.watertight) return true;
+	float d1 = distDirichlet<DIM>(S, x);
+	float d2 = distNeumann<DIM>(S, x, true);
+	return fabsf(d1) < fabsf(d2) ? d1 < 0.0f : d2 < 0.0f;
+}
+template <int DIM>
+NMC_HD bool outsideBox(const SceneView& S, V3 x) { // :649-651
+	bool in = x.x >= S.bboxLo[0] && x.x <= S.bboxHi[0] && x.y >= S.bboxLo[1] && x.y <= S.bboxHi[1];
+	if (DIM == 3) in = in && x.z >= S.bboxLo[2] && x.z <= S.bboxHi[2];
+	return !in;
+}
+// offsetPointAlongDirection (:252-290): integer-ULP ray-origin offset
+NMC_HD float offsetComp(float p, float n) {
+	const float origin = 1.0f/32.0f, floatScale = 1.0f/65536.0f, intScale = 256.0f;
+	int nOff = (int)(n*intScale);
+	float pOff = asFloat(asInt(p) + (p < 0 ? -nOff : nOff));
+	return fabsf(p) < origin ? p + floatScale*n : pOff;
+}
+template <int DIM>
+NMC_HD V3 offsetPoint(V3 p, V3 n) {
+	return mk(offsetComp(p.x, n.x), offsetComp(p.y, n.y), DIM == 3 ? offsetComp(p.z, n.z) : 0.0f);
+}
+template <int DIM, class M>
+NMC_HD float starRadius(const SceneView& S, V3 x, float minR, float maxR, float prec, bool flipOrient) { // :621-641
+	if (minR > maxR) return maxR;
+	if (S.nPrims > 0) {
+		bool flip = !flipOrient; // FCPW's convention needs flipped normals (:629)
+		float r2 = maxR < kMaxF ? maxR*maxR : kMaxF;
+		float d;
+		if (closestSilhouette<DIM, M>(S, x, r2, flip, minR*minR, prec, d)) return maxS(d, minR);
+	}
+	return maxS(maxR, minR);
+}
+template <int DIM>
+NMC_HD bool intersectNeumann(const SceneView& S, V3 org, V3 nrm, V3 dir, float tMax, bool onB, Hit& h) { // :458-484
+	if (S.nPrims == 0) return false;
+	V3 o = onB ? offsetPoint<DIM>(org, neg(nrm)) : org;
+	if (DIM == 2) { o.z = 0.0f; dir.z = 0.0f; }
+	return rayIntersect<DIM>(S, o, dir, tMax, false, h);
+}
+// pde.source: nearest-texel lookup (demo/scene.h:194-198 + image.h:70-75; zombie3d scene_3d.h:120-126)
+template <int DIM>
+NMC_HD float sourceAt(const SceneView& S, V3 x) {
+	float ux = (x.x - S.bboxLo[0])/(S.bboxHi[0] - S.bboxLo[0]);
+	float uy = (x.y - S.bboxLo[1])/(S.bboxHi[1] - S.bboxLo[1]);
+	if (DIM == 2) {
+		int h = S.n0, w = S.n1;
+		int i = (int)(uy*h); i = i < 0 ? 0 : (i > h - 1 ? h - 1 : i);
+		int j = (int)(ux*w); j = j < 0 ? 0 : (j > w - 1 ? w - 1 : j);
+		return S.src[(size_t)i*w + j];
+	}
+	float uz = (x.z - S.bboxLo[2])/(S.bboxHi[2] - S.bboxLo[2]);
+	int i = (int)(ux*S.n0); i = i < 0 ? 0 : (i > S.n0 - 1 ? S.n0 - 1 : i);
+	int j = (int)(uy*S.n1); j = j < 0 ? 0 : (j > S.n1 - 1 ? S.n1 - 1 : j);
+	int k = (int)(uz*S.n2); k = k < 0 ? 0 : (k > S.n2 - 1 ? S.n2 - 1 : k);
+	return S.src[((size_t)i*S.n1 + j)*S.n2 + k];
+}
+
+} // namespace nmc

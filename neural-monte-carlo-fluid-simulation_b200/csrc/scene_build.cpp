@@ -1,0 +1,360 @@
+// csrc/scene_build.cpp -- builds the flattened BVH + normal-cone hierarchy ("SNCH") that the walk
+// kernels traverse.
+//
+// The tree TOPOLOGY and the silhouette bookkeeping deliberately follow FCPW's scalar builder,
+// because closest-point / ray / silhouette results depend on traversal order whenever two
+// candidates tie, and the deterministic mode must return what the reference returns:
+//   object-split build, 8 centroid buckets, OverlapSurfaceArea cost, leaf size 4
+//     (deps/fcpw/include/fcpw/aggregates/sbvh.inl:4-234, fcpw.inl:523-573 without FCPW_USE_ENOKI)
+//   vertex / edge pseudo-normals (fcpw.inl:300-354), silhouette vertices / edges (fcpw.inl:224-291),
+//   per-leaf silhouette references filtered by ignoreCandidateSilhouette (sbvh.inl:314-443,
+//   demo/scene.h:84-90), bounding cones (sbvh.inl:236-301),
+//   2D vertex renumbering and its double wiring of silhouette vertices (fcpw.inl:374-410, 469-490).
+// The MEMORY LAYOUT is ours: fixed 16-byte records with pre-gathered vertex data, pre-normalised
+// face normals and pre-evaluated dihedral angles, so the device never chases an index.
+#include "scene_build.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+#include <map>
+#include <array>
+
+namespace nmc {
+namespace {
+
+struct P3 { float x, y, z; };
+inline P3 operator+(P3 a, P3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline P3 operator-(P3 a, P3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline P3 operator*(P3 a, float s) { return {a.x*s, a.y*s, a.z*s}; }
+inline float dot(P3 a, P3 b) { return a.x*b.x + (a.y*b.y + a.z*b.z); } // Eigen redux order
+inline P3 cross(P3 a, P3 b) { return {a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x}; }
+inline P3 unit(P3 a) { float z = dot(a, a); if (z > 0.0f) { float s = std::sqrt(z); return {a.x/s, a.y/s, a.z/s}; } return a; }
+inline float at(const P3& a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+inline float mn(float a, float b) { return (b < a) ? b : a; }
+inline float mx(float a, float b) { return (a < b) ? b : a; }
+inline float bits(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+struct Aabb {
+	P3 lo{FLT_MAX, FLT_MAX, FLT_MAX}, hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	void grow(P3 p) { // BoundingBox::expandToInclude(point), bounding_volumes.h:45-49
+		const float e = FLT_EPSILON;
+		lo = {mn(lo.x, p.x - e), mn(lo.y, p.y - e), mn(lo.z, p.z - e)};
+		hi = {mx(hi.x, p.x + e), mx(hi.y, p.y + e), mx(hi.z, p.z + e)};
+	}
+	void grow(const Aabb& b) {
+		lo = {mn(lo.x, b.lo.x), mn(lo.y, b.lo.y), mn(lo.z, b.lo.z)};
+		hi = {mx(hi.x, b.hi.x), mx(hi.y, b.hi.y), mx(hi.z, b.hi.z)};
+	}
+	float area() const { // surfaceArea(), bounding_volumes.h:139-142
+		float e0 = mx(hi.x - lo.x, 1e-5f), e1 = mx(hi.y - lo.y, 1e-5f), e2 = mx(hi.z - lo.z, 1e-5f);
+		float P = e0*(e1*e2);
+		return 2.0f*(P/e0 + (P/e1 + P/e2));
+	}
+};
+
+struct BuildNode {
+	Aabb box;
+	P3 axis{0, 0, 0}; float halfAngle = (float)M_PI;
+	int refOffset = 0, nRefs = 0, second = 0, silOffset = 0, nSil = 0;
+};
+struct Sil { int v[4] = {-1, -1, -1, -1}; int id = -1; };
+
+struct Builder {
+	int dim, nV, nP;
+	std::vector<P3> pos, vnrm, enrm;
+	std::vector<int> prim;      // nP x dim, permuted by the build
+	std::vector<int> primId;    // original primitive index of each slot
+	std::vector<int> eIdx;      // 3D: 3 edge ids per ORIGINAL primitive
+	std::vector<Sil> sil;
+	std::vector<BuildNode> nodes;
+	std::vector<Aabb> rbox; std::vector<P3> rcen;
+	int maxDepth = 0;
+
+	const int* pv(int slot) const { return &prim[(size_t)slot*dim]; }
+	P3 faceNormal(const int* v, bool normalize) const {
+		P3 n;
+		if (dim == 2) { P3 d = pos[v[1]] - pos[v[0]]; n = {d.y, -d.x, 0.0f}; }
+		else n = cross(pos[v[1]] - pos[v[0]], pos[v[2]] - pos[v[0]]);
+		return normalize ? unit(n) : n;
+	}
+	bool silHasFace(const Sil& s, int f) const { return f == 0 ? s.v[dim == 2 ? 2 : 3] != -1 : s.v[0] != -1; }
+	P3 silFaceNormal(const Sil& s, int f) const { // vertex_silhouettes.inl:36-46, edge_silhouettes.inl:45-68
+		if (dim == 2) { int i = f == 0 ? 1 : 0; P3 d = pos[s.v[i + 1]] - pos[s.v[i]]; return unit({d.y, -d.x, 0.0f}); }
+		int i = f == 0 ? 3 : 0, j = f == 0 ? 1 : 2, k = f == 0 ? 2 : 1;
+		return unit(cross(pos[s.v[k]] - pos[s.v[j]], pos[s.v[i]] - pos[s.v[j]]));
+	}
+
+	static float splitCost(const Aabb& L, const Aabb& R, int nL, int nR) { // sbvh.inl:18-23
+		Aabb I;
+		I.lo = {mx(L.lo.x, R.lo.x), mx(L.lo.y, R.lo.y), mx(L.lo.z, R.lo.z)};
+		I.hi = {mn(L.hi.x, R.hi.x), mn(L.hi.y, R.hi.y), mn(L.hi.z, R.hi.z)};
+		float cost = (nL/R.area() + nR/L.area())*std::fabs(I.area());
+		bool valid = I.hi.x >= I.lo.x && I.hi.y >= I.lo.y && I.hi.z >= I.lo.z;
+		return valid ? cost : cost*-1;
+	}
+	void swapSlots(int i, int j) {
+		for (int k = 0; k < dim; k++) std::swap(prim[(size_t)i*dim + k], prim[(size_t)j*dim + k]);
+		std::swap(primId[i], primId[j]); std::swap(rbox[i], rbox[j]); std::swap(rcen[i], rcen[j]);
+	}
+	void split(int parent, int start, int end, int depth) { // buildRecursive, sbvh.inl:141-207
+		const int kLeaf = 4, kBuckets = 8, kMaxDepth = 64;
+		maxDepth = std::max(maxDepth, depth);
+		int cur = (int)nodes.size();
+		nodes.emplace_back();
+		Aabb bb, bc;
+		for (int p = start; p < end; p++) { bb.grow(rbox[p]); bc.grow(rcen[p]); }
+		nodes[cur].box = bb;
+		bool leaf = end - start <= kLeaf || depth == kMaxDepth - 2;
+		if (leaf) { nodes[cur].refOffset = start; nodes[cur].nRefs = end - start; }
+		if (parent >= 0 && cur != parent + 1) nodes[parent].second = cur - parent;
+		if (leaf) return;
+
+		float best = FLT_MAX; int bestDim = -1; float bestCoord = 0.0f;
+		P3 ext = bb.hi - bb.lo;
+		for (int d = 0; d < 3; d++) { // computeObjectSplit, sbvh.inl:41-112
+			if (at(ext, d) < 1e-6f) continue;
+			float width = at(ext, d)/kBuckets;
+			Aabb bk[kBuckets], right[kBuckets]; int cnt[kBuckets] = {0}, rcnt[kBuckets] = {0};
+			for (int p = start; p < end; p++) {
+				int b = (int)((at(rcen[p], d) - at(bb.lo, d))/width);
+				b = b < 0 ? 0 : (b > kBuckets - 1 ? kBuckets - 1 : b);
+				bk[b].grow(rbox[p]); cnt[b]++;
+			}
+			Aabb acc;
+			for (int b = kBuckets - 1; b > 0; b--) {
+				acc.grow(bk[b]); right[b] = acc;
+				rcnt[b] = cnt[b] + (b != kBuckets - 1 ? rcnt[b + 1] : 0);
+			}
+			Aabb left; int nL = 0;
+			for (int b = 1; b < kBuckets; b++) {
+				left.grow(bk[b - 1]); nL += cnt[b - 1];
+				if (nL > 0 && rcnt[b] > 0) {
+					float c = splitCost(left, right[b], nL, rcnt[b]);
+					if (c < best) { best = c; bestDim = d; bestCoord = at(bb.lo, d) + b*width; }
+				}
+			}
+		}
+		if (bestDim == -1) { // centroid-box longest axis, sbvh.inl:105-109
+			P3 e = bc.hi - bc.lo;
+			bestDim = 0; if (e.y > at(e, bestDim)) bestDim = 1; if (e.z > at(e, bestDim)) bestDim = 2;
+			bestCoord = (at(bc.lo, bestDim) + at(bc.hi, bestDim))*0.5f;
+		}
+		int mid = start; // performObjectSplit, sbvh.inl:114-139
+		for (int i = start; i < end; i++) if (at(rcen[i], bestDim) < bestCoord) { swapSlots(i, mid); mid++; }
+		if (mid == start || mid == end) mid = start + (end - start)/2;
+		split(cur, start, mid, depth + 1);
+		split(cur, mid, end, depth + 1);
+	}
+
+	void cones(const std::vector<int>& refs, const std::vector<P3>& refN, const std::vector<std::array<P3, 2>>& refFN,
+			   int start, int end) { // computeBoundingConesRecursive, sbvh.inl:236-301
+		BuildNode& node = nodes[start];
+		P3 axis{0, 0, 0}; bool any = false, two = true;
+		for (int i = start; i < end; i++) for (int j = 0; j < nodes[i].nSil; j++) {
+			int r = nodes[i].silOffset + j;
+			axis = axis + refN[r];
+			two = two && silHasFace(sil[refs[r]], 0) && silHasFace(sil[refs[r]], 1);
+			any = true;
+		}
+		if (!any) node.halfAngle = (float)-M_PI;
+		else if (!two) node.halfAngle = (float)M_PI;
+		else {
+			float an = std::sqrt(dot(axis, axis));
+			if (an > FLT_EPSILON) {
+				axis = {axis.x/an, axis.y/an, axis.z/an};
+				float ha = 0.0f;
+				for (int i = start; i < end; i++) for (int j = 0; j < nodes[i].nSil; j++) {
+					int r = nodes[i].silOffset + j;
+					for (int k = 0; k < 2; k++) ha = mx(ha, std::acos(mx(-1.0f, mn(1.0f, dot(axis, refFN[r][k])))));
+				}
+				node.axis = axis; node.halfAngle = ha;
+			}
+		}
+		if (node.nRefs == 0) {
+			cones(refs, refN, refFN, start + 1, start + node.second);
+			cones(refs, refN, refFN, start + node.second, end);
+		}
+	}
+};
+
+} // namespace
+
+void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int nP, bool doubleSided, FlatScene& out) {
+	out = FlatScene();
+	out.dim = dim;
+	// zombie::computeBoundingBox over DIM components (fcpw_scene_loader.h:75-93)
+	for (int k = 0; k < 3; k++) { out.bboxLo[k] = FLT_MAX; out.bboxHi[k] = -FLT_MAX; }
+	for (int i = 0; i < nV; i++) for (int k = 0; k < dim; k++) {
+		float p = verts[(size_t)i*dim + k]*1.0f;
+		out.bboxLo[k] = mn(out.bboxLo[k], p - FLT_EPSILON); out.bboxHi[k] = mx(out.bboxHi[k], p + FLT_EPSILON);
+	}
+	if (nP <= 0) return;
+
+	Builder B; B.dim = dim; B.nV = nV; B.nP = nP;
+	B.pos.resize(nV);
+	for (int i = 0; i < nV; i++) B.pos[i] = {verts[(size_t)i*dim], verts[(size_t)i*dim + 1], dim == 3 ? verts[(size_t)i*dim + 2] : 0.0f};
+	B.prim.assign(prims, prims + (size_t)nP*dim);
+	B.primId.resize(nP);
+	for (int i = 0; i < nP; i++) B.primId[i] = i;
+
+	// pseudo-normals, unweighted at vertices, area-weighted at edges (fcpw.inl:300-354)
+	B.vnrm.assign(nV, P3{0, 0, 0});
+	if (dim == 3) { // assignEdgeIndices, fcpw.inl:200-221
+		std::map<std::pair<int, int>, int> ids;
+		B.eIdx.resize((size_t)3*nP);
+		for (int i = 0; i < nP; i++) for (int j = 0; j < 3; j++) {
+			int I = prims[3*i + j], J = prims[3*i + (j + 1)%3];
+			if (I > J) std::swap(I, J);
+			auto it = ids.find({I, J});
+			if (it == ids.end()) it = ids.emplace(std::make_pair(I, J), (int)ids.size()).first;
+			B.eIdx[3*i + j] = it->second;
+		}
+		B.enrm.assign(ids.size(), P3{0, 0, 0});
+	}
+	for (int i = 0; i < nP; i++) {
+		P3 n = B.faceNormal(B.pv(i), true);
+		if (dim == 2) { for (int j = 0; j < 2; j++) B.vnrm[B.pv(i)[j]] = B.vnrm[B.pv(i)[j]] + n*1.0f; }
+		else {
+			P3 un = B.faceNormal(B.pv(i), false);
+			float area = 0.5f*std::sqrt(dot(un, un));
+			for (int j = 0; j < 3; j++) {
+				B.vnrm[B.pv(i)[j]] = B.vnrm[B.pv(i)[j]] + n*1.0f;
+				B.enrm[B.eIdx[3*i + j]] = B.enrm[B.eIdx[3*i + j]] + n*area;
+			}
+		}
+	}
+	for (auto& n : B.vnrm) n = unit(n);
+	for (auto& n : B.enrm) n = unit(n);
+
+	// silhouettes wired in input order (computeSilhouettes, fcpw.inl:224-291)
+	if (dim == 2) {
+		B.sil.assign(nV, Sil());
+		for (int i = 0; i < nP; i++) {
+			int a = prims[2*i], b = prims[2*i + 1];
+			B.sil[a].v[1] = a; B.sil[a].v[2] = b; B.sil[a].id = a;
+			B.sil[b].v[0] = a; B.sil[b].v[1] = b; B.sil[b].id = b;
+		}
+	} else {
+		B.sil.assign(B.enrm.size(), Sil());
+		for (int i = 0; i < nP; i++) for (int j = 0; j < 3; j++) {
+			int I = j - 1 < 0 ? 2 : j - 1, J = j, K = j + 1 > 2 ? 0 : j + 1;
+			bool fwd = true;
+			if (prims[3*i + J] > prims[3*i + K]) { std::swap(J, K); fwd = false; }
+			Sil& s = B.sil[B.eIdx[3*i + j]];
+			s.v[fwd ? 0 : 3] = prims[3*i + I]; s.v[1] = prims[3*i + J]; s.v[2] = prims[3*i + K];
+			s.id = B.eIdx[3*i + j];
+		}
+	}
+
+	// tree
+	B.rbox.resize(nP); B.rcen.resize(nP);
+	for (int i = 0; i < nP; i++) {
+		const int* v = B.pv(i);
+		Aabb b; for (int k = 0; k < dim; k++) b.grow(B.pos[v[k]]);
+		B.rbox[i] = b;
+		B.rcen[i] = dim == 2 ? (B.pos[v[0]] + B.pos[v[1]])*0.5f
+							 : P3{((B.pos[v[0]].x + B.pos[v[1]].x) + B.pos[v[2]].x)/3.0f,
+								  ((B.pos[v[0]].y + B.pos[v[1]].y) + B.pos[v[2]].y)/3.0f,
+								  ((B.pos[v[0]].z + B.pos[v[1]].z) + B.pos[v[2]].z)/3.0f};
+	}
+	B.nodes.reserve((size_t)2*nP);
+	B.split(-1, 0, nP, 0);
+
+	// 2D: renumber vertices in leaf order and wire the silhouette vertices a second time on top of the
+	// first wiring (fcpw.inl:374-410, 469-490) -- stale neighbours at open polyline ends are reference behaviour
+	if (dim == 2) {
+		std::vector<int> remap(nV, -1);
+		std::vector<P3> npos(nV, P3{0, 0, 0}), nnrm(nV, P3{0, 0, 0});
+		int next = 0;
+		for (const BuildNode& n : B.nodes) for (int j = 0; j < n.nRefs; j++) for (int k = 0; k < 2; k++) {
+			int v = B.prim[(size_t)(n.refOffset + j)*2 + k];
+			if (remap[v] == -1) { npos[next] = B.pos[v]; nnrm[next] = B.vnrm[v]; remap[v] = next++; }
+		}
+		for (int& v : B.prim) v = remap[v];
+		B.pos.swap(npos); B.vnrm.swap(nnrm);
+		for (int i = 0; i < nP; i++) {
+			int a = B.prim[2*i], b = B.prim[2*i + 1];
+			B.sil[a].v[1] = a; B.sil[a].v[2] = b; B.sil[a].id = a;
+			B.sil[b].v[0] = a; B.sil[b].v[1] = b; B.sil[b].id = b;
+		}
+	}
+
+	// silhouette references per leaf (assignSilhouettesToNodes, sbvh.inl:314-443)
+	std::vector<int> refs; std::vector<P3> refN; std::vector<std::array<P3, 2>> refFN; std::vector<float> refAngle;
+	std::vector<int> stamp(B.sil.size(), -1);
+	for (int ni = 0; ni < (int)B.nodes.size(); ni++) {
+		BuildNode& node = B.nodes[ni];
+		node.silOffset = (int)refs.size();
+		for (int j = 0; j < node.nRefs; j++) {
+			int slot = node.refOffset + j;
+			for (int k = 0; k < dim; k++) {
+				int si = dim == 2 ? B.prim[(size_t)slot*2 + k] : B.eIdx[(size_t)3*B.primId[slot] + k];
+				if (stamp[si] == ni) continue;
+				stamp[si] = ni;
+				const Sil& s = B.sil[si];
+				P3 n{0, 0, 0}, n0{0, 0, 0}, n1{0, 0, 0}; float angle = 0.0f; bool ignore = false;
+				if (B.silHasFace(s, 0) && B.silHasFace(s, 1)) {
+					n = dim == 2 ? B.vnrm[s.v[1]] : B.enrm[s.id];
+					n0 = B.silFaceNormal(s, 0); n1 = B.silFaceNormal(s, 1);
+					if (dim == 2) angle = n0.x*n1.y - n1.x*n0.y;
+					else angle = std::atan2(dot(unit(B.pos[s.v[2]] - B.pos[s.v[1]]), cross(n0, n1)), dot(n0, n1));
+					ignore = doubleSided ? false : angle < 1e-3f; // demo/scene.h:84-90
+				}
+				if (!ignore) { refs.push_back(si); refN.push_back(n); refFN.push_back({n0, n1}); refAngle.push_back(angle); }
+			}
+		}
+		node.nSil = (int)refs.size() - node.silOffset;
+	}
+	B.cones(refs, refN, refFN, 0, (int)B.nodes.size());
+
+	// flatten
+	out.nNodes = (int)B.nodes.size(); out.nPrims = nP; out.nSilRefs = (int)refs.size(); out.maxDepth = B.maxDepth;
+	out.nodes.resize((size_t)4*out.nNodes);
+	for (int i = 0; i < out.nNodes; i++) {
+		const BuildNode& n = B.nodes[i];
+		out.nodes[4*i + 0] = {n.box.lo.x, n.box.lo.y, n.box.lo.z, bits(n.nRefs)};
+		out.nodes[4*i + 1] = {n.box.hi.x, n.box.hi.y, n.box.hi.z, bits(n.second)};
+		out.nodes[4*i + 2] = {n.axis.x, n.axis.y, n.axis.z, n.halfAngle};
+		out.nodes[4*i + 3] = {bits(n.refOffset), bits(n.silOffset), bits(n.nSil), 0.0f};
+	}
+	out.prims.resize((size_t)(dim == 2 ? 1 : 3)*nP); out.primN.resize(nP); out.nrmV.resize((size_t)(dim == 2 ? 2 : 6)*nP);
+	for (int i = 0; i < nP; i++) {
+		const int* v = B.pv(i);
+		P3 fn = B.faceNormal(v, true);
+		out.primN[i] = {fn.x, fn.y, fn.z, bits(B.primId[i])};
+		if (dim == 2) {
+			out.prims[i] = {B.pos[v[0]].x, B.pos[v[0]].y, B.pos[v[1]].x, B.pos[v[1]].y};
+			for (int k = 0; k < 2; k++) out.nrmV[2*i + k] = {B.vnrm[v[k]].x, B.vnrm[v[k]].y, B.vnrm[v[k]].z, 0.0f};
+		} else {
+			for (int k = 0; k < 3; k++) {
+				out.prims[3*i + k] = {B.pos[v[k]].x, B.pos[v[k]].y, B.pos[v[k]].z, 0.0f};
+				out.nrmV[6*i + k] = {B.vnrm[v[k]].x, B.vnrm[v[k]].y, B.vnrm[v[k]].z, 0.0f};
+				const P3& en = B.enrm[B.eIdx[(size_t)3*B.primId[i] + k]];
+				out.nrmV[6*i + 3 + k] = {en.x, en.y, en.z, 0.0f};
+			}
+		}
+	}
+	out.sils.resize((size_t)(dim == 2 ? 2 : 4)*refs.size());
+	for (size_t r = 0; r < refs.size(); r++) {
+		const Sil& s = B.sil[refs[r]];
+		int flags = (B.silHasFace(s, 0) ? 1 : 0) | (B.silHasFace(s, 1) ? 2 : 0);
+		// query-time face normals (SilhouetteVertex/Edge::normal(fIndex), normalised) -- only defined with two faces
+		P3 n0{0, 0, 0}, n1{0, 0, 0};
+		if (flags == 3) { n0 = refFN[r][0]; n1 = refFN[r][1]; }
+		if (dim == 2) {
+			const P3& p = B.pos[s.v[1]];
+			out.sils[2*r + 0] = {p.x, p.y, bits(flags), bits(s.id)};
+			out.sils[2*r + 1] = {n0.x, n0.y, n1.x, n1.y};
+		} else {
+			const P3 &pa = B.pos[s.v[1]], &pb = B.pos[s.v[2]];
+			out.sils[4*r + 0] = {pa.x, pa.y, pa.z, bits(flags)};
+			out.sils[4*r + 1] = {pb.x, pb.y, pb.z, bits(s.id)};
+			out.sils[4*r + 2] = {n0.x, n0.y, n0.z, refAngle[r]};
+			out.sils[4*r + 3] = {n1.x, n1.y, n1.z, 0.0f};
+		}
+	}
+}
+
+} // namespace nmc

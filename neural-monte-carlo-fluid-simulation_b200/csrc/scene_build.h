@@ -1,0 +1,26 @@
+// csrc/scene_build.h -- host-side construction of the flattened boundary structure (see nmc_geom.cuh
+// for the record layout).  Pure C++, no CUDA.
+#pragma once
+#include <vector>
+#include <cstdint>
+
+namespace nmc {
+
+struct Q4 { float x, y, z, w; };
+
+struct FlatScene {
+	int dim = 0;
+	int nNodes = 0, nPrims = 0, nSilRefs = 0, maxDepth = 0;
+	std::vector<Q4> nodes;  // 4 per node
+	std::vector<Q4> prims;  // 1 (2D) / 3 (3D) per primitive
+	std::vector<Q4> primN;  // 1 per primitive
+	std::vector<Q4> nrmV;   // 2 (2D) / 6 (3D) per primitive
+	std::vector<Q4> sils;   // 2 (2D) / 4 (3D) per silhouette reference
+	float bboxLo[3] = {0, 0, 0}, bboxHi[3] = {0, 0, 0};
+};
+
+// verts nV x dim, prims nP x dim. ignoreConvex: the bindings' ignoreCandidateSilhouette
+// (demo/scene.h:84-90) = !isDoubleSided.
+void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int nP, bool doubleSided, FlatScene& out);
+
+} // namespace nmc

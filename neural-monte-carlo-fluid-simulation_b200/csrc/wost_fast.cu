@@ -1,0 +1,373 @@
+// csrc/wost_fast.cu -- default-mode estimator: persistent walk kernel for sm_100a.
+//
+// Work decomposition (replaces tbb::parallel_for over points, walk_on_stars.h:91-103, and the
+// sequential per-point loop of estimateSolutionAndGradient, :466-617):
+//   * the grid is persistent: smCount x (resident CTAs per SM) CTAs, every WARP pulls sample points
+//     from a global atomic queue, so long and short points balance across the 148 SMs;
+//   * inside a warp one LANE runs one walk at a time.  A point's antithetic pairs are handed out to
+//     lanes through a ballot/popc compaction: every loop trip, lanes whose pair has finished are
+//     ranked with __ballot_sync/__popc and take the next pair indices, so lanes whose walks have
+//     terminated are refilled immediately instead of idling until the longest walk ends;
+//   * every loop trip each busy lane executes exactly one "slice": either the first-ball source sample
+//     of a new pair or one walk-on-stars step.  Both slice kinds share the expensive part (radial
+//     inverse-CDF sample of the ball Green's function + source-grid gather), so the warp stays
+//     converged there and only diverges in the geometric queries;
+//   * the boundary structure (nodes, primitives, face normals, silhouettes; 16-byte records) is staged
+//     in shared memory once per CTA when it fits, and read with vectorised loads;
+//   * per-point estimates are reduced in registers/shared memory: control variates come from per-warp
+//     shared-memory running sums, the final means from a shuffle tree; one lane writes p and grad p.
+//   * RNG is counter-based: every (seed, global point index, pair, stream) tuple hashes to its own
+//     pcg32 state, so results do not depend on which warp/GPU processes a point.
+// Statistical (not bitwise) equivalence to the reference: same estimator, same stratification of the
+// first-ball directions (Latin hypercube via a keyed permutation instead of a stored shuffle), same
+// antithetic pairing and control variates; the radial sample is drawn by inverting the CDF that the
+// reference's rejection sampler targets.
+#include "nmc_device.h"
+#include "../../include/nmcfs.h"
+
+namespace nmc {
+
+static constexpr int kBlock = 128;
+static constexpr int kWarps = kBlock/32;
+static constexpr unsigned kFull = 0xffffffffu;
+
+// Keyed bijection on [0, n): multiply/xorshift rounds on the enclosing power of two with cycle walking.
+__device__ __forceinline__ unsigned permute(unsigned i, unsigned n, unsigned key) {
+	unsigned w = n - 1;
+	w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+	do {
+		i ^= key; i *= 0xe170893du;
+		i ^= key >> 16;
+		i ^= (i & w) >> 4;
+		i ^= key >> 8; i *= 0x0929eb3fu;
+		i ^= key >> 23;
+		i ^= (i & w) >> 1; i *= 1u | key >> 27;
+		i *= 0x6935fa69u;
+		i ^= (i & w) >> 11; i *= 0x74dcb303u;
+		i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+		i ^= (i & w) >> 2; i *= 0xc860a3dfu;
+		i &= w;
+		i ^= i >> 5;
+	} while (i >= n);
+	return i;
+}
+
+__device__ __forceinline__ float warpSum(float v) {
+	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+	return v;
+}
+__device__ __forceinline__ unsigned warpSumU(unsigned v) {
+	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+	return v;
+}
+
+enum LaneState { kNeedPair = 0, kFirstBall = 1, kWalking = 2, kIdle = 3 };
+
+template <int DIM>
+__global__ void __launch_bounds__(kBlock)
+fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
+		   float* __restrict__ pOut, float* __restrict__ gOut, unsigned int* __restrict__ workCounter,
+		   Counters* __restrict__ counters, float* __restrict__ stats12, int stageQuads) {
+	typedef FastMath M;
+	extern __shared__ float4 stage[];
+	__shared__ float cvSum[kWarps][4]; // per warp: sum of totals, completed count, sum of first-source terms
+
+	// ---- stage the boundary structure in shared memory ------------------------------------------------
+	SceneView S = Sg;
+	if (stageQuads > 0) {
+		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*Sg.nSilRefs;
+		for (int i = threadIdx.x; i < qN; i += kBlock) stage[i] = Sg.nodes[i];
+		for (int i = threadIdx.x; i < qP; i += kBlock) stage[qN + i] = Sg.prims[i];
+		for (int i = threadIdx.x; i < qF; i += kBlock) stage[qN + qP + i] = Sg.primN[i];
+		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = Sg.sils[i];
+		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP; S.sils = stage + qN + qP + qF;
+		__syncthreads();
+	}
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned ltMask = (1u << lane) - 1u;
+	unsigned cStarted = 0, cCompleted = 0, cSteps = 0, cActive = 0;
+
+	int nPairs = o.nWalks, nAnti = 1;
+	if (o.useGradientAntitheticVariates) { nPairs = o.nWalks/2 > 1 ? o.nWalks/2 : 1; nAnti = 2; }
+	const unsigned nStrata = 2u*(unsigned)nPairs;
+	const float invStrata = 1.0f/(float)nStrata;
+	const bool yukawa0 = S.absorption > 0.0f && o.stepsBeforeApplyingTikhonov == 0;
+
+	for (;;) {
+		unsigned pi = 0;
+		if (lane == 0) pi = atomicAdd(workCounter, 1u);
+		pi = __shfl_sync(kFull, pi, 0);
+		if ((long long)pi >= n) break;
+
+		// ---- per-point set-up (uniform across the warp): createSolutionGrid + estimationQuantity --------
+		const V3 x0 = mk(pts[(size_t)pi*DIM], pts[(size_t)pi*DIM + 1], DIM == 3 ? pts[(size_t)pi*DIM + 2] : 0.0f);
+		const float dDist = distDirichlet<DIM>(S, x0);
+		const float nDist = distNeumann<DIM>(S, x0, false);
+		const bool inside = S.watertight ? insideDomain<DIM>(Sg, x0) : true; // pseudo-normals live in global memory
+		// points inside the boundary mask are zeroed on output (demo/grid.h:174,227); do not walk them
+		const bool masked = fabsf(nDist) < o.boundaryDistanceMask;
+		const bool active = (inside || S.doubleSided) && !masked && nDist > 0.0f;
+
+		float sTot = 0.0f, sTot2 = 0.0f, sG[3] = {0, 0, 0}, sG2[3] = {0, 0, 0}, sFirst = 0.0f;
+		unsigned nDone = 0, lenSum = 0;
+
+		if (active) {
+			const unsigned long long gidx = indexOffset + pi;
+			const unsigned long long key = pointSeed(o.seed, gidx);
+			const unsigned permKey0 = (unsigned)(key >> 32), permKey1 = (unsigned)key;
+			const float firstR = kShrink*fminf(dDist, nDist);
+			BallFast<DIM> fb; fb.init(yukawa0, S.absorption); fb.update(firstR);
+			const float normG0 = fb.normG(), exitT = fb.exitThroughput(), bfr = fb.bdyGradFactor()/firstR;
+			if (lane < 4) cvSum[warp][lane] = 0.0f;
+			__syncwarp();
+
+			int state = kNeedPair;
+			int nextPair = 0;          // warp-uniform
+			int pair = 0, anti = 0, walkLength = 0;
+			bool onNeumann = false;
+			Pcg32 rng; rng.state = 0; rng.inc = 1;
+			unsigned long long walkSeed = 0;
+			V3 pt = x0, normal = mk(0, 0, 0), d0 = mk(0, 0, 0), e0 = mk(0, 0, 0), prevDir = mk(0, 0, 0);
+			float throughput = 1.0f, totalSource = 0.0f, firstSource = 0.0f, sfr = 0.0f, bcv = 0.0f, scv = 0.0f;
+			BallFast<DIM> bl = fb;
+
+			for (;;) {
+				// ---- refill finished lanes with the next pairs (ballot + popc compaction) -------------------
+				unsigned need = __ballot_sync(kFull, state == kNeedPair);
+				if (need) {
+					if (state == kNeedPair) {
+						int mine = nextPair + __popc(need & ltMask);
+						if (mine < nPairs) {
+							pair = mine; anti = 0; state = kFirstBall;
+							if (o.useGradientControlVariates) { // running means over the walks finished so far
+								float cnt = fmaxf(cvSum[warp][1], 1.0f);
+								bcv = cvSum[warp][0]/cnt; scv = cvSum[warp][2]/cnt;
+							}
+							walkSeed = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(pair + 1)));
+						} else state = kIdle;
+					}
+					nextPair += __popc(need);
+				}
+				if (__ballot_sync(kFull, state == kFirstBall || state == kWalking) == 0u) break;
+
+				// ---- phase 1: geometry (walk steps only) --------------------------------------------------------
+				V3 dir = mk(0, 0, 0), ipt = pt, inrm = mk(0, 0, 0);
+				float idist = 0.0f, uRad = 0.0f, uRad2 = 0.0f, uRR = 1.0f;
+				bool hit = false, sliceActive = false, terminated = false, completed = false;
+				if (state == kFirstBall) {
+					// stratified first-ball directions (generateStratifiedSamples, sampling.h:434-457):
+					// sample 2w drives the source direction, 2w+1 the boundary direction
+					Pcg32 r0; r0.state = splitmix64(walkSeed ^ 0xA0761D6478BD642Full); r0.inc = 3;
+					float us0 = ((float)permute(2u*pair, nStrata, permKey0) + r0.nextFloat())*invStrata;
+					float ub0 = ((float)permute(2u*pair + 1u, nStrata, permKey0) + r0.nextFloat())*invStrata;
+					float us1 = 0.0f, ub1 = 0.0f;
+					if (DIM == 3) {
+						us1 = ((float)permute(2u*pair, nStrata, permKey1) + r0.nextFloat())*invStrata;
+						ub1 = ((float)permute(2u*pair + 1u, nStrata, permKey1) + r0.nextFloat())*invStrata;
+					}
+					dir = sphereDir<DIM, M>(fminf(us0, 1.0f - kEps), fminf(us1, 1.0f - kEps));
+					e0 = firstR*sphereDir<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
+					uRad = r0.nextFloat(); uRad2 = r0.nextFloat();
+					bl = fb; idist = firstR; ipt = x0;
+					sliceActive = !o.ignoreSource;
+				} else if (state == kWalking) {
+					cSteps++;
+					float dirichletDist = distDirichlet<DIM>(S, pt);
+					if (!(dirichletDist > o.epsilonShell)) { terminated = true; completed = true; }
+					else {
+						bool flipOrient = false;
+						if (S.doubleSided && onNeumann && dot(prevDir, normal) < 0.0f) { normal = normal*-1.0f; flipOrient = true; } // :154-160
+						float starR;
+						if (o.stepsBeforeUsingMaximalSpheres <= walkLength) starR = dirichletDist;
+						else {
+							starR = starRadius<DIM, M>(S, pt, o.minStarRadius, dirichletDist, o.silhouettePrecision, flipOrient);
+							if (o.minStarRadius <= dirichletDist) starR = fmaxf(kShrink*starR, o.minStarRadius);
+						}
+						bl.update(starR);
+						float u0 = rng.nextFloat(), u1 = rng.nextFloat();
+						uRad = rng.nextFloat(); uRad2 = rng.nextFloat(); uRR = rng.nextFloat();
+						dir = sphereDir<DIM, M>(u0, u1);
+						if (onNeumann && dot(normal, dir) > 0.0f) dir = dir*-1.0f;
+						Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
+						hit = intersectNeumann<DIM>(S, pt, normal, dir, starR, onNeumann, h);
+						if (hit) { ipt = h.p; inrm = h.n; idist = h.d; }
+						else {
+							V3 cp = onNeumann ? offsetPoint<DIM>(pt, neg(normal)) : pt;
+							ipt = cp + starR*dir; idist = starR;
+						}
+						sliceActive = !o.ignoreSource;
+					}
+				}
+
+				// ---- phase 2 (converged): radial sample of the ball Green's function + source gather ------
+				float contribution = 0.0f, xs = 0.0f, gs = 0.0f, rs = 0.0f; bool hframe = false;
+				if (sliceActive) {
+					xs = bl.sampleX(uRad, uRad2, gs, hframe);
+					rs = hframe ? xs*bl.R : xs/bl.mu;
+					rs = fminf(fmaxf(rs, 1e-4f), bl.R);        // rClamp, distributions.h:378-379
+					if (rs <= idist) {
+						V3 c = state == kFirstBall ? x0 : pt;
+						contribution = bl.normG()*sourceAt<DIM>(S, c + rs*dir);
+					}
+				}
+
+				// ---- phase 3: bookkeeping ---------------------------------------------------------------------
+				if (state == kFirstBall) {
+					d0 = rs*dir;
+					firstSource = contribution;
+					// sourceGradientDirection = d * gradientNorm / G(r)  (walk_on_stars.h:542)
+					float sf = sliceActive ? (hframe ? bl.srcGradFactorHarmonic(xs) : bl.srcGradFactor(xs, gs)) : 0.0f;
+					sfr = sf/fmaxf(rs, 1e-20f);
+					// start antithetic walk 0 from the boundary sample
+					pt = x0 + e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = e0;
+					throughput = exitT; totalSource = firstSource;
+					rng.state = walkSeed; rng.inc = 1;
+					bl = fb;
+					state = kWalking; cStarted++;
+				} else if (state == kWalking) {
+					if (!terminated) {
+						totalSource += throughput*contribution;
+						if (!hit && outsideBox<DIM>(S, ipt)) terminated = true; // EscapedDomain: discarded
+						else {
+							// directionSampledPoissonKernel at the new position: T(starR) is already known when the
+							// walk lands on the sphere, otherwise evaluate T at the hit distance
+							throughput *= hit ? bl.stepThroughput(idist) : bl.exitThroughput();
+							pt = ipt; normal = inrm; onNeumann = hit; prevDir = dir;
+							if (!(throughput == throughput)) { terminated = true; } // NaN guard: discard
+							if (throughput < o.russianRouletteThreshold) {
+								if (throughput/o.russianRouletteThreshold < uRR) { throughput = 0.0f; terminated = true; completed = true; }
+								else throughput = o.russianRouletteThreshold;
+							}
+							if (!terminated) {
+								walkLength++;
+								if (walkLength > o.maxWalkLength) terminated = true; // ExceededMaxWalkLength: discarded
+								else if (S.absorption > 0.0f && o.stepsBeforeApplyingTikhonov == walkLength) bl.init(true, S.absorption);
+							}
+						}
+					}
+					if (terminated) {
+						if (completed) { // walk_on_stars.h:583-614
+							float total = totalSource;
+							float sgn = anti == 0 ? 1.0f : -1.0f;
+							float bE = (total - firstSource - bcv)*bfr*sgn, sE = (firstSource - scv)*sfr*sgn;
+							float g0 = bE*e0.x + sE*d0.x, g1 = bE*e0.y + sE*d0.y, g2 = bE*e0.z + sE*d0.z;
+							sTot += total; sTot2 += total*total; sFirst += firstSource;
+							sG[0] += g0; sG[1] += g1; sG[2] += g2;
+							sG2[0] += g0*g0; sG2[1] += g1*g1; sG2[2] += g2*g2;
+							nDone++; lenSum += (unsigned)walkLength;
+							atomicAdd(&cvSum[warp][0], total); atomicAdd(&cvSum[warp][1], 1.0f); atomicAdd(&cvSum[warp][2], firstSource);
+						}
+						if (anti == 0 && nAnti == 2) {
+							// antithetic twin: mirrored source and boundary samples, same walk stream (:532-536, :564-567, :579)
+							anti = 1;
+							firstSource = o.ignoreSource ? 0.0f : normG0*sourceAt<DIM>(S, x0 - d0);
+							totalSource = firstSource;
+							pt = x0 - e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = neg(e0);
+							throughput = exitT;
+							rng.state = walkSeed; rng.inc = 1;
+							bl = fb;
+							cStarted++;
+						} else state = kNeedPair;
+					}
+				}
+			}
+			cActive += lane == 0 ? 1u : 0u;
+		}
+
+		// ---- reduce the per-lane sums and write the point's estimate -------------------------------------
+		float tot = warpSum(sTot), tot2 = warpSum(sTot2), first = warpSum(sFirst);
+		float g0 = warpSum(sG[0]), g1 = warpSum(sG[1]), g2 = warpSum(sG[2]);
+		unsigned cnt = warpSumU(nDone);
+		cCompleted += lane == 0 ? cnt : 0u;
+		float inv = 1.0f/(float)(cnt > 0u ? cnt : 1u);
+		if (stats12) {
+			float q0 = warpSum(sG2[0]), q1 = warpSum(sG2[1]), q2 = warpSum(sG2[2]);
+			unsigned len = warpSumU(lenSum);
+			if (lane == 0) {
+				float* t = stats12 + (size_t)pi*12;
+				float nv = (float)(cnt > 1u ? cnt - 1u : 1u);
+				t[0] = tot*inv; t[1] = fmaxf(tot2 - tot*tot*inv, 0.0f)/nv;
+				t[2] = g0*inv; t[3] = g1*inv; t[4] = DIM == 3 ? g2*inv : 0.0f;
+				t[5] = fmaxf(q0 - g0*g0*inv, 0.0f)/nv; t[6] = fmaxf(q1 - g1*g1*inv, 0.0f)/nv; t[7] = DIM == 3 ? fmaxf(q2 - g2*g2*inv, 0.0f)/nv : 0.0f;
+				t[8] = first*inv; t[9] = (float)cnt; t[10] = (float)len*inv; t[11] = active ? 1.0f : 0.0f;
+			}
+		}
+		if (lane == 0) { // getSolution / getGradient masks, demo/grid.h:155-179, 207-237
+			bool maskP = fabsf(nDist) < o.boundaryDistanceMask;
+			bool maskG = (!inside && !S.doubleSided) || maskP;
+			pOut[pi] = maskP ? 0.0f : tot*inv;
+			gOut[(size_t)pi*DIM] = maskG ? 0.0f : g0*inv;
+			gOut[(size_t)pi*DIM + 1] = maskG ? 0.0f : g1*inv;
+			if (DIM == 3) gOut[(size_t)pi*DIM + 2] = maskG ? 0.0f : g2*inv;
+		}
+		__syncwarp();
+	}
+
+	cStarted = warpSumU(cStarted); cSteps = warpSumU(cSteps);
+	if (lane == 0 && counters) {
+		atomicAdd(&counters->walksStarted, (unsigned long long)cStarted);
+		atomicAdd(&counters->walksCompleted, (unsigned long long)cCompleted);
+		atomicAdd(&counters->steps, (unsigned long long)cSteps);
+		atomicAdd(&counters->activePoints, (unsigned long long)cActive);
+	}
+}
+
+cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d_pts, long long n,
+					   unsigned long long indexOffset, float* d_p, float* d_g, unsigned int* d_workCounter,
+					   Counters* d_counters, float* d_stats12, int smCount, cudaStream_t stream, FastLaunchInfo* info) {
+	if (n <= 0) return cudaSuccess;
+	if (n >= (1ll << 32) - 65536) return cudaErrorInvalidValue;
+	const int dim = S.dim;
+	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*S.nSilRefs;
+	size_t bytes = quads*sizeof(float4);
+	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
+	size_t smem = stageQuads ? bytes : 0;
+	int perSM = 0;
+	cudaError_t e;
+	if (dim == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fastKernel<2>, kBlock, smem);
+	else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fastKernel<3>, kBlock, smem);
+	if (e != cudaSuccess) return e;
+	if (perSM < 1) perSM = 1;
+	long long warpsNeeded = n; // one point per warp at a time
+	long long grid = (long long)smCount*perSM;
+	long long gridNeeded = (warpsNeeded + kWarps - 1)/kWarps;
+	if (grid > gridNeeded) grid = gridNeeded;
+	if (info) { info->grid = (int)grid; info->block = kBlock; info->smemBytes = (int)smem; }
+	if (dim == 2) fastKernel<2><<<(unsigned)grid, kBlock, smem, stream>>>(S, o, d_pts, n, indexOffset, d_p, d_g, d_workCounter, d_counters, d_stats12, stageQuads);
+	else fastKernel<3><<<(unsigned)grid, kBlock, smem, stream>>>(S, o, d_pts, n, indexOffset, d_p, d_g, d_workCounter, d_counters, d_stats12, stageQuads);
+	return cudaGetLastError();
+}
+
+// ---- fast-mode probes -----------------------------------------------------------------------------------
+template <int DIM>
+__global__ void probeFastKernel(int kind, long long n, const float* __restrict__ a0, const float* __restrict__ a1,
+								const float* __restrict__ params, float* __restrict__ out) {
+	long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float lambda = params[0];
+	BallFast<DIM> b; b.init(lambda > 0.0f, lambda); b.update(a0[i]);
+	if (kind == NMC_PROBE_GREENS_FAST) {
+		float r = a1[i];
+		float x = b.yukawa ? r*b.mu : r/b.R, T = 1.0f, g = 0.0f;
+		if (b.yukawa) b.evalTg(x, T, g);
+		float* o = out + i*10;
+		o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor();
+		o[5] = b.yukawa ? b.srcGradFactor(x, g) : b.srcGradFactorHarmonic(x);
+		o[6] = b.stepThroughput(r); o[7] = o[8] = o[9] = 0.0f;
+	} else {
+		float g; bool hf;
+		float x = b.sampleX(a1[i], params[1], g, hf);
+		out[i*2] = hf ? x*b.R : x/b.mu; out[i*2 + 1] = g;
+	}
+}
+cudaError_t launchProbeFast(const SceneView& S, int kind, long long n, const float* a0, const float* a1,
+							const float* params, float* d_out, cudaStream_t stream) {
+	if (n <= 0) return cudaSuccess;
+	unsigned grid = (unsigned)((n + 127)/128);
+	if (S.dim == 2) probeFastKernel<2><<<grid, 128, 0, stream>>>(kind, n, a0, a1, params, d_out);
+	else probeFastKernel<3><<<grid, 128, 0, stream>>>(kind, n, a0, a1, params, d_out);
+	return cudaGetLastError();
+}
+
+} // namespace nmc

@@ -1,0 +1,79 @@
+// tests/host_emu/emu.cpp -- TEST HARNESS ONLY (never shipped, never loaded by the product).
+// Compiles the product's device headers (csrc/*.cuh) for the HOST with g++ so that their logic can be
+// checked against the oracle in the CPU-only container before any GPU time is spent.  libnmcfs.so
+// itself contains no host execution path for these functions.
+#include <vector>
+#include <cstring>
+#include "../../neural-monte-carlo-fluid-simulation_b200/csrc/nmc_estimator.cuh"
+#include "../../neural-monte-carlo-fluid-simulation_b200/csrc/scene_build.h"
+using namespace nmc;
+
+struct EmuScene { FlatScene flat; SceneView v; std::vector<float> src; };
+
+template <int DIM>
+static void wostT(EmuScene* s, const SolverParams& o, const float* pts, int n, uint64_t off, float* p, float* g, float* st) {
+	std::vector<float> scratch((size_t)4*(o.nWalks + 2));
+	for (int i = 0; i < n; i++) {
+		V3 x = mk(pts[i*DIM], pts[i*DIM + 1], DIM == 3 ? pts[i*DIM + 2] : 0.0f);
+		LhsScratch sc; sc.base = scratch.data(); sc.stride = 1;
+		PointResult r;
+		detEstimatePoint<DIM>(s->v, o, x, off + i, sc, r);
+		p[i] = r.p; for (int k = 0; k < DIM; k++) g[i*DIM + k] = r.g[k];
+		if (st) { float* t = st + (size_t)i*12; int nv = r.nSol - 1 > 1 ? r.nSol - 1 : 1;
+			t[0] = r.solMean; t[1] = r.solM2/nv; for (int k = 0; k < 3; k++) { t[2 + k] = k < DIM ? r.gradMean[k] : 0; t[5 + k] = k < DIM ? r.gradM2[k]/nv : 0; }
+			t[8] = r.meanFirstSource; t[9] = (float)r.nSol; t[10] = (float)r.totalWalkLength/(r.nSol > 1 ? r.nSol : 1); t[11] = (float)r.active;
+			if (!r.active) for (int k = 0; k < 11; k++) t[k] = 0; }
+	}
+}
+
+extern "C" {
+void* emu_scene_create(int dim, const float* verts, int nV, const int* prims, int nP, const float* src, int n0, int n1, int n2,
+					   float absorption, int watertight, int doubleSided) {
+	EmuScene* s = new EmuScene();
+	buildFlatScene(dim, verts, nV, prims, nP, doubleSided != 0, s->flat);
+	size_t cnt = (size_t)n0*n1*(dim == 3 ? n2 : 1);
+	s->src.assign(src, src + cnt);
+	SceneView& v = s->v; memset(&v, 0, sizeof(v));
+	v.dim = dim; v.nNodes = s->flat.nNodes; v.nPrims = s->flat.nPrims; v.nSilRefs = s->flat.nSilRefs;
+	v.nodes = (const float4*)s->flat.nodes.data(); v.prims = (const float4*)s->flat.prims.data();
+	v.primN = (const float4*)s->flat.primN.data(); v.nrmV = (const float4*)s->flat.nrmV.data(); v.sils = (const float4*)s->flat.sils.data();
+	for (int k = 0; k < 3; k++) { v.bboxLo[k] = s->flat.bboxLo[k]; v.bboxHi[k] = s->flat.bboxHi[k]; }
+	v.src = s->src.data(); v.n0 = n0; v.n1 = n1; v.n2 = dim == 3 ? n2 : 1;
+	v.absorption = absorption; v.watertight = watertight; v.doubleSided = doubleSided;
+	return s;
+}
+void emu_scene_destroy(void* h) { delete (EmuScene*)h; }
+int emu_num_nodes(void* h) { return ((EmuScene*)h)->flat.nNodes; }
+void emu_nodes(void* h, float* out) {
+	EmuScene* s = (EmuScene*)h;
+	for (int i = 0; i < s->flat.nNodes; i++) {
+		const Q4* q = &s->flat.nodes[(size_t)4*i]; float* o = out + (size_t)i*16;
+		o[0] = q[0].x; o[1] = q[0].y; o[2] = q[0].z; o[3] = q[1].x; o[4] = q[1].y; o[5] = q[1].z;
+		o[6] = q[2].x; o[7] = q[2].y; o[8] = q[2].z; o[9] = q[2].w;
+		o[10] = (float)asInt(q[3].x); o[11] = (float)asInt(q[3].y); o[12] = (float)asInt(q[0].w); o[13] = (float)asInt(q[3].z);
+		o[14] = (float)asInt(q[1].w); o[15] = 0;
+	}
+}
+void emu_wost(void* h, const SolverParams* o, const float* pts, int n, uint64_t off, float* p, float* g, float* st) {
+	EmuScene* s = (EmuScene*)h;
+	if (s->v.dim == 2) wostT<2>(s, *o, pts, n, off, p, g, st); else wostT<3>(s, *o, pts, n, off, p, g, st);
+}
+// fast-mode ball functions: out per entry: T(x) g(x) normG exitThroughput bdyGradFactor srcGradFactor(x)
+void emu_ball_fast(int dim, float lambda, const float* R, const float* r, int n, float* out) {
+	for (int i = 0; i < n; i++) {
+		float* o = out + (size_t)i*6;
+		if (dim == 2) { BallFast<2> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.yukawa ? r[i]*b.mu : r[i]/R[i]; float T = 1, g = 0; if (b.yukawa) b.evalTg(x, T, g);
+			o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor(); o[5] = b.yukawa ? b.srcGradFactor(x, g) : b.srcGradFactorHarmonic(x); }
+		else { BallFast<3> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.yukawa ? r[i]*b.mu : r[i]/R[i]; float T = 1, g = 0; if (b.yukawa) b.evalTg(x, T, g);
+			o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor(); o[5] = b.yukawa ? b.srcGradFactor(x, g) : b.srcGradFactorHarmonic(x); }
+	}
+}
+// inverse-CDF sampler: out r per entry
+void emu_sample_fast(int dim, float lambda, const float* R, const float* u, const float* u2, int n, float* out) {
+	for (int i = 0; i < n; i++) {
+		float g; bool hf;
+		if (dim == 2) { BallFast<2> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.sampleX(u[i], u2[i], g, hf); out[i] = hf ? x*R[i] : x/b.mu; }
+		else { BallFast<3> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.sampleX(u[i], u2[i], g, hf); out[i] = hf ? x*R[i] : x/b.mu; }
+	}
+}
+}

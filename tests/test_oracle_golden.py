@@ -1,0 +1,118 @@
+"""The plain-C oracle (oracle/nmc_oracle.c) against the golden vectors generated from the reference
+itself (tests/golden/make_golden_vectors.py) -- BIT-EXACT -- and, where oracle/_ref is present, against
+the reference's own code run live."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+V = os.path.join(util.GOLDEN, "vectors")
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({4: np.uint32, 8: np.uint64}[a.dtype.itemsize]) if a.dtype.kind == "f" else a
+
+
+def assert_same(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, what
+    same = bits(a) == bits(b)
+    if a.dtype.kind == "f":
+        same |= np.isnan(a) & np.isnan(b)
+    assert same.all(), "%s: %d of %d entries differ" % (what, (~same).sum(), same.size)
+
+
+def test_rng_and_samplers(oracle_lib):
+    k = np.load(os.path.join(V, "rng.npz"))
+    for dim in (2, 3):
+        assert_same(oracle_lib.pcg32_uint(dim, 42, 1, 64), k["uint_%d" % dim], "pcg32 uint")
+        assert_same(oracle_lib.pcg32_float(dim, 0x9E3779B97F4A7C15, 1, 64), k["float_%d" % dim], "pcg32 float")
+        assert_same(oracle_lib.pcg32_bounded(dim, 7, 1, k["bounds"]), k["bounded_%d" % dim], "pcg32 bounded")
+        s, st = oracle_lib.stratified(dim, 99, 100)
+        assert_same(s, k["strat_%d" % dim], "stratified samples")
+        assert_same(st, k["strat_state_%d" % dim], "rng state after stratification")
+        assert_same(oracle_lib.sphere_dir(dim, k["sphere_u_%d" % dim]), k["sphere_%d" % dim], "sphere directions")
+    assert_same(np.array([oracle_lib.point_seed(2, 5, i) for i in range(16)], np.uint64), k["point_seed"], "point seed")
+
+
+def test_special_functions(oracle_lib):
+    k = np.load(os.path.join(V, "special.npz"))
+    for kind in range(5):
+        assert_same(oracle_lib.bessel(2, kind, k["x"]), k["bessel_%d" % kind], "bessel kind %d" % kind)
+    for dim in (2, 3):
+        for lam in (350.0, 0.0):
+            assert_same(oracle_lib.greens_ball(dim, lam, k["R"], k["r"]), k["greens_%d_%g" % (dim, lam)], "ball greens fn")
+            r, pdf, draws = oracle_lib.sample_volume(dim, lam, k["R"], k["seeds"])
+            assert_same(r, k["sv_r_%d_%g" % (dim, lam)], "sampleVolume r")
+            assert_same(pdf, k["sv_pdf_%d_%g" % (dim, lam)], "sampleVolume pdf")
+            assert_same(draws, k["sv_draws_%d_%g" % (dim, lam)], "sampleVolume draw count")
+
+
+@pytest.mark.parametrize("case", list(util.CASES))
+def test_scene_queries_and_estimator(oracle_lib, case):
+    k = np.load(os.path.join(V, case + ".npz"))
+    cfg = util.load_case(case)
+    dim = cfg["dim"]
+    sc = oracle_lib.OracleScene(dim, cfg["scene"], util.source_grid(dim))
+    lo, hi = sc.bbox()
+    assert_same(lo, k["bbox_lo"], "bbox"); assert_same(hi, k["bbox_hi"], "bbox")
+    q = k["q"]
+    assert_same(sc.dist_neumann(q), k["dist"], "distance to boundary")
+    assert_same(sc.dist_neumann(q, True), k["sdist"], "signed distance")
+    assert_same(sc.dist_dirichlet(q), k["ddist"], "distance to (absent) Dirichlet boundary")
+    assert_same(sc.inside_domain(q), k["inside"], "insideDomain")
+    assert_same(sc.source(q), k["source"], "source lookup")
+    assert_same(sc.star_radius(q, 1e-3, k["ddist"], 1e-3, False), k["star0"], "star radius")
+    assert_same(sc.star_radius(q, 1e-3, k["ddist"], 1e-3, True), k["star1"], "star radius (flipped)")
+    ray = sc.intersect_neumann(q, np.zeros_like(q), k["dirs"], k["tmax"], 0)
+    assert_same(ray[:, 0], k["ray"][:, 0], "ray hit flag")
+    hit = ray[:, 0] > 0
+    assert_same(ray[hit], k["ray"][hit], "ray hit record")
+    if len(k["onb_p"]):
+        ray = sc.intersect_neumann(k["onb_p"], k["onb_n"], k["onb_d"], k["onb_t"], 1)
+        assert_same(ray[:, 0], k["onb_ray"][:, 0], "on-boundary ray hit flag")
+        hit = ray[:, 0] > 0
+        assert_same(ray[hit], k["onb_ray"][hit], "on-boundary ray hit record")
+        assert_same(sc.star_radius(k["onb_p"], 1e-3, sc.dist_dirichlet(k["onb_p"]), 1e-3, False), k["onb_star"], "star radius on boundary")
+    p, g, st = sc.wost(cfg["solver"], cfg["output"], k["pts"], seed=int(k["seed"]), nthreads=4, want_stats=True)
+    assert_same(p, k["p"], "p"); assert_same(g, k["g"], "grad p"); assert_same(st, k["stats"], "estimator statistics")
+    if case == "taylorgreen_shipped":  # SURVEY.md finding 4: every point is classified outside
+        assert not p.any() and not g.any()
+    sc.close()
+
+
+@pytest.mark.parametrize("case", ["karman", "smoke3d"])
+def test_oracle_against_live_reference(oracle_lib, case):
+    from oracle import refbind
+    cfg = util.load_case(case)
+    dim = cfg["dim"]
+    if not refbind.available(dim):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    src = util.source_grid(dim, scale=0.7)
+    a = refbind.RefScene(dim, cfg["scene"], src)
+    b = oracle_lib.OracleScene(dim, cfg["scene"], src)
+    lo, hi = a.bbox()
+    pts = util.random_points(lo, hi, 96, seed=21)
+    solver = dict(cfg["solver"], nWalks=64)
+    ra = a.wost(solver, cfg["output"], pts, seed=99, index_offset=1000, nthreads=4, want_stats=True)
+    rb = b.wost(solver, cfg["output"], pts, seed=99, index_offset=1000, nthreads=4, want_stats=True)
+    for x, y, w in zip(ra, rb, ("p", "grad", "stats")):
+        assert_same(y, x, w)
+    a.close(); b.close()
+
+
+def test_oracle_thread_and_shard_invariance(oracle_lib):
+    cfg = util.load_case("karman")
+    sc = oracle_lib.OracleScene(2, cfg["scene"], util.source_grid(2))
+    lo, hi = sc.bbox()
+    pts = util.random_points(lo, hi, 64, seed=1)
+    solver = dict(cfg["solver"], nWalks=40)
+    p1, g1, _ = sc.wost(solver, cfg["output"], pts, seed=5, nthreads=1)
+    p4, g4, _ = sc.wost(solver, cfg["output"], pts, seed=5, nthreads=4)
+    assert_same(p1, p4, "threads"); assert_same(g1, g4, "threads")
+    pa, ga, _ = sc.wost(solver, cfg["output"], pts[:30], seed=5, index_offset=0)
+    pb, gb, _ = sc.wost(solver, cfg["output"], pts[30:], seed=5, index_offset=30)
+    assert_same(np.concatenate([pa, pb]), p1, "shards"); assert_same(np.concatenate([ga, gb]), g1, "shards")

@@ -1,0 +1,60 @@
+"""Shared helpers for the tests: fixtures, synthetic inputs, loaders for the oracle and the product."""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SCENES = os.path.join(GOLDEN, "scenes")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# (fixture, scene overrides): the four distinct example geometries; Taylor-Green both as shipped
+# (isWatertight:true -> every point is classified outside -> zeros) and with the solver active.
+CASES = {
+    "taylorgreen_active": ("taylorgreen", {"isWatertight": False}),
+    "taylorgreen_shipped": ("taylorgreen", {}),
+    "karman": ("karman", {}),
+    "smoke3d": ("smoke3d", {}),
+    "karman3d": ("karman3d", {}),
+}
+
+
+def load_case(case):
+    name, over = CASES[case]
+    cfg = json.load(open(os.path.join(SCENES, name + ".json")))
+    cfg["scene"]["boundary"] = os.path.join(SCENES, name + ".obj")
+    cfg["scene"].update(over)
+    return cfg
+
+
+def source_grid(dim, scale=1.0):
+    """Smooth synthetic source on a small grid (non-square on purpose: row/column mix-ups show up)."""
+    if dim == 2:
+        h, w = 101, 103
+        y, x = np.meshgrid(np.linspace(0, 1, h), np.linspace(0, 1, w), indexing="ij")
+        return (scale*np.sin(6.1*x)*np.sin(4.3*y + 0.3)).astype(np.float32)
+    n0, n1, n2 = 22, 23, 24
+    x, y, z = np.meshgrid(np.linspace(0, 1, n0), np.linspace(0, 1, n1), np.linspace(0, 1, n2), indexing="ij")
+    return (scale*np.sin(6.1*x)*np.sin(4.3*y + 0.3)*np.cos(3*z)).astype(np.float32)
+
+
+def random_points(lo, hi, n, seed=0, margin=0.0):
+    rng = np.random.default_rng(seed)
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    ext = hi - lo
+    return (rng.random((n, len(lo)), dtype=np.float32)*ext*(1 + 2*margin) + lo - margin*ext).astype(np.float32)
+
+
+def package():
+    return importlib.import_module("neural-monte-carlo-fluid-simulation_b200")
+
+
+def close_mask(a, b, rtol=1e-5, atol_scale=1e-7):
+    """|a-b| <= rtol*max(|a|,|b|) + atol, atol = atol_scale * mean|channel|."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    atol = atol_scale*max(np.abs(b).mean(), 1e-30)
+    return np.abs(a - b) <= rtol*np.maximum(np.abs(a), np.abs(b)) + atol
