@@ -246,18 +246,12 @@ struct BallExact {
 };
 
 // ---- fast-mode special functions (fp32) -------------------------------------------------------------
-#if !defined(__CUDA_ARCH__)
-// host stand-ins so the header also compiles for the CPU-side unit harness (tests/host_emu)
-inline float __expf(float x) { return expf(x); }
-inline float __logf(float x) { return logf(x); }
-inline float rsqrtf(float x) { return 1.0f/sqrtf(x); }
-#endif
 
 // Exponentially scaled modified Bessel functions i0e = e^-x I0, i1e = e^-x I1, k0e = e^x K0,
 // k1e = e^x K1 from the Abramowitz-Stegun 9.8.1-9.8.8 fits (the ones bessel.hpp uses; |err| < 2e-7),
 // evaluated in float with the exponential factored out so that nothing overflows for large x.
 struct Bessel4 { float i0e, i1e, k0e, k1e; };
-NMC_HD Bessel4 besselScaled(float x) {
+NMC_TRAV Bessel4 besselScaled(float x) {
 	Bessel4 b;
 	if (x < 3.75f) {
 		float y = x*(1.0f/3.75f); y = y*y;
@@ -332,20 +326,27 @@ struct BallFast {
 			bdyFac = mu*0.5f*(1.0f - e2)/i32e;
 		}
 	}
-	// T(x), g(x), 0 < x <= X
-	NMC_HD void evalTg(float x, float& T, float& g) const {
+	// T(x), g(x) and q(x) = K1(x) - I1(x) K1(X)/I1(X) (2D) / K32(x) - I32(x) K32(X)/I32(X) (3D), 0 < x <= X
+	NMC_HD void evalTgq(float x, float& T, float& g, float& q) const {
 		if (DIM == 2) {
 			Bessel4 b = besselScaled(x);
-			float em = __expf(-x), ep = ratio0*__expf(x - 2.0f*X);
+			float em = __expf(-x), e2 = __expf(x - 2.0f*X);
+			float ep = ratio0*e2;
 			T = x*(b.k1e*em + b.i1e*ep);
 			g = b.k0e*em - b.i0e*ep;
+			q = b.k1e*em - b.i1e*ratio1*e2;
 		} else {
 			float em = __expf(-x), ed = __expf(-2.0f*(X - x));
 			float sh = em*(1.0f - ed)*ratio0, ch = em*(1.0f + ed)*ratio0;
 			T = x*ch + sh;
 			g = sh;
+			float e2x = em*em, x2 = x*x;
+			float k32 = em*(1.0f + 1.0f/x);
+			float i32e = x < 0.3f ? x2*(1.0f/3.0f)*(1.0f + x2*0.1f)*em : 0.5f*(1.0f + e2x) - 0.5f*(1.0f - e2x)/x; // e^-x I32(x)
+			q = k32 - i32e*ratio1*(em*ed);       // e^{x - 2X} = e^{-x} e^{-2(X - x)}
 		}
 	}
+	NMC_HD void evalTg(float x, float& T, float& g) const { float q; evalTgq(x, T, g, q); }
 	// |G| = integral of the Green's function over the ball
 	NMC_HD float normG() const {
 		if (!yukawa) return DIM == 2 ? R*R*0.25f : R*R*(1.0f/6.0f);
@@ -367,26 +368,15 @@ struct BallFast {
 		if (DIM == 2) return (1.0f/(y*R))*(1.0f - y*y)/fmaxf(-__logf(y), 1e-20f);  // r (1/r^2 - 1/R^2)/ln(R/r)
 		return (1.0f/(y*R))*(1.0f + y + y*y);                                        // r (1/r^3 - 1/R^3)/(1/r - 1/R)
 	}
-	NMC_HD float srcGradFactor(float x, float g) const {
-		if (DIM == 2) {
-			Bessel4 b = besselScaled(x);
-			float q = b.k1e*__expf(-x) - b.i1e*ratio1*__expf(x - 2.0f*X);
-			return mu*q/fmaxf(g, 1e-30f);
-		}
-		float e2x = __expf(-2.0f*x), x2 = x*x;
-		float k32 = __expf(-x)*(1.0f + 1.0f/x);
-		float i32e = x < 0.3f ? x2*(1.0f/3.0f)*(1.0f + x2*0.1f)*__expf(-x) : 0.5f*(1.0f + e2x) - 0.5f*(1.0f - e2x)/x; // e^-x I32(x)
-		float q = k32 - i32e*ratio1*__expf(x - 2.0f*X);
-		return mu*q/fmaxf(g, 1e-30f);
-	}
+	NMC_HD float srcGradFactor(float q, float g) const { return mu*q/fmaxf(g, 1e-30f); }
 	// inverse CDF of the radial density: returns x = r*mu (Yukawa) or y = r/R (harmonic) for u in [0,1);
 	// g receives g(x) (Yukawa only).  F vanishes quadratically at both ends of the interval, so Newton
 	// runs on sqrt(F) (u < 1/2) or sqrt(1 - F) (u >= 1/2), which are close to linear there.
 	// Tiny balls (X < 0.05) use the harmonic law: the two densities differ by O(X^2).
-	NMC_HD float sampleX(float u, float u2, float& g, bool& harmonicFrame) const {
+	NMC_HD float sampleX(float u, float u2, float& g, float& q, bool& harmonicFrame) const {
 		harmonicFrame = !yukawa || X < 0.05f;
 		if (harmonicFrame) {
-			g = 0.0f;
+			g = 0.0f; q = 0.0f;
 			if (DIM == 3) { // Ulrich's polar method, r/R = (1 + sqrt(1 - cbrt(u^2)) cos(2 pi u2))/2
 				float y = 0.5f*(1.0f + sqrtf(fmaxf(0.0f, 1.0f - cbrtf(u*u)))*cosf(6.2831853f*u2));
 				return fminf(fmaxf(y, 1e-6f), 1.0f);
@@ -419,19 +409,20 @@ struct BallFast {
 			x = fminf(x, 0.7f*X);
 		} else x = X - fminf(sqrtf(2.0f*mass/TX), 0.7f*X);
 		x = fminf(fmaxf(x, 1e-6f*X), X*(1.0f - 1e-6f));
-		float T, gg = 0.0f;
+		// g and q are returned at the last EVALUATED iterate; the final Newton correction is below the
+		// tolerance there (|dx| <= 1e-4 X), far inside the Monte Carlo noise of the gradient estimator
+		float T, gg = 0.0f, qq = 0.0f;
 		for (int it = 0; it < 6; it++) {
-			evalTg(x, T, gg);
-			float q = sqrtf(fmaxf(lower ? 1.0f - T : T - TX, 1e-30f));
-			float step = 2.0f*q*(q - target)/fmaxf(x*gg, 1e-30f);
+			evalTgq(x, T, gg, qq);
+			float s = sqrtf(fmaxf(lower ? 1.0f - T : T - TX, 1e-30f));
+			float step = 2.0f*s*(s - target)/fmaxf(x*gg, 1e-30f);
 			float xn = lower ? x - step : x + step;
 			xn = fminf(fmaxf(xn, 0.25f*x), 0.5f*(x + X));
-			bool done = fabsf(xn - x) <= 4e-6f*X;
+			bool done = fabsf(xn - x) <= 1e-4f*X;
 			x = xn;
 			if (done) break;
 		}
-		evalTg(x, T, gg);
-		g = gg;
+		g = gg; q = qq;
 		return x;
 	}
 };

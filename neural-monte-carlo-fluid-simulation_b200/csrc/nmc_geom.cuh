@@ -8,7 +8,7 @@
 // Layout (all 16-byte records so that a node / primitive is fetched with vectorised loads and the
 // whole structure can be staged in shared memory when it is small):
 //   nodes  4 x float4 per node : (lo.xyz, nRefs) (hi.xyz, secondChildOffset) (coneAxis.xyz, halfAngle)
-//                                (refOffset, silOffset, nSilRefs, -)            [ints stored bit-cast]
+//                                (refOffset, silOffset, nSilRefs, cos(halfAngle))  [ints stored bit-cast]
 //   prims  2D 1 x float4 per segment (pa.xy, pb.xy); 3D 3 x float4 per triangle (pa, pb, pc)
 //   primN  1 x float4 per primitive: unit face normal, w = primitive index in the input mesh
 //   nrmV   pseudo-normals for signed distance: 2D 2 x float4 (vertex a, b); 3D 6 x float4
@@ -104,6 +104,37 @@ NMC_HD bool coneOverlap(V3 axis, float halfAngle, V3 o, V3 lo, V3 hi, float dist
 	return sum >= kPi2 ? true : inRange((float)kPi2, dAxisAngle - sum, dAxisAngle + sum);
 }
 
+// Same predicate without inverse trigonometry (default mode): with c = axis.view,
+//   inRange(pi/2, a - h, a + h), a = acos(c)  <=>  |asin c| <= h  <=>  |c| <= sin h      (h < pi/2)
+// and for the widened test  |c| <= sin(h + v) = sin h cos v + cos h sin v, "h + v >= pi/2" <=> cos(h + v) <= 0,
+// where (sin v, cos v) = (r/l, sqrt(1 - r^2/l^2)) or (d, s)/sqrt(d^2 + s^2).  cosH = cos(halfAngle) is stored per node.
+NMC_HD bool coneOverlapFast(V3 axis, float cosH, V3 o, V3 lo, V3 hi, float distToBox) {
+	if (cosH <= 0.0f || distToBox < kEps) return true;
+	float sinH = sqrtf(fmaxf(0.0f, 1.0f - cosH*cosH));
+	V3 c = (lo + hi)*0.5f;
+	V3 vca = c - o;
+	float l2 = dot(vca, vca);
+	float il = rsqrtf(l2);
+	vca = vca*il;
+	float ca = fabsf(fminf(1.0f, fmaxf(-1.0f, dot(axis, vca))));
+	if (ca <= sinH) return true;
+	V3 e = hi - c;
+	float r2 = dot(e, e);
+	float sv, cv;
+	if (l2 > r2) { sv = sqrtf(r2)*il; cv = sqrtf(fmaxf(0.0f, 1.0f - sv*sv)); }
+	else {
+		float l = l2*il;
+		float d = dot(e, mk(fabsf(vca.x), fabsf(vca.y), fabsf(vca.z)));
+		float sgap = l - d;
+		if (sgap <= 0.0f) return true;
+		d = projectToPlane(vca, e);
+		float ih = rsqrtf(d*d + sgap*sgap);
+		sv = d*ih; cv = sgap*ih;
+	}
+	if (cosH*cv - sinH*sv <= 0.0f) return true;
+	return ca <= sinH*cv + cosH*sv;
+}
+
 // findClosestPointLineSegment (line_segments.inl:184-209)
 NMC_HD float closestOnSegment(V3 pa, V3 pb, V3 x, V3& pt, float& t) {
 	V3 u = pb - pa, v = x - pa;
@@ -154,7 +185,7 @@ struct Trav { int node; float dist; };
 // Returns false when nothing lies within sqrt(r2).  wantNormal: pseudo-normal as in
 // LineSegment/Triangle::normal(uv) with soup normals present (line_segments.inl:60-77, triangles.inl:62-90).
 template <int DIM>
-NMC_HD bool closestPoint(const SceneView& S, V3 x, float r2, bool wantNormal, Hit& out) {
+NMC_TRAV bool closestPoint(const SceneView& S, V3 x, float r2, bool wantNormal, Hit& out) {
 	if (S.nNodes == 0) return false;
 	Trav stack[NMC_STACK];
 	float b0, b1, b2, b3;
@@ -278,7 +309,7 @@ NMC_HD bool primRay(const SceneView& S, int ri, V3 o, V3 dir, float tMax, bool o
 }
 // closest-hit / any-hit ray: Sbvh::intersectFromNode + processSubtreeForIntersection (sbvh.inl:538-683)
 template <int DIM>
-NMC_HD bool rayIntersect(const SceneView& S, V3 o, V3 dir, float tMax, bool occl, Hit& out) {
+NMC_TRAV bool rayIntersect(const SceneView& S, V3 o, V3 dir, float tMax, bool occl, Hit& out) {
 	if (S.nNodes == 0) return false;
 	V3 invD = mk(1.0f/dir.x, 1.0f/dir.y, 1.0f/dir.z);
 	Trav stack[NMC_STACK];
@@ -332,7 +363,7 @@ NMC_HD bool isSilhouette(float concavity, V3 n0, V3 n1, V3 viewDir, float d, boo
 // closest silhouette point: Sbvh::findClosestSilhouettePointFromNode (sbvh.inl:1093-1255) with
 // SilhouetteVertex/Edge::findClosestSilhouettePoint (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143)
 template <int DIM, class M>
-NMC_HD bool closestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
+NMC_TRAV bool closestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
 	if (S.nNodes == 0) return false;
 	if (sqMinR >= r2) return false;
 	Trav stack[NMC_STACK];
@@ -389,13 +420,21 @@ NMC_HD bool closestSilhouette(const SceneView& S, V3 x, float r2, bool flip, flo
 			if (k0.w >= 0.0f) {
 				V3 lo = xyz(S.nodes[4*c0]), hi = xyz(S.nodes[4*c0 + 1]);
 				boxSqDist(lo, hi, x, b0, tmp);
+#if defined(NMC_FAST_GEOM)
+				hit0 = b0 <= r2 && coneOverlapFast(xyz(k0), S.nodes[4*c0 + 3].w, x, lo, hi, b0);
+#else
 				hit0 = b0 <= r2 && coneOverlap<M>(xyz(k0), k0.w, x, lo, hi, b0);
+#endif
 			}
 			float4 k1 = S.nodes[4*c1 + 2];
 			if (k1.w >= 0.0f) {
 				V3 lo = xyz(S.nodes[4*c1]), hi = xyz(S.nodes[4*c1 + 1]);
 				boxSqDist(lo, hi, x, b1, tmp);
+#if defined(NMC_FAST_GEOM)
+				hit1 = b1 <= r2 && coneOverlapFast(xyz(k1), S.nodes[4*c1 + 3].w, x, lo, hi, b1);
+#else
 				hit1 = b1 <= r2 && coneOverlap<M>(xyz(k1), k1.w, x, lo, hi, b1);
+#endif
 			}
 			if (hit0 && hit1) {
 				int closer = c0, other = c1;

@@ -18,8 +18,25 @@
 #define NMC_HD inline
 #define NMC_D inline
 #endif
+// NMC_FAST_GEOM (defined by wost_fast.cu only): the default mode needs statistical, not bitwise, agreement,
+// so min/max map to single FMNMX instructions, vector/scalar divisions become one reciprocal + multiplies,
+// the normal-cone test is evaluated without inverse trigonometric functions, and the three BVH traversals
+// are kept out of line (one copy each) to keep the kernel inside the instruction cache.
+#if defined(NMC_FAST_GEOM) && defined(__CUDACC__)
+#define NMC_TRAV __host__ __device__ __noinline__
+#else
+#define NMC_TRAV NMC_HD
+#endif
 
 namespace nmc {
+
+#if !defined(__CUDA_ARCH__)
+// host stand-ins (found before CUDA's device intrinsics by name lookup inside this namespace) so that the
+// headers also compile for the host pass and for the CPU-side unit harness (tests/host_emu)
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
+inline float rsqrtf(float x) { return 1.0f/sqrtf(x); }
+#endif
 
 static constexpr float kEps = FLT_EPSILON;
 static constexpr float kMaxF = FLT_MAX;
@@ -34,11 +51,20 @@ NMC_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 NMC_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 NMC_HD V3 operator*(V3 a, float s) { return mk(a.x*s, a.y*s, a.z*s); }
 NMC_HD V3 operator*(float s, V3 a) { return mk(s*a.x, s*a.y, s*a.z); }
+#if defined(NMC_FAST_GEOM)
+NMC_HD V3 operator/(V3 a, float s) { float r = 1.0f/s; return mk(a.x*r, a.y*r, a.z*r); }
+#else
 NMC_HD V3 operator/(V3 a, float s) { return mk(a.x/s, a.y/s, a.z/s); }
+#endif
 NMC_HD V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
 // std::min / std::max argument order and NaN behaviour
+#if defined(NMC_FAST_GEOM)
+NMC_HD float minS(float a, float b) { return fminf(a, b); }
+NMC_HD float maxS(float a, float b) { return fmaxf(a, b); }
+#else
 NMC_HD float minS(float a, float b) { return (b < a) ? b : a; }
 NMC_HD float maxS(float a, float b) { return (a < b) ? b : a; }
+#endif
 // Eigen fixed-size reductions associate as x0 + (x1 + x2)  (Eigen/src/Core/Redux.h:99-113)
 NMC_HD float dot(V3 a, V3 b) { return a.x*b.x + (a.y*b.y + a.z*b.z); }
 NMC_HD float norm(V3 a) { return sqrtf(dot(a, a)); }
@@ -119,6 +145,16 @@ NMC_HD uint64_t pointSeed(uint64_t seed, uint64_t index) {
 // sampleUnitSphereUniform<DIM>(float* u)  (reference: include/zombie/core/sampling.h:29-45)
 template <int DIM, class M>
 NMC_HD V3 sphereDir(float u0, float u1) {
+#if defined(NMC_FAST_GEOM) && defined(__CUDA_ARCH__)
+	{ // default mode: sincospi has no large-argument slow path
+		float sn, cs;
+		if (DIM == 2) { sincospif(2.0f*u0, &sn, &cs); return mk(cs, sn, 0.0f); }
+		float z = 1.0f - 2.0f*u0;
+		float r = sqrtf(fmaxf(0.0f, 1.0f - z*z));
+		sincospif(2.0f*u1, &sn, &cs);
+		return mk(r*cs, r*sn, z);
+	}
+#endif
 	if (DIM == 2) {
 		float phi = (float)(2.0f*kPi*u0);
 		return mk(M::cos_(phi), M::sin_(phi), 0.0f);

