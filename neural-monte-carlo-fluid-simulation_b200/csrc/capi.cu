@@ -176,7 +176,7 @@ static int solveDevice(nmc_scene* s, const nmc_solver_opts* opts, const float* d
 	} else {
 		FastLaunchInfo info;
 		CK(cudaMemsetAsync(s->d_workCounter, 0, sizeof(unsigned int), stream));
-		CK(launchFast(s->view, p, d_pts, n, indexOffset, d_p, d_g, s->d_workCounter, s->d_counters, d_stats12, s->smCount, stream, &info));
+		CK(launchFast(s->view, p, d_pts, n, indexOffset, d_p, d_g, s->d_workCounter, s->d_counters, d_stats12, s->smCount, s->flat.maxDepth, stream, &info));
 		launches++;
 	}
 	CK(cudaEventRecord(s->ev[1], stream));

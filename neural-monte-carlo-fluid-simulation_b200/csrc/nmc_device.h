@@ -21,7 +21,7 @@ int probeWidth(int dim, int kind);
 struct FastLaunchInfo { int grid, block, smemBytes; };
 cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d_pts, long long n,
 					   unsigned long long indexOffset, float* d_p, float* d_g, unsigned int* d_workCounter,
-					   Counters* d_counters, float* d_stats12, int smCount, cudaStream_t stream, FastLaunchInfo* info);
+					   Counters* d_counters, float* d_stats12, int smCount, int maxDepth, cudaStream_t stream, FastLaunchInfo* info);
 cudaError_t launchProbeFast(const SceneView& S, int kind, long long n, const float* a0, const float* a1,
 							const float* params, float* d_out, cudaStream_t stream);
 

@@ -179,15 +179,28 @@ NMC_HD float closestOnTriangle(V3 pa, V3 pb, V3 pc, V3 x, V3& pt, float& t0, flo
 	return norm(x - pt);
 }
 
-struct Trav { int node; float dist; };
+// Traversal stack policies.  LocalStack: a plain per-thread array (deterministic mode, host harness).
+// StridedStack: entries of one thread interleaved with those of the other threads of the CTA in shared
+// memory (slot i of thread t at base[i*stride + t]) -- bank-conflict free and no local-memory traffic.
+struct LocalStack {
+	int n[NMC_STACK]; float d[NMC_STACK];
+	NMC_HD void put(int i, int node, float dist) { n[i] = node; d[i] = dist; }
+	NMC_HD int node(int i) const { return n[i]; }
+	NMC_HD float dist(int i) const { return d[i]; }
+};
+struct StridedStack {
+	int* nodes; float* dists; int stride;
+	NMC_HD void put(int i, int node, float dist) { nodes[i*stride] = node; dists[i*stride] = dist; }
+	NMC_HD int node(int i) const { return nodes[i*stride]; }
+	NMC_HD float dist(int i) const { return dists[i*stride]; }
+};
 
 // closest point on the boundary mesh: Sbvh::findClosestPointFromNode (sbvh.inl:948-1074).
 // Returns false when nothing lies within sqrt(r2).  wantNormal: pseudo-normal as in
 // LineSegment/Triangle::normal(uv) with soup normals present (line_segments.inl:60-77, triangles.inl:62-90).
-template <int DIM>
-NMC_TRAV bool closestPoint(const SceneView& S, V3 x, float r2, bool wantNormal, Hit& out) {
+template <int DIM, class Stack>
+NMC_TRAV bool closestPoint(const SceneView& S, Stack& stack, V3 x, float r2, bool wantNormal, Hit& out) {
 	if (S.nNodes == 0) return false;
-	Trav stack[NMC_STACK];
 	float b0, b1, b2, b3;
 	bool found = false;
 	{
@@ -196,11 +209,11 @@ NMC_TRAV bool closestPoint(const SceneView& S, V3 x, float r2, bool wantNormal, 
 	}
 	if (!(b0 <= r2)) return false;
 	r2 = minS(r2, b1);
-	stack[0].node = 0; stack[0].dist = b0;
+	stack.put(0, 0, b0);
 	int sp = 0;
 	out.d = kMaxF; out.ref = -1; out.u = 0.0f; out.v = 0.0f;
 	while (sp >= 0) {
-		int ni = stack[sp].node; float cd = stack[sp].dist; sp--;
+		int ni = stack.node(sp); float cd = stack.dist(sp); sp--;
 		if (cd > r2) continue;
 		float4 na = S.nodes[4*ni], nb = S.nodes[4*ni + 1];
 		int nRefs = asInt(na.w);
@@ -235,10 +248,10 @@ NMC_TRAV bool closestPoint(const SceneView& S, V3 x, float r2, bool wantNormal, 
 					float t = b0; b0 = b2; b2 = t;
 					closer = c1; other = c0;
 				}
-				sp++; stack[sp].node = other; stack[sp].dist = b2;
-				sp++; stack[sp].node = closer; stack[sp].dist = b0;
-			} else if (hit0) { sp++; stack[sp].node = c0; stack[sp].dist = b0; }
-			else if (hit1) { sp++; stack[sp].node = c1; stack[sp].dist = b2; }
+				sp++; stack.put(sp, other, b2);
+				sp++; stack.put(sp, closer, b0);
+			} else if (hit0) { sp++; stack.put(sp, c0, b0); }
+			else if (hit1) { sp++; stack.put(sp, c1, b2); }
 		}
 	}
 	if (found && wantNormal) {
@@ -308,18 +321,17 @@ NMC_HD bool primRay(const SceneView& S, int ri, V3 o, V3 dir, float tMax, bool o
 	return false;
 }
 // closest-hit / any-hit ray: Sbvh::intersectFromNode + processSubtreeForIntersection (sbvh.inl:538-683)
-template <int DIM>
-NMC_TRAV bool rayIntersect(const SceneView& S, V3 o, V3 dir, float tMax, bool occl, Hit& out) {
+template <int DIM, class Stack>
+NMC_TRAV bool rayIntersect(const SceneView& S, Stack& stack, V3 o, V3 dir, float tMax, bool occl, Hit& out) {
 	if (S.nNodes == 0) return false;
 	V3 invD = mk(1.0f/dir.x, 1.0f/dir.y, 1.0f/dir.z);
-	Trav stack[NMC_STACK];
 	float b0, b1, b2, b3;
 	int hits = 0;
 	if (!boxRay(xyz(S.nodes[0]), xyz(S.nodes[1]), o, invD, tMax, b0, b1)) return false;
-	stack[0].node = 0; stack[0].dist = b0;
+	stack.put(0, 0, b0);
 	int sp = 0;
 	while (sp >= 0) {
-		int ni = stack[sp].node; float cd = stack[sp].dist; sp--;
+		int ni = stack.node(sp); float cd = stack.dist(sp); sp--;
 		if (cd > tMax) continue;
 		float4 na = S.nodes[4*ni];
 		int nRefs = asInt(na.w);
@@ -341,10 +353,10 @@ NMC_TRAV bool rayIntersect(const SceneView& S, V3 o, V3 dir, float tMax, bool oc
 			if (hit0 && hit1) {
 				int closer = c0, other = c1;
 				if (b2 < b0) { float t = b0; b0 = b2; b2 = t; closer = c1; other = c0; }
-				sp++; stack[sp].node = other; stack[sp].dist = b2;
-				sp++; stack[sp].node = closer; stack[sp].dist = b0;
-			} else if (hit0) { sp++; stack[sp].node = c0; stack[sp].dist = b0; }
-			else if (hit1) { sp++; stack[sp].node = c1; stack[sp].dist = b2; }
+				sp++; stack.put(sp, other, b2);
+				sp++; stack.put(sp, closer, b0);
+			} else if (hit0) { sp++; stack.put(sp, c0, b0); }
+			else if (hit1) { sp++; stack.put(sp, c1, b2); }
 		}
 	}
 	return hits > 0;
@@ -362,19 +374,18 @@ NMC_HD bool isSilhouette(float concavity, V3 n0, V3 n1, V3 viewDir, float d, boo
 }
 // closest silhouette point: Sbvh::findClosestSilhouettePointFromNode (sbvh.inl:1093-1255) with
 // SilhouetteVertex/Edge::findClosestSilhouettePoint (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143)
-template <int DIM, class M>
-NMC_TRAV bool closestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
+template <int DIM, class M, class Stack>
+NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
 	if (S.nNodes == 0) return false;
 	if (sqMinR >= r2) return false;
-	Trav stack[NMC_STACK];
 	float b0, b1, tmp;
 	bool found = false; int lastId = -1;
 	boxSqDist(xyz(S.nodes[0]), xyz(S.nodes[1]), x, b0, tmp);
 	if (!(b0 <= r2)) return false;
-	stack[0].node = 0; stack[0].dist = b0;
+	stack.put(0, 0, b0);
 	int sp = 0;
 	while (sp >= 0) {
-		int ni = stack[sp].node; float cd = stack[sp].dist; sp--;
+		int ni = stack.node(sp); float cd = stack.dist(sp); sp--;
 		if (cd > r2) continue;
 		int nRefs = asInt(S.nodes[4*ni].w);
 		if (nRefs > 0) {
@@ -439,10 +450,10 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, V3 x, float r2, bool flip, f
 			if (hit0 && hit1) {
 				int closer = c0, other = c1;
 				if (b1 < b0) { float t = b0; b0 = b1; b1 = t; closer = c1; other = c0; }
-				sp++; stack[sp].node = other; stack[sp].dist = b1;
-				sp++; stack[sp].node = closer; stack[sp].dist = b0;
-			} else if (hit0) { sp++; stack[sp].node = c0; stack[sp].dist = b0; }
-			else if (hit1) { sp++; stack[sp].node = c1; stack[sp].dist = b1; }
+				sp++; stack.put(sp, other, b1);
+				sp++; stack.put(sp, closer, b0);
+			} else if (hit0) { sp++; stack.put(sp, c0, b0); }
+			else if (hit1) { sp++; stack.put(sp, c1, b1); }
 		}
 	}
 	return found;
@@ -459,21 +470,25 @@ NMC_HD float distDirichlet(const SceneView& S, V3 x) {
 	return sqrtf(cx*cx + (cy*cy + cz*cz));
 }
 // computeDistToNeumann (:316-330) + Interaction::signedDistance (core/interaction.h:32-34)
-template <int DIM>
-NMC_HD float distNeumann(const SceneView& S, V3 x, bool sgn) {
+template <int DIM, class Stack>
+NMC_HD float distNeumann(const SceneView& S, Stack& stack, V3 x, bool sgn) {
 	if (S.nPrims == 0) return kMaxF;
 	Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
-	closestPoint<DIM>(S, x, kMaxF, sgn, h);
+	closestPoint<DIM>(S, stack, x, kMaxF, sgn, h);
 	if (!sgn) return h.d;
 	return (dot(x - h.p, h.n) > 0.0f ? 1.0f : -1.0f)*h.d;
 }
 template <int DIM>
-NMC_HD bool insideDomain(const SceneView& S, V3 x) { // :642-648
+NMC_HD float distNeumann(const SceneView& S, V3 x, bool sgn) { LocalStack st; return distNeumann<DIM>(S, st, x, sgn); }
+template <int DIM, class Stack>
+NMC_HD bool insideDomain(const SceneView& S, Stack& stack, V3 x) { // :642-648
 	if (!S.watertight) return true;
 	float d1 = distDirichlet<DIM>(S, x);
-	float d2 = distNeumann<DIM>(S, x, true);
+	float d2 = distNeumann<DIM>(S, stack, x, true);
 	return fabsf(d1) < fabsf(d2) ? d1 < 0.0f : d2 < 0.0f;
 }
+template <int DIM>
+NMC_HD bool insideDomain(const SceneView& S, V3 x) { LocalStack st; return insideDomain<DIM>(S, st, x); }
 template <int DIM>
 NMC_HD bool outsideBox(const SceneView& S, V3 x) { // :649-651
 	bool in = x.x >= S.bboxLo[0] && x.x <= S.bboxHi[0] && x.y >= S.bboxLo[1] && x.y <= S.bboxHi[1];
@@ -491,23 +506,31 @@ template <int DIM>
 NMC_HD V3 offsetPoint(V3 p, V3 n) {
 	return mk(offsetComp(p.x, n.x), offsetComp(p.y, n.y), DIM == 3 ? offsetComp(p.z, n.z) : 0.0f);
 }
-template <int DIM, class M>
-NMC_HD float starRadius(const SceneView& S, V3 x, float minR, float maxR, float prec, bool flipOrient) { // :621-641
+template <int DIM, class M, class Stack>
+NMC_HD float starRadius(const SceneView& S, Stack& stack, V3 x, float minR, float maxR, float prec, bool flipOrient) { // :621-641
 	if (minR > maxR) return maxR;
 	if (S.nPrims > 0) {
 		bool flip = !flipOrient; // FCPW's convention needs flipped normals (:629)
 		float r2 = maxR < kMaxF ? maxR*maxR : kMaxF;
 		float d;
-		if (closestSilhouette<DIM, M>(S, x, r2, flip, minR*minR, prec, d)) return maxS(d, minR);
+		if (closestSilhouette<DIM, M>(S, stack, x, r2, flip, minR*minR, prec, d)) return maxS(d, minR);
 	}
 	return maxS(maxR, minR);
 }
-template <int DIM>
-NMC_HD bool intersectNeumann(const SceneView& S, V3 org, V3 nrm, V3 dir, float tMax, bool onB, Hit& h) { // :458-484
+template <int DIM, class M>
+NMC_HD float starRadius(const SceneView& S, V3 x, float minR, float maxR, float prec, bool flipOrient) {
+	LocalStack st; return starRadius<DIM, M>(S, st, x, minR, maxR, prec, flipOrient);
+}
+template <int DIM, class Stack>
+NMC_HD bool intersectNeumann(const SceneView& S, Stack& stack, V3 org, V3 nrm, V3 dir, float tMax, bool onB, Hit& h) { // :458-484
 	if (S.nPrims == 0) return false;
 	V3 o = onB ? offsetPoint<DIM>(org, neg(nrm)) : org;
 	if (DIM == 2) { o.z = 0.0f; dir.z = 0.0f; }
-	return rayIntersect<DIM>(S, o, dir, tMax, false, h);
+	return rayIntersect<DIM>(S, stack, o, dir, tMax, false, h);
+}
+template <int DIM>
+NMC_HD bool intersectNeumann(const SceneView& S, V3 org, V3 nrm, V3 dir, float tMax, bool onB, Hit& h) {
+	LocalStack st; return intersectNeumann<DIM>(S, st, org, nrm, dir, tMax, onB, h);
 }
 // pde.source: nearest-texel lookup (demo/scene.h:194-198 + image.h:70-75; zombie3d scene_3d.h:120-126)
 template <int DIM>

@@ -14,8 +14,8 @@
 //     converged there and only diverges in the geometric queries;
 //   * the boundary structure (nodes, primitives, face normals, silhouettes; 16-byte records) is staged
 //     in shared memory once per CTA when it fits, and read with vectorised loads;
-//   * per-point estimates are reduced in registers/shared memory: control variates come from per-warp
-//     shared-memory running sums, the final means from a shuffle tree; one lane writes p and grad p.
+//   * per-point estimates are reduced in registers/shared memory: control variates come from warp-wide
+//     running sums (shuffle-reduced at the refill point), the final means from a shuffle tree; one lane writes p and grad p.
 //   * RNG is counter-based: every (seed, global point index, pair, stream) tuple hashes to its own
 //     pcg32 state, so results do not depend on which warp/GPU processes a point.
 // Statistical (not bitwise) equivalence to the reference: same estimator, same stratification of the
@@ -64,14 +64,24 @@ __device__ __forceinline__ unsigned warpSumU(unsigned v) {
 
 enum LaneState { kNeedPair = 0, kFirstBall = 1, kWalking = 2, kIdle = 3 };
 
-template <int DIM>
-__global__ void __launch_bounds__(kBlock)
+#ifndef NMC_MINB
+#define NMC_MINB 4
+#endif
+__device__ __forceinline__ void stackInit(StridedStack& s, int* base, int slots) {
+	s.nodes = base + threadIdx.x; s.dists = reinterpret_cast<float*>(base + slots*kBlock) + threadIdx.x; s.stride = kBlock;
+}
+__device__ __forceinline__ void stackInit(LocalStack&, int*, int) {}
+
+template <int DIM, class STACK>
+__global__ void __launch_bounds__(kBlock, NMC_MINB)
 fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
 		   float* __restrict__ pOut, float* __restrict__ gOut, unsigned int* __restrict__ workCounter,
-		   Counters* __restrict__ counters, float* __restrict__ stats12, int stageQuads) {
+		   Counters* __restrict__ counters, float* __restrict__ stats12, int stageQuads, int stackSlots) {
 	typedef FastMath M;
 	extern __shared__ float4 stage[];
-	__shared__ float cvSum[kWarps][4]; // per warp: sum of totals, completed count, sum of first-source terms
+	// per-thread traversal stack in shared memory, interleaved across the CTA (after the staged scene)
+	STACK stack;
+	stackInit(stack, reinterpret_cast<int*>(stage + stageQuads), stackSlots);
 
 	// ---- stage the boundary structure in shared memory ------------------------------------------------
 	SceneView S = Sg;
@@ -89,7 +99,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		__syncthreads();
 	}
 
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
 	unsigned cStarted = 0, cCompleted = 0, cSteps = 0, cActive = 0;
 
@@ -108,8 +118,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		// ---- per-point set-up (uniform across the warp): createSolutionGrid + estimationQuantity --------
 		const V3 x0 = mk(pts[(size_t)pi*DIM], pts[(size_t)pi*DIM + 1], DIM == 3 ? pts[(size_t)pi*DIM + 2] : 0.0f);
 		const float dDist = distDirichlet<DIM>(S, x0);
-		const float nDist = distNeumann<DIM>(S, x0, false);
-		const bool inside = S.watertight ? insideDomain<DIM>(Sg, x0) : true; // pseudo-normals live in global memory
+		const float nDist = distNeumann<DIM>(S, stack, x0, false);
+		const bool inside = S.watertight ? insideDomain<DIM>(S, stack, x0) : true; // pseudo-normals (nrmV) stay in global memory
 		// points inside the boundary mask are zeroed on output (demo/grid.h:174,227); do not walk them
 		const bool masked = fabsf(nDist) < o.boundaryDistanceMask;
 		const bool active = (inside || S.doubleSided) && !masked && nDist > 0.0f;
@@ -124,8 +134,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 			const float firstR = kShrink*fminf(dDist, nDist);
 			BallFast<DIM> fb; fb.init(yukawa0, S.absorption); fb.update(firstR);
 			const float normG0 = fb.normG(), exitT = fb.exitThroughput(), bfr = fb.bdyGradFactor()/firstR;
-			if (lane < 4) cvSum[warp][lane] = 0.0f;
-			__syncwarp();
+			float cvTot = 0.0f, cvCnt = 0.0f, cvFirst = 0.0f;   // warp-uniform running sums over finished walks
+			float pendTot = 0.0f, pendCnt = 0.0f, pendFirst = 0.0f; // this lane's finished walks not yet folded in
 
 			int state = kNeedPair;
 			int nextPair = 0;          // warp-uniform
@@ -141,13 +151,17 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 				// ---- refill finished lanes with the next pairs (ballot + popc compaction) -------------------
 				unsigned need = __ballot_sync(kFull, state == kNeedPair);
 				if (need) {
+					if (o.useGradientControlVariates) { // fold the finished walks into the running means (converged code)
+						cvTot += warpSum(pendTot); cvCnt += warpSum(pendCnt); cvFirst += warpSum(pendFirst);
+						pendTot = pendCnt = pendFirst = 0.0f;
+					}
 					if (state == kNeedPair) {
 						int mine = nextPair + __popc(need & ltMask);
 						if (mine < nPairs) {
 							pair = mine; anti = 0; state = kFirstBall;
 							if (o.useGradientControlVariates) { // running means over the walks finished so far
-								float cnt = fmaxf(cvSum[warp][1], 1.0f);
-								bcv = cvSum[warp][0]/cnt; scv = cvSum[warp][2]/cnt;
+								float icnt = 1.0f/fmaxf(cvCnt, 1.0f);
+								bcv = cvTot*icnt; scv = cvFirst*icnt;
 							}
 							walkSeed = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(pair + 1)));
 						} else state = kIdle;
@@ -186,7 +200,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						float starR;
 						if (o.stepsBeforeUsingMaximalSpheres <= walkLength) starR = dirichletDist;
 						else {
-							starR = starRadius<DIM, M>(S, pt, o.minStarRadius, dirichletDist, o.silhouettePrecision, flipOrient);
+							starR = starRadius<DIM, M>(S, stack, pt, o.minStarRadius, dirichletDist, o.silhouettePrecision, flipOrient);
 							if (o.minStarRadius <= dirichletDist) starR = fmaxf(kShrink*starR, o.minStarRadius);
 						}
 						bl.update(starR);
@@ -195,7 +209,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						dir = sphereDir<DIM, M>(u0, u1);
 						if (onNeumann && dot(normal, dir) > 0.0f) dir = dir*-1.0f;
 						Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
-						hit = intersectNeumann<DIM>(S, pt, normal, dir, starR, onNeumann, h);
+						hit = intersectNeumann<DIM>(S, stack, pt, normal, dir, starR, onNeumann, h);
 						if (hit) { ipt = h.p; inrm = h.n; idist = h.d; }
 						else {
 							V3 cp = onNeumann ? offsetPoint<DIM>(pt, neg(normal)) : pt;
@@ -238,6 +252,11 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							// directionSampledPoissonKernel at the new position: T(starR) is already known when the
 							// walk lands on the sphere, otherwise evaluate T at the hit distance
 							throughput *= hit ? bl.stepThroughput(idist) : bl.exitThroughput();
+							// Reference quirk kept on purpose: its float Bessel/exp members overflow once r*sqrt(lambda)
+							// exceeds 91.906 (2D, bessi1 -> inf) / 103.9 (3D, expf -> 0), the throughput becomes NaN, the
+							// walk can no longer be stopped by Russian roulette and is eventually discarded
+							// (distributions.h:669-677, 801-813).
+							if (bl.yukawa && fmaxf(1e-4f, hit ? idist : bl.R)*bl.mu > (DIM == 2 ? 91.9063f : 103.9f)) terminated = true;
 							pt = ipt; normal = inrm; onNeumann = hit; prevDir = dir;
 							if (!(throughput == throughput)) { terminated = true; } // NaN guard: discard
 							if (throughput < o.russianRouletteThreshold) {
@@ -261,7 +280,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							sG[0] += g0; sG[1] += g1; sG[2] += g2;
 							sG2[0] += g0*g0; sG2[1] += g1*g1; sG2[2] += g2*g2;
 							nDone++; lenSum += (unsigned)walkLength;
-							atomicAdd(&cvSum[warp][0], total); atomicAdd(&cvSum[warp][1], 1.0f); atomicAdd(&cvSum[warp][2], firstSource);
+							pendTot += total; pendCnt += 1.0f; pendFirst += firstSource;
 						}
 						if (anti == 0 && nAnti == 2) {
 							// antithetic twin: mirrored source and boundary samples, same walk stream (:532-536, :564-567, :579)
@@ -320,27 +339,29 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 
 cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d_pts, long long n,
 					   unsigned long long indexOffset, float* d_p, float* d_g, unsigned int* d_workCounter,
-					   Counters* d_counters, float* d_stats12, int smCount, cudaStream_t stream, FastLaunchInfo* info) {
+					   Counters* d_counters, float* d_stats12, int smCount, int maxDepth, cudaStream_t stream, FastLaunchInfo* info) {
 	if (n <= 0) return cudaSuccess;
 	if (n >= (1ll << 32) - 65536) return cudaErrorInvalidValue;
 	const int dim = S.dim;
 	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*S.nSilRefs;
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
-	size_t smem = stageQuads ? bytes : 0;
+	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
+	int stackSlots = maxDepth + 3;
+	bool smemStack = stackSlots <= 24;
+	size_t smem = (stageQuads ? bytes : 0) + (smemStack ? (size_t)stackSlots*kBlock*8 : 0);
+	void (*kern)(SceneView, SolverParams, const float*, long long, unsigned long long, float*, float*, unsigned int*, Counters*, float*, int, int);
+	if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack> : fastKernel<2, LocalStack>;
+	else kern = smemStack ? fastKernel<3, StridedStack> : fastKernel<3, LocalStack>;
 	int perSM = 0;
-	cudaError_t e;
-	if (dim == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fastKernel<2>, kBlock, smem);
-	else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fastKernel<3>, kBlock, smem);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kBlock, smem);
 	if (e != cudaSuccess) return e;
 	if (perSM < 1) perSM = 1;
-	long long warpsNeeded = n; // one point per warp at a time
 	long long grid = (long long)smCount*perSM;
-	long long gridNeeded = (warpsNeeded + kWarps - 1)/kWarps;
+	long long gridNeeded = (n + kWarps - 1)/kWarps; // one point per warp at a time
 	if (grid > gridNeeded) grid = gridNeeded;
 	if (info) { info->grid = (int)grid; info->block = kBlock; info->smemBytes = (int)smem; }
-	if (dim == 2) fastKernel<2><<<(unsigned)grid, kBlock, smem, stream>>>(S, o, d_pts, n, indexOffset, d_p, d_g, d_workCounter, d_counters, d_stats12, stageQuads);
-	else fastKernel<3><<<(unsigned)grid, kBlock, smem, stream>>>(S, o, d_pts, n, indexOffset, d_p, d_g, d_workCounter, d_counters, d_stats12, stageQuads);
+	kern<<<(unsigned)grid, kBlock, smem, stream>>>(S, o, d_pts, n, indexOffset, d_p, d_g, d_workCounter, d_counters, d_stats12, stageQuads, stackSlots);
 	return cudaGetLastError();
 }
 
