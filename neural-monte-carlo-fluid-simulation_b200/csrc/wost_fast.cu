@@ -259,7 +259,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							if (bl.yukawa && fmaxf(1e-4f, hit ? idist : bl.R)*bl.mu > (DIM == 2 ? 91.9063f : 103.9f)) terminated = true;
 							pt = ipt; normal = inrm; onNeumann = hit; prevDir = dir;
 							if (!(throughput == throughput)) { terminated = true; } // NaN guard: discard
-							if (throughput < o.russianRouletteThreshold) {
+							if (!terminated && throughput < o.russianRouletteThreshold) {
 								if (throughput/o.russianRouletteThreshold < uRR) { throughput = 0.0f; terminated = true; completed = true; }
 								else throughput = o.russianRouletteThreshold;
 							}

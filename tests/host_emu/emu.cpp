@@ -77,3 +77,12 @@ void emu_sample_fast(int dim, float lambda, const float* R, const float* u, cons
 	}
 }
 }
+
+// star radius through the product's traversal (LocalStack), for both geometry flavours of the headers
+extern "C" void emu_star_radius(void* h, const float* pts, int n, float minR, const float* maxR, float prec, int flip, float* out) {
+	EmuScene* s = (EmuScene*)h;
+	for (int i = 0; i < n; i++) {
+		if (s->v.dim == 2) out[i] = starRadius<2, FastMath>(s->v, mk(pts[2*i], pts[2*i + 1], 0.0f), minR, maxR[i], prec, flip != 0);
+		else out[i] = starRadius<3, FastMath>(s->v, mk(pts[3*i], pts[3*i + 1], pts[3*i + 2]), minR, maxR[i], prec, flip != 0);
+	}
+}
