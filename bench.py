@@ -141,8 +141,8 @@ def main():
         x, y, z = np.meshgrid(g, g, g, indexing="ij")
         src = (np.sin(6.1*x)*np.sin(4.3*y + 0.3)*np.cos(3*z)).astype(np.float32)
 
-    from oracle import oraclebind
-    v, _ = oraclebind.load_obj(cfg["scene"]["boundary"], dim)
+    import __graft_entry__ as ge
+    v, _ = ge.load_package().zombie.load_obj(cfg["scene"]["boundary"], dim)  # host-side OBJ reader of the product
     lo, hi = v.min(axis=0), v.max(axis=0)
 
     if args.impl == "reference":
@@ -150,7 +150,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import __graft_entry__ as ge
     pkg = ge.load_package()
     capi = pkg.capi
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,50 @@
+/* include/nmcfs_siren.h -- C ABI of the fused SIREN neural-field kernels in libnmcfs.so.
+ *
+ * Replaces the stock-PyTorch evaluation / fit of the velocity network on the hot path
+ * (src/2d/models/networks.py:15-68 MLP + Sine; src/2d/models/base.py:83-96 update_network;
+ * src/2d/models/model_split.py:88-120, 246-284 fit loops; utils/diff_ops.py:45-51 divergence).
+ * All pointers are DEVICE pointers on the current CUDA device; `stream` is a cudaStream_t (may be 0).
+ * Layer l has weight W[l] (row-major [out_l][in_l], the nn.Linear layout, so state_dicts are
+ * interchangeable) and bias b[l]; l = 0 .. n_hidden_layers + 1.
+ */
+#ifndef NMCFS_SIREN_H
+#define NMCFS_SIREN_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+	int in_dim;          /* 2 or 3 (1..3 accepted) */
+	int out_dim;         /* 2 or 3 (1..3 accepted) */
+	int hidden;          /* 64 or 128 */
+	int n_hidden_layers; /* number of H x H layers */
+	float w0;            /* 30 (Sine.forward, networks.py:19-21) */
+} nmc_siren_shape;
+
+const char* nmc_siren_last_error(void);
+
+/* y[n][out] = net(x[n][in]).  z_saved (may be NULL) receives the pre-activations of every sine layer,
+ * (n_hidden_layers + 1) * hidden * n floats laid out [layer][neuron][sample], for nmc_siren_backward. */
+int nmc_siren_forward(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
+					  int64_t n, float* y, float* z_saved, void* stream);
+
+/* Accumulates dL/dW[l], dL/db[l] into gW[l], gb[l] (caller zero-fills) given grad_y = dL/dy [n][out];
+ * grad_x (may be NULL) receives dL/dx [n][in]. */
+int nmc_siren_backward(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
+					   int64_t n, const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
+					   float* grad_x, void* stream);
+
+/* Tensor-core forward (tcgen05, 3xTF32 split => fp32-level accuracy) for inference batches; same contract as
+ * nmc_siren_forward without z_saved. Falls back to an error (never to another path) on unsupported shapes. */
+int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
+						 int64_t n, float* y, void* stream);
+
+/* torch.optim.Adam step (no weight decay, no amsgrad) over one flat parameter buffer; step is 1-based. */
+int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+				  float eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

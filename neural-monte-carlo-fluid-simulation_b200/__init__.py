@@ -7,10 +7,17 @@ Layout:
   zombie.py        Python mirror of the reference's module surface: Scene(config, sourceValue), wost(...)
   zombie2d/, zombie3d/   the compiled drop-in modules named `zombie_bindings` (one per dimension)
   sharding.py      multi-GPU point sharding (one process per GPU, gather of the estimates)
+  siren.py         fused SIREN velocity network (drop-in for the reference's MLP) + fused Adam (csrc/siren*.cu)
 
 The directory name contains '-', so import it with
     importlib.import_module("neural-monte-carlo-fluid-simulation_b200")
 or through __graft_entry__.load_package().
 """
 from . import capi, zombie, sharding  # noqa: F401
+
+
+def load_siren():
+    """Lazy import of the fused SIREN ops (needs torch)."""
+    from . import siren as _s
+    return _s
 from .zombie import Scene, wost  # noqa: F401

@@ -1,0 +1,314 @@
+// csrc/siren.cu -- fused SIREN neural-field kernels (fp32): forward, backward (parameter and input
+// gradients) and Adam, one launch each.
+//
+// Replaces, for the velocity network of the time-stepper, the chain of stock PyTorch kernels behind
+//   MLP / Sine            src/2d/models/networks.py:15-68 (nn.Sequential of Linear -> sin(30 .) ...)
+//   update_network        src/2d/models/base.py:83-96  (backward + Adam.step)
+//   divergence (autograd) src/2d/utils/diff_ops.py:45-51 (needs d(out)/d(coords): grad_x below)
+// The network is  x[in] -> (Linear H, sin(w0 .)) -> L x (Linear HxH, sin(w0 .)) -> Linear out ; w0 = 30.
+// One thread owns one sample; its activation vector lives in registers, the layer's weights are staged
+// in shared memory and read as broadcast float4s, so a layer costs H*H FMAs + H*H/4 LDS.128 per sample.
+// The backward pass recomputes activations from the saved pre-activations z_l (written by the training
+// forward, layout [layer][neuron][sample], coalesced), forms dW_l = dZ_l^T A_{l-1} per 128-sample tile with
+// a register-tiled shared-memory GEMM and accumulates tiles with atomics.
+// This is the exact-fp32 path (parity with torch within summation-order error); the tensor-core path for
+// large inference batches is csrc/siren_tc.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nmcfs_siren.h"
+
+namespace {
+
+constexpr int kTile = 128;     // samples per CTA tile == threads per CTA
+constexpr int kMaxLayers = 18; // first + hidden + last
+
+struct Params {
+	const float* W[kMaxLayers];
+	const float* b[kMaxLayers];
+	float* gW[kMaxLayers];
+	float* gb[kMaxLayers];
+};
+
+template <int H>
+__global__ void __launch_bounds__(kTile)
+sirenForward(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+			 float* __restrict__ y, float* __restrict__ zSaved) {
+	extern __shared__ float smem[];
+	float* Wt = smem;                 // [H][H + 4]  transposed weights of the current hidden layer: Wt[k][n]
+	float* act = smem + H*(H + 4);    // [H][kTile]  activation exchange (column per thread)
+	const int tid = threadIdx.x;
+	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
+		const long long s = tile*kTile + tid;
+		const bool live = s < n;
+		float a[H];
+		{ // first layer: in -> H
+			float xi[3] = {0.0f, 0.0f, 0.0f};
+			if (live) for (int i = 0; i < inDim; i++) xi[i] = x[s*inDim + i];
+#pragma unroll
+			for (int j = 0; j < H; j++) {
+				float z = __ldg(&P.b[0][j]);
+				for (int i = 0; i < inDim; i++) z += __ldg(&P.W[0][j*inDim + i])*xi[i];
+				if (zSaved && live) zSaved[(size_t)j*n + s] = z;
+				a[j] = sinf(w0*z);
+			}
+		}
+		for (int l = 1; l <= nHidden; l++) {
+			__syncthreads();
+			for (int i = tid; i < H*H; i += kTile) { int nn = i/H, k = i - nn*H; Wt[k*(H + 4) + nn] = __ldg(&P.W[l][i]); }
+			__syncthreads();
+#pragma unroll 1
+			for (int n0 = 0; n0 < H; n0 += 16) {
+				float acc[16];
+#pragma unroll
+				for (int j = 0; j < 16; j++) acc[j] = __ldg(&P.b[l][n0 + j]);
+#pragma unroll
+				for (int k = 0; k < H; k++) {
+					const float4* w = reinterpret_cast<const float4*>(&Wt[k*(H + 4) + n0]);
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						float4 v = w[q];
+						acc[4*q + 0] += a[k]*v.x; acc[4*q + 1] += a[k]*v.y; acc[4*q + 2] += a[k]*v.z; acc[4*q + 3] += a[k]*v.w;
+					}
+				}
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					if (zSaved && live) zSaved[((size_t)l*H + n0 + j)*n + s] = acc[j];
+					act[(n0 + j)*kTile + tid] = sinf(w0*acc[j]);
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < H; k++) a[k] = act[k*kTile + tid];
+		}
+		// last layer: H -> out (no activation, outermost_linear=True)
+		const int last = nHidden + 1;
+		for (int j = 0; j < outDim; j++) {
+			float z = __ldg(&P.b[last][j]);
+#pragma unroll
+			for (int k = 0; k < H; k++) z += __ldg(&P.W[last][j*H + k])*a[k];
+			if (live) y[s*outDim + j] = z;
+		}
+	}
+}
+
+__device__ __forceinline__ float warpSum(float v) {
+	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+	return v;
+}
+
+// Backward: gy = dL/dy [n][out]; accumulates into gW/gb (caller zero-fills), optional gx = dL/dx [n][in].
+template <int H>
+__global__ void __launch_bounds__(kTile)
+sirenBackward(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+			  const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ gx) {
+	extern __shared__ float smem[];
+	constexpr int LD = H + 4;
+	float* Ws = smem;                  // [H][LD]      W_l row-major (n, k)
+	float* dzT = Ws + H*LD;            // [kTile][LD]  dZ tile, sample-major
+	float* aT = dzT + kTile*LD;        // [kTile][LD]  A_{l-1} tile, sample-major
+	const int tid = threadIdx.x, lane = tid & 31;
+	// register tile of the dW GEMM: (H/TN) x (H/TK) thread grid = 128 threads
+	constexpr int TN = 4, TK = H*H/(kTile*TN);  // H=64: 4x8, H=128: 4x32
+	const int nT = tid/(H/TK), kT = tid - nT*(H/TK);
+	const int last = nHidden + 1;
+	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
+		const long long s = tile*kTile + tid;
+		const bool live = s < n;
+		float g[H];
+		{ // last layer
+			float gyv[3] = {0.0f, 0.0f, 0.0f};
+			if (live) for (int j = 0; j < outDim; j++) gyv[j] = gy[s*outDim + j];
+#pragma unroll
+			for (int k = 0; k < H; k++) {
+				float aL = live ? sinf(w0*zSaved[((size_t)nHidden*H + k)*n + s]) : 0.0f;
+				float acc = 0.0f;
+				for (int j = 0; j < outDim; j++) {
+					acc += __ldg(&P.W[last][j*H + k])*gyv[j];
+					float r = warpSum(gyv[j]*aL);
+					if (lane == 0) atomicAdd(&P.gW[last][j*H + k], r);
+				}
+				g[k] = acc;
+			}
+			for (int j = 0; j < outDim; j++) { float r = warpSum(gyv[j]); if (lane == 0) atomicAdd(&P.gb[last][j], r); }
+		}
+		for (int l = nHidden; l >= 1; l--) {
+			__syncthreads();
+			for (int i = tid; i < H*H; i += kTile) { int nn = i/H, k = i - nn*H; Ws[nn*LD + k] = __ldg(&P.W[l][i]); }
+			float dz[H];
+#pragma unroll
+			for (int j = 0; j < H; j++) {
+				float zl = live ? zSaved[((size_t)l*H + j)*n + s] : 0.0f;
+				float zp = live ? zSaved[((size_t)(l - 1)*H + j)*n + s] : 0.0f;
+				dz[j] = live ? g[j]*w0*cosf(w0*zl) : 0.0f;
+				dzT[tid*LD + j] = dz[j];
+				aT[tid*LD + j] = live ? sinf(w0*zp) : 0.0f;
+			}
+			__syncthreads();
+			{ // dW_l[nn][k] += sum_s dz[s][nn] * a[s][k]
+				float acc[TN][TK];
+#pragma unroll
+				for (int i = 0; i < TN; i++)
+#pragma unroll
+					for (int j = 0; j < TK; j++) acc[i][j] = 0.0f;
+#pragma unroll 4
+				for (int ss = 0; ss < kTile; ss++) {
+					float4 dv = *reinterpret_cast<const float4*>(&dzT[ss*LD + nT*TN]);
+					float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+					for (int j = 0; j < TK; j += 4) {
+						float4 av = *reinterpret_cast<const float4*>(&aT[ss*LD + kT*TK + j]);
+#pragma unroll
+						for (int i = 0; i < TN; i++) {
+							acc[i][j] += d4[i]*av.x; acc[i][j + 1] += d4[i]*av.y; acc[i][j + 2] += d4[i]*av.z; acc[i][j + 3] += d4[i]*av.w;
+						}
+					}
+				}
+#pragma unroll
+				for (int i = 0; i < TN; i++)
+#pragma unroll
+					for (int j = 0; j < TK; j++) atomicAdd(&P.gW[l][(nT*TN + i)*H + kT*TK + j], acc[i][j]);
+				if (tid < H) { float r = 0.0f; for (int ss = 0; ss < kTile; ss++) r += dzT[ss*LD + tid]; atomicAdd(&P.gb[l][tid], r); }
+			}
+			// reload this sample's dz (not kept live across the GEMM), then let everybody finish reading the tiles
+			// before the rows are reused as the exchange buffer for g_{l-1}
+#pragma unroll
+			for (int j = 0; j < H; j++) dz[j] = dzT[tid*LD + j];
+			__syncthreads();
+			// g_{l-1}[k] = sum_nn W_l[nn][k] dz[nn]
+#pragma unroll 1
+			for (int k0 = 0; k0 < H; k0 += 16) {
+				float acc[16];
+#pragma unroll
+				for (int j = 0; j < 16; j++) acc[j] = 0.0f;
+#pragma unroll
+				for (int nn = 0; nn < H; nn++) {
+					const float4* w = reinterpret_cast<const float4*>(&Ws[nn*LD + k0]);
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						float4 v = w[q];
+						acc[4*q + 0] += dz[nn]*v.x; acc[4*q + 1] += dz[nn]*v.y; acc[4*q + 2] += dz[nn]*v.z; acc[4*q + 3] += dz[nn]*v.w;
+					}
+				}
+#pragma unroll
+				for (int j = 0; j < 16; j++) dzT[tid*LD + k0 + j] = acc[j]; // own row: reuse as exchange buffer
+			}
+#pragma unroll
+			for (int k = 0; k < H; k++) g[k] = dzT[tid*LD + k];
+		}
+		{ // first layer
+			float xi[3] = {0.0f, 0.0f, 0.0f}, gxi[3] = {0.0f, 0.0f, 0.0f};
+			if (live) for (int i = 0; i < inDim; i++) xi[i] = x[s*inDim + i];
+#pragma unroll
+			for (int j = 0; j < H; j++) {
+				float dz = live ? g[j]*w0*cosf(w0*zSaved[(size_t)j*n + s]) : 0.0f;
+				for (int i = 0; i < inDim; i++) {
+					gxi[i] += __ldg(&P.W[0][j*inDim + i])*dz;
+					float r = warpSum(dz*xi[i]);
+					if (lane == 0) atomicAdd(&P.gW[0][j*inDim + i], r);
+				}
+				float r = warpSum(dz);
+				if (lane == 0) atomicAdd(&P.gb[0][j], r);
+			}
+			if (gx && live) for (int i = 0; i < inDim; i++) gx[s*inDim + i] = gxi[i];
+		}
+	}
+}
+
+// torch.optim.Adam (no amsgrad, no weight decay) over one flat buffer; step is 1-based
+__global__ void adamKernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+						   long long n, float lr, float b1, float b2, float eps, float bc1, float bc2sqrt) {
+	long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float gi = g[i];
+	float mi = b1*m[i] + (1.0f - b1)*gi;
+	float vi = b2*v[i] + (1.0f - b2)*gi*gi;
+	m[i] = mi; v[i] = vi;
+	float denom = sqrtf(vi)/bc2sqrt + eps;
+	p[i] -= (lr/bc1)*(mi/denom);
+}
+
+thread_local const char* g_err = "";
+int fail(const char* m) { g_err = m; return 1; }
+
+int fill(Params& P, const nmc_siren_shape* sh, const float* const* W, const float* const* b, float* const* gW, float* const* gb) {
+	if (!sh || !W || !b) return fail("null argument");
+	if (sh->hidden != 64 && sh->hidden != 128) return fail("hidden_features must be 64 or 128");
+	if (sh->in_dim < 1 || sh->in_dim > 3 || sh->out_dim < 1 || sh->out_dim > 3) return fail("in/out features must be 1..3");
+	if (sh->n_hidden_layers < 0 || sh->n_hidden_layers + 2 > kMaxLayers) return fail("too many layers");
+	for (int l = 0; l < sh->n_hidden_layers + 2; l++) {
+		P.W[l] = W[l]; P.b[l] = b[l];
+		P.gW[l] = gW ? gW[l] : nullptr; P.gb[l] = gb ? gb[l] : nullptr;
+		if (!W[l] || !b[l] || (gW && (!gW[l] || !gb[l]))) return fail("null layer pointer");
+	}
+	return 0;
+}
+
+int smCount() {
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	return sms;
+}
+
+} // namespace
+
+namespace nmc_siren_detail { void setError(const char* m) { g_err = m; } }
+
+extern "C" const char* nmc_siren_last_error(void) { return g_err; }
+
+extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
+								 int64_t n, float* y, float* z_saved, void* stream) {
+	Params P;
+	if (fill(P, sh, W, b, nullptr, nullptr)) return 1;
+	if (n <= 0) return 0;
+	if (!x || !y) return fail("null buffer");
+	const int H = sh->hidden;
+	size_t smem = ((size_t)H*(H + 4) + (size_t)H*kTile)*sizeof(float);
+	long long tiles = (n + kTile - 1)/kTile;
+	int grid = (int)(tiles < 4ll*smCount() ? tiles : 4ll*smCount());
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaError_t e;
+	if (H == 64) {
+		e = cudaFuncSetAttribute(sirenForward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenForward<64><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+	} else {
+		e = cudaFuncSetAttribute(sirenForward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenForward<128><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+	}
+	if (!e) e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
+								  int64_t n, const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
+								  float* grad_x, void* stream) {
+	Params P;
+	if (fill(P, sh, W, b, gW, gb)) return 1;
+	if (!gW || !gb) return fail("null gradient pointers");
+	if (n <= 0) return 0;
+	if (!x || !z_saved || !grad_y) return fail("null buffer");
+	const int H = sh->hidden;
+	size_t smem = ((size_t)H*(H + 4) + 2*(size_t)kTile*(H + 4))*sizeof(float);
+	long long tiles = (n + kTile - 1)/kTile;
+	int grid = (int)(tiles < 2ll*smCount() ? tiles : 2ll*smCount());
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaError_t e;
+	if (H == 64) {
+		e = cudaFuncSetAttribute(sirenBackward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenBackward<64><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
+	} else {
+		e = cudaFuncSetAttribute(sirenBackward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenBackward<128><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
+	}
+	if (!e) e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+							 float eps, int64_t step, void* stream) {
+	if (n <= 0) return 0;
+	if (!p || !g || !m || !v || step < 1) return fail("bad arguments");
+	float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+	adamKernel<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+	cudaError_t e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}

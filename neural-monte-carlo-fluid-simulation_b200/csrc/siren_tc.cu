@@ -1,0 +1,224 @@
+// csrc/siren_tc.cu -- tensor-core (tcgen05 / TMEM) forward pass of the SIREN velocity network for sm_100a.
+//
+// The hidden layers  A_l = sin(w0 (A_{l-1} W_l^T + b_l))  are the only dense contractions on the hot path
+// (src/2d/models/networks.py:47-57).  One CTA of 128 threads owns a tile of 128
+// samples: thread t <-> sample row t <-> TMEM lane t.
+//   * operands live in shared memory in the K-major, un-swizzled UMMA canonical layout (8 x 16-byte core
+//     matrices); activations A [128 x H] and one 64-row chunk of W_l [64 x H] at a time;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 64, K = 8) into a TMEM
+//     accumulator of H fp32 columns and commits to an mbarrier; everybody else waits on the barrier;
+//   * fp32 accuracy is recovered with the 3xTF32 split  A = A_hi + A_lo, W = W_hi + W_lo,
+//     D = A_hi W_hi + A_hi W_lo + A_lo W_hi  (SIREN's sin(30 .) amplifies TF32 rounding by 30, and the fit
+//     runs at lr = 1e-5: plain TF32 is not accurate enough);
+//   * the epilogue reads each thread's row with tcgen05.ld (32x32b), adds the bias, applies sin(w0 .),
+//     splits the result and writes it back as the next layer's A operand -- activations never leave the SM.
+// The first (in -> H, K = 2|3) and last (H -> out, N = 2|3) layers are not GEMM-shaped and run on the FMA pipe
+// inside the same kernel.  No TMA: a layer's weights are 16-64 KB, L2-resident and re-split on load.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nmcfs_siren.h"
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kMaxLayers = 18;
+constexpr int kNChunk = 64;   // output neurons per MMA group (UMMA N)
+
+struct Params {
+	const float* W[kMaxLayers];
+	const float* b[kMaxLayers];
+};
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: element (r, k) of an operand with K columns (fp32/tf32, 4 per 16 bytes)
+template <int K>
+__device__ __forceinline__ int coreOffsetBytes(int r, int k) {
+	return (r >> 3)*(K*32) + (k >> 2)*128 + (r & 7)*16 + (k & 3)*4;
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, mma_sm100_desc.hpp:98-123)
+__device__ __forceinline__ uint64_t smemDesc(uint32_t addr, uint32_t lboBytes, uint32_t sboBytes) {
+	return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lboBytes >> 4) << 16) | ((uint64_t)(sboBytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mmaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+				 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+				 :: "r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+					 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void splitTf32(float v, float& hi, float& lo) {
+	hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); // the 10 mantissa bits the tensor core keeps
+	lo = v - hi;
+}
+
+template <int H>
+__global__ void __launch_bounds__(kTile)
+sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned char* Ahi = smem;
+	unsigned char* Alo = Ahi + kTile*H*4;
+	unsigned char* Bhi = Alo + kTile*H*4;
+	unsigned char* Blo = Bhi + kNChunk*H*4;
+	__shared__ __align__(8) unsigned long long mbar;
+	__shared__ uint32_t tmemBaseSh;
+	const int tid = threadIdx.x, warp = tid >> 5;
+
+	if (warp == 0) { // TMEM: H fp32 columns x 128 lanes
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemAddr(&tmemBaseSh)), "r"((uint32_t)H) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smemAddr(&mbar)) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmemBase = tmemBaseSh;
+	const uint32_t barAddr = smemAddr(&mbar);
+	// instruction descriptor (cute::UMMA::InstrDescriptor, mma_sm100_desc.hpp:412-439):
+	// D = F32, A = B = TF32, both K-major, N = 64, M = 128
+	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNChunk >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+	uint32_t phase = 0;
+	const int last = nHidden + 1;
+
+	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
+		const long long s = tile*kTile + tid;
+		const bool live = s < n;
+		{ // first layer on the FMA pipe, written straight into the A operand
+			float xi[3] = {0.0f, 0.0f, 0.0f};
+			if (live) for (int i = 0; i < inDim; i++) xi[i] = x[s*inDim + i];
+			for (int c = 0; c < H; c += 4) {
+				float hi[4], lo[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					float z = __ldg(&P.b[0][c + q]);
+					for (int i = 0; i < inDim; i++) z += __ldg(&P.W[0][(c + q)*inDim + i])*xi[i];
+					splitTf32(live ? sinf(w0*z) : 0.0f, hi[q], lo[q]);
+				}
+				int off = coreOffsetBytes<H>(tid, c);
+				*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+				*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+			}
+		}
+		float yacc[3] = {0.0f, 0.0f, 0.0f};
+		for (int l = 1; l <= nHidden; l++) {
+			for (int nc = 0; nc < H/kNChunk; nc++) {
+				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
+				for (int idx = tid; idx < kNChunk*H/4; idx += kTile) {
+					int r = idx/(H/4), k4 = idx - r*(H/4);
+					float4 w = __ldg(reinterpret_cast<const float4*>(&P.W[l][(size_t)(nc*kNChunk + r)*H + 4*k4]));
+					float4 h, o;
+					splitTf32(w.x, h.x, o.x); splitTf32(w.y, h.y, o.y); splitTf32(w.z, h.z, o.z); splitTf32(w.w, h.w, o.w);
+					int off = coreOffsetBytes<H>(r, 4*k4);
+					*reinterpret_cast<float4*>(Bhi + off) = h;
+					*reinterpret_cast<float4*>(Blo + off) = o;
+				}
+				// generic-proxy writes (A from the previous epilogue, B from above) -> visible to the tensor core
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncthreads();
+				if (tid == 0) {
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t d = tmemBase + (uint32_t)(nc*kNChunk);
+					const uint32_t aH = smemAddr(Ahi), aL = smemAddr(Alo), bH = smemAddr(Bhi), bL = smemAddr(Blo);
+					const uint32_t sbo = H*32;
+#pragma unroll 1
+					for (int ks = 0; ks < H/8; ks++) { // UMMA K = 8 tf32 = two 16-byte core-matrix columns = 256 bytes
+						uint64_t dAh = smemDesc(aH + ks*256, 128, sbo), dAl = smemDesc(aL + ks*256, 128, sbo);
+						uint64_t dBh = smemDesc(bH + ks*256, 128, sbo), dBl = smemDesc(bL + ks*256, 128, sbo);
+						mmaTf32(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
+						mmaTf32(d, dAh, dBl, idesc, 1u);
+						mmaTf32(d, dAl, dBh, idesc, 1u);
+					}
+					// arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
+					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barAddr) : "memory");
+				}
+				mbarWait(barAddr, phase);
+				phase ^= 1u;
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			}
+			// epilogue: this thread's row of the accumulator -> bias, sin, next layer's operand
+			for (int c0 = 0; c0 < H; c0 += 16) {
+				uint32_t v[16];
+				uint32_t taddr = tmemBase + ((uint32_t)(warp*32) << 16) + (uint32_t)c0;
+				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+							 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+							   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+							 : "r"(taddr) : "memory");
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+				for (int q4 = 0; q4 < 16; q4 += 4) {
+					float hi[4], lo[4];
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						int c = c0 + q4 + q;
+						float a = sinf(w0*(__uint_as_float(v[q4 + q]) + __ldg(&P.b[l][c])));
+						if (!live) a = 0.0f;
+						if (l == nHidden) { for (int j = 0; j < outDim; j++) yacc[j] += __ldg(&P.W[last][j*H + c])*a; }
+						splitTf32(a, hi[q], lo[q]);
+					}
+					if (l < nHidden) {
+						int off = coreOffsetBytes<H>(tid, c0 + q4);
+						*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+						*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+					}
+				}
+			}
+		}
+		if (live) for (int j = 0; j < outDim; j++) y[s*outDim + j] = yacc[j] + __ldg(&P.b[last][j]);
+		// the next tile's first layer overwrites A: every thread is past its last use (MMAs completed via the mbarrier)
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		__syncthreads();
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"((uint32_t)H) : "memory");
+}
+
+} // namespace
+
+extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
+									int64_t n, float* y, void* stream);
+
+namespace nmc_siren_detail { void setError(const char* m); }
+
+extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
+									int64_t n, float* y, void* stream) {
+	if (!sh || !W || !b) { nmc_siren_detail::setError("null argument"); return 1; }
+	if ((sh->hidden != 64 && sh->hidden != 128) || sh->n_hidden_layers < 1 || sh->n_hidden_layers + 2 > kMaxLayers ||
+		sh->in_dim < 1 || sh->in_dim > 3 || sh->out_dim < 1 || sh->out_dim > 3) {
+		nmc_siren_detail::setError("tensor-core forward: unsupported shape (hidden 64|128, >= 1 hidden layer, in/out 1..3)");
+		return 1;
+	}
+	if (n <= 0) return 0;
+	if (!x || !y) { nmc_siren_detail::setError("null buffer"); return 1; }
+	Params P;
+	for (int l = 0; l < sh->n_hidden_layers + 2; l++) { P.W[l] = W[l]; P.b[l] = b[l]; }
+	const int H = sh->hidden;
+	size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	long long tiles = (n + kTile - 1)/kTile;
+	int perSM = H == 64 ? 2 : 1;
+	int grid = (int)(tiles < (long long)perSM*sms ? tiles : (long long)perSM*sms);
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaError_t e;
+	if (H == 64) {
+		e = cudaFuncSetAttribute(sirenForwardTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenForwardTc<64><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+	} else {
+		e = cudaFuncSetAttribute(sirenForwardTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenForwardTc<128><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+	}
+	if (!e) e = cudaGetLastError();
+	if (e) { nmc_siren_detail::setError(cudaGetErrorString(e)); return 1; }
+	return 0;
+}

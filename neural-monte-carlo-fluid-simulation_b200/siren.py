@@ -1,0 +1,196 @@
+"""Fused SIREN velocity network: drop-in for the reference's `MLP` (src/2d/models/networks.py:24-68).
+
+`FusedSiren` keeps the reference module's parameter names and layout (`net.0.weight`, `net.0.bias`,
+`net.2.weight`, ... -- an nn.Sequential of nn.Linear and Sine), so `state_dict()` / checkpoints
+(src/2d/models/base.py:102-127) are interchangeable, and the same initialisation (sine_init,
+first_layer_sine_init).  `forward` runs ONE CUDA kernel (csrc/siren.cu) instead of 2(L+2) stock kernels;
+`backward` runs one kernel that produces every parameter gradient and, when the coordinates require grad
+(the divergence of src/2d/utils/diff_ops.py:45-51), the input gradient.  Inference batches can use the
+tensor-core kernel (csrc/siren_tc.cu) with `tensor_cores=True`.  CUDA tensors only: there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import capi
+
+
+class Shape(C.Structure):
+    _fields_ = [("in_dim", C.c_int), ("out_dim", C.c_int), ("hidden", C.c_int), ("n_hidden_layers", C.c_int), ("w0", C.c_float)]
+
+
+_configured = False
+
+
+def _lib():
+    global _configured
+    L = capi.lib()
+    if not _configured:
+        vp = C.c_void_p
+        L.nmc_siren_last_error.restype = C.c_char_p
+        L.nmc_siren_forward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, vp]
+        L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp]
+        L.nmc_siren_backward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp,
+                                         C.POINTER(vp), C.POINTER(vp), vp, vp]
+        L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
+        _configured = True
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("libnmcfs siren: " + _lib().nmc_siren_last_error().decode())
+
+
+def _ptrs(tensors):
+    return (C.c_void_p*len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _shape_of(weights, w0):
+    return Shape(weights[0].shape[1], weights[-1].shape[0], weights[0].shape[0], len(weights) - 2, float(w0))
+
+
+class _SirenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w0, tensor_cores, *params):
+        n_layers = len(params)//2
+        W = [p.contiguous() for p in params[:n_layers]]
+        b = [p.contiguous() for p in params[n_layers:]]
+        if not x.is_cuda:
+            raise RuntimeError("FusedSiren needs CUDA tensors (there is no CPU path)")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1]).contiguous().float()
+        n = x2.shape[0]
+        sh = _shape_of(W, w0)
+        y = torch.empty((n, sh.out_dim), device=x.device, dtype=torch.float32)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        L = _lib()
+        with torch.cuda.device(x.device):
+            if need_grad:
+                z = torch.empty(((sh.n_hidden_layers + 1)*sh.hidden, n), device=x.device, dtype=torch.float32)
+                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), _stream()))
+                ctx.save_for_backward(x2, z, *W, *b)
+            elif tensor_cores:
+                _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), _stream()))
+            else:
+                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, _stream()))
+        ctx.w0, ctx.n_layers, ctx.lead, ctx.x_needs = w0, n_layers, lead, x.requires_grad
+        return y.reshape(*lead, sh.out_dim)
+
+    @staticmethod
+    def backward(ctx, gy):
+        saved = ctx.saved_tensors
+        x2, z = saved[0], saved[1]
+        W = list(saved[2:2 + ctx.n_layers]); b = list(saved[2 + ctx.n_layers:])
+        sh = _shape_of(W, ctx.w0)
+        n = x2.shape[0]
+        gy2 = gy.reshape(n, sh.out_dim).contiguous().float()
+        gW = [torch.zeros_like(w) for w in W]
+        gb = [torch.zeros_like(v) for v in b]
+        gx = torch.empty_like(x2) if ctx.x_needs else None
+        with torch.cuda.device(x2.device):
+            _check(_lib().nmc_siren_backward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, z.data_ptr(), gy2.data_ptr(),
+                                             _ptrs(gW), _ptrs(gb), gx.data_ptr() if gx is not None else None, _stream()))
+        return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, *gW, *gb)
+
+
+class Sine(nn.Module):
+    """Placeholder with the reference's name so that `net` has the same module indices (networks.py:15-21)."""
+
+    def forward(self, input):
+        return torch.sin(30*input)
+
+
+def sine_init(m):  # networks.py:78-83
+    with torch.no_grad():
+        if hasattr(m, "weight"):
+            num_input = m.weight.size(-1)
+            m.weight.uniform_(-np.sqrt(6/num_input)/30, np.sqrt(6/num_input)/30)
+
+
+def first_layer_sine_init(m):  # networks.py:85-90
+    with torch.no_grad():
+        if hasattr(m, "weight"):
+            num_input = m.weight.size(-1)
+            m.weight.uniform_(-1/num_input, 1/num_input)
+
+
+class FusedSiren(nn.Module):
+    """MLP(in_features, out_features, num_hidden_layers, hidden_features, nonlinearity='sine') with fused kernels."""
+
+    def __init__(self, in_features, out_features, num_hidden_layers, hidden_features, outermost_linear=True,
+                 nonlinearity="sine", weight_init=None, tensor_cores=False):
+        super().__init__()
+        if nonlinearity != "sine" or not outermost_linear:
+            raise NotImplementedError("the time-stepper only uses nonlinearity='sine' with a linear last layer (run.sh)")
+        if hidden_features not in (64, 128):
+            raise NotImplementedError("hidden_features must be 64 or 128 (the shipped configs)")
+        self.weight_init = weight_init if weight_init is not None else sine_init
+        self.first_layer_init = None if weight_init is not None else first_layer_sine_init
+        layers = [nn.Linear(in_features, hidden_features), Sine()]
+        for _ in range(num_hidden_layers):
+            layers.extend([nn.Linear(hidden_features, hidden_features), Sine()])
+        layers.append(nn.Linear(hidden_features, out_features))
+        self.net = nn.Sequential(*layers)
+        self.net.apply(self.weight_init)
+        if self.first_layer_init is not None:
+            self.net[0].apply(self.first_layer_init)
+        self.tensor_cores = tensor_cores
+
+    def _linears(self):
+        return [m for m in self.net if isinstance(m, nn.Linear)]
+
+    def forward(self, coords, weights=None):
+        lin = self._linears()
+        out = _SirenFn.apply(coords, 30.0, self.tensor_cores, *[m.weight for m in lin], *[m.bias for m in lin])
+        if weights is not None:
+            out = out*weights
+        return out
+
+    def forward_reference(self, coords):
+        """The reference's own evaluation (stock PyTorch ops) -- used by the parity tests."""
+        return self.net(coords)
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (lr, betas=(0.9, 0.999), eps=1e-8) with one kernel per step over a flat copy
+    of the parameters' gradients (base.py:61-77 creates torch.optim.Adam with default betas/eps)."""
+
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.step_count = lr, betas, eps, 0
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, device=dev); self.m = torch.zeros(n, device=dev); self.v = torch.zeros(n, device=dev)
+        self.g = torch.zeros(n, device=dev)
+        with torch.no_grad():  # re-home the parameters as views into one flat buffer
+            off = 0
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k] = p.reshape(-1)
+                p.data = self.flat[off:off + k].view_as(p)
+                off += k
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def step(self):
+        self.step_count += 1
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is not None:
+                self.g[off:off + k] = p.grad.reshape(-1)
+            else:
+                self.g[off:off + k].zero_()
+            off += k
+        with torch.cuda.device(self.flat.device):
+            _check(_lib().nmc_adam_step(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                        self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, _stream()))

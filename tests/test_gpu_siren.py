@@ -1,0 +1,125 @@
+"""Fused SIREN kernels (csrc/siren.cu, csrc/siren_tc.cu) against a plain PyTorch fp32 evaluation of the same
+network (the reference's MLP: nn.Sequential of Linear / sin(30 .), src/2d/models/networks.py:24-68)."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+# (in, hidden, hidden layers, out): the four network shapes of the shipped configs
+SHAPES = [(2, 64, 6, 2), (2, 128, 2, 2), (3, 64, 5, 3), (3, 128, 2, 3)]
+
+
+@pytest.fixture(scope="module")
+def siren():
+    pkg = util.package()
+    assert pkg.capi.device_count() > 0
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return pkg.load_siren()
+
+
+def _net(siren, shape, seed=0, tensor_cores=False):
+    torch.manual_seed(seed)
+    i, h, l, o = shape
+    return siren.FusedSiren(i, o, l, h, nonlinearity="sine", tensor_cores=tensor_cores).cuda()
+
+
+def _coords(n, dim, seed=1):
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    return torch.rand((n, dim), generator=g, device="cuda")*2 - 1
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("n", [4096, 1000, 1])
+def test_forward_matches_torch(siren, shape, n):
+    net = _net(siren, shape)
+    x = _coords(n, shape[0])
+    with torch.no_grad():
+        y = net(x)
+        ref = net.forward_reference(x)
+    assert y.shape == ref.shape
+    # fp32 with a different summation order; sin(30 .) amplifies rounding layer by layer
+    assert (y - ref).abs().max().item() <= 2e-5*max(ref.abs().max().item(), 1e-3) + 2e-6
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_backward_matches_torch_autograd(siren, shape):
+    net = _net(siren, shape, seed=3)
+    n = 2048 + 37
+    x = _coords(n, shape[0], seed=5).requires_grad_(True)
+    target = torch.sin(3*x[:, :1]).expand(-1, shape[3])
+    loss = ((net(x) - target)**2).mean()
+    grads = torch.autograd.grad(loss, [x] + list(net.parameters()))
+    xr = x.detach().clone().requires_grad_(True)
+    loss_r = ((net.forward_reference(xr) - target)**2).mean()
+    grads_r = torch.autograd.grad(loss_r, [xr] + list(net.parameters()))
+    assert abs(loss.item() - loss_r.item()) <= 1e-5*abs(loss_r.item()) + 1e-9
+    for g, r in zip(grads, grads_r):
+        assert g.shape == r.shape
+        assert (g - r).abs().max().item() <= 2e-4*r.abs().max().item() + 1e-9, (tuple(g.shape), (g - r).abs().max().item(), r.abs().max().item())
+
+
+def test_divergence_through_fused_network(siren):
+    """get_divergence (model_split.py:230-243) differentiates the network w.r.t. its input coordinates."""
+    net = _net(siren, (2, 64, 6, 2), seed=7)
+    x = _coords(3000, 2, seed=9).requires_grad_(True)
+    u = net(x)
+    div = sum(torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=True)[0][:, i] for i in range(2))
+    xr = x.detach().clone().requires_grad_(True)
+    ur = net.forward_reference(xr)
+    div_r = sum(torch.autograd.grad(ur[:, i], xr, torch.ones_like(ur[:, i]), retain_graph=True)[0][:, i] for i in range(2))
+    assert (div - div_r).abs().max().item() <= 2e-4*div_r.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("n", [128*300 + 5, 77])
+def test_tensor_core_forward_matches_fp32_kernel(siren, shape, n):
+    """tcgen05 path with the 3xTF32 split vs the exact-fp32 kernel and vs torch."""
+    net = _net(siren, shape, seed=11)
+    x = _coords(n, shape[0], seed=13)
+    with torch.no_grad():
+        ref = net.forward_reference(x)
+        y32 = net(x)
+        net.tensor_cores = True
+        ytc = net(x)
+        net.tensor_cores = False
+    scale = max(ref.abs().max().item(), 1e-3)
+    assert (ytc - y32).abs().max().item() <= 1e-4*scale, (ytc - y32).abs().max().item()/scale
+    assert (ytc - ref).abs().max().item() <= 1e-4*scale
+
+
+def test_fused_adam_matches_torch(siren):
+    torch.manual_seed(0)
+    p0 = [torch.randn(64, 64, device="cuda"), torch.randn(64, device="cuda"), torch.randn(2, 64, device="cuda")]
+    a = [torch.nn.Parameter(p.clone()) for p in p0]
+    b = [torch.nn.Parameter(p.clone()) for p in p0]
+    oa = siren.FusedAdam(a, lr=1e-3)
+    ob = torch.optim.Adam(b, lr=1e-3)
+    for it in range(12):
+        for pa, pb in zip(a, b):
+            g = torch.randn_like(pb)*(1 + it)
+            pa.grad = g.clone(); pb.grad = g.clone()
+        oa.step(); ob.step()
+    for pa, pb in zip(a, b):
+        assert (pa - pb).abs().max().item() <= 2e-6*pb.abs().max().item() + 1e-7
+
+
+def test_fit_loop_tracks_reference(siren):
+    """A short advection-style fit (model_split.py:88-120 shape: MSE against a frozen target network, Adam lr 1e-5
+    scaled up so that 60 iterations move the loss) with fused kernels vs stock ops from the same initial weights."""
+    shape = (2, 64, 6, 2)
+    net_f, net_r = _net(siren, shape, seed=21), _net(siren, shape, seed=21)
+    tgt = _net(siren, shape, seed=22)
+    opt_f = siren.FusedAdam(list(net_f.parameters()), lr=1e-4)
+    opt_r = torch.optim.Adam(net_r.parameters(), lr=1e-4)
+    lf = lr_ = None
+    for it in range(60):
+        x = _coords(4096, 2, seed=100 + it)
+        with torch.no_grad():
+            t = tgt.forward_reference(x)
+        lf = ((net_f(x) - t)**2).mean(); opt_f.zero_grad(); lf.backward(); opt_f.step()
+        lr_ = ((net_r.forward_reference(x) - t)**2).mean(); opt_r.zero_grad(); lr_.backward(); opt_r.step()
+    assert abs(lf.item() - lr_.item()) <= 2e-3*abs(lr_.item())

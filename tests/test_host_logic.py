@@ -216,3 +216,27 @@ def test_fast_mode_ball_functions_against_scipy(emu):
             F = (1 - Ts)/(1 - TX)
             sel = X >= 0.05 if dim == 3 else np.ones(len(R), bool)  # tiny 3D balls use the two-uniform polar method
             assert np.abs(F - u)[sel].max() < 2e-3
+
+
+def test_siren_symbols_and_state_dict_layout():
+    """libnmcfs.so exports the SIREN ABI (include/nmcfs_siren.h) and FusedSiren keeps the reference MLP's
+    parameter names, shapes and initialisation ranges (networks.py:24-90), so checkpoints are interchangeable."""
+    torch = pytest.importorskip("torch")
+    pkg = util.package()
+    hdr = open(os.path.join(util.ROOT, "include", "nmcfs_siren.h")).read()
+    declared = set(re.findall(r"\b(nmc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg.capi.SIREN_EXPORTS)
+    L = pkg.capi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    s = pkg.load_siren()
+    net = s.FusedSiren(2, 2, 6, 64, nonlinearity="sine")
+    keys = list(net.state_dict().keys())
+    assert keys == ["net.%d.%s" % (2*i, k) for i in range(8) for k in ("weight", "bias")]
+    assert net.state_dict()["net.0.weight"].shape == (64, 2) and net.state_dict()["net.14.weight"].shape == (2, 64)
+    assert net.net[0].weight.abs().max() <= 0.5 + 1e-6            # first_layer_sine_init: U(-1/in, 1/in)
+    assert net.net[2].weight.abs().max() <= np.sqrt(6/64)/30 + 1e-7  # sine_init
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(4, 2))
+    with pytest.raises(NotImplementedError):
+        s.FusedSiren(2, 2, 6, 64, nonlinearity="relu")
