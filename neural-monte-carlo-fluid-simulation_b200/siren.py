@@ -69,7 +69,7 @@ class _SirenFn(torch.autograd.Function):
         n = x2.shape[0]
         sh = _shape_of(W, w0)
         y = torch.empty((n, sh.out_dim), device=x.device, dtype=torch.float32)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need_grad = any(ctx.needs_input_grad)  # forward() itself runs with grad mode off
         L = _lib()
         with torch.cuda.device(x.device):
             if need_grad:
@@ -80,7 +80,7 @@ class _SirenFn(torch.autograd.Function):
                 _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), _stream()))
             else:
                 _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, _stream()))
-        ctx.w0, ctx.n_layers, ctx.lead, ctx.x_needs = w0, n_layers, lead, x.requires_grad
+        ctx.w0, ctx.n_layers, ctx.lead, ctx.x_needs = w0, n_layers, lead, ctx.needs_input_grad[0]
         return y.reshape(*lead, sh.out_dim)
 
     @staticmethod

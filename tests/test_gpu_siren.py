@@ -50,7 +50,7 @@ def test_backward_matches_torch_autograd(siren, shape):
     net = _net(siren, shape, seed=3)
     n = 2048 + 37
     x = _coords(n, shape[0], seed=5).requires_grad_(True)
-    target = torch.sin(3*x[:, :1]).expand(-1, shape[3])
+    target = torch.sin(3*x[:, :1]).expand(-1, shape[3]).detach()
     loss = ((net(x) - target)**2).mean()
     grads = torch.autograd.grad(loss, [x] + list(net.parameters()))
     xr = x.detach().clone().requires_grad_(True)
