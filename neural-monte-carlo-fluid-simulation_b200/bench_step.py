@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""bench_step.py -- simulation steps per second (BASELINE.json metric, second half): one operator-split step of
+the Taylor-Green configuration (examples/taylorgreen/run.sh: SIREN 6x64, batch 64^2, 512^2 pressure samples,
+1002^2 divergence grid, nWalks 500) with K Adam iterations per fit, through the device-resident stepper, next to
+the reference's arrangement of the same work: stock PyTorch ops for the fits (one loss.item() per iteration),
+divergence grid to the host, the reference's CPU walk-on-stars (oracle/_ref, bounded sample), gradients back.
+`--watertight` keeps the scene as shipped (the reference then classifies every point outside and returns zeros);
+default is the solver-active variant."""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+from importlib import import_module
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import util  # noqa: E402
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=1000, help="Adam iterations per fit (reference: 10000)")
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--watertight", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=8192)
+    args = ap.parse_args()
+    pkg = ge.load_package()
+    st = import_module(pkg.__name__ + ".stepper")
+    cfg = util.load_case("taylorgreen_shipped" if args.watertight else "taylorgreen_active")
+    size = (0.0, 2*math.pi, 0.0, 2*math.pi)
+    s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1)
+    tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
+    s.fit_initial(tg, 300, lr=1e-3)
+    s.step(50)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    parts = {"advect_ms": 0.0, "pressure_ms": 0.0, "project_ms": 0.0}
+    for _ in range(args.steps):
+        a = time.perf_counter(); s._sync_prev(); s.advect_velocity(args.iters); torch.cuda.synchronize()
+        b = time.perf_counter(); s._sync_prev()
+        pts = s.sample_random(s.wost_resolution**2).contiguous(); s.pressure_solve(pts); torch.cuda.synchronize()
+        c = time.perf_counter(); s.project_velocity(args.iters); torch.cuda.synchronize()
+        d = time.perf_counter()
+        parts["advect_ms"] += 1e3*(b - a); parts["pressure_ms"] += 1e3*(c - b); parts["project_ms"] += 1e3*(d - c)
+    total = time.perf_counter() - t0
+    ours = args.steps/total
+
+    # reference arrangement of the same step
+    S = pkg.load_siren()
+    net = S.FusedSiren(2, 2, 6, 64, nonlinearity="sine").cuda(); prev = S.FusedSiren(2, 2, 6, 64, nonlinearity="sine").cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-5)
+
+    def ref_iter():
+        x = s.sample_random(64*64)
+        with torch.no_grad():
+            pu = prev.forward_reference(x)*s.envelope(x)
+            back = (x - pu*s.dt).clamp(0, 2*math.pi)
+            adv = prev.forward_reference(back)*s.envelope(back)
+        loss = torch.mean((net.forward_reference(x)*s.envelope(x) - adv)**2)
+        opt.zero_grad(); loss.backward(retain_graph=True); opt.step()
+        return loss.item()  # base.py:142
+    for _ in range(20):
+        ref_iter()
+    torch.cuda.synchronize(); t = time.perf_counter()
+    n_ref = min(args.iters, 300)
+    for _ in range(n_ref):
+        ref_iter()
+    torch.cuda.synchronize(); ref_iter_ms = 1e3*(time.perf_counter() - t)/n_ref
+    div = s.last["div"].cpu().numpy()
+    from oracle import refbind
+    threads = os.cpu_count() or 1
+    t = time.perf_counter()
+    sc = refbind.RefScene(2, cfg["scene"], div)
+    pts = util.random_points(np.array([0, 0], np.float32), np.array([2*math.pi]*2, np.float32), args.cpu_sample, seed=5)
+    sc.wost(cfg["solver"], cfg["output"], pts, seed=1, nthreads=threads)
+    cpu_wost_s = (time.perf_counter() - t)*(512*512/args.cpu_sample)
+    ref_step_s = 2*args.iters*ref_iter_ms*1e-3 + cpu_wost_s
+    print(json.dumps({"metric": "sim_steps_per_sec", "value": ours, "unit": "steps/s", "config": {"workload": "taylorgreen step, %d Adam iterations per fit, 512^2 pressure samples x 500 walks, 1002^2 divergence grid" % args.iters,
+                                                                                              "scene": "as shipped (isWatertight)" if args.watertight else "solver active (isWatertight:false)",
+                                                                                              "cuda_graph": not args.no_graph},
+                      "ms_per_step": 1e3*total/args.steps, "breakdown_ms_per_step": {k: v/args.steps for k, v in parts.items()},
+                      "walks_per_step": int(s.last["walks"]), "wost_kernel_ms": s.last["wost_ms"],
+                      "reference_arrangement": {"fit_iteration_ms_stock_torch": ref_iter_ms, "cpu_wost_s_extrapolated_from_%d_points" % args.cpu_sample: cpu_wost_s,
+                                                "cores": threads, "step_s": ref_step_s, "steps_per_sec": 1.0/ref_step_s}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

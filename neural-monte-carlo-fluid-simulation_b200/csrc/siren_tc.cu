@@ -20,6 +20,29 @@
 
 namespace {
 
+// sin/cos of the SIREN pre-activation w0*z.  |w0 z| stays below a few hundred, so one explicit reduction to
+// [-pi, pi] (t = x/2pi - rint(x/2pi), exact subtraction) followed by the SFU sine/cosine is accurate to
+// ~5e-7 absolute -- the same size as the fp32 rounding of the argument itself (ulp(100) = 7.6e-6) -- and costs
+// 4 instructions instead of the ~40 of sinf's generic range reduction.  -DNMC_SIREN_LIBM_SIN restores sinf/cosf.
+__device__ __forceinline__ float sinReduced(float x) {
+#ifdef NMC_SIREN_LIBM_SIN
+	return sinf(x);
+#else
+	float t = x*0.15915494309189535f;
+	t -= rintf(t);
+	return __sinf(6.283185307179586f*t);
+#endif
+}
+__device__ __forceinline__ float cosReduced(float x) {
+#ifdef NMC_SIREN_LIBM_SIN
+	return cosf(x);
+#else
+	float t = x*0.15915494309189535f;
+	t -= rintf(t);
+	return __cosf(6.283185307179586f*t);
+#endif
+}
+
 constexpr int kTile = 128;
 constexpr int kMaxLayers = 18;
 constexpr int kNChunk = 64;   // output neurons per MMA group (UMMA N)
@@ -92,27 +115,29 @@ sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const flo
 		const long long s = tile*kTile + tid;
 		const bool live = s < n;
 		{ // first layer on the FMA pipe, written straight into the A operand
-			float xi[3] = {0.0f, 0.0f, 0.0f};
-			if (live) for (int i = 0; i < inDim; i++) xi[i] = x[s*inDim + i];
+			float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+			if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
 			for (int c = 0; c < H; c += 4) {
 				float hi[4], lo[4];
 #pragma unroll
 				for (int q = 0; q < 4; q++) {
-					float z = __ldg(&P.b[0][c + q]);
-					for (int i = 0; i < inDim; i++) z += __ldg(&P.W[0][(c + q)*inDim + i])*xi[i];
-					splitTf32(live ? sinf(w0*z) : 0.0f, hi[q], lo[q]);
+					const float* w = &P.W[0][(c + q)*inDim];
+					float z = __ldg(&P.b[0][c + q]) + __ldg(w)*x0;
+					if (inDim > 1) z += __ldg(w + 1)*x1;
+					if (inDim > 2) z += __ldg(w + 2)*x2;
+					splitTf32(live ? sinReduced(w0*z) : 0.0f, hi[q], lo[q]);
 				}
 				int off = coreOffsetBytes<H>(tid, c);
 				*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
 				*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 			}
 		}
-		float yacc[3] = {0.0f, 0.0f, 0.0f};
+		float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f;
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
 				for (int idx = tid; idx < kNChunk*H/4; idx += kTile) {
-					int r = idx/(H/4), k4 = idx - r*(H/4);
+					int k4 = idx/kNChunk, r = idx - k4*kNChunk; // lanes walk down the rows of one core-matrix column
 					float4 w = __ldg(reinterpret_cast<const float4*>(&P.W[l][(size_t)(nc*kNChunk + r)*H + 4*k4]));
 					float4 h, o;
 					splitTf32(w.x, h.x, o.x); splitTf32(w.y, h.y, o.y); splitTf32(w.z, h.z, o.z); splitTf32(w.w, h.w, o.w);
@@ -159,9 +184,13 @@ sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const flo
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
 						int c = c0 + q4 + q;
-						float a = sinf(w0*(__uint_as_float(v[q4 + q]) + __ldg(&P.b[l][c])));
+						float a = sinReduced(w0*(__uint_as_float(v[q4 + q]) + __ldg(&P.b[l][c])));
 						if (!live) a = 0.0f;
-						if (l == nHidden) { for (int j = 0; j < outDim; j++) yacc[j] += __ldg(&P.W[last][j*H + c])*a; }
+						if (l == nHidden) {
+							y0 += __ldg(&P.W[last][c])*a;
+							if (outDim > 1) y1 += __ldg(&P.W[last][H + c])*a;
+							if (outDim > 2) y2 += __ldg(&P.W[last][2*H + c])*a;
+						}
 						splitTf32(a, hi[q], lo[q]);
 					}
 					if (l < nHidden) {
@@ -172,7 +201,11 @@ sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const flo
 				}
 			}
 		}
-		if (live) for (int j = 0; j < outDim; j++) y[s*outDim + j] = yacc[j] + __ldg(&P.b[last][j]);
+		if (live) {
+			y[s*outDim] = y0 + __ldg(&P.b[last][0]);
+			if (outDim > 1) y[s*outDim + 1] = y1 + __ldg(&P.b[last][1]);
+			if (outDim > 2) y[s*outDim + 2] = y2 + __ldg(&P.b[last][2]);
+		}
 		// the next tile's first layer overwrites A: every thread is past its last use (MMAs completed via the mbarrier)
 		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 		__syncthreads();

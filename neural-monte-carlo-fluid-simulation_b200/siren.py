@@ -58,7 +58,7 @@ def _shape_of(weights, w0):
 
 class _SirenFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w0, tensor_cores, *params):
+    def forward(ctx, x, w0, tensor_cores, need_grad, *params):
         n_layers = len(params)//2
         W = [p.contiguous() for p in params[:n_layers]]
         b = [p.contiguous() for p in params[n_layers:]]
@@ -69,7 +69,6 @@ class _SirenFn(torch.autograd.Function):
         n = x2.shape[0]
         sh = _shape_of(W, w0)
         y = torch.empty((n, sh.out_dim), device=x.device, dtype=torch.float32)
-        need_grad = any(ctx.needs_input_grad)  # forward() itself runs with grad mode off
         L = _lib()
         with torch.cuda.device(x.device):
             if need_grad:
@@ -97,7 +96,7 @@ class _SirenFn(torch.autograd.Function):
         with torch.cuda.device(x2.device):
             _check(_lib().nmc_siren_backward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, z.data_ptr(), gy2.data_ptr(),
                                              _ptrs(gW), _ptrs(gb), gx.data_ptr() if gx is not None else None, _stream()))
-        return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, *gW, *gb)
+        return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, None, *gW, *gb)
 
 
 class Sine(nn.Module):
@@ -148,7 +147,9 @@ class FusedSiren(nn.Module):
 
     def forward(self, coords, weights=None):
         lin = self._linears()
-        out = _SirenFn.apply(coords, 30.0, self.tensor_cores, *[m.weight for m in lin], *[m.bias for m in lin])
+        # grad mode is off inside autograd.Function.forward, so decide here whether activations must be saved
+        need_grad = torch.is_grad_enabled() and (coords.requires_grad or any(p.requires_grad for p in self.parameters()))
+        out = _SirenFn.apply(coords, 30.0, self.tensor_cores, need_grad, *[m.weight for m in lin], *[m.bias for m in lin])
         if weights is not None:
             out = out*weights
         return out

@@ -1,0 +1,206 @@
+"""Device-resident operator-split time step: advect fit -> divergence grid -> Monte Carlo pressure solve ->
+projection fit, with every array staying in HBM.
+
+Mirrors the reference's NeuralFluidSplit.step for adv_ref = 0 (src/2d/models/model_split.py:44-62):
+    _advect_velocity   model_split.py:88-120      semi-Lagrangian backtrace, MSE fit by Adam
+    get_divergence     model_split.py:230-243     -div u on the (res+2)^2 grid, autograd w.r.t. the coordinates
+    wost_pressure      model_split.py:185-228     Scene(sceneConfig, div) + wost(...)
+    _project_velocity  model_split.py:246-284     fit u <- u_prev - grad p on the pressure samples
+    query_velocity     base.py:158-224            network + boundary envelope (taylorgreen branch :179-187)
+    _training_loop     base.py:129-152            max_n_iters Adam iterations, early stop at loss <= 1.1e-10
+What changes is where the data lives: the divergence grid is written into the scene with
+nmc_scene_set_source(src_is_device = 1), the solve runs through nmc_wost_solve_device on torch's stream and
+grad p never leaves the GPU (the reference round-trips all three through numpy / Python lists,
+model_split.py:194, :272).  The boundary structure is built once, not once per step (:191).
+One fit iteration = 2 no-grad forwards + 1 forward/backward of the fused SIREN kernels + 1 fused Adam kernel,
+optionally replayed from a CUDA graph (no per-iteration host synchronisation; the reference calls loss.item()
+every iteration, base.py:142 -- the early-stop test here runs every `check_every` iterations).
+"""
+import ctypes as C
+
+import torch
+
+from . import capi, zombie
+from .siren import FusedSiren, FusedAdam
+
+
+def sample_uniform_2d(resolution, size, device, with_boundary=True):
+    """utils/model_utils.py:3-20 (normalize=True, meshgrid indexing 'xy': result[i][j] = (x_j, y_i))."""
+    if (size[1] - size[0]) > (size[3] - size[2]):
+        res_x, res_y = resolution, int(resolution*(size[3] - size[2])/(size[1] - size[0]))
+    else:
+        res_x, res_y = int(resolution*(size[1] - size[0])/(size[3] - size[2])), resolution
+    x = torch.linspace(0.5, res_x - 0.5, res_x, device=device)
+    y = torch.linspace(0.5, res_y - 0.5, res_y, device=device)
+    if with_boundary:
+        x = torch.cat([torch.tensor([0.0], device=device), x, torch.tensor([res_x*1.0], device=device)])
+        y = torch.cat([torch.tensor([0.0], device=device), y, torch.tensor([res_y*1.0], device=device)])
+    coords = torch.stack(torch.meshgrid(x, y, indexing="xy"), dim=-1)
+    coords[..., 0] = coords[..., 0]/res_x*(size[1] - size[0]) + size[0]
+    coords[..., 1] = coords[..., 1]/res_y*(size[3] - size[2]) + size[2]
+    return coords
+
+
+class SplitStepper:
+    """2D split stepper on a rectangular domain `scene_size` = (x0, x1, y0, y1) with the wall envelope of the
+    reference's taylorgreen branch (boundary='taylorgreen') or no envelope (boundary=None)."""
+
+    def __init__(self, wost_config, scene_size, hidden_features=64, num_hidden_layers=6, dt=0.001, lr=1e-5,
+                 sample_resolution=64, wost_resolution=512, grid_resolution=1000, bdry_eps=1e-3, max_n_iters=10000,
+                 early_stop=True, check_every=100, boundary="taylorgreen", mode=capi.MODE_FAST, seed=0, device=0,
+                 use_cuda_graph=True, tensor_cores=True, init_velocity=None, init_iters=0):
+        self.dev = torch.device("cuda", device)
+        self.cfg = wost_config
+        self.size = tuple(float(v) for v in scene_size)
+        self.dt, self.lr, self.eps = dt, lr, bdry_eps
+        self.sample_resolution, self.wost_resolution, self.grid_resolution = sample_resolution, wost_resolution, grid_resolution
+        self.max_n_iters, self.early_stop, self.check_every = max_n_iters, early_stop, check_every
+        self.boundary, self.use_graph = boundary, use_cuda_graph
+        torch.manual_seed(seed)
+        mk = lambda: FusedSiren(2, 2, num_hidden_layers, hidden_features, nonlinearity="sine", tensor_cores=tensor_cores).to(self.dev)  # noqa: E731
+        self.velocity_field, self.velocity_field_prev = mk(), mk()
+        for p in self.velocity_field_prev.parameters():
+            p.requires_grad_(False)
+        # Scene(config, div): built once; the source grid is replaced every step
+        grid = sample_uniform_2d(grid_resolution, self.size, self.dev)
+        self.grid_shape = tuple(grid.shape[:2])
+        self.grid_samples = grid.reshape(-1, 2).contiguous()
+        self.scene = zombie.Scene(wost_config["scene"], torch.zeros(self.grid_shape).numpy(), device=device)
+        self.opts = zombie.solver_opts(wost_config["solver"], wost_config["output"], mode=mode, seed=seed)
+        self.timestep, self.seed = 0, seed
+        self.last = {}
+        if init_velocity is not None and init_iters > 0:
+            self.fit_initial(init_velocity, init_iters)
+
+    # ---- network + envelope (base.py:158-224, taylorgreen branch) ---------------------------------------------
+    def envelope(self, samples):
+        if self.boundary != "taylorgreen":
+            return None
+        s, e = self.size, self.eps
+        u_w = torch.min((samples[..., 0] - s[0]).abs().clamp(min=0, max=e), (samples[..., 0] - s[1]).abs().clamp(min=0, max=e))/e
+        v_w = torch.min((samples[..., 1] - s[2]).abs().clamp(min=0, max=e), (samples[..., 1] - s[3]).abs().clamp(min=0, max=e))/e
+        return torch.stack([u_w, v_w], dim=-1).detach()
+
+    def query_velocity(self, samples, use_prev=False):
+        net = self.velocity_field_prev if use_prev else self.velocity_field
+        out = net(samples)
+        w = self.envelope(samples)
+        return out if w is None else w*out
+
+    def sample_random(self, n):
+        s = self.size
+        c = torch.rand(n, 2, device=self.dev)
+        return torch.stack([c[:, 0]*(s[1] - s[0]) + s[0], c[:, 1]*(s[3] - s[2]) + s[2]], dim=-1)
+
+    # ---- fit loops ---------------------------------------------------------------------------------------------
+    def _loop(self, iteration, n_iters):
+        """_training_loop (base.py:129-152) without a host sync per iteration."""
+        opt = FusedAdam(list(self.velocity_field.parameters()), lr=self.lr)
+        loss_buf = torch.zeros((), device=self.dev)
+
+        def one():
+            loss = iteration()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            loss_buf.copy_(loss.detach())
+
+        graph = None
+        if self.use_graph:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm-up outside capture (allocator, lazy module state)
+                    one()
+            torch.cuda.current_stream().wait_stream(side)
+            done = 3
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one()
+            done += 1
+        else:
+            done = 0
+        it = done
+        while it < n_iters:
+            if graph is not None:
+                graph.replay()
+            else:
+                one()
+            it += 1
+            if self.early_stop and it % self.check_every == 0 and loss_buf.item() <= 1.1e-10:
+                break
+        return it, loss_buf
+
+    def advect_velocity(self, n_iters=None):
+        n = self.sample_resolution**2
+        s = self.size
+
+        def iteration():
+            samples = self.sample_random(n)
+            with torch.no_grad():
+                prev_u = self.query_velocity(samples, use_prev=True)
+                back = samples - prev_u*self.dt
+                back = torch.stack([back[:, 0].clamp(s[0], s[1]), back[:, 1].clamp(s[2], s[3])], dim=-1)
+                advected = self.query_velocity(back, use_prev=True)
+            cur = self.query_velocity(samples)
+            return torch.mean((cur - advected)**2)
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters)
+
+    def divergence_grid(self):
+        """-div u_prev on the (res+2)^2 grid, device tensor [rows(y)][cols(x)] (model_split.py:230-243)."""
+        x = self.grid_samples.detach().clone().requires_grad_(True)
+        u = self.query_velocity(x, use_prev=True)
+        div = 0.0
+        for i in range(2):
+            div = div + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=(i == 0))[0][:, i]
+        return (-div).reshape(self.grid_shape).contiguous()
+
+    def pressure_solve(self, samples):
+        div = self.divergence_grid()
+        self.scene.handle.set_source_device(div.data_ptr(), div.shape)
+        n = samples.shape[0]
+        p = torch.empty(n, device=self.dev); g = torch.empty((n, 2), device=self.dev)
+        st = capi.SolveStats()
+        self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=0,
+                                       stream=torch.cuda.current_stream().cuda_stream, stats=st)
+        self.last.update(walks=st.walks_started, wost_ms=st.kernel_ms, div=div)
+        return p, g
+
+    def project_velocity(self, n_iters=None):
+        samples_all = self.sample_random(self.wost_resolution**2).contiguous()
+        p, grad_p = self.pressure_solve(samples_all)
+        self.last.update(p=p, grad_p=grad_p, pressure_samples=samples_all)
+        n, big = self.sample_resolution**2, samples_all.shape[0]
+
+        def iteration():
+            idx = torch.randint(0, big - 1, (n,), device=self.dev)  # the reference excludes the last point (:274)
+            samples = samples_all[idx]
+            with torch.no_grad():
+                target = self.query_velocity(samples, use_prev=True) - grad_p[idx]
+            cur = self.query_velocity(samples)
+            return torch.mean((cur - target)**2)
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters)
+
+    def _sync_prev(self):
+        self.velocity_field_prev.load_state_dict(self.velocity_field.state_dict())
+
+    def step(self, n_iters=None):
+        """NeuralFluidSplit.step, adv_ref = 0, reset_wts = 0 (model_split.py:44-62)."""
+        self._sync_prev()
+        it_a, loss_a = self.advect_velocity(n_iters)
+        self._sync_prev()
+        it_p, loss_p = self.project_velocity(n_iters)
+        self._sync_prev()
+        self.timestep += 1
+        self.opts.seed = (self.seed + self.timestep) & 0xFFFFFFFFFFFFFFFF
+        return {"advect_iters": it_a, "advect_loss": loss_a, "project_iters": it_p, "project_loss": loss_p}
+
+    def fit_initial(self, velocity_fn, n_iters, lr=1e-4):
+        """Fit the network to an analytic initial velocity (main.py: initial condition fit)."""
+        opt = torch.optim.Adam(self.velocity_field.parameters(), lr=lr)
+        for _ in range(n_iters):
+            x = self.sample_random(self.sample_resolution**2)
+            loss = torch.mean((self.query_velocity(x) - velocity_fn(x))**2)
+            opt.zero_grad(); loss.backward(); opt.step()
+        self._sync_prev()
+        return loss.item()
