@@ -22,23 +22,33 @@ typedef struct {
 	float w0;            /* 30 (Sine.forward, networks.py:19-21) */
 } nmc_siren_shape;
 
+/* Boundary envelope multiplied onto the network output inside the kernels (query_velocity, base.py:158-224).
+ * kind 0: none.  kind 1: wall weights of the taylorgreen branch (base.py:179-187; 3D analogue with z):
+ *   w_i(x) = min(|x_i - lo_i|, |x_i - hi_i|) clamped to [0, eps] / eps  for output component i (< in_dim).
+ * The reference detaches the weights, so no gradient flows through them. May be passed as NULL (= kind 0). */
+typedef struct {
+	int kind;
+	float lo[3], hi[3];
+	float eps;
+} nmc_siren_envelope;
+
 const char* nmc_siren_last_error(void);
 
 /* y[n][out] = net(x[n][in]).  z_saved (may be NULL) receives the pre-activations of every sine layer,
  * (n_hidden_layers + 1) * hidden * n floats laid out [layer][neuron][sample], for nmc_siren_backward. */
 int nmc_siren_forward(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
-					  int64_t n, float* y, float* z_saved, void* stream);
+					  int64_t n, float* y, float* z_saved, const nmc_siren_envelope* env, void* stream);
 
 /* Accumulates dL/dW[l], dL/db[l] into gW[l], gb[l] (caller zero-fills) given grad_y = dL/dy [n][out];
  * grad_x (may be NULL) receives dL/dx [n][in]. */
 int nmc_siren_backward(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
 					   int64_t n, const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
-					   float* grad_x, void* stream);
+					   float* grad_x, const nmc_siren_envelope* env, void* stream);
 
 /* Tensor-core forward (tcgen05, 3xTF32 split => fp32-level accuracy) for inference batches; same contract as
  * nmc_siren_forward without z_saved. Falls back to an error (never to another path) on unsupported shapes. */
 int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
-						 int64_t n, float* y, void* stream);
+						 int64_t n, float* y, const nmc_siren_envelope* env, void* stream);
 
 /* torch.optim.Adam step (no weight decay, no amsgrad) over one flat parameter buffer; step is 1-based. */
 int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -52,9 +52,16 @@ struct Params {
 	float* gb[kMaxLayers];
 };
 
+struct Env { int kind; float lo[3], hi[3], eps; };
+__device__ __forceinline__ float envWeight(const Env& e, int i, float xi) {
+	float a = fminf(fmaxf(fabsf(xi - e.lo[i]), 0.0f), e.eps), b = fminf(fmaxf(fabsf(xi - e.hi[i]), 0.0f), e.eps);
+	return fminf(a, b)/e.eps;
+}
+
+
 template <int H>
 __global__ void __launch_bounds__(kTile)
-sirenForward(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+sirenForward(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 			 float* __restrict__ y, float* __restrict__ zSaved) {
 	extern __shared__ float smem[];
 	float* Wt = smem;                 // [H][H + 4]  transposed weights of the current hidden layer: Wt[k][n]
@@ -64,13 +71,15 @@ sirenForward(Params P, int inDim, int outDim, int nHidden, float w0, const float
 		const long long s = tile*kTile + tid;
 		const bool live = s < n;
 		float a[H];
+		float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+		if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
 		{ // first layer: in -> H
-			float xi[3] = {0.0f, 0.0f, 0.0f};
-			if (live) for (int i = 0; i < inDim; i++) xi[i] = x[s*inDim + i];
 #pragma unroll
 			for (int j = 0; j < H; j++) {
-				float z = __ldg(&P.b[0][j]);
-				for (int i = 0; i < inDim; i++) z += __ldg(&P.W[0][j*inDim + i])*xi[i];
+				const float* w = &P.W[0][j*inDim];
+				float z = __ldg(&P.b[0][j]) + __ldg(w)*x0;
+				if (inDim > 1) z += __ldg(w + 1)*x1;
+				if (inDim > 2) z += __ldg(w + 2)*x2;
 				if (zSaved && live) zSaved[(size_t)j*n + s] = z;
 				a[j] = sinReduced(w0*z);
 			}
@@ -108,6 +117,7 @@ sirenForward(Params P, int inDim, int outDim, int nHidden, float w0, const float
 			float z = __ldg(&P.b[last][j]);
 #pragma unroll
 			for (int k = 0; k < H; k++) z += __ldg(&P.W[last][j*H + k])*a[k];
+			if (env.kind == 1 && j < inDim) z *= envWeight(env, j, j == 0 ? x0 : (j == 1 ? x1 : x2));
 			if (live) y[s*outDim + j] = z;
 		}
 	}
@@ -121,7 +131,7 @@ __device__ __forceinline__ float warpSum(float v) {
 // Backward: gy = dL/dy [n][out]; accumulates into gW/gb (caller zero-fills), optional gx = dL/dx [n][in].
 template <int H>
 __global__ void __launch_bounds__(kTile)
-sirenBackward(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+sirenBackward(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 			  const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ gx) {
 	extern __shared__ float smem[];
 	constexpr int LD = H + 4;
@@ -139,7 +149,10 @@ sirenBackward(Params P, int inDim, int outDim, int nHidden, float w0, const floa
 		float g[H];
 		{ // last layer
 			float gyv[3] = {0.0f, 0.0f, 0.0f};
-			if (live) for (int j = 0; j < outDim; j++) gyv[j] = gy[s*outDim + j];
+			if (live) for (int j = 0; j < outDim; j++) {
+				gyv[j] = gy[s*outDim + j];
+				if (env.kind == 1 && j < inDim) gyv[j] *= envWeight(env, j, x[s*inDim + j]); // detached weights: scale only
+			}
 #pragma unroll
 			for (int k = 0; k < H; k++) {
 				float aL = live ? sinReduced(w0*zSaved[((size_t)nHidden*H + k)*n + s]) : 0.0f;
@@ -278,10 +291,19 @@ namespace nmc_siren_detail { void setError(const char* m) { g_err = m; } }
 
 extern "C" const char* nmc_siren_last_error(void) { return g_err; }
 
+static Env toEnv(const nmc_siren_envelope* e) {
+	Env v; v.kind = 0; v.eps = 1.0f;
+	for (int i = 0; i < 3; i++) { v.lo[i] = 0.0f; v.hi[i] = 0.0f; }
+	if (e && e->kind == 1) { v.kind = 1; v.eps = e->eps; for (int i = 0; i < 3; i++) { v.lo[i] = e->lo[i]; v.hi[i] = e->hi[i]; } }
+	return v;
+}
+
 extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
-								 int64_t n, float* y, float* z_saved, void* stream) {
+								 int64_t n, float* y, float* z_saved, const nmc_siren_envelope* envp, void* stream) {
 	Params P;
 	if (fill(P, sh, W, b, nullptr, nullptr)) return 1;
+	if (envp && envp->kind != 0 && envp->kind != 1) return fail("unknown envelope kind");
+	Env env = toEnv(envp);
 	if (n <= 0) return 0;
 	if (!x || !y) return fail("null buffer");
 	const int H = sh->hidden;
@@ -292,10 +314,10 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenForward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForward<64><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+		if (!e) sirenForward<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
 	} else {
 		e = cudaFuncSetAttribute(sirenForward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForward<128><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+		if (!e) sirenForward<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
 	}
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
@@ -303,9 +325,11 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 
 extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
 								  int64_t n, const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
-								  float* grad_x, void* stream) {
+								  float* grad_x, const nmc_siren_envelope* envp, void* stream) {
 	Params P;
 	if (fill(P, sh, W, b, gW, gb)) return 1;
+	if (envp && envp->kind != 0 && envp->kind != 1) return fail("unknown envelope kind");
+	Env env = toEnv(envp);
 	if (!gW || !gb) return fail("null gradient pointers");
 	if (n <= 0) return 0;
 	if (!x || !z_saved || !grad_y) return fail("null buffer");
@@ -317,10 +341,10 @@ extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const*
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenBackward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenBackward<64><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
+		if (!e) sirenBackward<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
 	} else {
 		e = cudaFuncSetAttribute(sirenBackward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenBackward<128><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
+		if (!e) sirenBackward<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
 	}
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;

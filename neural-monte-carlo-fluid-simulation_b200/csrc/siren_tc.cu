@@ -52,6 +52,13 @@ struct Params {
 	const float* b[kMaxLayers];
 };
 
+struct Env { int kind; float lo[3], hi[3], eps; };
+__device__ __forceinline__ float envWeight(const Env& e, int i, float xi) {
+	float a = fminf(fmaxf(fabsf(xi - e.lo[i]), 0.0f), e.eps), b = fminf(fmaxf(fabsf(xi - e.hi[i]), 0.0f), e.eps);
+	return fminf(a, b)/e.eps;
+}
+
+
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // K-major, no swizzle: element (r, k) of an operand with K columns (fp32/tf32, 4 per 16 bytes)
@@ -82,7 +89,7 @@ __device__ __forceinline__ void splitTf32(float v, float& hi, float& lo) {
 
 template <int H>
 __global__ void __launch_bounds__(kTile)
-sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y) {
+sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned char* Ahi = smem;
 	unsigned char* Alo = Ahi + kTile*H*4;
@@ -133,6 +140,12 @@ sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const flo
 			}
 		}
 		float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f;
+		float e0 = 1.0f, e1 = 1.0f, e2 = 1.0f;
+		if (env.kind == 1 && live) {
+			e0 = envWeight(env, 0, x[s*inDim]);
+			if (inDim > 1) e1 = envWeight(env, 1, x[s*inDim + 1]);
+			if (inDim > 2) e2 = envWeight(env, 2, x[s*inDim + 2]);
+		}
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
@@ -202,9 +215,9 @@ sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const flo
 			}
 		}
 		if (live) {
-			y[s*outDim] = y0 + __ldg(&P.b[last][0]);
-			if (outDim > 1) y[s*outDim + 1] = y1 + __ldg(&P.b[last][1]);
-			if (outDim > 2) y[s*outDim + 2] = y2 + __ldg(&P.b[last][2]);
+			y[s*outDim] = (y0 + __ldg(&P.b[last][0]))*e0;
+			if (outDim > 1) y[s*outDim + 1] = (y1 + __ldg(&P.b[last][1]))*(inDim > 1 ? e1 : 1.0f);
+			if (outDim > 2) y[s*outDim + 2] = (y2 + __ldg(&P.b[last][2]))*(inDim > 2 ? e2 : 1.0f);
 		}
 		// the next tile's first layer overwrites A: every thread is past its last use (MMAs completed via the mbarrier)
 		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -218,12 +231,12 @@ sirenForwardTc(Params P, int inDim, int outDim, int nHidden, float w0, const flo
 } // namespace
 
 extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
-									int64_t n, float* y, void* stream);
+									int64_t n, float* y, const nmc_siren_envelope* envp, void* stream);
 
 namespace nmc_siren_detail { void setError(const char* m); }
 
 extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
-									int64_t n, float* y, void* stream) {
+									int64_t n, float* y, const nmc_siren_envelope* envp, void* stream) {
 	if (!sh || !W || !b) { nmc_siren_detail::setError("null argument"); return 1; }
 	if ((sh->hidden != 64 && sh->hidden != 128) || sh->n_hidden_layers < 1 || sh->n_hidden_layers + 2 > kMaxLayers ||
 		sh->in_dim < 1 || sh->in_dim > 3 || sh->out_dim < 1 || sh->out_dim > 3) {
@@ -234,6 +247,10 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	if (!x || !y) { nmc_siren_detail::setError("null buffer"); return 1; }
 	Params P;
 	for (int l = 0; l < sh->n_hidden_layers + 2; l++) { P.W[l] = W[l]; P.b[l] = b[l]; }
+	Env env; env.kind = 0; env.eps = 1.0f;
+	for (int i = 0; i < 3; i++) { env.lo[i] = 0.0f; env.hi[i] = 0.0f; }
+	if (envp && envp->kind == 1) { env.kind = 1; env.eps = envp->eps; for (int i = 0; i < 3; i++) { env.lo[i] = envp->lo[i]; env.hi[i] = envp->hi[i]; } }
+	else if (envp && envp->kind != 0) { nmc_siren_detail::setError("unknown envelope kind"); return 1; }
 	const int H = sh->hidden;
 	size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4;
 	int dev = 0, sms = 148;
@@ -246,10 +263,10 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenForwardTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<64><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+		if (!e) sirenForwardTc<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
 	} else {
 		e = cudaFuncSetAttribute(sirenForwardTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<128><<<grid, kTile, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+		if (!e) sirenForwardTc<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
 	}
 	if (!e) e = cudaGetLastError();
 	if (e) { nmc_siren_detail::setError(cudaGetErrorString(e)); return 1; }

@@ -21,6 +21,20 @@ class Shape(C.Structure):
     _fields_ = [("in_dim", C.c_int), ("out_dim", C.c_int), ("hidden", C.c_int), ("n_hidden_layers", C.c_int), ("w0", C.c_float)]
 
 
+class Envelope(C.Structure):
+    """nmc_siren_envelope: wall weights multiplied onto the output inside the kernels (base.py:179-187)."""
+    _fields_ = [("kind", C.c_int), ("lo", C.c_float*3), ("hi", C.c_float*3), ("eps", C.c_float)]
+
+
+def wall_envelope(size, eps):
+    """size = (x0, x1, y0, y1[, z0, z1]) as the reference's scene_size."""
+    e = Envelope()
+    e.kind, e.eps = 1, float(eps)
+    for i in range(len(size)//2):
+        e.lo[i], e.hi[i] = float(size[2*i]), float(size[2*i + 1])
+    return e
+
+
 _configured = False
 
 
@@ -30,10 +44,10 @@ def _lib():
     if not _configured:
         vp = C.c_void_p
         L.nmc_siren_last_error.restype = C.c_char_p
-        L.nmc_siren_forward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, vp]
-        L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp]
+        L.nmc_siren_forward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, C.POINTER(Envelope), vp]
+        L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_backward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp,
-                                         C.POINTER(vp), C.POINTER(vp), vp, vp]
+                                         C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(Envelope), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         _configured = True
     return L
@@ -58,7 +72,7 @@ def _shape_of(weights, w0):
 
 class _SirenFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w0, tensor_cores, need_grad, *params):
+    def forward(ctx, x, w0, tensor_cores, need_grad, env, *params):
         n_layers = len(params)//2
         W = [p.contiguous() for p in params[:n_layers]]
         b = [p.contiguous() for p in params[n_layers:]]
@@ -73,13 +87,13 @@ class _SirenFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             if need_grad:
                 z = torch.empty(((sh.n_hidden_layers + 1)*sh.hidden, n), device=x.device, dtype=torch.float32)
-                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), _stream()))
+                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, _stream()))
                 ctx.save_for_backward(x2, z, *W, *b)
             elif tensor_cores:
-                _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), _stream()))
+                _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), env, _stream()))
             else:
-                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, _stream()))
-        ctx.w0, ctx.n_layers, ctx.lead, ctx.x_needs = w0, n_layers, lead, ctx.needs_input_grad[0]
+                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, env, _stream()))
+        ctx.w0, ctx.n_layers, ctx.lead, ctx.x_needs, ctx.env = w0, n_layers, lead, ctx.needs_input_grad[0], env
         return y.reshape(*lead, sh.out_dim)
 
     @staticmethod
@@ -95,8 +109,8 @@ class _SirenFn(torch.autograd.Function):
         gx = torch.empty_like(x2) if ctx.x_needs else None
         with torch.cuda.device(x2.device):
             _check(_lib().nmc_siren_backward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, z.data_ptr(), gy2.data_ptr(),
-                                             _ptrs(gW), _ptrs(gb), gx.data_ptr() if gx is not None else None, _stream()))
-        return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, None, *gW, *gb)
+                                             _ptrs(gW), _ptrs(gb), gx.data_ptr() if gx is not None else None, ctx.env, _stream()))
+        return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, None, None, *gW, *gb)
 
 
 class Sine(nn.Module):
@@ -145,11 +159,12 @@ class FusedSiren(nn.Module):
     def _linears(self):
         return [m for m in self.net if isinstance(m, nn.Linear)]
 
-    def forward(self, coords, weights=None):
+    def forward(self, coords, weights=None, envelope=None):
+        """envelope: optional siren.Envelope fused into the kernels (detached weights, as in the reference)."""
         lin = self._linears()
         # grad mode is off inside autograd.Function.forward, so decide here whether activations must be saved
         need_grad = torch.is_grad_enabled() and (coords.requires_grad or any(p.requires_grad for p in self.parameters()))
-        out = _SirenFn.apply(coords, 30.0, self.tensor_cores, need_grad, *[m.weight for m in lin], *[m.bias for m in lin])
+        out = _SirenFn.apply(coords, 30.0, self.tensor_cores, need_grad, envelope, *[m.weight for m in lin], *[m.bias for m in lin])
         if weights is not None:
             out = out*weights
         return out
@@ -178,9 +193,23 @@ class FusedAdam:
                 p.data = self.flat[off:off + k].view_as(p)
                 off += k
 
+        self.grad_views = []
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.grad_views.append(self.g[off:off + k].view_as(p))
+            off += k
+
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+
+    def step_flat(self):
+        """Adam step when the gradients were written straight into `grad_views` (no autograd, one kernel)."""
+        self.step_count += 1
+        with torch.cuda.device(self.flat.device):
+            _check(_lib().nmc_adam_step(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                        self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, _stream()))
 
     def step(self):
         self.step_count += 1
@@ -195,3 +224,36 @@ class FusedAdam:
         with torch.cuda.device(self.flat.device):
             _check(_lib().nmc_adam_step(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
                                         self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, _stream()))
+
+
+class DirectFit:
+    """One Adam iteration of an MSE fit without autograd: forward (saving pre-activations), dL/dy, zero one flat
+    gradient buffer, backward straight into it, Adam -- 5 launches.  Replaces update_network (base.py:83-96)."""
+
+    def __init__(self, net, lr, envelope=None, max_batch=16384):
+        self.net, self.env = net, envelope
+        self.lin = net._linears()
+        params = [t for m in self.lin for t in (m.weight, m.bias)]
+        self.opt = FusedAdam(params, lr=lr)
+        self.W = [m.weight for m in self.lin]; self.b = [m.bias for m in self.lin]
+        self.gW = self.opt.grad_views[0::2]; self.gb = self.opt.grad_views[1::2]
+        self.sh = _shape_of(self.W, 30.0)
+        dev = self.opt.flat.device
+        self.z = torch.empty(((self.sh.n_hidden_layers + 1)*self.sh.hidden, max_batch), device=dev)
+        self.max_batch = max_batch
+
+    def iterate(self, x, target):
+        n = x.shape[0]
+        assert n <= self.max_batch and x.is_contiguous()
+        L = _lib()
+        y = torch.empty((n, self.sh.out_dim), device=x.device)
+        z = self.z.reshape(-1)[: (self.sh.n_hidden_layers + 1)*self.sh.hidden*n]  # [layer*H + neuron][sample], stride n
+        with torch.cuda.device(x.device):
+            _check(L.nmc_siren_forward(C.byref(self.sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
+            diff = y - target
+            gy = diff*(2.0/diff.numel())
+            self.opt.g.zero_()
+            _check(L.nmc_siren_backward(C.byref(self.sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
+                                        _ptrs(self.gW), _ptrs(self.gb), None, self.env, _stream()))
+        self.opt.step_flat()
+        return diff

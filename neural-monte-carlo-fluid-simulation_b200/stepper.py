@@ -21,7 +21,7 @@ import ctypes as C
 import torch
 
 from . import capi, zombie
-from .siren import FusedSiren, FusedAdam
+from .siren import FusedSiren, DirectFit, wall_envelope
 
 
 def sample_uniform_2d(resolution, size, device, with_boundary=True):
@@ -69,6 +69,9 @@ class SplitStepper:
         self.opts = zombie.solver_opts(wost_config["solver"], wost_config["output"], mode=mode, seed=seed)
         self.timestep, self.seed = 0, seed
         self.last = {}
+        self.env = wall_envelope(self.size, bdry_eps) if boundary == "taylorgreen" else None
+        self._lo = torch.tensor([self.size[0], self.size[2]], device=self.dev)
+        self._hi = torch.tensor([self.size[1], self.size[3]], device=self.dev)
         if init_velocity is not None and init_iters > 0:
             self.fit_initial(init_velocity, init_iters)
 
@@ -82,45 +85,38 @@ class SplitStepper:
         return torch.stack([u_w, v_w], dim=-1).detach()
 
     def query_velocity(self, samples, use_prev=False):
+        """network x envelope in ONE kernel (the envelope is fused: include/nmcfs_siren.h nmc_siren_envelope)."""
         net = self.velocity_field_prev if use_prev else self.velocity_field
-        out = net(samples)
-        w = self.envelope(samples)
-        return out if w is None else w*out
+        return net(samples, envelope=self.env)
 
     def sample_random(self, n):
-        s = self.size
-        c = torch.rand(n, 2, device=self.dev)
-        return torch.stack([c[:, 0]*(s[1] - s[0]) + s[0], c[:, 1]*(s[3] - s[2]) + s[2]], dim=-1)
+        """sample_random_2D (utils/model_utils.py:22-31)."""
+        return torch.rand(n, 2, device=self.dev)*(self._hi - self._lo) + self._lo
 
     # ---- fit loops ---------------------------------------------------------------------------------------------
     def _loop(self, iteration, n_iters):
-        """_training_loop (base.py:129-152) without a host sync per iteration."""
-        opt = FusedAdam(list(self.velocity_field.parameters()), lr=self.lr)
+        """_training_loop (base.py:129-152) without autograd and without a host sync per iteration:
+        `iteration()` returns (samples, target); the MSE fit step is DirectFit.iterate (5 launches)."""
+        fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2)
         loss_buf = torch.zeros((), device=self.dev)
 
         def one():
-            loss = iteration()
-            opt.zero_grad()
-            loss.backward()
-            opt.step()
-            loss_buf.copy_(loss.detach())
+            samples, target = iteration()
+            diff = fit.iterate(samples, target)
+            loss_buf.copy_(torch.mean(diff*diff))
 
-        graph = None
+        graph, it = None, 0
         if self.use_graph:
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(3):  # warm-up outside capture (allocator, lazy module state)
+                for _ in range(3):  # warm-up outside capture
                     one()
             torch.cuda.current_stream().wait_stream(side)
-            done = 3
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 one()
-            done += 1
-        else:
-            done = 0
-        it = done
+            it = 4
         while it < n_iters:
             if graph is not None:
                 graph.replay()
@@ -139,11 +135,9 @@ class SplitStepper:
             samples = self.sample_random(n)
             with torch.no_grad():
                 prev_u = self.query_velocity(samples, use_prev=True)
-                back = samples - prev_u*self.dt
-                back = torch.stack([back[:, 0].clamp(s[0], s[1]), back[:, 1].clamp(s[2], s[3])], dim=-1)
+                back = torch.clamp(samples - prev_u*self.dt, min=self._lo, max=self._hi)
                 advected = self.query_velocity(back, use_prev=True)
-            cur = self.query_velocity(samples)
-            return torch.mean((cur - advected)**2)
+            return samples, advected
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters)
 
     def divergence_grid(self):
@@ -177,8 +171,7 @@ class SplitStepper:
             samples = samples_all[idx]
             with torch.no_grad():
                 target = self.query_velocity(samples, use_prev=True) - grad_p[idx]
-            cur = self.query_velocity(samples)
-            return torch.mean((cur - target)**2)
+            return samples, target
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters)
 
     def _sync_prev(self):

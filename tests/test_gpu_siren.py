@@ -123,3 +123,55 @@ def test_fit_loop_tracks_reference(siren):
         lf = ((net_f(x) - t)**2).mean(); opt_f.zero_grad(); lf.backward(); opt_f.step()
         lr_ = ((net_r.forward_reference(x) - t)**2).mean(); opt_r.zero_grad(); lr_.backward(); opt_r.step()
     assert abs(lf.item() - lr_.item()) <= 2e-3*abs(lr_.item())
+
+
+def _torch_envelope(x, size, eps):
+    w = []
+    for i in range(x.shape[1]):
+        lo, hi = size[2*i], size[2*i + 1]
+        w.append(torch.min((x[:, i] - lo).abs().clamp(min=0, max=eps), (x[:, i] - hi).abs().clamp(min=0, max=eps))/eps)
+    return torch.stack(w, dim=-1).detach()
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 6, 2), (3, 128, 2, 3)])
+def test_fused_envelope_matches_reference_query_velocity(siren, shape):
+    """query_velocity's wall weights (base.py:179-187) fused into the kernels: forward (fp32 and tensor-core)
+    and backward (parameter gradients and the detached-weight input gradient used by the divergence)."""
+    net = _net(siren, shape, seed=31)
+    dim = shape[0]
+    size = (-1.0, 1.0)*dim
+    eps = 0.2  # wide enough that many samples sit inside the ramp
+    env = siren.wall_envelope(size, eps)
+    x = _coords(3000, dim, seed=33).requires_grad_(True)
+    y = net(x, envelope=env)
+    loss = (y**2).sum()
+    grads = torch.autograd.grad(loss, [x] + list(net.parameters()))
+    xr = x.detach().clone().requires_grad_(True)
+    yr = net.forward_reference(xr)*_torch_envelope(xr, size, eps)
+    grads_r = torch.autograd.grad((yr**2).sum(), [xr] + list(net.parameters()))
+    scale = yr.abs().max().item()
+    assert (y - yr).abs().max().item() <= 3e-5*scale
+    for g, r in zip(grads, grads_r):
+        assert (g - r).abs().max().item() <= 3e-4*r.abs().max().item() + 1e-9
+    with torch.no_grad():
+        net.tensor_cores = True
+        ytc = net(x.detach(), envelope=env)
+        net.tensor_cores = False
+    assert (ytc - yr).abs().max().item() <= 1e-4*scale
+
+
+def test_direct_fit_iteration_equals_autograd_iteration(siren):
+    """DirectFit.iterate (no autograd, 5 launches) vs loss.backward() + FusedAdam on the same data."""
+    shape = (2, 64, 6, 2)
+    a, b = _net(siren, shape, seed=41), _net(siren, shape, seed=41)
+    env = siren.wall_envelope((-1.0, 1.0, -1.0, 1.0), 0.1)
+    fit = siren.DirectFit(a, lr=1e-3, envelope=env, max_batch=4096)
+    opt = siren.FusedAdam(list(b.parameters()), lr=1e-3)
+    for it in range(5):
+        x = _coords(4096, 2, seed=50 + it)
+        t = torch.sin(2*x)
+        fit.iterate(x, t)
+        loss = torch.mean((b(x, envelope=env) - t)**2)
+        opt.zero_grad(); loss.backward(); opt.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert (pa - pb).abs().max().item() <= 1e-5*pb.abs().max().item() + 1e-8
