@@ -29,6 +29,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util  # noqa: E402  (fixtures + synthetic inputs shared with the tests)
 
 B_WALK = {2: 8.04, 3: 8.06}  # algorithmic HBM bytes per walk, SURVEY.md section 8(d)
+# dram__bytes_read.sum + dram__bytes_write.sum of fastKernel<2> for the default workload, one launch, from the
+# ncu --set full capture summarised in profiles/r01_fastKernel2d_capture2.txt (2.83 MB + 2.16 MB): the source grid,
+# the points and the outputs once each -- the 8 B/walk of texel gathers are served by L2
+TRAFFIC_BYTES_DEFAULT_WORKLOAD = 4995072
 
 
 def peaks():
@@ -234,7 +238,8 @@ def main():
             "config": {"workload": args.workload, "case": args.case, "points_per_step_per_gpu": n, "nWalks": cfg["solver"]["nWalks"],
                        "mode": args.mode, "source_grid": list(src.shape), "l2": "flushed (256 MiB write) between timed steps",
                        "walk_steps_per_walk": wsteps/max(walks, 1), "parallelism": "points sharded, scene replicated, dp%d" % world},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach/pk["hbm_gbs"], "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach/pk["hbm_gbs"],
+                         "traffic": TRAFFIC_BYTES_DEFAULT_WORKLOAD if (args.case == "karman" and n == 100000 and args.mode == "fast") else None,
                          "peak_source": which,
                          "note": "walk kernel is instruction-issue bound (transcendentals + BVH traversal), HBM fraction is small by construction; see DESIGN.md"},
             "e2e": {"value": e2e_walks/e2e_s, "unit": "walks/s", "h2d_bytes_per_step": n*dim*4, "d2h_bytes_per_step": n*(1 + dim)*4},

@@ -39,10 +39,15 @@ const char* nmc_siren_last_error(void);
 int nmc_siren_forward(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
 					  int64_t n, float* y, float* z_saved, const nmc_siren_envelope* env, void* stream);
 
-/* Accumulates dL/dW[l], dL/db[l] into gW[l], gb[l] (caller zero-fills) given grad_y = dL/dy [n][out];
- * grad_x (may be NULL) receives dL/dx [n][in]. */
+/* Backward "delta chain": given grad_y = dL/dy [n][out] and the z_saved of the forward pass, writes
+ *   dZ[l][j][s] = dL/dz_l and A[l][j][s] = sin(w0 z_l) for l = 0 .. n_hidden_layers (layout of z_saved;
+ *   A has (L+1)*hidden*n floats, dZ has ((L+1)*hidden + out_dim)*n: its last out_dim rows receive grad_y'),
+ *   and, if grad_x != NULL, dL/dx [n][in].
+ * The parameter gradients are then GEMMs over the batch dimension (done by the caller, one batched call):
+ *   dW_0 = dZ_0 x,  dW_l = dZ_l A_{l-1}^T (l = 1..L),  dW_last = grad_y'^T A_L^T,  db_l = rowsum(dZ_l),
+ *   with grad_y' = grad_y times the (detached) envelope weights when an envelope is given. */
 int nmc_siren_backward(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
-					   int64_t n, const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
+					   int64_t n, const float* z_saved, const float* grad_y, float* dZ, float* A,
 					   float* grad_x, const nmc_siren_envelope* env, void* stream);
 
 /* Tensor-core forward (tcgen05, 3xTF32 split => fp32-level accuracy) for inference batches; same contract as

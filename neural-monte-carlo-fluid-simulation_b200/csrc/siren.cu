@@ -9,8 +9,8 @@
 // One thread owns one sample; its activation vector lives in registers, the layer's weights are staged
 // in shared memory and read as broadcast float4s, so a layer costs H*H FMAs + H*H/4 LDS.128 per sample.
 // The backward pass recomputes activations from the saved pre-activations z_l (written by the training
-// forward, layout [layer][neuron][sample], coalesced), forms dW_l = dZ_l^T A_{l-1} per 128-sample tile with
-// a register-tiled shared-memory GEMM and accumulates tiles with atomics.
+// forward, layout [layer][neuron][sample], coalesced) and emits the per-layer deltas dZ_l and activations A_l;
+// the weight gradients dW_l = dZ_l A_{l-1}^T are batch-dimension GEMMs issued by the host layer (siren.py).
 // This is the exact-fp32 path (parity with torch within summation-order error); the tensor-core path for
 // large inference batches is csrc/siren_tc.cu.
 #include <cuda_runtime.h>
@@ -128,86 +128,65 @@ __device__ __forceinline__ float warpSum(float v) {
 	return v;
 }
 
-// Backward: gy = dL/dy [n][out]; accumulates into gW/gb (caller zero-fills), optional gx = dL/dx [n][in].
+// Backward, stage 1 ("delta chain"): per sample, back-propagates dL/dy through the layers and writes
+//   dZ[l][j][s] = dL/dz_l  (l = 0..L)   and   A[l][j][s] = sin(w0 z_l)  (l = 0..L)
+// coalesced, plus dL/dx.  The weight gradients are then plain GEMMs over the batch dimension,
+//   dW_l = dZ_l A_{l-1}^T  (K = n),  db_l = rowsum(dZ_l),
+// which the host layer issues as ONE batched cuBLAS call for the hidden layers (a library GEMM is the right tool
+// for a plain GEMM; a 128-sample tile per CTA cannot fill 148 SMs at the fit loops' batch sizes of 4096-16384).
 template <int H>
 __global__ void __launch_bounds__(kTile)
-sirenBackward(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
-			  const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ gx) {
+sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+				   const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ gx,
+				   float* __restrict__ dZ, float* __restrict__ A) {
 	extern __shared__ float smem[];
 	constexpr int LD = H + 4;
-	float* Ws = smem;                  // [H][LD]      W_l row-major (n, k)
-	float* dzT = Ws + H*LD;            // [kTile][LD]  dZ tile, sample-major
-	float* aT = dzT + kTile*LD;        // [kTile][LD]  A_{l-1} tile, sample-major
-	const int tid = threadIdx.x, lane = tid & 31;
-	// register tile of the dW GEMM: (H/TN) x (H/TK) thread grid = 128 threads
-	constexpr int TN = 4, TK = H*H/(kTile*TN);  // H=64: 4x8, H=128: 4x32
-	const int nT = tid/(H/TK), kT = tid - nT*(H/TK);
+	float* Ws = smem;                  // [H][LD]  W_l row-major (n, k)
+	float* ex = Ws + H*LD;             // [H][kTile] exchange buffer (column per thread)
+	const int tid = threadIdx.x;
 	const int last = nHidden + 1;
 	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
 		const long long s = tile*kTile + tid;
 		const bool live = s < n;
 		float g[H];
-		{ // last layer
-			float gyv[3] = {0.0f, 0.0f, 0.0f};
-			if (live) for (int j = 0; j < outDim; j++) {
-				gyv[j] = gy[s*outDim + j];
-				if (env.kind == 1 && j < inDim) gyv[j] *= envWeight(env, j, x[s*inDim + j]); // detached weights: scale only
+		{ // last layer: g_L = W_last^T gy  (and A_L for dW_last)
+			float gy0 = 0.0f, gy1 = 0.0f, gy2 = 0.0f;
+			if (live) {
+				gy0 = gy[s*outDim]; if (outDim > 1) gy1 = gy[s*outDim + 1]; if (outDim > 2) gy2 = gy[s*outDim + 2];
+				if (env.kind == 1) { // detached weights: scale only
+					gy0 *= envWeight(env, 0, x[s*inDim]);
+					if (outDim > 1 && inDim > 1) gy1 *= envWeight(env, 1, x[s*inDim + 1]);
+					if (outDim > 2 && inDim > 2) gy2 *= envWeight(env, 2, x[s*inDim + 2]);
+				}
+				// rows (L+1)*H .. of dZ: the (envelope-scaled) output gradient, for dW_last = gy'^T A_L^T
+				const size_t r0 = (size_t)(nHidden + 1)*H;
+				dZ[(r0 + 0)*n + s] = gy0;
+				if (outDim > 1) dZ[(r0 + 1)*n + s] = gy1;
+				if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
 			}
 #pragma unroll
 			for (int k = 0; k < H; k++) {
-				float aL = live ? sinReduced(w0*zSaved[((size_t)nHidden*H + k)*n + s]) : 0.0f;
-				float acc = 0.0f;
-				for (int j = 0; j < outDim; j++) {
-					acc += __ldg(&P.W[last][j*H + k])*gyv[j];
-					float r = warpSum(gyv[j]*aL);
-					if (lane == 0) atomicAdd(&P.gW[last][j*H + k], r);
-				}
+				float acc = __ldg(&P.W[last][k])*gy0;
+				if (outDim > 1) acc += __ldg(&P.W[last][H + k])*gy1;
+				if (outDim > 2) acc += __ldg(&P.W[last][2*H + k])*gy2;
 				g[k] = acc;
 			}
-			for (int j = 0; j < outDim; j++) { float r = warpSum(gyv[j]); if (lane == 0) atomicAdd(&P.gb[last][j], r); }
 		}
-		for (int l = nHidden; l >= 1; l--) {
-			__syncthreads();
-			for (int i = tid; i < H*H; i += kTile) { int nn = i/H, k = i - nn*H; Ws[nn*LD + k] = __ldg(&P.W[l][i]); }
-			float dz[H];
+		for (int l = nHidden; l >= 0; l--) {
+			// dz_l = g * w0 cos(w0 z_l);  A_l = sin(w0 z_l)
 #pragma unroll
 			for (int j = 0; j < H; j++) {
 				float zl = live ? zSaved[((size_t)l*H + j)*n + s] : 0.0f;
-				float zp = live ? zSaved[((size_t)(l - 1)*H + j)*n + s] : 0.0f;
-				dz[j] = live ? g[j]*w0*cosReduced(w0*zl) : 0.0f;
-				dzT[tid*LD + j] = dz[j];
-				aT[tid*LD + j] = live ? sinReduced(w0*zp) : 0.0f;
+				float t = w0*zl*0.15915494309189535f;
+				t -= rintf(t);
+				float sn, cs;
+				__sincosf(6.283185307179586f*t, &sn, &cs);
+				g[j] = g[j]*w0*cs;
+				if (live) { dZ[((size_t)l*H + j)*n + s] = g[j]; A[((size_t)l*H + j)*n + s] = sn; }
 			}
+			if (l == 0) break;
 			__syncthreads();
-			{ // dW_l[nn][k] += sum_s dz[s][nn] * a[s][k]
-				float acc[TN][TK];
-#pragma unroll
-				for (int i = 0; i < TN; i++)
-#pragma unroll
-					for (int j = 0; j < TK; j++) acc[i][j] = 0.0f;
-#pragma unroll 4
-				for (int ss = 0; ss < kTile; ss++) {
-					float4 dv = *reinterpret_cast<const float4*>(&dzT[ss*LD + nT*TN]);
-					float d4[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-					for (int j = 0; j < TK; j += 4) {
-						float4 av = *reinterpret_cast<const float4*>(&aT[ss*LD + kT*TK + j]);
-#pragma unroll
-						for (int i = 0; i < TN; i++) {
-							acc[i][j] += d4[i]*av.x; acc[i][j + 1] += d4[i]*av.y; acc[i][j + 2] += d4[i]*av.z; acc[i][j + 3] += d4[i]*av.w;
-						}
-					}
-				}
-#pragma unroll
-				for (int i = 0; i < TN; i++)
-#pragma unroll
-					for (int j = 0; j < TK; j++) atomicAdd(&P.gW[l][(nT*TN + i)*H + kT*TK + j], acc[i][j]);
-				if (tid < H) { float r = 0.0f; for (int ss = 0; ss < kTile; ss++) r += dzT[ss*LD + tid]; atomicAdd(&P.gb[l][tid], r); }
-			}
-			// reload this sample's dz (not kept live across the GEMM), then let everybody finish reading the tiles
-			// before the rows are reused as the exchange buffer for g_{l-1}
-#pragma unroll
-			for (int j = 0; j < H; j++) dz[j] = dzT[tid*LD + j];
+			for (int i = tid; i < H*H; i += kTile) { int nn = i/H, k = i - nn*H; Ws[nn*LD + k] = __ldg(&P.W[l][i]); }
 			__syncthreads();
 			// g_{l-1}[k] = sum_nn W_l[nn][k] dz[nn]
 #pragma unroll 1
@@ -221,30 +200,25 @@ sirenBackward(Params P, Env env, int inDim, int outDim, int nHidden, float w0, c
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
 						float4 v = w[q];
-						acc[4*q + 0] += dz[nn]*v.x; acc[4*q + 1] += dz[nn]*v.y; acc[4*q + 2] += dz[nn]*v.z; acc[4*q + 3] += dz[nn]*v.w;
+						acc[4*q + 0] += g[nn]*v.x; acc[4*q + 1] += g[nn]*v.y; acc[4*q + 2] += g[nn]*v.z; acc[4*q + 3] += g[nn]*v.w;
 					}
 				}
 #pragma unroll
-				for (int j = 0; j < 16; j++) dzT[tid*LD + k0 + j] = acc[j]; // own row: reuse as exchange buffer
+				for (int j = 0; j < 16; j++) ex[(k0 + j)*kTile + tid] = acc[j];
 			}
 #pragma unroll
-			for (int k = 0; k < H; k++) g[k] = dzT[tid*LD + k];
+			for (int k = 0; k < H; k++) g[k] = ex[k*kTile + tid];
 		}
-		{ // first layer
-			float xi[3] = {0.0f, 0.0f, 0.0f}, gxi[3] = {0.0f, 0.0f, 0.0f};
-			if (live) for (int i = 0; i < inDim; i++) xi[i] = x[s*inDim + i];
+		if (gx && live) { // dL/dx = W_0^T dz_0
+			float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
 			for (int j = 0; j < H; j++) {
-				float dz = live ? g[j]*w0*cosReduced(w0*zSaved[(size_t)j*n + s]) : 0.0f;
-				for (int i = 0; i < inDim; i++) {
-					gxi[i] += __ldg(&P.W[0][j*inDim + i])*dz;
-					float r = warpSum(dz*xi[i]);
-					if (lane == 0) atomicAdd(&P.gW[0][j*inDim + i], r);
-				}
-				float r = warpSum(dz);
-				if (lane == 0) atomicAdd(&P.gb[0][j], r);
+				const float* w = &P.W[0][j*inDim];
+				a0 += __ldg(w)*g[j];
+				if (inDim > 1) a1 += __ldg(w + 1)*g[j];
+				if (inDim > 2) a2 += __ldg(w + 2)*g[j];
 			}
-			if (gx && live) for (int i = 0; i < inDim; i++) gx[s*inDim + i] = gxi[i];
+			gx[s*inDim] = a0; if (inDim > 1) gx[s*inDim + 1] = a1; if (inDim > 2) gx[s*inDim + 2] = a2;
 		}
 	}
 }
@@ -324,27 +298,26 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 }
 
 extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
-								  int64_t n, const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
+								  int64_t n, const float* z_saved, const float* grad_y, float* dZ, float* A,
 								  float* grad_x, const nmc_siren_envelope* envp, void* stream) {
 	Params P;
-	if (fill(P, sh, W, b, gW, gb)) return 1;
+	if (fill(P, sh, W, b, nullptr, nullptr)) return 1;
 	if (envp && envp->kind != 0 && envp->kind != 1) return fail("unknown envelope kind");
 	Env env = toEnv(envp);
-	if (!gW || !gb) return fail("null gradient pointers");
 	if (n <= 0) return 0;
-	if (!x || !z_saved || !grad_y) return fail("null buffer");
+	if (!x || !z_saved || !grad_y || !dZ || !A) return fail("null buffer");
 	const int H = sh->hidden;
-	size_t smem = ((size_t)H*(H + 4) + 2*(size_t)kTile*(H + 4))*sizeof(float);
+	size_t smem = ((size_t)H*(H + 4) + (size_t)H*kTile)*sizeof(float);
 	long long tiles = (n + kTile - 1)/kTile;
-	int grid = (int)(tiles < 2ll*smCount() ? tiles : 2ll*smCount());
+	int grid = (int)(tiles < 4ll*smCount() ? tiles : 4ll*smCount());
 	cudaStream_t st = (cudaStream_t)stream;
 	cudaError_t e;
 	if (H == 64) {
-		e = cudaFuncSetAttribute(sirenBackward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenBackward<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
+		e = cudaFuncSetAttribute(sirenBackwardChain<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenBackwardChain<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
 	} else {
-		e = cudaFuncSetAttribute(sirenBackward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenBackward<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x);
+		e = cudaFuncSetAttribute(sirenBackwardChain<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (!e) sirenBackwardChain<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
 	}
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;

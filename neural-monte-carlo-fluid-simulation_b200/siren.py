@@ -47,7 +47,7 @@ def _lib():
         L.nmc_siren_forward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_backward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp,
-                                         C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(Envelope), vp]
+                                         vp, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         _configured = True
     return L
@@ -104,13 +104,40 @@ class _SirenFn(torch.autograd.Function):
         sh = _shape_of(W, ctx.w0)
         n = x2.shape[0]
         gy2 = gy.reshape(n, sh.out_dim).contiguous().float()
-        gW = [torch.zeros_like(w) for w in W]
-        gb = [torch.zeros_like(v) for v in b]
         gx = torch.empty_like(x2) if ctx.x_needs else None
-        with torch.cuda.device(x2.device):
-            _check(_lib().nmc_siren_backward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, z.data_ptr(), gy2.data_ptr(),
-                                             _ptrs(gW), _ptrs(gb), gx.data_ptr() if gx is not None else None, ctx.env, _stream()))
+        dZ, A = _backward_chain(sh, W, b, x2, n, z, gy2, gx, ctx.env)
+        gW0, gb0, gWh, gbh, gWl, gbl = _param_grads(sh, x2, n, dZ, A)
+        gW = [gW0] + list(gWh.unbind(0)) + [gWl]
+        gb = [gb0] + list(gbh.unbind(0)) + [gbl]
         return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, None, None, *gW, *gb)
+
+
+def _backward_chain(sh, W, b, x2, n, z, gy2, gx, env):
+    """One kernel: per-layer deltas dZ and activations A (csrc/siren.cu sirenBackwardChain)."""
+    rows = (sh.n_hidden_layers + 1)*sh.hidden
+    dZ = torch.empty((rows + sh.out_dim, n), device=x2.device, dtype=torch.float32)
+    A = torch.empty((rows, n), device=x2.device, dtype=torch.float32)
+    with torch.cuda.device(x2.device):
+        _check(_lib().nmc_siren_backward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, z.data_ptr(), gy2.data_ptr(),
+                                         dZ.data_ptr(), A.data_ptr(), gx.data_ptr() if gx is not None else None, env, _stream()))
+    return dZ, A
+
+
+def _param_grads(sh, x2, n, dZ, A, out=None):
+    """Weight gradients = GEMMs over the batch dimension (one batched cuBLAS call for the hidden layers):
+    dW_0 = dZ_0 x, dW_l = dZ_l A_{l-1}^T, dW_last = gy'^T A_L^T, db_l = rowsum(dZ_l)."""
+    H, Lh = sh.hidden, sh.n_hidden_layers
+    rows = (Lh + 1)*H
+    dZv, Av, gyT = dZ[:rows].view(Lh + 1, H, n), A.view(Lh + 1, H, n), dZ[rows:]
+    if out is None:
+        return (dZv[0] @ x2, dZv[0].sum(dim=1), torch.bmm(dZv[1:], Av[:-1].transpose(1, 2)), dZv[1:].sum(dim=2),
+                gyT @ Av[Lh].t(), gyT.sum(dim=1))
+    gW0, gb0, gWh, gbh, gWl, gbl = out
+    torch.matmul(dZv[0], x2, out=gW0); torch.sum(dZv[0], dim=1, out=gb0)
+    if Lh > 0:
+        torch.bmm(dZv[1:], Av[:-1].transpose(1, 2), out=gWh); torch.sum(dZv[1:], dim=2, out=gbh)
+    torch.matmul(gyT, Av[Lh].t(), out=gWl); torch.sum(gyT, dim=1, out=gbl)
+    return out
 
 
 class Sine(nn.Module):
@@ -227,33 +254,42 @@ class FusedAdam:
 
 
 class DirectFit:
-    """One Adam iteration of an MSE fit without autograd: forward (saving pre-activations), dL/dy, zero one flat
-    gradient buffer, backward straight into it, Adam -- 5 launches.  Replaces update_network (base.py:83-96)."""
+    """One Adam iteration of an MSE fit without autograd: forward (saving pre-activations), dL/dy, delta-chain
+    kernel, batched GEMMs straight into one flat gradient buffer, one Adam kernel.  Replaces update_network
+    (base.py:83-96).  Flat layout: W_0, b_0, W_1..W_L (one [L,H,H] block), b_1..b_L, W_last, b_last."""
 
     def __init__(self, net, lr, envelope=None, max_batch=16384):
         self.net, self.env = net, envelope
-        self.lin = net._linears()
-        params = [t for m in self.lin for t in (m.weight, m.bias)]
-        self.opt = FusedAdam(params, lr=lr)
-        self.W = [m.weight for m in self.lin]; self.b = [m.bias for m in self.lin]
-        self.gW = self.opt.grad_views[0::2]; self.gb = self.opt.grad_views[1::2]
+        lin = net._linears()
+        self.W = [m.weight for m in lin]; self.b = [m.bias for m in lin]
+        order = [self.W[0], self.b[0]] + self.W[1:-1] + self.b[1:-1] + [self.W[-1], self.b[-1]]
+        self.opt = FusedAdam(order, lr=lr)
         self.sh = _shape_of(self.W, 30.0)
-        dev = self.opt.flat.device
-        self.z = torch.empty(((self.sh.n_hidden_layers + 1)*self.sh.hidden, max_batch), device=dev)
+        H, Lh, g = self.sh.hidden, self.sh.n_hidden_layers, self.opt.g
+        off = [0]
+
+        def take(shape):
+            k = 1
+            for v in shape:
+                k *= v
+            t = g[off[0]:off[0] + k].view(*shape); off[0] += k
+            return t
+        self.out = (take((H, self.sh.in_dim)), take((H,)), take((Lh, H, H)), take((Lh, H)), take((self.sh.out_dim, H)), take((self.sh.out_dim,)))
+        assert off[0] == g.numel()
+        self.z = torch.empty((Lh + 1)*H*max_batch, device=g.device)
         self.max_batch = max_batch
 
     def iterate(self, x, target):
         n = x.shape[0]
         assert n <= self.max_batch and x.is_contiguous()
-        L = _lib()
-        y = torch.empty((n, self.sh.out_dim), device=x.device)
-        z = self.z.reshape(-1)[: (self.sh.n_hidden_layers + 1)*self.sh.hidden*n]  # [layer*H + neuron][sample], stride n
+        sh = self.sh
+        y = torch.empty((n, sh.out_dim), device=x.device)
+        z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]  # [layer*H + neuron][sample], stride n
         with torch.cuda.device(x.device):
-            _check(L.nmc_siren_forward(C.byref(self.sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
-            diff = y - target
-            gy = diff*(2.0/diff.numel())
-            self.opt.g.zero_()
-            _check(L.nmc_siren_backward(C.byref(self.sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
-                                        _ptrs(self.gW), _ptrs(self.gb), None, self.env, _stream()))
+            _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
+        diff = y - target
+        gy = diff*(2.0/diff.numel())
+        dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)
+        _param_grads(sh, x, n, dZ, A, out=self.out)
         self.opt.step_flat()
         return diff
