@@ -191,6 +191,7 @@ def main():
                                   stats=stats if timed else None)
         e1.record()
         torch.cuda.synchronize()
+        step.lane = (stats.lane_slices, stats.warp_trips)
         return e0.elapsed_time(e1), stats.walks_started, stats.kernel_ms, stats.kernel_launches, stats.walk_steps
 
     for i in range(args.warmup):
@@ -237,7 +238,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "case": args.case, "points_per_step_per_gpu": n, "nWalks": cfg["solver"]["nWalks"],
                        "mode": args.mode, "source_grid": list(src.shape), "l2": "flushed (256 MiB write) between timed steps",
-                       "walk_steps_per_walk": wsteps/max(walks, 1), "parallelism": "points sharded, scene replicated, dp%d" % world},
+                       "walk_steps_per_walk": wsteps/max(walks, 1),
+                       "lane_occupancy_of_slice_loop": (step.lane[0]/(32.0*step.lane[1]) if getattr(step, "lane", (0, 0))[1] else None), "parallelism": "points sharded, scene replicated, dp%d" % world},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach/pk["hbm_gbs"],
                          "traffic": TRAFFIC_BYTES_DEFAULT_WORKLOAD if (args.case == "karman" and n == 100000 and args.mode == "fast") else None,
                          "peak_source": which,

@@ -74,6 +74,8 @@ typedef struct {
 	float kernel_ms;          /* device time of the estimator kernel(s), CUDA events on the launch stream */
 	float total_ms;           /* device time of the whole call incl. copies */
 	int kernel_launches;
+	uint64_t warp_trips;      /* default mode: trips of the per-warp slice loop ... */
+	uint64_t lane_slices;     /* ... and busy lanes summed over those trips (lane_slices / (32 warp_trips) = lane occupancy) */
 } nmc_solve_stats;
 
 const char* nmc_last_error(void);

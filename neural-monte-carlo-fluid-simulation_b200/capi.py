@@ -34,7 +34,7 @@ class SolverOpts(C.Structure):
 class SolveStats(C.Structure):
     _fields_ = [("walks_started", C.c_uint64), ("walks_completed", C.c_uint64), ("walk_steps", C.c_uint64),
                 ("active_points", C.c_uint64), ("kernel_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_int)]
+                ("kernel_launches", C.c_int), ("warp_trips", C.c_uint64), ("lane_slices", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

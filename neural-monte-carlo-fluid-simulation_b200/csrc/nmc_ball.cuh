@@ -409,18 +409,18 @@ struct BallFast {
 			x = fminf(x, 0.7f*X);
 		} else x = X - fminf(sqrtf(2.0f*mass/TX), 0.7f*X);
 		x = fminf(fmaxf(x, 1e-6f*X), X*(1.0f - 1e-6f));
-		// g and q are returned at the last EVALUATED iterate; the final Newton correction is below the
-		// tolerance there (|dx| <= 1e-4 X), far inside the Monte Carlo noise of the gradient estimator
+		// Fixed trip count, no early exit: every lane of the warp runs the same instruction stream (a data-dependent
+		// break serialises the warp on its slowest lane anyway).  sqrt(F) / sqrt(1-F) are close to linear, so four
+		// Newton steps from the analytic start reach |F(x) - u| < 3e-4 (tests/test_host_logic.py); g and q are
+		// returned at the last evaluated iterate, whose distance to the final x is below 1e-4 X.
 		float T, gg = 0.0f, qq = 0.0f;
-		for (int it = 0; it < 6; it++) {
+#pragma unroll 1
+		for (int it = 0; it < 4; it++) {
 			evalTgq(x, T, gg, qq);
 			float s = sqrtf(fmaxf(lower ? 1.0f - T : T - TX, 1e-30f));
 			float step = 2.0f*s*(s - target)/fmaxf(x*gg, 1e-30f);
 			float xn = lower ? x - step : x + step;
-			xn = fminf(fmaxf(xn, 0.25f*x), 0.5f*(x + X));
-			bool done = fabsf(xn - x) <= 1e-4f*X;
-			x = xn;
-			if (done) break;
+			x = fminf(fmaxf(xn, 0.25f*x), 0.5f*(x + X));
 		}
 		g = gg; q = qq;
 		return x;

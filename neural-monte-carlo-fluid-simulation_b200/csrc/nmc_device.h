@@ -6,7 +6,7 @@
 namespace nmc {
 
 // device-side counters accumulated by the estimator kernels
-struct Counters { unsigned long long walksStarted, walksCompleted, steps, activePoints; };
+struct Counters { unsigned long long walksStarted, walksCompleted, steps, activePoints, trips, laneSlices; };
 
 // wost_det.cu (compiled with -fmad=false)
 cudaError_t launchDeterministic(const SceneView& S, const SolverParams& o, const float* d_pts, long long n,

@@ -33,6 +33,7 @@ struct SceneView {
 	const float4* primN;
 	const float4* nrmV;
 	const float4* sils;
+	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
 	float bboxLo[3], bboxHi[3];
 	const float* src; int n0, n1, n2;
 	float absorption; int watertight, doubleSided;
@@ -400,6 +401,9 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 					if (id == lastId) continue;
 					if (sqMinR >= r2) continue;
 					viewDir = x - mk(s0.x, s0.y, 0.0f);
+#if defined(NMC_FAST_GEOM)
+					if (dot(viewDir, viewDir) > r2) continue; // reject on the squared distance before paying for the sqrt
+#endif
 					d = norm(viewDir);
 					n0 = mk(s1.x, s1.y, 0.0f); n1 = mk(s1.z, s1.w, 0.0f);
 					concavity = n0.x*n1.y - n1.x*n0.y;
@@ -457,6 +461,85 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 		}
 	}
 	return found;
+}
+
+// ---- flat scans for small scenes (default mode only) ------------------------------------------------------
+// With a few dozen primitives the tree bookkeeping (stack traffic, box sorting, cone tests) costs more than it
+// saves, and it makes the lanes of a warp diverge.  These scans visit every record in the same order in every
+// lane (the loads are shared-memory broadcasts), reject on one squared distance / one determinant, and return
+// the same minimum as the traversals above (ties may pick another primitive of equal distance).
+template <int DIM>
+NMC_HD bool flatClosestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
+	if (sqMinR >= r2) return false;
+	bool found = false;
+	for (int i = 0; i < S.nSilU; i++) {
+		V3 viewDir, n0, n1; float d2, concavity; int flags;
+		if (DIM == 2) {
+			float4 s0 = S.silsU[2*i];
+			viewDir = x - mk(s0.x, s0.y, 0.0f);
+			d2 = dot(viewDir, viewDir);
+			if (d2 > r2) continue;
+			float4 s1 = S.silsU[2*i + 1];
+			flags = asInt(s0.z);
+			n0 = mk(s1.x, s1.y, 0.0f); n1 = mk(s1.z, s1.w, 0.0f);
+			concavity = n0.x*n1.y - n1.x*n0.y;
+		} else {
+			float4 s0 = S.silsU[4*i], s1 = S.silsU[4*i + 1];
+			V3 pt; float t;
+			float d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
+			d2 = d*d;
+			if (d2 > r2) continue;
+			viewDir = x - pt;
+			flags = asInt(s0.w);
+			float4 s2 = S.silsU[4*i + 2];
+			n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.silsU[4*i + 3]);
+		}
+		bool isSil = (flags & 3) != 3;
+		if (!isSil) isSil = isSilhouette(concavity, n0, n1, viewDir, sqrtf(d2), flip, precision);
+		if (isSil) {
+			found = true; r2 = d2;
+			if (sqMinR >= r2) break;
+		}
+	}
+	if (found) dOut = sqrtf(r2);
+	return found;
+}
+template <int DIM>
+NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
+	int best = -1; float bu = 0.0f, bv = 0.0f;
+	for (int i = 0; i < S.nPrims; i++) {
+		if (DIM == 2) {
+			float4 q = S.prims[i];
+			float ux = q.x - o.x, uy = q.y - o.y, vx = q.z - q.x, vy = q.w - q.y;
+			float dv = dir.x*vy - dir.y*vx;
+			if (fabsf(dv) <= kEps) continue;
+			float inv = 1.0f/dv;
+			float s = (ux*dir.y - uy*dir.x)*inv, t = (ux*vy - uy*vx)*inv;
+			if (s >= 0.0f && s <= 1.0f && t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = s; }
+		} else {
+			V3 pa = xyz(S.prims[3*i]), v1 = xyz(S.prims[3*i + 1]) - pa, v2 = xyz(S.prims[3*i + 2]) - pa;
+			V3 p = cross(dir, v2);
+			float det = dot(v1, p);
+			if (fabsf(det) <= kEps) continue;
+			float inv = 1.0f/det;
+			V3 sv = o - pa;
+			float v = dot(sv, p)*inv;
+			if (v < 0.0f || v > 1.0f) continue;
+			V3 qv = cross(sv, v1);
+			float w = dot(dir, qv)*inv;
+			if (w < 0.0f || v + w > 1.0f) continue;
+			float t = dot(v2, qv)*inv;
+			if (t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = v; bv = w; }
+		}
+	}
+	if (best < 0) return false;
+	out.d = tMax; out.ref = best; out.n = xyz(S.primN[best]);
+	if (DIM == 2) { float4 q = S.prims[best]; out.p = mk(q.x + bu*(q.z - q.x), q.y + bu*(q.w - q.y), 0.0f); out.u = bu; out.v = -1.0f; }
+	else {
+		V3 pa = xyz(S.prims[3*best]), v1 = xyz(S.prims[3*best + 1]) - pa, v2 = xyz(S.prims[3*best + 2]) - pa;
+		out.p = (pa + v1*bu) + v2*bv; out.u = 1.0f - bu - bv; out.v = bu;
+	}
+	return true;
 }
 
 // ---- zombie's query adapters (fcpw_scene_loader.h:292-652) --------------------------------------

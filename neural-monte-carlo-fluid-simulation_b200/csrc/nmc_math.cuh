@@ -22,7 +22,7 @@
 // so min/max map to single FMNMX instructions, vector/scalar divisions become one reciprocal + multiplies,
 // the normal-cone test is evaluated without inverse trigonometric functions, and the three BVH traversals
 // are kept out of line (one copy each) to keep the kernel inside the instruction cache.
-#if defined(NMC_FAST_GEOM) && defined(__CUDACC__)
+#if defined(NMC_FAST_GEOM) && defined(__CUDACC__) && !defined(NMC_TRAV_INLINE)
 #define NMC_TRAV __host__ __device__ __noinline__
 #else
 #define NMC_TRAV NMC_HD

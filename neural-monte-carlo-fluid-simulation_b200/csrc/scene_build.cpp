@@ -337,6 +337,7 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 		}
 	}
 	out.sils.resize((size_t)(dim == 2 ? 2 : 4)*refs.size());
+	std::vector<char> emitted(B.sil.size(), 0);
 	for (size_t r = 0; r < refs.size(); r++) {
 		const Sil& s = B.sil[refs[r]];
 		int flags = (B.silHasFace(s, 0) ? 1 : 0) | (B.silHasFace(s, 1) ? 2 : 0);
@@ -353,6 +354,12 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 			out.sils[4*r + 1] = {pb.x, pb.y, pb.z, bits(s.id)};
 			out.sils[4*r + 2] = {n0.x, n0.y, n0.z, refAngle[r]};
 			out.sils[4*r + 3] = {n1.x, n1.y, n1.z, 0.0f};
+		}
+		if (!emitted[refs[r]]) { // de-duplicated copy: a silhouette shared by several leaves appears once
+			emitted[refs[r]] = 1;
+			const int w = dim == 2 ? 2 : 4;
+			for (int q = 0; q < w; q++) out.silsU.push_back(out.sils[w*r + q]);
+			out.nSilU++;
 		}
 	}
 }

@@ -16,6 +16,8 @@ struct FlatScene {
 	std::vector<Q4> primN;  // 1 per primitive
 	std::vector<Q4> nrmV;   // 2 (2D) / 6 (3D) per primitive
 	std::vector<Q4> sils;   // 2 (2D) / 4 (3D) per silhouette reference
+	std::vector<Q4> silsU;  // the same records, one per distinct silhouette (flat scan of small scenes)
+	int nSilU = 0;
 	float bboxLo[3] = {0, 0, 0}, bboxHi[3] = {0, 0, 0};
 };
 

@@ -72,7 +72,7 @@ __device__ __forceinline__ void stackInit(StridedStack& s, int* base, int slots)
 }
 __device__ __forceinline__ void stackInit(LocalStack&, int*, int) {}
 
-template <int DIM, class STACK>
+template <int DIM, class STACK, bool FLAT>
 __global__ void __launch_bounds__(kBlock, NMC_MINB)
 fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
 		   float* __restrict__ pOut, float* __restrict__ gOut, unsigned int* __restrict__ workCounter,
@@ -86,7 +86,9 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	// ---- stage the boundary structure in shared memory ------------------------------------------------
 	SceneView S = Sg;
 	if (stageQuads > 0) {
-		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*Sg.nSilRefs;
+		// FLAT: the de-duplicated silhouette list replaces the per-leaf references (the tree is only walked once per point)
+		const float4* silSrc = FLAT ? Sg.silsU : Sg.sils;
+		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*(FLAT ? Sg.nSilU : Sg.nSilRefs);
 #pragma unroll 1
 		for (int i = threadIdx.x; i < qN; i += kBlock) stage[i] = Sg.nodes[i];
 #pragma unroll 1
@@ -94,14 +96,16 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 #pragma unroll 1
 		for (int i = threadIdx.x; i < qF; i += kBlock) stage[qN + qP + i] = Sg.primN[i];
 #pragma unroll 1
-		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = Sg.sils[i];
-		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP; S.sils = stage + qN + qP + qF;
+		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = silSrc[i];
+		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP;
+		if (FLAT) S.silsU = stage + qN + qP + qF; else S.sils = stage + qN + qP + qF;
 		__syncthreads();
 	}
 
 	const int lane = threadIdx.x & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
 	unsigned cStarted = 0, cCompleted = 0, cSteps = 0, cActive = 0;
+	unsigned long long cTrips = 0, cLaneSlices = 0; // warp-level: loop trips and busy lanes per trip (lane 0 only)
 
 	int nPairs = o.nWalks, nAnti = 1;
 	if (o.useGradientAntitheticVariates) { nPairs = o.nWalks/2 > 1 ? o.nWalks/2 : 1; nAnti = 2; }
@@ -168,7 +172,9 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 					}
 					nextPair += __popc(need);
 				}
-				if (__ballot_sync(kFull, state == kFirstBall || state == kWalking) == 0u) break;
+				const unsigned busy = __ballot_sync(kFull, state == kFirstBall || state == kWalking);
+				if (busy == 0u) break;
+				cTrips++; cLaneSlices += __popc(busy);
 
 				// ---- phase 1: geometry (walk steps only) --------------------------------------------------------
 				V3 dir = mk(0, 0, 0), ipt = pt, inrm = mk(0, 0, 0);
@@ -200,6 +206,15 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						float starR;
 						if (o.stepsBeforeUsingMaximalSpheres <= walkLength) starR = dirichletDist;
 						else {
+							if (FLAT) { // fcpw_scene_loader.h:621-641 with the flat scan
+								starR = dirichletDist;
+								if (o.minStarRadius <= dirichletDist) {
+									float dsil;
+									float r2max = dirichletDist < kMaxF ? dirichletDist*dirichletDist : kMaxF;
+									bool f = flatClosestSilhouette<DIM>(S, pt, r2max, !flipOrient, o.minStarRadius*o.minStarRadius, o.silhouettePrecision, dsil);
+									starR = f ? fmaxf(dsil, o.minStarRadius) : fmaxf(dirichletDist, o.minStarRadius);
+								}
+							} else
 							starR = starRadius<DIM, M>(S, stack, pt, o.minStarRadius, dirichletDist, o.silhouettePrecision, flipOrient);
 							if (o.minStarRadius <= dirichletDist) starR = fmaxf(kShrink*starR, o.minStarRadius);
 						}
@@ -209,6 +224,10 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						dir = sphereDir<DIM, M>(u0, u1);
 						if (onNeumann && dot(normal, dir) > 0.0f) dir = dir*-1.0f;
 						Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
+						if (FLAT) {
+							V3 ro = onNeumann ? offsetPoint<DIM>(pt, neg(normal)) : pt;
+							hit = flatRay<DIM>(S, ro, dir, starR, h);
+						} else
 						hit = intersectNeumann<DIM>(S, stack, pt, normal, dir, starR, onNeumann, h);
 						if (hit) { ipt = h.p; inrm = h.n; idist = h.d; }
 						else {
@@ -334,6 +353,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		atomicAdd(&counters->walksCompleted, (unsigned long long)cCompleted);
 		atomicAdd(&counters->steps, (unsigned long long)cSteps);
 		atomicAdd(&counters->activePoints, (unsigned long long)cActive);
+		atomicAdd(&counters->trips, cTrips);
+		atomicAdd(&counters->laneSlices, cLaneSlices);
 	}
 }
 
@@ -343,7 +364,9 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (n <= 0) return cudaSuccess;
 	if (n >= (1ll << 32) - 65536) return cudaErrorInvalidValue;
 	const int dim = S.dim;
-	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*S.nSilRefs;
+	// small scenes are scanned flat (no per-step tree traversal)
+	const bool flat = S.nPrims <= 128 && S.nSilU <= 128;
+	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? S.nSilU : S.nSilRefs);
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
@@ -351,8 +374,10 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	bool smemStack = stackSlots <= 24;
 	size_t smem = (stageQuads ? bytes : 0) + (smemStack ? (size_t)stackSlots*kBlock*8 : 0);
 	void (*kern)(SceneView, SolverParams, const float*, long long, unsigned long long, float*, float*, unsigned int*, Counters*, float*, int, int);
-	if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack> : fastKernel<2, LocalStack>;
-	else kern = smemStack ? fastKernel<3, StridedStack> : fastKernel<3, LocalStack>;
+	if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true> : fastKernel<3, StridedStack, true>;
+	else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false> : fastKernel<2, LocalStack, false>;
+	else kern = smemStack ? fastKernel<3, StridedStack, false> : fastKernel<3, LocalStack, false>;
+	if (flat && !smemStack) return cudaErrorInvalidConfiguration; // cannot happen: <= 128 primitives give a shallow tree
 	int perSM = 0;
 	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kBlock, smem);
 	if (e != cudaSuccess) return e;
