@@ -34,6 +34,7 @@ struct SceneView {
 	const float4* nrmV;
 	const float4* sils;
 	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
+	const float4* grpP; const float4* grpS; // (lo, hi) per group of 8 primitives / silhouettes
 	float bboxLo[3], bboxHi[3];
 	const float* src; int n0, n1, n2;
 	float absorption; int watertight, doubleSided;
@@ -472,7 +473,15 @@ template <int DIM>
 NMC_HD bool flatClosestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
 	if (sqMinR >= r2) return false;
 	bool found = false;
-	for (int i = 0; i < S.nSilU; i++) {
+	const int gs = S.nSilU > 16 ? 8 : 16; // tiny lists are one group: no culling, no nest overhead
+	for (int g0 = 0; g0 < S.nSilU; g0 += gs) {
+		if (gs == 8) { // every lane of the warp sits near the same query point, so this cull is warp-coherent
+			float dmin, dmax;
+			boxSqDist(xyz(S.grpS[g0 >> 2]), xyz(S.grpS[(g0 >> 2) + 1]), x, dmin, dmax);
+			if (dmin > r2) continue;
+		}
+		const int g1 = g0 + gs < S.nSilU ? g0 + gs : S.nSilU;
+	for (int i = g0; i < g1; i++) {
 		V3 viewDir, n0, n1; float d2, concavity; int flags;
 		if (DIM == 2) {
 			float4 s0 = S.silsU[2*i];
@@ -501,13 +510,23 @@ NMC_HD bool flatClosestSilhouette(const SceneView& S, V3 x, float r2, bool flip,
 			if (sqMinR >= r2) break;
 		}
 	}
+		if (sqMinR >= r2) break;
+	}
 	if (found) dOut = sqrtf(r2);
 	return found;
 }
 template <int DIM>
 NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
 	int best = -1; float bu = 0.0f, bv = 0.0f;
-	for (int i = 0; i < S.nPrims; i++) {
+	const int gp = S.nPrims > 16 ? 8 : 16;
+	for (int g0 = 0; g0 < S.nPrims; g0 += gp) {
+		if (gp == 8) { // the ray is at most tMax long: skip groups farther than that from its origin (warp-coherent, see above)
+			float dmin, dmax;
+			boxSqDist(xyz(S.grpP[g0 >> 2]), xyz(S.grpP[(g0 >> 2) + 1]), o, dmin, dmax);
+			if (dmin > tMax*tMax) continue;
+		}
+		const int g1 = g0 + gp < S.nPrims ? g0 + gp : S.nPrims;
+	for (int i = g0; i < g1; i++) {
 		if (DIM == 2) {
 			float4 q = S.prims[i];
 			float ux = q.x - o.x, uy = q.y - o.y, vx = q.z - q.x, vy = q.w - q.y;
@@ -531,6 +550,7 @@ NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
 			float t = dot(v2, qv)*inv;
 			if (t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = v; bv = w; }
 		}
+	}
 	}
 	if (best < 0) return false;
 	out.d = tMax; out.ref = best; out.n = xyz(S.primN[best]);

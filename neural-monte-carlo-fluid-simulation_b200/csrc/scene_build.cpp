@@ -362,6 +362,21 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 			out.nSilU++;
 		}
 	}
+	// group boxes for the flat scans (tree order keeps neighbours together)
+	auto groupBoxes = [&](const std::vector<Q4>& rec, int perItem, int nItems, int ptsPerItem, std::vector<Q4>& outBoxes) {
+		for (int g0 = 0; g0 < nItems; g0 += 8) {
+			float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+			for (int i = g0; i < std::min(nItems, g0 + 8); i++) for (int q = 0; q < ptsPerItem; q++) {
+				const Q4& r = rec[(size_t)perItem*i + q];
+				float pts[2][3] = {{r.x, r.y, dim == 3 ? r.z : 0.0f}, {r.z, r.w, 0.0f}};
+				int np = (dim == 2 && perItem == 1) ? 2 : 1; // a 2D segment record packs both end points
+				for (int k = 0; k < np; k++) for (int c = 0; c < 3; c++) { lo[c] = std::min(lo[c], pts[k][c]); hi[c] = std::max(hi[c], pts[k][c]); }
+			}
+			outBoxes.push_back({lo[0], lo[1], lo[2], 0.0f}); outBoxes.push_back({hi[0], hi[1], hi[2], 0.0f});
+		}
+	};
+	groupBoxes(out.prims, dim == 2 ? 1 : 3, nP, dim == 2 ? 1 : 3, out.grpP);
+	groupBoxes(out.silsU, dim == 2 ? 2 : 4, out.nSilU, dim == 2 ? 1 : 2, out.grpS); // 2D: the vertex; 3D: both edge end points
 }
 
 } // namespace nmc

@@ -18,6 +18,8 @@ struct FlatScene {
 	std::vector<Q4> sils;   // 2 (2D) / 4 (3D) per silhouette reference
 	std::vector<Q4> silsU;  // the same records, one per distinct silhouette (flat scan of small scenes)
 	int nSilU = 0;
+	// flat-scan culling boxes: one (lo, hi) pair per group of 8 consecutive primitives / distinct silhouettes
+	std::vector<Q4> grpP, grpS;
 	float bboxLo[3] = {0, 0, 0}, bboxHi[3] = {0, 0, 0};
 };
 

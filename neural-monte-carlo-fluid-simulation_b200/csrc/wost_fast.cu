@@ -65,7 +65,7 @@ __device__ __forceinline__ unsigned warpSumU(unsigned v) {
 enum LaneState { kNeedPair = 0, kFirstBall = 1, kWalking = 2, kIdle = 3 };
 
 #ifndef NMC_MINB
-#define NMC_MINB 4
+#define NMC_MINB 8   // 64 registers/thread, 32 warps/SM: measured best on B200 (profiles/README.md)
 #endif
 __device__ __forceinline__ void stackInit(StridedStack& s, int* base, int slots) {
 	s.nodes = base + threadIdx.x; s.dists = reinterpret_cast<float*>(base + slots*kBlock) + threadIdx.x; s.stride = kBlock;
@@ -98,7 +98,16 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 #pragma unroll 1
 		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = silSrc[i];
 		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP;
-		if (FLAT) S.silsU = stage + qN + qP + qF; else S.sils = stage + qN + qP + qF;
+		if (FLAT) {
+			S.silsU = stage + qN + qP + qF;
+			const int qGP = 2*((Sg.nPrims + 7)/8), qGS = 2*((Sg.nSilU + 7)/8);
+			float4* gp = stage + qN + qP + qF + qS;
+#pragma unroll 1
+			for (int i = threadIdx.x; i < qGP; i += kBlock) gp[i] = Sg.grpP[i];
+#pragma unroll 1
+			for (int i = threadIdx.x; i < qGS; i += kBlock) gp[qGP + i] = Sg.grpS[i];
+			S.grpP = gp; S.grpS = gp + qGP;
+		} else S.sils = stage + qN + qP + qF;
 		__syncthreads();
 	}
 
@@ -366,7 +375,8 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	const int dim = S.dim;
 	// small scenes are scanned flat (no per-step tree traversal)
 	const bool flat = S.nPrims <= 128 && S.nSilU <= 128;
-	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? S.nSilU : S.nSilRefs);
+	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? S.nSilU : S.nSilRefs)
+				 + (flat ? (size_t)2*((S.nPrims + 7)/8) + (size_t)2*((S.nSilU + 7)/8) : 0);
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
