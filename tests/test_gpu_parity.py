@@ -206,3 +206,27 @@ def test_edge_cases(pkg):
     assert isinstance(sol, list) and isinstance(grad[0], list) and len(grad[0]) == 2 and pts[1][0] == pytest.approx(0.3)
     with pytest.raises(RuntimeError, match="not supported"):
         pkg.zombie.wost_array(sc, dict(cfg["solver"], useCosineSamplingForDirectionalDerivatives=True), cfg["output"], mid)
+
+
+def test_full_size_3d_properties_one_million_points(pkg):
+    """BASELINE.json configs[4] size (3D, ~1e6 query points/step, 5e8 walks): finite results, exact walk
+    accounting, linearity in the source and shard invariance checked on slices."""
+    cfg = util.load_case("smoke3d")
+    src = util.source_grid(3)
+    sc = _scene(pkg, cfg, src)
+    lo, hi = sc.bbox()
+    n = 1000000
+    pts = util.random_points(lo, hi, n, seed=8)
+    p, g, _, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_FAST, seed=21)
+    assert np.isfinite(p).all() and np.isfinite(g).all()
+    assert st.walks_started == 500*st.active_points and st.active_points > 0.99*n
+    assert st.walks_completed >= 0.999*st.walks_started  # closed cube: (almost) no walk escapes (reference: 100 % on 1024 points)
+    sc.handle.set_source(2.0*src)
+    p2, g2, _, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts[:50000], mode=pkg.capi.MODE_FAST, seed=21)
+    assert util.close_mask(p2, 2.0*p[:50000], rtol=1e-4, atol_scale=1e-5).mean() > 0.999
+    sc.handle.set_source(src)
+    pb, gb, _, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts[900000:], mode=pkg.capi.MODE_FAST, seed=21, index_offset=900000)
+    assert util.close_mask(pb, p[900000:], rtol=1e-4, atol_scale=1e-5).mean() > 0.999
+    # a smooth source gives a smooth field: the Monte Carlo estimate must correlate with itself across seeds
+    p3, _, _, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts[:50000], mode=pkg.capi.MODE_FAST, seed=22)
+    assert np.corrcoef(p[:50000], p3)[0, 1] > 0.9
