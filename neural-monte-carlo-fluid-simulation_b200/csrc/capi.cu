@@ -18,7 +18,7 @@ struct nmc_scene {
 	int device = 0, smCount = 148;
 	FlatScene flat;
 	SceneView view;
-	float4 *d_nodes = nullptr, *d_prims = nullptr, *d_primN = nullptr, *d_nrmV = nullptr, *d_sils = nullptr, *d_silsU = nullptr, *d_grpP = nullptr, *d_grpS = nullptr;
+	float4 *d_nodes = nullptr, *d_prims = nullptr, *d_primN = nullptr, *d_nrmV = nullptr, *d_sils = nullptr, *d_silsU = nullptr, *d_grpP = nullptr, *d_grpS = nullptr, *d_rayP = nullptr, *d_rayN = nullptr;
 	float* d_src = nullptr; size_t srcCap = 0;
 	// grow-only work buffers
 	float* d_work = nullptr; size_t workCap = 0;      // points + outputs for the host-buffer entry point
@@ -83,13 +83,13 @@ extern "C" nmc_scene* nmc_scene_create(int dim, const float* verts, int nV, cons
 	v.absorption = opts->absorptionCoeff; v.watertight = opts->isWatertight != 0; v.doubleSided = opts->isDoubleSided != 0;
 	bool ok = upload(s->d_nodes, s->flat.nodes) == cudaSuccess && upload(s->d_prims, s->flat.prims) == cudaSuccess &&
 			  upload(s->d_primN, s->flat.primN) == cudaSuccess && upload(s->d_nrmV, s->flat.nrmV) == cudaSuccess &&
-			  upload(s->d_sils, s->flat.sils) == cudaSuccess && upload(s->d_silsU, s->flat.silsU) == cudaSuccess && upload(s->d_grpP, s->flat.grpP) == cudaSuccess && upload(s->d_grpS, s->flat.grpS) == cudaSuccess &&
+			  upload(s->d_sils, s->flat.sils) == cudaSuccess && upload(s->d_silsU, s->flat.silsU) == cudaSuccess && upload(s->d_grpP, s->flat.grpP) == cudaSuccess && upload(s->d_grpS, s->flat.grpS) == cudaSuccess && upload(s->d_rayP, s->flat.rayP) == cudaSuccess && upload(s->d_rayN, s->flat.rayN) == cudaSuccess &&
 			  cudaMalloc((void**)&s->d_counters, sizeof(Counters)) == cudaSuccess &&
 			  cudaMalloc((void**)&s->d_workCounter, sizeof(unsigned int)) == cudaSuccess;
 	for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&s->ev[i]) == cudaSuccess;
 	if (!ok) { fail(NMC_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError())); nmc_scene_destroy(s); return nullptr; }
 	v.nodes = s->d_nodes; v.prims = s->d_prims; v.primN = s->d_primN; v.nrmV = s->d_nrmV; v.sils = s->d_sils;
-	v.silsU = s->d_silsU; v.nSilU = s->flat.nSilU; v.grpP = s->d_grpP; v.grpS = s->d_grpS;
+	v.silsU = s->d_silsU; v.nSilU = s->flat.nSilU; v.grpP = s->d_grpP; v.grpS = s->d_grpS; v.rayP = s->d_rayP; v.rayN = s->d_rayN; v.nRay = s->flat.nRay;
 	if (setSource(s, src, n0, n1, n2, 0) != NMC_OK) { nmc_scene_destroy(s); return nullptr; }
 	return s;
 }
@@ -97,7 +97,7 @@ extern "C" nmc_scene* nmc_scene_create(int dim, const float* verts, int nV, cons
 extern "C" void nmc_scene_destroy(nmc_scene* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
-	cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_primN); cudaFree(s->d_nrmV); cudaFree(s->d_sils); cudaFree(s->d_silsU); cudaFree(s->d_grpP); cudaFree(s->d_grpS);
+	cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_primN); cudaFree(s->d_nrmV); cudaFree(s->d_sils); cudaFree(s->d_silsU); cudaFree(s->d_grpP); cudaFree(s->d_grpS); cudaFree(s->d_rayP); cudaFree(s->d_rayN);
 	cudaFree(s->d_src); cudaFree(s->d_work); cudaFree(s->d_lhs); cudaFree(s->d_counters); cudaFree(s->d_workCounter);
 	for (int i = 0; i < 4; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	cudaGetLastError();

@@ -34,7 +34,8 @@ struct SceneView {
 	const float4* nrmV;
 	const float4* sils;
 	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
-	const float4* grpP; const float4* grpS; // (lo, hi) per group of 8 primitives / silhouettes
+	const float4* grpP; const float4* grpS; // (lo, hi) per group of 8 ray primitives / silhouettes
+	const float4* rayP; const float4* rayN; int nRay; // ray-scan primitives (2D: collinear chains merged)
 	float bboxLo[3], bboxHi[3];
 	const float* src; int n0, n1, n2;
 	float absorption; int watertight, doubleSided;
@@ -518,17 +519,17 @@ NMC_HD bool flatClosestSilhouette(const SceneView& S, V3 x, float r2, bool flip,
 template <int DIM>
 NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
 	int best = -1; float bu = 0.0f, bv = 0.0f;
-	const int gp = S.nPrims > 16 ? 8 : 16;
-	for (int g0 = 0; g0 < S.nPrims; g0 += gp) {
+	const int gp = S.nRay > 16 ? 8 : 16;
+	for (int g0 = 0; g0 < S.nRay; g0 += gp) {
 		if (gp == 8) { // the ray is at most tMax long: skip groups farther than that from its origin (warp-coherent, see above)
 			float dmin, dmax;
 			boxSqDist(xyz(S.grpP[g0 >> 2]), xyz(S.grpP[(g0 >> 2) + 1]), o, dmin, dmax);
 			if (dmin > tMax*tMax) continue;
 		}
-		const int g1 = g0 + gp < S.nPrims ? g0 + gp : S.nPrims;
+		const int g1 = g0 + gp < S.nRay ? g0 + gp : S.nRay;
 	for (int i = g0; i < g1; i++) {
 		if (DIM == 2) {
-			float4 q = S.prims[i];
+			float4 q = S.rayP[i];
 			float ux = q.x - o.x, uy = q.y - o.y, vx = q.z - q.x, vy = q.w - q.y;
 			float dv = dir.x*vy - dir.y*vx;
 			if (fabsf(dv) <= kEps) continue;
@@ -536,7 +537,7 @@ NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
 			float s = (ux*dir.y - uy*dir.x)*inv, t = (ux*vy - uy*vx)*inv;
 			if (s >= 0.0f && s <= 1.0f && t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = s; }
 		} else {
-			V3 pa = xyz(S.prims[3*i]), v1 = xyz(S.prims[3*i + 1]) - pa, v2 = xyz(S.prims[3*i + 2]) - pa;
+			V3 pa = xyz(S.rayP[3*i]), v1 = xyz(S.rayP[3*i + 1]) - pa, v2 = xyz(S.rayP[3*i + 2]) - pa;
 			V3 p = cross(dir, v2);
 			float det = dot(v1, p);
 			if (fabsf(det) <= kEps) continue;
@@ -553,10 +554,10 @@ NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
 	}
 	}
 	if (best < 0) return false;
-	out.d = tMax; out.ref = best; out.n = xyz(S.primN[best]);
-	if (DIM == 2) { float4 q = S.prims[best]; out.p = mk(q.x + bu*(q.z - q.x), q.y + bu*(q.w - q.y), 0.0f); out.u = bu; out.v = -1.0f; }
+	out.d = tMax; out.ref = best; out.n = xyz(S.rayN[best]);
+	if (DIM == 2) { float4 q = S.rayP[best]; out.p = mk(q.x + bu*(q.z - q.x), q.y + bu*(q.w - q.y), 0.0f); out.u = bu; out.v = -1.0f; }
 	else {
-		V3 pa = xyz(S.prims[3*best]), v1 = xyz(S.prims[3*best + 1]) - pa, v2 = xyz(S.prims[3*best + 2]) - pa;
+		V3 pa = xyz(S.rayP[3*best]), v1 = xyz(S.rayP[3*best + 1]) - pa, v2 = xyz(S.rayP[3*best + 2]) - pa;
 		out.p = (pa + v1*bu) + v2*bv; out.u = 1.0f - bu - bv; out.v = bu;
 	}
 	return true;

@@ -362,6 +362,42 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 			out.nSilU++;
 		}
 	}
+	// ray-scan primitives (default mode): merge chains of connected, collinear, equally oriented 2D segments
+	if (dim == 2) {
+		std::vector<int> outSeg(nV, -1), inSeg(nV, -1), degOut(nV, 0), degIn(nV, 0);
+		for (int i = 0; i < nP; i++) { int a = B.prim[2*i], b = B.prim[2*i + 1]; outSeg[a] = i; degOut[a]++; inSeg[b] = i; degIn[b]++; }
+		auto collinear = [&](int i, int j) { // segment i ends where j starts
+			P3 u = B.pos[B.prim[2*i + 1]] - B.pos[B.prim[2*i]], v = B.pos[B.prim[2*j + 1]] - B.pos[B.prim[2*j]];
+			float cr = u.x*v.y - u.y*v.x, dt = u.x*v.x + u.y*v.y;
+			return dt > 0.0f && std::fabs(cr) <= 1e-6f*std::sqrt(dot(u, u)*dot(v, v));
+		};
+		std::vector<char> used(nP, 0);
+		for (int i = 0; i < nP; i++) {
+			if (used[i]) continue;
+			int first = i, lastSeg = i;
+			used[i] = 1;
+			for (;;) { // grow backwards
+				int a = B.prim[2*first];
+				if (degIn[a] != 1 || degOut[a] != 1) break;
+				int pr = inSeg[a];
+				if (pr < 0 || used[pr] || !collinear(pr, first)) break;
+				used[pr] = 1; first = pr;
+			}
+			for (;;) { // grow forwards
+				int b = B.prim[2*lastSeg + 1];
+				if (degIn[b] != 1 || degOut[b] != 1) break;
+				int nx = outSeg[b];
+				if (nx < 0 || used[nx] || !collinear(lastSeg, nx)) break;
+				used[nx] = 1; lastSeg = nx;
+			}
+			const P3 &pa = B.pos[B.prim[2*first]], &pb = B.pos[B.prim[2*lastSeg + 1]];
+			P3 d = pb - pa, nn = unit({d.y, -d.x, 0.0f});
+			out.rayP.push_back({pa.x, pa.y, pb.x, pb.y});
+			out.rayN.push_back({nn.x, nn.y, 0.0f, 0.0f});
+		}
+		out.nRay = (int)out.rayN.size();
+	} else { out.rayP = out.prims; out.rayN = out.primN; out.nRay = nP; }
+
 	// group boxes for the flat scans (tree order keeps neighbours together)
 	auto groupBoxes = [&](const std::vector<Q4>& rec, int perItem, int nItems, int ptsPerItem, std::vector<Q4>& outBoxes) {
 		for (int g0 = 0; g0 < nItems; g0 += 8) {
@@ -375,7 +411,7 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 			outBoxes.push_back({lo[0], lo[1], lo[2], 0.0f}); outBoxes.push_back({hi[0], hi[1], hi[2], 0.0f});
 		}
 	};
-	groupBoxes(out.prims, dim == 2 ? 1 : 3, nP, dim == 2 ? 1 : 3, out.grpP);
+	groupBoxes(out.rayP, dim == 2 ? 1 : 3, out.nRay, dim == 2 ? 1 : 3, out.grpP);
 	groupBoxes(out.silsU, dim == 2 ? 2 : 4, out.nSilU, dim == 2 ? 1 : 2, out.grpS); // 2D: the vertex; 3D: both edge end points
 }
 

@@ -20,6 +20,10 @@ struct FlatScene {
 	int nSilU = 0;
 	// flat-scan culling boxes: one (lo, hi) pair per group of 8 consecutive primitives / distinct silhouettes
 	std::vector<Q4> grpP, grpS;
+	// ray-scan primitives of the default mode: in 2D, chains of connected collinear segments are merged into one
+	// segment (a subdivided straight wall is one ray target); in 3D a copy of `prims`.  rayN: unit normals.
+	std::vector<Q4> rayP, rayN;
+	int nRay = 0;
 	float bboxLo[3] = {0, 0, 0}, bboxHi[3] = {0, 0, 0};
 };
 

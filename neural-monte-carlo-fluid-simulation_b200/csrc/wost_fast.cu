@@ -100,13 +100,20 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP;
 		if (FLAT) {
 			S.silsU = stage + qN + qP + qF;
-			const int qGP = 2*((Sg.nPrims + 7)/8), qGS = 2*((Sg.nSilU + 7)/8);
+			const int qGP = 2*((Sg.nRay + 7)/8), qGS = 2*((Sg.nSilU + 7)/8);
 			float4* gp = stage + qN + qP + qF + qS;
 #pragma unroll 1
 			for (int i = threadIdx.x; i < qGP; i += kBlock) gp[i] = Sg.grpP[i];
 #pragma unroll 1
 			for (int i = threadIdx.x; i < qGS; i += kBlock) gp[qGP + i] = Sg.grpS[i];
 			S.grpP = gp; S.grpS = gp + qGP;
+			const int qRP = (DIM == 2 ? 1 : 3)*Sg.nRay;
+			float4* rp = gp + qGP + qGS;
+#pragma unroll 1
+			for (int i = threadIdx.x; i < qRP; i += kBlock) rp[i] = Sg.rayP[i];
+#pragma unroll 1
+			for (int i = threadIdx.x; i < Sg.nRay; i += kBlock) rp[qRP + i] = Sg.rayN[i];
+			S.rayP = rp; S.rayN = rp + qRP;
 		} else S.sils = stage + qN + qP + qF;
 		__syncthreads();
 	}
@@ -376,7 +383,7 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	// small scenes are scanned flat (no per-step tree traversal)
 	const bool flat = S.nPrims <= 128 && S.nSilU <= 128;
 	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? S.nSilU : S.nSilRefs)
-				 + (flat ? (size_t)2*((S.nPrims + 7)/8) + (size_t)2*((S.nSilU + 7)/8) : 0);
+				 + (flat ? (size_t)2*((S.nRay + 7)/8) + (size_t)2*((S.nSilU + 7)/8) + (size_t)((dim == 2 ? 1 : 3) + 1)*S.nRay : 0);
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small

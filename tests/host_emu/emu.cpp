@@ -86,3 +86,9 @@ extern "C" void emu_star_radius(void* h, const float* pts, int n, float minR, co
 		else out[i] = starRadius<3, FastMath>(s->v, mk(pts[3*i], pts[3*i + 1], pts[3*i + 2]), minR, maxR[i], prec, flip != 0);
 	}
 }
+
+// sizes of the flattened structure: nodes, prims, silhouette refs, distinct silhouettes, ray primitives, depth
+extern "C" void emu_scene_info(void* h, int* out) {
+	EmuScene* s = (EmuScene*)h;
+	out[0] = s->flat.nNodes; out[1] = s->flat.nPrims; out[2] = s->flat.nSilRefs; out[3] = s->flat.nSilU; out[4] = s->flat.nRay; out[5] = s->flat.maxDepth;
+}

@@ -240,3 +240,16 @@ def test_siren_symbols_and_state_dict_layout():
         net(torch.zeros(4, 2))
     with pytest.raises(NotImplementedError):
         s.FusedSiren(2, 2, 6, 64, nonlinearity="relu")
+
+
+def test_flat_scan_tables_of_the_example_scenes(emu, oracle_lib):
+    """Host builder bookkeeping for the default-mode flat scans: distinct silhouettes and merged ray segments
+    (a straight wall subdivided into collinear segments is ONE ray target; the 40-gon cylinder is not merged)."""
+    expect = {"karman": (80, 42), "taylorgreen_active": (40, 4), "smoke3d": (12, 12), "karman3d": (10, 10)}
+    for case, (n_prims, n_ray) in expect.items():
+        h, _ = _emu_scene(emu, oracle_lib, util.load_case(case))
+        info = (C.c_int*6)()
+        emu.emu_scene_info(h, info)
+        assert info[1] == n_prims and info[4] == n_ray, (case, list(info))
+        assert info[3] <= info[2] and info[5] < 62
+        emu.emu_scene_destroy(h)
