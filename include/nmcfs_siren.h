@@ -50,6 +50,11 @@ int nmc_siren_backward(const nmc_siren_shape* shape, const float* const* W, cons
 					   int64_t n, const float* z_saved, const float* grad_y, float* dZ, float* A,
 					   float* grad_x, const nmc_siren_envelope* env, void* stream);
 
+/* Backward, stage 2: every weight / bias gradient from the dZ and A of nmc_siren_backward in one launch,
+ * accumulated (atomics over batch splits) into gW[l], gb[l], which the caller zero-fills. */
+int nmc_siren_weight_grads(const nmc_siren_shape* shape, const float* x, int64_t n, const float* dZ, const float* A,
+						   float* const* gW, float* const* gb, void* stream);
+
 /* Tensor-core forward (tcgen05, 3xTF32 split => fp32-level accuracy) for inference batches; same contract as
  * nmc_siren_forward without z_saved. Falls back to an error (never to another path) on unsupported shapes. */
 int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,

@@ -223,6 +223,89 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 	}
 }
 
+// Backward, stage 2: all weight and bias gradients in ONE launch.  Every gradient is C[i][j] = sum_s P[i][s] Q[j][s]
+// over the batch (P = dZ_l or the scaled output gradient, Q = A_{l-1} or x^T), so the grid is (K-splits, layers):
+// a CTA stages 32-sample tiles of its two operands in shared memory, accumulates a 4x4 register tile per thread
+// (hidden layers) or a strided set of scalars (first / last layer), and adds its partial result with atomics.
+constexpr int kGT = 256;   // threads
+constexpr int kGS = 32;    // samples per staged tile
+constexpr int kGChunk = 512; // samples per CTA
+template <int H>
+__global__ void __launch_bounds__(kGT)
+sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __restrict__ x, long long n,
+				const float* __restrict__ dZ, const float* __restrict__ A) {
+	__shared__ float Ps[H][kGS + 1];
+	__shared__ float Qs[H][kGS + 1];
+	const int tid = threadIdx.x;
+	const int l = blockIdx.y;                 // 0 .. nHidden + 1
+	const int last = nHidden + 1;
+	const long long s0 = (long long)blockIdx.x*kGChunk;
+	const long long s1 = s0 + kGChunk < n ? s0 + kGChunk : n;
+	const int RP = l == last ? outDim : H;    // rows of P
+	const int RQ = l == 0 ? inDim : H;        // rows of Q
+	const float* Pg = l == last ? dZ + (size_t)(nHidden + 1)*H*n : dZ + (size_t)l*H*n;
+	const float* Qg = l == 0 ? nullptr : A + (size_t)(l - 1)*H*n;
+	constexpr int NP = (H*H)/(16*kGT);        // 4x4 tiles per thread: 1 (H = 64) or 4 (H = 128)
+	constexpr int RB = (kGT/(H/4))*4;          // rows covered by one pass
+	float acc[NP][4][4];
+#pragma unroll
+	for (int q = 0; q < NP; q++)
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) acc[q][i][j] = 0.0f;
+	float small[(3*H + kGT - 1)/kGT];         // first/last layer: <= 3*H outputs
+#pragma unroll
+	for (int q = 0; q < (3*H + kGT - 1)/kGT; q++) small[q] = 0.0f;
+	float bsum = 0.0f;
+	const bool hidden = l >= 1 && l <= nHidden;
+	const int ti = (tid/(H/4))*4, tj = (tid%(H/4))*4; // 4x4 tile origin (H = 64: 16x16 threads; H = 128: uses two passes)
+	for (long long sb = s0; sb < s1; sb += kGS) {
+		const int ns = (int)(s1 - sb < kGS ? s1 - sb : kGS);
+		__syncthreads();
+		for (int idx = tid; idx < RP*kGS; idx += kGT) { int r = idx/kGS, c = idx - r*kGS; Ps[r][c] = c < ns ? Pg[(size_t)r*n + sb + c] : 0.0f; }
+		if (l == 0) { for (int idx = tid; idx < kGS*inDim; idx += kGT) { int c = idx/inDim, r = idx - c*inDim; Qs[r][c] = c < ns ? x[(sb + c)*inDim + r] : 0.0f; } }
+		else { for (int idx = tid; idx < RQ*kGS; idx += kGT) { int r = idx/kGS, c = idx - r*kGS; Qs[r][c] = c < ns ? Qg[(size_t)r*n + sb + c] : 0.0f; } }
+		__syncthreads();
+		if (hidden) {
+#pragma unroll 4
+			for (int c = 0; c < kGS; c++) {
+				float q0 = Qs[tj][c], q1 = Qs[tj + 1][c], q2 = Qs[tj + 2][c], q3 = Qs[tj + 3][c];
+#pragma unroll
+				for (int ps = 0; ps < NP; ps++) {
+					const int i0 = ti + ps*RB;
+					float p0 = Ps[i0][c], p1 = Ps[i0 + 1][c], p2 = Ps[i0 + 2][c], p3 = Ps[i0 + 3][c];
+					acc[ps][0][0] += p0*q0; acc[ps][0][1] += p0*q1; acc[ps][0][2] += p0*q2; acc[ps][0][3] += p0*q3;
+					acc[ps][1][0] += p1*q0; acc[ps][1][1] += p1*q1; acc[ps][1][2] += p1*q2; acc[ps][1][3] += p1*q3;
+					acc[ps][2][0] += p2*q0; acc[ps][2][1] += p2*q1; acc[ps][2][2] += p2*q2; acc[ps][2][3] += p2*q3;
+					acc[ps][3][0] += p3*q0; acc[ps][3][1] += p3*q1; acc[ps][3][2] += p3*q2; acc[ps][3][3] += p3*q3;
+				}
+			}
+		} else {
+			int q = 0;
+			for (int o = tid; o < RP*RQ; o += kGT, q++) {
+				int i = o/RQ, j = o - i*RQ;
+				float a = 0.0f;
+				for (int c = 0; c < kGS; c++) a += Ps[i][c]*Qs[j][c];
+				small[q] += a;
+			}
+		}
+		if (tid < RP) { float a = 0.0f; for (int c = 0; c < kGS; c++) a += Ps[tid][c]; bsum += a; }
+	}
+	if (hidden) {
+#pragma unroll
+		for (int ps = 0; ps < NP; ps++)
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) atomicAdd(&P.gW[l][(ti + ps*RB + i)*H + tj + j], acc[ps][i][j]);
+	} else {
+		int q = 0;
+		for (int o = tid; o < RP*RQ; o += kGT, q++) atomicAdd(&P.gW[l][o], small[q]);
+	}
+	if (tid < RP) atomicAdd(&P.gb[l][tid], bsum);
+}
+
 // torch.optim.Adam (no amsgrad, no weight decay) over one flat buffer; step is 1-based
 __global__ void adamKernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
 						   long long n, float lr, float b1, float b2, float eps, float bc1, float bc2sqrt) {
@@ -320,6 +403,23 @@ extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const*
 		if (!e) sirenBackwardChain<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
 	}
 	if (!e) e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_siren_weight_grads(const nmc_siren_shape* sh, const float* x, int64_t n, const float* dZ, const float* A,
+									  float* const* gW, float* const* gb, void* stream) {
+	if (!sh || !gW || !gb) return fail("null argument");
+	if (sh->hidden != 64 && sh->hidden != 128) return fail("hidden_features must be 64 or 128");
+	if (sh->n_hidden_layers < 0 || sh->n_hidden_layers + 2 > kMaxLayers) return fail("too many layers");
+	if (n <= 0) return 0;
+	if (!x || !dZ || !A) return fail("null buffer");
+	Params P;
+	for (int l = 0; l < sh->n_hidden_layers + 2; l++) { P.W[l] = nullptr; P.b[l] = nullptr; P.gW[l] = gW[l]; P.gb[l] = gb[l]; if (!gW[l] || !gb[l]) return fail("null layer pointer"); }
+	dim3 grid((unsigned)((n + kGChunk - 1)/kGChunk), (unsigned)(sh->n_hidden_layers + 2));
+	cudaStream_t st = (cudaStream_t)stream;
+	if (sh->hidden == 64) sirenWeightGrad<64><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A);
+	else sirenWeightGrad<128><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A);
+	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
 

@@ -48,6 +48,7 @@ def _lib():
         L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_backward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp,
                                          vp, vp, vp, C.POINTER(Envelope), vp]
+        L.nmc_siren_weight_grads.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         _configured = True
     return L
@@ -124,19 +125,19 @@ def _backward_chain(sh, W, b, x2, n, z, gy2, gx, env):
 
 
 def _param_grads(sh, x2, n, dZ, A, out=None):
-    """Weight gradients = GEMMs over the batch dimension (one batched cuBLAS call for the hidden layers):
-    dW_0 = dZ_0 x, dW_l = dZ_l A_{l-1}^T, dW_last = gy'^T A_L^T, db_l = rowsum(dZ_l)."""
+    """All weight / bias gradients in one launch (csrc/siren.cu sirenWeightGrad): batch-dimension GEMMs
+    dW_0 = dZ_0 x, dW_l = dZ_l A_{l-1}^T, dW_last = gy'^T A_L^T, db_l = rowsum(dZ_l), accumulated with atomics
+    into zero-filled buffers.  `out` = (gW0, gb0, gWh[L,H,H], gbh[L,H], gWl, gbl) already zeroed, or None."""
     H, Lh = sh.hidden, sh.n_hidden_layers
-    rows = (Lh + 1)*H
-    dZv, Av, gyT = dZ[:rows].view(Lh + 1, H, n), A.view(Lh + 1, H, n), dZ[rows:]
     if out is None:
-        return (dZv[0] @ x2, dZv[0].sum(dim=1), torch.bmm(dZv[1:], Av[:-1].transpose(1, 2)), dZv[1:].sum(dim=2),
-                gyT @ Av[Lh].t(), gyT.sum(dim=1))
+        dev = x2.device
+        out = (torch.zeros((H, sh.in_dim), device=dev), torch.zeros(H, device=dev), torch.zeros((Lh, H, H), device=dev),
+               torch.zeros((Lh, H), device=dev), torch.zeros((sh.out_dim, H), device=dev), torch.zeros(sh.out_dim, device=dev))
     gW0, gb0, gWh, gbh, gWl, gbl = out
-    torch.matmul(dZv[0], x2, out=gW0); torch.sum(dZv[0], dim=1, out=gb0)
-    if Lh > 0:
-        torch.bmm(dZv[1:], Av[:-1].transpose(1, 2), out=gWh); torch.sum(dZv[1:], dim=2, out=gbh)
-    torch.matmul(gyT, Av[Lh].t(), out=gWl); torch.sum(gyT, dim=1, out=gbl)
+    gW = [gW0] + [gWh[i] for i in range(Lh)] + [gWl]
+    gb = [gb0] + [gbh[i] for i in range(Lh)] + [gbl]
+    with torch.cuda.device(x2.device):
+        _check(_lib().nmc_siren_weight_grads(C.byref(sh), x2.data_ptr(), n, dZ.data_ptr(), A.data_ptr(), _ptrs(gW), _ptrs(gb), _stream()))
     return out
 
 
@@ -290,6 +291,7 @@ class DirectFit:
         diff = y - target
         gy = diff*(2.0/diff.numel())
         dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)
+        self.opt.g.zero_()
         _param_grads(sh, x, n, dZ, A, out=self.out)
         self.opt.step_flat()
         return diff
