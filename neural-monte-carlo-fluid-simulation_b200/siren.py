@@ -107,10 +107,13 @@ class _SirenFn(torch.autograd.Function):
         gy2 = gy.reshape(n, sh.out_dim).contiguous().float()
         gx = torch.empty_like(x2) if ctx.x_needs else None
         dZ, A = _backward_chain(sh, W, b, x2, n, z, gy2, gx, ctx.env)
+        gxr = gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None
+        if not any(ctx.needs_input_grad[5:]):  # e.g. the divergence of a frozen network: only dL/dx is wanted
+            return (gxr, None, None, None, None) + (None,)*(2*ctx.n_layers)
         gW0, gb0, gWh, gbh, gWl, gbl = _param_grads(sh, x2, n, dZ, A)
         gW = [gW0] + list(gWh.unbind(0)) + [gWl]
         gb = [gb0] + list(gbh.unbind(0)) + [gbl]
-        return (gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None, None, None, None, None, *gW, *gb)
+        return (gxr, None, None, None, None, *gW, *gb)
 
 
 def _backward_chain(sh, W, b, x2, n, z, gy2, gx, env):

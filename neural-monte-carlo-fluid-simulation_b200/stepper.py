@@ -162,7 +162,11 @@ class SplitStepper:
 
     def project_velocity(self, n_iters=None):
         samples_all = self.sample_random(self.wost_resolution**2).contiguous()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         p, grad_p = self.pressure_solve(samples_all)
+        e1.record(); e1.synchronize()
+        self.last["pressure_ms"] = e0.elapsed_time(e1)
         self.last.update(p=p, grad_p=grad_p, pressure_samples=samples_all)
         n, big = self.sample_resolution**2, samples_all.shape[0]
 
