@@ -119,7 +119,7 @@ def test_deterministic_mode_against_reference_vectors(pkg, case, oracle_lib):
     assert util.close_mask(p, op).mean() >= 0.99 and util.close_mask(g, og).mean() >= 0.99
 
 
-@pytest.mark.parametrize("case", ["taylorgreen_active", "karman", "smoke3d", "karman3d"])
+@pytest.mark.parametrize("case", ["taylorgreen_active", "karman", "smoke3d", "karman3d", "channel_circle", "box_sphere"])
 def test_fast_mode_matches_reference_statistically(pkg, case):
     """north_star criterion 2: default mode vs the reference's per-point means within 3 standard errors,
     variance ratios near 1 (the reference's means/variances come from the golden vectors' SampleStatistics)."""

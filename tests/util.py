@@ -20,6 +20,9 @@ CASES = {
     "karman": ("karman", {}),
     "smoke3d": ("smoke3d", {}),
     "karman3d": ("karman3d", {}),
+    # SURVEY 8(d) M-BVH: > 128 primitives, so the default mode walks the tree (tests/golden/make_synthetic_scenes.py)
+    "channel_circle": ("channel_circle", {}),
+    "box_sphere": ("box_sphere", {}),
 }
 
 
