@@ -8,10 +8,11 @@
 //     lanes through a ballot/popc compaction: every loop trip, lanes whose pair has finished are
 //     ranked with __ballot_sync/__popc and take the next pair indices, so lanes whose walks have
 //     terminated are refilled immediately instead of idling until the longest walk ends;
-//   * every loop trip each busy lane executes exactly one "slice": either the first-ball source sample
-//     of a new pair or one walk-on-stars step.  Both slice kinds share the expensive part (radial
-//     inverse-CDF sample of the ball Green's function + source-grid gather), so the warp stays
-//     converged there and only diverges in the geometric queries;
+//   * every loop trip each busy lane executes exactly one walk-on-stars step (geometric queries, radial
+//     inverse-CDF sample of the ball Green's function, source-grid gather, bookkeeping);
+//   * the first-ball source samples of a point (one per antithetic pair, all in the SAME ball, no geometry)
+//     are not interleaved with the steps: they are computed 32 pairs at a time by the whole warp in
+//     converged code, parked in shared memory, and picked up by whichever lane is handed the pair;
 //   * the boundary structure (nodes, primitives, face normals, silhouettes; 16-byte records) is staged
 //     in shared memory once per CTA when it fits, and read with vectorised loads;
 //   * per-point estimates are reduced in registers/shared memory: control variates come from warp-wide
@@ -62,7 +63,8 @@ __device__ __forceinline__ unsigned warpSumU(unsigned v) {
 	return v;
 }
 
-enum LaneState { kNeedPair = 0, kFirstBall = 1, kWalking = 2, kIdle = 3 };
+enum LaneState { kNeedPair = 0, kWalking = 2, kIdle = 3 };
+static constexpr int kFbFields = 8; // first-ball record per pair: d0.xyz, e0.xyz, firstSource, sfr
 
 #ifndef NMC_MINB
 #define NMC_MINB 8   // 64 registers/thread, 32 warps/SM: measured best on B200 (profiles/README.md)
@@ -82,6 +84,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	// per-thread traversal stack in shared memory, interleaved across the CTA (after the staged scene)
 	STACK stack;
 	stackInit(stack, reinterpret_cast<int*>(stage + stageQuads), stackSlots);
+	// first-ball chunk of this warp: [field][lane] floats, behind the stacks
+	float* fbuf = reinterpret_cast<float*>(stage + stageQuads) + (size_t)2*stackSlots*kBlock + (threadIdx.x >> 5)*(kFbFields*32);
 
 	// ---- stage the boundary structure in shared memory ------------------------------------------------
 	SceneView S = Sg;
@@ -158,7 +162,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 			float pendTot = 0.0f, pendCnt = 0.0f, pendFirst = 0.0f; // this lane's finished walks not yet folded in
 
 			int state = kNeedPair;
-			int nextPair = 0;          // warp-uniform
+			int nextPair = 0, chunkBase = 0, chunkEnd = 0; // warp-uniform; pairs [chunkBase, chunkEnd) are parked in fbuf
 			int pair = 0, anti = 0, walkLength = 0;
 			bool onNeumann = false;
 			Pcg32 rng; rng.state = 0; rng.inc = 1;
@@ -175,44 +179,81 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						cvTot += warpSum(pendTot); cvCnt += warpSum(pendCnt); cvFirst += warpSum(pendFirst);
 						pendTot = pendCnt = pendFirst = 0.0f;
 					}
+					const int mine = nextPair + __popc(need & ltMask), total = __popc(need);
+					const int lastNeeded = nextPair + total < nPairs ? nextPair + total : nPairs;
+					const bool want = state == kNeedPair && mine < nPairs;
+					bool fetched = false;
+#define NMC_FETCH_FIRST_BALL(slot) do { const int sl_ = (slot); \
+						d0 = mk(fbuf[sl_], fbuf[32 + sl_], DIM == 3 ? fbuf[64 + sl_] : 0.0f); \
+						e0 = mk(fbuf[96 + sl_], fbuf[128 + sl_], DIM == 3 ? fbuf[160 + sl_] : 0.0f); \
+						firstSource = fbuf[192 + sl_]; sfr = fbuf[224 + sl_]; fetched = true; } while (0)
+					if (want && mine < chunkEnd) NMC_FETCH_FIRST_BALL(mine - chunkBase);
+					if (lastNeeded > chunkEnd) {
+						// ---- first-ball source samples of the next 32 pairs, one per lane, converged ---------------
+						__syncwarp();
+						chunkBase = chunkEnd; chunkEnd = chunkBase + 32 < nPairs ? chunkBase + 32 : nPairs;
+						const int cp = chunkBase + lane;
+						if (cp < chunkEnd) {
+							// stratified first-ball directions (generateStratifiedSamples, sampling.h:434-457):
+							// sample 2w drives the source direction, 2w+1 the boundary direction
+							const unsigned long long ws = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(cp + 1)));
+							Pcg32 r0; r0.state = splitmix64(ws ^ 0xA0761D6478BD642Full); r0.inc = 3;
+							float us0 = ((float)permute(2u*cp, nStrata, permKey0) + r0.nextFloat())*invStrata;
+							float ub0 = ((float)permute(2u*cp + 1u, nStrata, permKey0) + r0.nextFloat())*invStrata;
+							float us1 = 0.0f, ub1 = 0.0f;
+							if (DIM == 3) {
+								us1 = ((float)permute(2u*cp, nStrata, permKey1) + r0.nextFloat())*invStrata;
+								ub1 = ((float)permute(2u*cp + 1u, nStrata, permKey1) + r0.nextFloat())*invStrata;
+							}
+							const V3 sdir = sphereDir<DIM, M>(fminf(us0, 1.0f - kEps), fminf(us1, 1.0f - kEps));
+							const V3 be = firstR*sphereDir<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
+							const float uA = r0.nextFloat(), uB = r0.nextFloat();
+							float rs = 0.0f, fsrc = 0.0f, sf = 0.0f;
+							if (!o.ignoreSource) {
+								float gs, qs; bool hframe;
+								float xs = fb.sampleX(uA, uB, gs, qs, hframe);
+								rs = hframe ? xs*fb.R : xs/fb.mu;
+								rs = fminf(fmaxf(rs, 1e-4f), fb.R);        // rClamp, distributions.h:378-379
+								fsrc = normG0*sourceAt<DIM>(S, x0 + rs*sdir);
+								// sourceGradientDirection = d * gradientNorm / G(r)  (walk_on_stars.h:542)
+								sf = hframe ? fb.srcGradFactorHarmonic(xs) : fb.srcGradFactor(qs, gs);
+							}
+							fbuf[lane] = rs*sdir.x; fbuf[32 + lane] = rs*sdir.y; if (DIM == 3) fbuf[64 + lane] = rs*sdir.z;
+							fbuf[96 + lane] = be.x; fbuf[128 + lane] = be.y; if (DIM == 3) fbuf[160 + lane] = be.z;
+							fbuf[192 + lane] = fsrc; fbuf[224 + lane] = sf/fmaxf(rs, 1e-20f);
+						}
+						cTrips++; cLaneSlices += (unsigned)(chunkEnd - chunkBase);
+						__syncwarp();
+						if (want && !fetched) NMC_FETCH_FIRST_BALL(mine - chunkBase);
+					}
+#undef NMC_FETCH_FIRST_BALL
 					if (state == kNeedPair) {
-						int mine = nextPair + __popc(need & ltMask);
-						if (mine < nPairs) {
-							pair = mine; anti = 0; state = kFirstBall;
+						if (want) {
+							pair = mine; anti = 0;
 							if (o.useGradientControlVariates) { // running means over the walks finished so far
 								float icnt = 1.0f/fmaxf(cvCnt, 1.0f);
 								bcv = cvTot*icnt; scv = cvFirst*icnt;
 							}
 							walkSeed = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(pair + 1)));
+							// start antithetic walk 0 from the boundary sample
+							pt = x0 + e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = e0;
+							throughput = exitT; totalSource = firstSource;
+							rng.state = walkSeed; rng.inc = 1;
+							bl = fb;
+							state = kWalking; cStarted++;
 						} else state = kIdle;
 					}
-					nextPair += __popc(need);
+					nextPair += total;
 				}
-				const unsigned busy = __ballot_sync(kFull, state == kFirstBall || state == kWalking);
+				const unsigned busy = __ballot_sync(kFull, state == kWalking);
 				if (busy == 0u) break;
 				cTrips++; cLaneSlices += __popc(busy);
 
-				// ---- phase 1: geometry (walk steps only) --------------------------------------------------------
+				// ---- phase 1: geometry ---------------------------------------------------------------------------
 				V3 dir = mk(0, 0, 0), ipt = pt, inrm = mk(0, 0, 0);
 				float idist = 0.0f, uRad = 0.0f, uRad2 = 0.0f, uRR = 1.0f;
 				bool hit = false, sliceActive = false, terminated = false, completed = false;
-				if (state == kFirstBall) {
-					// stratified first-ball directions (generateStratifiedSamples, sampling.h:434-457):
-					// sample 2w drives the source direction, 2w+1 the boundary direction
-					Pcg32 r0; r0.state = splitmix64(walkSeed ^ 0xA0761D6478BD642Full); r0.inc = 3;
-					float us0 = ((float)permute(2u*pair, nStrata, permKey0) + r0.nextFloat())*invStrata;
-					float ub0 = ((float)permute(2u*pair + 1u, nStrata, permKey0) + r0.nextFloat())*invStrata;
-					float us1 = 0.0f, ub1 = 0.0f;
-					if (DIM == 3) {
-						us1 = ((float)permute(2u*pair, nStrata, permKey1) + r0.nextFloat())*invStrata;
-						ub1 = ((float)permute(2u*pair + 1u, nStrata, permKey1) + r0.nextFloat())*invStrata;
-					}
-					dir = sphereDir<DIM, M>(fminf(us0, 1.0f - kEps), fminf(us1, 1.0f - kEps));
-					e0 = firstR*sphereDir<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
-					uRad = r0.nextFloat(); uRad2 = r0.nextFloat();
-					bl = fb; idist = firstR; ipt = x0;
-					sliceActive = !o.ignoreSource;
-				} else if (state == kWalking) {
+				if (state == kWalking) {
 					cSteps++;
 					float dirichletDist = distDirichlet<DIM>(S, pt);
 					if (!(dirichletDist > o.epsilonShell)) { terminated = true; completed = true; }
@@ -260,26 +301,11 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 					xs = bl.sampleX(uRad, uRad2, gs, qs, hframe);
 					rs = hframe ? xs*bl.R : xs/bl.mu;
 					rs = fminf(fmaxf(rs, 1e-4f), bl.R);        // rClamp, distributions.h:378-379
-					if (rs <= idist) {
-						V3 c = state == kFirstBall ? x0 : pt;
-						contribution = bl.normG()*sourceAt<DIM>(S, c + rs*dir);
-					}
+					if (rs <= idist) contribution = bl.normG()*sourceAt<DIM>(S, pt + rs*dir);
 				}
 
 				// ---- phase 3: bookkeeping ---------------------------------------------------------------------
-				if (state == kFirstBall) {
-					d0 = rs*dir;
-					firstSource = contribution;
-					// sourceGradientDirection = d * gradientNorm / G(r)  (walk_on_stars.h:542)
-					float sf = sliceActive ? (hframe ? bl.srcGradFactorHarmonic(xs) : bl.srcGradFactor(qs, gs)) : 0.0f;
-					sfr = sf/fmaxf(rs, 1e-20f);
-					// start antithetic walk 0 from the boundary sample
-					pt = x0 + e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = e0;
-					throughput = exitT; totalSource = firstSource;
-					rng.state = walkSeed; rng.inc = 1;
-					bl = fb;
-					state = kWalking; cStarted++;
-				} else if (state == kWalking) {
+				if (state == kWalking) {
 					if (!terminated) {
 						totalSource += throughput*contribution;
 						if (!hit && outsideBox<DIM>(S, ipt)) terminated = true; // EscapedDomain: discarded
@@ -389,7 +415,8 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
 	int stackSlots = maxDepth + 3;
 	bool smemStack = stackSlots <= 24;
-	size_t smem = (stageQuads ? bytes : 0) + (smemStack ? (size_t)stackSlots*kBlock*8 : 0);
+	if (!smemStack) stackSlots = 0; // LocalStack: the first-ball chunks sit right behind the staged scene
+	size_t smem = (stageQuads ? bytes : 0) + (size_t)stackSlots*kBlock*8 + (size_t)kWarps*kFbFields*32*sizeof(float);
 	void (*kern)(SceneView, SolverParams, const float*, long long, unsigned long long, float*, float*, unsigned int*, Counters*, float*, int, int);
 	if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true> : fastKernel<3, StridedStack, true>;
 	else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false> : fastKernel<2, LocalStack, false>;
