@@ -251,7 +251,7 @@ struct BallExact {
 // k1e = e^x K1 from the Abramowitz-Stegun 9.8.1-9.8.8 fits (the ones bessel.hpp uses; |err| < 2e-7),
 // evaluated in float with the exponential factored out so that nothing overflows for large x.
 struct Bessel4 { float i0e, i1e, k0e, k1e; };
-NMC_TRAV Bessel4 besselScaled(float x) {
+NMC_OUTLINE Bessel4 besselScaled(float x) {
 	Bessel4 b;
 	if (x < 3.75f) {
 		float y = x*(1.0f/3.75f); y = y*y;

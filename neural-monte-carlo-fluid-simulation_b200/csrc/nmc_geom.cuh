@@ -34,8 +34,8 @@ struct SceneView {
 	const float4* nrmV;
 	const float4* sils;
 	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
-	const float4* grpP; const float4* grpS; // (lo, hi) per group of 8 ray primitives / silhouettes
-	const float4* rayP; const float4* rayN; int nRay; // ray-scan primitives (2D: collinear chains merged)
+	const float4* grpP; const float4* grpS; // (lo, hi) per group (8 in 2D, 4 in 3D) of ray primitives / silhouettes
+	const float4* rayP; const float4* rayN; int nRay; // ray-scan primitives as (origin, edge vectors); 2D: collinear chains merged; padded to whole groups
 	float bboxLo[3], bboxHi[3];
 	const float* src; int n0, n1, n2;
 	float absorption; int watertight, doubleSided;
@@ -467,97 +467,110 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 
 // ---- flat scans for small scenes (default mode only) ------------------------------------------------------
 // With a few dozen primitives the tree bookkeeping (stack traffic, box sorting, cone tests) costs more than it
-// saves, and it makes the lanes of a warp diverge.  These scans visit every record in the same order in every
-// lane (the loads are shared-memory broadcasts), reject on one squared distance / one determinant, and return
-// the same minimum as the traversals above (ties may pick another primitive of equal distance).
+// saves, and it makes the lanes of a warp diverge.  These scans visit the records group by group (8 in 2D, 4 in
+// 3D; the lists are padded to whole groups by scene_build.cpp), skip a group whose box is out of reach, and
+// return the same minimum as the traversals above (ties may pick another primitive of equal distance).
+// The tables live in shared memory: FlatTab's pointers are derived from the kernel's shared array only, so the
+// compiler emits LDS (no generic-address loads).
+template <int DIM> struct FlatGroup { static constexpr int n = DIM == 2 ? 8 : 4; };
+struct FlatTab {
+	const float4 *silsU, *grpS; int nSilU;   // distinct silhouettes, (lo, hi) per group
+	const float4 *rayP, *rayN, *grpP; int nRay; // ray primitives as (origin, edge vectors), unit normals, (lo, hi) per group
+};
 template <int DIM>
-NMC_HD bool flatClosestSilhouette(const SceneView& S, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
+NMC_HD float boxSqDistMin(float4 lo, float4 hi, V3 p) {
+	float ax = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f), ay = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f);
+	float d = ax*ax + ay*ay;
+	if (DIM == 3) { float az = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f); d += az*az; }
+	return d;
+}
+template <int DIM>
+NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
 	if (sqMinR >= r2) return false;
+	constexpr int G = FlatGroup<DIM>::n;
+	const float prec2 = precision*precision;
 	bool found = false;
-	const int gs = S.nSilU > 16 ? 8 : 16; // tiny lists are one group: no culling, no nest overhead
-	for (int g0 = 0; g0 < S.nSilU; g0 += gs) {
-		if (gs == 8) { // every lane of the warp sits near the same query point, so this cull is warp-coherent
-			float dmin, dmax;
-			boxSqDist(xyz(S.grpS[g0 >> 2]), xyz(S.grpS[(g0 >> 2) + 1]), x, dmin, dmax);
-			if (dmin > r2) continue;
+	for (int g0 = 0, gi = 0; g0 < F.nSilU; g0 += G, gi += 2) {
+		// every lane of the warp sits near the same query point, so this cull is nearly warp-coherent
+		if (boxSqDistMin<DIM>(F.grpS[gi], F.grpS[gi + 1], x) > r2) continue;
+#pragma unroll 1
+		for (int j = 0; j < G; j++) {
+			const int i = g0 + j;
+			if (DIM == 2) {
+				// SilhouetteVertex (vertex_silhouettes.inl:62-118) without normalising the view direction:
+				// |dot(v/d, n)| <= precision  <=>  dot(v, n)^2 <= precision^2 d^2; the exact rules only run in that band
+				const float4 s0 = F.silsU[2*i], s1 = F.silsU[2*i + 1];
+				const float vx = x.x - s0.x, vy = x.y - s0.y;
+				const float d2 = vx*vx + vy*vy;
+				const float dot0 = vx*s1.x + vy*s1.y, dot1 = vx*s1.z + vy*s1.w;
+				const float pd2 = prec2*d2;
+				bool isSil = (asInt(s0.z) & 3) != 3;
+				const bool band = dot0*dot0 <= pd2 || dot1*dot1 <= pd2 || d2 <= prec2;
+				if (band && !isSil) isSil = isSilhouette(s1.x*s1.w - s1.z*s1.y, mk(s1.x, s1.y, 0.0f), mk(s1.z, s1.w, 0.0f), mk(vx, vy, 0.0f), sqrtf(d2), flip, precision);
+				else isSil = isSil || dot0*dot1 < 0.0f;
+				if (isSil && d2 <= r2) { found = true; r2 = d2; }
+			} else {
+				const float4 s0 = F.silsU[4*i], s1 = F.silsU[4*i + 1];
+				V3 pt; float t;
+				const float d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
+				const float d2 = d*d;
+				if (d2 > r2) continue;
+				bool isSil = (asInt(s0.w) & 3) != 3;
+				if (!isSil) {
+					const float4 s2 = F.silsU[4*i + 2];
+					isSil = isSilhouette(s2.w, xyz(s2), xyz(F.silsU[4*i + 3]), x - pt, d, flip, precision);
+				}
+				if (isSil) { found = true; r2 = d2; }
+			}
 		}
-		const int g1 = g0 + gs < S.nSilU ? g0 + gs : S.nSilU;
-	for (int i = g0; i < g1; i++) {
-		V3 viewDir, n0, n1; float d2, concavity; int flags;
-		if (DIM == 2) {
-			float4 s0 = S.silsU[2*i];
-			viewDir = x - mk(s0.x, s0.y, 0.0f);
-			d2 = dot(viewDir, viewDir);
-			if (d2 > r2) continue;
-			float4 s1 = S.silsU[2*i + 1];
-			flags = asInt(s0.z);
-			n0 = mk(s1.x, s1.y, 0.0f); n1 = mk(s1.z, s1.w, 0.0f);
-			concavity = n0.x*n1.y - n1.x*n0.y;
-		} else {
-			float4 s0 = S.silsU[4*i], s1 = S.silsU[4*i + 1];
-			V3 pt; float t;
-			float d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
-			d2 = d*d;
-			if (d2 > r2) continue;
-			viewDir = x - pt;
-			flags = asInt(s0.w);
-			float4 s2 = S.silsU[4*i + 2];
-			n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.silsU[4*i + 3]);
-		}
-		bool isSil = (flags & 3) != 3;
-		if (!isSil) isSil = isSilhouette(concavity, n0, n1, viewDir, sqrtf(d2), flip, precision);
-		if (isSil) {
-			found = true; r2 = d2;
-			if (sqMinR >= r2) break;
-		}
-	}
 		if (sqMinR >= r2) break;
 	}
 	if (found) dOut = sqrtf(r2);
 	return found;
 }
 template <int DIM>
-NMC_HD bool flatRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
+NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
+	constexpr int G = FlatGroup<DIM>::n;
 	int best = -1; float bu = 0.0f, bv = 0.0f;
-	const int gp = S.nRay > 16 ? 8 : 16;
-	for (int g0 = 0; g0 < S.nRay; g0 += gp) {
-		if (gp == 8) { // the ray is at most tMax long: skip groups farther than that from its origin (warp-coherent, see above)
-			float dmin, dmax;
-			boxSqDist(xyz(S.grpP[g0 >> 2]), xyz(S.grpP[(g0 >> 2) + 1]), o, dmin, dmax);
-			if (dmin > tMax*tMax) continue;
+	for (int g0 = 0, gi = 0; g0 < F.nRay; g0 += G, gi += 2) {
+		// the ray is at most tMax long: skip groups farther than that from its origin
+		if (boxSqDistMin<DIM>(F.grpP[gi], F.grpP[gi + 1], o) > tMax*tMax) continue;
+#pragma unroll 1
+		for (int j = 0; j < G; j++) {
+			const int i = g0 + j;
+			if (DIM == 2) { // LineSegment::intersect (line_segments.inl:96-140); the division only runs for hits
+				const float4 q = F.rayP[i];
+				const float ux = q.x - o.x, uy = q.y - o.y;
+				const float dv = dir.x*q.w - dir.y*q.z;
+				const float a = ux*dir.y - uy*dir.x, b = ux*q.w - uy*q.z;
+				const float adv = fabsf(dv);
+				if (adv > kEps && a*dv >= 0.0f && fabsf(a) <= adv && b*dv >= 0.0f && fabsf(b) <= tMax*adv) {
+					const float inv = 1.0f/dv;
+					const float s = a*inv, t = b*inv;
+					if (s >= 0.0f && s <= 1.0f && t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = s; }
+				}
+			} else { // Triangle::intersect (triangles.inl:96-160)
+				const V3 pa = xyz(F.rayP[3*i]), v1 = xyz(F.rayP[3*i + 1]), v2 = xyz(F.rayP[3*i + 2]);
+				const V3 p = cross(dir, v2);
+				const float det = dot(v1, p);
+				if (fabsf(det) <= kEps) continue;
+				const float inv = 1.0f/det;
+				const V3 sv = o - pa;
+				const float v = dot(sv, p)*inv;
+				if (v < 0.0f || v > 1.0f) continue;
+				const V3 qv = cross(sv, v1);
+				const float w = dot(dir, qv)*inv;
+				if (w < 0.0f || v + w > 1.0f) continue;
+				const float t = dot(v2, qv)*inv;
+				if (t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = v; bv = w; }
+			}
 		}
-		const int g1 = g0 + gp < S.nRay ? g0 + gp : S.nRay;
-	for (int i = g0; i < g1; i++) {
-		if (DIM == 2) {
-			float4 q = S.rayP[i];
-			float ux = q.x - o.x, uy = q.y - o.y, vx = q.z - q.x, vy = q.w - q.y;
-			float dv = dir.x*vy - dir.y*vx;
-			if (fabsf(dv) <= kEps) continue;
-			float inv = 1.0f/dv;
-			float s = (ux*dir.y - uy*dir.x)*inv, t = (ux*vy - uy*vx)*inv;
-			if (s >= 0.0f && s <= 1.0f && t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = s; }
-		} else {
-			V3 pa = xyz(S.rayP[3*i]), v1 = xyz(S.rayP[3*i + 1]) - pa, v2 = xyz(S.rayP[3*i + 2]) - pa;
-			V3 p = cross(dir, v2);
-			float det = dot(v1, p);
-			if (fabsf(det) <= kEps) continue;
-			float inv = 1.0f/det;
-			V3 sv = o - pa;
-			float v = dot(sv, p)*inv;
-			if (v < 0.0f || v > 1.0f) continue;
-			V3 qv = cross(sv, v1);
-			float w = dot(dir, qv)*inv;
-			if (w < 0.0f || v + w > 1.0f) continue;
-			float t = dot(v2, qv)*inv;
-			if (t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = v; bv = w; }
-		}
-	}
 	}
 	if (best < 0) return false;
-	out.d = tMax; out.ref = best; out.n = xyz(S.rayN[best]);
-	if (DIM == 2) { float4 q = S.rayP[best]; out.p = mk(q.x + bu*(q.z - q.x), q.y + bu*(q.w - q.y), 0.0f); out.u = bu; out.v = -1.0f; }
+	out.d = tMax; out.ref = best; out.n = xyz(F.rayN[best]);
+	if (DIM == 2) { const float4 q = F.rayP[best]; out.p = mk(q.x + bu*q.z, q.y + bu*q.w, 0.0f); out.u = bu; out.v = -1.0f; }
 	else {
-		V3 pa = xyz(S.rayP[3*best]), v1 = xyz(S.rayP[3*best + 1]) - pa, v2 = xyz(S.rayP[3*best + 2]) - pa;
+		const V3 pa = xyz(F.rayP[3*best]), v1 = xyz(F.rayP[3*best + 1]), v2 = xyz(F.rayP[3*best + 2]);
 		out.p = (pa + v1*bu) + v2*bv; out.u = 1.0f - bu - bv; out.v = bu;
 	}
 	return true;

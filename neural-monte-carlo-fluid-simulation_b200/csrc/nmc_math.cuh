@@ -27,6 +27,12 @@
 #else
 #define NMC_TRAV NMC_HD
 #endif
+// NMC_OUTLINE: one out-of-line copy in the default-mode kernels (instruction-cache footprint, see profiles/README.md)
+#if defined(NMC_FAST_GEOM) && defined(__CUDACC__) && !defined(NMC_NO_OUTLINE)
+#define NMC_OUTLINE __host__ __device__ __noinline__
+#else
+#define NMC_OUTLINE NMC_HD
+#endif
 
 namespace nmc {
 

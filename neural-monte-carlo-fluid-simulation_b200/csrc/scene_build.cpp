@@ -398,11 +398,12 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 		out.nRay = (int)out.rayN.size();
 	} else { out.rayP = out.prims; out.rayN = out.primN; out.nRay = nP; }
 
-	// group boxes for the flat scans (tree order keeps neighbours together)
+	// group boxes for the flat scans (tree order keeps neighbours together); group = 8 records in 2D, 4 in 3D
+	const int G = dim == 2 ? 8 : 4;
 	auto groupBoxes = [&](const std::vector<Q4>& rec, int perItem, int nItems, int ptsPerItem, std::vector<Q4>& outBoxes) {
-		for (int g0 = 0; g0 < nItems; g0 += 8) {
+		for (int g0 = 0; g0 < nItems; g0 += G) {
 			float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-			for (int i = g0; i < std::min(nItems, g0 + 8); i++) for (int q = 0; q < ptsPerItem; q++) {
+			for (int i = g0; i < std::min(nItems, g0 + G); i++) for (int q = 0; q < ptsPerItem; q++) {
 				const Q4& r = rec[(size_t)perItem*i + q];
 				float pts[2][3] = {{r.x, r.y, dim == 3 ? r.z : 0.0f}, {r.z, r.w, 0.0f}};
 				int np = (dim == 2 && perItem == 1) ? 2 : 1; // a 2D segment record packs both end points
@@ -413,6 +414,26 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 	};
 	groupBoxes(out.rayP, dim == 2 ? 1 : 3, out.nRay, dim == 2 ? 1 : 3, out.grpP);
 	groupBoxes(out.silsU, dim == 2 ? 2 : 4, out.nSilU, dim == 2 ? 1 : 2, out.grpS); // 2D: the vertex; 3D: both edge end points
+
+	// scan-friendly records (after the boxes, which need the end points):
+	//  * ray primitives become (origin, edge vectors): 2D (pa.xy, pb - pa), 3D (pa)(pb - pa)(pc - pa);
+	//  * both lists are padded to a whole number of groups with records no query can accept (a silhouette at
+	//    infinity, a degenerate primitive), so the scans run fixed-trip inner loops.
+	if (dim == 2) for (int i = 0; i < out.nRay; i++) { Q4& q = out.rayP[i]; q.z -= q.x; q.w -= q.y; }
+	else for (int i = 0; i < out.nRay; i++) {
+		Q4 &a = out.rayP[3*i], &b = out.rayP[3*i + 1], &c = out.rayP[3*i + 2];
+		b.x -= a.x; b.y -= a.y; b.z -= a.z; c.x -= a.x; c.y -= a.y; c.z -= a.z;
+	}
+	const float far = 1e30f; // (x - far)^2 overflows to +inf > any search radius
+	for (int i = out.nSilU; i % G != 0; i++) {
+		if (dim == 2) { out.silsU.push_back({far, far, bits(3), bits(-1)}); out.silsU.push_back({0, 0, 0, 0}); }
+		else { out.silsU.push_back({far, far, far, bits(3)}); out.silsU.push_back({far, far, far, bits(-1)}); out.silsU.push_back({0, 0, 0, 0}); out.silsU.push_back({0, 0, 0, 0}); }
+	}
+	for (int i = out.nRay; i % G != 0; i++) {
+		out.rayP.push_back({far, far, 0.0f, 0.0f}); // zero edge vectors: determinant 0, rejected
+		if (dim == 3) { out.rayP.push_back({0, 0, 0, 0}); out.rayP.push_back({0, 0, 0, 0}); }
+		out.rayN.push_back({0, 0, 0, 0});
+	}
 }
 
 } // namespace nmc

@@ -88,11 +88,15 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	float* fbuf = reinterpret_cast<float*>(stage + stageQuads) + (size_t)2*stackSlots*kBlock + (threadIdx.x >> 5)*(kFbFields*32);
 
 	// ---- stage the boundary structure in shared memory ------------------------------------------------
+	// layout: nodes | prims | primN | silhouettes | [FLAT: group boxes (ray, sil) | ray primitives | ray normals]
 	SceneView S = Sg;
-	if (stageQuads > 0) {
+	FlatTab F = {};
+	constexpr int G = FlatGroup<DIM>::n; // the flat-scan lists are padded to whole groups (scene_build.cpp)
+	const int nSilP = (Sg.nSilU + G - 1)/G*G, nRayP = (Sg.nRay + G - 1)/G*G;
+	if (FLAT || stageQuads > 0) { // FLAT scenes always fit (launchFast)
 		// FLAT: the de-duplicated silhouette list replaces the per-leaf references (the tree is only walked once per point)
 		const float4* silSrc = FLAT ? Sg.silsU : Sg.sils;
-		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*(FLAT ? Sg.nSilU : Sg.nSilRefs);
+		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*(FLAT ? nSilP : Sg.nSilRefs);
 #pragma unroll 1
 		for (int i = threadIdx.x; i < qN; i += kBlock) stage[i] = Sg.nodes[i];
 #pragma unroll 1
@@ -103,21 +107,20 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = silSrc[i];
 		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP;
 		if (FLAT) {
-			S.silsU = stage + qN + qP + qF;
-			const int qGP = 2*((Sg.nRay + 7)/8), qGS = 2*((Sg.nSilU + 7)/8);
-			float4* gp = stage + qN + qP + qF + qS;
+			const int qGP = 2*(nRayP/G), qGS = 2*(nSilP/G), qRP = (DIM == 2 ? 1 : 3)*nRayP;
+			const int oG = qN + qP + qF + qS, oR = oG + qGP + qGS;
 #pragma unroll 1
-			for (int i = threadIdx.x; i < qGP; i += kBlock) gp[i] = Sg.grpP[i];
+			for (int i = threadIdx.x; i < qGP; i += kBlock) stage[oG + i] = Sg.grpP[i];
 #pragma unroll 1
-			for (int i = threadIdx.x; i < qGS; i += kBlock) gp[qGP + i] = Sg.grpS[i];
-			S.grpP = gp; S.grpS = gp + qGP;
-			const int qRP = (DIM == 2 ? 1 : 3)*Sg.nRay;
-			float4* rp = gp + qGP + qGS;
+			for (int i = threadIdx.x; i < qGS; i += kBlock) stage[oG + qGP + i] = Sg.grpS[i];
 #pragma unroll 1
-			for (int i = threadIdx.x; i < qRP; i += kBlock) rp[i] = Sg.rayP[i];
+			for (int i = threadIdx.x; i < qRP; i += kBlock) stage[oR + i] = Sg.rayP[i];
 #pragma unroll 1
-			for (int i = threadIdx.x; i < Sg.nRay; i += kBlock) rp[qRP + i] = Sg.rayN[i];
-			S.rayP = rp; S.rayN = rp + qRP;
+			for (int i = threadIdx.x; i < nRayP; i += kBlock) stage[oR + qRP + i] = Sg.rayN[i];
+			// pointers derived from the shared array only: the scans compile to LDS
+			F.silsU = stage + (qN + qP + qF); F.nSilU = Sg.nSilU;
+			F.grpP = stage + oG; F.grpS = stage + (oG + qGP);
+			F.rayP = stage + oR; F.rayN = stage + (oR + qRP); F.nRay = Sg.nRay;
 		} else S.sils = stage + qN + qP + qF;
 		__syncthreads();
 	}
@@ -268,7 +271,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 								if (o.minStarRadius <= dirichletDist) {
 									float dsil;
 									float r2max = dirichletDist < kMaxF ? dirichletDist*dirichletDist : kMaxF;
-									bool f = flatClosestSilhouette<DIM>(S, pt, r2max, !flipOrient, o.minStarRadius*o.minStarRadius, o.silhouettePrecision, dsil);
+									bool f = flatClosestSilhouette<DIM>(F, pt, r2max, !flipOrient, o.minStarRadius*o.minStarRadius, o.silhouettePrecision, dsil);
 									starR = f ? fmaxf(dsil, o.minStarRadius) : fmaxf(dirichletDist, o.minStarRadius);
 								}
 							} else
@@ -283,7 +286,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
 						if (FLAT) {
 							V3 ro = onNeumann ? offsetPoint<DIM>(pt, neg(normal)) : pt;
-							hit = flatRay<DIM>(S, ro, dir, starR, h);
+							hit = flatRay<DIM>(F, ro, dir, starR, h);
 						} else
 						hit = intersectNeumann<DIM>(S, stack, pt, normal, dir, starR, onNeumann, h);
 						if (hit) { ipt = h.p; inrm = h.n; idist = h.d; }
@@ -407,9 +410,11 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (n >= (1ll << 32) - 65536) return cudaErrorInvalidValue;
 	const int dim = S.dim;
 	// small scenes are scanned flat (no per-step tree traversal)
-	const bool flat = S.nPrims <= 128 && S.nSilU <= 128;
-	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? S.nSilU : S.nSilRefs)
-				 + (flat ? (size_t)2*((S.nRay + 7)/8) + (size_t)2*((S.nSilU + 7)/8) + (size_t)((dim == 2 ? 1 : 3) + 1)*S.nRay : 0);
+	const bool flat = S.nPrims <= 128 && S.nSilU <= 128; // <= 41 KB of tables
+	const int G = dim == 2 ? FlatGroup<2>::n : FlatGroup<3>::n;
+	const size_t nSilP = (size_t)(S.nSilU + G - 1)/G*G, nRayP = (size_t)(S.nRay + G - 1)/G*G;
+	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? nSilP : (size_t)S.nSilRefs)
+				 + (flat ? 2*(nRayP/G) + 2*(nSilP/G) + (size_t)((dim == 2 ? 1 : 3) + 1)*nRayP : 0);
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
@@ -423,7 +428,10 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	else kern = smemStack ? fastKernel<3, StridedStack, false> : fastKernel<3, LocalStack, false>;
 	if (flat && !smemStack) return cudaErrorInvalidConfiguration; // cannot happen: <= 128 primitives give a shallow tree
 	int perSM = 0;
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kBlock, smem);
+	cudaError_t e = cudaSuccess;
+	if (smem > 48*1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // <= 48 + 24 + 4 KB
+	if (e != cudaSuccess) return e;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kBlock, smem);
 	if (e != cudaSuccess) return e;
 	if (perSM < 1) perSM = 1;
 	long long grid = (long long)smCount*perSM;

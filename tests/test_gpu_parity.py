@@ -184,6 +184,41 @@ def test_size_independent_properties_at_scale(pkg, mode):
         assert util.close_mask(ps, p1, rtol=1e-4, atol_scale=1e-5).mean() > 0.999
 
 
+@pytest.mark.parametrize("n_circle", [24, 128, 400])
+def test_mesh_size_regimes_of_the_default_mode(pkg, oracle_lib, tmp_path, n_circle):
+    """The default mode picks its data path by mesh size: flat tables in shared memory (<= 128 primitives),
+    tree + staged records + stacks in shared memory (here > 48 KB, the opt-in range), tree through L1/L2.
+    Each regime is checked against the oracle: bit-exact star radii and statistically equal estimates."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mss", os.path.join(util.GOLDEN, "make_synthetic_scenes.py"))
+    mss = importlib.util.module_from_spec(spec); spec.loader.exec_module(mss)
+    v, e = mss.channel_circle(n_circle=n_circle, wall_split=2 if n_circle > 24 else 1)
+    obj = str(tmp_path/"mesh.obj")
+    mss.write_obj(obj, "mesh size regime test", v, e, "l")
+    cfg = util.load_case("karman")
+    cfg["scene"]["boundary"] = obj
+    src = util.source_grid(2)
+    sc = pkg.Scene(cfg["scene"], src, device=0)
+    osc = oracle_lib.OracleScene(2, cfg["scene"], src)
+    lo, hi = sc.bbox()
+    q = util.random_points(lo, hi, 3000, seed=9)
+    dd = osc.dist_dirichlet(q)
+    star = sc.handle.probe(pkg.capi.PROBE_STAR_RADIUS, len(q), q, aux0=dd, params=[1e-3, 1e-3, 0.0])
+    assert _bits_equal(star, osc.star_radius(q, 1e-3, dd, 1e-3, False)).mean() >= 0.999
+    pts = util.random_points(lo, hi, 96, seed=4)
+    _, _, ref = osc.wost(cfg["solver"], cfg["output"], pts, seed=5, nthreads=4, want_stats=True)
+    p, g, s, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_FAST, seed=77, want_stats=True)
+    both = (ref[:, 11] > 0) & (s[:, 11] > 0)
+    assert both.sum() > 48
+    nf, nr = np.maximum(s[both, 9], 1), np.maximum(ref[both, 9], 1)
+    assert abs(nf.mean() - nr.mean()) < 0.03*500
+    z = (s[both, 0] - ref[both, 0])/np.sqrt(s[both, 1]/nf + ref[both, 1]/nr + 1e-30)
+    assert (np.abs(z) < 3).mean() >= 0.97 and abs(z.mean()) < 0.4
+    for d in range(2):
+        zg = (s[both, 2 + d] - ref[both, 2 + d])/np.sqrt(s[both, 5 + d]/nf + ref[both, 5 + d]/nr + 1e-30)
+        assert (np.abs(zg) < 3).mean() >= 0.97 and abs(zg.mean()) < 0.4
+
+
 def test_edge_cases(pkg):
     cfg = util.load_case("karman")
     sc = _scene(pkg, cfg)
