@@ -492,7 +492,7 @@ NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, f
 	bool found = false;
 	for (int g0 = 0, gi = 0; g0 < F.nSilU; g0 += G, gi += 2) {
 		// every lane of the warp sits near the same query point, so this cull is nearly warp-coherent
-		if (boxSqDistMin<DIM>(F.grpS[gi], F.grpS[gi + 1], x) > r2) continue;
+		if (F.nSilU > 4*G && boxSqDistMin<DIM>(F.grpS[gi], F.grpS[gi + 1], x) > r2) continue;
 #pragma unroll 1
 		for (int j = 0; j < G; j++) {
 			const int i = g0 + j;
@@ -505,10 +505,10 @@ NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, f
 				const float dot0 = vx*s1.x + vy*s1.y, dot1 = vx*s1.z + vy*s1.w;
 				const float pd2 = prec2*d2;
 				bool isSil = (asInt(s0.z) & 3) != 3;
-				const bool band = dot0*dot0 <= pd2 || dot1*dot1 <= pd2 || d2 <= prec2;
+				const bool band = (dot0*dot0 <= pd2) | (dot1*dot1 <= pd2) | (d2 <= prec2);
 				if (band && !isSil) isSil = isSilhouette(s1.x*s1.w - s1.z*s1.y, mk(s1.x, s1.y, 0.0f), mk(s1.z, s1.w, 0.0f), mk(vx, vy, 0.0f), sqrtf(d2), flip, precision);
-				else isSil = isSil || dot0*dot1 < 0.0f;
-				if (isSil && d2 <= r2) { found = true; r2 = d2; }
+				else isSil = isSil | (dot0*dot1 < 0.0f);
+				if (isSil & (d2 <= r2)) { found = true; r2 = d2; }
 			} else {
 				const float4 s0 = F.silsU[4*i], s1 = F.silsU[4*i + 1];
 				V3 pt; float t;
@@ -532,9 +532,21 @@ template <int DIM>
 NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 	constexpr int G = FlatGroup<DIM>::n;
 	int best = -1; float bu = 0.0f, bv = 0.0f;
+	// slab test of the ray segment [0, tMax] against each group's box (fminf/fmaxf drop the NaN of 0*inf)
+	const float ix = 1.0f/dir.x, iy = 1.0f/dir.y, iz = DIM == 3 ? 1.0f/dir.z : 0.0f;
+	const float ox = -o.x*ix, oy = -o.y*iy, oz = DIM == 3 ? -o.z*iz : 0.0f;
+	const bool cull = F.nRay > 4*G; // a handful of primitives (a box): testing them costs less than culling
 	for (int g0 = 0, gi = 0; g0 < F.nRay; g0 += G, gi += 2) {
-		// the ray is at most tMax long: skip groups farther than that from its origin
-		if (boxSqDistMin<DIM>(F.grpP[gi], F.grpP[gi + 1], o) > tMax*tMax) continue;
+		if (cull) {
+			const float4 lo = F.grpP[gi], hi = F.grpP[gi + 1];
+			const float a0 = fmaf(lo.x, ix, ox), a1 = fmaf(hi.x, ix, ox), b0 = fmaf(lo.y, iy, oy), b1 = fmaf(hi.y, iy, oy);
+			float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), 0.0f), tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tMax);
+			if (DIM == 3) {
+				const float c0 = fmaf(lo.z, iz, oz), c1 = fmaf(hi.z, iz, oz);
+				tn = fmaxf(tn, fminf(c0, c1)); tf = fminf(tf, fmaxf(c0, c1));
+			}
+			if (tn > tf*1.0001f + 1e-6f) continue; // boxes are exact bounds of the records: leave a rounding margin
+		}
 #pragma unroll 1
 		for (int j = 0; j < G; j++) {
 			const int i = g0 + j;
@@ -544,7 +556,7 @@ NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 				const float dv = dir.x*q.w - dir.y*q.z;
 				const float a = ux*dir.y - uy*dir.x, b = ux*q.w - uy*q.z;
 				const float adv = fabsf(dv);
-				if (adv > kEps && a*dv >= 0.0f && fabsf(a) <= adv && b*dv >= 0.0f && fabsf(b) <= tMax*adv) {
+				if ((adv > kEps) & (a*dv >= 0.0f) & (fabsf(a) <= adv) & (b*dv >= 0.0f) & (fabsf(b) <= tMax*adv)) { // no short-circuit branches
 					const float inv = 1.0f/dv;
 					const float s = a*inv, t = b*inv;
 					if (s >= 0.0f && s <= 1.0f && t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = s; }
