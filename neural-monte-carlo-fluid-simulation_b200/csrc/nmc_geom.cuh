@@ -484,44 +484,64 @@ NMC_HD float boxSqDistMin(float4 lo, float4 hi, V3 p) {
 	if (DIM == 3) { float az = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f); d += az*az; }
 	return d;
 }
+NMC_HD int lowestBit(unsigned m) {
+#if defined(__CUDA_ARCH__)
+	return __ffs((int)m) - 1;
+#else
+	return __builtin_ffs((int)m) - 1;
+#endif
+}
+// Two-stage closest-silhouette scan (record layout: scene_build.cpp).  Stage 1, unrolled and branch-free, marks
+// the records whose two face planes see x from opposite sides (or within the precision band |s| <= precision*d,
+// bounded with d <= sqrt(r2)); stage 2 runs SilhouetteVertex/Edge::findClosestSilhouettePoint
+// (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143) on the marked records only.  Every lane walks
+// its own candidate list, so a warp pays for the longest list, not for the union of the lanes' candidates.
 template <int DIM>
 NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
 	if (sqMinR >= r2) return false;
 	constexpr int G = FlatGroup<DIM>::n;
-	const float prec2 = precision*precision;
+	const float bandW = precision*sqrtf(r2);
+	const bool cull = F.nSilU > 4*G; // a handful of records (a box): testing them costs less than culling
 	bool found = false;
 	for (int g0 = 0, gi = 0; g0 < F.nSilU; g0 += G, gi += 2) {
 		// every lane of the warp sits near the same query point, so this cull is nearly warp-coherent
-		if (F.nSilU > 4*G && boxSqDistMin<DIM>(F.grpS[gi], F.grpS[gi + 1], x) > r2) continue;
-#pragma unroll 1
+		if (cull && boxSqDistMin<DIM>(F.grpS[gi], F.grpS[gi + 1], x) > r2) continue;
+		unsigned cand = 0u;
+#pragma unroll
 		for (int j = 0; j < G; j++) {
-			const int i = g0 + j;
+			float s0, s1;
 			if (DIM == 2) {
-				// SilhouetteVertex (vertex_silhouettes.inl:62-118) without normalising the view direction:
-				// |dot(v/d, n)| <= precision  <=>  dot(v, n)^2 <= precision^2 d^2; the exact rules only run in that band
-				const float4 s0 = F.silsU[2*i], s1 = F.silsU[2*i + 1];
-				const float vx = x.x - s0.x, vy = x.y - s0.y;
-				const float d2 = vx*vx + vy*vy;
-				const float dot0 = vx*s1.x + vy*s1.y, dot1 = vx*s1.z + vy*s1.w;
-				const float pd2 = prec2*d2;
-				bool isSil = (asInt(s0.z) & 3) != 3;
-				const bool band = (dot0*dot0 <= pd2) | (dot1*dot1 <= pd2) | (d2 <= prec2);
-				if (band && !isSil) isSil = isSilhouette(s1.x*s1.w - s1.z*s1.y, mk(s1.x, s1.y, 0.0f), mk(s1.z, s1.w, 0.0f), mk(vx, vy, 0.0f), sqrtf(d2), flip, precision);
-				else isSil = isSil | (dot0*dot1 < 0.0f);
-				if (isSil & (d2 <= r2)) { found = true; r2 = d2; }
+				const float4 q0 = F.silsU[2*(g0 + j)], q1 = F.silsU[2*(g0 + j) + 1];
+				s0 = fmaf(q0.x, x.x, fmaf(q0.y, x.y, q0.z)); s1 = fmaf(q0.w, x.x, fmaf(q1.x, x.y, q1.y));
 			} else {
-				const float4 s0 = F.silsU[4*i], s1 = F.silsU[4*i + 1];
-				V3 pt; float t;
-				const float d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
-				const float d2 = d*d;
-				if (d2 > r2) continue;
-				bool isSil = (asInt(s0.w) & 3) != 3;
-				if (!isSil) {
-					const float4 s2 = F.silsU[4*i + 2];
-					isSil = isSilhouette(s2.w, xyz(s2), xyz(F.silsU[4*i + 3]), x - pt, d, flip, precision);
-				}
-				if (isSil) { found = true; r2 = d2; }
+				const float4 e0 = F.silsU[4*(g0 + j)], e1 = F.silsU[4*(g0 + j) + 1];
+				s0 = fmaf(e0.x, x.x, fmaf(e0.y, x.y, fmaf(e0.z, x.z, e0.w))); s1 = fmaf(e1.x, x.x, fmaf(e1.y, x.y, fmaf(e1.z, x.z, e1.w)));
 			}
+			const bool c = (s0*s1 < 0.0f) | (fminf(fabsf(s0), fabsf(s1)) <= bandW);
+			cand = c ? (cand | (1u << j)) : cand;
+		}
+		while (cand) {
+			const int i = g0 + lowestBit(cand);
+			cand &= cand - 1u;
+			V3 viewDir, n0, n1; float d2, concavity;
+			if (DIM == 2) {
+				const float4 q0 = F.silsU[2*i], q1 = F.silsU[2*i + 1];
+				viewDir = mk(x.x - q1.z, x.y - q1.w, 0.0f);
+				d2 = viewDir.x*viewDir.x + viewDir.y*viewDir.y;
+				if (d2 > r2) continue;
+				n0 = mk(q0.x, q0.y, 0.0f); n1 = mk(q0.w, q1.x, 0.0f);
+				concavity = n0.x*n1.y - n1.x*n0.y;
+			} else {
+				const float4 e2 = F.silsU[4*i + 2], e3 = F.silsU[4*i + 3];
+				V3 pt; float t;
+				const float d = closestOnSegment(xyz(e2), xyz(e3), x, pt, t);
+				d2 = d*d;
+				if (d2 > r2) continue;
+				viewDir = x - pt;
+				n0 = xyz(F.silsU[4*i]); n1 = xyz(F.silsU[4*i + 1]); concavity = e3.w;
+			}
+			const bool twoFaces = (n0.x != 0.0f) | (n0.y != 0.0f) | (n0.z != 0.0f);
+			if (!twoFaces || isSilhouette(concavity, n0, n1, viewDir, sqrtf(d2), flip, precision)) { found = true; r2 = d2; }
 		}
 		if (sqMinR >= r2) break;
 	}

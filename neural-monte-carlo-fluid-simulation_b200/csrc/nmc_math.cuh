@@ -152,12 +152,13 @@ NMC_HD uint64_t pointSeed(uint64_t seed, uint64_t index) {
 template <int DIM, class M>
 NMC_HD V3 sphereDir(float u0, float u1) {
 #if defined(NMC_FAST_GEOM) && defined(__CUDA_ARCH__)
-	{ // default mode: sincospi has no large-argument slow path
-		float sn, cs;
-		if (DIM == 2) { sincospif(2.0f*u0, &sn, &cs); return mk(cs, sn, 0.0f); }
+	{ // default mode: the SFU's sin/cos on [-pi, pi) (abs. error 2^-21, two instructions each):
+	  // cos(2 pi u) = -cos(2 pi (u - 1/2)), likewise sin
+		const float a0 = 6.2831853f*((DIM == 2 ? u0 : u1) - 0.5f);
+		const float sn = -__sinf(a0), cs = -__cosf(a0);
+		if (DIM == 2) return mk(cs, sn, 0.0f);
 		float z = 1.0f - 2.0f*u0;
 		float r = sqrtf(fmaxf(0.0f, 1.0f - z*z));
-		sincospif(2.0f*u1, &sn, &cs);
 		return mk(r*cs, r*sn, z);
 	}
 #endif

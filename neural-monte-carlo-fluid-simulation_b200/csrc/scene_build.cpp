@@ -418,16 +418,42 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 	// scan-friendly records (after the boxes, which need the end points):
 	//  * ray primitives become (origin, edge vectors): 2D (pa.xy, pb - pa), 3D (pa)(pb - pa)(pc - pa);
 	//  * both lists are padded to a whole number of groups with records no query can accept (a silhouette at
-	//    infinity, a degenerate primitive), so the scans run fixed-trip inner loops.
+	//    infinity, a degenerate primitive), so the scans run fixed-trip inner loops;
 	if (dim == 2) for (int i = 0; i < out.nRay; i++) { Q4& q = out.rayP[i]; q.z -= q.x; q.w -= q.y; }
 	else for (int i = 0; i < out.nRay; i++) {
 		Q4 &a = out.rayP[3*i], &b = out.rayP[3*i + 1], &c = out.rayP[3*i + 2];
 		b.x -= a.x; b.y -= a.y; b.z -= a.z; c.x -= a.x; c.y -= a.y; c.z -= a.z;
 	}
+	//  * silhouettes are rewritten for a two-stage test.  Both faces of a silhouette vertex / edge contain it, so
+	//    dot(x - p, n_k) is the signed distance of x to the plane of face k: s_k(x) = n_k.x + c_k with c_k = -n_k.p.
+	//    Stage 1 needs only (n0, c0, n1, c1): a record can be a silhouette from x only if s_0 s_1 < 0 (or x is within
+	//    the precision band of a plane).  Stage 2 (distance, exact rules) reads the position.  Records with a single
+	//    face (always silhouettes) carry zero normals and c0 = 1, c1 = -1, so stage 1 always passes them on.
+	//      2D: (n0.x, n0.y, c0, n1.x) (n1.y, c1, p.x, p.y)
+	//      3D: (n0.xyz, c0) (n1.xyz, c1) (pa.xyz, flags) (pb.xyz, dihedral)
+	for (int i = 0; i < out.nSilU; i++) {
+		if (dim == 2) {
+			Q4 a = out.silsU[2*i], b = out.silsU[2*i + 1]; // (p.x, p.y, flags, id) (n0.x, n0.y, n1.x, n1.y)
+			int flags; std::memcpy(&flags, &a.z, 4);
+			if (flags == 3) {
+				out.silsU[2*i] = {b.x, b.y, -(b.x*a.x + b.y*a.y), b.z};
+				out.silsU[2*i + 1] = {b.w, -(b.z*a.x + b.w*a.y), a.x, a.y};
+			} else { out.silsU[2*i] = {0.0f, 0.0f, 1.0f, 0.0f}; out.silsU[2*i + 1] = {0.0f, -1.0f, a.x, a.y}; }
+		} else {
+			Q4 a = out.silsU[4*i], b = out.silsU[4*i + 1], c = out.silsU[4*i + 2], d = out.silsU[4*i + 3]; // (pa, flags) (pb, id) (n0, dihedral) (n1, -)
+			int flags; std::memcpy(&flags, &a.w, 4);
+			if (flags == 3) {
+				out.silsU[4*i] = {c.x, c.y, c.z, -(c.x*a.x + c.y*a.y + c.z*a.z)};
+				out.silsU[4*i + 1] = {d.x, d.y, d.z, -(d.x*a.x + d.y*a.y + d.z*a.z)};
+			} else { out.silsU[4*i] = {0.0f, 0.0f, 0.0f, 1.0f}; out.silsU[4*i + 1] = {0.0f, 0.0f, 0.0f, -1.0f}; }
+			out.silsU[4*i + 2] = a;
+			out.silsU[4*i + 3] = {b.x, b.y, b.z, c.w};
+		}
+	}
 	const float far = 1e30f; // (x - far)^2 overflows to +inf > any search radius
-	for (int i = out.nSilU; i % G != 0; i++) {
-		if (dim == 2) { out.silsU.push_back({far, far, bits(3), bits(-1)}); out.silsU.push_back({0, 0, 0, 0}); }
-		else { out.silsU.push_back({far, far, far, bits(3)}); out.silsU.push_back({far, far, far, bits(-1)}); out.silsU.push_back({0, 0, 0, 0}); out.silsU.push_back({0, 0, 0, 0}); }
+	for (int i = out.nSilU; i % G != 0; i++) { // never a candidate (s0 s1 = 1, |s| = 1 outside any sane band), and infinitely far if it is
+		if (dim == 2) { out.silsU.push_back({0.0f, 0.0f, 1.0f, 0.0f}); out.silsU.push_back({0.0f, 1.0f, far, far}); }
+		else { out.silsU.push_back({0, 0, 0, 1.0f}); out.silsU.push_back({0, 0, 0, 1.0f}); out.silsU.push_back({far, far, far, bits(3)}); out.silsU.push_back({far, far, far, 0.0f}); }
 	}
 	for (int i = out.nRay; i % G != 0; i++) {
 		out.rayP.push_back({far, far, 0.0f, 0.0f}); // zero edge vectors: determinant 0, rejected
