@@ -552,21 +552,33 @@ template <int DIM>
 NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 	constexpr int G = FlatGroup<DIM>::n;
 	int best = -1; float bu = 0.0f, bv = 0.0f;
-	// slab test of the ray segment [0, tMax] against each group's box (fminf/fmaxf drop the NaN of 0*inf)
+	// slab test of the ray segment [0, tMax] against each group's box (fminf/fmaxf drop the NaN of 0*inf).
+	// Lanes shoot different rays: each lane first collects the groups ITS ray can reach, then walks its own
+	// list, so a warp pays for the longest list and not for the union of the lanes' groups.
 	const float ix = 1.0f/dir.x, iy = 1.0f/dir.y, iz = DIM == 3 ? 1.0f/dir.z : 0.0f;
 	const float ox = -o.x*ix, oy = -o.y*iy, oz = DIM == 3 ? -o.z*iz : 0.0f;
-	const bool cull = F.nRay > 4*G; // a handful of primitives (a box): testing them costs less than culling
-	for (int g0 = 0, gi = 0; g0 < F.nRay; g0 += G, gi += 2) {
-		if (cull) {
-			const float4 lo = F.grpP[gi], hi = F.grpP[gi + 1];
-			const float a0 = fmaf(lo.x, ix, ox), a1 = fmaf(hi.x, ix, ox), b0 = fmaf(lo.y, iy, oy), b1 = fmaf(hi.y, iy, oy);
-			float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), 0.0f), tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tMax);
-			if (DIM == 3) {
-				const float c0 = fmaf(lo.z, iz, oz), c1 = fmaf(hi.z, iz, oz);
-				tn = fmaxf(tn, fminf(c0, c1)); tf = fminf(tf, fmaxf(c0, c1));
-			}
-			if (tn > tf*1.0001f + 1e-6f) continue; // boxes are exact bounds of the records: leave a rounding margin
+	auto reach = [&](int gi, float tm) {
+		const float4 lo = F.grpP[gi], hi = F.grpP[gi + 1];
+		const float a0 = fmaf(lo.x, ix, ox), a1 = fmaf(hi.x, ix, ox), b0 = fmaf(lo.y, iy, oy), b1 = fmaf(hi.y, iy, oy);
+		float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), 0.0f), tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tm);
+		if (DIM == 3) {
+			const float c0 = fmaf(lo.z, iz, oz), c1 = fmaf(hi.z, iz, oz);
+			tn = fmaxf(tn, fminf(c0, c1)); tf = fminf(tf, fmaxf(c0, c1));
 		}
+		return tn <= tf*1.0001f + 1e-6f; // boxes are exact bounds of the records: leave a rounding margin
+	};
+	const int nG = (F.nRay + G - 1)/G; // <= 32
+	const bool cull = F.nRay > 4*G;    // a handful of primitives (a box): testing them costs less than culling
+	unsigned todo = nG >= 32 ? 0xffffffffu : (1u << nG) - 1u;
+	if (cull) {
+		todo = 0u;
+#pragma unroll 1
+		for (int g = 0; g < nG; g++) todo |= (reach(2*g, tMax) ? 1u : 0u) << g;
+	}
+	while (todo) {
+		const int g = lowestBit(todo), g0 = g*G;
+		todo &= todo - 1u;
+		if (cull && best >= 0 && !reach(2*g, tMax)) continue; // the ray got shorter since the list was made
 #pragma unroll 1
 		for (int j = 0; j < G; j++) {
 			const int i = g0 + j;
