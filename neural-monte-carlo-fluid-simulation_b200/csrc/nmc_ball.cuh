@@ -288,7 +288,7 @@ NMC_OUTLINE Bessel4 besselScaled(float x) {
 // T(x) is the un-absorbed exit probability through the sphere of radius r (the reference's
 // directionSampledPoissonKernel, distributions.h:669-677, 801-813); T(0) = 1, T' = -x g (both dims),
 // |G| = (1 - T(X))/lambda (:650-652, :782-784) and the radial CDF of a source sample is
-// F(x) = (1 - T(x))/(1 - T(X)), which sampleX() inverts by safeguarded Newton instead of the
+// F(x) = (1 - T(x))/(1 - T(X)), which sampleX() inverts by a safeguarded Halley iteration instead of the
 // reference's rejection loop (:362-383).  Harmonic (lambda = 0) limits are handled in the same frame
 // with y = r/R:  2D F = y^2 (1 - 2 ln y),  3D: Ulrich's polar method (:483-496).
 template <int DIM>
@@ -373,7 +373,7 @@ struct BallFast {
 	// g receives g(x) (Yukawa only).  F vanishes quadratically at both ends of the interval, so Newton
 	// runs on sqrt(F) (u < 1/2) or sqrt(1 - F) (u >= 1/2), which are close to linear there.
 	// Tiny balls (X < 0.05) use the harmonic law: the two densities differ by O(X^2).
-	NMC_HD float sampleX(float u, float u2, float& g, float& q, bool& harmonicFrame) const {
+	NMC_HD float sampleX(float u, float u2, float& g, float& q, bool& harmonicFrame, bool refine = false) const {
 		harmonicFrame = !yukawa || X < 0.05f;
 		if (harmonicFrame) {
 			g = 0.0f; q = 0.0f;
@@ -407,21 +407,38 @@ struct BallFast {
 			x = sqrtf(2.0f*mass);
 			if (DIM == 2) { float L = fmaxf(-0.0772f - __logf(0.5f*fminf(x, 1.5f)), 0.35f); x = sqrtf(2.0f*mass/L); L = fmaxf(-0.0772f - __logf(0.5f*fminf(x, 1.5f)), 0.35f); x = sqrtf(2.0f*mass/L); }
 			x = fminf(x, 0.7f*X);
-		} else x = X - fminf(sqrtf(2.0f*mass/TX), 0.7f*X);
+		} else {
+			x = X - fminf(sqrtf(2.0f*mass/TX), 0.7f*X);   // T - TX ~ TX (X - x)^2/2 near the sphere
+			if (X >= 8.0f) { // large balls: the root sits where T(x) ~ sqrt(pi x/2) e^-x (2D) / (1 + x) e^-x (3D) equals TX + mass
+				float l = -__logf(fminf(TX + mass, 0.999f)), xa;
+				if (DIM == 2) { xa = l + 0.5f*__logf(fmaxf(1.5707963f*fmaxf(l, 0.3f), 1.0f)); xa = l + 0.5f*__logf(fmaxf(1.5707963f*xa, 1.0f)); }
+				else { xa = l + __logf(1.0f + l); xa = l + __logf(1.0f + xa); }
+				x = fminf(x, xa);
+			}
+		}
 		x = fminf(fmaxf(x, 1e-6f*X), X*(1.0f - 1e-6f));
 		// Fixed trip count, no early exit: every lane of the warp runs the same instruction stream (a data-dependent
-		// break serialises the warp on its slowest lane anyway).  sqrt(F) / sqrt(1-F) are close to linear, so four
-		// Newton steps from the analytic start reach |F(x) - u| < 3e-4 (tests/test_host_logic.py); g and q are
-		// returned at the last evaluated iterate, whose distance to the final x is below 1e-4 X.
+		// break serialises the warp on its slowest lane anyway).  sqrt(1 - T) / sqrt(T - TX) are close to linear in x,
+		// and T' = -x g, g' = -T/x (2D) / -(T - g)/x (3D) come for free, so the iteration is Halley's on
+		// h(x) = sqrt(m(x)) - sqrt(mass): two steps from the analytic start reach |F(x) - u| < 1e-4 over
+		// 0.05 <= X <= 100 (tests/test_host_logic.py).  With `refine` one more evaluation returns g and q AT the
+		// returned x (the first-ball gradient weights need them); otherwise they belong to the last iterate.
 		float T, gg = 0.0f, qq = 0.0f;
 #pragma unroll 1
-		for (int it = 0; it < 4; it++) {
+		for (int it = 0; it < 2; it++) {
 			evalTgq(x, T, gg, qq);
-			float s = sqrtf(fmaxf(lower ? 1.0f - T : T - TX, 1e-30f));
-			float step = 2.0f*s*(s - target)/fmaxf(x*gg, 1e-30f);
-			float xn = lower ? x - step : x + step;
+			float m = fmaxf(lower ? 1.0f - T : T - TX, 1e-30f);
+			float sq = sqrtf(m), h = sq - target;
+			float a = fmaxf(x*gg, 1e-30f);                                  // |m'|
+			float m2 = gg - (DIM == 2 ? T : T - gg);                          // g + x g'
+			// lower: m' = a, m'' = m2; upper: m' = -a, m'' = -m2.  Halley step = 4 h m' m / (m'^2 (2 sq + h) - 2 h m'' m)
+			float sgn = lower ? 1.0f : -1.0f;
+			float den = a*a*(2.0f*sq + h) - 2.0f*h*(sgn*m2)*m;
+			float step = den > 0.0f ? 4.0f*h*a*m/den : 2.0f*sq*h/a;            // Newton if Halley's denominator degenerates
+			float xn = x - sgn*step;
 			x = fminf(fmaxf(xn, 0.25f*x), 0.5f*(x + X));
 		}
+		if (refine) evalTgq(x, T, gg, qq);
 		g = gg; q = qq;
 		return x;
 	}

@@ -214,7 +214,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							float rs = 0.0f, fsrc = 0.0f, sf = 0.0f;
 							if (!o.ignoreSource) {
 								float gs, qs; bool hframe;
-								float xs = fb.sampleX(uA, uB, gs, qs, hframe);
+								float xs = fb.sampleX(uA, uB, gs, qs, hframe, true); // g, q at the returned x
 								rs = hframe ? xs*fb.R : xs/fb.mu;
 								rs = fminf(fmaxf(rs, 1e-4f), fb.R);        // rClamp, distributions.h:378-379
 								fsrc = normG0*sourceAt<DIM>(S, x0 + rs*sdir);

@@ -215,7 +215,8 @@ def test_fast_mode_ball_functions_against_scipy(emu):
             Ts, _, _ = exact(rs.astype(np.float64)*mu)
             F = (1 - Ts)/(1 - TX)
             sel = X >= 0.05 if dim == 3 else np.ones(len(R), bool)  # tiny 3D balls use the two-uniform polar method
-            assert np.abs(F - u)[sel].max() < 2e-3
+            assert np.abs(F - u)[sel].max() < 2e-3              # X < 1: fp32 cancellation in 1 - T bounds the accuracy
+            assert np.abs(F - u)[sel & (X >= 1)].max() < 1e-4   # two Halley steps from the analytic start
 
 
 def test_siren_symbols_and_state_dict_layout():
