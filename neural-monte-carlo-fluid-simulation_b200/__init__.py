@@ -8,12 +8,20 @@ Layout:
   zombie2d/, zombie3d/   the compiled drop-in modules named `zombie_bindings` (one per dimension)
   sharding.py      multi-GPU point sharding (one process per GPU, gather of the estimates)
   siren.py         fused SIREN velocity network (drop-in for the reference's MLP) + fused Adam (csrc/siren*.cu)
+  stepper.py       device-resident operator-split time step (advect fit, divergence grid, wost, projection fit)
+  fields.py        density advection + Taylor-Green error on the device (csrc/fields.cu, include/nmcfs_fields.h)
 
 The directory name contains '-', so import it with
     importlib.import_module("neural-monte-carlo-fluid-simulation_b200")
 or through __graft_entry__.load_package().
 """
 from . import capi, zombie, sharding  # noqa: F401
+
+
+def load_fields():
+    """Lazy import of the grid post-processing ops (needs torch)."""
+    from . import fields as _f
+    return _f
 
 
 def load_siren():

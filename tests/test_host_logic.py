@@ -219,6 +219,26 @@ def test_fast_mode_ball_functions_against_scipy(emu):
             assert np.abs(F - u)[sel & (X >= 1)].max() < 1e-4   # two Halley steps from the analytic start
 
 
+def test_fields_symbols():
+    """libnmcfs.so exports everything include/nmcfs_fields.h declares; the wrappers refuse CPU tensors."""
+    torch = pytest.importorskip("torch")
+    pkg = util.package()
+    f = pkg.load_fields()
+    hdr = open(os.path.join(util.ROOT, "include", "nmcfs_fields.h")).read()
+    declared = set(re.findall(r"\b(nmc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(f.FIELDS_EXPORTS)
+    for name in declared:
+        assert hasattr(pkg.capi.lib(), name), name
+    with pytest.raises(RuntimeError, match="CUDA"):
+        f.advect_density(torch.zeros(4, 4), torch.zeros(4, 4, 2), 0.1, [0, 0], [1, 1])
+    # the analytic Taylor-Green field (sources.py:19-32) is divergence free and periodic on the rescaled domain
+    x = torch.rand(64, 2, dtype=torch.float64)*2 - 1
+    x.requires_grad_(True)
+    u = f.taylor_green_velocity(x, (-1.0, 1.0, -1.0, 1.0))
+    div = torch.autograd.grad(u[:, 0].sum(), x, retain_graph=True)[0][:, 0] + torch.autograd.grad(u[:, 1].sum(), x)[0][:, 1]
+    assert div.abs().max() < 1e-12
+
+
 def test_siren_symbols_and_state_dict_layout():
     """libnmcfs.so exports the SIREN ABI (include/nmcfs_siren.h) and FusedSiren keeps the reference MLP's
     parameter names, shapes and initialisation ranges (networks.py:24-90), so checkpoints are interchangeable."""
