@@ -72,3 +72,90 @@ def test_step_runs_and_fits(graph):
     _, l5 = s2.advect_velocity(5)
     _, l200 = s2.advect_velocity(200)
     assert l200.item() <= l5.item()*1.5
+
+
+def _reference_arrangement_step(pkg, s, net, prev, lr, oracle_lib, n_iters, seed):
+    """One NeuralFluidSplit.step (model_split.py:44-62, adv_ref = 0) the way the reference runs it: stock PyTorch
+    ops for the network (forward_reference = nn.Linear + sin), torch.optim.Adam, autograd divergence, the
+    divergence grid moved to the host, the CPU solver (oracle, bit-exact with the reference's), grad p moved back."""
+    env = s.envelope
+    n = s.sample_resolution**2
+    prev.load_state_dict(net.state_dict())
+    opt = torch.optim.Adam(net.parameters(), lr=lr)  # create_optimizer() at the top of every _training_loop (base.py:133)
+    for _ in range(n_iters):  # _advect_velocity, model_split.py:88-120
+        x = s.sample_random(n)
+        with torch.no_grad():
+            pu = prev.forward_reference(x)*env(x)
+            back = torch.clamp(x - pu*s.dt, min=s._lo, max=s._hi)
+            adv = prev.forward_reference(back)*env(back)
+        loss = torch.mean((net.forward_reference(x)*env(x) - adv)**2)
+        opt.zero_grad(); loss.backward(); opt.step()
+    prev.load_state_dict(net.state_dict())
+    x = s.grid_samples.detach().clone().requires_grad_(True)  # get_divergence, model_split.py:230-243
+    u = prev.forward_reference(x)*env(x)
+    div = 0.0
+    for i in range(2):
+        div = div + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=(i == 0))[0][:, i]
+    div = (-div).reshape(s.grid_shape).detach().cpu().numpy()
+    pts = s.sample_random(s.wost_resolution**2)
+    osc = oracle_lib.OracleScene(2, s.cfg["scene"], div)  # wost_pressure, model_split.py:185-228
+    _, g, _ = osc.wost(s.cfg["solver"], s.cfg["output"], pts.cpu().numpy(), seed=seed, nthreads=8)
+    grad_p = torch.from_numpy(g).to(pts.device)
+    opt = torch.optim.Adam(net.parameters(), lr=lr)
+    for _ in range(n_iters):  # _project_velocity, model_split.py:246-284
+        idx = torch.randint(0, pts.shape[0] - 1, (n,), device=pts.device)
+        xs = pts[idx]
+        with torch.no_grad():
+            target = prev.forward_reference(xs)*env(xs) - grad_p[idx]
+        loss = torch.mean((net.forward_reference(xs)*env(xs) - target)**2)
+        opt.zero_grad(); loss.backward(); opt.step()
+    prev.load_state_dict(net.state_dict())
+
+
+def test_taylor_green_velocity_error_tracks_the_reference_arrangement(oracle_lib):
+    """north_star, second criterion: the end-of-run Taylor-Green velocity error (move_density.py:143-146 metric)
+    of the device-resident stepper stays within 1 % of the reference arrangement's, from the same initial
+    network, on a reduced configuration (solver-active scene, 3 time steps).
+    Part A removes the sampling noise so that 1 % is a meaningful bar: both arrangements draw the same training
+    samples (same torch seed, eager launches) and the pressure solve runs in deterministic mode with the seed
+    the CPU solver gets, so the only differences left are the fused kernels' rounding and the solver's 1e-5.
+    Part B is the production setting (default mode, CUDA-graph replay): different samples and walks, so the
+    errors agree only up to the run-to-run spread of either arrangement (measured: +-35 % at this size)."""
+    lr, K, steps = 2e-5, 120, 3
+    kw = dict(max_n_iters=K, lr=lr, dt=0.01, grid_resolution=300, wost_resolution=96, sample_resolution=48, early_stop=False, seed=11)
+    pkg, s = _stepper(use_cuda_graph=False, mode=util.package().capi.MODE_DETERMINISTIC, **kw)
+    F = pkg.load_fields(); S = pkg.load_siren()
+    size = s.size
+    s.fit_initial(_tg, 2500, lr=3e-4)
+    init = {k: v.clone() for k, v in s.velocity_field.state_dict().items()}
+    ref_net = S.FusedSiren(2, 2, 6, 64, nonlinearity="sine").cuda(); ref_prev = S.FusedSiren(2, 2, 6, 64, nonlinearity="sine").cuda()
+    ref_net.load_state_dict(init)
+    e0 = F.taylor_green_error(s.velocity_field, size, 500)
+    assert e0 < 2e-3, "initial fit did not converge: %g" % e0
+    assert e0 == pytest.approx(F.taylor_green_error(ref_net, size, 500), rel=1e-3)   # same weights, fused vs stock evaluation
+    torch.manual_seed(77)
+    ours, seeds = [], []
+    for t in range(steps):
+        seeds.append(int(s.opts.seed))
+        s.step()
+        ours.append(F.taylor_green_error(s.velocity_field, size, 500))
+    torch.manual_seed(77)
+    ref = []
+    for t in range(steps):
+        _reference_arrangement_step(pkg, s, ref_net, ref_prev, lr, oracle_lib, K, seed=seeds[t])
+        ref.append(F.taylor_green_error(ref_net, size, 500))
+    print("taylor-green velocity error, same samples: initial %.4e, ours %s, reference arrangement %s" % (e0, ours, ref))
+    for a, b in zip(ours, ref):
+        assert abs(a - b) <= 0.01*b, (ours, ref)
+    assert abs(ref[-1] - e0) > 0.05*e0   # the steps moved the field by far more than the tolerance
+
+    # Part B: production setting from the same initial network
+    pkg, s2 = _stepper(use_cuda_graph=True, **kw)
+    s2.velocity_field.load_state_dict(init); s2._sync_prev()
+    fast = []
+    for t in range(steps):
+        s2.step()
+        fast.append(F.taylor_green_error(s2.velocity_field, size, 500))
+    print("default mode + graph replay:", fast)
+    assert all(math.isfinite(e) for e in fast)
+    assert 0.5*ref[-1] <= fast[-1] <= 2.0*ref[-1], (fast, ref)
