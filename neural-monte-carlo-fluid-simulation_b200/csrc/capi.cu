@@ -58,6 +58,15 @@ static int setSource(nmc_scene* s, const float* src, int n0, int n1, int n2, int
 	}
 	CK(cudaMemcpy(s->d_src, src, count*sizeof(float), isDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	s->view.src = s->d_src; s->view.n0 = n0; s->view.n1 = n1; s->view.n2 = s->flat.dim == 3 ? n2 : 1;
+	{ // texel index = (int)(x*scale + off) for the default mode: axis k of the box maps to n_k texels (2D: rows <-> y)
+		const SceneView& v = s->view;
+		const int nAx[3] = {s->flat.dim == 2 ? n1 : n0, s->flat.dim == 2 ? n0 : n1, s->flat.dim == 3 ? n2 : 1};
+		for (int k = 0; k < 3; k++) {
+			float ext = v.bboxHi[k] - v.bboxLo[k];
+			s->view.srcScale[k] = ext > 0.0f ? (float)nAx[k]/ext : 0.0f;
+			s->view.srcOff[k] = -v.bboxLo[k]*s->view.srcScale[k];
+		}
+	}
 	return NMC_OK;
 }
 

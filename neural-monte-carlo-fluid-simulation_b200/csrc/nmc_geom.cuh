@@ -38,6 +38,7 @@ struct SceneView {
 	const float4* rayP; const float4* rayN; int nRay; // ray-scan primitives as (origin, edge vectors); 2D: collinear chains merged; padded to whole groups
 	float bboxLo[3], bboxHi[3];
 	const float* src; int n0, n1, n2;
+	float srcScale[3], srcOff[3];     // default mode: texel index along box axis k = (int)(x_k*srcScale[k] + srcOff[k])
 	float absorption; int watertight, doubleSided;
 };
 
@@ -696,6 +697,18 @@ NMC_HD bool intersectNeumann(const SceneView& S, V3 org, V3 nrm, V3 dir, float t
 // pde.source: nearest-texel lookup (demo/scene.h:194-198 + image.h:70-75; zombie3d scene_3d.h:120-126)
 template <int DIM>
 NMC_HD float sourceAt(const SceneView& S, V3 x) {
+#if defined(NMC_FAST_GEOM)
+	{ // default mode: one FMA per axis ((x - lo)/(hi - lo)*n folded into scale and offset); texel boundaries move by an ulp
+		int a = (int)fmaf(x.x, S.srcScale[0], S.srcOff[0]), b = (int)fmaf(x.y, S.srcScale[1], S.srcOff[1]);
+		if (DIM == 2) { // rows <-> y, columns <-> x
+			a = min(max(a, 0), S.n1 - 1); b = min(max(b, 0), S.n0 - 1);
+			return S.src[b*S.n1 + a];
+		}
+		int c = (int)fmaf(x.z, S.srcScale[2], S.srcOff[2]);
+		a = min(max(a, 0), S.n0 - 1); b = min(max(b, 0), S.n1 - 1); c = min(max(c, 0), S.n2 - 1);
+		return S.src[(a*S.n1 + b)*S.n2 + c];
+	}
+#endif
 	float ux = (x.x - S.bboxLo[0])/(S.bboxHi[0] - S.bboxLo[0]);
 	float uy = (x.y - S.bboxLo[1])/(S.bboxHi[1] - S.bboxLo[1]);
 	if (DIM == 2) {
