@@ -22,14 +22,26 @@ typedef struct {
 	float w0;            /* 30 (Sine.forward, networks.py:19-21) */
 } nmc_siren_shape;
 
-/* Boundary envelope multiplied onto the network output inside the kernels (query_velocity, base.py:158-224).
- * kind 0: none.  kind 1: wall weights of the taylorgreen branch (base.py:179-187; 3D analogue with z):
- *   w_i(x) = min(|x_i - lo_i|, |x_i - hi_i|) clamped to [0, eps] / eps  for output component i (< in_dim).
- * The reference detaches the weights, so no gradient flows through them. May be passed as NULL (= kind 0). */
+/* Boundary envelope applied to the network output inside the kernels (query_velocity, src/2d/models/base.py:158-224,
+ * src/3d/models/base.py:172-260).  May be passed as NULL (= kind 0, none).
+ * kind 1: wall weights on every output component i (< in_dim), the taylorgreen / vortex_collide branches:
+ *   w_i(x) = min(|x_i - lo_i|, |x_i - hi_i|) clamped to [0, eps] / eps.  The reference detaches these weights.
+ * kind 2: general, in the reference's order of operations:
+ *   1. region override: inside the region (region_kind 1: box [region_lo, region_hi]; 2: ball, centre region_lo,
+ *      radius region_hi[0], strict <) the components in region_mask take region_vel (karman inlet strip on u,
+ *      base.py:170-171; smoke_obs inlet ball on w, 3d base.py:225-229).  No gradient reaches the network there.
+ *   2. obstacle weight clamp(|x - sphere_c| - sphere_r, 0, eps)/eps on every component when has_sphere
+ *      (smoothstep_circular_obs, base.py:352-358).  NOT detached in the reference: nmc_siren_backward adds the
+ *      gradient that reaches x through it.
+ *   3. wall weights (as kind 1) on the components in wall_mask (karman: v only, base.py:175-180).
+ * The fields after eps are ignored for kind 0 and 1. */
 typedef struct {
 	int kind;
 	float lo[3], hi[3];
 	float eps;
+	int wall_mask;
+	int has_sphere; float sphere_c[3]; float sphere_r;
+	int region_kind; int region_mask; float region_lo[3], region_hi[3], region_vel[3];
 } nmc_siren_envelope;
 
 const char* nmc_siren_last_error(void);

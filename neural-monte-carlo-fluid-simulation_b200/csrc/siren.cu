@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
+#include "siren_env.cuh"
 
 namespace {
 
@@ -52,11 +53,7 @@ struct Params {
 	float* gb[kMaxLayers];
 };
 
-struct Env { int kind; float lo[3], hi[3], eps; };
-__device__ __forceinline__ float envWeight(const Env& e, int i, float xi) {
-	float a = fminf(fmaxf(fabsf(xi - e.lo[i]), 0.0f), e.eps), b = fminf(fmaxf(fabsf(xi - e.hi[i]), 0.0f), e.eps);
-	return fminf(a, b)/e.eps;
-}
+using nmc_siren_detail::Env;
 
 
 template <int H>
@@ -113,12 +110,18 @@ sirenForward(Params P, Env env, int inDim, int outDim, int nHidden, float w0, co
 		}
 		// last layer: H -> out (no activation, outermost_linear=True)
 		const int last = nHidden + 1;
+		float yo[3] = {0.0f, 0.0f, 0.0f};
 		for (int j = 0; j < outDim; j++) {
 			float z = __ldg(&P.b[last][j]);
 #pragma unroll
 			for (int k = 0; k < H; k++) z += __ldg(&P.W[last][j*H + k])*a[k];
-			if (env.kind == 1 && j < inDim) z *= envWeight(env, j, j == 0 ? x0 : (j == 1 ? x1 : x2));
-			if (live) y[s*outDim + j] = z;
+			if (j == 0) yo[0] = z; else if (j == 1) yo[1] = z; else yo[2] = z;
+		}
+		if (env.active) { const float xs[3] = {x0, x1, x2}; nmc_siren_detail::envForward(env, inDim, outDim, xs, yo); }
+		if (live) {
+			y[s*outDim] = yo[0];
+			if (outDim > 1) y[s*outDim + 1] = yo[1];
+			if (outDim > 2) y[s*outDim + 2] = yo[2];
 		}
 	}
 }
@@ -149,14 +152,27 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 		const long long s = tile*kTile + tid;
 		const bool live = s < n;
 		float g[H];
+		float gxe[3] = {0.0f, 0.0f, 0.0f}; // gradient reaching x through the obstacle weight of the envelope
 		{ // last layer: g_L = W_last^T gy  (and A_L for dW_last)
 			float gy0 = 0.0f, gy1 = 0.0f, gy2 = 0.0f;
 			if (live) {
 				gy0 = gy[s*outDim]; if (outDim > 1) gy1 = gy[s*outDim + 1]; if (outDim > 2) gy2 = gy[s*outDim + 2];
-				if (env.kind == 1) { // detached weights: scale only
-					gy0 *= envWeight(env, 0, x[s*inDim]);
-					if (outDim > 1 && inDim > 1) gy1 *= envWeight(env, 1, x[s*inDim + 1]);
-					if (outDim > 2 && inDim > 2) gy2 *= envWeight(env, 2, x[s*inDim + 2]);
+				if (env.active) {
+					const float xs[3] = {x[s*inDim], inDim > 1 ? x[s*inDim + 1] : 0.0f, inDim > 2 ? x[s*inDim + 2] : 0.0f};
+					float gys[3] = {gy0, gy1, gy2}, yn[3] = {0.0f, 0.0f, 0.0f};
+					const bool viaObstacle = env.sphere && gx != nullptr; // the obstacle weight is not detached (base.py:352-358)
+					if (viaObstacle) { // network output y = W_last sin(w0 z_L) + b, needed for d(weight)/dx * y
+						for (int j = 0; j < outDim; j++) yn[j] = __ldg(&P.b[last][j]);
+#pragma unroll 4
+						for (int k = 0; k < H; k++) {
+							float t = w0*zSaved[((size_t)nHidden*H + k)*n + s]*0.15915494309189535f;
+							t -= rintf(t);
+							float ak = __sinf(6.283185307179586f*t);
+							for (int j = 0; j < outDim; j++) yn[j] += __ldg(&P.W[last][j*H + k])*ak;
+						}
+					}
+					nmc_siren_detail::envBackward(env, inDim, outDim, xs, yn, gys, viaObstacle ? gxe : nullptr);
+					gy0 = gys[0]; gy1 = gys[1]; gy2 = gys[2];
 				}
 				// rows (L+1)*H .. of dZ: the (envelope-scaled) output gradient, for dW_last = gy'^T A_L^T
 				const size_t r0 = (size_t)(nHidden + 1)*H;
@@ -218,7 +234,7 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				if (inDim > 1) a1 += __ldg(w + 1)*g[j];
 				if (inDim > 2) a2 += __ldg(w + 2)*g[j];
 			}
-			gx[s*inDim] = a0; if (inDim > 1) gx[s*inDim + 1] = a1; if (inDim > 2) gx[s*inDim + 2] = a2;
+			gx[s*inDim] = a0 + gxe[0]; if (inDim > 1) gx[s*inDim + 1] = a1 + gxe[1]; if (inDim > 2) gx[s*inDim + 2] = a2 + gxe[2];
 		}
 	}
 }
@@ -348,19 +364,13 @@ namespace nmc_siren_detail { void setError(const char* m) { g_err = m; } }
 
 extern "C" const char* nmc_siren_last_error(void) { return g_err; }
 
-static Env toEnv(const nmc_siren_envelope* e) {
-	Env v; v.kind = 0; v.eps = 1.0f;
-	for (int i = 0; i < 3; i++) { v.lo[i] = 0.0f; v.hi[i] = 0.0f; }
-	if (e && e->kind == 1) { v.kind = 1; v.eps = e->eps; for (int i = 0; i < 3; i++) { v.lo[i] = e->lo[i]; v.hi[i] = e->hi[i]; } }
-	return v;
-}
 
 extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
 								 int64_t n, float* y, float* z_saved, const nmc_siren_envelope* envp, void* stream) {
 	Params P;
 	if (fill(P, sh, W, b, nullptr, nullptr)) return 1;
-	if (envp && envp->kind != 0 && envp->kind != 1) return fail("unknown envelope kind");
-	Env env = toEnv(envp);
+	Env env;
+	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
 	if (n <= 0) return 0;
 	if (!x || !y) return fail("null buffer");
 	const int H = sh->hidden;
@@ -385,8 +395,8 @@ extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const*
 								  float* grad_x, const nmc_siren_envelope* envp, void* stream) {
 	Params P;
 	if (fill(P, sh, W, b, nullptr, nullptr)) return 1;
-	if (envp && envp->kind != 0 && envp->kind != 1) return fail("unknown envelope kind");
-	Env env = toEnv(envp);
+	Env env;
+	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
 	if (n <= 0) return 0;
 	if (!x || !z_saved || !grad_y || !dZ || !A) return fail("null buffer");
 	const int H = sh->hidden;

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
+#include "siren_env.cuh"
 
 namespace {
 
@@ -52,11 +53,7 @@ struct Params {
 	const float* b[kMaxLayers];
 };
 
-struct Env { int kind; float lo[3], hi[3], eps; };
-__device__ __forceinline__ float envWeight(const Env& e, int i, float xi) {
-	float a = fminf(fmaxf(fabsf(xi - e.lo[i]), 0.0f), e.eps), b = fminf(fmaxf(fabsf(xi - e.hi[i]), 0.0f), e.eps);
-	return fminf(a, b)/e.eps;
-}
+using nmc_siren_detail::Env;
 
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,12 +137,6 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 			}
 		}
 		float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f;
-		float e0 = 1.0f, e1 = 1.0f, e2 = 1.0f;
-		if (env.kind == 1 && live) {
-			e0 = envWeight(env, 0, x[s*inDim]);
-			if (inDim > 1) e1 = envWeight(env, 1, x[s*inDim + 1]);
-			if (inDim > 2) e2 = envWeight(env, 2, x[s*inDim + 2]);
-		}
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
@@ -215,9 +206,14 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 			}
 		}
 		if (live) {
-			y[s*outDim] = (y0 + __ldg(&P.b[last][0]))*e0;
-			if (outDim > 1) y[s*outDim + 1] = (y1 + __ldg(&P.b[last][1]))*(inDim > 1 ? e1 : 1.0f);
-			if (outDim > 2) y[s*outDim + 2] = (y2 + __ldg(&P.b[last][2]))*(inDim > 2 ? e2 : 1.0f);
+			float yo[3] = {y0 + __ldg(&P.b[last][0]), outDim > 1 ? y1 + __ldg(&P.b[last][1]) : 0.0f, outDim > 2 ? y2 + __ldg(&P.b[last][2]) : 0.0f};
+			if (env.active) {
+				const float xs[3] = {x[s*inDim], inDim > 1 ? x[s*inDim + 1] : 0.0f, inDim > 2 ? x[s*inDim + 2] : 0.0f};
+				nmc_siren_detail::envForward(env, inDim, outDim, xs, yo);
+			}
+			y[s*outDim] = yo[0];
+			if (outDim > 1) y[s*outDim + 1] = yo[1];
+			if (outDim > 2) y[s*outDim + 2] = yo[2];
 		}
 		// the next tile's first layer overwrites A: every thread is past its last use (MMAs completed via the mbarrier)
 		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -247,10 +243,8 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	if (!x || !y) { nmc_siren_detail::setError("null buffer"); return 1; }
 	Params P;
 	for (int l = 0; l < sh->n_hidden_layers + 2; l++) { P.W[l] = W[l]; P.b[l] = b[l]; }
-	Env env; env.kind = 0; env.eps = 1.0f;
-	for (int i = 0; i < 3; i++) { env.lo[i] = 0.0f; env.hi[i] = 0.0f; }
-	if (envp && envp->kind == 1) { env.kind = 1; env.eps = envp->eps; for (int i = 0; i < 3; i++) { env.lo[i] = envp->lo[i]; env.hi[i] = envp->hi[i]; } }
-	else if (envp && envp->kind != 0) { nmc_siren_detail::setError("unknown envelope kind"); return 1; }
+	Env env;
+	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) { nmc_siren_detail::setError(bad); return 1; }
 	const int H = sh->hidden;
 	size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4;
 	int dev = 0, sms = 148;

@@ -22,17 +22,92 @@ class Shape(C.Structure):
 
 
 class Envelope(C.Structure):
-    """nmc_siren_envelope: wall weights multiplied onto the output inside the kernels (base.py:179-187)."""
-    _fields_ = [("kind", C.c_int), ("lo", C.c_float*3), ("hi", C.c_float*3), ("eps", C.c_float)]
+    """nmc_siren_envelope: the boundary envelope of query_velocity evaluated inside the kernels (include/nmcfs_siren.h)."""
+    _fields_ = [("kind", C.c_int), ("lo", C.c_float*3), ("hi", C.c_float*3), ("eps", C.c_float),
+                ("wall_mask", C.c_int), ("has_sphere", C.c_int), ("sphere_c", C.c_float*3), ("sphere_r", C.c_float),
+                ("region_kind", C.c_int), ("region_mask", C.c_int), ("region_lo", C.c_float*3), ("region_hi", C.c_float*3),
+                ("region_vel", C.c_float*3)]
 
 
 def wall_envelope(size, eps):
-    """size = (x0, x1, y0, y1[, z0, z1]) as the reference's scene_size."""
+    """taylorgreen / vortex_collide (base.py:179-187): wall weights on every component.
+    size = (x0, x1, y0, y1[, z0, z1]) as the reference's scene_size."""
     e = Envelope()
     e.kind, e.eps = 1, float(eps)
     for i in range(len(size)//2):
         e.lo[i], e.hi[i] = float(size[2*i]), float(size[2*i + 1])
     return e
+
+
+def general_envelope(size, eps, wall_mask, sphere=None, region=None):
+    """kind 2.  sphere = (centre, radius) of the no-slip obstacle or None; region = ("box", lo, hi, mask, vel) or
+    ("ball", centre, radius, mask, vel) or None, `mask` = bit set of the overridden components."""
+    e = wall_envelope(size, eps)
+    e.kind, e.wall_mask = 2, int(wall_mask)
+    if sphere is not None:
+        c, r = sphere
+        e.has_sphere, e.sphere_r = 1, float(r)
+        for i, v in enumerate(c):
+            e.sphere_c[i] = float(v)
+    if region is not None:
+        kind, a, b, mask, vel = region
+        e.region_kind, e.region_mask = {"box": 1, "ball": 2}[kind], int(mask)
+        for i, v in enumerate(a):
+            e.region_lo[i] = float(v)
+        if kind == "box":
+            for i, v in enumerate(b):
+                e.region_hi[i] = float(v)
+        else:
+            e.region_hi[0] = float(b)
+        for i, v in enumerate(vel):
+            e.region_vel[i] = float(v)
+    return e
+
+
+def karman_envelope(size, eps, centre, radius, karman_vel):
+    """src/2d/models/base.py:169-181: u = karman_vel in the inlet strip [x0, x0 + eps], no-slip cylinder, wall weight on v."""
+    lo = (size[0], -3.0e38)
+    hi = (size[0] + eps, 3.0e38)
+    return general_envelope(size, eps, wall_mask=0b10, sphere=(centre, radius), region=("box", lo, hi, 0b01, (karman_vel, 0.0)))
+
+
+def smoke_obs_envelope(size, eps, centre, radius, inlet_centre=(0.0, 0.0, -0.6), inlet_radius=0.1, inlet_w=1.0):
+    """src/3d/models/base.py:224-244: w = 1 inside the inlet ball, no-slip sphere obstacle, wall weights on u, v, w."""
+    return general_envelope(size, eps, wall_mask=0b111, sphere=(centre, radius),
+                            region=("ball", inlet_centre, inlet_radius, 0b100, (0.0, 0.0, inlet_w)))
+
+
+def envelope_reference(env, samples, net_vel):
+    """The same envelope with stock torch ops, written like the reference's query_velocity (autograd flows through the
+    obstacle weight, the wall weights are detached).  For tests and for callers who want the un-fused path."""
+    if env is None or env.kind == 0:
+        return net_vel
+    dim = samples.shape[-1]
+    eps = env.eps
+    vel = net_vel.clone()
+    if env.kind == 2 and env.region_kind:
+        if env.region_kind == 1:
+            m = torch.ones_like(samples[..., 0], dtype=torch.bool)
+            for i in range(dim):
+                m = m & (samples[..., i] >= env.region_lo[i]) & (samples[..., i] <= env.region_hi[i])
+        else:
+            c = torch.tensor([env.region_lo[i] for i in range(dim)], device=samples.device, dtype=samples.dtype)
+            m = torch.linalg.norm(samples - c, dim=-1) < env.region_hi[0]
+        for j in range(vel.shape[-1]):
+            if (env.region_mask >> j) & 1:
+                vel[..., j] = torch.where(m, torch.full_like(vel[..., j], env.region_vel[j]), vel[..., j])
+    if env.kind == 2 and env.has_sphere:
+        c = torch.tensor([env.sphere_c[i] for i in range(dim)], device=samples.device, dtype=samples.dtype)
+        dist = torch.linalg.norm(samples - c, dim=-1) - env.sphere_r
+        vel = vel*(torch.clamp(dist, 0, eps)/eps).unsqueeze(-1)
+    mask = 7 if env.kind == 1 else env.wall_mask
+    ws = []
+    for j in range(vel.shape[-1]):
+        if (mask >> j) & 1 and j < dim:
+            ws.append(torch.min((samples[..., j] - env.lo[j]).abs().clamp(min=0, max=eps), (samples[..., j] - env.hi[j]).abs().clamp(min=0, max=eps))/eps)
+        else:
+            ws.append(torch.ones_like(samples[..., 0]))
+    return torch.stack(ws, dim=-1).detach()*vel
 
 
 _configured = False

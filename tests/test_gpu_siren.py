@@ -160,6 +160,51 @@ def test_fused_envelope_matches_reference_query_velocity(siren, shape):
     assert (ytc - yr).abs().max().item() <= 1e-4*scale
 
 
+@pytest.mark.parametrize("scenario", ["karman", "smoke_obs"])
+def test_general_envelope_matches_reference_query_velocity(siren, scenario):
+    """The karman (base.py:169-181) and smoke_obs (3d base.py:224-244) branches of query_velocity inside the kernels:
+    region override, obstacle weight (NOT detached: its gradient reaches x), wall weights; forward on both kernels
+    and backward against stock autograd on the torch transcription of the reference (siren.envelope_reference)."""
+    if scenario == "karman":
+        shape, size, eps = (2, 128, 2, 2), (-1.0, 1.0, -0.4, 0.4), 0.15
+        env = siren.karman_envelope(size, eps, centre=(-0.3, 0.05), radius=0.12, karman_vel=0.5)
+    else:
+        shape, size, eps = (3, 64, 5, 3), (-1.0, 1.0)*3, 0.2
+        env = siren.smoke_obs_envelope(size, eps, centre=(0.1, 0.0, 0.2), radius=0.25, inlet_centre=(0.0, 0.0, -0.6), inlet_radius=0.3)
+    dim = shape[0]
+    net = _net(siren, shape, seed=41)
+    lo = torch.tensor(size[0::2], device="cuda"); hi = torch.tensor(size[1::2], device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(43)
+    x = (torch.rand(6000, dim, device="cuda", generator=g)*(hi - lo)*1.04 + lo - 0.02*(hi - lo)).requires_grad_(True)
+    y = net(x, envelope=env)
+    w = torch.randn(y.shape, device="cuda", generator=g)
+    grads = torch.autograd.grad((y*w).sum() + (y**2).sum(), [x] + list(net.parameters()))
+    xr = x.detach().clone().requires_grad_(True)
+    yr = siren.envelope_reference(env, xr, net.forward_reference(xr))
+    grads_r = torch.autograd.grad((yr*w).sum() + (yr**2).sum(), [xr] + list(net.parameters()))
+    scale = yr.abs().max().item()
+    # every part of the envelope is exercised by the sample set
+    dist = torch.linalg.norm(x.detach() - torch.tensor([env.sphere_c[i] for i in range(dim)], device="cuda"), dim=-1) - env.sphere_r
+    assert ((dist > 0) & (dist < eps)).sum() > 100 and (dist < 0).sum() > 20
+    assert (y - yr).abs().max().item() <= 3e-5*scale
+    gx, gxr = grads[0], grads_r[0]
+    assert (gx - gxr).abs().max().item() <= 5e-4*gxr.abs().max().item() + 1e-9
+    for a, b in zip(grads[1:], grads_r[1:]):
+        assert (a - b).abs().max().item() <= 5e-4*b.abs().max().item() + 1e-9
+    # the obstacle weight contributes to dL/dx: without it the input gradient would be off by far more than the tolerance
+    yd = siren.envelope_reference(env, xr, net.forward_reference(xr).detach())
+    gobs = torch.autograd.grad((yd*w).sum() + (yd**2).sum(), xr)[0]
+    assert gobs.abs().max().item() > 50*5e-4*gxr.abs().max().item()
+    with torch.no_grad():
+        net.tensor_cores = True
+        ytc = net(x.detach(), envelope=env)
+        net.tensor_cores = False
+    assert (ytc - yr).abs().max().item() <= 1e-4*scale
+    with pytest.raises(RuntimeError, match="eps"):
+        bad = siren.wall_envelope(size, 0.0)
+        net(x.detach(), envelope=bad)
+
+
 def test_direct_fit_iteration_equals_autograd_iteration(siren):
     """DirectFit.iterate (no autograd, 5 launches) vs loss.backward() + FusedAdam on the same data."""
     shape = (2, 64, 6, 2)
