@@ -22,8 +22,26 @@ import util  # noqa: E402
 import __graft_entry__ as ge  # noqa: E402
 
 
+def build(args, pkg, st):
+    """(stepper, initial-velocity function, network shape, description) for the chosen example configuration."""
+    if args.case == "taylorgreen":
+        cfg = util.load_case("taylorgreen_shipped" if args.watertight else "taylorgreen_active")
+        size = (0.0, 2*math.pi, 0.0, 2*math.pi)
+        s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1)
+        tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
+        return s, cfg, tg, (6, 64), "taylorgreen step (SIREN 6x64, batch 64^2, dt 1e-3), 512^2 pressure samples x 500 walks, 1002^2 divergence grid"
+    # examples/karman/run.sh: SIREN 2x128, batch 128^2, dt 0.05, bdry_eps 3e-2, karman_vel 0.5, reset_wts 1, wost_resolution 512
+    cfg = util.load_case("karman")
+    centre, radius, size = util.karman_obstacle(cfg["output"]["boundaryDistanceMask"])
+    s = st.SplitStepper(cfg, scene_size=size, hidden_features=128, num_hidden_layers=2, dt=0.05, lr=1e-5, sample_resolution=128,
+                        wost_resolution=512, grid_resolution=1000, bdry_eps=3e-2, max_n_iters=args.iters, early_stop=False,
+                        use_cuda_graph=not args.no_graph, boundary="karman", obstacle=(centre, radius), karman_vel=0.5, reset_wts=True, seed=1)
+    return s, cfg, s.karman_initial_velocity, (2, 128), "karman step (SIREN 2x128, batch 128^2, dt 0.05, reset_wts), <= 512^2 pressure samples outside the cylinder x 500 walks, 401x1002 divergence grid"
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="taylorgreen", choices=["taylorgreen", "karman"])
     ap.add_argument("--iters", type=int, default=1000, help="Adam iterations per fit (reference: 10000)")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--watertight", action="store_true")
@@ -32,11 +50,8 @@ def main():
     args = ap.parse_args()
     pkg = ge.load_package()
     st = import_module(pkg.__name__ + ".stepper")
-    cfg = util.load_case("taylorgreen_shipped" if args.watertight else "taylorgreen_active")
-    size = (0.0, 2*math.pi, 0.0, 2*math.pi)
-    s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1)
-    tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
-    s.fit_initial(tg, 300, lr=1e-3)
+    s, cfg, init_fn, (n_hidden, hidden), what = build(args, pkg, st)
+    s.fit_initial(init_fn, 300, lr=1e-3)
     s.step(50)  # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -50,20 +65,21 @@ def main():
     total = time.perf_counter() - t0
     ours = args.steps/total
 
-    # reference arrangement of the same step
+    # reference arrangement of the same step: stock torch ops + torch Adam + one loss.item() per iteration (base.py:142)
     S = pkg.load_siren()
-    net = S.FusedSiren(2, 2, 6, 64, nonlinearity="sine").cuda(); prev = S.FusedSiren(2, 2, 6, 64, nonlinearity="sine").cuda()
+    net = S.FusedSiren(2, 2, n_hidden, hidden, nonlinearity="sine").cuda(); prev = S.FusedSiren(2, 2, n_hidden, hidden, nonlinearity="sine").cuda()
     opt = torch.optim.Adam(net.parameters(), lr=1e-5)
+    nb = s.sample_resolution**2
 
     def ref_iter():
-        x = s.sample_random(64*64)
+        x = s.sample_random(nb)
         with torch.no_grad():
-            pu = prev.forward_reference(x)*s.envelope(x)
-            back = (x - pu*s.dt).clamp(0, 2*math.pi)
-            adv = prev.forward_reference(back)*s.envelope(back)
-        loss = torch.mean((net.forward_reference(x)*s.envelope(x) - adv)**2)
+            pu = s.apply_envelope_reference(x, prev.forward_reference(x))
+            back = torch.clamp(x - pu*s.dt, min=s._lo, max=s._hi)
+            adv = s.apply_envelope_reference(back, prev.forward_reference(back))
+        loss = torch.mean((s.apply_envelope_reference(x, net.forward_reference(x)) - adv)**2)
         opt.zero_grad(); loss.backward(retain_graph=True); opt.step()
-        return loss.item()  # base.py:142
+        return loss.item()
     for _ in range(20):
         ref_iter()
     torch.cuda.synchronize(); t = time.perf_counter()
@@ -74,18 +90,20 @@ def main():
     div = s.last["div"].cpu().numpy()
     from oracle import refbind
     threads = os.cpu_count() or 1
+    n_press = int(s.last["pressure_samples"].shape[0])
+    pts = s.last["pressure_samples"][: args.cpu_sample].cpu().numpy()
     t = time.perf_counter()
     sc = refbind.RefScene(2, cfg["scene"], div)
-    pts = util.random_points(np.array([0, 0], np.float32), np.array([2*math.pi]*2, np.float32), args.cpu_sample, seed=5)
     sc.wost(cfg["solver"], cfg["output"], pts, seed=1, nthreads=threads)
-    cpu_wost_s = (time.perf_counter() - t)*(512*512/args.cpu_sample)
+    cpu_wost_s = (time.perf_counter() - t)*(n_press/len(pts))
     ref_step_s = 2*args.iters*ref_iter_ms*1e-3 + cpu_wost_s
-    print(json.dumps({"metric": "sim_steps_per_sec", "value": ours, "unit": "steps/s", "config": {"workload": "taylorgreen step, %d Adam iterations per fit, 512^2 pressure samples x 500 walks, 1002^2 divergence grid" % args.iters,
-                                                                                              "scene": "as shipped (isWatertight)" if args.watertight else "solver active (isWatertight:false)",
-                                                                                              "cuda_graph": not args.no_graph},
+    print(json.dumps({"metric": "sim_steps_per_sec", "value": ours, "unit": "steps/s",
+                      "config": {"workload": "%s, %d Adam iterations per fit" % (what, args.iters), "case": args.case,
+                                 "scene": ("as shipped (isWatertight)" if args.watertight else "solver active (isWatertight:false)") if args.case == "taylorgreen" else "as shipped",
+                                 "cuda_graph": not args.no_graph},
                       "ms_per_step": 1e3*total/args.steps, "breakdown_ms_per_step": {k: v/args.steps for k, v in parts.items()},
-                      "walks_per_step": int(s.last["walks"]), "wost_kernel_ms": s.last["wost_ms"],
-                      "reference_arrangement": {"fit_iteration_ms_stock_torch": ref_iter_ms, "cpu_wost_s_extrapolated_from_%d_points" % args.cpu_sample: cpu_wost_s,
+                      "walks_per_step": int(s.last["walks"]), "pressure_samples": n_press, "wost_kernel_ms": s.last["wost_ms"],
+                      "reference_arrangement": {"fit_iteration_ms_stock_torch": ref_iter_ms, "cpu_wost_s_extrapolated_from_%d_points" % len(pts): cpu_wost_s,
                                                 "cores": threads, "step_s": ref_step_s, "steps_per_sec": 1.0/ref_step_s}}), flush=True)
 
 

@@ -21,7 +21,7 @@ import ctypes as C
 import torch
 
 from . import capi, zombie
-from .siren import FusedSiren, DirectFit, wall_envelope
+from .siren import FusedSiren, DirectFit, wall_envelope, karman_envelope, envelope_reference
 
 
 def sample_uniform_2d(resolution, size, device, with_boundary=True):
@@ -42,13 +42,17 @@ def sample_uniform_2d(resolution, size, device, with_boundary=True):
 
 
 class SplitStepper:
-    """2D split stepper on a rectangular domain `scene_size` = (x0, x1, y0, y1) with the wall envelope of the
-    reference's taylorgreen branch (boundary='taylorgreen') or no envelope (boundary=None)."""
+    """2D split stepper on a rectangular domain `scene_size` = (x0, x1, y0, y1) with the envelope of the reference's
+    taylorgreen branch (boundary='taylorgreen': wall weights), of its karman branch (boundary='karman': inlet strip,
+    no-slip cylinder `obstacle` = (centre, radius), wall weight on v; samples inside the cylinder are not used,
+    base.py:239-241) or no envelope (boundary=None).  reset_wts re-initialises the network before every fit
+    (create_optimizer(reset=True), model_split.py:44-62; the karman example runs with --reset_wts 1)."""
 
     def __init__(self, wost_config, scene_size, hidden_features=64, num_hidden_layers=6, dt=0.001, lr=1e-5,
                  sample_resolution=64, wost_resolution=512, grid_resolution=1000, bdry_eps=1e-3, max_n_iters=10000,
                  early_stop=True, check_every=100, boundary="taylorgreen", mode=capi.MODE_FAST, seed=0, device=0,
-                 use_cuda_graph=True, tensor_cores=True, init_velocity=None, init_iters=0):
+                 use_cuda_graph=True, tensor_cores=True, init_velocity=None, init_iters=0, obstacle=None, karman_vel=0.5,
+                 reset_wts=False):
         self.dev = torch.device("cuda", device)
         self.cfg = wost_config
         self.size = tuple(float(v) for v in scene_size)
@@ -69,7 +73,18 @@ class SplitStepper:
         self.opts = zombie.solver_opts(wost_config["solver"], wost_config["output"], mode=mode, seed=seed)
         self.timestep, self.seed = 0, seed
         self.last = {}
-        self.env = wall_envelope(self.size, bdry_eps) if boundary == "taylorgreen" else None
+        self.obstacle, self.karman_vel, self.reset_wts = obstacle, float(karman_vel), bool(reset_wts)
+        if boundary == "taylorgreen":
+            self.env = wall_envelope(self.size, bdry_eps)
+        elif boundary == "karman":
+            if obstacle is None:
+                raise ValueError("boundary='karman' needs obstacle=(centre, radius)")
+            self.env = karman_envelope(self.size, bdry_eps, obstacle[0], obstacle[1], karman_vel)
+            self._obs_c = torch.tensor([float(obstacle[0][0]), float(obstacle[0][1])], device=self.dev)
+        elif boundary is None:
+            self.env = None
+        else:
+            raise ValueError("boundary must be 'taylorgreen', 'karman' or None")
         self._lo = torch.tensor([self.size[0], self.size[2]], device=self.dev)
         self._hi = torch.tensor([self.size[1], self.size[3]], device=self.dev)
         if init_velocity is not None and init_iters > 0:
@@ -77,6 +92,7 @@ class SplitStepper:
 
     # ---- network + envelope (base.py:158-224, taylorgreen branch) ---------------------------------------------
     def envelope(self, samples):
+        """Multiplicative wall weights of the taylorgreen branch as a tensor (tests); see apply_envelope_reference."""
         if self.boundary != "taylorgreen":
             return None
         s, e = self.size, self.eps
@@ -89,14 +105,41 @@ class SplitStepper:
         net = self.velocity_field_prev if use_prev else self.velocity_field
         return net(samples, envelope=self.env)
 
-    def sample_random(self, n):
-        """sample_random_2D (utils/model_utils.py:22-31)."""
-        return torch.rand(n, 2, device=self.dev)*(self._hi - self._lo) + self._lo
+    def apply_envelope_reference(self, samples, net_vel):
+        """query_velocity's boundary treatment with stock torch ops (what the fused kernels replace)."""
+        return envelope_reference(self.env, samples, net_vel)
+
+    def obstacle_distance(self, samples):
+        """circle_obstable_functions (main.py:101-104): signed distance to the cylinder."""
+        return torch.linalg.norm(samples - self._obs_c, dim=-1) - self.obstacle[1]
+
+    def sample_random(self, n, keep_shape=True):
+        """sample_in_training with the 'random' pattern (base.py:225-241, utils/model_utils.py:22-31).  With an
+        obstacle the reference drops the samples inside it (a batch a fraction of a percent smaller); here a sample
+        inside is redrawn once so that the batch keeps its shape (CUDA-graph replay), or, with keep_shape=False,
+        dropped exactly like the reference."""
+        x = torch.rand(n, 2, device=self.dev)*(self._hi - self._lo) + self._lo
+        if self.boundary == "karman":
+            if keep_shape:
+                x2 = torch.rand(n, 2, device=self.dev)*(self._hi - self._lo) + self._lo
+                x = torch.where((self.obstacle_distance(x) > 0).unsqueeze(-1), x, x2)
+            else:
+                x = x[self.obstacle_distance(x) > 0]
+        return x
 
     # ---- fit loops ---------------------------------------------------------------------------------------------
+    def _reset_weights(self):
+        net = self.velocity_field
+        with torch.no_grad():
+            net.net.apply(net.weight_init)
+            if net.first_layer_init is not None:
+                net.net[0].apply(net.first_layer_init)
+
     def _loop(self, iteration, n_iters):
         """_training_loop (base.py:129-152) without autograd and without a host sync per iteration:
         `iteration()` returns (samples, target); the MSE fit step is DirectFit.iterate (5 launches)."""
+        if self.reset_wts:
+            self._reset_weights()
         fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2)
         loss_buf = torch.zeros((), device=self.dev)
 
@@ -161,7 +204,7 @@ class SplitStepper:
         return p, g
 
     def project_velocity(self, n_iters=None):
-        samples_all = self.sample_random(self.wost_resolution**2).contiguous()
+        samples_all = self.sample_random(self.wost_resolution**2, keep_shape=False).contiguous()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         p, grad_p = self.pressure_solve(samples_all)
@@ -191,6 +234,11 @@ class SplitStepper:
         self.timestep += 1
         self.opts.seed = (self.seed + self.timestep) & 0xFFFFFFFFFFFFFFFF
         return {"advect_iters": it_a, "advect_loss": loss_a, "project_iters": it_p, "project_loss": loss_p}
+
+    def karman_initial_velocity(self, samples):
+        """karman_vortex_velocity (sources.py:34-43): (karman_vel, 0) times the obstacle weight."""
+        w = torch.clamp(self.obstacle_distance(samples), 0, self.eps)/self.eps
+        return torch.stack([self.karman_vel*w, torch.zeros_like(w)], dim=-1)
 
     def fit_initial(self, velocity_fn, n_iters, lr=1e-4):
         """Fit the network to an analytic initial velocity (main.py: initial condition fit)."""

@@ -159,3 +159,45 @@ def test_taylor_green_velocity_error_tracks_the_reference_arrangement(oracle_lib
     print("default mode + graph replay:", fast)
     assert all(math.isfinite(e) for e in fast)
     assert 0.5*ref[-1] <= fast[-1] <= 2.0*ref[-1], (fast, ref)
+
+
+def _karman_stepper(**kw):
+    pkg = util.package()
+    st = import_module(pkg.__name__ + ".stepper")
+    cfg = util.load_case("karman")
+    centre, radius, size = util.karman_obstacle(cfg["output"]["boundaryDistanceMask"])
+    args = dict(scene_size=size, hidden_features=128, num_hidden_layers=2, dt=0.05, lr=1e-5, grid_resolution=250, wost_resolution=64,
+                sample_resolution=32, bdry_eps=3e-2, max_n_iters=40, check_every=10, boundary="karman", obstacle=(centre, radius),
+                karman_vel=0.5, seed=5, device=0)
+    args.update(kw)
+    return pkg, st.SplitStepper(cfg, **args)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_karman_configuration_steps(graph):
+    """examples/karman shape (SIREN 2x128, inlet strip + no-slip cylinder + wall envelope, --reset_wts 1, samples
+    inside the cylinder unused): the divergence grid equals stock autograd through the reference's query_velocity
+    (the obstacle weight is differentiated, base.py:352-358), and a step runs end to end on the device."""
+    pkg, s = _karman_stepper(use_cuda_graph=graph, reset_wts=True)
+    s.fit_initial(s.karman_initial_velocity, 200, lr=1e-3)
+    div = s.divergence_grid()
+    x = s.grid_samples.detach().clone().requires_grad_(True)
+    u = s.apply_envelope_reference(x, s.velocity_field_prev.forward_reference(x))
+    ref = 0.0
+    for i in range(2):
+        ref = ref + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=True)[0][:, i]
+    ref = (-ref).reshape(s.grid_shape)
+    assert tuple(div.shape) == tuple(ref.shape) and div.shape[1] > div.shape[0]   # channel: more columns (x) than rows (y)
+    assert (div - ref).abs().max().item() <= 5e-4*ref.abs().max().item() + 1e-6
+    xs = s.sample_random(20000)
+    assert xs.shape == (20000, 2) and (s.obstacle_distance(xs) > 0).float().mean().item() > 0.9999
+    assert s.sample_random(20000, keep_shape=False).shape[0] < 20000
+    w0 = s.velocity_field.net[0].weight.detach().clone()
+    out = s.step()
+    assert out["advect_iters"] == 40 and out["project_iters"] == 40
+    assert math.isfinite(out["advect_loss"].item()) and math.isfinite(out["project_loss"].item())
+    assert (s.obstacle_distance(s.last["pressure_samples"]) > 0).all() and s.last["pressure_samples"].shape[0] < 64*64
+    assert s.last["walks"] > 0 and torch.isfinite(s.last["grad_p"]).all()
+    assert (s.velocity_field.net[0].weight.detach() - w0).abs().max().item() > 1e-3   # reset_wts: re-initialised before each fit
+    inlet = torch.tensor([[s.size[0] + 0.5*s.eps, 0.5*(s.size[2] + s.size[3])]], device="cuda")
+    assert s.query_velocity(inlet)[0, 0].item() == pytest.approx(0.5, rel=1e-5)   # inlet strip: u = karman_vel (far from the cylinder)
