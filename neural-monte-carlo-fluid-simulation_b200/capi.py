@@ -123,7 +123,10 @@ class SceneHandle:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().nmc_scene_destroy(self._h)
+            try:
+                lib().nmc_scene_destroy(self._h)
+            except TypeError:  # interpreter shutdown: module globals are already gone, the driver reclaims the memory
+                pass
             self._h = None
 
     __del__ = close

@@ -4,10 +4,11 @@
 // sequential per-point loop of estimateSolutionAndGradient, :466-617):
 //   * the grid is persistent: smCount x (resident CTAs per SM) CTAs, every WARP pulls sample points
 //     from a global atomic queue, so long and short points balance across the 148 SMs;
-//   * inside a warp one LANE runs one walk at a time.  A point's antithetic pairs are handed out to
-//     lanes through a ballot/popc compaction: every loop trip, lanes whose pair has finished are
-//     ranked with __ballot_sync/__popc and take the next pair indices, so lanes whose walks have
-//     terminated are refilled immediately instead of idling until the longest walk ends;
+//   * inside a warp one LANE runs one walk at a time.  A point's walks (two per antithetic pair) are handed
+//     out to lanes through a ballot/popc compaction: every loop trip, lanes whose walk has finished are
+//     ranked with __ballot_sync/__popc and take the next walk indices, so lanes whose walks have
+//     terminated are refilled immediately instead of idling until the longest walk ends; the two walks of a
+//     pair may run on different lanes (mirrored first-ball samples, same walk stream);
 //   * every loop trip each busy lane executes exactly one walk-on-stars step (geometric queries, radial
 //     inverse-CDF sample of the ball Green's function, source-grid gather, bookkeeping);
 //   * the first-ball source samples of a point (one per antithetic pair, all in the SAME ball, no geometry)
@@ -64,7 +65,7 @@ __device__ __forceinline__ unsigned warpSumU(unsigned v) {
 }
 
 enum LaneState { kNeedPair = 0, kWalking = 2, kIdle = 3 };
-static constexpr int kFbFields = 8; // first-ball record per pair: d0.xyz, e0.xyz, firstSource, sfr
+static constexpr int kFbFields = 9; // first-ball record per pair: d0.xyz, e0.xyz, firstSource (walk 0), firstSource (twin), sfr
 
 #ifndef NMC_MINB
 #define NMC_MINB 8   // 64 registers/thread, 32 warps/SM: measured best on B200 (profiles/README.md)
@@ -165,7 +166,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 			float pendTot = 0.0f, pendCnt = 0.0f, pendFirst = 0.0f; // this lane's finished walks not yet folded in
 
 			int state = kNeedPair;
-			int nextPair = 0, chunkBase = 0, chunkEnd = 0; // warp-uniform; pairs [chunkBase, chunkEnd) are parked in fbuf
+			int nextWalk = 0, chunkBase = 0, chunkEnd = 0; // warp-uniform; walks are handed out one by one (walk w = pair w/nAnti, twin w%nAnti);
+			const int nWalksPt = nPairs*nAnti;             // pairs [chunkBase, chunkEnd) are parked in fbuf
 			int pair = 0, anti = 0, walkLength = 0;
 			bool onNeumann = false;
 			Pcg32 rng; rng.state = 0; rng.inc = 1;
@@ -182,14 +184,18 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						cvTot += warpSum(pendTot); cvCnt += warpSum(pendCnt); cvFirst += warpSum(pendFirst);
 						pendTot = pendCnt = pendFirst = 0.0f;
 					}
-					const int mine = nextPair + __popc(need & ltMask), total = __popc(need);
-					const int lastNeeded = nextPair + total < nPairs ? nextPair + total : nPairs;
-					const bool want = state == kNeedPair && mine < nPairs;
+					// the unit handed to a lane is ONE walk, so the two antithetic walks of a pair may run on different lanes
+					// (same first-ball samples mirrored, same walk stream): half the granularity, a shorter tail per point
+					const int mineW = nextWalk + __popc(need & ltMask), total = __popc(need);
+					const int lastW = nextWalk + total < nWalksPt ? nextWalk + total : nWalksPt;      // exclusive
+					const int mine = nAnti == 2 ? mineW >> 1 : mineW, myAnti = nAnti == 2 ? mineW & 1 : 0;
+					const int lastNeeded = nAnti == 2 ? (lastW + 1) >> 1 : lastW;                      // pairs, exclusive
+					const bool want = state == kNeedPair && mineW < nWalksPt;
 					bool fetched = false;
 #define NMC_FETCH_FIRST_BALL(slot) do { const int sl_ = (slot); \
 						d0 = mk(fbuf[sl_], fbuf[32 + sl_], DIM == 3 ? fbuf[64 + sl_] : 0.0f); \
 						e0 = mk(fbuf[96 + sl_], fbuf[128 + sl_], DIM == 3 ? fbuf[160 + sl_] : 0.0f); \
-						firstSource = fbuf[192 + sl_]; sfr = fbuf[224 + sl_]; fetched = true; } while (0)
+						firstSource = fbuf[(myAnti ? 224 : 192) + sl_]; sfr = fbuf[256 + sl_]; fetched = true; } while (0)
 					if (want && mine < chunkEnd) NMC_FETCH_FIRST_BALL(mine - chunkBase);
 					if (lastNeeded > chunkEnd) {
 						// ---- first-ball source samples of the next 32 pairs, one per lane, converged ---------------
@@ -211,19 +217,20 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							const V3 sdir = sphereDir<DIM, M>(fminf(us0, 1.0f - kEps), fminf(us1, 1.0f - kEps));
 							const V3 be = firstR*sphereDir<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
 							const float uA = r0.nextFloat(), uB = r0.nextFloat();
-							float rs = 0.0f, fsrc = 0.0f, sf = 0.0f;
+							float rs = 0.0f, fsrc = 0.0f, fsrc1 = 0.0f, sf = 0.0f;
 							if (!o.ignoreSource) {
 								float gs, qs; bool hframe;
 								float xs = fb.sampleX(uA, uB, gs, qs, hframe, true); // g, q at the returned x
 								rs = hframe ? xs*fb.R : xs/fb.mu;
 								rs = fminf(fmaxf(rs, 1e-4f), fb.R);        // rClamp, distributions.h:378-379
 								fsrc = normG0*sourceAt<DIM>(S, x0 + rs*sdir);
+								if (nAnti == 2) fsrc1 = normG0*sourceAt<DIM>(S, x0 - rs*sdir); // antithetic twin: mirrored source sample (:532-536)
 								// sourceGradientDirection = d * gradientNorm / G(r)  (walk_on_stars.h:542)
 								sf = hframe ? fb.srcGradFactorHarmonic(xs) : fb.srcGradFactor(qs, gs);
 							}
 							fbuf[lane] = rs*sdir.x; fbuf[32 + lane] = rs*sdir.y; if (DIM == 3) fbuf[64 + lane] = rs*sdir.z;
 							fbuf[96 + lane] = be.x; fbuf[128 + lane] = be.y; if (DIM == 3) fbuf[160 + lane] = be.z;
-							fbuf[192 + lane] = fsrc; fbuf[224 + lane] = sf/fmaxf(rs, 1e-20f);
+							fbuf[192 + lane] = fsrc; fbuf[224 + lane] = fsrc1; fbuf[256 + lane] = sf/fmaxf(rs, 1e-20f);
 						}
 						cTrips++; cLaneSlices += (unsigned)(chunkEnd - chunkBase);
 						__syncwarp();
@@ -232,21 +239,22 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 #undef NMC_FETCH_FIRST_BALL
 					if (state == kNeedPair) {
 						if (want) {
-							pair = mine; anti = 0;
+							pair = mine; anti = myAnti;
 							if (o.useGradientControlVariates) { // running means over the walks finished so far
 								float icnt = 1.0f/fmaxf(cvCnt, 1.0f);
 								bcv = cvTot*icnt; scv = cvFirst*icnt;
 							}
 							walkSeed = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(pair + 1)));
-							// start antithetic walk 0 from the boundary sample
-							pt = x0 + e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = e0;
+							// start from the boundary sample, mirrored for the antithetic twin (:564-567), same walk stream (:579)
+							prevDir = anti ? neg(e0) : e0;
+							pt = x0 + prevDir; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0;
 							throughput = exitT; totalSource = firstSource;
 							rng.state = walkSeed; rng.inc = 1;
 							bl = fb;
 							state = kWalking; cStarted++;
 						} else state = kIdle;
 					}
-					nextPair += total;
+					nextWalk += total;
 				}
 				const unsigned busy = __ballot_sync(kFull, state == kWalking);
 				if (busy == 0u) break;
@@ -346,17 +354,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							nDone++; lenSum += (unsigned)walkLength;
 							pendTot += total; pendCnt += 1.0f; pendFirst += firstSource;
 						}
-						if (anti == 0 && nAnti == 2) {
-							// antithetic twin: mirrored source and boundary samples, same walk stream (:532-536, :564-567, :579)
-							anti = 1;
-							firstSource = o.ignoreSource ? 0.0f : normG0*sourceAt<DIM>(S, x0 - d0);
-							totalSource = firstSource;
-							pt = x0 - e0; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0; prevDir = neg(e0);
-							throughput = exitT;
-							rng.state = walkSeed; rng.inc = 1;
-							bl = fb;
-							cStarted++;
-						} else state = kNeedPair;
+						state = kNeedPair;
 					}
 				}
 			}
