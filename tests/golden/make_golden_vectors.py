@@ -87,6 +87,21 @@ def main():
         np.savez_compressed(os.path.join(OUT, case + ".npz"), **d)
         sc.close()
         print(case, "ok: mean|p| %.3e  completed/started %.3f" % (np.abs(p).mean(), st[:, 9].mean()/500))
+    # (v) option variants (deterministic estimator only)
+    d = {}
+    for case in util.OPTION_CASES:
+        for name in util.OPTION_VARIANTS:
+            cfg = util.load_variant(case, name)
+            dim = cfg["dim"]
+            sc = refbind.RefScene(dim, cfg["scene"], util.source_grid(dim))
+            lo, hi = sc.bbox()
+            pts = util.random_points(lo, hi, 64, seed=21)
+            p, g, st = sc.wost(cfg["solver"], cfg["output"], pts, seed=9, index_offset=0, nthreads=8, want_stats=True)
+            k = case + "/" + name
+            d[k + "/pts"], d[k + "/p"], d[k + "/g"], d[k + "/stats"] = pts, p, g, st
+            sc.close()
+            print("variant", k, "completed/started %.3f  mean walk length %.2f" % (st[:, 9].mean()/cfg["solver"]["nWalks"], st[:, 10].mean()))
+    np.savez_compressed(os.path.join(OUT, "options.npz"), **d)
 
 
 if __name__ == "__main__":

@@ -148,6 +148,44 @@ def test_fast_mode_matches_reference_statistically(pkg, case):
     assert 0.6 < vg < 1.6, "median gradient variance ratio %.3f" % vg
 
 
+@pytest.mark.parametrize("variant", list(util.OPTION_VARIANTS))
+@pytest.mark.parametrize("case", list(util.OPTION_CASES))
+def test_option_variants_in_both_modes(pkg, case, variant):
+    """SURVEY 8(f) rank 2, the part the bindings can express: Tikhonov switch-over after k harmonic steps, double-sided
+    boundaries, control / antithetic variates off, Russian roulette off, maximal spheres, ignoreSource.
+    Deterministic mode against the reference's vectors (same bar as the shipped configs), default mode statistically."""
+    k = np.load(os.path.join(V, "options.npz"))
+    key = case + "/" + variant
+    cfg = util.load_variant(case, variant)
+    dim = cfg["dim"]
+    sc = _scene(pkg, cfg)
+    pts, ref = k[key + "/pts"], k[key + "/stats"]
+    nw = cfg["solver"]["nWalks"]
+    p, g, st12, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_DETERMINISTIC, seed=9, want_stats=True)
+    assert st.walks_started == (nw if variant == "no_anti" else 2*(nw//2))*int((ref[:, 11] > 0).sum())
+    assert (st12[:, 9] == ref[:, 9]).mean() >= 0.98, key
+    assert util.close_mask(p, k[key + "/p"]).mean() >= 0.98 and util.close_mask(g, k[key + "/g"]).mean() >= 0.98, key
+    pf, gf, s, stf = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_FAST, seed=4242, want_stats=True)
+    assert np.isfinite(pf).all() and np.isfinite(gf).all()
+    both = (ref[:, 11] > 0) & (s[:, 11] > 0)
+    if variant == "no_rr":       # every walk runs out of steps and is discarded on both sides
+        assert not ref[:, 9].any() and not s[:, 9].any() and not pf.any()
+        return
+    if variant == "ignore_source":
+        assert not pf.any() and not gf.any() and not k[key + "/p"].any()
+        return
+    nf, nr = np.maximum(s[both, 9], 1), np.maximum(ref[both, 9], 1)
+    assert abs(nf.mean() - nr.mean()) < 0.04*nw, key
+    assert abs(s[both, 10].mean() - ref[both, 10].mean()) < 0.1*max(ref[both, 10].mean(), 0.2), key   # mean walk length
+    z = (s[both, 0] - ref[both, 0])/np.sqrt(s[both, 1]/nf + ref[both, 1]/nr + 1e-30)
+    assert (np.abs(z) < 3.2).mean() >= 0.95 and abs(z.mean()) < 0.5, (key, z.mean())
+    for d in range(dim):
+        zg = (s[both, 2 + d] - ref[both, 2 + d])/np.sqrt(s[both, 5 + d]/nf + ref[both, 5 + d]/nr + 1e-30)
+        assert (np.abs(zg) < 3.2).mean() >= 0.95 and abs(zg.mean()) < 0.5, (key, d, zg.mean())
+    vr = np.median(s[both, 1]/np.maximum(ref[both, 1], 1e-30))
+    assert 0.6 < vr < 1.6, (key, vr)
+
+
 @pytest.mark.parametrize("mode", ["fast", "det"])
 def test_size_independent_properties_at_scale(pkg, mode):
     """Properties checked at a size the CPU oracle would need minutes for: linearity in the source (a power

@@ -116,3 +116,18 @@ def test_oracle_thread_and_shard_invariance(oracle_lib):
     pa, ga, _ = sc.wost(solver, cfg["output"], pts[:30], seed=5, index_offset=0)
     pb, gb, _ = sc.wost(solver, cfg["output"], pts[30:], seed=5, index_offset=30)
     assert_same(np.concatenate([pa, pb]), p1, "shards"); assert_same(np.concatenate([ga, gb]), g1, "shards")
+
+
+@pytest.mark.parametrize("case", list(util.OPTION_CASES))
+def test_oracle_option_variants_against_reference_vectors(oracle_lib, case):
+    """Options beyond the shipped configs (Tikhonov switch-over, double-sided boundaries, variance reduction off,
+    no Russian roulette, maximal spheres, ignoreSource): the C restatement reproduces the reference bit for bit."""
+    k = np.load(os.path.join(V, "options.npz"))
+    for name in util.OPTION_VARIANTS:
+        cfg = util.load_variant(case, name)
+        dim = cfg["dim"]
+        key = case + "/" + name
+        sc = oracle_lib.OracleScene(dim, cfg["scene"], util.source_grid(dim))
+        p, g, st = sc.wost(cfg["solver"], cfg["output"], k[key + "/pts"], seed=9, nthreads=4, want_stats=True)
+        assert np.array_equal(p, k[key + "/p"]) and np.array_equal(g, k[key + "/g"]), key
+        assert np.array_equal(st, k[key + "/stats"]), key

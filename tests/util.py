@@ -77,3 +77,25 @@ def karman_obstacle(mask=1e-3):
     inner = np.unique(inner, axis=0)
     c = inner.mean(0)
     return (float(c[0]), float(c[1])), float(np.linalg.norm(inner - c, axis=1).mean() + mask), (float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1]))
+
+
+# Solver / scene options beyond the shipped configs that the bindings can express:
+# name -> (scene overrides, solver overrides).  Golden vectors: tests/golden/vectors/options.npz.
+OPTION_VARIANTS = {
+    "tikhonov2": ({}, {"setpsBeforeApplyingTikhonov": 2}),                       # two harmonic steps, then screened (walk_on_stars.h:319-321)
+    "harmonic_then_yukawa": ({}, {"setpsBeforeApplyingTikhonov": 1, "maxWalkLength": 64}),
+    "doublesided": ({"isDoubleSided": True}, {}),                                # normal flipping on thin boundaries (:154-160)
+    "no_cv": ({}, {"disableGradientControlVariates": True}),
+    "no_anti": ({}, {"disableGradientAntitheticVariates": True, "nWalks": 120}),
+    "no_rr": ({}, {"russianRouletteThreshold": 0.0, "maxWalkLength": 256}),      # nothing stops a walk: all exceed the length and are discarded
+    "maxsph": ({}, {"setpsBeforeUsingMaximalSpheres": 1}),
+    "ignore_source": ({}, {"ignoreSource": True}),
+}
+OPTION_CASES = ("karman", "karman3d")
+
+
+def load_variant(case, variant):
+    cfg = load_case(case)
+    so, sv = OPTION_VARIANTS[variant]
+    cfg["scene"].update(so); cfg["solver"].update(sv)
+    return cfg
