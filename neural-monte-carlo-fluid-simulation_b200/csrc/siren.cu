@@ -14,6 +14,7 @@
 // This is the exact-fp32 path (parity with torch within summation-order error); the tensor-core path for
 // large inference batches is csrc/siren_tc.cu.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
@@ -239,6 +240,210 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 	}
 }
 
+// ---- small-batch variants: one sample's layer split over H/16 threads -------------------------------------------
+// The fit loops run on 4096-16384 samples.  With a thread per sample that is 32-128 CTAs of 4 warps: most of the
+// 148 SMs idle and nothing hides latency.  Here a CTA takes 32 samples (the lanes of a warp) and warp g computes
+// neurons [16 g, 16 g + 16) of every layer for them, so a batch of 4096 is 128 CTAs of H/16 warps and the weights
+// are read from shared memory as warp-wide broadcasts.  Activations (forward) / deltas (backward) of a layer are
+// exchanged through a double-buffered [H][32] array; the last layer and dL/dx are reduced across the warps.
+constexpr int kTS = 32;
+
+template <int H>
+__global__ void __launch_bounds__(2*H, H == 128 ? 2 : 4)
+sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+				  float* __restrict__ y, float* __restrict__ zSaved) {
+	extern __shared__ float smem[];
+	constexpr int LD = H + 4, NT = 2*H;
+	float* Wt = smem;                   // [H][LD]  Wt[k][nn] = W_l[nn][k]
+	float* act = Wt + H*LD;             // [2][H][kTS]
+	float* part = act + 2*H*kTS;        // [H/16][3][kTS]
+	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = 16*g;
+	const int last = nHidden + 1;
+	for (long long tile = blockIdx.x; tile*kTS < n; tile += gridDim.x) {
+		const long long s = tile*kTS + lane;
+		const bool live = s < n;
+		float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+		if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
+		float a16[16];
+#pragma unroll
+		for (int j = 0; j < 16; j++) { // first layer: in -> H
+			const float* w = &P.W[0][(n0 + j)*inDim];
+			float z = __ldg(&P.b[0][n0 + j]) + __ldg(w)*x0;
+			if (inDim > 1) z += __ldg(w + 1)*x1;
+			if (inDim > 2) z += __ldg(w + 2)*x2;
+			if (zSaved && live) zSaved[(size_t)(n0 + j)*n + s] = z;
+			a16[j] = sinReduced(w0*z);
+			act[(n0 + j)*kTS + lane] = a16[j];
+		}
+		int cur = 0;
+		for (int l = 1; l <= nHidden; l++) {
+			__syncthreads(); // act[cur] is complete, nobody reads Wt any more
+			// transposing copy, bank-conflict free: a warp writes an 8 (k) x 4 (nn) patch = banks 4 kk + nq
+			for (int idx = tid; idx < H*H; idx += NT) {
+				const int b = idx >> 5, kk = idx & 7, nq = (idx >> 3) & 3;
+				const int k = (b % (H/8))*8 + kk, nn = (b/(H/8))*4 + nq;
+				Wt[k*LD + nn] = __ldg(&P.W[l][nn*H + k]);
+			}
+			__syncthreads();
+			float acc[16];
+#pragma unroll
+			for (int j = 0; j < 16; j++) acc[j] = __ldg(&P.b[l][n0 + j]);
+			const float* ac = act + cur*H*kTS + lane;
+#pragma unroll 8
+			for (int k = 0; k < H; k++) {
+				const float av = ac[k*kTS];
+				const float4* w = reinterpret_cast<const float4*>(&Wt[k*LD + n0]);
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const float4 v = w[q];
+					acc[4*q + 0] += av*v.x; acc[4*q + 1] += av*v.y; acc[4*q + 2] += av*v.z; acc[4*q + 3] += av*v.w;
+				}
+			}
+			cur ^= 1;
+			float* an = act + cur*H*kTS + lane;
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				if (zSaved && live) zSaved[((size_t)l*H + n0 + j)*n + s] = acc[j];
+				a16[j] = sinReduced(w0*acc[j]);
+				an[(n0 + j)*kTS] = a16[j];
+			}
+		}
+		// last layer: H -> out, partial dot products over this warp's 16 neurons
+		for (int j = 0; j < outDim; j++) {
+			float pj = 0.0f;
+#pragma unroll
+			for (int i = 0; i < 16; i++) pj += __ldg(&P.W[last][j*H + n0 + i])*a16[i];
+			part[(g*3 + j)*kTS + lane] = pj;
+		}
+		__syncthreads();
+		if (g == 0) {
+			float yo[3] = {0.0f, 0.0f, 0.0f};
+			for (int j = 0; j < outDim; j++) {
+				float z = __ldg(&P.b[last][j]);
+				for (int q = 0; q < H/16; q++) z += part[(q*3 + j)*kTS + lane];
+				if (j == 0) yo[0] = z; else if (j == 1) yo[1] = z; else yo[2] = z;
+			}
+			if (env.active) { const float xs[3] = {x0, x1, x2}; nmc_siren_detail::envForward(env, inDim, outDim, xs, yo); }
+			if (live) {
+				y[s*outDim] = yo[0];
+				if (outDim > 1) y[s*outDim + 1] = yo[1];
+				if (outDim > 2) y[s*outDim + 2] = yo[2];
+			}
+		}
+		// the next tile writes act[0] (read last before the barrier above) and `part` only after two more barriers
+	}
+}
+
+template <int H>
+__global__ void __launch_bounds__(2*H, H == 128 ? 2 : 4)
+sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
+				   const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ gx,
+				   float* __restrict__ dZ, float* __restrict__ A) {
+	extern __shared__ float smem[];
+	constexpr int LD = H + 4, NT = 2*H;
+	float* Ws = smem;                   // [H][LD]  W_l row-major (nn, k)
+	float* ex = Ws + H*LD;              // [2][H][kTS] delta exchange
+	float* part = ex + 2*H*kTS;         // [H/16][3][kTS]
+	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = 16*g;
+	const int last = nHidden + 1;
+	for (long long tile = blockIdx.x; tile*kTS < n; tile += gridDim.x) {
+		const long long s = tile*kTS + lane;
+		const bool live = s < n;
+		float gy0 = 0.0f, gy1 = 0.0f, gy2 = 0.0f;
+		float gxe[3] = {0.0f, 0.0f, 0.0f}; // gradient reaching x through the obstacle weight of the envelope
+		if (live) {
+			gy0 = gy[s*outDim]; if (outDim > 1) gy1 = gy[s*outDim + 1]; if (outDim > 2) gy2 = gy[s*outDim + 2];
+			if (env.active) {
+				const float xs[3] = {x[s*inDim], inDim > 1 ? x[s*inDim + 1] : 0.0f, inDim > 2 ? x[s*inDim + 2] : 0.0f};
+				float gys[3] = {gy0, gy1, gy2}, yn[3] = {0.0f, 0.0f, 0.0f};
+				const bool viaObstacle = env.sphere && gx != nullptr;
+				if (viaObstacle) { // network output, recomputed by every warp (only the divergence grid takes this path)
+					for (int j = 0; j < outDim; j++) yn[j] = __ldg(&P.b[last][j]);
+#pragma unroll 4
+					for (int k = 0; k < H; k++) {
+						const float ak = sinReduced(w0*zSaved[((size_t)nHidden*H + k)*n + s]);
+						for (int j = 0; j < outDim; j++) yn[j] += __ldg(&P.W[last][j*H + k])*ak;
+					}
+				}
+				nmc_siren_detail::envBackward(env, inDim, outDim, xs, yn, gys, viaObstacle ? gxe : nullptr);
+				gy0 = gys[0]; gy1 = gys[1]; gy2 = gys[2];
+			}
+			if (g == 0) { // rows (L+1)*H .. of dZ: the (envelope-scaled) output gradient, for dW_last = gy'^T A_L^T
+				const size_t r0 = (size_t)(nHidden + 1)*H;
+				dZ[(r0 + 0)*n + s] = gy0;
+				if (outDim > 1) dZ[(r0 + 1)*n + s] = gy1;
+				if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
+			}
+		}
+		float g16[16];
+#pragma unroll
+		for (int i = 0; i < 16; i++) { // g_L = W_last^T gy'
+			float acc = __ldg(&P.W[last][n0 + i])*gy0;
+			if (outDim > 1) acc += __ldg(&P.W[last][H + n0 + i])*gy1;
+			if (outDim > 2) acc += __ldg(&P.W[last][2*H + n0 + i])*gy2;
+			g16[i] = acc;
+		}
+		int cur = 0;
+		for (int l = nHidden; l >= 0; l--) {
+			float* exw = ex + cur*H*kTS + lane;
+#pragma unroll
+			for (int i = 0; i < 16; i++) { // dz_l = g * w0 cos(w0 z_l);  A_l = sin(w0 z_l)
+				const float zl = live ? zSaved[((size_t)l*H + n0 + i)*n + s] : 0.0f;
+				float t = w0*zl*0.15915494309189535f;
+				t -= rintf(t);
+				float sn, cs;
+				__sincosf(6.283185307179586f*t, &sn, &cs);
+				g16[i] = g16[i]*w0*cs;
+				if (live) { dZ[((size_t)l*H + n0 + i)*n + s] = g16[i]; A[((size_t)l*H + n0 + i)*n + s] = sn; }
+				exw[(n0 + i)*kTS] = g16[i];
+			}
+			if (l == 0) break;
+			__syncthreads(); // ex[cur] complete, nobody reads Ws any more
+			for (int idx = tid; idx < H*H/4; idx += NT) {
+				const int nn = idx/(H/4), k4 = idx - nn*(H/4);
+				*reinterpret_cast<float4*>(&Ws[nn*LD + 4*k4]) = __ldg(reinterpret_cast<const float4*>(&P.W[l][nn*H + 4*k4]));
+			}
+			__syncthreads();
+			float acc[16];
+#pragma unroll
+			for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+			const float* er = ex + cur*H*kTS + lane;
+#pragma unroll 8
+			for (int nn = 0; nn < H; nn++) { // g_{l-1}[k] = sum_nn W_l[nn][k] dz[nn]
+				const float dv = er[nn*kTS];
+				const float4* w = reinterpret_cast<const float4*>(&Ws[nn*LD + n0]);
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const float4 v = w[q];
+					acc[4*q + 0] += dv*v.x; acc[4*q + 1] += dv*v.y; acc[4*q + 2] += dv*v.z; acc[4*q + 3] += dv*v.w;
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < 16; i++) g16[i] = acc[i];
+			cur ^= 1;
+		}
+		if (gx) { // dL/dx = W_0^T dz_0: partial sums over this warp's 16 neurons, reduced by warp 0
+			float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+			for (int i = 0; i < 16; i++) {
+				const float* w = &P.W[0][(n0 + i)*inDim];
+				a0 += __ldg(w)*g16[i];
+				if (inDim > 1) a1 += __ldg(w + 1)*g16[i];
+				if (inDim > 2) a2 += __ldg(w + 2)*g16[i];
+			}
+			__syncthreads(); // `part` of the previous tile has been consumed
+			part[(g*3 + 0)*kTS + lane] = a0; part[(g*3 + 1)*kTS + lane] = a1; part[(g*3 + 2)*kTS + lane] = a2;
+			__syncthreads();
+			if (g == 0 && live) {
+				float r[3] = {gxe[0], gxe[1], gxe[2]};
+				for (int q = 0; q < H/16; q++) { r[0] += part[(q*3 + 0)*kTS + lane]; r[1] += part[(q*3 + 1)*kTS + lane]; r[2] += part[(q*3 + 2)*kTS + lane]; }
+				gx[s*inDim] = r[0]; if (inDim > 1) gx[s*inDim + 1] = r[1]; if (inDim > 2) gx[s*inDim + 2] = r[2];
+			}
+		}
+		__syncthreads(); // the next tile reuses ex[0]
+	}
+}
+
 // Backward, stage 2: all weight and bias gradients in ONE launch.  Every gradient is C[i][j] = sum_s P[i][s] Q[j][s]
 // over the batch (P = dZ_l or the scaled output gradient, Q = A_{l-1} or x^T), so the grid is (K-splits, layers):
 // a CTA stages 32-sample tiles of its two operands in shared memory, accumulates a 4x4 register tile per thread
@@ -351,6 +556,14 @@ int fill(Params& P, const nmc_siren_shape* sh, const float* const* W, const floa
 	return 0;
 }
 
+// batches below this size run the split kernels (NMC_SIREN_SPLIT_MAX overrides; 0 disables them)
+bool useSplit(long long n) {
+	static long long limit = -1;
+	if (limit < 0) { const char* e = getenv("NMC_SIREN_SPLIT_MAX"); limit = e ? atoll(e) : 65536; }
+	return n <= limit;
+}
+size_t splitSmem(int H) { return ((size_t)H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/16)*3*kTS)*sizeof(float); }
+
 int smCount() {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
@@ -374,11 +587,25 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 	if (n <= 0) return 0;
 	if (!x || !y) return fail("null buffer");
 	const int H = sh->hidden;
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaError_t e;
+	if (useSplit(n)) { // small batches: a sample's layer split over H/16 threads (see sirenForwardSplit)
+		size_t smemS = splitSmem(H);
+		long long tilesS = (n + kTS - 1)/kTS;
+		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
+		if (H == 64) {
+			e = cudaFuncSetAttribute(sirenForwardSplit<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenForwardSplit<64><<<gridS, 128, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+		} else {
+			e = cudaFuncSetAttribute(sirenForwardSplit<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenForwardSplit<128><<<gridS, 256, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+		}
+		if (!e) e = cudaGetLastError();
+		return e ? fail(cudaGetErrorString(e)) : 0;
+	}
 	size_t smem = ((size_t)H*(H + 4) + (size_t)H*kTile)*sizeof(float);
 	long long tiles = (n + kTile - 1)/kTile;
 	int grid = (int)(tiles < 4ll*smCount() ? tiles : 4ll*smCount());
-	cudaStream_t st = (cudaStream_t)stream;
-	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenForward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (!e) sirenForward<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
@@ -400,11 +627,25 @@ extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const*
 	if (n <= 0) return 0;
 	if (!x || !z_saved || !grad_y || !dZ || !A) return fail("null buffer");
 	const int H = sh->hidden;
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaError_t e;
+	if (useSplit(n)) {
+		size_t smemS = splitSmem(H);
+		long long tilesS = (n + kTS - 1)/kTS;
+		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
+		if (H == 64) {
+			e = cudaFuncSetAttribute(sirenBackwardSplit<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenBackwardSplit<64><<<gridS, 128, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
+		} else {
+			e = cudaFuncSetAttribute(sirenBackwardSplit<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenBackwardSplit<128><<<gridS, 256, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
+		}
+		if (!e) e = cudaGetLastError();
+		return e ? fail(cudaGetErrorString(e)) : 0;
+	}
 	size_t smem = ((size_t)H*(H + 4) + (size_t)H*kTile)*sizeof(float);
 	long long tiles = (n + kTile - 1)/kTile;
 	int grid = (int)(tiles < 4ll*smCount() ? tiles : 4ll*smCount());
-	cudaStream_t st = (cudaStream_t)stream;
-	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenBackwardChain<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (!e) sirenBackwardChain<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
