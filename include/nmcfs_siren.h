@@ -76,6 +76,12 @@ int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, co
 int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
 				  float eps, int64_t step, void* stream);
 
+/* The same update with the step counter in DEVICE memory (int64, zero before the first call): the call first adds
+ * 1 to *step on the stream, then applies the update with the bias corrections of the new value.  This is the variant
+ * to capture in a CUDA graph: a replayed nmc_adam_step would keep the corrections of its capture-time step. */
+int nmc_adam_step_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+						 float eps, long long* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -450,18 +450,18 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 // (hidden layers) or a strided set of scalars (first / last layer), and adds its partial result with atomics.
 constexpr int kGT = 256;   // threads
 constexpr int kGS = 32;    // samples per staged tile
-constexpr int kGChunk = 512; // samples per CTA
+constexpr int kGChunkMax = 512; // samples per CTA at most; small batches use smaller chunks to fill the SMs
 template <int H>
 __global__ void __launch_bounds__(kGT)
 sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __restrict__ x, long long n,
-				const float* __restrict__ dZ, const float* __restrict__ A) {
+				const float* __restrict__ dZ, const float* __restrict__ A, int chunk) {
 	__shared__ float Ps[H][kGS + 1];
 	__shared__ float Qs[H][kGS + 1];
 	const int tid = threadIdx.x;
 	const int l = blockIdx.y;                 // 0 .. nHidden + 1
 	const int last = nHidden + 1;
-	const long long s0 = (long long)blockIdx.x*kGChunk;
-	const long long s1 = s0 + kGChunk < n ? s0 + kGChunk : n;
+	const long long s0 = (long long)blockIdx.x*chunk;
+	const long long s1 = s0 + chunk < n ? s0 + chunk : n;
 	const int RP = l == last ? outDim : H;    // rows of P
 	const int RQ = l == 0 ? inDim : H;        // rows of Q
 	const float* Pg = l == last ? dZ + (size_t)(nHidden + 1)*H*n : dZ + (size_t)l*H*n;
@@ -525,6 +525,28 @@ sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __res
 		for (int o = tid; o < RP*RQ; o += kGT, q++) atomicAdd(&P.gW[l][o], small[q]);
 	}
 	if (tid < RP) atomicAdd(&P.gb[l][tid], bsum);
+}
+
+// Adam with the step counter in device memory: a CUDA graph that replays one fit iteration must not freeze the bias
+// corrections at their capture-time values, so the counter is advanced by a one-thread kernel and read by the update.
+__global__ void adamAdvance(long long* step) { *step += 1; }
+__global__ void adamKernelDev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+							  long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step) {
+	__shared__ float bc[2];
+	if (threadIdx.x == 0) {
+		const double t = (double)*step;
+		bc[0] = (float)(1.0 - pow((double)b1, t));
+		bc[1] = sqrtf((float)(1.0 - pow((double)b2, t)));
+	}
+	__syncthreads();
+	long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float gi = g[i];
+	float mi = b1*m[i] + (1.0f - b1)*gi;
+	float vi = b2*v[i] + (1.0f - b2)*gi*gi;
+	m[i] = mi; v[i] = vi;
+	float denom = sqrtf(vi)/bc[1] + eps;
+	p[i] -= (lr/bc[0])*(mi/denom);
 }
 
 // torch.optim.Adam (no amsgrad, no weight decay) over one flat buffer; step is 1-based
@@ -666,10 +688,24 @@ extern "C" int nmc_siren_weight_grads(const nmc_siren_shape* sh, const float* x,
 	if (!x || !dZ || !A) return fail("null buffer");
 	Params P;
 	for (int l = 0; l < sh->n_hidden_layers + 2; l++) { P.W[l] = nullptr; P.b[l] = nullptr; P.gW[l] = gW[l]; P.gb[l] = gb[l]; if (!gW[l] || !gb[l]) return fail("null layer pointer"); }
-	dim3 grid((unsigned)((n + kGChunk - 1)/kGChunk), (unsigned)(sh->n_hidden_layers + 2));
+	// samples per CTA: as large as possible (fewer atomics) while the hidden layers' CTAs still cover the SMs twice
+	int chunk = kGChunkMax;
+	const int heavy = sh->n_hidden_layers > 0 ? sh->n_hidden_layers : 1;
+	while (chunk > 64 && ((n + chunk - 1)/chunk)*heavy < 2ll*smCount()) chunk >>= 1;
+	dim3 grid((unsigned)((n + chunk - 1)/chunk), (unsigned)(sh->n_hidden_layers + 2));
 	cudaStream_t st = (cudaStream_t)stream;
-	if (sh->hidden == 64) sirenWeightGrad<64><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A);
-	else sirenWeightGrad<128><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A);
+	if (sh->hidden == 64) sirenWeightGrad<64><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A, chunk);
+	else sirenWeightGrad<128><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A, chunk);
+	cudaError_t e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_adam_step_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+									float eps, long long* step, void* stream) {
+	if (n <= 0) return 0;
+	if (!p || !g || !m || !v || !step) return fail("bad arguments");
+	adamAdvance<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

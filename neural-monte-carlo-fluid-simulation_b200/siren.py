@@ -125,6 +125,7 @@ def _lib():
                                          vp, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_weight_grads.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
+        L.nmc_adam_step_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
         _configured = True
     return L
 
@@ -165,7 +166,7 @@ class _SirenFn(torch.autograd.Function):
                 z = torch.empty(((sh.n_hidden_layers + 1)*sh.hidden, n), device=x.device, dtype=torch.float32)
                 _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, _stream()))
                 ctx.save_for_backward(x2, z, *W, *b)
-            elif tensor_cores:
+            elif tensor_cores and n >= 16384:  # smaller batches: the split fp32 kernel beats the per-tile latency of the tcgen05 one
                 _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), env, _stream()))
             else:
                 _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, env, _stream()))
@@ -291,6 +292,7 @@ class FusedAdam:
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev); self.m = torch.zeros(n, device=dev); self.v = torch.zeros(n, device=dev)
         self.g = torch.zeros(n, device=dev)
+        self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)  # Adam's t lives on the device (CUDA-graph replay)
         with torch.no_grad():  # re-home the parameters as views into one flat buffer
             off = 0
             for p in self.params:
@@ -310,12 +312,18 @@ class FusedAdam:
         for p in self.params:
             p.grad = None
 
+    def reset(self):
+        """A fresh optimizer on the same parameters (create_optimizer() at the top of every fit, base.py:133)."""
+        self.m.zero_(); self.v.zero_(); self.step_dev.zero_()
+        self.step_count = 0
+
     def step_flat(self):
-        """Adam step when the gradients were written straight into `grad_views` (no autograd, one kernel)."""
+        """Adam step when the gradients were written straight into `grad_views` (no autograd).  The step counter is
+        advanced on the device, so the call can be captured once in a CUDA graph and replayed."""
         self.step_count += 1
         with torch.cuda.device(self.flat.device):
-            _check(_lib().nmc_adam_step(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
-                                        self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, _stream()))
+            _check(_lib().nmc_adam_step_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                               self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
 
     def step(self):
         self.step_count += 1
@@ -328,8 +336,8 @@ class FusedAdam:
                 self.g[off:off + k].zero_()
             off += k
         with torch.cuda.device(self.flat.device):
-            _check(_lib().nmc_adam_step(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
-                                        self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, _stream()))
+            _check(_lib().nmc_adam_step_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                               self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
 
 
 class DirectFit:

@@ -220,3 +220,42 @@ def test_direct_fit_iteration_equals_autograd_iteration(siren):
         opt.zero_grad(); loss.backward(); opt.step()
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert (pa - pb).abs().max().item() <= 1e-5*pb.abs().max().item() + 1e-8
+
+
+def test_graph_replayed_fit_matches_torch_adam(siren):
+    """The fit iteration captured once in a CUDA graph and replayed (stepper.py) must be torch.optim.Adam step for
+    step: Adam's bias corrections depend on the step number, which therefore lives in device memory
+    (nmc_adam_step_device) instead of being frozen into the graph at capture time."""
+    shape = (2, 64, 6, 2)
+    net = _net(siren, shape, seed=51)
+    ref = _net(siren, shape, seed=51)
+    x = _coords(4096, 2, seed=52)
+    target = torch.stack([torch.sin(3*x[:, 0]), torch.cos(2*x[:, 1])], dim=-1)
+    lr, iters = 1e-4, 60
+    fit = siren.DirectFit(net, lr, None, max_batch=4096)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fit.iterate(x, target)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fit.iterate(x, target)
+    for _ in range(iters - 3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert int(fit.opt.step_dev.item()) == iters
+    opt = torch.optim.Adam(ref.parameters(), lr=lr)
+    for _ in range(iters):
+        loss = torch.mean((ref.forward_reference(x) - target)**2)
+        opt.zero_grad(); loss.backward(); opt.step()
+    moved = 0.0
+    fresh = _net(siren, shape, seed=51)
+    for a, b, c in zip(net.parameters(), ref.parameters(), fresh.parameters()):
+        step = (b - c).abs().max().item()
+        moved = max(moved, step)
+        assert (a - b).abs().max().item() <= 0.02*step + 1e-7   # frozen corrections would be off by a factor of ~5
+    assert moved > 10*lr
+    fit.opt.reset()
+    assert int(fit.opt.step_dev.item()) == 0 and not fit.opt.m.any()
