@@ -73,6 +73,7 @@ class SplitStepper:
         self.opts = zombie.solver_opts(wost_config["solver"], wost_config["output"], mode=mode, seed=seed)
         self.timestep, self.seed = 0, seed
         self.last = {}
+        self._fit, self._graphs, self._proj = None, {}, None
         self.obstacle, self.karman_vel, self.reset_wts = obstacle, float(karman_vel), bool(reset_wts)
         if boundary == "taylorgreen":
             self.env = wall_envelope(self.size, bdry_eps)
@@ -135,31 +136,45 @@ class SplitStepper:
             if net.first_layer_init is not None:
                 net.net[0].apply(net.first_layer_init)
 
-    def _loop(self, iteration, n_iters):
+    def _loop(self, iteration, n_iters, key=None):
         """_training_loop (base.py:129-152) without autograd and without a host sync per iteration:
-        `iteration()` returns (samples, target); the MSE fit step is DirectFit.iterate (5 launches)."""
+        `iteration()` returns (samples, target); the MSE fit step is DirectFit.iterate.  One DirectFit (one flat
+        parameter / Adam buffer) serves every fit and is reset where the reference creates a new optimizer
+        (base.py:133).  With CUDA graphs the iteration of each phase (`key`) is captured ONCE and replayed in every
+        later time step: its inputs live in buffers that persist across steps, and Adam's step counter is on the
+        device.  (Capturing per fit costs a synchronise + allocator flush per phase, i.e. tens to hundreds of ms.)"""
+        if self._fit is None:
+            self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2)
+        fit = self._fit
+        fit.opt.reset()
         if self.reset_wts:
             self._reset_weights()
-        fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2)
-        loss_buf = torch.zeros((), device=self.dev)
+        cached = self._graphs.get(key) if (self.use_graph and key is not None) else None
+        it = 0
+        if cached is not None:
+            graph, loss_buf = cached
+        else:
+            loss_buf = torch.zeros((), device=self.dev)
 
-        def one():
-            samples, target = iteration()
-            diff = fit.iterate(samples, target)
-            loss_buf.copy_(torch.mean(diff*diff))
+            def one():
+                samples, target = iteration()
+                diff = fit.iterate(samples, target)
+                loss_buf.copy_(torch.mean(diff*diff))
 
-        graph, it = None, 0
-        if self.use_graph:
-            side = torch.cuda.Stream(device=self.dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):  # warm-up outside capture
+            graph = None
+            if self.use_graph:
+                side = torch.cuda.Stream(device=self.dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):  # warm-up outside capture
+                        one()
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
                     one()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                one()
-            it = 4
+                it = 3
+                if key is not None:
+                    self._graphs[key] = (graph, loss_buf)
         while it < n_iters:
             if graph is not None:
                 graph.replay()
@@ -181,7 +196,7 @@ class SplitStepper:
                 back = torch.clamp(samples - prev_u*self.dt, min=self._lo, max=self._hi)
                 advected = self.query_velocity(back, use_prev=True)
             return samples, advected
-        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters)
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect")
 
     def divergence_grid(self):
         """-div u_prev on the (res+2)^2 grid, device tensor [rows(y)][cols(x)] (model_split.py:230-243)."""
@@ -212,14 +227,30 @@ class SplitStepper:
         self.last["pressure_ms"] = e0.elapsed_time(e1)
         self.last.update(p=p, grad_p=grad_p, pressure_samples=samples_all)
         n, big = self.sample_resolution**2, samples_all.shape[0]
+        if self.use_graph:  # persistent inputs of the captured iteration: samples, gradients and their count
+            if self._proj is None:
+                cap = self.wost_resolution**2
+                self._proj = (torch.zeros(cap, 2, device=self.dev), torch.zeros(cap, 2, device=self.dev), torch.zeros((), device=self.dev))
+            ps, pg, pc = self._proj
+            ps[:big].copy_(samples_all); pg[:big].copy_(grad_p); pc.fill_(float(big - 1))
 
-        def iteration():
-            idx = torch.randint(0, big - 1, (n,), device=self.dev)  # the reference excludes the last point (:274)
-            samples = samples_all[idx]
-            with torch.no_grad():
-                target = self.query_velocity(samples, use_prev=True) - grad_p[idx]
-            return samples, target
-        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters)
+            def iteration():
+                # uniform index in [0, big - 2] (the reference's randint(0, big - 1) excludes the last point, :274);
+                # the bound is a device scalar so the captured graph serves every step's sample count
+                idx = torch.clamp((torch.rand(n, device=self.dev)*pc).long(), max=cap_idx)
+                samples = ps[idx]
+                with torch.no_grad():
+                    target = self.query_velocity(samples, use_prev=True) - pg[idx]
+                return samples, target
+            cap_idx = ps.shape[0] - 1
+        else:
+            def iteration():
+                idx = torch.randint(0, big - 1, (n,), device=self.dev)  # the reference excludes the last point (:274)
+                samples = samples_all[idx]
+                with torch.no_grad():
+                    target = self.query_velocity(samples, use_prev=True) - grad_p[idx]
+                return samples, target
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="project")
 
     def _sync_prev(self):
         self.velocity_field_prev.load_state_dict(self.velocity_field.state_dict())
