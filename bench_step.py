@@ -30,6 +30,14 @@ def build(args, pkg, st):
         s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1)
         tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
         return s, cfg, tg, (6, 64), "taylorgreen step (SIREN 6x64, batch 64^2, dt 1e-3), 512^2 pressure samples x 500 walks, 1002^2 divergence grid"
+    if args.case == "smoke_obs":
+        # examples/smoke_obs/run.sh: SIREN 5x64 3->3, batch 128^2, dt 0.05, bdry_eps 1e-2, reset_wts 1, wost_resolution 256, 82^3 grid
+        cfg = util.load_case("smoke3d")
+        s = st.SplitStepper(cfg, scene_size=(-1.0, 1.0)*3, hidden_features=64, num_hidden_layers=5, dt=0.05, lr=1e-5, sample_resolution=128,
+                            wost_resolution=256, grid_resolution=80, bdry_eps=1e-2, max_n_iters=args.iters, early_stop=False,
+                            use_cuda_graph=not args.no_graph, boundary="smoke_obs", obstacle=((0.0, 0.0, -0.3), 0.1), reset_wts=True, seed=1)
+        rest = lambda x: torch.zeros_like(x)  # noqa: E731  (the smoke examples start from rest; the inlet ball drives the flow)
+        return s, cfg, rest, (5, 64), "smoke_obs step (SIREN 5x64 3->3, batch 128^2, dt 0.05, reset_wts), 256^2 pressure samples x 500 walks, 82^3 divergence grid"
     # examples/karman/run.sh: SIREN 2x128, batch 128^2, dt 0.05, bdry_eps 3e-2, karman_vel 0.5, reset_wts 1, wost_resolution 512
     cfg = util.load_case("karman")
     centre, radius, size = util.karman_obstacle(cfg["output"]["boundaryDistanceMask"])
@@ -41,7 +49,7 @@ def build(args, pkg, st):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--case", default="taylorgreen", choices=["taylorgreen", "karman"])
+    ap.add_argument("--case", default="taylorgreen", choices=["taylorgreen", "karman", "smoke_obs"])
     ap.add_argument("--iters", type=int, default=1000, help="Adam iterations per fit (reference: 10000)")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--watertight", action="store_true")
@@ -67,7 +75,7 @@ def main():
 
     # reference arrangement of the same step: stock torch ops + torch Adam + one loss.item() per iteration (base.py:142)
     S = pkg.load_siren()
-    net = S.FusedSiren(2, 2, n_hidden, hidden, nonlinearity="sine").cuda(); prev = S.FusedSiren(2, 2, n_hidden, hidden, nonlinearity="sine").cuda()
+    net = S.FusedSiren(s.dim, s.dim, n_hidden, hidden, nonlinearity="sine").cuda(); prev = S.FusedSiren(s.dim, s.dim, n_hidden, hidden, nonlinearity="sine").cuda()
     opt = torch.optim.Adam(net.parameters(), lr=1e-5)
     nb = s.sample_resolution**2
 
@@ -93,7 +101,7 @@ def main():
     n_press = int(s.last["pressure_samples"].shape[0])
     pts = s.last["pressure_samples"][: args.cpu_sample].cpu().numpy()
     t = time.perf_counter()
-    sc = refbind.RefScene(2, cfg["scene"], div)
+    sc = refbind.RefScene(s.dim, cfg["scene"], div)
     sc.wost(cfg["solver"], cfg["output"], pts, seed=1, nthreads=threads)
     cpu_wost_s = (time.perf_counter() - t)*(n_press/len(pts))
     ref_step_s = 2*args.iters*ref_iter_ms*1e-3 + cpu_wost_s

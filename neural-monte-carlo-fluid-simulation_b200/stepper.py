@@ -21,7 +21,7 @@ import ctypes as C
 import torch
 
 from . import capi, zombie
-from .siren import FusedSiren, DirectFit, wall_envelope, karman_envelope, envelope_reference
+from .siren import FusedSiren, DirectFit, wall_envelope, karman_envelope, smoke_obs_envelope, envelope_reference
 
 
 def sample_uniform_2d(resolution, size, device, with_boundary=True):
@@ -41,12 +41,32 @@ def sample_uniform_2d(resolution, size, device, with_boundary=True):
     return coords
 
 
+def sample_uniform_3d(resolution, size, device, with_boundary=True):
+    """src/3d/utils/model_utils.py:3-34 (meshgrid indexing 'ij': result[i][j][k] = (x_i, y_j, z_k), the layout
+    zombie3d's Scene expects).  The reference sizes the z axis with res_y samples (:19); for the cubic domains of
+    all 3D examples the three resolutions coincide, which is what this implements."""
+    ext = [size[1] - size[0], size[3] - size[2], size[5] - size[4]]
+    m = min(ext)
+    res = [int(resolution*e/m) for e in ext]
+    axes = []
+    for r in res:
+        a = torch.linspace(0.5, r - 0.5, r, device=device)
+        if with_boundary:
+            a = torch.cat([torch.tensor([0.0], device=device), a, torch.tensor([r*1.0], device=device)])
+        axes.append(a)
+    coords = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1)
+    for k in range(3):
+        coords[..., k] = coords[..., k]/res[k]*ext[k] + size[2*k]
+    return coords
+
+
 class SplitStepper:
-    """2D split stepper on a rectangular domain `scene_size` = (x0, x1, y0, y1) with the envelope of the reference's
-    taylorgreen branch (boundary='taylorgreen': wall weights), of its karman branch (boundary='karman': inlet strip,
-    no-slip cylinder `obstacle` = (centre, radius), wall weight on v; samples inside the cylinder are not used,
-    base.py:239-241) or no envelope (boundary=None).  reset_wts re-initialises the network before every fit
-    (create_optimizer(reset=True), model_split.py:44-62; the karman example runs with --reset_wts 1)."""
+    """Operator-split stepper on a box domain `scene_size` = (x0, x1, y0, y1[, z0, z1]); 2D or 3D by its length.
+    boundary = 'taylorgreen' / 'walls': wall weights on every component (taylorgreen, vortex_collide branches);
+    'karman' (2D): inlet strip, no-slip cylinder `obstacle` = (centre, radius), wall weight on v, samples inside the
+    cylinder unused (base.py:169-181, 239-241); 'smoke_obs' (3D): inlet ball, no-slip sphere `obstacle`, wall weights
+    (3d base.py:224-244); None: no envelope.  reset_wts re-initialises the network before every fit
+    (create_optimizer(reset=True), model_split.py:44-62; the karman and 3D examples run with --reset_wts 1)."""
 
     def __init__(self, wost_config, scene_size, hidden_features=64, num_hidden_layers=6, dt=0.001, lr=1e-5,
                  sample_resolution=64, wost_resolution=512, grid_resolution=1000, bdry_eps=1e-3, max_n_iters=10000,
@@ -61,45 +81,51 @@ class SplitStepper:
         self.max_n_iters, self.early_stop, self.check_every = max_n_iters, early_stop, check_every
         self.boundary, self.use_graph = boundary, use_cuda_graph
         torch.manual_seed(seed)
-        mk = lambda: FusedSiren(2, 2, num_hidden_layers, hidden_features, nonlinearity="sine", tensor_cores=tensor_cores).to(self.dev)  # noqa: E731
+        self.dim = dim = len(self.size)//2
+        if dim not in (2, 3):
+            raise ValueError("scene_size must have 4 (2D) or 6 (3D) entries")
+        mk = lambda: FusedSiren(dim, dim, num_hidden_layers, hidden_features, nonlinearity="sine", tensor_cores=tensor_cores).to(self.dev)  # noqa: E731
         self.velocity_field, self.velocity_field_prev = mk(), mk()
         for p in self.velocity_field_prev.parameters():
             p.requires_grad_(False)
         # Scene(config, div): built once; the source grid is replaced every step
-        grid = sample_uniform_2d(grid_resolution, self.size, self.dev)
-        self.grid_shape = tuple(grid.shape[:2])
-        self.grid_samples = grid.reshape(-1, 2).contiguous()
+        grid = (sample_uniform_2d if dim == 2 else sample_uniform_3d)(grid_resolution, self.size, self.dev)
+        self.grid_shape = tuple(grid.shape[:dim])
+        self.grid_samples = grid.reshape(-1, dim).contiguous()
         self.scene = zombie.Scene(wost_config["scene"], torch.zeros(self.grid_shape).numpy(), device=device)
         self.opts = zombie.solver_opts(wost_config["solver"], wost_config["output"], mode=mode, seed=seed)
         self.timestep, self.seed = 0, seed
         self.last = {}
         self._fit, self._graphs, self._proj = None, {}, None
         self.obstacle, self.karman_vel, self.reset_wts = obstacle, float(karman_vel), bool(reset_wts)
-        if boundary == "taylorgreen":
+        if boundary in ("taylorgreen", "walls"):
             self.env = wall_envelope(self.size, bdry_eps)
-        elif boundary == "karman":
-            if obstacle is None:
-                raise ValueError("boundary='karman' needs obstacle=(centre, radius)")
-            self.env = karman_envelope(self.size, bdry_eps, obstacle[0], obstacle[1], karman_vel)
-            self._obs_c = torch.tensor([float(obstacle[0][0]), float(obstacle[0][1])], device=self.dev)
+        elif boundary in ("karman", "smoke_obs"):
+            if obstacle is None or dim != (2 if boundary == "karman" else 3):
+                raise ValueError("boundary='karman' (2D) / 'smoke_obs' (3D) needs obstacle=(centre, radius)")
+            if boundary == "karman":
+                self.env = karman_envelope(self.size, bdry_eps, obstacle[0], obstacle[1], karman_vel)
+            else:
+                self.env = smoke_obs_envelope(self.size, bdry_eps, obstacle[0], obstacle[1])
+            self._obs_c = torch.tensor([float(c) for c in obstacle[0]], device=self.dev)
         elif boundary is None:
             self.env = None
         else:
-            raise ValueError("boundary must be 'taylorgreen', 'karman' or None")
-        self._lo = torch.tensor([self.size[0], self.size[2]], device=self.dev)
-        self._hi = torch.tensor([self.size[1], self.size[3]], device=self.dev)
+            raise ValueError("boundary must be 'taylorgreen', 'walls', 'karman', 'smoke_obs' or None")
+        self._lo = torch.tensor(self.size[0::2], device=self.dev)
+        self._hi = torch.tensor(self.size[1::2], device=self.dev)
         if init_velocity is not None and init_iters > 0:
             self.fit_initial(init_velocity, init_iters)
 
     # ---- network + envelope (base.py:158-224, taylorgreen branch) ---------------------------------------------
     def envelope(self, samples):
         """Multiplicative wall weights of the taylorgreen branch as a tensor (tests); see apply_envelope_reference."""
-        if self.boundary != "taylorgreen":
+        if self.boundary not in ("taylorgreen", "walls"):
             return None
         s, e = self.size, self.eps
-        u_w = torch.min((samples[..., 0] - s[0]).abs().clamp(min=0, max=e), (samples[..., 0] - s[1]).abs().clamp(min=0, max=e))/e
-        v_w = torch.min((samples[..., 1] - s[2]).abs().clamp(min=0, max=e), (samples[..., 1] - s[3]).abs().clamp(min=0, max=e))/e
-        return torch.stack([u_w, v_w], dim=-1).detach()
+        w = [torch.min((samples[..., k] - s[2*k]).abs().clamp(min=0, max=e), (samples[..., k] - s[2*k + 1]).abs().clamp(min=0, max=e))/e
+             for k in range(self.dim)]
+        return torch.stack(w, dim=-1).detach()
 
     def query_velocity(self, samples, use_prev=False):
         """network x envelope in ONE kernel (the envelope is fused: include/nmcfs_siren.h nmc_siren_envelope)."""
@@ -119,10 +145,10 @@ class SplitStepper:
         obstacle the reference drops the samples inside it (a batch a fraction of a percent smaller); here a sample
         inside is redrawn once so that the batch keeps its shape (CUDA-graph replay), or, with keep_shape=False,
         dropped exactly like the reference."""
-        x = torch.rand(n, 2, device=self.dev)*(self._hi - self._lo) + self._lo
+        x = torch.rand(n, self.dim, device=self.dev)*(self._hi - self._lo) + self._lo
         if self.boundary == "karman":
             if keep_shape:
-                x2 = torch.rand(n, 2, device=self.dev)*(self._hi - self._lo) + self._lo
+                x2 = torch.rand(n, self.dim, device=self.dev)*(self._hi - self._lo) + self._lo
                 x = torch.where((self.obstacle_distance(x) > 0).unsqueeze(-1), x, x2)
             else:
                 x = x[self.obstacle_distance(x) > 0]
@@ -199,19 +225,20 @@ class SplitStepper:
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect")
 
     def divergence_grid(self):
-        """-div u_prev on the (res+2)^2 grid, device tensor [rows(y)][cols(x)] (model_split.py:230-243)."""
+        """-div u_prev on the grid with boundary samples, as the source array the scene expects: 2D [rows(y)][cols(x)]
+        (model_split.py:230-243), 3D [x][y][z] (3d model_split.py:232-235)."""
         x = self.grid_samples.detach().clone().requires_grad_(True)
         u = self.query_velocity(x, use_prev=True)
         div = 0.0
-        for i in range(2):
-            div = div + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=(i == 0))[0][:, i]
+        for i in range(self.dim):
+            div = div + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=(i < self.dim - 1))[0][:, i]
         return (-div).reshape(self.grid_shape).contiguous()
 
     def pressure_solve(self, samples):
         div = self.divergence_grid()
         self.scene.handle.set_source_device(div.data_ptr(), div.shape)
         n = samples.shape[0]
-        p = torch.empty(n, device=self.dev); g = torch.empty((n, 2), device=self.dev)
+        p = torch.empty(n, device=self.dev); g = torch.empty((n, self.dim), device=self.dev)
         st = capi.SolveStats()
         self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=0,
                                        stream=torch.cuda.current_stream().cuda_stream, stats=st)
@@ -230,7 +257,7 @@ class SplitStepper:
         if self.use_graph:  # persistent inputs of the captured iteration: samples, gradients and their count
             if self._proj is None:
                 cap = self.wost_resolution**2
-                self._proj = (torch.zeros(cap, 2, device=self.dev), torch.zeros(cap, 2, device=self.dev), torch.zeros((), device=self.dev))
+                self._proj = (torch.zeros(cap, self.dim, device=self.dev), torch.zeros(cap, self.dim, device=self.dev), torch.zeros((), device=self.dev))
             ps, pg, pc = self._proj
             ps[:big].copy_(samples_all); pg[:big].copy_(grad_p); pc.fill_(float(big - 1))
 

@@ -201,3 +201,42 @@ def test_karman_configuration_steps(graph):
     assert (s.velocity_field.net[0].weight.detach() - w0).abs().max().item() > 1e-3   # reset_wts: re-initialised before each fit
     inlet = torch.tensor([[s.size[0] + 0.5*s.eps, 0.5*(s.size[2] + s.size[3])]], device="cuda")
     assert s.query_velocity(inlet)[0, 0].item() == pytest.approx(0.5, rel=1e-5)   # inlet strip: u = karman_vel (far from the cylinder)
+
+
+@pytest.mark.parametrize("boundary", ["walls", "smoke_obs"])
+def test_3d_configuration_steps(boundary):
+    """examples/smoke3d / vortex_collide (wall envelope) and smoke_obs (inlet ball + no-slip sphere + walls) shapes:
+    SIREN 5x64 3->3, 82^3-style divergence grid laid out [x][y][z] for zombie3d, 3D pressure solve on the device."""
+    pkg = util.package()
+    st = import_module(pkg.__name__ + ".stepper")
+    cfg = util.load_case("smoke3d")
+    kw = dict(scene_size=(-1.0, 1.0)*3, hidden_features=64, num_hidden_layers=5, dt=0.05, lr=1e-5, grid_resolution=30, wost_resolution=48,
+              sample_resolution=32, bdry_eps=1e-2, max_n_iters=30, check_every=10, boundary=boundary, reset_wts=True, seed=7, device=0)
+    if boundary == "smoke_obs":
+        kw["obstacle"] = ((0.0, 0.0, -0.3), 0.1)   # src/3d/main.py:85-91
+    s = st.SplitStepper(cfg, **kw)
+    swirl = lambda x: torch.stack([-x[:, 1], x[:, 0], 0.2*torch.ones_like(x[:, 0])], dim=-1)*0.3  # noqa: E731
+    s.fit_initial(swirl, 150, lr=1e-3)
+    div = s.divergence_grid()
+    assert tuple(div.shape) == (32, 32, 32)
+    x = s.grid_samples.detach().clone().requires_grad_(True)
+    u = s.apply_envelope_reference(x, s.velocity_field_prev.forward_reference(x))
+    ref = 0.0
+    for i in range(3):
+        ref = ref + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=True)[0][:, i]
+    ref = (-ref).reshape(32, 32, 32)
+    assert (div - ref).abs().max().item() <= 5e-4*ref.abs().max().item() + 1e-6
+    g = s.grid_samples.reshape(32, 32, 32, 3)   # [x][y][z]: the first index moves x only
+    assert g[5, 0, 0, 0] > g[4, 0, 0, 0] and g[5, 0, 0, 1] == g[4, 0, 0, 1] and g[0, 0, 5, 2] > g[0, 0, 4, 2]
+    out = s.step()
+    assert out["advect_iters"] == 30 and out["project_iters"] == 30
+    assert math.isfinite(out["advect_loss"].item()) and math.isfinite(out["project_loss"].item())
+    assert s.last["grad_p"].shape == (48*48, 3) and torch.isfinite(s.last["grad_p"]).all()
+    assert 0.95*500*48*48 < s.last["walks"] <= 500*48*48   # points inside the boundary mask are not walked
+    # device-resident 3D solve == host entry point on the same divergence grid (deterministic mode)
+    s.opts.mode = pkg.capi.MODE_DETERMINISTIC
+    pts = s.sample_random(500).contiguous()
+    p, gp = s.pressure_solve(pts)
+    sc = pkg.Scene(s.cfg["scene"], s.last["div"].cpu().numpy(), device=0)
+    ph, gh, _, _ = pkg.zombie.wost_array(sc, s.cfg["solver"], s.cfg["output"], pts.cpu().numpy(), mode=pkg.capi.MODE_DETERMINISTIC, seed=int(s.opts.seed))
+    assert np.array_equal(p.cpu().numpy(), ph) and np.array_equal(gp.cpu().numpy(), gh)
