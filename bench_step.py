@@ -22,12 +22,20 @@ import util  # noqa: E402
 import __graft_entry__ as ge  # noqa: E402
 
 
+def _leave():
+    """destroy_process_group() blocks while CUDA graphs holding captured NCCL collectives are alive: flush and exit."""
+    torch.cuda.synchronize()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
+
+
 def build(args, pkg, st):
     """(stepper, initial-velocity function, network shape, description) for the chosen example configuration."""
+    dd = dict(device=getattr(args, "device", 0), distributed=getattr(args, "distributed", False))
     if args.case == "taylorgreen":
         cfg = util.load_case("taylorgreen_shipped" if args.watertight else "taylorgreen_active")
         size = (0.0, 2*math.pi, 0.0, 2*math.pi)
-        s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1)
+        s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1, **dd)
         tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
         return s, cfg, tg, (6, 64), "taylorgreen step (SIREN 6x64, batch 64^2, dt 1e-3), 512^2 pressure samples x 500 walks, 1002^2 divergence grid"
     if args.case == "smoke_obs":
@@ -35,7 +43,7 @@ def build(args, pkg, st):
         cfg = util.load_case("smoke3d")
         s = st.SplitStepper(cfg, scene_size=(-1.0, 1.0)*3, hidden_features=64, num_hidden_layers=5, dt=0.05, lr=1e-5, sample_resolution=128,
                             wost_resolution=256, grid_resolution=80, bdry_eps=1e-2, max_n_iters=args.iters, early_stop=False,
-                            use_cuda_graph=not args.no_graph, boundary="smoke_obs", obstacle=((0.0, 0.0, -0.3), 0.1), reset_wts=True, seed=1)
+                            use_cuda_graph=not args.no_graph, boundary="smoke_obs", obstacle=((0.0, 0.0, -0.3), 0.1), reset_wts=True, seed=1, **dd)
         rest = lambda x: torch.zeros_like(x)  # noqa: E731  (the smoke examples start from rest; the inlet ball drives the flow)
         return s, cfg, rest, (5, 64), "smoke_obs step (SIREN 5x64 3->3, batch 128^2, dt 0.05, reset_wts), 256^2 pressure samples x 500 walks, 82^3 divergence grid"
     # examples/karman/run.sh: SIREN 2x128, batch 128^2, dt 0.05, bdry_eps 3e-2, karman_vel 0.5, reset_wts 1, wost_resolution 512
@@ -43,7 +51,7 @@ def build(args, pkg, st):
     centre, radius, size = util.karman_obstacle(cfg["output"]["boundaryDistanceMask"])
     s = st.SplitStepper(cfg, scene_size=size, hidden_features=128, num_hidden_layers=2, dt=0.05, lr=1e-5, sample_resolution=128,
                         wost_resolution=512, grid_resolution=1000, bdry_eps=3e-2, max_n_iters=args.iters, early_stop=False,
-                        use_cuda_graph=not args.no_graph, boundary="karman", obstacle=(centre, radius), karman_vel=0.5, reset_wts=True, seed=1)
+                        use_cuda_graph=not args.no_graph, boundary="karman", obstacle=(centre, radius), karman_vel=0.5, reset_wts=True, seed=1, **dd)
     return s, cfg, s.karman_initial_velocity, (2, 128), "karman step (SIREN 2x128, batch 128^2, dt 0.05, reset_wts), <= 512^2 pressure samples outside the cylinder x 500 walks, 401x1002 divergence grid"
 
 
@@ -55,7 +63,16 @@ def main():
     ap.add_argument("--watertight", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--gpus", type=int, default=1, help="under torchrun: data-parallel fits + sharded pressure solve")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    args.device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
+    args.distributed = world > 1
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(args.device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
     pkg = ge.load_package()
     st = import_module(pkg.__name__ + ".stepper")
     s, cfg, init_fn, (n_hidden, hidden), what = build(args, pkg, st)
@@ -71,6 +88,16 @@ def main():
         d = time.perf_counter()
         parts["advect_ms"] += 1e3*(b - a); parts["pressure_ms"] += s.last["pressure_ms"]; parts["project_ms"] += 1e3*(d - b) - s.last["pressure_ms"]
     total = time.perf_counter() - t0
+    if world > 1:  # max over ranks; only rank 0 reports and times the reference arrangement
+        import torch.distributed as dist
+        t = torch.tensor([total] + [parts[k] for k in sorted(parts)], device=s.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t[0].item())
+        for i, k in enumerate(sorted(parts)):
+            parts[k] = float(t[1 + i].item())
+        dist.barrier()
+        if rank != 0:
+            _leave()
     ours = args.steps/total
 
     # reference arrangement of the same step: stock torch ops + torch Adam + one loss.item() per iteration (base.py:142)
@@ -108,11 +135,14 @@ def main():
     print(json.dumps({"metric": "sim_steps_per_sec", "value": ours, "unit": "steps/s",
                       "config": {"workload": "%s, %d Adam iterations per fit" % (what, args.iters), "case": args.case,
                                  "scene": ("as shipped (isWatertight)" if args.watertight else "solver active (isWatertight:false)") if args.case == "taylorgreen" else "as shipped",
-                                 "cuda_graph": not args.no_graph},
+                                 "cuda_graph": not args.no_graph, "n_gpus": world,
+                                 "parallelism": "replicated networks, data-parallel fits (1 gradient all_reduce per iteration), pressure samples sharded + all_gather" if world > 1 else "single GPU"},
                       "ms_per_step": 1e3*total/args.steps, "breakdown_ms_per_step": {k: v/args.steps for k, v in parts.items()},
                       "walks_per_step": int(s.last["walks"]), "pressure_samples": n_press, "wost_kernel_ms": s.last["wost_ms"],
                       "reference_arrangement": {"fit_iteration_ms_stock_torch": ref_iter_ms, "cpu_wost_s_extrapolated_from_%d_points" % len(pts): cpu_wost_s,
                                                 "cores": threads, "step_s": ref_step_s, "steps_per_sec": 1.0/ref_step_s}}), flush=True)
+    if world > 1:
+        _leave()
 
 
 if __name__ == "__main__":

@@ -345,8 +345,16 @@ class DirectFit:
     kernel, batched GEMMs straight into one flat gradient buffer, one Adam kernel.  Replaces update_network
     (base.py:83-96).  Flat layout: W_0, b_0, W_1..W_L (one [L,H,H] block), b_1..b_L, W_last, b_last."""
 
-    def __init__(self, net, lr, envelope=None, max_batch=16384):
+    def __init__(self, net, lr, envelope=None, max_batch=16384, group=None, distributed=False):
+        """distributed: data-parallel fit over the ranks of `group` (torch.distributed, NCCL): every rank passes its
+        own shard of the batch to iterate(); the flat gradient buffer (21-34 k floats for the shipped shapes) is
+        averaged with ONE all_reduce per iteration and every rank applies the same Adam step.  The parameters are
+        broadcast from rank 0 by sync_parameters()."""
         self.net, self.env = net, envelope
+        self.group, self.world = group, 1
+        if distributed:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
         lin = net._linears()
         self.W = [m.weight for m in lin]; self.b = [m.bias for m in lin]
         order = [self.W[0], self.b[0]] + self.W[1:-1] + self.b[1:-1] + [self.W[-1], self.b[-1]]
@@ -379,5 +387,14 @@ class DirectFit:
         dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)
         self.opt.g.zero_()
         _param_grads(sh, x, n, dZ, A, out=self.out)
+        if self.world > 1:  # mean over the global batch = mean over ranks of the local means (equal shard sizes)
+            import torch.distributed as dist
+            dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG, group=self.group)
         self.opt.step_flat()
         return diff
+
+    def sync_parameters(self, src=0):
+        """Broadcast the flat parameter buffer from rank `src` (after initialisation / re-initialisation)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.opt.flat, src=src, group=self.group)

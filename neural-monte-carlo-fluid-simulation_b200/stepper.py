@@ -72,8 +72,16 @@ class SplitStepper:
                  sample_resolution=64, wost_resolution=512, grid_resolution=1000, bdry_eps=1e-3, max_n_iters=10000,
                  early_stop=True, check_every=100, boundary="taylorgreen", mode=capi.MODE_FAST, seed=0, device=0,
                  use_cuda_graph=True, tensor_cores=True, init_velocity=None, init_iters=0, obstacle=None, karman_vel=0.5,
-                 reset_wts=False):
+                 reset_wts=False, distributed=False):
+        """distributed: one process per GPU under torch.distributed (NCCL).  The fits are data-parallel (each rank
+        draws 1/world of every batch, one gradient all_reduce per iteration), the pressure samples are drawn and
+        solved per rank and all-gathered (points, p, grad p), the divergence grid and the networks are replicated.
+        Every rank ends a step with identical weights."""
         self.dev = torch.device("cuda", device)
+        self.rank, self.world = 0, 1
+        if distributed:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.cfg = wost_config
         self.size = tuple(float(v) for v in scene_size)
         self.dt, self.lr, self.eps = dt, lr, bdry_eps
@@ -97,6 +105,8 @@ class SplitStepper:
         self.timestep, self.seed = 0, seed
         self.last = {}
         self._fit, self._graphs, self._proj = None, {}, None
+        if self.world > 1:  # identical initial weights (same seed above), different training samples per rank from here on
+            torch.manual_seed(seed*7919 + 1 + self.rank)
         self.obstacle, self.karman_vel, self.reset_wts = obstacle, float(karman_vel), bool(reset_wts)
         if boundary in ("taylorgreen", "walls"):
             self.env = wall_envelope(self.size, bdry_eps)
@@ -170,11 +180,12 @@ class SplitStepper:
         later time step: its inputs live in buffers that persist across steps, and Adam's step counter is on the
         device.  (Capturing per fit costs a synchronise + allocator flush per phase, i.e. tens to hundreds of ms.)"""
         if self._fit is None:
-            self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2)
+            self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2, distributed=self.world > 1)
         fit = self._fit
         fit.opt.reset()
         if self.reset_wts:
             self._reset_weights()
+            fit.sync_parameters()  # the re-initialisation draws from per-rank random streams
         cached = self._graphs.get(key) if (self.use_graph and key is not None) else None
         it = 0
         if cached is not None:
@@ -212,7 +223,7 @@ class SplitStepper:
         return it, loss_buf
 
     def advect_velocity(self, n_iters=None):
-        n = self.sample_resolution**2
+        n = self.sample_resolution**2//self.world
         s = self.size
 
         def iteration():
@@ -240,20 +251,36 @@ class SplitStepper:
         n = samples.shape[0]
         p = torch.empty(n, device=self.dev); g = torch.empty((n, self.dim), device=self.dev)
         st = capi.SolveStats()
-        self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=0,
+        self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=self.rank*(self.wost_resolution**2),
                                        stream=torch.cuda.current_stream().cuda_stream, stats=st)
         self.last.update(walks=st.walks_started, wost_ms=st.kernel_ms, div=div)
         return p, g
 
+    def _gather_pressure(self, samples, p, grad_p):
+        """all_gather of every rank's (points, p, grad p); shard sizes may differ (obstacle rejection)."""
+        import torch.distributed as dist
+        cap = self.wost_resolution**2//self.world
+        buf = torch.zeros(cap + 1, 2*self.dim + 1, device=self.dev)
+        k = samples.shape[0]
+        buf[:k, :self.dim] = samples; buf[:k, self.dim] = p; buf[:k, self.dim + 1:] = grad_p
+        buf[cap, 0] = float(k)
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf)
+        parts = [o[: int(o[cap, 0].item())] for o in out]
+        full = torch.cat(parts, dim=0)
+        return full[:, :self.dim].contiguous(), full[:, self.dim].contiguous(), full[:, self.dim + 1:].contiguous()
+
     def project_velocity(self, n_iters=None):
-        samples_all = self.sample_random(self.wost_resolution**2, keep_shape=False).contiguous()
+        samples_all = self.sample_random(self.wost_resolution**2//self.world, keep_shape=False).contiguous()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         p, grad_p = self.pressure_solve(samples_all)
+        if self.world > 1:
+            samples_all, p, grad_p = self._gather_pressure(samples_all, p, grad_p)
         e1.record(); e1.synchronize()
         self.last["pressure_ms"] = e0.elapsed_time(e1)
         self.last.update(p=p, grad_p=grad_p, pressure_samples=samples_all)
-        n, big = self.sample_resolution**2, samples_all.shape[0]
+        n, big = self.sample_resolution**2//self.world, samples_all.shape[0]
         if self.use_graph:  # persistent inputs of the captured iteration: samples, gradients and their count
             if self._proj is None:
                 cap = self.wost_resolution**2
@@ -305,5 +332,9 @@ class SplitStepper:
             x = self.sample_random(self.sample_resolution**2)
             loss = torch.mean((self.query_velocity(x) - velocity_fn(x))**2)
             opt.zero_grad(); loss.backward(); opt.step()
+        if self.world > 1:  # every rank fitted on its own samples: continue from rank 0's weights
+            import torch.distributed as dist
+            for prm in self.velocity_field.parameters():
+                dist.broadcast(prm.data, src=0)
         self._sync_prev()
         return loss.item()

@@ -240,3 +240,16 @@ def test_3d_configuration_steps(boundary):
     sc = pkg.Scene(s.cfg["scene"], s.last["div"].cpu().numpy(), device=0)
     ph, gh, _, _ = pkg.zombie.wost_array(sc, s.cfg["solver"], s.cfg["output"], pts.cpu().numpy(), mode=pkg.capi.MODE_DETERMINISTIC, seed=int(s.opts.seed))
     assert np.array_equal(p.cpu().numpy(), ph) and np.array_equal(gp.cpu().numpy(), gh)
+
+
+def test_distributed_stepper_two_gpus():
+    """Data-parallel fits (gradient all_reduce) + sharded pressure solve (all_gather) under torchrun; needs 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(here, "dist_stepper_check.py")], capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0 and "DIST_STEPPER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
