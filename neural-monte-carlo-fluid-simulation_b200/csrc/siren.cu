@@ -248,25 +248,25 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 // exchanged through a double-buffered [H][32] array; the last layer and dL/dx are reduced across the warps.
 constexpr int kTS = 32;
 
-template <int H>
-__global__ void __launch_bounds__(2*H, H == 128 ? 2 : 4)
+template <int H, int NPT>
+__global__ void __launch_bounds__(32*(H/NPT), H == 128 ? 2 : 4)
 sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 				  float* __restrict__ y, float* __restrict__ zSaved) {
 	extern __shared__ float smem[];
-	constexpr int LD = H + 4, NT = 2*H;
+	constexpr int LD = H + 4, NG = H/NPT, NT = 32*NG;
 	float* Wt = smem;                   // [H][LD]  Wt[k][nn] = W_l[nn][k]
 	float* act = Wt + H*LD;             // [2][H][kTS]
-	float* part = act + 2*H*kTS;        // [H/16][3][kTS]
-	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = 16*g;
+	float* part = act + 2*H*kTS;        // [H/NPT][3][kTS]
+	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = NPT*g;
 	const int last = nHidden + 1;
 	for (long long tile = blockIdx.x; tile*kTS < n; tile += gridDim.x) {
 		const long long s = tile*kTS + lane;
 		const bool live = s < n;
 		float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
 		if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
-		float a16[16];
+		float a16[NPT];
 #pragma unroll
-		for (int j = 0; j < 16; j++) { // first layer: in -> H
+		for (int j = 0; j < NPT; j++) { // first layer: in -> H
 			const float* w = &P.W[0][(n0 + j)*inDim];
 			float z = __ldg(&P.b[0][n0 + j]) + __ldg(w)*x0;
 			if (inDim > 1) z += __ldg(w + 1)*x1;
@@ -285,16 +285,16 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 				Wt[k*LD + nn] = __ldg(&P.W[l][nn*H + k]);
 			}
 			__syncthreads();
-			float acc[16];
+			float acc[NPT];
 #pragma unroll
-			for (int j = 0; j < 16; j++) acc[j] = __ldg(&P.b[l][n0 + j]);
+			for (int j = 0; j < NPT; j++) acc[j] = __ldg(&P.b[l][n0 + j]);
 			const float* ac = act + cur*H*kTS + lane;
 #pragma unroll 8
 			for (int k = 0; k < H; k++) {
 				const float av = ac[k*kTS];
 				const float4* w = reinterpret_cast<const float4*>(&Wt[k*LD + n0]);
 #pragma unroll
-				for (int q = 0; q < 4; q++) {
+				for (int q = 0; q < NPT/4; q++) {
 					const float4 v = w[q];
 					acc[4*q + 0] += av*v.x; acc[4*q + 1] += av*v.y; acc[4*q + 2] += av*v.z; acc[4*q + 3] += av*v.w;
 				}
@@ -302,7 +302,7 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 			cur ^= 1;
 			float* an = act + cur*H*kTS + lane;
 #pragma unroll
-			for (int j = 0; j < 16; j++) {
+			for (int j = 0; j < NPT; j++) {
 				if (zSaved && live) zSaved[((size_t)l*H + n0 + j)*n + s] = acc[j];
 				a16[j] = sinReduced(w0*acc[j]);
 				an[(n0 + j)*kTS] = a16[j];
@@ -312,7 +312,7 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 		for (int j = 0; j < outDim; j++) {
 			float pj = 0.0f;
 #pragma unroll
-			for (int i = 0; i < 16; i++) pj += __ldg(&P.W[last][j*H + n0 + i])*a16[i];
+			for (int i = 0; i < NPT; i++) pj += __ldg(&P.W[last][j*H + n0 + i])*a16[i];
 			part[(g*3 + j)*kTS + lane] = pj;
 		}
 		__syncthreads();
@@ -320,7 +320,7 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 			float yo[3] = {0.0f, 0.0f, 0.0f};
 			for (int j = 0; j < outDim; j++) {
 				float z = __ldg(&P.b[last][j]);
-				for (int q = 0; q < H/16; q++) z += part[(q*3 + j)*kTS + lane];
+				for (int q = 0; q < NG; q++) z += part[(q*3 + j)*kTS + lane];
 				if (j == 0) yo[0] = z; else if (j == 1) yo[1] = z; else yo[2] = z;
 			}
 			if (env.active) { const float xs[3] = {x0, x1, x2}; nmc_siren_detail::envForward(env, inDim, outDim, xs, yo); }
@@ -334,17 +334,17 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 	}
 }
 
-template <int H>
-__global__ void __launch_bounds__(2*H, H == 128 ? 2 : 4)
+template <int H, int NPT>
+__global__ void __launch_bounds__(32*(H/NPT), H == 128 ? 2 : 4)
 sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 				   const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ gx,
 				   float* __restrict__ dZ, float* __restrict__ A) {
 	extern __shared__ float smem[];
-	constexpr int LD = H + 4, NT = 2*H;
+	constexpr int LD = H + 4, NG = H/NPT, NT = 32*NG;
 	float* Ws = smem;                   // [H][LD]  W_l row-major (nn, k)
 	float* ex = Ws + H*LD;              // [2][H][kTS] delta exchange
-	float* part = ex + 2*H*kTS;         // [H/16][3][kTS]
-	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = 16*g;
+	float* part = ex + 2*H*kTS;         // [H/NPT][3][kTS]
+	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = NPT*g;
 	const int last = nHidden + 1;
 	for (long long tile = blockIdx.x; tile*kTS < n; tile += gridDim.x) {
 		const long long s = tile*kTS + lane;
@@ -375,9 +375,9 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
 			}
 		}
-		float g16[16];
+		float g16[NPT];
 #pragma unroll
-		for (int i = 0; i < 16; i++) { // g_L = W_last^T gy'
+		for (int i = 0; i < NPT; i++) { // g_L = W_last^T gy'
 			float acc = __ldg(&P.W[last][n0 + i])*gy0;
 			if (outDim > 1) acc += __ldg(&P.W[last][H + n0 + i])*gy1;
 			if (outDim > 2) acc += __ldg(&P.W[last][2*H + n0 + i])*gy2;
@@ -387,7 +387,7 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 		for (int l = nHidden; l >= 0; l--) {
 			float* exw = ex + cur*H*kTS + lane;
 #pragma unroll
-			for (int i = 0; i < 16; i++) { // dz_l = g * w0 cos(w0 z_l);  A_l = sin(w0 z_l)
+			for (int i = 0; i < NPT; i++) { // dz_l = g * w0 cos(w0 z_l);  A_l = sin(w0 z_l)
 				const float zl = live ? zSaved[((size_t)l*H + n0 + i)*n + s] : 0.0f;
 				float t = w0*zl*0.15915494309189535f;
 				t -= rintf(t);
@@ -404,28 +404,28 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				*reinterpret_cast<float4*>(&Ws[nn*LD + 4*k4]) = __ldg(reinterpret_cast<const float4*>(&P.W[l][nn*H + 4*k4]));
 			}
 			__syncthreads();
-			float acc[16];
+			float acc[NPT];
 #pragma unroll
-			for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+			for (int i = 0; i < NPT; i++) acc[i] = 0.0f;
 			const float* er = ex + cur*H*kTS + lane;
 #pragma unroll 8
 			for (int nn = 0; nn < H; nn++) { // g_{l-1}[k] = sum_nn W_l[nn][k] dz[nn]
 				const float dv = er[nn*kTS];
 				const float4* w = reinterpret_cast<const float4*>(&Ws[nn*LD + n0]);
 #pragma unroll
-				for (int q = 0; q < 4; q++) {
+				for (int q = 0; q < NPT/4; q++) {
 					const float4 v = w[q];
 					acc[4*q + 0] += dv*v.x; acc[4*q + 1] += dv*v.y; acc[4*q + 2] += dv*v.z; acc[4*q + 3] += dv*v.w;
 				}
 			}
 #pragma unroll
-			for (int i = 0; i < 16; i++) g16[i] = acc[i];
+			for (int i = 0; i < NPT; i++) g16[i] = acc[i];
 			cur ^= 1;
 		}
 		if (gx) { // dL/dx = W_0^T dz_0: partial sums over this warp's 16 neurons, reduced by warp 0
 			float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
-			for (int i = 0; i < 16; i++) {
+			for (int i = 0; i < NPT; i++) {
 				const float* w = &P.W[0][(n0 + i)*inDim];
 				a0 += __ldg(w)*g16[i];
 				if (inDim > 1) a1 += __ldg(w + 1)*g16[i];
@@ -436,7 +436,7 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 			__syncthreads();
 			if (g == 0 && live) {
 				float r[3] = {gxe[0], gxe[1], gxe[2]};
-				for (int q = 0; q < H/16; q++) { r[0] += part[(q*3 + 0)*kTS + lane]; r[1] += part[(q*3 + 1)*kTS + lane]; r[2] += part[(q*3 + 2)*kTS + lane]; }
+				for (int q = 0; q < NG; q++) { r[0] += part[(q*3 + 0)*kTS + lane]; r[1] += part[(q*3 + 1)*kTS + lane]; r[2] += part[(q*3 + 2)*kTS + lane]; }
 				gx[s*inDim] = r[0]; if (inDim > 1) gx[s*inDim + 1] = r[1]; if (inDim > 2) gx[s*inDim + 2] = r[2];
 			}
 		}
@@ -584,7 +584,8 @@ bool useSplit(long long n) {
 	if (limit < 0) { const char* e = getenv("NMC_SIREN_SPLIT_MAX"); limit = e ? atoll(e) : 65536; }
 	return n <= limit;
 }
-size_t splitSmem(int H) { return ((size_t)H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/16)*3*kTS)*sizeof(float); }
+constexpr int kNpt64 = 8, kNpt128 = 16; // neurons per thread: 8 warps per CTA for both widths
+size_t splitSmem(int H) { return ((size_t)H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/(H == 64 ? kNpt64 : kNpt128))*3*kTS)*sizeof(float); }
 
 int smCount() {
 	int dev = 0, sms = 148;
@@ -616,11 +617,11 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 		long long tilesS = (n + kTS - 1)/kTS;
 		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
 		if (H == 64) {
-			e = cudaFuncSetAttribute(sirenForwardSplit<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-			if (!e) sirenForwardSplit<64><<<gridS, 128, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+			e = cudaFuncSetAttribute(sirenForwardSplit<64, kNpt64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenForwardSplit<64, kNpt64><<<gridS, 32*(64/kNpt64), smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
 		} else {
-			e = cudaFuncSetAttribute(sirenForwardSplit<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-			if (!e) sirenForwardSplit<128><<<gridS, 256, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+			e = cudaFuncSetAttribute(sirenForwardSplit<128, kNpt128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenForwardSplit<128, kNpt128><<<gridS, 32*(128/kNpt128), smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
 		}
 		if (!e) e = cudaGetLastError();
 		return e ? fail(cudaGetErrorString(e)) : 0;
@@ -656,11 +657,11 @@ extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const*
 		long long tilesS = (n + kTS - 1)/kTS;
 		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
 		if (H == 64) {
-			e = cudaFuncSetAttribute(sirenBackwardSplit<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-			if (!e) sirenBackwardSplit<64><<<gridS, 128, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
+			e = cudaFuncSetAttribute(sirenBackwardSplit<64, kNpt64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenBackwardSplit<64, kNpt64><<<gridS, 32*(64/kNpt64), smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
 		} else {
-			e = cudaFuncSetAttribute(sirenBackwardSplit<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-			if (!e) sirenBackwardSplit<128><<<gridS, 256, smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
+			e = cudaFuncSetAttribute(sirenBackwardSplit<128, kNpt128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+			if (!e) sirenBackwardSplit<128, kNpt128><<<gridS, 32*(128/kNpt128), smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, grad_x, dZ, A);
 		}
 		if (!e) e = cudaGetLastError();
 		return e ? fail(cudaGetErrorString(e)) : 0;
