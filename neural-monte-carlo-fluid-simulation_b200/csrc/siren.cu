@@ -584,7 +584,7 @@ bool useSplit(long long n) {
 	if (limit < 0) { const char* e = getenv("NMC_SIREN_SPLIT_MAX"); limit = e ? atoll(e) : 65536; }
 	return n <= limit;
 }
-constexpr int kNpt64 = 8, kNpt128 = 16; // neurons per thread: 8 warps per CTA for both widths
+constexpr int kNpt64 = 8, kNpt128 = 8; // neurons per thread: 8 warps per CTA for both widths
 size_t splitSmem(int H) { return ((size_t)H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/(H == 64 ? kNpt64 : kNpt128))*3*kTS)*sizeof(float); }
 
 int smCount() {
