@@ -689,10 +689,11 @@ extern "C" int nmc_siren_weight_grads(const nmc_siren_shape* sh, const float* x,
 	if (!x || !dZ || !A) return fail("null buffer");
 	Params P;
 	for (int l = 0; l < sh->n_hidden_layers + 2; l++) { P.W[l] = nullptr; P.b[l] = nullptr; P.gW[l] = gW[l]; P.gb[l] = gb[l]; if (!gW[l] || !gb[l]) return fail("null layer pointer"); }
-	// samples per CTA: as large as possible (fewer atomics) while the hidden layers' CTAs still cover the SMs twice
+	// samples per CTA: as large as possible (fewer atomics) while the hidden layers' CTAs still cover the SMs
 	int chunk = kGChunkMax;
 	const int heavy = sh->n_hidden_layers > 0 ? sh->n_hidden_layers : 1;
-	while (chunk > 64 && ((n + chunk - 1)/chunk)*heavy < 2ll*smCount()) chunk >>= 1;
+	const long long want = (sh->hidden == 64 ? 2ll : 1ll)*smCount(); // H = 128 threads carry 4x the atomics: fewer, larger chunks (measured)
+	while (chunk > 64 && ((n + chunk - 1)/chunk)*heavy < want) chunk >>= 1;
 	dim3 grid((unsigned)((n + chunk - 1)/chunk), (unsigned)(sh->n_hidden_layers + 2));
 	cudaStream_t st = (cudaStream_t)stream;
 	if (sh->hidden == 64) sirenWeightGrad<64><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A, chunk);
