@@ -84,8 +84,13 @@ __device__ __forceinline__ void splitTf32(float v, float& hi, float& lo) {
 	lo = v - hi;
 }
 
+// Two threads per accumulator row: thread `row` and thread `row + 128` split the columns of the row between them in
+// the first layer and in the epilogues (warps w and w + 4 read the same 32 TMEM lanes), and all 256 threads stage
+// the weight operand, so the serial part between two MMA batches is half as long.
+constexpr int kThreads = 2*kTile;
+
 template <int H>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kThreads)
 sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned char* Ahi = smem;
@@ -94,7 +99,9 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 	unsigned char* Blo = Bhi + kNChunk*H*4;
 	__shared__ __align__(8) unsigned long long mbar;
 	__shared__ uint32_t tmemBaseSh;
-	const int tid = threadIdx.x, warp = tid >> 5;
+	__shared__ float ypart[3][kTile];
+	const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), half = tid >> 7;
+	const int cBeg = half*(H/2), cEnd = cBeg + H/2;
 
 	if (warp == 0) { // TMEM: H fp32 columns x 128 lanes
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemAddr(&tmemBaseSh)), "r"((uint32_t)H) : "memory");
@@ -116,12 +123,12 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 	const int last = nHidden + 1;
 
 	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
-		const long long s = tile*kTile + tid;
+		const long long s = tile*kTile + row;
 		const bool live = s < n;
 		{ // first layer on the FMA pipe, written straight into the A operand
 			float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
 			if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
-			for (int c = 0; c < H; c += 4) {
+			for (int c = cBeg; c < cEnd; c += 4) {
 				float hi[4], lo[4];
 #pragma unroll
 				for (int q = 0; q < 4; q++) {
@@ -131,7 +138,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 					if (inDim > 2) z += __ldg(w + 2)*x2;
 					splitTf32(live ? sinReduced(w0*z) : 0.0f, hi[q], lo[q]);
 				}
-				int off = coreOffsetBytes<H>(tid, c);
+				int off = coreOffsetBytes<H>(row, c);
 				*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
 				*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 			}
@@ -140,7 +147,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
-				for (int idx = tid; idx < kNChunk*H/4; idx += kTile) {
+				for (int idx = tid; idx < kNChunk*H/4; idx += kThreads) {
 					int k4 = idx/kNChunk, r = idx - k4*kNChunk; // lanes walk down the rows of one core-matrix column
 					float4 w = __ldg(reinterpret_cast<const float4*>(&P.W[l][(size_t)(nc*kNChunk + r)*H + 4*k4]));
 					float4 h, o;
@@ -174,9 +181,9 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			}
 			// epilogue: this thread's row of the accumulator -> bias, sin, next layer's operand
-			for (int c0 = 0; c0 < H; c0 += 16) {
+			for (int c0 = cBeg; c0 < cEnd; c0 += 16) {
 				uint32_t v[16];
-				uint32_t taddr = tmemBase + ((uint32_t)(warp*32) << 16) + (uint32_t)c0;
+				uint32_t taddr = tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)c0;
 				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
 							 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
 							   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
@@ -198,14 +205,17 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 						splitTf32(a, hi[q], lo[q]);
 					}
 					if (l < nHidden) {
-						int off = coreOffsetBytes<H>(tid, c0 + q4);
+						int off = coreOffsetBytes<H>(row, c0 + q4);
 						*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
 						*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 					}
 				}
 			}
 		}
-		if (live) {
+		if (half == 1) { ypart[0][row] = y0; ypart[1][row] = y1; ypart[2][row] = y2; } // the other half of this row's last-layer dot product
+		__syncthreads();
+		if (live && half == 0) {
+			y0 += ypart[0][row]; y1 += ypart[1][row]; y2 += ypart[2][row];
 			float yo[3] = {y0 + __ldg(&P.b[last][0]), outDim > 1 ? y1 + __ldg(&P.b[last][1]) : 0.0f, outDim > 2 ? y2 + __ldg(&P.b[last][2]) : 0.0f};
 			if (env.active) {
 				const float xs[3] = {x[s*inDim], inDim > 1 ? x[s*inDim + 1] : 0.0f, inDim > 2 ? x[s*inDim + 2] : 0.0f};
@@ -257,10 +267,10 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenForwardTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<64><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+		if (!e) sirenForwardTc<64><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
 	} else {
 		e = cudaFuncSetAttribute(sirenForwardTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<128><<<grid, kTile, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+		if (!e) sirenForwardTc<128><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
 	}
 	if (!e) e = cudaGetLastError();
 	if (e) { nmc_siren_detail::setError(cudaGetErrorString(e)); return 1; }
