@@ -1,0 +1,77 @@
+"""Exercises the compiled drop-in module `zombie_bindings` of one dimension in a fresh interpreter (the 2D and 3D
+modules share their name, exactly like the reference's, so they cannot live in one process).
+usage: bindings_check.py <2|3> <cpu|gpu>"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE); sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import util  # noqa: E402
+
+dim, where = int(sys.argv[1]), sys.argv[2]
+sys.path.insert(0, os.path.join(ROOT, "neural-monte-carlo-fluid-simulation_b200", "zombie%dd" % dim))  # what INTEGRATION.md tells a user to do
+import zombie_bindings as zb  # noqa: E402
+
+assert zb.__doc__ == "pybind11 WoSt"                       # demo.cpp:394
+assert hasattr(zb, "wost") and hasattr(zb, "Scene")
+assert hasattr(zb, "bvc") == (dim == 2)                     # zombie3d has no bvc (demo.cpp:119-125)
+cfg = util.load_case("karman" if dim == 2 else "smoke3d")
+src = util.source_grid(dim)
+
+
+def raises(exc, fn):
+    try:
+        fn()
+    except exc:
+        return True
+    except Exception as e:  # noqa: BLE001
+        raise AssertionError("expected %s, got %r" % (exc.__name__, e))
+    raise AssertionError("expected %s, nothing raised" % exc.__name__)
+
+
+# error behaviour: raise where the reference abort()s / exit()s
+bad = dict(cfg["scene"]); del bad["boundary"]
+assert raises(KeyError, lambda: zb.Scene(bad, src))
+assert raises(RuntimeError, lambda: zb.Scene(dict(cfg["scene"], boundary="/nonexistent.obj"), src))
+assert raises(TypeError, lambda: zb.Scene(cfg["scene"], np.zeros((3,)*(dim + 1), np.float32)))
+if dim == 2:
+    assert raises(RuntimeError, lambda: zb.Scene(cfg["scene"]))          # image-file source: not provided
+if where == "cpu":
+    # no GPU here: creating a scene must fail loudly (no CPU fallback)
+    assert raises(RuntimeError, lambda: zb.Scene(cfg["scene"], src))
+    print("BINDINGS_OK cpu dim=%d" % dim)
+    sys.exit(0)
+
+scene = zb.Scene(cfg["scene"], src.tolist())                # nested lists, as src/*/models/model_split.py passes them
+if dim == 2:
+    assert raises(RuntimeError, lambda: zb.bvc(scene, cfg["solver"], cfg["output"]))
+no_grid = dict(cfg["output"]); del no_grid["gridRes"]
+pts = util.random_points(*[np.asarray(v, np.float32) for v in ((-0.9,)*dim, (0.9,)*dim)], 300, seed=3) if dim == 3 else \
+    util.random_points(np.array([-1.0, -0.5], np.float32), np.array([1.8, 0.5], np.float32), 300, seed=3)
+assert raises(KeyError, lambda: zb.wost(scene, cfg["solver"], no_grid, pts.tolist()))   # gridRes is required (demo.cpp:132)
+assert raises(TypeError, lambda: zb.wost(scene, cfg["solver"], cfg["output"], np.zeros((5, dim + 1), np.float32)))
+zb.set_mode("deterministic"); zb.set_seed(11)
+out_pts, p, g = zb.wost(scene, cfg["solver"], cfg["output"], pts.tolist())
+assert isinstance(out_pts, list) and isinstance(p, list) and isinstance(g, list) and isinstance(g[0], list)
+assert len(p) == 300 and len(g) == 300 and len(g[0]) == dim and len(out_pts[0]) == dim
+assert np.allclose(np.array(out_pts, np.float32), pts)
+pa, ga = zb.wost_array(scene, cfg["solver"], cfg["output"], pts)
+assert np.array_equal(np.array(p, np.float32), pa) and np.array_equal(np.array(g, np.float32), ga)
+st = zb.last_stats()
+assert st["walks_started"] > 0 and st["kernel_launches"] >= 1
+# the same numbers as the Python mirror of the module (tests / bench use that one)
+pkg = util.package()
+sc = pkg.Scene(cfg["scene"], src, device=0)
+pm, gm, _, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_DETERMINISTIC, seed=11)
+assert np.array_equal(pa, pm) and np.array_equal(ga, gm)
+zb.set_mode("fast"); zb.set_seed(None)
+_, p2, g2 = zb.wost(scene, cfg["solver"], cfg["output"], pts)
+_, p3, g3 = zb.wost(scene, cfg["solver"], cfg["output"], pts)
+p2, p3 = np.array(p2), np.array(p3)
+assert np.isfinite(p2).all() and not np.array_equal(p2, p3)            # unseeded: a fresh seed per call, like the reference's clock
+assert np.abs(p2 - pa).max() < 0.05*np.abs(pa).max() + 1e-6
+assert raises(ValueError, lambda: zb.set_mode("bogus"))
+print("BINDINGS_OK gpu dim=%d" % dim, json.dumps({k: int(v) if isinstance(v, (int, np.integer)) else float(v) for k, v in st.items()}))

@@ -303,3 +303,14 @@ def test_full_size_3d_properties_one_million_points(pkg):
     # a smooth source gives a smooth field: the Monte Carlo estimate must correlate with itself across seeds
     p3, _, _, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts[:50000], mode=pkg.capi.MODE_FAST, seed=22)
     assert np.corrcoef(p[:50000], p3)[0, 1] > 0.9
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_compiled_drop_in_module_on_the_gpu(dim):
+    """`import zombie_bindings` exactly as src/2d / src/3d do (module directory on sys.path): Scene(config, nested
+    lists), wost(...) -> (points, p, grad p) as nested lists, identical to the C ABI results; additive wost_array,
+    set_mode, set_seed, last_stats."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "bindings_check.py"), str(dim), "gpu"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "BINDINGS_OK gpu dim=%d" % dim in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -274,3 +274,13 @@ def test_flat_scan_tables_of_the_example_scenes(emu, oracle_lib):
         assert info[1] == n_prims and info[4] == n_ray, (case, list(info))
         assert info[3] <= info[2] and info[5] < 62
         emu.emu_scene_destroy(h)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_compiled_drop_in_module_surface_and_errors(dim):
+    """The pybind11 modules `zombie2d/zombie_bindings`, `zombie3d/zombie_bindings` (the drop-in boundary):
+    names, docstring, constructor overloads, exceptions instead of abort(), and no CPU fallback when there is no GPU."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "bindings_check.py"), str(dim), "cpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "BINDINGS_OK cpu dim=%d" % dim in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
