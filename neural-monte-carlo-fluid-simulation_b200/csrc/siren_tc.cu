@@ -121,6 +121,30 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNChunk >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 	uint32_t phase = 0;
 	const int last = nHidden + 1;
+	// Weight operand pipeline: the next 64-row chunk of W is fetched from L2 into registers while the tensor core works
+	// on the current one (the single B buffer can only be rewritten once those MMAs have completed), so the
+	// global-load latency no longer sits between two MMA batches.
+	constexpr int RW = kNChunk*H/4/kThreads;
+	float4 wreg[RW];
+	auto loadW = [&](int l, int nc) {
+#pragma unroll
+		for (int i = 0; i < RW; i++) {
+			const int idx = tid + i*kThreads, k4 = idx/kNChunk, r = idx - k4*kNChunk; // lanes walk down the rows of one core-matrix column
+			wreg[i] = __ldg(reinterpret_cast<const float4*>(&P.W[l][(size_t)(nc*kNChunk + r)*H + 4*k4]));
+		}
+	};
+	auto storeW = [&]() { // hi/lo TF32 split into the K-major core-matrix layout
+#pragma unroll
+		for (int i = 0; i < RW; i++) {
+			const int idx = tid + i*kThreads, k4 = idx/kNChunk, r = idx - k4*kNChunk;
+			float4 h, o;
+			splitTf32(wreg[i].x, h.x, o.x); splitTf32(wreg[i].y, h.y, o.y); splitTf32(wreg[i].z, h.z, o.z); splitTf32(wreg[i].w, h.w, o.w);
+			const int off = coreOffsetBytes<H>(r, 4*k4);
+			*reinterpret_cast<float4*>(Bhi + off) = h;
+			*reinterpret_cast<float4*>(Blo + off) = o;
+		}
+	};
+	if (nHidden >= 1 && (long long)blockIdx.x*kTile < n) loadW(1, 0);
 
 	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
 		const long long s = tile*kTile + row;
@@ -147,15 +171,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
-				for (int idx = tid; idx < kNChunk*H/4; idx += kThreads) {
-					int k4 = idx/kNChunk, r = idx - k4*kNChunk; // lanes walk down the rows of one core-matrix column
-					float4 w = __ldg(reinterpret_cast<const float4*>(&P.W[l][(size_t)(nc*kNChunk + r)*H + 4*k4]));
-					float4 h, o;
-					splitTf32(w.x, h.x, o.x); splitTf32(w.y, h.y, o.y); splitTf32(w.z, h.z, o.z); splitTf32(w.w, h.w, o.w);
-					int off = coreOffsetBytes<H>(r, 4*k4);
-					*reinterpret_cast<float4*>(Bhi + off) = h;
-					*reinterpret_cast<float4*>(Blo + off) = o;
-				}
+				storeW();
 				// generic-proxy writes (A from the previous epilogue, B from above) -> visible to the tensor core
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -175,6 +191,12 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 					}
 					// arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
 					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barAddr) : "memory");
+				}
+				{ // fetch the chunk that follows (this layer, the next layer, or the first one of the next tile) during the MMAs
+					int ln = l, ncn = nc + 1;
+					if (ncn == H/kNChunk) { ncn = 0; ln = l + 1; }
+					if (ln <= nHidden) loadW(ln, ncn);
+					else if ((tile + gridDim.x)*kTile < n) loadW(1, 0);
 				}
 				mbarWait(barAddr, phase);
 				phase ^= 1u;
