@@ -67,10 +67,11 @@ int nmc_siren_backward(const nmc_siren_shape* shape, const float* const* W, cons
 int nmc_siren_weight_grads(const nmc_siren_shape* shape, const float* x, int64_t n, const float* dZ, const float* A,
 						   float* const* gW, float* const* gb, void* stream);
 
-/* Tensor-core forward (tcgen05, 3xTF32 split => fp32-level accuracy) for inference batches; same contract as
- * nmc_siren_forward without z_saved. Falls back to an error (never to another path) on unsupported shapes. */
+/* Tensor-core forward (tcgen05, 3xTF32 split => fp32-level accuracy); same contract as nmc_siren_forward, including the
+ * optional z_saved for a following nmc_siren_backward.  Returns an error (never takes another path) on unsupported
+ * shapes (hidden 64 | 128, at least one hidden layer). */
 int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
-						 int64_t n, float* y, const nmc_siren_envelope* env, void* stream);
+						 int64_t n, float* y, float* z_saved, const nmc_siren_envelope* env, void* stream);
 
 /* torch.optim.Adam step (no weight decay, no amsgrad) over one flat parameter buffer; step is 1-based. */
 int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -91,7 +91,8 @@ constexpr int kThreads = 2*kTile;
 
 template <int H>
 __global__ void __launch_bounds__(kThreads)
-sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y) {
+sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y,
+			   float* __restrict__ zSaved) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned char* Ahi = smem;
 	unsigned char* Alo = Ahi + kTile*H*4;
@@ -160,6 +161,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 					float z = __ldg(&P.b[0][c + q]) + __ldg(w)*x0;
 					if (inDim > 1) z += __ldg(w + 1)*x1;
 					if (inDim > 2) z += __ldg(w + 2)*x2;
+					if (zSaved && live) zSaved[(size_t)(c + q)*n + s] = z;   // a warp writes 32 consecutive samples of one neuron
 					splitTf32(live ? sinReduced(w0*z) : 0.0f, hi[q], lo[q]);
 				}
 				int off = coreOffsetBytes<H>(row, c);
@@ -217,7 +219,9 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
 						int c = c0 + q4 + q;
-						float a = sinReduced(w0*(__uint_as_float(v[q4 + q]) + __ldg(&P.b[l][c])));
+						const float z = __uint_as_float(v[q4 + q]) + __ldg(&P.b[l][c]);
+						if (zSaved && live) zSaved[((size_t)l*H + c)*n + s] = z;
+						float a = sinReduced(w0*z);
 						if (!live) a = 0.0f;
 						if (l == nHidden) {
 							y0 += __ldg(&P.W[last][c])*a;
@@ -259,12 +263,12 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 } // namespace
 
 extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
-									int64_t n, float* y, const nmc_siren_envelope* envp, void* stream);
+									int64_t n, float* y, float* z_saved, const nmc_siren_envelope* envp, void* stream);
 
 namespace nmc_siren_detail { void setError(const char* m); }
 
 extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
-									int64_t n, float* y, const nmc_siren_envelope* envp, void* stream) {
+									int64_t n, float* y, float* z_saved, const nmc_siren_envelope* envp, void* stream) {
 	if (!sh || !W || !b) { nmc_siren_detail::setError("null argument"); return 1; }
 	if ((sh->hidden != 64 && sh->hidden != 128) || sh->n_hidden_layers < 1 || sh->n_hidden_layers + 2 > kMaxLayers ||
 		sh->in_dim < 1 || sh->in_dim > 3 || sh->out_dim < 1 || sh->out_dim > 3) {
@@ -289,10 +293,10 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenForwardTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<64><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+		if (!e) sirenForwardTc<64><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
 	} else {
 		e = cudaFuncSetAttribute(sirenForwardTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<128><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y);
+		if (!e) sirenForwardTc<128><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
 	}
 	if (!e) e = cudaGetLastError();
 	if (e) { nmc_siren_detail::setError(cudaGetErrorString(e)); return 1; }

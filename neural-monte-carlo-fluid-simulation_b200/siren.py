@@ -120,7 +120,7 @@ def _lib():
         vp = C.c_void_p
         L.nmc_siren_last_error.restype = C.c_char_p
         L.nmc_siren_forward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, C.POINTER(Envelope), vp]
-        L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, C.POINTER(Envelope), vp]
+        L.nmc_siren_forward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_backward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp,
                                          vp, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_weight_grads.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
@@ -167,7 +167,7 @@ class _SirenFn(torch.autograd.Function):
                 _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, _stream()))
                 ctx.save_for_backward(x2, z, *W, *b)
             elif tensor_cores and n >= 16384:  # smaller batches: the split fp32 kernel beats the per-tile latency of the tcgen05 one
-                _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), env, _stream()))
+                _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, env, _stream()))
             else:
                 _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, env, _stream()))
         ctx.w0, ctx.n_layers, ctx.lead, ctx.x_needs, ctx.env = w0, n_layers, lead, ctx.needs_input_grad[0], env
@@ -351,6 +351,7 @@ class DirectFit:
         averaged with ONE all_reduce per iteration and every rank applies the same Adam step.  The parameters are
         broadcast from rank 0 by sync_parameters()."""
         self.net, self.env = net, envelope
+        self.tensor_cores = bool(getattr(net, "tensor_cores", False))
         self.group, self.world = group, 1
         if distributed:
             import torch.distributed as dist
@@ -381,7 +382,10 @@ class DirectFit:
         y = torch.empty((n, sh.out_dim), device=x.device)
         z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]  # [layer*H + neuron][sample], stride n
         with torch.cuda.device(x.device):
-            _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
+            if self.tensor_cores and n >= 16384 and sh.n_hidden_layers >= 1:  # tcgen05 forward that also writes the pre-activations
+                _check(_lib().nmc_siren_forward_tc(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
+            else:
+                _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
         diff = y - target
         gy = diff*(2.0/diff.numel())
         dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)

@@ -259,3 +259,26 @@ def test_graph_replayed_fit_matches_torch_adam(siren):
     assert moved > 10*lr
     fit.opt.reset()
     assert int(fit.opt.step_dev.item()) == 0 and not fit.opt.m.any()
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 2, 2), (3, 64, 5, 3)])
+def test_tensor_core_training_forward_equals_fp32_path(siren, shape):
+    """DirectFit at batch 16384 takes the tcgen05 forward, which also writes the pre-activations for the backward
+    chain (3xTF32 split: fp32-level accuracy): same parameter trajectory as the fp32 split kernels."""
+    a = _net(siren, shape, seed=61, tensor_cores=True)
+    b = _net(siren, shape, seed=61, tensor_cores=False)
+    start = [p.detach().clone() for p in a.parameters()]
+    x = _coords(16384, shape[0], seed=62)
+    target = torch.sin(x[:, :1]*3.0).repeat(1, shape[3])
+    env = siren.wall_envelope((-1.0, 1.0)*shape[0], 0.1)
+    fa = siren.DirectFit(a, 1e-4, env, max_batch=16384)
+    fb = siren.DirectFit(b, 1e-4, env, max_batch=16384)
+    assert fa.tensor_cores and not fb.tensor_cores
+    for _ in range(6):
+        da = fa.iterate(x, target); db = fb.iterate(x, target)
+    assert (da - db).abs().max().item() <= 2e-5*db.abs().max().item() + 1e-7
+    za, zb = fa.z[: fb.z.numel()], fb.z
+    assert (za - zb).abs().max().item() <= 2e-5*zb.abs().max().item()      # saved pre-activations of the last iteration
+    for p, q, r in zip(a.parameters(), b.parameters(), start):
+        moved = (q - r).abs().max().item()
+        assert (p - q).abs().max().item() <= 0.02*moved + 1e-8
