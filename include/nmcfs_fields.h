@@ -23,6 +23,10 @@ const char* nmc_fields_last_error(void);
 int nmc_advect_density(int dim, const int* shape, const float* d_in, const float* vel, float dt,
 					   const float* lo, const float* extent, int mode, float* d_out, void* stream);
 
+/* Semi-Lagrangian back-trace of the advection fit (model_split.py:97-103): out[s][a] = clamp(x[s][a] - dt u[s][a],
+ * lo[a], hi[a]); lo / hi are HOST arrays of dim floats. */
+int nmc_backtrace(int dim, const float* x, const float* u, int64_t n, float dt, const float* lo, const float* hi, float* out, void* stream);
+
 /* sum over n samples of || u[s][:] - u_ref[s][:] ||^2 (dim floats per sample) accumulated in double into *out_sum,
  * which the caller zero-fills; the mean is the Taylor-Green error metric (move_density.py:143-146). */
 int nmc_sum_squared_error(int dim, const float* u, const float* u_ref, int64_t n, double* out_sum, void* stream);

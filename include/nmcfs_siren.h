@@ -73,6 +73,10 @@ int nmc_siren_weight_grads(const nmc_siren_shape* shape, const float* x, int64_t
 int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
 						 int64_t n, float* y, float* z_saved, const nmc_siren_envelope* env, void* stream);
 
+/* MSE loss of a fit iteration in one launch: diff = y - target, grad_y = dL/dy = diff * 2/count, *loss = mean(diff^2)
+ * (count = n * out_dim floats; base.py:83-96 with the loss of model_split.py:113). */
+int nmc_mse_grad(const float* y, const float* target, int64_t count, float* diff, float* grad_y, float* loss, void* stream);
+
 /* torch.optim.Adam step (no weight decay, no amsgrad) over one flat parameter buffer; step is 1-based. */
 int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
 				  float eps, int64_t step, void* stream);

@@ -44,7 +44,7 @@ class SolveStats(C.Structure):
 EXPORTS = ["nmc_last_error", "nmc_device_count", "nmc_scene_create", "nmc_scene_destroy", "nmc_scene_set_source",
            "nmc_scene_dim", "nmc_scene_bbox", "nmc_scene_num_nodes", "nmc_scene_nodes", "nmc_wost_solve",
            "nmc_wost_solve_device", "nmc_wost_solve_stats", "nmc_point_seed", "nmc_probe"]
-SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_adam_step", "nmc_adam_step_device"]
+SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_adam_step", "nmc_adam_step_device", "nmc_mse_grad"]
 
 _lib = None
 _fp = C.POINTER(C.c_float)

@@ -75,6 +75,16 @@ __global__ void sumSquaredError(const float* __restrict__ u, const float* __rest
 	}
 }
 
+struct Box3 { float lo[3], hi[3]; };
+// semi-Lagrangian back-trace of the fit loops: out = clamp(x - dt u, lo, hi)  (model_split.py:100-103)
+__global__ void backtrace(const float* __restrict__ x, const float* __restrict__ u, long long count, int dim, float dt, Box3 b,
+						  float* __restrict__ out) {
+	for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x*blockDim.x) {
+		const int a = (int)(t % dim);
+		out[t] = fminf(fmaxf(x[t] - u[t]*dt, b.lo[a]), b.hi[a]);
+	}
+}
+
 int smCount() {
 	static int n = 0;
 	if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -106,6 +116,20 @@ int nmc_advect_density(int dim, const int* shape, const float* d_in, const float
 	else advectDensity<3><<<grid, block, 0, (cudaStream_t)stream>>>(G, d_in, vel, dt, mode, d_out, total);
 	cudaError_t e = cudaGetLastError();
 	return e == cudaSuccess ? 0 : fail("advectDensity launch", e);
+}
+
+int nmc_backtrace(int dim, const float* x, const float* u, int64_t n, float dt, const float* lo, const float* hi, float* out, void* stream) {
+	if (dim < 1 || dim > 3) return fail("dim must be 1..3");
+	if (n <= 0) return 0;
+	if (!x || !u || !lo || !hi || !out) return fail("null argument");
+	Box3 b;
+	for (int a = 0; a < 3; a++) { b.lo[a] = a < dim ? lo[a] : 0.0f; b.hi[a] = a < dim ? hi[a] : 0.0f; }
+	const long long count = (long long)n*dim;
+	const int block = 256;
+	long long blocks = (count + block - 1)/block, cap = 16ll*smCount();
+	backtrace<<<(unsigned)(blocks < cap ? blocks : cap), block, 0, (cudaStream_t)stream>>>(x, u, count, dim, dt, b, out);
+	cudaError_t e = cudaGetLastError();
+	return e == cudaSuccess ? 0 : fail("backtrace launch", e);
 }
 
 int nmc_sum_squared_error(int dim, const float* u, const float* u_ref, int64_t n, double* out_sum, void* stream) {

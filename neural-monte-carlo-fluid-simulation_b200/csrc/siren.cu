@@ -527,6 +527,28 @@ sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __res
 	if (tid < RP) atomicAdd(&P.gb[l][tid], bsum);
 }
 
+// MSE loss of a fit iteration in one pass: diff = y - target, grad_y = diff * 2/count, loss = mean(diff^2).
+// One CTA (the fit batches hold at most a few 10^5 floats): no atomics, the loss needs no zero-fill.
+__global__ void __launch_bounds__(1024) mseGrad(const float* __restrict__ y, const float* __restrict__ target, long long count,
+												 float* __restrict__ diff, float* __restrict__ gy, float* __restrict__ loss) {
+	const float scale = 2.0f/(float)count;
+	float acc = 0.0f;
+	for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+		const float d = y[i] - target[i];
+		diff[i] = d; gy[i] = d*scale;
+		acc += d*d;
+	}
+	for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+	__shared__ float part[32];
+	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0f;
+		for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+		if (threadIdx.x == 0) *loss = v/(float)count;
+	}
+}
+
 // Adam with the step counter in device memory: a CUDA graph that replays one fit iteration must not freeze the bias
 // corrections at their capture-time values, so the counter is advanced by a one-thread kernel and read by the update.
 __global__ void adamAdvance(long long* step) { *step += 1; }
@@ -698,6 +720,14 @@ extern "C" int nmc_siren_weight_grads(const nmc_siren_shape* sh, const float* x,
 	cudaStream_t st = (cudaStream_t)stream;
 	if (sh->hidden == 64) sirenWeightGrad<64><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A, chunk);
 	else sirenWeightGrad<128><<<grid, kGT, 0, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, x, n, dZ, A, chunk);
+	cudaError_t e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_mse_grad(const float* y, const float* target, int64_t count, float* diff, float* grad_y, float* loss, void* stream) {
+	if (count <= 0) return 0;
+	if (!y || !target || !diff || !grad_y || !loss) return fail("null buffer");
+	mseGrad<<<1, 1024, 0, (cudaStream_t)stream>>>(y, target, count, diff, grad_y, loss);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

@@ -13,7 +13,7 @@ import torch
 
 from . import capi
 
-FIELDS_EXPORTS = ["nmc_fields_last_error", "nmc_advect_density", "nmc_sum_squared_error"]
+FIELDS_EXPORTS = ["nmc_fields_last_error", "nmc_advect_density", "nmc_backtrace", "nmc_sum_squared_error"]
 _ready = False
 
 
@@ -25,6 +25,7 @@ def _lib():
         L.nmc_advect_density.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_float),
                                          C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_void_p]
         L.nmc_sum_squared_error.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.nmc_backtrace.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
         _ready = True
     return L
 
@@ -57,6 +58,20 @@ def advect_density(density, velocity, dt, lo, extent, mode="constant"):
     m = {"constant": 0, "nearest": 1}[mode]
     with torch.cuda.device(d.device):
         _check(_lib().nmc_advect_density(dim, shape, d.data_ptr(), v.data_ptr(), float(dt), flo, fex, m, out.data_ptr(), _stream()))
+    return out
+
+
+def backtrace(x, u, dt, lo, hi):
+    """clamp(x - dt*u, lo, hi) in one launch (the back-traced positions of _advect_velocity, model_split.py:97-103)."""
+    a = _cuda_f32(x, "x"); b = _cuda_f32(u, "u")
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    dim = a.shape[-1]
+    out = torch.empty_like(a)
+    flo = (C.c_float*3)(*[float(v) for v in lo], *([0.0]*(3 - dim)))
+    fhi = (C.c_float*3)(*[float(v) for v in hi], *([0.0]*(3 - dim)))
+    with torch.cuda.device(a.device):
+        _check(_lib().nmc_backtrace(dim, a.data_ptr(), b.data_ptr(), a.numel()//dim, float(dt), flo, fhi, out.data_ptr(), _stream()))
     return out
 
 

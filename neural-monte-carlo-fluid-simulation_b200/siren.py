@@ -126,6 +126,7 @@ def _lib():
         L.nmc_siren_weight_grads.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         L.nmc_adam_step_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+        L.nmc_mse_grad.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
         _configured = True
     return L
 
@@ -374,6 +375,7 @@ class DirectFit:
         assert off[0] == g.numel()
         self.z = torch.empty((Lh + 1)*H*max_batch, device=g.device)
         self.max_batch = max_batch
+        self.loss = torch.zeros((), device=g.device)  # mean squared error of the last iterate() call
 
     def iterate(self, x, target):
         n = x.shape[0]
@@ -386,8 +388,10 @@ class DirectFit:
                 _check(_lib().nmc_siren_forward_tc(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
             else:
                 _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
-        diff = y - target
-        gy = diff*(2.0/diff.numel())
+        diff = torch.empty_like(y); gy = torch.empty_like(y)
+        tgt = target.contiguous()
+        with torch.cuda.device(x.device):  # diff, dL/dy and the loss in one launch
+            _check(_lib().nmc_mse_grad(y.data_ptr(), tgt.data_ptr(), y.numel(), diff.data_ptr(), gy.data_ptr(), self.loss.data_ptr(), _stream()))
         dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)
         self.opt.g.zero_()
         _param_grads(sh, x, n, dZ, A, out=self.out)

@@ -20,7 +20,7 @@ import ctypes as C
 
 import torch
 
-from . import capi, zombie
+from . import capi, zombie, fields
 from .siren import FusedSiren, DirectFit, wall_envelope, karman_envelope, smoke_obs_envelope, envelope_reference
 
 
@@ -191,12 +191,11 @@ class SplitStepper:
         if cached is not None:
             graph, loss_buf = cached
         else:
-            loss_buf = torch.zeros((), device=self.dev)
+            loss_buf = fit.loss  # mean squared error, written by the iteration itself
 
             def one():
                 samples, target = iteration()
-                diff = fit.iterate(samples, target)
-                loss_buf.copy_(torch.mean(diff*diff))
+                fit.iterate(samples, target)
 
             graph = None
             if self.use_graph:
@@ -230,7 +229,7 @@ class SplitStepper:
             samples = self.sample_random(n)
             with torch.no_grad():
                 prev_u = self.query_velocity(samples, use_prev=True)
-                back = torch.clamp(samples - prev_u*self.dt, min=self._lo, max=self._hi)
+                back = fields.backtrace(samples, prev_u, self.dt, self.size[0::2], self.size[1::2])
                 advected = self.query_velocity(back, use_prev=True)
             return samples, advected
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect")

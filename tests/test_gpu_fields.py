@@ -91,3 +91,22 @@ def test_taylor_green_error_metric(F):
     a = torch.rand(1000, 3, device="cuda"); b = torch.rand(1000, 3, device="cuda")
     assert F.mean_squared_error(a, b) == pytest.approx(((a - b).double()**2).sum(-1).mean().item(), rel=1e-6)
     assert math.isfinite(e)
+
+
+def test_backtrace_and_fused_mse(F):
+    """The two glue kernels of the fit iteration: clamp(x - dt u, lo, hi) and (diff, dL/dy, loss) of the MSE."""
+    for dim in (2, 3):
+        x = torch.rand(5000, dim, device="cuda")*2 - 1
+        u = torch.randn(5000, dim, device="cuda")*3
+        lo, hi = [-1.0, -0.5, -0.25][:dim], [1.0, 0.75, 0.5][:dim]
+        want = torch.clamp(x - u*0.1, min=torch.tensor(lo, device="cuda"), max=torch.tensor(hi, device="cuda"))
+        assert torch.allclose(F.backtrace(x, u, 0.1, lo, hi), want, atol=1e-6)
+    pkg = util.package()
+    S = pkg.load_siren()
+    import ctypes as C
+    L = S._lib()
+    y = torch.randn(4096, 3, device="cuda"); t = torch.randn(4096, 3, device="cuda")
+    diff = torch.empty_like(y); gy = torch.empty_like(y); loss = torch.full((), 123.0, device="cuda")   # no zero-fill needed
+    assert L.nmc_mse_grad(y.data_ptr(), t.data_ptr(), y.numel(), diff.data_ptr(), gy.data_ptr(), loss.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    assert torch.equal(diff, y - t) and torch.allclose(gy, (y - t)*(2.0/y.numel()), rtol=1e-6, atol=0)
+    assert loss.item() == pytest.approx(((y - t).double()**2).mean().item(), rel=1e-5)
