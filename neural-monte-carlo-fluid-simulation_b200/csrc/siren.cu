@@ -254,8 +254,11 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 				  float* __restrict__ y, float* __restrict__ zSaved) {
 	extern __shared__ float smem[];
 	constexpr int LD = H + 4, NG = H/NPT, NT = 32*NG;
-	float* Wt = smem;                   // [H][LD]  Wt[k][nn] = W_l[nn][k]
-	float* act = Wt + H*LD;             // [2][H][kTS]
+	// H = 64: two weight buffers, the next layer's weights stream in with cp.async while this layer is computed
+	// (a layer is ~2.5 us, of which the L2 -> shared copy was more than a third); H = 128 keeps one buffer (occupancy).
+	constexpr int NB = H == 64 ? 2 : 1;
+	float* Wt = smem;                   // [NB][H][LD]  Wt[k][nn] = W_l[nn][k]
+	float* act = Wt + NB*H*LD;          // [2][H][kTS]
 	float* part = act + 2*H*kTS;        // [H/NPT][3][kTS]
 	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = NPT*g;
 	const int last = nHidden + 1;
@@ -264,6 +267,16 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 		const bool live = s < n;
 		float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
 		if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
+		auto stageAsync = [&](int l, float* dst) { // transposing copy (8 (k) x 4 (nn) patches per warp), asynchronous
+			for (int idx = tid; idx < H*H; idx += NT) {
+				const int b = idx >> 5, kk = idx & 7, nq = (idx >> 3) & 3;
+				const int k = (b % (H/8))*8 + kk, nn = (b/(H/8))*4 + nq;
+				const unsigned d = (unsigned)__cvta_generic_to_shared(&dst[k*LD + nn]);
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(&P.W[l][nn*H + k]) : "memory");
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		};
+		if (NB == 2 && nHidden >= 1) stageAsync(1, Wt); // nobody reads buffer 0 any more: every warp passed the barrier before the output
 		float a16[NPT];
 #pragma unroll
 		for (int j = 0; j < NPT; j++) { // first layer: in -> H
@@ -277,14 +290,22 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 		}
 		int cur = 0;
 		for (int l = 1; l <= nHidden; l++) {
-			__syncthreads(); // act[cur] is complete, nobody reads Wt any more
-			// transposing copy, bank-conflict free: a warp writes an 8 (k) x 4 (nn) patch = banks 4 kk + nq
-			for (int idx = tid; idx < H*H; idx += NT) {
-				const int b = idx >> 5, kk = idx & 7, nq = (idx >> 3) & 3;
-				const int k = (b % (H/8))*8 + kk, nn = (b/(H/8))*4 + nq;
-				Wt[k*LD + nn] = __ldg(&P.W[l][nn*H + k]);
+			const float* Wl = Wt;
+			if (NB == 2) {
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+				__syncthreads(); // this layer's weights have landed (all threads' copies), act[cur] is complete
+				Wl = Wt + ((l - 1) & 1)*H*LD;
+				if (l < nHidden) stageAsync(l + 1, Wt + (l & 1)*H*LD); // the other buffer was last read by layer l - 1
+			} else {
+				__syncthreads(); // act[cur] is complete, nobody reads Wt any more
+				// transposing copy, bank-conflict free: a warp writes an 8 (k) x 4 (nn) patch = banks 4 kk + nq
+				for (int idx = tid; idx < H*H; idx += NT) {
+					const int b = idx >> 5, kk = idx & 7, nq = (idx >> 3) & 3;
+					const int k = (b % (H/8))*8 + kk, nn = (b/(H/8))*4 + nq;
+					Wt[k*LD + nn] = __ldg(&P.W[l][nn*H + k]);
+				}
+				__syncthreads();
 			}
-			__syncthreads();
 			float acc[NPT];
 #pragma unroll
 			for (int j = 0; j < NPT; j++) acc[j] = __ldg(&P.b[l][n0 + j]);
@@ -292,7 +313,7 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 #pragma unroll 8
 			for (int k = 0; k < H; k++) {
 				const float av = ac[k*kTS];
-				const float4* w = reinterpret_cast<const float4*>(&Wt[k*LD + n0]);
+				const float4* w = reinterpret_cast<const float4*>(&Wl[k*LD + n0]);
 #pragma unroll
 				for (int q = 0; q < NPT/4; q++) {
 					const float4 v = w[q];
@@ -607,7 +628,7 @@ bool useSplit(long long n) {
 	return n <= limit;
 }
 constexpr int kNpt64 = 8, kNpt128 = 8; // neurons per thread: 8 warps per CTA for both widths
-size_t splitSmem(int H) { return ((size_t)H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/(H == 64 ? kNpt64 : kNpt128))*3*kTS)*sizeof(float); }
+size_t splitSmem(int H, bool forward = false) { return ((size_t)(forward && H == 64 ? 2 : 1)*H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/(H == 64 ? kNpt64 : kNpt128))*3*kTS)*sizeof(float); }
 
 int smCount() {
 	int dev = 0, sms = 148;
@@ -634,8 +655,8 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 	const int H = sh->hidden;
 	cudaStream_t st = (cudaStream_t)stream;
 	cudaError_t e;
-	if (useSplit(n)) { // small batches: a sample's layer split over H/16 threads (see sirenForwardSplit)
-		size_t smemS = splitSmem(H);
+	if (useSplit(n)) { // small batches: a sample's layer split over several threads (see sirenForwardSplit)
+		size_t smemS = splitSmem(H, true);
 		long long tilesS = (n + kTS - 1)/kTS;
 		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
 		if (H == 64) {
