@@ -362,8 +362,9 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				   float* __restrict__ dZ, float* __restrict__ A) {
 	extern __shared__ float smem[];
 	constexpr int LD = H + 4, NG = H/NPT, NT = 32*NG;
-	float* Ws = smem;                   // [H][LD]  W_l row-major (nn, k)
-	float* ex = Ws + H*LD;              // [2][H][kTS] delta exchange
+	constexpr int NB = H == 64 ? 2 : 1; // H = 64: the next layer's weights stream in with cp.async (see sirenForwardSplit)
+	float* Ws = smem;                   // [NB][H][LD]  W_l row-major (nn, k)
+	float* ex = Ws + NB*H*LD;           // [2][H][kTS] delta exchange
 	float* part = ex + 2*H*kTS;         // [H/NPT][3][kTS]
 	const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5, n0 = NPT*g;
 	const int last = nHidden + 1;
@@ -396,6 +397,15 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
 			}
 		}
+		auto stageAsync = [&](int l, float* dst) {
+			for (int idx = tid; idx < H*H/4; idx += NT) {
+				const int nn = idx/(H/4), k4 = idx - nn*(H/4);
+				const unsigned d = (unsigned)__cvta_generic_to_shared(&dst[nn*LD + 4*k4]);
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(&P.W[l][nn*H + 4*k4]) : "memory");
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		};
+		if (NB == 2 && nHidden >= 1) stageAsync(nHidden, Ws); // layer index l uses buffer (nHidden - l) & 1; buffer 0 is free (barrier at the tile's end)
 		float g16[NPT];
 #pragma unroll
 		for (int i = 0; i < NPT; i++) { // g_L = W_last^T gy'
@@ -419,12 +429,20 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				exw[(n0 + i)*kTS] = g16[i];
 			}
 			if (l == 0) break;
-			__syncthreads(); // ex[cur] complete, nobody reads Ws any more
-			for (int idx = tid; idx < H*H/4; idx += NT) {
-				const int nn = idx/(H/4), k4 = idx - nn*(H/4);
-				*reinterpret_cast<float4*>(&Ws[nn*LD + 4*k4]) = __ldg(reinterpret_cast<const float4*>(&P.W[l][nn*H + 4*k4]));
+			const float* Wl = Ws;
+			if (NB == 2) {
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+				__syncthreads(); // W_l has landed, ex[cur] complete
+				Wl = Ws + ((nHidden - l) & 1)*H*LD;
+				if (l > 1) stageAsync(l - 1, Ws + ((nHidden - l + 1) & 1)*H*LD); // the other buffer was last read by layer l + 1
+			} else {
+				__syncthreads(); // ex[cur] complete, nobody reads Ws any more
+				for (int idx = tid; idx < H*H/4; idx += NT) {
+					const int nn = idx/(H/4), k4 = idx - nn*(H/4);
+					*reinterpret_cast<float4*>(&Ws[nn*LD + 4*k4]) = __ldg(reinterpret_cast<const float4*>(&P.W[l][nn*H + 4*k4]));
+				}
+				__syncthreads();
 			}
-			__syncthreads();
 			float acc[NPT];
 #pragma unroll
 			for (int i = 0; i < NPT; i++) acc[i] = 0.0f;
@@ -432,7 +450,7 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 #pragma unroll 8
 			for (int nn = 0; nn < H; nn++) { // g_{l-1}[k] = sum_nn W_l[nn][k] dz[nn]
 				const float dv = er[nn*kTS];
-				const float4* w = reinterpret_cast<const float4*>(&Ws[nn*LD + n0]);
+				const float4* w = reinterpret_cast<const float4*>(&Wl[nn*LD + n0]);
 #pragma unroll
 				for (int q = 0; q < NPT/4; q++) {
 					const float4 v = w[q];
@@ -628,7 +646,7 @@ bool useSplit(long long n) {
 	return n <= limit;
 }
 constexpr int kNpt64 = 8, kNpt128 = 8; // neurons per thread: 8 warps per CTA for both widths
-size_t splitSmem(int H, bool forward = false) { return ((size_t)(forward && H == 64 ? 2 : 1)*H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/(H == 64 ? kNpt64 : kNpt128))*3*kTS)*sizeof(float); }
+size_t splitSmem(int H) { return ((size_t)(H == 64 ? 2 : 1)*H*(H + 4) + (size_t)2*H*kTS + (size_t)(H/(H == 64 ? kNpt64 : kNpt128))*3*kTS)*sizeof(float); }
 
 int smCount() {
 	int dev = 0, sms = 148;
@@ -656,7 +674,7 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 	cudaStream_t st = (cudaStream_t)stream;
 	cudaError_t e;
 	if (useSplit(n)) { // small batches: a sample's layer split over several threads (see sirenForwardSplit)
-		size_t smemS = splitSmem(H, true);
+		size_t smemS = splitSmem(H);
 		long long tilesS = (n + kTS - 1)/kTS;
 		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
 		if (H == 64) {
