@@ -494,8 +494,11 @@ template <int H>
 __global__ void __launch_bounds__(kGT)
 sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __restrict__ x, long long n,
 				const float* __restrict__ dZ, const float* __restrict__ A, int chunk) {
-	__shared__ float Ps[H][kGS + 1];
-	__shared__ float Qs[H][kGS + 1];
+	// staged tiles are sample-major, [sample][row], so that a thread's four rows are one 16-byte load and the lanes of a
+	// warp read consecutive 16-byte words (the row-major layout cost four 4-way-conflicted scalar loads instead)
+	constexpr int LDS = H + 4;
+	__shared__ __align__(16) float Ps[kGS][LDS];
+	__shared__ __align__(16) float Qs[kGS][LDS];
 	const int tid = threadIdx.x;
 	const int l = blockIdx.y;                 // 0 .. nHidden + 1
 	const int last = nHidden + 1;
@@ -523,18 +526,20 @@ sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __res
 	for (long long sb = s0; sb < s1; sb += kGS) {
 		const int ns = (int)(s1 - sb < kGS ? s1 - sb : kGS);
 		__syncthreads();
-		for (int idx = tid; idx < RP*kGS; idx += kGT) { int r = idx/kGS, c = idx - r*kGS; Ps[r][c] = c < ns ? Pg[(size_t)r*n + sb + c] : 0.0f; }
-		if (l == 0) { for (int idx = tid; idx < kGS*inDim; idx += kGT) { int c = idx/inDim, r = idx - c*inDim; Qs[r][c] = c < ns ? x[(sb + c)*inDim + r] : 0.0f; } }
-		else { for (int idx = tid; idx < RQ*kGS; idx += kGT) { int r = idx/kGS, c = idx - r*kGS; Qs[r][c] = c < ns ? Qg[(size_t)r*n + sb + c] : 0.0f; } }
+		for (int idx = tid; idx < RP*kGS; idx += kGT) { int r = idx/kGS, c = idx - r*kGS; Ps[c][r] = c < ns ? Pg[(size_t)r*n + sb + c] : 0.0f; }
+		if (l == 0) { for (int idx = tid; idx < kGS*inDim; idx += kGT) { int c = idx/inDim, r = idx - c*inDim; Qs[c][r] = c < ns ? x[(sb + c)*inDim + r] : 0.0f; } }
+		else { for (int idx = tid; idx < RQ*kGS; idx += kGT) { int r = idx/kGS, c = idx - r*kGS; Qs[c][r] = c < ns ? Qg[(size_t)r*n + sb + c] : 0.0f; } }
 		__syncthreads();
 		if (hidden) {
 #pragma unroll 4
 			for (int c = 0; c < kGS; c++) {
-				float q0 = Qs[tj][c], q1 = Qs[tj + 1][c], q2 = Qs[tj + 2][c], q3 = Qs[tj + 3][c];
+				const float4 qv = *reinterpret_cast<const float4*>(&Qs[c][tj]);
+				const float q0 = qv.x, q1 = qv.y, q2 = qv.z, q3 = qv.w;
 #pragma unroll
 				for (int ps = 0; ps < NP; ps++) {
 					const int i0 = ti + ps*RB;
-					float p0 = Ps[i0][c], p1 = Ps[i0 + 1][c], p2 = Ps[i0 + 2][c], p3 = Ps[i0 + 3][c];
+					const float4 pv = *reinterpret_cast<const float4*>(&Ps[c][i0]);
+					const float p0 = pv.x, p1 = pv.y, p2 = pv.z, p3 = pv.w;
 					acc[ps][0][0] += p0*q0; acc[ps][0][1] += p0*q1; acc[ps][0][2] += p0*q2; acc[ps][0][3] += p0*q3;
 					acc[ps][1][0] += p1*q0; acc[ps][1][1] += p1*q1; acc[ps][1][2] += p1*q2; acc[ps][1][3] += p1*q3;
 					acc[ps][2][0] += p2*q0; acc[ps][2][1] += p2*q1; acc[ps][2][2] += p2*q2; acc[ps][2][3] += p2*q3;
@@ -546,11 +551,11 @@ sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __res
 			for (int o = tid; o < RP*RQ; o += kGT, q++) {
 				int i = o/RQ, j = o - i*RQ;
 				float a = 0.0f;
-				for (int c = 0; c < kGS; c++) a += Ps[i][c]*Qs[j][c];
+				for (int c = 0; c < kGS; c++) a += Ps[c][i]*Qs[c][j];
 				small[q] += a;
 			}
 		}
-		if (tid < RP) { float a = 0.0f; for (int c = 0; c < kGS; c++) a += Ps[tid][c]; bsum += a; }
+		if (tid < RP) { float a = 0.0f; for (int c = 0; c < kGS; c++) a += Ps[c][tid]; bsum += a; }
 	}
 	if (hidden) {
 #pragma unroll
