@@ -3,7 +3,7 @@
 the Taylor-Green configuration (examples/taylorgreen/run.sh: SIREN 6x64, batch 64^2, 512^2 pressure samples,
 1002^2 divergence grid, nWalks 500) with K Adam iterations per fit, through the device-resident stepper, next to
 the reference's arrangement of the same work: stock PyTorch ops for the fits (one loss.item() per iteration),
-divergence grid to the host, the reference's CPU walk-on-stars (oracle/_ref, bounded sample), gradients back.
+divergence grid to the host, the reference's CPU walk-on-stars (its rate comes from `bench.py --impl reference` on the same scene), gradients back.
 `--watertight` keeps the scene as shipped (the reference then classifies every point outside and returns zeros);
 default is the solver-active variant."""
 import argparse
@@ -122,15 +122,15 @@ def main():
     for _ in range(n_ref):
         ref_iter()
     torch.cuda.synchronize(); ref_iter_ms = 1e3*(time.perf_counter() - t)/n_ref
-    div = s.last["div"].cpu().numpy()
-    from oracle import refbind
-    threads = os.cpu_count() or 1
+    # CPU solver rate: the reference arm of bench.py (the one place that runs oracle/_ref) on this configuration's scene
+    import subprocess
     n_press = int(s.last["pressure_samples"].shape[0])
-    pts = s.last["pressure_samples"][: args.cpu_sample].cpu().numpy()
-    t = time.perf_counter()
-    sc = refbind.RefScene(s.dim, cfg["scene"], div)
-    sc.wost(cfg["solver"], cfg["output"], pts, seed=1, nthreads=threads)
-    cpu_wost_s = (time.perf_counter() - t)*(n_press/len(pts))
+    ref_case = {"taylorgreen": "taylorgreen_shipped" if args.watertight else "taylorgreen_active", "karman": "karman", "smoke_obs": "smoke3d"}[args.case]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--case", ref_case, "--points", str(args.cpu_sample),
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900)
+    arm = json.loads(r.stdout.strip().splitlines()[-1])
+    threads = arm["cpu_baseline"]["cores"]
+    cpu_wost_s = float(s.last["walks"])/arm["value"] if arm["value"] > 0 else float("nan")
     ref_step_s = 2*args.iters*ref_iter_ms*1e-3 + cpu_wost_s
     print(json.dumps({"metric": "sim_steps_per_sec", "value": ours, "unit": "steps/s",
                       "config": {"workload": "%s, %d Adam iterations per fit" % (what, args.iters), "case": args.case,
@@ -139,7 +139,7 @@ def main():
                                  "parallelism": "replicated networks, data-parallel fits (1 gradient all_reduce per iteration), pressure samples sharded + all_gather" if world > 1 else "single GPU"},
                       "ms_per_step": 1e3*total/args.steps, "breakdown_ms_per_step": {k: v/args.steps for k, v in parts.items()},
                       "walks_per_step": int(s.last["walks"]), "pressure_samples": n_press, "wost_kernel_ms": s.last["wost_ms"],
-                      "reference_arrangement": {"fit_iteration_ms_stock_torch": ref_iter_ms, "cpu_wost_s_extrapolated_from_%d_points" % len(pts): cpu_wost_s,
+                      "reference_arrangement": {"fit_iteration_ms_stock_torch": ref_iter_ms, "cpu_walks_per_sec": arm["value"], "cpu_wost_s": cpu_wost_s,
                                                 "cores": threads, "step_s": ref_step_s, "steps_per_sec": 1.0/ref_step_s}}), flush=True)
     if world > 1:
         _leave()
