@@ -54,7 +54,8 @@ int nmc_siren_forward(const nmc_siren_shape* shape, const float* const* W, const
 /* Backward "delta chain": given grad_y = dL/dy [n][out] and the z_saved of the forward pass, writes
  *   dZ[l][j][s] = dL/dz_l and A[l][j][s] = sin(w0 z_l) for l = 0 .. n_hidden_layers (layout of z_saved;
  *   A has (L+1)*hidden*n floats, dZ has ((L+1)*hidden + out_dim)*n: its last out_dim rows receive grad_y'),
- *   and, if grad_x != NULL, dL/dx [n][in].
+ *   and, if grad_x != NULL, dL/dx [n][in].  dZ and A may both be NULL when only dL/dx is wanted (the divergence of a
+ *   frozen network): nothing but grad_x is written then.
  * The parameter gradients are then GEMMs over the batch dimension (done by the caller, one batched call):
  *   dW_0 = dZ_0 x,  dW_l = dZ_l A_{l-1}^T (l = 1..L),  dW_last = grad_y'^T A_L^T,  db_l = rowsum(dZ_l),
  *   with grad_y' = grad_y times the (detached) envelope weights when an envelope is given. */

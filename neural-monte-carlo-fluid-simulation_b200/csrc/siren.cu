@@ -177,9 +177,11 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				}
 				// rows (L+1)*H .. of dZ: the (envelope-scaled) output gradient, for dW_last = gy'^T A_L^T
 				const size_t r0 = (size_t)(nHidden + 1)*H;
-				dZ[(r0 + 0)*n + s] = gy0;
-				if (outDim > 1) dZ[(r0 + 1)*n + s] = gy1;
-				if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
+				if (dZ) {
+					dZ[(r0 + 0)*n + s] = gy0;
+					if (outDim > 1) dZ[(r0 + 1)*n + s] = gy1;
+					if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
+				}
 			}
 #pragma unroll
 			for (int k = 0; k < H; k++) {
@@ -199,7 +201,7 @@ sirenBackwardChain(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				float sn, cs;
 				__sincosf(6.283185307179586f*t, &sn, &cs);
 				g[j] = g[j]*w0*cs;
-				if (live) { dZ[((size_t)l*H + j)*n + s] = g[j]; A[((size_t)l*H + j)*n + s] = sn; }
+				if (live && dZ) { dZ[((size_t)l*H + j)*n + s] = g[j]; A[((size_t)l*H + j)*n + s] = sn; }
 			}
 			if (l == 0) break;
 			__syncthreads();
@@ -392,9 +394,11 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 			}
 			if (g == 0) { // rows (L+1)*H .. of dZ: the (envelope-scaled) output gradient, for dW_last = gy'^T A_L^T
 				const size_t r0 = (size_t)(nHidden + 1)*H;
-				dZ[(r0 + 0)*n + s] = gy0;
-				if (outDim > 1) dZ[(r0 + 1)*n + s] = gy1;
-				if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
+				if (dZ) {
+					dZ[(r0 + 0)*n + s] = gy0;
+					if (outDim > 1) dZ[(r0 + 1)*n + s] = gy1;
+					if (outDim > 2) dZ[(r0 + 2)*n + s] = gy2;
+				}
 			}
 		}
 		auto stageAsync = [&](int l, float* dst) {
@@ -425,7 +429,7 @@ sirenBackwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float 
 				float sn, cs;
 				__sincosf(6.283185307179586f*t, &sn, &cs);
 				g16[i] = g16[i]*w0*cs;
-				if (live) { dZ[((size_t)l*H + n0 + i)*n + s] = g16[i]; A[((size_t)l*H + n0 + i)*n + s] = sn; }
+				if (live && dZ) { dZ[((size_t)l*H + n0 + i)*n + s] = g16[i]; A[((size_t)l*H + n0 + i)*n + s] = sn; }
 				exw[(n0 + i)*kTS] = g16[i];
 			}
 			if (l == 0) break;
@@ -714,7 +718,7 @@ extern "C" int nmc_siren_backward(const nmc_siren_shape* sh, const float* const*
 	Env env;
 	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
 	if (n <= 0) return 0;
-	if (!x || !z_saved || !grad_y || !dZ || !A) return fail("null buffer");
+	if (!x || !z_saved || !grad_y || (!dZ) != (!A) || (!dZ && !grad_x)) return fail("null buffer");
 	const int H = sh->hidden;
 	cudaStream_t st = (cudaStream_t)stream;
 	cudaError_t e;

@@ -165,7 +165,10 @@ class _SirenFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             if need_grad:
                 z = torch.empty(((sh.n_hidden_layers + 1)*sh.hidden, n), device=x.device, dtype=torch.float32)
-                _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, _stream()))
+                if tensor_cores and n >= 16384 and sh.n_hidden_layers >= 1:
+                    _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, _stream()))
+                else:
+                    _check(L.nmc_siren_forward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, _stream()))
                 ctx.save_for_backward(x2, z, *W, *b)
             elif tensor_cores and n >= 16384:  # smaller batches: the split fp32 kernel beats the per-tile latency of the tcgen05 one
                 _check(L.nmc_siren_forward_tc(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, y.data_ptr(), None, env, _stream()))
@@ -183,9 +186,12 @@ class _SirenFn(torch.autograd.Function):
         n = x2.shape[0]
         gy2 = gy.reshape(n, sh.out_dim).contiguous().float()
         gx = torch.empty_like(x2) if ctx.x_needs else None
-        dZ, A = _backward_chain(sh, W, b, x2, n, z, gy2, gx, ctx.env)
+        need_params = any(ctx.needs_input_grad[5:])  # False e.g. for the divergence of a frozen network: only dL/dx is wanted
+        if not need_params and gx is None:
+            return (None,)*(5 + 2*ctx.n_layers)
+        dZ, A = _backward_chain(sh, W, b, x2, n, z, gy2, gx, ctx.env, need_params)
         gxr = gx.reshape(*ctx.lead, sh.in_dim) if gx is not None else None
-        if not any(ctx.needs_input_grad[5:]):  # e.g. the divergence of a frozen network: only dL/dx is wanted
+        if not need_params:
             return (gxr, None, None, None, None) + (None,)*(2*ctx.n_layers)
         gW0, gb0, gWh, gbh, gWl, gbl = _param_grads(sh, x2, n, dZ, A)
         gW = [gW0] + list(gWh.unbind(0)) + [gWl]
@@ -193,14 +199,18 @@ class _SirenFn(torch.autograd.Function):
         return (gxr, None, None, None, None, *gW, *gb)
 
 
-def _backward_chain(sh, W, b, x2, n, z, gy2, gx, env):
-    """One kernel: per-layer deltas dZ and activations A (csrc/siren.cu sirenBackwardChain)."""
+def _backward_chain(sh, W, b, x2, n, z, gy2, gx, env, need_params=True):
+    """One kernel: per-layer deltas dZ and activations A (csrc/siren.cu sirenBackwardChain / sirenBackwardSplit).
+    need_params=False: only dL/dx is produced (no dZ / A buffers: 2 * (L+1) * H * n floats not written)."""
     rows = (sh.n_hidden_layers + 1)*sh.hidden
-    dZ = torch.empty((rows + sh.out_dim, n), device=x2.device, dtype=torch.float32)
-    A = torch.empty((rows, n), device=x2.device, dtype=torch.float32)
+    dZ = A = None
+    if need_params:
+        dZ = torch.empty((rows + sh.out_dim, n), device=x2.device, dtype=torch.float32)
+        A = torch.empty((rows, n), device=x2.device, dtype=torch.float32)
     with torch.cuda.device(x2.device):
         _check(_lib().nmc_siren_backward(C.byref(sh), _ptrs(W), _ptrs(b), x2.data_ptr(), n, z.data_ptr(), gy2.data_ptr(),
-                                         dZ.data_ptr(), A.data_ptr(), gx.data_ptr() if gx is not None else None, env, _stream()))
+                                         dZ.data_ptr() if need_params else None, A.data_ptr() if need_params else None,
+                                         gx.data_ptr() if gx is not None else None, env, _stream()))
     return dZ, A
 
 
