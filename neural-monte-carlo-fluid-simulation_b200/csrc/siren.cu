@@ -34,15 +34,6 @@ __device__ __forceinline__ float sinReduced(float x) {
 	return __sinf(6.283185307179586f*t);
 #endif
 }
-__device__ __forceinline__ float cosReduced(float x) {
-#ifdef NMC_SIREN_LIBM_SIN
-	return cosf(x);
-#else
-	float t = x*0.15915494309189535f;
-	t -= rintf(t);
-	return __cosf(6.283185307179586f*t);
-#endif
-}
 
 constexpr int kTile = 128;     // samples per CTA tile == threads per CTA
 constexpr int kMaxLayers = 18; // first + hidden + last
@@ -127,10 +118,6 @@ sirenForward(Params P, Env env, int inDim, int outDim, int nHidden, float w0, co
 	}
 }
 
-__device__ __forceinline__ float warpSum(float v) {
-	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-	return v;
-}
 
 // Backward, stage 1 ("delta chain"): per sample, back-propagates dL/dy through the layers and writes
 //   dZ[l][j][s] = dL/dz_l  (l = 0..L)   and   A[l][j][s] = sin(w0 z_l)  (l = 0..L)

@@ -34,15 +34,6 @@ __device__ __forceinline__ float sinReduced(float x) {
 	return __sinf(6.283185307179586f*t);
 #endif
 }
-__device__ __forceinline__ float cosReduced(float x) {
-#ifdef NMC_SIREN_LIBM_SIN
-	return cosf(x);
-#else
-	float t = x*0.15915494309189535f;
-	t -= rintf(t);
-	return __cosf(6.283185307179586f*t);
-#endif
-}
 
 constexpr int kTile = 128;
 constexpr int kMaxLayers = 18;
