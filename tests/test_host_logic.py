@@ -284,3 +284,35 @@ def test_compiled_drop_in_module_surface_and_errors(dim):
     import sys
     r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "bindings_check.py"), str(dim), "cpu"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "BINDINGS_OK cpu dim=%d" % dim in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_ctypes_structs_match_the_c_headers(tmp_path):
+    """Every ctypes.Structure the Python layer passes across the C ABI has the size and field offsets the compiler gives
+    the corresponding struct in include/*.h (a field added on one side only would silently shift the arguments)."""
+    import ctypes as C
+    import subprocess
+    torch = pytest.importorskip("torch")  # noqa: F841  (siren.py imports it)
+    pkg = util.package()
+    S = pkg.load_siren()
+    pairs = [("nmcfs.h", "nmc_scene_opts", pkg.capi.SceneOpts), ("nmcfs.h", "nmc_solver_opts", pkg.capi.SolverOpts),
+             ("nmcfs.h", "nmc_solve_stats", pkg.capi.SolveStats), ("nmcfs_siren.h", "nmc_siren_shape", S.Shape),
+             ("nmcfs_siren.h", "nmc_siren_envelope", S.Envelope)]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "nmcfs.h"', '#include "nmcfs_siren.h"', '#include "nmcfs_fields.h"', 'int main(void) {']
+    for _, cname, cls in pairs:
+        src.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _t in cls._fields_:
+            src.append('printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        src.append('printf("\\n");')
+    src.append('return 0; }')
+    cfile = tmp_path/"layout.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path/"layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(util.ROOT, "include"), str(cfile), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    assert len(out) == len(pairs)
+    for line, (_, cname, cls) in zip(out, pairs):
+        t = line.split()
+        assert t[0] == cname
+        assert int(t[1]) == C.sizeof(cls), "%s: sizeof %s in C, %d in ctypes" % (cname, t[1], C.sizeof(cls))
+        for off, (fname, _t) in zip(t[2:], cls._fields_):
+            assert int(off) == getattr(cls, fname).offset, "%s.%s: offset %s in C, %d in ctypes" % (cname, fname, off, getattr(cls, fname).offset)
