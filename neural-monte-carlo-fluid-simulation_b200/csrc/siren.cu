@@ -340,7 +340,7 @@ sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w
 				if (outDim > 2) y[s*outDim + 2] = yo[2];
 			}
 		}
-		// the next tile writes act[0] (read last before the barrier above) and `part` only after two more barriers
+		__syncthreads(); // `part` (and, without hidden layers, act[0]) is rewritten by the next tile
 	}
 }
 
