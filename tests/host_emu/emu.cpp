@@ -92,3 +92,44 @@ extern "C" void emu_scene_info(void* h, int* out) {
 	EmuScene* s = (EmuScene*)h;
 	out[0] = s->flat.nNodes; out[1] = s->flat.nPrims; out[2] = s->flat.nSilRefs; out[3] = s->flat.nSilU; out[4] = s->flat.nRay; out[5] = s->flat.maxDepth;
 }
+
+// default-mode flat scans (nmc_geom.cuh: flatClosestSilhouette / flatRay) on the host, with the kernel's calling
+// convention (wost_fast.cu, phase 1), next to the tree traversals they replace
+static FlatTab flatTab(EmuScene* s) {
+	FlatTab F;
+	F.silsU = (const float4*)s->flat.silsU.data(); F.grpS = (const float4*)s->flat.grpS.data(); F.nSilU = s->flat.nSilU;
+	F.rayP = (const float4*)s->flat.rayP.data(); F.rayN = (const float4*)s->flat.rayN.data(); F.grpP = (const float4*)s->flat.grpP.data(); F.nRay = s->flat.nRay;
+	return F;
+}
+extern "C" void emu_flat_star_radius(void* h, const float* pts, int n, float minR, const float* maxR, float prec, int flipOrient, float* out) {
+	EmuScene* s = (EmuScene*)h;
+	FlatTab F = flatTab(s);
+	for (int i = 0; i < n; i++) {
+		const int D = s->v.dim;
+		V3 pt = mk(pts[D*i], pts[D*i + 1], D == 3 ? pts[D*i + 2] : 0.0f);
+		float dd = maxR[i], starR = dd;
+		if (minR <= dd) {
+			float dsil = 0.0f, r2max = dd < kMaxF ? dd*dd : kMaxF;
+			bool f = D == 2 ? flatClosestSilhouette<2>(F, pt, r2max, flipOrient == 0, minR*minR, prec, dsil)
+							: flatClosestSilhouette<3>(F, pt, r2max, flipOrient == 0, minR*minR, prec, dsil);
+			starR = f ? fmaxf(dsil, minR) : fmaxf(dd, minR);
+		}
+		out[i] = starR;
+	}
+}
+// out per ray: hit, distance, normal.xyz  (both variants)
+extern "C" void emu_rays(void* h, const float* o, const float* d, const float* tmax, int n, float* outFlat, float* outTree) {
+	EmuScene* s = (EmuScene*)h;
+	FlatTab F = flatTab(s);
+	const int D = s->v.dim;
+	for (int i = 0; i < n; i++) {
+		V3 ro = mk(o[D*i], o[D*i + 1], D == 3 ? o[D*i + 2] : 0.0f), dir = mk(d[D*i], d[D*i + 1], D == 3 ? d[D*i + 2] : 0.0f);
+		Hit a; a.d = kMaxF; a.p = mk(0, 0, 0); a.n = mk(0, 0, 0);
+		Hit b = a;
+		bool ha = D == 2 ? flatRay<2>(F, ro, dir, tmax[i], a) : flatRay<3>(F, ro, dir, tmax[i], a);
+		bool hb = D == 2 ? intersectNeumann<2>(s->v, ro, mk(0, 0, 0), dir, tmax[i], false, b) : intersectNeumann<3>(s->v, ro, mk(0, 0, 0), dir, tmax[i], false, b);
+		float* x = outFlat + 5*i; float* y = outTree + 5*i;
+		x[0] = ha; x[1] = ha ? a.d : 0.0f; x[2] = ha ? a.n.x : 0.0f; x[3] = ha ? a.n.y : 0.0f; x[4] = ha ? a.n.z : 0.0f;
+		y[0] = hb; y[1] = hb ? b.d : 0.0f; y[2] = hb ? b.n.x : 0.0f; y[3] = hb ? b.n.y : 0.0f; y[4] = hb ? b.n.z : 0.0f;
+	}
+}

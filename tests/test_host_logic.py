@@ -316,3 +316,46 @@ def test_ctypes_structs_match_the_c_headers(tmp_path):
         assert int(t[1]) == C.sizeof(cls), "%s: sizeof %s in C, %d in ctypes" % (cname, t[1], C.sizeof(cls))
         for off, (fname, _t) in zip(t[2:], cls._fields_):
             assert int(off) == getattr(cls, fname).offset, "%s.%s: offset %s in C, %d in ctypes" % (cname, fname, off, getattr(cls, fname).offset)
+
+
+@pytest.mark.parametrize("case", ["taylorgreen_active", "karman", "smoke3d", "karman3d"])
+def test_default_mode_flat_scans_equal_the_tree_queries(emu, oracle_lib, case):
+    """The default mode's geometry for small scenes (two-stage silhouette scan on face-plane distances, slab-culled
+    ray scan over merged segments; nmc_geom.cuh) compiled for the host: same star radii as the reference's
+    closest-silhouette query (oracle) and the same closest hits as the tree traversal, on random queries."""
+    cfg = util.load_case(case)
+    dim = cfg["dim"]
+    h, src = _emu_scene(emu, oracle_lib, cfg)
+    osc = oracle_lib.OracleScene(dim, cfg["scene"], src)
+    lo, hi = osc.bbox()
+    rng = np.random.default_rng(31)
+    q = util.random_points(lo, hi, 6000, seed=17, margin=0.02)
+    dd = osc.dist_dirichlet(q)
+    for flip in (0, 1):
+        want = osc.star_radius(q, 1e-3, dd, 1e-3, bool(flip))
+        got = np.zeros(len(q), np.float32)
+        emu.emu_flat_star_radius(h, _fp(q), len(q), C.c_float(1e-3), _fp(dd), C.c_float(1e-3), flip, _fp(got))
+        rel = np.abs(got - want)/np.maximum(np.abs(want), 1e-6)
+        # the flat scan measures |x - p| with its own rounding and decides near-perpendicular views from plane
+        # distances: a different silhouette may win only inside the precision band
+        assert (rel < 1e-5).mean() > 0.998, (case, flip, (rel < 1e-5).mean(), rel.max())
+        assert (rel < 1e-5).mean() == 1.0 or np.sort(rel)[-max(1, len(q)//500)] < 0.5
+    # rays from the same points in random directions, bounded by the star radius like a walk step
+    u = rng.random((len(q), dim - 1), dtype=np.float32)
+    if dim == 2:
+        ang = 2*np.pi*u[:, 0]
+        d = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)
+    else:
+        z = 1 - 2*u[:, 0]; r = np.sqrt(np.maximum(0, 1 - z*z)); ang = 2*np.pi*u[:, 1]
+        d = np.stack([r*np.cos(ang), r*np.sin(ang), z], 1).astype(np.float32)
+    tmax = (osc.star_radius(q, 1e-3, dd, 1e-3, False)*np.float32(0.99)).astype(np.float32)
+    tmax[::3] = np.float32((hi - lo).max()*2)   # and some unbounded ones
+    a = np.zeros((len(q), 5), np.float32); b = np.zeros((len(q), 5), np.float32)
+    emu.emu_rays(h, _fp(q), _fp(d), _fp(tmax), len(q), _fp(a), _fp(b))
+    same_hit = a[:, 0] == b[:, 0]
+    assert same_hit.mean() > 0.9995, (case, same_hit.mean())        # grazing rays may flip at the last ulp
+    both = (a[:, 0] > 0) & (b[:, 0] > 0)
+    assert both.sum() > 500
+    assert np.abs(a[both, 1] - b[both, 1]).max() <= 2e-5*np.abs(b[both, 1]).max() + 1e-6
+    assert (np.abs(a[both, 2:] - b[both, 2:]).max(axis=1) < 1e-5).mean() > 0.999   # same face normal
+    emu.emu_scene_destroy(h); osc.close()
