@@ -56,8 +56,8 @@ def load_obj(path, dim, flip_orientation=False):
                     i = int(tok.split("/")[0])
                     prims.append(i - 1 if i > 0 else len(verts) + i)
     v = np.asarray(verts, np.float32).reshape(-1, dim)
-    p = np.asarray(prims, np.int32)
-    p = p[: (len(p) // dim) * dim].reshape(-1, dim)
+    p = np.asarray(prims, np.int32).reshape(-1)       # 2D rows are pairs already, 3D indices arrive one by one
+    p = p[: (len(p) // dim) * dim].reshape(-1, dim)   # a trailing incomplete face is dropped
     return v, p
 
 

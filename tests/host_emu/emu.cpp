@@ -133,3 +133,12 @@ extern "C" void emu_rays(void* h, const float* o, const float* d, const float* t
 		y[0] = hb; y[1] = hb ? b.d : 0.0f; y[2] = hb ? b.n.x : 0.0f; y[3] = hb ? b.n.y : 0.0f; y[4] = hb ? b.n.z : 0.0f;
 	}
 }
+
+extern "C" void emu_dist_neumann(void* h, const float* pts, int n, int signedDist, float* out) {
+	EmuScene* s = (EmuScene*)h;
+	const int D = s->v.dim;
+	for (int i = 0; i < n; i++) {
+		V3 x = mk(pts[D*i], pts[D*i + 1], D == 3 ? pts[D*i + 2] : 0.0f);
+		out[i] = D == 2 ? distNeumann<2>(s->v, x, signedDist != 0) : distNeumann<3>(s->v, x, signedDist != 0);
+	}
+}

@@ -314,3 +314,41 @@ def test_compiled_drop_in_module_on_the_gpu(dim):
     import sys
     r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "bindings_check.py"), str(dim), "gpu"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "BINDINGS_OK gpu dim=%d" % dim in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_random_meshes_against_the_oracle(pkg, oracle_lib, tmp_path):
+    """Beyond the fixtures: seeded random polygons / perturbed icospheres (closed and open, both orientations,
+    double-sided; the oracle is pinned bit-for-bit to the reference on the same meshes by the CPU suite).
+    Device queries bit-exact, deterministic estimator at the 1e-5 bar, default mode statistically."""
+    c = pkg.capi
+    for name, dim, cfg in util.random_meshes(tmp_path):
+        src = util.source_grid(dim)
+        sc = pkg.Scene(cfg["scene"], src, device=0)
+        osc = oracle_lib.OracleScene(dim, cfg["scene"], src)
+        h = sc.handle
+        lo, hi = osc.bbox()
+        q = util.random_points(lo, hi, 2000, seed=5, margin=0.1); n = len(q)
+        for kind, sg in ((c.PROBE_DIST_NEUMANN, False), (c.PROBE_SIGNED_DIST_NEUMANN, True)):
+            got, want = h.probe(kind, n, q), osc.dist_neumann(q, sg)
+            eq = _bits_equal(got, want)
+            rel = np.abs(got - want)/np.maximum(np.abs(want), 1e-30)
+            print("%s %s distance: %d of %d differ in bits, max relative difference %.2e" % (name, "signed" if sg else "unsigned", int((~eq).sum()), n, rel.max()))
+            assert eq.mean() >= 0.995 and rel.max() <= 5e-7, (name, sg, int((~eq).sum()), rel.max())
+        assert np.array_equal(h.probe(c.PROBE_INSIDE_DOMAIN, n, q) > 0, osc.inside_domain(q) > 0), name
+        dd = osc.dist_dirichlet(q)
+        for flip in (0.0, 1.0):
+            s = h.probe(c.PROBE_STAR_RADIUS, n, q, aux0=dd, params=[1e-3, 1e-3, flip])
+            assert _bits_equal(s, osc.star_radius(q, 1e-3, dd, 1e-3, bool(flip))).mean() >= 0.999, (name, flip)
+        pts = util.random_points(lo, hi, 96, seed=11)
+        op, og, ost = osc.wost(cfg["solver"], cfg["output"], pts, seed=3, nthreads=8, want_stats=True)
+        p, g, st12, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=c.MODE_DETERMINISTIC, seed=3, want_stats=True)
+        assert (st12[:, 9] == ost[:, 9]).mean() >= 0.98, name
+        assert util.close_mask(p, op).mean() >= 0.98 and util.close_mask(g, og).mean() >= 0.98, name
+        pf, gf, s, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=c.MODE_FAST, seed=99, want_stats=True)
+        both = (ost[:, 11] > 0) & (s[:, 11] > 0)
+        if both.sum() < 16:
+            continue
+        nf, nr = np.maximum(s[both, 9], 1), np.maximum(ost[both, 9], 1)
+        assert abs(nf.mean() - nr.mean()) < 0.05*500, (name, nf.mean(), nr.mean())
+        z = (s[both, 0] - ost[both, 0])/np.sqrt(s[both, 1]/nf + ost[both, 1]/nr + 1e-30)
+        assert (np.abs(z) < 3.5).mean() >= 0.94 and abs(z.mean()) < 0.6, (name, (np.abs(z) < 3.5).mean(), z.mean())

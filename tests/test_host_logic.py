@@ -359,3 +359,18 @@ def test_default_mode_flat_scans_equal_the_tree_queries(emu, oracle_lib, case):
     assert np.abs(a[both, 1] - b[both, 1]).max() <= 2e-5*np.abs(b[both, 1]).max() + 1e-6
     assert (np.abs(a[both, 2:] - b[both, 2:]).max(axis=1) < 1e-5).mean() > 0.999   # same face normal
     emu.emu_scene_destroy(h); osc.close()
+
+
+def test_obj_loader_keeps_every_segment(tmp_path):
+    """Regression: the Python mirror's OBJ loader dropped the last segment of 2D meshes with an odd segment count."""
+    pkg = util.package()
+    for n in (3, 4, 7):
+        path = tmp_path/("poly%d.obj" % n)
+        lines = ["v %d %d 0" % (i, i*i) for i in range(n)] + ["l %d %d" % (i + 1, (i + 1) % n + 1) for i in range(n)]
+        path.write_text("\n".join(lines) + "\n")
+        v, p = pkg.zombie.load_obj(str(path), 2)
+        assert v.shape == (n, 2) and p.shape == (n, 2) and p[-1].tolist() == [n - 1, 0]
+    path = tmp_path/"tri.obj"
+    path.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nf 1 2 3\nf 1/1/1 3/2/2 4/3/3\nf -1 -2 -3\n")
+    v, p = pkg.zombie.load_obj(str(path), 3)
+    assert p.tolist() == [[0, 1, 2], [0, 2, 3], [3, 2, 1]]

@@ -131,3 +131,32 @@ def test_oracle_option_variants_against_reference_vectors(oracle_lib, case):
         p, g, st = sc.wost(cfg["solver"], cfg["output"], k[key + "/pts"], seed=9, nthreads=4, want_stats=True)
         assert np.array_equal(p, k[key + "/p"]) and np.array_equal(g, k[key + "/g"]), key
         assert np.array_equal(st, k[key + "/stats"]), key
+
+
+def test_oracle_against_live_reference_on_random_meshes(oracle_lib, tmp_path):
+    """Pins the C restatement beyond the fixtures: on seeded random polygons / perturbed icospheres (closed and open,
+    both orientations, double-sided) every query and the full estimator are bit-identical to the reference's own
+    headers (oracle/_ref).  Skipped where the reference build does not exist."""
+    from oracle import refbind
+    if not (refbind.available(2) and refbind.available(3)):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(3)
+    for name, dim, cfg in util.random_meshes(tmp_path):
+        src = util.source_grid(dim)
+        r = refbind.RefScene(dim, cfg["scene"], src); o = oracle_lib.OracleScene(dim, cfg["scene"], src)
+        lo, hi = r.bbox()
+        q = util.random_points(lo, hi, 2000, seed=5, margin=0.1)
+        assert np.array_equal(r.dist_neumann(q), o.dist_neumann(q)), name
+        assert np.array_equal(r.dist_neumann(q, True), o.dist_neumann(q, True)), name
+        assert np.array_equal(r.inside_domain(q), o.inside_domain(q)), name
+        dd = r.dist_dirichlet(q)
+        for flip in (False, True):
+            assert np.array_equal(r.star_radius(q, 1e-3, dd, 1e-3, flip), o.star_radius(q, 1e-3, dd, 1e-3, flip)), (name, flip)
+        dirs = refbind.sphere_dir(dim, rng.random((len(q), dim - 1), dtype=np.float32))
+        tmax = (rng.random(len(q), dtype=np.float32)*(hi - lo).max()).astype(np.float32)
+        assert np.array_equal(r.intersect_neumann(q, np.zeros_like(q), dirs, tmax, 0), o.intersect_neumann(q, np.zeros_like(q), dirs, tmax, 0)), name
+        pts = util.random_points(lo, hi, 32, seed=11)
+        a = r.wost(cfg["solver"], cfg["output"], pts, seed=3, index_offset=0, nthreads=8, want_stats=True)
+        b = o.wost(cfg["solver"], cfg["output"], pts, seed=3, index_offset=0, nthreads=8, want_stats=True)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), name
+        r.close(); o.close()

@@ -99,3 +99,39 @@ def load_variant(case, variant):
     so, sv = OPTION_VARIANTS[variant]
     cfg["scene"].update(so); cfg["solver"].update(sv)
     return cfg
+
+
+def random_meshes(tmpdir):
+    """Seeded random boundaries beyond the fixtures: star-shaped polygons (closed / open chains, both orientations,
+    double-sided) and perturbed icospheres (both orientations, with holes).  Yields (name, dim, cfg)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mss", os.path.join(GOLDEN, "make_synthetic_scenes.py"))
+    mss = importlib.util.module_from_spec(spec); spec.loader.exec_module(mss)
+    rng = np.random.default_rng(7)
+    out = []
+    for k in range(4):
+        n = int(rng.integers(5, 60))
+        th = np.sort(rng.random(n))*2*np.pi
+        rad = 0.5 + 0.25*rng.random(n)
+        v = np.stack([rad*np.cos(th), rad*np.sin(th)], 1)
+        e = np.stack([np.arange(n), (np.arange(n) + 1) % n], 1)
+        if k % 2:
+            e = e[:, ::-1]
+        if k >= 2:
+            e = e[:-2]
+        out.append(("poly%d" % k, 2, v, e, {"isWatertight": k < 2, "isDoubleSided": k == 3}))
+    for k in range(3):
+        sv, sf = mss.icosphere(1 + (k % 2))
+        sv = sv*(0.6 + 0.15*rng.random((len(sv), 1)))
+        if k == 1:
+            sf = sf[:, ::-1]
+        if k == 2:
+            sf = sf[:-7]
+        out.append(("ico%d" % k, 3, sv, sf, {"isWatertight": k < 2, "isDoubleSided": k == 2}))
+    for name, dim, v, e, over in out:
+        obj = os.path.join(str(tmpdir), name + ".obj")
+        mss.write_obj(obj, name, v, e, "l" if dim == 2 else "f")
+        cfg = load_case("karman" if dim == 2 else "smoke3d")
+        cfg["scene"]["boundary"] = obj
+        cfg["scene"].update(over)
+        yield name, dim, cfg
