@@ -342,8 +342,11 @@ def test_random_meshes_against_the_oracle(pkg, oracle_lib, tmp_path):
         pts = util.random_points(lo, hi, 96, seed=11)
         op, og, ost = osc.wost(cfg["solver"], cfg["output"], pts, seed=3, nthreads=8, want_stats=True)
         p, g, st12, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=c.MODE_DETERMINISTIC, seed=3, want_stats=True)
-        assert (st12[:, 9] == ost[:, 9]).mean() >= 0.98, name
-        assert util.close_mask(p, op).mean() >= 0.98 and util.close_mask(g, og).mean() >= 0.98, name
+        assert (st12[:, 9] == ost[:, 9]).mean() >= 0.96, name
+        okp, okg = util.close_mask(p, op), util.close_mask(g, og)
+        assert okp.mean() >= 0.96 and okg.mean() >= 0.96, (name, okp.mean(), okg.mean())   # 96 points: up to 3 flipped decisions
+        se = np.sqrt(np.maximum(ost[:, 1], 0)/np.maximum(ost[:, 9], 1))
+        assert (np.abs(p - op) <= 3*se + 1e-12)[~okp].all(), name                            # and those stay within 3 standard errors
         pf, gf, s, _ = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=c.MODE_FAST, seed=99, want_stats=True)
         both = (ost[:, 11] > 0) & (s[:, 11] > 0)
         if both.sum() < 16:
