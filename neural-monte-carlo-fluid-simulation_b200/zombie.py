@@ -61,6 +61,22 @@ def load_obj(path, dim, flip_orientation=False):
     return v, p
 
 
+def normalize_domain(v):
+    """scene.h:132-142 with the reference's float arithmetic: the centre of mass is accumulated vertex by vertex
+    (numpy's pairwise sum would round differently), the radius is the largest sqrt(x*x + y*y), then a true division."""
+    f = np.float32
+    cx, cy = f(0), f(0)
+    for x, y in v:
+        cx = f(cx + x); cy = f(cy + y)
+    n = f(len(v))
+    cm = np.array([f(cx/n), f(cy/n)], f)
+    w = (v - cm).astype(f)
+    radius = f(0)
+    for x, y in w:
+        radius = max(radius, f(np.sqrt(f(f(x*x) + f(y*y)))))
+    return (w/radius).astype(f)
+
+
 def solver_opts(solver, output, mode=None, seed=None):
     """demo.cpp:121-137 (both dimensions): defaults and the misspelt `setps...` keys are API."""
     o = capi.SolverOpts()
@@ -107,11 +123,8 @@ class Scene:
         self.isDoubleSided = bool(config.get("isDoubleSided", False))
         flip = bool(config.get("flipOrientation", False)) if self.dim == 2 else False  # 3D ignores both flags
         v, p = load_obj(boundary, self.dim, flip)
-        if self.dim == 2 and config.get("normalizeDomain", False):  # scene.h:132-142
-            cm = v.sum(axis=0, dtype=np.float32)/np.float32(len(v))
-            v = (v - cm).astype(np.float32)
-            radius = np.float32(np.sqrt((v*v).sum(axis=1, dtype=np.float32)).max())
-            v = (v/radius).astype(np.float32)
+        if self.dim == 2 and config.get("normalizeDomain", False):
+            v = normalize_domain(v)
         dev = _DEFAULTS["device"] if device is None else device
         if dev is None:
             dev = int(os.environ.get("LOCAL_RANK", "0")) if capi.device_count() > 1 else 0

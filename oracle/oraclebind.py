@@ -123,9 +123,15 @@ class OracleScene:
         flip = bool(config.get("flipOrientation", False)) if dim == 2 else False
         v, p = load_obj(config["boundary"], dim, flip)
         if dim == 2 and config.get("normalizeDomain", False):  # scene.h:132-142
-            cm = v.sum(axis=0, dtype=_f32) / _f32(len(v))
+            # the reference accumulates the centre of mass vertex by vertex in float and divides by the largest norm
+            cx, cy = _f32(0), _f32(0)
+            for x, y in v:
+                cx = _f32(cx + x); cy = _f32(cy + y)
+            cm = np.array([_f32(cx / _f32(len(v))), _f32(cy / _f32(len(v)))], _f32)
             v = (v - cm).astype(_f32)
-            radius = _f32(np.sqrt((v.astype(_f32) ** 2).sum(axis=1, dtype=_f32)).max())
+            radius = _f32(0)
+            for x, y in v:
+                radius = max(radius, _f32(np.sqrt(_f32(_f32(x * x) + _f32(y * y)))))
             v = (v / radius).astype(_f32)
         self.verts, self.prims = np.ascontiguousarray(v), np.ascontiguousarray(p)
         src = np.ascontiguousarray(source, dtype=_f32)

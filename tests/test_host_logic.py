@@ -374,3 +374,30 @@ def test_obj_loader_keeps_every_segment(tmp_path):
     path.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nf 1 2 3\nf 1/1/1 3/2/2 4/3/3\nf -1 -2 -3\n")
     v, p = pkg.zombie.load_obj(str(path), 3)
     assert p.tolist() == [[0, 1, 2], [0, 2, 3], [3, 2, 1]]
+
+
+def test_normalize_domain_arithmetic(tmp_path):
+    """normalizeDomain (scene.h:132-142): sequential float accumulation of the centre of mass, largest norm, true
+    division -- the Python mirror must round exactly like the compiled loaders (C arithmetic below = the reference's)."""
+    import subprocess
+    pkg = util.package()
+    rng = np.random.default_rng(1)
+    v = (rng.random((257, 2))*3 - 1).astype(np.float32)
+    src = r"""
+#include <stdio.h>
+#include <math.h>
+int main(void) { int n; if (scanf("%d", &n) != 1) return 1; static float x[4096], y[4096];
+  for (int i = 0; i < n; i++) if (scanf("%f %f", &x[i], &y[i]) != 2) return 1;
+  float cx = 0, cy = 0; for (int i = 0; i < n; i++) { cx += x[i]; cy += y[i]; } cx /= n; cy /= n;
+  float r = 0; for (int i = 0; i < n; i++) { x[i] -= cx; y[i] -= cy; float d = sqrtf(x[i]*x[i] + y[i]*y[i]); if (d > r) r = d; }
+  for (int i = 0; i < n; i++) printf("%.9g %.9g\n", x[i]/r, y[i]/r); return 0; }
+"""
+    cfile = tmp_path/"norm.c"; cfile.write_text(src)
+    exe = tmp_path/"norm"
+    subprocess.check_call(["gcc", "-O0", "-ffp-contract=off", str(cfile), "-o", str(exe), "-lm"])
+    inp = "%d\n" % len(v) + "\n".join("%.9g %.9g" % (a, b) for a, b in v) + "\n"
+    out = subprocess.run([str(exe)], input=inp, capture_output=True, text=True, check=True).stdout
+    want = np.array([[float(t) for t in line.split()] for line in out.strip().splitlines()], np.float32)
+    got = pkg.zombie.normalize_domain(v.copy())
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.abs(np.sqrt((got.astype(np.float64)**2).sum(1)).max() - 1.0) < 1e-6
