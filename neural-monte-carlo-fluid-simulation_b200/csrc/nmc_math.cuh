@@ -148,6 +148,27 @@ NMC_HD uint64_t pointSeed(uint64_t seed, uint64_t index) {
 	return splitmix64(seed + 0x9E3779B97F4A7C15ull*(index + 1ull));
 }
 
+// Keyed bijection on [0, n): multiply/xorshift rounds on the enclosing power of two with cycle walking.
+NMC_HD unsigned permute(unsigned i, unsigned n, unsigned key) {
+	unsigned w = n - 1;
+	w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+	do {
+		i ^= key; i *= 0xe170893du;
+		i ^= key >> 16;
+		i ^= (i & w) >> 4;
+		i ^= key >> 8; i *= 0x0929eb3fu;
+		i ^= key >> 23;
+		i ^= (i & w) >> 1; i *= 1u | key >> 27;
+		i *= 0x6935fa69u;
+		i ^= (i & w) >> 11; i *= 0x74dcb303u;
+		i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+		i ^= (i & w) >> 2; i *= 0xc860a3dfu;
+		i &= w;
+		i ^= i >> 5;
+	} while (i >= n);
+	return i;
+}
+
 // sampleUnitSphereUniform<DIM>(float* u)  (reference: include/zombie/core/sampling.h:29-45)
 template <int DIM, class M>
 NMC_HD V3 sphereDir(float u0, float u1) {

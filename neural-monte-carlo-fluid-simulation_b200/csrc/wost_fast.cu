@@ -34,27 +34,6 @@ static constexpr int kBlock = 128;
 static constexpr int kWarps = kBlock/32;
 static constexpr unsigned kFull = 0xffffffffu;
 
-// Keyed bijection on [0, n): multiply/xorshift rounds on the enclosing power of two with cycle walking.
-__device__ __forceinline__ unsigned permute(unsigned i, unsigned n, unsigned key) {
-	unsigned w = n - 1;
-	w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
-	do {
-		i ^= key; i *= 0xe170893du;
-		i ^= key >> 16;
-		i ^= (i & w) >> 4;
-		i ^= key >> 8; i *= 0x0929eb3fu;
-		i ^= key >> 23;
-		i ^= (i & w) >> 1; i *= 1u | key >> 27;
-		i *= 0x6935fa69u;
-		i ^= (i & w) >> 11; i *= 0x74dcb303u;
-		i ^= (i & w) >> 2; i *= 0x9e501cc3u;
-		i ^= (i & w) >> 2; i *= 0xc860a3dfu;
-		i &= w;
-		i ^= i >> 5;
-	} while (i >= n);
-	return i;
-}
-
 __device__ __forceinline__ float warpSum(float v) {
 	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
 	return v;

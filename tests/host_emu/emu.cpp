@@ -142,3 +142,6 @@ extern "C" void emu_dist_neumann(void* h, const float* pts, int n, int signedDis
 		out[i] = D == 2 ? distNeumann<2>(s->v, x, signedDist != 0) : distNeumann<3>(s->v, x, signedDist != 0);
 	}
 }
+
+// keyed permutation of the default mode's Latin-hypercube strata (nmc_math.cuh: permute)
+extern "C" void emu_permute(unsigned n, unsigned key, unsigned* out) { for (unsigned i = 0; i < n; i++) out[i] = permute(i, n, key); }

@@ -401,3 +401,23 @@ int main(void) { int n; if (scanf("%d", &n) != 1) return 1; static float x[4096]
     got = pkg.zombie.normalize_domain(v.copy())
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(np.sqrt((got.astype(np.float64)**2).sum(1)).max() - 1.0) < 1e-6
+
+
+def test_stratum_permutation_is_a_bijection(emu):
+    """The default mode draws its Latin-hypercube strata through a keyed permutation of [0, n) instead of the
+    reference's stored shuffle (sampling.h:434-457): it must hit every stratum exactly once for every n and key,
+    and different keys must give different orders."""
+    rng = np.random.default_rng(2)
+    for n in (1, 2, 3, 7, 64, 250, 500, 501, 1000, 4096, 5000):
+        seen = set()
+        for key in rng.integers(0, 2**32, 6, dtype=np.uint64):
+            out = np.zeros(n, np.uint32)
+            emu.emu_permute(C.c_uint(n), C.c_uint(int(key)), out.ctypes.data_as(C.POINTER(C.c_uint)))
+            assert np.array_equal(np.sort(out), np.arange(n, dtype=np.uint32)), (n, int(key))
+            seen.add(out.tobytes())
+        if n >= 64:
+            assert len(seen) == 6
+    # no gross structure: the permuted index is uncorrelated with the input index
+    out = np.zeros(500, np.uint32)
+    emu.emu_permute(C.c_uint(500), C.c_uint(12345), out.ctypes.data_as(C.POINTER(C.c_uint)))
+    assert abs(np.corrcoef(np.arange(500), out.astype(np.float64))[0, 1]) < 0.15
