@@ -1,0 +1,67 @@
+// tests/host_emu/emu_fast.cpp -- TEST HARNESS ONLY.  The product's geometry headers compiled for the host in the
+// DEFAULT-MODE flavour (NMC_FAST_GEOM: trig-free normal-cone test, fminf/fmaxf, reciprocal divisions, one-FMA source
+// lookup), so that the tree queries the default mode uses on meshes beyond the flat-scan limit can be checked against
+// the oracle without a GPU.
+#define NMC_FAST_GEOM 1
+#define NMC_TRAV_INLINE 1
+#include <vector>
+#include <cstring>
+#include "../../neural-monte-carlo-fluid-simulation_b200/csrc/nmc_math.cuh"
+namespace nmc { static inline int min(int a, int b) { return a < b ? a : b; } static inline int max(int a, int b) { return a > b ? a : b; } } // CUDA's integer min/max
+#include "../../neural-monte-carlo-fluid-simulation_b200/csrc/nmc_geom.cuh"
+#include "../../neural-monte-carlo-fluid-simulation_b200/csrc/scene_build.h"
+using namespace nmc;
+
+struct FastScene { FlatScene flat; SceneView v; std::vector<float> src; };
+
+extern "C" {
+void* emuf_scene_create(int dim, const float* verts, int nV, const int* prims, int nP, const float* src, int n0, int n1, int n2,
+						float absorption, int watertight, int doubleSided) {
+	FastScene* s = new FastScene();
+	buildFlatScene(dim, verts, nV, prims, nP, doubleSided != 0, s->flat);
+	size_t cnt = (size_t)n0*n1*(dim == 3 ? n2 : 1);
+	s->src.assign(src, src + cnt);
+	SceneView& v = s->v; memset(&v, 0, sizeof(v));
+	v.dim = dim; v.nNodes = s->flat.nNodes; v.nPrims = s->flat.nPrims; v.nSilRefs = s->flat.nSilRefs;
+	v.nodes = (const float4*)s->flat.nodes.data(); v.prims = (const float4*)s->flat.prims.data();
+	v.primN = (const float4*)s->flat.primN.data(); v.nrmV = (const float4*)s->flat.nrmV.data(); v.sils = (const float4*)s->flat.sils.data();
+	for (int k = 0; k < 3; k++) { v.bboxLo[k] = s->flat.bboxLo[k]; v.bboxHi[k] = s->flat.bboxHi[k]; }
+	v.src = s->src.data(); v.n0 = n0; v.n1 = n1; v.n2 = dim == 3 ? n2 : 1;
+	v.absorption = absorption; v.watertight = watertight; v.doubleSided = doubleSided;
+	// as csrc/capi.cu setSource: texel index along box axis k = (int)(x_k*srcScale[k] + srcOff[k])
+	const int nAx[3] = {dim == 2 ? n1 : n0, dim == 2 ? n0 : n1, dim == 3 ? n2 : 1};
+	for (int k = 0; k < 3; k++) {
+		float ext = v.bboxHi[k] - v.bboxLo[k];
+		v.srcScale[k] = ext > 0.0f ? (float)nAx[k]/ext : 0.0f;
+		v.srcOff[k] = -v.bboxLo[k]*v.srcScale[k];
+	}
+	return s;
+}
+void emuf_scene_destroy(void* h) { delete (FastScene*)h; }
+void emuf_star_radius(void* h, const float* pts, int n, float minR, const float* maxR, float prec, int flip, float* out) {
+	FastScene* s = (FastScene*)h;
+	for (int i = 0; i < n; i++) {
+		if (s->v.dim == 2) out[i] = starRadius<2, FastMath>(s->v, mk(pts[2*i], pts[2*i + 1], 0.0f), minR, maxR[i], prec, flip != 0);
+		else out[i] = starRadius<3, FastMath>(s->v, mk(pts[3*i], pts[3*i + 1], pts[3*i + 2]), minR, maxR[i], prec, flip != 0);
+	}
+}
+void emuf_source(void* h, const float* pts, int n, float* out) {
+	FastScene* s = (FastScene*)h;
+	const int D = s->v.dim;
+	for (int i = 0; i < n; i++) {
+		V3 x = mk(pts[D*i], pts[D*i + 1], D == 3 ? pts[D*i + 2] : 0.0f);
+		out[i] = D == 2 ? sourceAt<2>(s->v, x) : sourceAt<3>(s->v, x);
+	}
+}
+// out per ray: hit, distance
+void emuf_rays(void* h, const float* o, const float* d, const float* tmax, int n, float* out) {
+	FastScene* s = (FastScene*)h;
+	const int D = s->v.dim;
+	for (int i = 0; i < n; i++) {
+		V3 ro = mk(o[D*i], o[D*i + 1], D == 3 ? o[D*i + 2] : 0.0f), dir = mk(d[D*i], d[D*i + 1], D == 3 ? d[D*i + 2] : 0.0f);
+		Hit b; b.d = kMaxF; b.p = mk(0, 0, 0); b.n = mk(0, 0, 0);
+		bool hb = D == 2 ? intersectNeumann<2>(s->v, ro, mk(0, 0, 0), dir, tmax[i], false, b) : intersectNeumann<3>(s->v, ro, mk(0, 0, 0), dir, tmax[i], false, b);
+		out[2*i] = hb; out[2*i + 1] = hb ? b.d : 0.0f;
+	}
+}
+}

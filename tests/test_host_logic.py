@@ -421,3 +421,58 @@ def test_stratum_permutation_is_a_bijection(emu):
     out = np.zeros(500, np.uint32)
     emu.emu_permute(C.c_uint(500), C.c_uint(12345), out.ctypes.data_as(C.POINTER(C.c_uint)))
     assert abs(np.corrcoef(np.arange(500), out.astype(np.float64))[0, 1]) < 0.15
+
+
+@pytest.fixture(scope="module")
+def emu_fast():
+    d = os.path.join(util.ROOT, "tests", "host_emu")
+    so = os.path.join(d, "libnmc_emu_fast.so")
+    srcs = [os.path.join(d, "emu_fast.cpp"), os.path.join(PKG_DIR, "csrc", "scene_build.cpp")]
+    deps = srcs + [os.path.join(PKG_DIR, "csrc", f) for f in os.listdir(os.path.join(PKG_DIR, "csrc")) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so] + srcs)
+    L = C.CDLL(so)
+    L.emuf_scene_create.restype = C.c_void_p
+    return L
+
+
+def test_default_mode_tree_queries_equal_the_oracle(emu_fast, oracle_lib, tmp_path):
+    """The default-mode flavour of the geometry headers (NMC_FAST_GEOM: trig-free normal-cone culling, fminf/fmaxf,
+    one-FMA source lookup) compiled for the host: on every fixture -- including the meshes beyond the flat-scan limit,
+    where the default mode walks the tree -- and on the random meshes, star radii, source texels and closest hits
+    equal the oracle's.  (The cone test only decides what is culled: it must never drop the closest silhouette.)"""
+    rng = np.random.default_rng(4)
+    scenes = [(c, util.load_case(c)) for c in util.CASES] + [(n, cfg) for n, _, cfg in util.random_meshes(tmp_path)]
+    for name, cfg in scenes:
+        dim, sc = cfg["dim"], cfg["scene"]
+        v, p = oracle_lib.load_obj(sc["boundary"], dim, False)
+        src = util.source_grid(dim); shp = list(src.shape) + [1]*(3 - dim)
+        h = C.c_void_p(emu_fast.emuf_scene_create(dim, _fp(v), len(v), p.ctypes.data_as(C.POINTER(C.c_int)), len(p), _fp(src), shp[0], shp[1], shp[2],
+                                                  C.c_float(sc.get("absorptionCoeff", 0.0)), int(sc.get("isWatertight", False)), int(sc.get("isDoubleSided", False))))
+        osc = oracle_lib.OracleScene(dim, sc, src)
+        lo, hi = osc.bbox()
+        q = util.random_points(lo, hi, 2500, seed=5, margin=0.05)
+        dd = osc.dist_dirichlet(q)
+        for flip in (0, 1):
+            want = osc.star_radius(q, 1e-3, dd, 1e-3, bool(flip)); got = np.zeros(len(q), np.float32)
+            emu_fast.emuf_star_radius(h, _fp(q), len(q), C.c_float(1e-3), _fp(dd), C.c_float(1e-3), flip, _fp(got))
+            rel = np.abs(got - want)/np.maximum(np.abs(want), 1e-6)
+            assert (rel < 1e-5).mean() >= 0.999, (name, flip, (rel < 1e-5).mean(), rel.max())
+        want = osc.source(q); got = np.zeros(len(q), np.float32)
+        emu_fast.emuf_source(h, _fp(q), len(q), _fp(got))
+        assert (want == got).mean() >= 0.998, (name, (want == got).mean())     # a texel boundary may move by an ulp
+        u = rng.random((len(q), dim - 1), dtype=np.float32)
+        if dim == 2:
+            a = 2*np.pi*u[:, 0]; d = np.stack([np.cos(a), np.sin(a)], 1).astype(np.float32)
+        else:
+            z = 1 - 2*u[:, 0]; r = np.sqrt(np.maximum(0, 1 - z*z)); a = 2*np.pi*u[:, 1]
+            d = np.stack([r*np.cos(a), r*np.sin(a), z], 1).astype(np.float32)
+        tmax = (rng.random(len(q), dtype=np.float32)*(hi - lo).max()).astype(np.float32)
+        ray = osc.intersect_neumann(q, np.zeros_like(q), d, tmax, 0)
+        out = np.zeros((len(q), 2), np.float32)
+        emu_fast.emuf_rays(h, _fp(q), _fp(d), _fp(tmax), len(q), _fp(out))
+        assert (out[:, 0] == ray[:, 0]).mean() >= 0.9995, name
+        both = (out[:, 0] > 0) & (ray[:, 0] > 0)
+        if both.any():
+            assert (np.abs(out[both, 1] - ray[both, 1]) <= 2e-5*np.abs(ray[both, 1]) + 1e-6).all(), name
+        emu_fast.emuf_scene_destroy(h); osc.close()
