@@ -15,11 +15,11 @@ import time
 from importlib import import_module
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-import util  # noqa: E402
 import __graft_entry__ as ge  # noqa: E402
+util = ge.load_package().workloads  # scene fixtures + the karman obstacle
 
 
 def _leave():
@@ -38,6 +38,24 @@ def build(args, pkg, st):
         s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1, **dd)
         tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
         return s, cfg, tg, (6, 64), "taylorgreen step (SIREN 6x64, batch 64^2, dt 1e-3), 512^2 pressure samples x 500 walks, 1002^2 divergence grid"
+    if args.case in ("smoke3d", "karman3d"):
+        # examples/smoke3d/run.sh (--src smoke): SIREN 5x64; examples/karman3d/run.sh: SIREN 2x128, karman_vel 0.5;
+        # both: batch 128^2, dt 0.05, bdry_eps 1e-2, reset_wts 1, wost_resolution 256, 82^3 divergence grid
+        cfg = util.load_case(args.case)
+        smoke = args.case == "smoke3d"
+        s = st.SplitStepper(cfg, scene_size=(-1.0, 1.0)*3, hidden_features=64 if smoke else 128, num_hidden_layers=5 if smoke else 2, dt=0.05,
+                            lr=1e-5, sample_resolution=128, wost_resolution=256, grid_resolution=80, bdry_eps=1e-2, max_n_iters=args.iters,
+                            early_stop=False, use_cuda_graph=not args.no_graph, boundary="smoke" if smoke else "karman3d",
+                            obstacle=None if smoke else ((0.0, -0.8), 0.1), karman_vel=0.5, reset_wts=True, seed=1, **dd)
+        if smoke:
+            init = lambda x: torch.zeros_like(x)  # noqa: E731  (smoke_velocity, 3d sources.py:20-45: zero outside the inlet ball, which the envelope overrides)
+        else:
+            def init(x):  # karman_velocity, 3d sources.py:98-107: (0, 0, karman_vel) times the cylinder weight
+                d = torch.sqrt(x[:, 0]**2 + (x[:, 2] + 0.8)**2) - 0.1
+                w = torch.clamp(d, 0, 1e-2)/1e-2
+                return torch.stack([torch.zeros_like(w), torch.zeros_like(w), 0.5*w], dim=-1)
+        return s, cfg, init, ((5, 64) if smoke else (2, 128)), "%s step (SIREN %s 3->3, batch 128^2, dt 0.05, reset_wts), 256^2 pressure samples x 500 walks, 82^3 divergence grid" % (
+            "smoke3d" if smoke else "karman3d", "5x64" if smoke else "2x128")
     if args.case == "smoke_obs":
         # examples/smoke_obs/run.sh: SIREN 5x64 3->3, batch 128^2, dt 0.05, bdry_eps 1e-2, reset_wts 1, wost_resolution 256, 82^3 grid
         cfg = util.load_case("smoke3d")
@@ -57,7 +75,7 @@ def build(args, pkg, st):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--case", default="taylorgreen", choices=["taylorgreen", "karman", "smoke_obs"])
+    ap.add_argument("--case", default="taylorgreen", choices=["taylorgreen", "karman", "smoke_obs", "smoke3d", "karman3d"])
     ap.add_argument("--iters", type=int, default=1000, help="Adam iterations per fit (reference: 10000)")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--watertight", action="store_true")
@@ -125,7 +143,7 @@ def main():
     # CPU solver rate: the reference arm of bench.py (the one place that runs oracle/_ref) on this configuration's scene
     import subprocess
     n_press = int(s.last["pressure_samples"].shape[0])
-    ref_case = {"taylorgreen": "taylorgreen_shipped" if args.watertight else "taylorgreen_active", "karman": "karman", "smoke_obs": "smoke3d"}[args.case]
+    ref_case = {"taylorgreen": "taylorgreen_shipped" if args.watertight else "taylorgreen_active", "karman": "karman", "smoke_obs": "smoke3d", "smoke3d": "smoke3d", "karman3d": "karman3d"}[args.case]
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--case", ref_case, "--points", str(args.cpu_sample),
                         "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900)
     arm = json.loads(r.stdout.strip().splitlines()[-1])

@@ -92,6 +92,9 @@ void nmc_scene_destroy(nmc_scene* scene);
 /* Replace the source grid without rebuilding the boundary structure (the reference rebuilds the
  * whole Scene every step, src/2d/models/model_split.py:191). src_is_device != 0: device pointer. */
 int nmc_scene_set_source(nmc_scene* scene, const float* src, int n0, int n1, int n2, int src_is_device);
+/* Same, enqueued on `stream` (a cudaStream_t): ordered after the kernel that produced a device-resident grid and
+ * before a following nmc_wost_solve_device on the same stream; no host synchronisation. */
+int nmc_scene_set_source_async(nmc_scene* scene, const float* src, int n0, int n1, int n2, int src_is_device, void* stream);
 int nmc_scene_dim(const nmc_scene* scene);
 int nmc_scene_bbox(const nmc_scene* scene, float* lo_hi /* 2*dim */);
 int nmc_scene_num_nodes(const nmc_scene* scene);
@@ -135,6 +138,11 @@ uint64_t nmc_point_seed(uint64_t seed, uint64_t index);
 #define NMC_PROBE_SAMPLE_RADIUS_FAST 10 /* fast-mode inverse-CDF radial sampler: aux0 = R[n], aux1 = u[n]  out: r, pdf */
 int nmc_probe(nmc_scene* scene, int kind, int64_t n, const float* pts, const float* aux0, const float* aux1,
 			  const float* aux2, const float* aux3, const float* params, float* out);
+
+/* Instruction-throughput peaks of `device`, measured by micro-benchmarks (csrc/peaks.cu), in warp-instructions per
+ * second: out3[0] fp32 FMA (= the issue limit, one instruction per scheduler per clock), out3[1] MUFU (ex2),
+ * out3[2] fp64 FMA.  Denominators of the issue-bound roofline bench.py reports for the walk kernels. */
+int nmc_measure_peaks(int device, float* out3);
 
 #ifdef __cplusplus
 }

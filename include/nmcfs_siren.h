@@ -33,7 +33,8 @@ typedef struct {
  *   2. obstacle weight clamp(|x - sphere_c| - sphere_r, 0, eps)/eps on every component when has_sphere
  *      (smoothstep_circular_obs, base.py:352-358).  NOT detached in the reference: nmc_siren_backward adds the
  *      gradient that reaches x through it.
- *   3. wall weights (as kind 1) on the components in wall_mask (karman: v only, base.py:175-180).
+ *   3. wall weights (as kind 1) on the components in wall_mask (karman: v only, base.py:175-180; karman3d: u and v,
+ *      3d base.py:262-270).
  * The fields after eps are ignored for kind 0 and 1. */
 typedef struct {
 	int kind;
@@ -42,6 +43,12 @@ typedef struct {
 	int wall_mask;
 	int has_sphere; float sphere_c[3]; float sphere_r;
 	int region_kind; int region_mask; float region_lo[3], region_hi[3], region_vel[3];
+	int sphere_axes;            /* bit i: coordinate i enters the obstacle distance; 0 = all (sphere / circle).  0b101: the
+	                               cylinder along y of karman3d (cylinder_obstacle_function, src/3d/sources.py:141-145) */
+	float region_noise[3];      /* region value = region_vel[j] + region_noise[j] * u, u uniform in [-1, 1), one u per sample
+	                               (the 3D smoke inlet, src/3d/models/base.py:197-209); u is a hash of the sample's
+	                               coordinates and *noise_seed, i.e. fixed within a time step */
+	const unsigned* noise_seed; /* DEVICE pointer to the time step (read at kernel time: CUDA-graph replays see updates); may be NULL */
 } nmc_siren_envelope;
 
 const char* nmc_siren_last_error(void);

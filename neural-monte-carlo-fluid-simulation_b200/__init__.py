@@ -7,6 +7,7 @@ Layout:
   zombie.py        Python mirror of the reference's module surface: Scene(config, sourceValue), wost(...)
   zombie2d/, zombie3d/   the compiled drop-in modules named `zombie_bindings` (one per dimension)
   sharding.py      multi-GPU point sharding (one process per GPU, gather of the estimates)
+  workloads.py     synthetic workloads of each example configuration's shape (bench.py, bench-size parity tests)
   siren.py         fused SIREN velocity network (drop-in for the reference's MLP) + fused Adam (csrc/siren*.cu)
   stepper.py       device-resident operator-split time step (advect fit, divergence grid, wost, projection fit)
   fields.py        density advection + Taylor-Green error on the device (csrc/fields.cu, include/nmcfs_fields.h)
@@ -15,7 +16,7 @@ The directory name contains '-', so import it with
     importlib.import_module("neural-monte-carlo-fluid-simulation_b200")
 or through __graft_entry__.load_package().
 """
-from . import capi, zombie, sharding  # noqa: F401
+from . import capi, zombie, sharding, workloads  # noqa: F401
 
 
 def load_fields():

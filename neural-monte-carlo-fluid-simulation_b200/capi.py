@@ -43,7 +43,8 @@ class SolveStats(C.Structure):
 # every symbol include/nmcfs.h declares (tests check that the library exports them all)
 EXPORTS = ["nmc_last_error", "nmc_device_count", "nmc_scene_create", "nmc_scene_destroy", "nmc_scene_set_source",
            "nmc_scene_dim", "nmc_scene_bbox", "nmc_scene_num_nodes", "nmc_scene_nodes", "nmc_wost_solve",
-           "nmc_wost_solve_device", "nmc_wost_solve_stats", "nmc_point_seed", "nmc_probe"]
+           "nmc_wost_solve_device", "nmc_wost_solve_stats", "nmc_point_seed", "nmc_probe", "nmc_scene_set_source_async",
+           "nmc_measure_peaks"]
 SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_adam_step", "nmc_adam_step_device", "nmc_mse_grad"]
 
 _lib = None
@@ -63,6 +64,8 @@ def lib():
                                        C.POINTER(SceneOpts), C.c_int]
         L.nmc_scene_destroy.argtypes = [C.c_void_p]
         L.nmc_scene_set_source.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.nmc_scene_set_source_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.nmc_measure_peaks.argtypes = [C.c_int, _fp]
         L.nmc_scene_dim.argtypes = [C.c_void_p]
         L.nmc_scene_bbox.argtypes = [C.c_void_p, _fp]
         L.nmc_scene_num_nodes.argtypes = [C.c_void_p]
@@ -92,6 +95,13 @@ def check(rc):
 
 def device_count():
     return int(lib().nmc_device_count())
+
+
+def measure_peaks(device=0):
+    """Instruction-throughput peaks of the device in warp-instructions/s: (fp32 FMA = issue limit, MUFU, fp64 FMA)."""
+    out = (C.c_float*3)()
+    check(lib().nmc_measure_peaks(int(device), out))
+    return float(out[0]), float(out[1]), float(out[2])
 
 
 def _f32(a):
@@ -136,9 +146,14 @@ class SceneHandle:
         shp = list(src.shape) + [1] * (3 - self.dim)
         check(lib().nmc_scene_set_source(self._h, _ptr(src), shp[0], shp[1], shp[2], 0))
 
-    def set_source_device(self, ptr, shape):
+    def set_source_device(self, ptr, shape, stream=None):
+        """Device-resident grid.  With `stream` (a cudaStream_t value) the copy is enqueued on that stream, i.e. ordered
+        after the grid's producer and before a solve_device on the same stream."""
         shp = list(shape) + [1] * (3 - self.dim)
-        check(lib().nmc_scene_set_source(self._h, C.c_void_p(ptr), shp[0], shp[1], shp[2], 1))
+        if stream is None:
+            check(lib().nmc_scene_set_source(self._h, C.c_void_p(ptr), shp[0], shp[1], shp[2], 1))
+        else:
+            check(lib().nmc_scene_set_source_async(self._h, C.c_void_p(ptr), shp[0], shp[1], shp[2], 1, C.c_void_p(stream)))
 
     def bbox(self):
         out = np.zeros(2 * self.dim, np.float32)

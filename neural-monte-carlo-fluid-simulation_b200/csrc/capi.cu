@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,7 +27,11 @@ struct nmc_scene {
 	Counters* d_counters = nullptr;
 	unsigned int* d_workCounter = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	// the work buffers, counters and events above are per-scene mutable state: calls on one scene are serialised
+	// (the reference serialises them by holding the GIL, demo.cpp:119; the bindings here release it)
+	std::mutex mu;
 };
+typedef std::lock_guard<std::mutex> Lock;
 
 extern "C" const char* nmc_last_error(void) { return g_err.c_str(); }
 
@@ -47,7 +52,7 @@ static cudaError_t upload(T*& dst, const std::vector<Q4>& src) {
 	return cudaMemcpy(dst, src.data(), src.size()*sizeof(Q4), cudaMemcpyHostToDevice);
 }
 
-static int setSource(nmc_scene* s, const float* src, int n0, int n1, int n2, int isDevice) {
+static int setSource(nmc_scene* s, const float* src, int n0, int n1, int n2, int isDevice, cudaStream_t stream = 0, bool async = false) {
 	if (!src || n0 <= 0 || n1 <= 0 || (s->flat.dim == 3 && n2 <= 0)) return fail(NMC_ERR_INVALID, "source grid: null pointer or empty shape");
 	size_t count = (size_t)n0*n1*(s->flat.dim == 3 ? n2 : 1);
 	if (count > s->srcCap) {
@@ -56,7 +61,8 @@ static int setSource(nmc_scene* s, const float* src, int n0, int n1, int n2, int
 		CK(cudaMalloc((void**)&s->d_src, count*sizeof(float)));
 		s->srcCap = count;
 	}
-	CK(cudaMemcpy(s->d_src, src, count*sizeof(float), isDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+	if (async) CK(cudaMemcpyAsync(s->d_src, src, count*sizeof(float), isDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+	else CK(cudaMemcpy(s->d_src, src, count*sizeof(float), isDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	s->view.src = s->d_src; s->view.n0 = n0; s->view.n1 = n1; s->view.n2 = s->flat.dim == 3 ? n2 : 1;
 	{ // texel index = (int)(x*scale + off) for the default mode: axis k of the box maps to n_k texels (2D: rows <-> y)
 		const SceneView& v = s->view;
@@ -115,8 +121,15 @@ extern "C" void nmc_scene_destroy(nmc_scene* s) {
 
 extern "C" int nmc_scene_set_source(nmc_scene* s, const float* src, int n0, int n1, int n2, int src_is_device) {
 	if (!s) return fail(NMC_ERR_INVALID, "null scene");
+	Lock lock(s->mu);
 	CK(cudaSetDevice(s->device));
 	return setSource(s, src, n0, n1, n2, src_is_device);
+}
+extern "C" int nmc_scene_set_source_async(nmc_scene* s, const float* src, int n0, int n1, int n2, int src_is_device, void* stream) {
+	if (!s) return fail(NMC_ERR_INVALID, "null scene");
+	Lock lock(s->mu);
+	CK(cudaSetDevice(s->device));
+	return setSource(s, src, n0, n1, n2, src_is_device, (cudaStream_t)stream, true);
 }
 extern "C" int nmc_scene_dim(const nmc_scene* s) { return s ? s->flat.dim : 0; }
 extern "C" int nmc_scene_bbox(const nmc_scene* s, float* out) {
@@ -207,6 +220,7 @@ extern "C" int nmc_wost_solve_device(nmc_scene* s, const nmc_solver_opts* opts, 
 									 uint64_t index_offset, float* d_p_out, float* d_grad_out, void* stream,
 									 nmc_solve_stats* stats) {
 	if (!s) return fail(NMC_ERR_INVALID, "null scene");
+	Lock lock(s->mu);
 	CK(cudaSetDevice(s->device));
 	if (stats) memset(stats, 0, sizeof(*stats));
 	cudaStream_t st = (cudaStream_t)stream;
@@ -237,6 +251,7 @@ extern "C" int nmc_wost_solve_stats(nmc_scene* s, const nmc_solver_opts* opts, c
 									nmc_solve_stats* stats) {
 	if (!s) return fail(NMC_ERR_INVALID, "null scene");
 	if (n < 0 || (n > 0 && (!pts || !p_out || !grad_out))) return fail(NMC_ERR_INVALID, "null buffer");
+	Lock lock(s->mu);
 	CK(cudaSetDevice(s->device));
 	if (stats) memset(stats, 0, sizeof(*stats));
 	if (n == 0) return NMC_OK;
@@ -268,6 +283,7 @@ extern "C" int nmc_probe(nmc_scene* s, int kind, int64_t n, const float* pts, co
 						 const float* aux2, const float* aux3, const float* params, float* out) {
 	if (!s || !out || n < 0) return fail(NMC_ERR_INVALID, "bad arguments");
 	if (n == 0) return NMC_OK;
+	Lock lock(s->mu);
 	CK(cudaSetDevice(s->device));
 	const int dim = s->flat.dim;
 	int W = probeWidth(dim, kind);

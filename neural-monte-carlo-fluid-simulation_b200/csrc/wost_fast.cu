@@ -386,12 +386,17 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (n <= 0) return cudaSuccess;
 	if (n >= (1ll << 32) - 65536) return cudaErrorInvalidValue;
 	const int dim = S.dim;
-	// small scenes are scanned flat (no per-step tree traversal)
-	const bool flat = S.nPrims <= 128 && S.nSilU <= 128; // <= 41 KB of tables
+	// small scenes are scanned flat (no per-step tree traversal); the flat kernels stage every table in shared memory
+	// unconditionally, so a scene whose tables do not fit the 48 KB stage falls back to the tree kernels
+	bool flat = S.nPrims <= 128 && S.nSilU <= 128; // <= 43 KB of tables (asserted by tests/test_host_logic.py)
 	const int G = dim == 2 ? FlatGroup<2>::n : FlatGroup<3>::n;
 	const size_t nSilP = (size_t)(S.nSilU + G - 1)/G*G, nRayP = (size_t)(S.nRay + G - 1)/G*G;
-	size_t quads = (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(flat ? nSilP : (size_t)S.nSilRefs)
-				 + (flat ? 2*(nRayP/G) + 2*(nSilP/G) + (size_t)((dim == 2 ? 1 : 3) + 1)*nRayP : 0);
+	auto stageQuadsFor = [&](bool fl) {
+		return (size_t)4*S.nNodes + (size_t)(dim == 2 ? 1 : 3)*S.nPrims + (size_t)S.nPrims + (size_t)(dim == 2 ? 2 : 4)*(fl ? nSilP : (size_t)S.nSilRefs)
+			 + (fl ? 2*(nRayP/G) + 2*(nSilP/G) + (size_t)((dim == 2 ? 1 : 3) + 1)*nRayP : 0);
+	};
+	if (flat && stageQuadsFor(true)*sizeof(float4) > 48*1024) flat = false;
+	size_t quads = stageQuadsFor(flat);
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
@@ -403,7 +408,7 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true> : fastKernel<3, StridedStack, true>;
 	else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false> : fastKernel<2, LocalStack, false>;
 	else kern = smemStack ? fastKernel<3, StridedStack, false> : fastKernel<3, LocalStack, false>;
-	if (flat && !smemStack) return cudaErrorInvalidConfiguration; // cannot happen: <= 128 primitives give a shallow tree
+	if (flat && (!smemStack || stageQuads == 0)) return cudaErrorInvalidConfiguration; // cannot happen: <= 128 primitives give a shallow tree, and see above
 	int perSM = 0;
 	cudaError_t e = cudaSuccess;
 	if (smem > 48*1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // <= 48 + 24 + 4 KB

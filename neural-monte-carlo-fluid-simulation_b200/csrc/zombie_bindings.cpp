@@ -153,10 +153,14 @@ static void solve(const Scene& scene, const py::dict& solver, const py::dict& ou
 	nmc_solver_opts o = solverOpts(solver, output);
 	p.assign((size_t)n, 0.0f); g.assign((size_t)n*DIM, 0.0f);
 	int rc;
+	nmc_solve_stats st = {};
 	{
-		py::gil_scoped_release nogil; // the reference holds the GIL for the whole solve
-		rc = nmc_wost_solve(scene.handle, &o, pts.data(), n, 0, p.data(), g.data(), &g_lastStats);
+		// the reference holds the GIL for the whole solve; here other Python threads may run meanwhile -- calls on
+		// the same Scene are serialised inside the C ABI (per-scene mutex)
+		py::gil_scoped_release nogil;
+		rc = nmc_wost_solve(scene.handle, &o, pts.data(), n, 0, p.data(), g.data(), &st);
 	}
+	g_lastStats = st; // under the GIL again
 	if (rc != NMC_OK) throw std::runtime_error(std::string("zombie_bindings.wost: ") + nmc_last_error());
 }
 

@@ -26,7 +26,7 @@ class Envelope(C.Structure):
     _fields_ = [("kind", C.c_int), ("lo", C.c_float*3), ("hi", C.c_float*3), ("eps", C.c_float),
                 ("wall_mask", C.c_int), ("has_sphere", C.c_int), ("sphere_c", C.c_float*3), ("sphere_r", C.c_float),
                 ("region_kind", C.c_int), ("region_mask", C.c_int), ("region_lo", C.c_float*3), ("region_hi", C.c_float*3),
-                ("region_vel", C.c_float*3)]
+                ("region_vel", C.c_float*3), ("sphere_axes", C.c_int), ("region_noise", C.c_float*3), ("noise_seed", C.c_void_p)]
 
 
 def wall_envelope(size, eps):
@@ -39,11 +39,19 @@ def wall_envelope(size, eps):
     return e
 
 
-def general_envelope(size, eps, wall_mask, sphere=None, region=None):
+def general_envelope(size, eps, wall_mask, sphere=None, region=None, sphere_axes=0, region_noise=None, noise_seed=None):
     """kind 2.  sphere = (centre, radius) of the no-slip obstacle or None; region = ("box", lo, hi, mask, vel) or
-    ("ball", centre, radius, mask, vel) or None, `mask` = bit set of the overridden components."""
+    ("ball", centre, radius, mask, vel) or None, `mask` = bit set of the overridden components.  sphere_axes: bit set of
+    the coordinates entering the obstacle distance (0 = all).  region_noise: per-component amplitude of the per-sample
+    uniform(-1, 1) inlet noise; noise_seed: a uint32 CUDA tensor holding the time step (kept alive by the caller)."""
     e = wall_envelope(size, eps)
     e.kind, e.wall_mask = 2, int(wall_mask)
+    e.sphere_axes = int(sphere_axes)
+    if region_noise is not None:
+        for i, v in enumerate(region_noise):
+            e.region_noise[i] = float(v)
+    if noise_seed is not None:
+        e.noise_seed = register_seed(noise_seed).data_ptr()
     if sphere is not None:
         c, r = sphere
         e.has_sphere, e.sphere_r = 1, float(r)
@@ -77,6 +85,50 @@ def smoke_obs_envelope(size, eps, centre, radius, inlet_centre=(0.0, 0.0, -0.6),
                             region=("ball", inlet_centre, inlet_radius, 0b100, (0.0, 0.0, inlet_w)))
 
 
+def karman3d_envelope(size, eps, centre_xz, radius, karman_vel):
+    """src/3d/models/base.py:257-275 with the obstacle of src/3d/main.py:92-98: w = karman_vel in the inlet slab
+    z in [z0, z0 + eps], no-slip cylinder along y (distance in the x-z plane), wall weights on u and v only."""
+    big = 3.0e38
+    lo = (-big, -big, size[4])
+    hi = (big, big, size[4] + eps)
+    return general_envelope(size, eps, wall_mask=0b011, sphere=((centre_xz[0], 0.0, centre_xz[1]), radius),
+                            region=("box", lo, hi, 0b100, (0.0, 0.0, karman_vel)), sphere_axes=0b101)
+
+
+def smoke_envelope(size, eps, noise_seed, inlet_centre=(0.0, 0.0, -0.6), inlet_radius=0.1):
+    """src/3d/models/base.py:197-222 (--src smoke): inside the inlet ball (u, v, w) = (0.01 r, 0.01 r, 0.2 + 0.01 r) with
+    r uniform in [-10, 10] per sample (numpy re-seeded with the time step), wall weights on u, v, w, no obstacle."""
+    return general_envelope(size, eps, wall_mask=0b111, region=("ball", inlet_centre, inlet_radius, 0b111, (0.0, 0.0, 0.2)),
+                            region_noise=(0.1, 0.1, 0.1), noise_seed=noise_seed)
+
+
+_SEEDS = {}
+
+
+def register_seed(t):
+    """Keeps a noise-seed tensor (uint32 / int32, one element, CUDA) alive and findable by its device address."""
+    _SEEDS[t.data_ptr()] = t
+    return t
+
+
+def _env_noise_reference(env, samples):
+    """The kernels' inlet-noise hash (csrc/siren_env.cuh envNoise) with torch integer ops, for envelope_reference."""
+    M = 0xFFFFFFFF
+    h0 = 0x7F4A7C15
+    if env.noise_seed:
+        seed = int(_SEEDS[env.noise_seed].item()) & M
+        h0 = (seed*0x9E3779B9 + 0x7F4A7C15) & M
+    h = torch.full(samples.shape[:-1], h0, dtype=torch.int64, device=samples.device)
+    bits = samples.detach().contiguous().view(torch.int32).to(torch.int64) & M
+    for i in range(samples.shape[-1]):
+        h = h ^ bits[..., i]
+        h = (h*0x85EBCA6B) & M
+        h = h ^ (h >> 13)
+        h = (h*0xC2B2AE35) & M
+        h = h ^ (h >> 16)
+    return (h >> 8).to(torch.float32)*(2.0/16777216.0) - 1.0
+
+
 def envelope_reference(env, samples, net_vel):
     """The same envelope with stock torch ops, written like the reference's query_velocity (autograd flows through the
     obstacle weight, the wall weights are detached).  For tests and for callers who want the un-fused path."""
@@ -93,12 +145,19 @@ def envelope_reference(env, samples, net_vel):
         else:
             c = torch.tensor([env.region_lo[i] for i in range(dim)], device=samples.device, dtype=samples.dtype)
             m = torch.linalg.norm(samples - c, dim=-1) < env.region_hi[0]
+        noisy = any(env.region_noise[j] != 0.0 for j in range(3))
+        un = _env_noise_reference(env, samples) if noisy else None
         for j in range(vel.shape[-1]):
             if (env.region_mask >> j) & 1:
-                vel[..., j] = torch.where(m, torch.full_like(vel[..., j], env.region_vel[j]), vel[..., j])
+                val = torch.full_like(vel[..., j], env.region_vel[j])
+                if noisy:
+                    val = torch.addcmul(val, un, torch.full_like(un, env.region_noise[j]))
+                vel[..., j] = torch.where(m, val, vel[..., j])
     if env.kind == 2 and env.has_sphere:
         c = torch.tensor([env.sphere_c[i] for i in range(dim)], device=samples.device, dtype=samples.dtype)
-        dist = torch.linalg.norm(samples - c, dim=-1) - env.sphere_r
+        axes = env.sphere_axes & 7 or 7
+        sel = torch.tensor([float((axes >> i) & 1) for i in range(dim)], device=samples.device, dtype=samples.dtype)
+        dist = torch.linalg.norm((samples - c)*sel, dim=-1) - env.sphere_r
         vel = vel*(torch.clamp(dist, 0, eps)/eps).unsqueeze(-1)
     mask = 7 if env.kind == 1 else env.wall_mask
     ws = []
@@ -410,6 +469,11 @@ class DirectFit:
             dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG, group=self.group)
         self.opt.step_flat()
         return diff
+
+    def close(self):
+        """Releases the scratch buffers; the network keeps its (flat-backed) parameters."""
+        self.z = None
+        self.out = None
 
     def sync_parameters(self, src=0):
         """Broadcast the flat parameter buffer from rank `src` (after initialisation / re-initialisation)."""

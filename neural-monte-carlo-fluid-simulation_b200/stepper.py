@@ -21,7 +21,8 @@ import ctypes as C
 import torch
 
 from . import capi, zombie, fields
-from .siren import FusedSiren, DirectFit, wall_envelope, karman_envelope, smoke_obs_envelope, envelope_reference
+from .siren import (FusedSiren, DirectFit, wall_envelope, karman_envelope, smoke_obs_envelope, karman3d_envelope, smoke_envelope,
+                    envelope_reference)
 
 
 def sample_uniform_2d(resolution, size, device, with_boundary=True):
@@ -60,12 +61,25 @@ def sample_uniform_3d(resolution, size, device, with_boundary=True):
     return coords
 
 
+def collective_stop(loss, world, group=None, threshold=1.1e-10):
+    """True when the mean over ranks of `loss` (a scalar tensor, each rank's shard MSE) is at or below the
+    reference's early-stop threshold (base.py:148).  One all_reduce, issued by every rank."""
+    if world > 1:
+        import torch.distributed as dist
+        loss = loss.detach().clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        loss = loss/world
+    return loss.item() <= threshold
+
+
 class SplitStepper:
     """Operator-split stepper on a box domain `scene_size` = (x0, x1, y0, y1[, z0, z1]); 2D or 3D by its length.
     boundary = 'taylorgreen' / 'walls': wall weights on every component (taylorgreen, vortex_collide branches);
     'karman' (2D): inlet strip, no-slip cylinder `obstacle` = (centre, radius), wall weight on v, samples inside the
     cylinder unused (base.py:169-181, 239-241); 'smoke_obs' (3D): inlet ball, no-slip sphere `obstacle`, wall weights
-    (3d base.py:224-244); None: no envelope.  reset_wts re-initialises the network before every fit
+    (3d base.py:224-244); 'karman3d' (3D): inlet slab on w, no-slip cylinder along y `obstacle` = ((cx, cz), radius), wall
+    weights on u and v (3d base.py:257-275, main.py:92-98); 'smoke' (3D): noisy inlet ball re-drawn every time step, wall
+    weights (3d base.py:197-222); None: no envelope.  reset_wts re-initialises the network before every fit
     (create_optimizer(reset=True), model_split.py:44-62; the karman and 3D examples run with --reset_wts 1)."""
 
     def __init__(self, wost_config, scene_size, hidden_features=64, num_hidden_layers=6, dt=0.001, lr=1e-5,
@@ -118,10 +132,20 @@ class SplitStepper:
             else:
                 self.env = smoke_obs_envelope(self.size, bdry_eps, obstacle[0], obstacle[1])
             self._obs_c = torch.tensor([float(c) for c in obstacle[0]], device=self.dev)
+        elif boundary == "karman3d":
+            if obstacle is None or dim != 3:
+                raise ValueError("boundary='karman3d' needs obstacle=((cx, cz), radius) and a 3D scene")
+            self.env = karman3d_envelope(self.size, bdry_eps, obstacle[0], obstacle[1], karman_vel)
+        elif boundary == "smoke":
+            if dim != 3:
+                raise ValueError("boundary='smoke' is the 3D smoke plume")
+            # the reference re-seeds numpy with the time step on every query (3d base.py:203); the kernels read this cell
+            self._noise_seed = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.env = smoke_envelope(self.size, bdry_eps, self._noise_seed)
         elif boundary is None:
             self.env = None
         else:
-            raise ValueError("boundary must be 'taylorgreen', 'walls', 'karman', 'smoke_obs' or None")
+            raise ValueError("boundary must be 'taylorgreen', 'walls', 'karman', 'smoke_obs', 'karman3d', 'smoke' or None")
         self._lo = torch.tensor(self.size[0::2], device=self.dev)
         self._hi = torch.tensor(self.size[1::2], device=self.dev)
         if init_velocity is not None and init_iters > 0:
@@ -217,9 +241,39 @@ class SplitStepper:
             else:
                 one()
             it += 1
-            if self.early_stop and it % self.check_every == 0 and loss_buf.item() <= 1.1e-10:
+            if self.early_stop and it % self.check_every == 0 and self._stop_now(loss_buf):
                 break
         return it, loss_buf
+
+    def _stop_now(self, loss_buf):
+        """Early-stop test of _training_loop (base.py:148).  Data-parallel fits: `loss_buf` is this rank's shard MSE, so
+        the decision is taken on the mean over ranks -- every rank issues this all_reduce at the same iteration and
+        reaches the same verdict (a rank that stopped alone would leave the others waiting in the gradient all_reduce)."""
+        return collective_stop(loss_buf, self.world)
+
+    def close(self):
+        """Drops the captured CUDA graphs (they hold the NCCL gradient all_reduce of the data-parallel fits: while they
+        are alive torch.distributed.destroy_process_group() blocks), the fit buffers and the scene."""
+        torch.cuda.synchronize(self.dev)
+        for key in list(self._graphs):
+            graph, _ = self._graphs.pop(key)
+            graph.reset()
+        self._graphs = {}
+        self._proj = None
+        if self._fit is not None:
+            self._fit.close()
+            self._fit = None
+        if self.scene is not None:
+            self.scene.handle.close()
+            self.scene = None
+        torch.cuda.synchronize(self.dev)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def advect_velocity(self, n_iters=None):
         n = self.sample_resolution**2//self.world
@@ -246,12 +300,13 @@ class SplitStepper:
 
     def pressure_solve(self, samples):
         div = self.divergence_grid()
-        self.scene.handle.set_source_device(div.data_ptr(), div.shape)
+        stream = torch.cuda.current_stream().cuda_stream  # the grid's producer, the copy and the solve share one stream
+        self.scene.handle.set_source_device(div.data_ptr(), div.shape, stream=stream)
         n = samples.shape[0]
         p = torch.empty(n, device=self.dev); g = torch.empty((n, self.dim), device=self.dev)
         st = capi.SolveStats()
         self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=self.rank*(self.wost_resolution**2),
-                                       stream=torch.cuda.current_stream().cuda_stream, stats=st)
+                                       stream=stream, stats=st)
         self.last.update(walks=st.walks_started, wost_ms=st.kernel_ms, div=div)
         return p, g
 
@@ -285,7 +340,8 @@ class SplitStepper:
                 cap = self.wost_resolution**2
                 self._proj = (torch.zeros(cap, self.dim, device=self.dev), torch.zeros(cap, self.dim, device=self.dev), torch.zeros((), device=self.dev))
             ps, pg, pc = self._proj
-            ps[:big].copy_(samples_all); pg[:big].copy_(grad_p); pc.fill_(float(big - 1))
+            # 2D: randint(0, N - 1) excludes the last point (2d model_split.py:274); 3D: randint(0, N) (3d model_split.py:295)
+            ps[:big].copy_(samples_all); pg[:big].copy_(grad_p); pc.fill_(float(big - 1 if self.dim == 2 else big))
 
             def iteration():
                 # uniform index in [0, big - 2] (the reference's randint(0, big - 1) excludes the last point, :274);
@@ -298,7 +354,7 @@ class SplitStepper:
             cap_idx = ps.shape[0] - 1
         else:
             def iteration():
-                idx = torch.randint(0, big - 1, (n,), device=self.dev)  # the reference excludes the last point (:274)
+                idx = torch.randint(0, big - 1 if self.dim == 2 else big, (n,), device=self.dev)  # 2D excludes the last point (:274)
                 samples = samples_all[idx]
                 with torch.no_grad():
                     target = self.query_velocity(samples, use_prev=True) - grad_p[idx]
@@ -309,7 +365,9 @@ class SplitStepper:
         self.velocity_field_prev.load_state_dict(self.velocity_field.state_dict())
 
     def step(self, n_iters=None):
-        """NeuralFluidSplit.step, adv_ref = 0, reset_wts = 0 (model_split.py:44-62)."""
+        """NeuralFluidSplit.step, adv_ref = 0 (model_split.py:44-62)."""
+        if self.boundary == "smoke":
+            self._noise_seed.fill_(self.timestep)
         self._sync_prev()
         it_a, loss_a = self.advect_velocity(n_iters)
         self._sync_prev()

@@ -69,13 +69,18 @@ def main():
         assert torch.equal(ps, s.last["pressure_samples"])
         # the ranks trained on different samples: their shards of the gathered pressure set differ
         assert not torch.equal(s.last["pressure_samples"][:2048], s.last["pressure_samples"][2048:4096])
+        # early stop is a collective decision: rank 0 alone below the threshold must not stop anybody
+        mine = torch.tensor(1e-12 if rank == 0 else 1.0, device="cuda")
+        assert s._stop_now(mine) is False
+        assert s._stop_now(torch.tensor(1e-12, device="cuda")) is True
+        s.close()   # drops the graphs that captured the gradient all_reduce
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
         print("DIST_STEPPER_OK world=%d" % world, flush=True)
-    # destroy_process_group() blocks while CUDA graphs that captured NCCL collectives are alive: leave without it
-    sys.stdout.flush(); sys.stderr.flush()
-    os._exit(0)
+    dist.destroy_process_group()   # returns because close() released the NCCL-capturing graphs
+    if rank == 0:
+        print("DIST_STEPPER_CLEAN_EXIT", flush=True)
 
 
 if __name__ == "__main__":

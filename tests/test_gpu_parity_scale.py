@@ -1,0 +1,121 @@
+"""Parity at the sizes and source grids that are benchmarked ("next" item 1).
+
+Every BASELINE configuration's scene with the divergence-grid shape the time-stepper writes (401x1002, 1002^2, 82^3;
+package workloads.py -- the same module bench.py takes its inputs from), >= 4096 query points x 500 walks, both
+estimator modes, compared with the reference itself run LIVE on the box's host cores (oracle/_ref, the reference's own
+solver headers; the plain-C oracle, pinned bit-for-bit to it, when _ref is absent):
+
+  deterministic mode  per-point estimates within 1e-5 relative, identical averaged-walk counts   (north_star criterion 1)
+  default mode        per-point z-scores, bias bound |mean z| < 4/sqrt(N), variance ratios,
+                      per-point completed-walk fraction and mean walk length                     (north_star criterion 2)
+
+Reference: walk_on_stars.h:466-617 driven through oracle/ref_harness.cpp:175-266.  Measured fractions are printed
+(`pytest -s`) and quoted in DESIGN.md section 3.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+# (case, points): the meshes beyond the flat-scan limit are slow on the CPU side (1.6e4 walks/s/8 threads on box_sphere)
+BENCH_CASES = [("karman", 4096), ("taylorgreen_active", 4096), ("smoke3d", 4096), ("karman3d", 4096),
+               ("channel_circle", 1024), ("box_sphere", 1024)]
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = util.package()
+    assert p.capi.device_count() > 0, "no CUDA device visible"
+    return p
+
+
+_ref_cache = {}
+
+
+def _reference(case, n):
+    """(cfg, src, pts, p, g, stats12) of the reference on this workload; one CPU run per case, shared by both modes."""
+    if case in _ref_cache:
+        return _ref_cache[case]
+    from oracle import refbind, oraclebind
+    wl = util.package().workloads
+    cfg = wl.load_case(case)
+    dim = cfg["dim"]
+    src = wl.source_grid(case)
+    if refbind.available(dim):
+        sc, kind = refbind.RefScene(dim, cfg["scene"], src), "oracle/_ref (reference headers)"
+    else:
+        sc, kind = oraclebind.OracleScene(dim, cfg["scene"], src), "oracle C restatement"
+    lo, hi = sc.bbox()
+    pts = wl.random_points(lo, hi, n, seed=31)
+    p, g, st = sc.wost(cfg["solver"], cfg["output"], pts, seed=11, nthreads=os.cpu_count() or 4, want_stats=True)
+    sc.close()
+    _ref_cache[case] = (cfg, src, pts, p, g, st, kind)
+    return _ref_cache[case]
+
+
+@pytest.mark.parametrize("case,n", BENCH_CASES)
+def test_deterministic_mode_at_bench_size(pkg, case, n):
+    cfg, src, pts, rp, rg, rst, kind = _reference(case, n)
+    sc = pkg.Scene(cfg["scene"], src, device=0)
+    p, g, st12, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_DETERMINISTIC, seed=11, want_stats=True)
+    act = rst[:, 11] > 0
+    assert np.array_equal(st12[:, 11] > 0, act), "estimationQuantity != None disagrees"
+    assert st.walks_started == pkg.workloads.walks_per_point(cfg["solver"])*int(act.sum())
+    same_counts = (st12[:, 9] == rst[:, 9]).mean()
+    okp, okg = util.close_mask(p, rp), util.close_mask(g, rg)
+    print("\n[det %s, %d pts, vs %s] identical averaged-walk counts %.4f; p within 1e-5: %.4f; grad within 1e-5: %.4f"
+          % (case, n, kind, same_counts, okp.mean(), okg.mean()))
+    assert same_counts >= 0.99
+    assert okp.mean() >= 0.99 and okg.mean() >= 0.99
+    se = np.sqrt(np.maximum(rst[:, 1], 0)/np.maximum(rst[:, 9], 1))
+    assert (np.abs(p - rp) <= 3*se + 1e-12)[~okp].all()  # a flipped accept/reject decision moves a point by O(1/500)
+
+
+@pytest.mark.parametrize("case,n", BENCH_CASES)
+def test_default_mode_at_bench_size(pkg, case, n):
+    cfg, src, pts, rp, rg, ref, kind = _reference(case, n)
+    dim = cfg["dim"]
+    nw = pkg.workloads.walks_per_point(cfg["solver"])
+    sc = pkg.Scene(cfg["scene"], src, device=0)
+    p, g, s, st = pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], pts, mode=pkg.capi.MODE_FAST, seed=20261018, want_stats=True)
+    act = ref[:, 11] > 0
+    assert ((s[:, 11] > 0) <= act).all()        # the default mode does not walk points the output mask zeroes
+    both = act & (s[:, 11] > 0)
+    N = int(both.sum())
+    assert N >= 0.9*act.sum() and N > 500
+    nf, nr = np.maximum(s[both, 9], 1), np.maximum(ref[both, 9], 1)
+    bias_bound = 4.0/np.sqrt(N)
+    report = ["[fast %s, %d active pts, vs %s]" % (case, N, kind)]
+
+    def zscore(a, va, b, vb):
+        return (a - b)/np.sqrt(va/nf + vb/nr + 1e-30)
+    z = zscore(s[both, 0], s[both, 1], ref[both, 0], ref[both, 1])
+    report.append("p: %.4f within 3 sigma, mean z %+.4f (bound %.4f), std z %.3f" % ((np.abs(z) < 3).mean(), z.mean(), bias_bound, z.std()))
+    zs = [z]
+    for d in range(dim):
+        zg = zscore(s[both, 2 + d], s[both, 5 + d], ref[both, 2 + d], ref[both, 5 + d])
+        report.append("grad[%d]: %.4f within 3 sigma, mean z %+.4f, std z %.3f" % (d, (np.abs(zg) < 3).mean(), zg.mean(), zg.std()))
+        zs.append(zg)
+    # per-point completed-walk fraction (escaped / over-long walks are discarded on both sides): binomial errors
+    ff, fr = nf/nw, nr/nw
+    zc = (ff - fr)/np.sqrt((ff*(1 - ff) + fr*(1 - fr))/nw + 1e-6)
+    report.append("completed-walk fraction: ours %.4f reference %.4f, per point %.4f within 3.5 sigma" % (ff.mean(), fr.mean(), (np.abs(zc) < 3.5).mean()))
+    # per-point mean walk length: roughly geometric, variance ~ m (1 + m)
+    lf, lr = s[both, 10], ref[both, 10]
+    zl = (lf - lr)/np.sqrt(lf*(1 + lf)/nf + lr*(1 + lr)/nr + 1e-6)
+    report.append("mean walk length: ours %.4f reference %.4f, per point %.4f within 3.5 sigma" % (lf.mean(), lr.mean(), (np.abs(zl) < 3.5).mean()))
+    vr = np.median(s[both, 1]/np.maximum(ref[both, 1], 1e-30))
+    vg = np.median(s[both, 5]/np.maximum(ref[both, 5], 1e-30))
+    report.append("median variance ratio: p %.3f, grad %.3f" % (vr, vg))
+    print("\n" + "\n  ".join(report))
+    for k, zz in enumerate(zs):
+        assert (np.abs(zz) < 3).mean() >= 0.985, (case, k, (np.abs(zz) < 3).mean())
+        assert abs(zz.mean()) < bias_bound, "systematic bias (channel %d): mean z = %+.4f, bound %.4f" % (k, zz.mean(), bias_bound)
+        assert 0.85 < zz.std() < 1.15, (case, k, zz.std())
+    assert abs(ff.mean() - fr.mean()) < 0.005 and (np.abs(zc) < 3.5).mean() >= 0.98
+    assert abs(lf.mean() - lr.mean()) < 0.02*max(lr.mean(), 0.05) + 0.002 and (np.abs(zl) < 3.5).mean() >= 0.97
+    assert 0.8 < vr < 1.25 and 0.7 < vg < 1.4

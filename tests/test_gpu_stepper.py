@@ -252,4 +252,4 @@ def test_distributed_stepper_two_gpus():
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", os.path.join(here, "dist_stepper_check.py")], capture_output=True, text=True, timeout=400)
-    assert r.returncode == 0 and "DIST_STEPPER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.returncode == 0 and "DIST_STEPPER_OK" in r.stdout and "DIST_STEPPER_CLEAN_EXIT" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -114,6 +114,39 @@ def test_sharded_solve_world_size_2_gloo(tmp_path, oracle_lib):
         assert p.returncode == 0, o
 
 
+_STOP_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch, torch.distributed as dist
+import util
+from importlib import import_module
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+st = import_module(util.package().__name__ + ".stepper")
+# rank 0's shard loss falls below the threshold first: nobody stops (both ranks must give the same verdict)
+assert st.collective_stop(torch.tensor(1e-12 if rank == 0 else 1.0), 2) is False
+# the mean over ranks is what is compared with 1.1e-10
+assert st.collective_stop(torch.tensor(0.2e-10 if rank == 0 else 1.9e-10), 2) is True
+assert st.collective_stop(torch.tensor(0.2e-10 if rank == 0 else 2.1e-10), 2) is False
+assert st.collective_stop(torch.tensor(1e-12), 1) is True
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_early_stop_is_a_collective_decision_world_size_2_gloo(tmp_path):
+    """Data-parallel fits: a rank whose shard loss reaches the early-stop threshold alone must keep iterating, or the
+    other rank waits for ever in the gradient all_reduce (ADVICE r1).  The verdict comes from the mean over ranks."""
+    script = tmp_path / "stop_worker.py"
+    script.write_text(_STOP_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), util.ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 # ---- product device headers compiled for the host -------------------------------------------------------
 class _EmuParams(C.Structure):
     _fields_ = [("nWalks", C.c_int), ("maxWalkLength", C.c_int), ("sT", C.c_int), ("sM", C.c_int),

@@ -64,19 +64,7 @@ def close_mask(a, b, rtol=1e-5, atol_scale=1e-7):
 
 
 def karman_obstacle(mask=1e-3):
-    """Centre and radius of the cylinder of the karman fixture the way src/2d/main.py:36-57,90-102 derives them:
-    the vertices strictly inside the bounding box, mean centre, mean radius + output.boundaryDistanceMask."""
-    v = []
-    for line in open(os.path.join(SCENES, "karman.obj")):
-        t = line.split()
-        if t and t[0] == "v":
-            v.append([float(t[1]), float(t[2])])
-    v = np.array(v)
-    lo, hi = v.min(0), v.max(0)
-    inner = v[(v[:, 0] > lo[0]) & (v[:, 0] < hi[0]) & (v[:, 1] > lo[1]) & (v[:, 1] < hi[1])]
-    inner = np.unique(inner, axis=0)
-    c = inner.mean(0)
-    return (float(c[0]), float(c[1])), float(np.linalg.norm(inner - c, axis=1).mean() + mask), (float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1]))
+    return package().workloads.karman_obstacle(mask)
 
 
 # Solver / scene options beyond the shipped configs that the bindings can express (SURVEY.md section 8(f) rank 2):
