@@ -139,6 +139,12 @@ uint64_t nmc_point_seed(uint64_t seed, uint64_t index);
 int nmc_probe(nmc_scene* scene, int kind, int64_t n, const float* pts, const float* aux0, const float* aux1,
 			  const float* aux2, const float* aux3, const float* params, float* out);
 
+/* The default mode's table of the exponentially scaled modified Bessel functions i0e, i1e, k0e, k1e (2D screened
+ * Poisson; csrc/bessel_table.cpp): cubic pieces in t = log2(x), 16 floats per interval (4 functions x c0..c3,
+ * f = ((c3 u + c2) u + c1) u + c0, u = (t - t0) * per_octave - interval).  Host-only (no device needed): returns the
+ * number of intervals and copies up to capacity_floats coefficients.  For the tests. */
+int nmc_bessel_table(float* out, int capacity_floats, float* t0, int* per_octave);
+
 /* Instruction-throughput peaks of `device`, measured by micro-benchmarks (csrc/peaks.cu), in warp-instructions per
  * second: out3[0] fp32 FMA (= the issue limit, one instruction per scheduler per clock), out3[1] MUFU (ex2),
  * out3[2] fp64 FMA.  Denominators of the issue-bound roofline bench.py reports for the walk kernels. */

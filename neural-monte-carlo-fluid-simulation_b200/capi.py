@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnmcfs.so")
+# NMC_LIBNMCFS: another build of the same library (A/B measurements of kernel variants, profiles/tools/ab_walk.py)
+LIB_PATH = os.environ.get("NMC_LIBNMCFS") or os.path.join(_HERE, "libnmcfs.so")
 
 MODE_FAST = 0
 MODE_DETERMINISTIC = 1
@@ -44,7 +45,7 @@ class SolveStats(C.Structure):
 EXPORTS = ["nmc_last_error", "nmc_device_count", "nmc_scene_create", "nmc_scene_destroy", "nmc_scene_set_source",
            "nmc_scene_dim", "nmc_scene_bbox", "nmc_scene_num_nodes", "nmc_scene_nodes", "nmc_wost_solve",
            "nmc_wost_solve_device", "nmc_wost_solve_stats", "nmc_point_seed", "nmc_probe", "nmc_scene_set_source_async",
-           "nmc_measure_peaks"]
+           "nmc_measure_peaks", "nmc_bessel_table"]
 SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_adam_step", "nmc_adam_step_device", "nmc_mse_grad"]
 
 _lib = None
@@ -102,6 +103,17 @@ def measure_peaks(device=0):
     out = (C.c_float*3)()
     check(lib().nmc_measure_peaks(int(device), out))
     return float(out[0]), float(out[1]), float(out[2])
+
+
+def bessel_table():
+    """(coef[n, 4, 4], t0, per_octave) of the default mode's Bessel lookup table (host-only call)."""
+    L = lib()
+    L.nmc_bessel_table.argtypes = [_fp, C.c_int, _fp, C.POINTER(C.c_int)]
+    t0, po = C.c_float(), C.c_int()
+    n = L.nmc_bessel_table(None, 0, C.byref(t0), C.byref(po))
+    out = np.zeros((n, 4, 4), np.float32)
+    L.nmc_bessel_table(out.ctypes.data_as(_fp), out.size, None, None)
+    return out, float(t0.value), int(po.value)
 
 
 def _f32(a):

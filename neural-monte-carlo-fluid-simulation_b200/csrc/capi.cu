@@ -2,6 +2,7 @@
 #include "../../include/nmcfs.h"
 #include "nmc_device.h"
 #include "scene_build.h"
+#include "bessel_table.h"
 
 #include <cstdio>
 #include <cstring>
@@ -39,6 +40,14 @@ extern "C" int nmc_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
 	return n;
+}
+
+extern "C" int nmc_bessel_table(float* out, int capacity_floats, float* t0, int* per_octave) {
+	const BesselTable& T = besselTable();
+	if (t0) *t0 = T.t0;
+	if (per_octave) *per_octave = T.perOctave;
+	if (out) for (size_t i = 0; i < T.coef.size() && i < (size_t)(capacity_floats > 0 ? capacity_floats : 0); i++) out[i] = T.coef[i];
+	return T.n;
 }
 
 extern "C" uint64_t nmc_point_seed(uint64_t seed, uint64_t index) { return pointSeed(seed, index); }

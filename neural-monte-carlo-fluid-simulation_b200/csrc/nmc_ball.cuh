@@ -282,6 +282,33 @@ NMC_OUTLINE Bessel4 besselScaled(float x) {
 	return b;
 }
 
+#if defined(NMC_BESSEL_TAB) && defined(__CUDACC__)
+// Default mode on the device: the same four functions from a table of cubic pieces in t = log2(x) (bessel_table.cpp),
+// one code path for every x, so the lanes of a warp do not split over the polynomial regimes above.  Only ONE
+// translation unit may define NMC_BESSEL_TAB (wost_fast.cu): it owns cBesselTab and fills it (ensureBesselTable).
+struct BesselTabView { const float4* c; float t0, perOctave; int n; };
+__constant__ BesselTabView cBesselTab;
+#endif
+#if defined(NMC_BESSEL_TAB) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ Bessel4 besselScaledTab(const BesselTabView& tab, float x) {
+	const float u = (__log2f(x) - tab.t0)*tab.perOctave;
+	if (!(u >= 0.0f && u < (float)tab.n)) return besselScaled(x); // outside the table: the polynomials (cold path)
+	const int i = (int)u;
+	const float f = u - (float)i;
+	const float4* c = tab.c + 4*i;
+	const float4 a = __ldg(c), b = __ldg(c + 1), k = __ldg(c + 2), l = __ldg(c + 3);
+	Bessel4 r;
+	r.i0e = fmaf(fmaf(fmaf(a.w, f, a.z), f, a.y), f, a.x);
+	r.i1e = fmaf(fmaf(fmaf(b.w, f, b.z), f, b.y), f, b.x);
+	r.k0e = fmaf(fmaf(fmaf(k.w, f, k.z), f, k.y), f, k.x);
+	r.k1e = fmaf(fmaf(fmaf(l.w, f, l.z), f, l.y), f, l.x);
+	return r;
+}
+#define NMC_BESSEL4(x) besselScaledTab(cBesselTab, (x))
+#else
+#define NMC_BESSEL4(x) besselScaled(x)
+#endif
+
 // BallFast: centred ball Green's function written in x = r*mu, X = R*mu (mu = sqrt(lambda)):
 //   2D  G = g(x)/(2 pi),       g = K0(x) - I0(x) K0(X)/I0(X)        T = x [K1(x) + I1(x) K0(X)/I0(X)]
 //   3D  G = mu g(x)/(4 pi x),  g = sinh(X - x)/sinh X               T = [x cosh(X - x) + sinh(X - x)]/sinh X
@@ -308,7 +335,7 @@ struct BallFast {
 		if (!yukawa) { TX = 1.0f; oneMinusTX = 0.0f; bdyFac = (DIM == 2 ? 2.0f : 3.0f)/R; return; }
 		X = R*mu;
 		if (DIM == 2) {
-			Bessel4 b = besselScaled(X);
+			Bessel4 b = NMC_BESSEL4(X);
 			ratio0 = b.k0e/b.i0e; ratio1 = b.k1e/b.i1e;
 			TX = __expf(-X)/b.i0e;                       // 1/I0(X)
 			oneMinusTX = X < 0.25f ? X*X*0.25f*(1.0f - X*X*(3.0f/16.0f)*(1.0f - X*X*(19.0f/108.0f))) : 1.0f - TX;
@@ -329,7 +356,7 @@ struct BallFast {
 	// T(x), g(x) and q(x) = K1(x) - I1(x) K1(X)/I1(X) (2D) / K32(x) - I32(x) K32(X)/I32(X) (3D), 0 < x <= X
 	NMC_HD void evalTgq(float x, float& T, float& g, float& q) const {
 		if (DIM == 2) {
-			Bessel4 b = besselScaled(x);
+			Bessel4 b = NMC_BESSEL4(x);
 			float em = __expf(-x), e2 = __expf(x - 2.0f*X);
 			float ep = ratio0*e2;
 			T = x*(b.k1e*em + b.i1e*ep);

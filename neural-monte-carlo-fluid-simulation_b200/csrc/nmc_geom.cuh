@@ -549,10 +549,14 @@ NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, f
 	if (found) dOut = sqrtf(r2);
 	return found;
 }
+#ifndef NMC_RAY_UNROLL
+#define NMC_RAY_UNROLL 1
+#endif
 template <int DIM>
 NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 	constexpr int G = FlatGroup<DIM>::n;
-	int best = -1; float bu = 0.0f, bv = 0.0f;
+	constexpr int kRayUnroll = DIM == 3 ? NMC_RAY_UNROLL : 1; // 3D: the plane-form test is branch-free, unrolling buys instruction-level parallelism
+	int best = -1; float bu = 0.0f;
 	// slab test of the ray segment [0, tMax] against each group's box (fminf/fmaxf drop the NaN of 0*inf).
 	// Lanes shoot different rays: each lane first collects the groups ITS ray can reach, then walks its own
 	// list, so a warp pays for the longest list and not for the union of the lanes' groups.
@@ -580,7 +584,7 @@ NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 		const int g = lowestBit(todo), g0 = g*G;
 		todo &= todo - 1u;
 		if (cull && best >= 0 && !reach(2*g, tMax)) continue; // the ray got shorter since the list was made
-#pragma unroll 1
+#pragma unroll kRayUnroll
 		for (int j = 0; j < G; j++) {
 			const int i = g0 + j;
 			if (DIM == 2) { // LineSegment::intersect (line_segments.inl:96-140); the division only runs for hits
@@ -594,30 +598,23 @@ NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 					const float s = a*inv, t = b*inv;
 					if (s >= 0.0f && s <= 1.0f && t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = s; }
 				}
-			} else { // Triangle::intersect (triangles.inl:96-160)
-				const V3 pa = xyz(F.rayP[3*i]), v1 = xyz(F.rayP[3*i + 1]), v2 = xyz(F.rayP[3*i + 2]);
-				const V3 p = cross(dir, v2);
-				const float det = dot(v1, p);
-				if (fabsf(det) <= kEps) continue;
-				const float inv = 1.0f/det;
-				const V3 sv = o - pa;
-				const float v = dot(sv, p)*inv;
-				if (v < 0.0f || v > 1.0f) continue;
-				const V3 qv = cross(sv, v1);
-				const float w = dot(dir, qv)*inv;
-				if (w < 0.0f || v + w > 1.0f) continue;
-				const float t = dot(v2, qv)*inv;
-				if (t >= 0.0f && t <= tMax) { tMax = t; best = i; bu = v; bv = w; }
+			} else { // Triangle::intersect (triangles.inl:219-256) in plane form (record layout: scene_build.cpp), branch-free
+				const float4 r0 = F.rayP[3*i], r1 = F.rayP[3*i + 1], r2 = F.rayP[3*i + 2];
+				const float den = fmaf(r0.x, dir.x, fmaf(r0.y, dir.y, r0.z*dir.z));
+				const float sd = fmaf(r0.x, o.x, fmaf(r0.y, o.y, fmaf(r0.z, o.z, r0.w)));
+				const float t = -sd*(1.0f/den);
+				const float px = fmaf(t, dir.x, o.x), py = fmaf(t, dir.y, o.y), pz = fmaf(t, dir.z, o.z);
+				const float v = fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w)));
+				const float w = fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w)));
+				const bool ok = (fabsf(den) > kEps) & (t >= 0.0f) & (t <= tMax) & (v >= 0.0f) & (w >= 0.0f) & (v + w <= 1.0f);
+				tMax = ok ? t : tMax; best = ok ? i : best;
 			}
 		}
 	}
 	if (best < 0) return false;
 	out.d = tMax; out.ref = best; out.n = xyz(F.rayN[best]);
 	if (DIM == 2) { const float4 q = F.rayP[best]; out.p = mk(q.x + bu*q.z, q.y + bu*q.w, 0.0f); out.u = bu; out.v = -1.0f; }
-	else {
-		const V3 pa = xyz(F.rayP[3*best]), v1 = xyz(F.rayP[3*best + 1]), v2 = xyz(F.rayP[3*best + 2]);
-		out.p = (pa + v1*bu) + v2*bv; out.u = 1.0f - bu - bv; out.v = bu;
-	}
+	else { out.p = mk(fmaf(tMax, dir.x, o.x), fmaf(tMax, dir.y, o.y), fmaf(tMax, dir.z, o.z)); out.u = 0.0f; out.v = 0.0f; } // barycentrics are not used by the walk
 	return true;
 }
 

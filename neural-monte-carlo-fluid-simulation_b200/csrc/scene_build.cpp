@@ -416,13 +416,28 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 	groupBoxes(out.silsU, dim == 2 ? 2 : 4, out.nSilU, dim == 2 ? 1 : 2, out.grpS); // 2D: the vertex; 3D: both edge end points
 
 	// scan-friendly records (after the boxes, which need the end points):
-	//  * ray primitives become (origin, edge vectors): 2D (pa.xy, pb - pa), 3D (pa)(pb - pa)(pc - pa);
+	//  * ray primitives: 2D (origin, edge vector) = (pa.xy, pb - pa); 3D plane form (N, d0)(A, d1)(B, d2), see below;
 	//  * both lists are padded to a whole number of groups with records no query can accept (a silhouette at
 	//    infinity, a degenerate primitive), so the scans run fixed-trip inner loops;
 	if (dim == 2) for (int i = 0; i < out.nRay; i++) { Q4& q = out.rayP[i]; q.z -= q.x; q.w -= q.y; }
 	else for (int i = 0; i < out.nRay; i++) {
+		// 3D: plane form.  With v1 = pb - pa, v2 = pc - pa, N = v1 x v2 (not normalised), A = (v2 x N)/|N|^2, B = (N x v1)/|N|^2:
+		//   t = -(N.o + d0)/(N.dir),  P = o + t dir,  P = pa + v v1 + w v2 with v = A.P + d1, w = B.P + d2
+		// (d0 = -N.pa, d1 = -A.pa, d2 = -B.pa): 15 FMA + 1 reciprocal per triangle and no branches, against two cross
+		// products and three early exits for the Moeller-Trumbore form of Triangle::intersect (triangles.inl:219-256).
+		// A degenerate triangle gives N = 0: the denominator test rejects it.  Evaluated in double, stored in float.
 		Q4 &a = out.rayP[3*i], &b = out.rayP[3*i + 1], &c = out.rayP[3*i + 2];
-		b.x -= a.x; b.y -= a.y; b.z -= a.z; c.x -= a.x; c.y -= a.y; c.z -= a.z;
+		const double pa[3] = {a.x, a.y, a.z}, v1[3] = {(double)b.x - a.x, (double)b.y - a.y, (double)b.z - a.z},
+					 v2[3] = {(double)c.x - a.x, (double)c.y - a.y, (double)c.z - a.z};
+		const double N[3] = {v1[1]*v2[2] - v1[2]*v2[1], v1[2]*v2[0] - v1[0]*v2[2], v1[0]*v2[1] - v1[1]*v2[0]};
+		const double nn = N[0]*N[0] + N[1]*N[1] + N[2]*N[2];
+		if (nn > 0.0) {
+			const double A[3] = {(v2[1]*N[2] - v2[2]*N[1])/nn, (v2[2]*N[0] - v2[0]*N[2])/nn, (v2[0]*N[1] - v2[1]*N[0])/nn};
+			const double Bv[3] = {(N[1]*v1[2] - N[2]*v1[1])/nn, (N[2]*v1[0] - N[0]*v1[2])/nn, (N[0]*v1[1] - N[1]*v1[0])/nn};
+			a = {(float)N[0], (float)N[1], (float)N[2], (float)-(N[0]*pa[0] + N[1]*pa[1] + N[2]*pa[2])};
+			b = {(float)A[0], (float)A[1], (float)A[2], (float)-(A[0]*pa[0] + A[1]*pa[1] + A[2]*pa[2])};
+			c = {(float)Bv[0], (float)Bv[1], (float)Bv[2], (float)-(Bv[0]*pa[0] + Bv[1]*pa[1] + Bv[2]*pa[2])};
+		} else { a = {0, 0, 0, 0}; b = {0, 0, 0, 0}; c = {0, 0, 0, 0}; }
 	}
 	//  * silhouettes are rewritten for a two-stage test.  Both faces of a silhouette vertex / edge contain it, so
 	//    dot(x - p, n_k) is the signed distance of x to the plane of face k: s_k(x) = n_k.x + c_k with c_k = -n_k.p.
@@ -456,8 +471,8 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 		else { out.silsU.push_back({0, 0, 0, 1.0f}); out.silsU.push_back({0, 0, 0, 1.0f}); out.silsU.push_back({far, far, far, bits(3)}); out.silsU.push_back({far, far, far, 0.0f}); }
 	}
 	for (int i = out.nRay; i % G != 0; i++) {
-		out.rayP.push_back({far, far, 0.0f, 0.0f}); // zero edge vectors: determinant 0, rejected
-		if (dim == 3) { out.rayP.push_back({0, 0, 0, 0}); out.rayP.push_back({0, 0, 0, 0}); }
+		if (dim == 2) out.rayP.push_back({far, far, 0.0f, 0.0f}); // zero edge vector: determinant 0, rejected
+		else { out.rayP.push_back({0, 0, 0, 0}); out.rayP.push_back({0, 0, 0, 0}); out.rayP.push_back({0, 0, 0, 0}); } // N = 0: rejected
 		out.rayN.push_back({0, 0, 0, 0});
 	}
 }

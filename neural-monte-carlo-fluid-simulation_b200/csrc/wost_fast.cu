@@ -25,8 +25,13 @@
 // antithetic pairing and control variates; the radial sample is drawn by inverting the CDF that the
 // reference's rejection sampler targets.
 #define NMC_FAST_GEOM 1
+#ifndef NMC_NO_BESSEL_TAB
+#define NMC_BESSEL_TAB 1
+#endif
 #include "nmc_device.h"
+#include "bessel_table.h"
 #include "../../include/nmcfs.h"
+#include <mutex>
 
 namespace nmc {
 
@@ -44,18 +49,30 @@ __device__ __forceinline__ unsigned warpSumU(unsigned v) {
 }
 
 enum LaneState { kNeedPair = 0, kWalking = 2, kIdle = 3 };
-static constexpr int kFbFields = 9; // first-ball record per pair: d0.xyz, e0.xyz, firstSource (walk 0), firstSource (twin), sfr
+// first-ball record per pair: d0.xyz, e0.xyz, firstSource (walk 0), firstSource (twin), sfr, the pair's control variates (bcv, scv)
+static constexpr int kFbFields = 11;
 
-#ifndef NMC_MINB
-#define NMC_MINB 8   // 64 registers/thread, 32 warps/SM: measured best on B200 (profiles/README.md)
+// resident CTAs per SM the compiler must allow for: 2D 6 (80 registers/thread: the Bessel code spills less), 3D 7
+// (72 registers) -- measured on B200 against 8 (64 registers): profiles/README.md, r02 A/B table
+#ifdef NMC_MINB
+#define NMC_MINB2 NMC_MINB
+#define NMC_MINB3 NMC_MINB
+#endif
+#ifndef NMC_MINB2
+#define NMC_MINB2 6
+#endif
+#ifndef NMC_MINB3
+#define NMC_MINB3 7
 #endif
 __device__ __forceinline__ void stackInit(StridedStack& s, int* base, int slots) {
 	s.nodes = base + threadIdx.x; s.dists = reinterpret_cast<float*>(base + slots*kBlock) + threadIdx.x; s.stride = kBlock;
 }
 __device__ __forceinline__ void stackInit(LocalStack&, int*, int) {}
 
-template <int DIM, class STACK, bool FLAT>
-__global__ void __launch_bounds__(kBlock, NMC_MINB)
+// STATS: the per-point statistics record of the parity tests (variances, mean walk length) costs five more
+// accumulators per lane; the product path (stats12 == nullptr) runs the instantiation without them.
+template <int DIM, class STACK, bool FLAT, bool STATS>
+__global__ void __launch_bounds__(kBlock, DIM == 2 ? NMC_MINB2 : NMC_MINB3)
 fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
 		   float* __restrict__ pOut, float* __restrict__ gOut, unsigned int* __restrict__ workCounter,
 		   Counters* __restrict__ counters, float* __restrict__ stats12, int stageQuads, int stackSlots) {
@@ -151,7 +168,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 			bool onNeumann = false;
 			Pcg32 rng; rng.state = 0; rng.inc = 1;
 			unsigned long long walkSeed = 0;
-			V3 pt = x0, normal = mk(0, 0, 0), d0 = mk(0, 0, 0), e0 = mk(0, 0, 0), prevDir = mk(0, 0, 0);
+			V3 pt = x0, normal = mk(0, 0, 0), d0 = mk(0, 0, 0), e0 = mk(0, 0, 0);
+		bool flipNext = false; // double-sided boundaries: the walk arrived on the back side of the face it sits on
 			float throughput = 1.0f, totalSource = 0.0f, firstSource = 0.0f, sfr = 0.0f, bcv = 0.0f, scv = 0.0f;
 			BallFast<DIM> bl = fb;
 
@@ -171,13 +189,24 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 					const int lastNeeded = nAnti == 2 ? (lastW + 1) >> 1 : lastW;                      // pairs, exclusive
 					const bool want = state == kNeedPair && mineW < nWalksPt;
 					bool fetched = false;
+					// Control variates = running means over the walks finished so far (walk_on_stars.h:501-506), fixed ONCE per
+					// pair as in the reference: the lane that takes a pair's first walk parks them next to the pair's first-ball
+					// samples and the twin reads them, so a twin handed out in a later refill does not see a mean that already
+					// contains its partner's (correlated) total.
+					const float icnt_ = 1.0f/fmaxf(cvCnt, 1.0f);
+					const float bcvNow = o.useGradientControlVariates ? cvTot*icnt_ : 0.0f, scvNow = o.useGradientControlVariates ? cvFirst*icnt_ : 0.0f;
 #define NMC_FETCH_FIRST_BALL(slot) do { const int sl_ = (slot); \
 						d0 = mk(fbuf[sl_], fbuf[32 + sl_], DIM == 3 ? fbuf[64 + sl_] : 0.0f); \
 						e0 = mk(fbuf[96 + sl_], fbuf[128 + sl_], DIM == 3 ? fbuf[160 + sl_] : 0.0f); \
-						firstSource = fbuf[(myAnti ? 224 : 192) + sl_]; sfr = fbuf[256 + sl_]; fetched = true; } while (0)
+						firstSource = fbuf[(myAnti ? 224 : 192) + sl_]; sfr = fbuf[256 + sl_]; \
+						if (myAnti == 0) { fbuf[288 + sl_] = bcvNow; fbuf[320 + sl_] = scvNow; } fetched = true; } while (0)
 					if (want && mine < chunkEnd) NMC_FETCH_FIRST_BALL(mine - chunkBase);
+					bool cvTaken = false;
 					if (lastNeeded > chunkEnd) {
 						// ---- first-ball source samples of the next 32 pairs, one per lane, converged ---------------
+						__syncwarp();
+						// a twin served from the chunk that is about to be replaced takes its pair's control variates with it
+						if (want && fetched && myAnti == 1) { bcv = fbuf[288 + mine - chunkBase]; scv = fbuf[320 + mine - chunkBase]; cvTaken = true; }
 						__syncwarp();
 						chunkBase = chunkEnd; chunkEnd = chunkBase + 32 < nPairs ? chunkBase + 32 : nPairs;
 						const int cp = chunkBase + lane;
@@ -216,17 +245,15 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						if (want && !fetched) NMC_FETCH_FIRST_BALL(mine - chunkBase);
 					}
 #undef NMC_FETCH_FIRST_BALL
+					__syncwarp();
 					if (state == kNeedPair) {
 						if (want) {
 							pair = mine; anti = myAnti;
-							if (o.useGradientControlVariates) { // running means over the walks finished so far
-								float icnt = 1.0f/fmaxf(cvCnt, 1.0f);
-								bcv = cvTot*icnt; scv = cvFirst*icnt;
-							}
+							if (myAnti == 0) { bcv = bcvNow; scv = scvNow; }
+							else if (!cvTaken) { bcv = fbuf[288 + mine - chunkBase]; scv = fbuf[320 + mine - chunkBase]; }
 							walkSeed = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(pair + 1)));
 							// start from the boundary sample, mirrored for the antithetic twin (:564-567), same walk stream (:579)
-							prevDir = anti ? neg(e0) : e0;
-							pt = x0 + prevDir; normal = mk(0, 0, 0); onNeumann = false; walkLength = 0;
+							pt = x0 + (anti ? neg(e0) : e0); normal = mk(0, 0, 0); onNeumann = false; flipNext = false; walkLength = 0;
 							throughput = exitT; totalSource = firstSource;
 							rng.state = walkSeed; rng.inc = 1;
 							bl = fb;
@@ -249,7 +276,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 					if (!(dirichletDist > o.epsilonShell)) { terminated = true; completed = true; }
 					else {
 						bool flipOrient = false;
-						if (S.doubleSided && onNeumann && dot(prevDir, normal) < 0.0f) { normal = normal*-1.0f; flipOrient = true; } // :154-160
+						if (S.doubleSided && onNeumann && flipNext) { normal = normal*-1.0f; flipOrient = true; } // :154-160
 						float starR;
 						if (o.stepsBeforeUsingMaximalSpheres <= walkLength) starR = dirichletDist;
 						else {
@@ -308,7 +335,8 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							// walk can no longer be stopped by Russian roulette and is eventually discarded
 							// (distributions.h:669-677, 801-813).
 							if (bl.yukawa && fmaxf(1e-4f, hit ? idist : bl.R)*bl.mu > (DIM == 2 ? 91.9063f : 103.9f)) terminated = true;
-							pt = ipt; normal = inrm; onNeumann = hit; prevDir = dir;
+							flipNext = hit && dot(dir, inrm) < 0.0f; // what dot(prevDirection, currentNormal) < 0 will say at the next step (:154-160)
+							pt = ipt; normal = inrm; onNeumann = hit;
 							if (!(throughput == throughput)) { terminated = true; } // NaN guard: discard
 							if (!terminated && throughput < o.russianRouletteThreshold) {
 								if (throughput/o.russianRouletteThreshold < uRR) { throughput = 0.0f; terminated = true; completed = true; }
@@ -327,10 +355,10 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							float sgn = anti == 0 ? 1.0f : -1.0f;
 							float bE = (total - firstSource - bcv)*bfr*sgn, sE = (firstSource - scv)*sfr*sgn;
 							float g0 = bE*e0.x + sE*d0.x, g1 = bE*e0.y + sE*d0.y, g2 = bE*e0.z + sE*d0.z;
-							sTot += total; sTot2 += total*total; sFirst += firstSource;
+							sTot += total; sFirst += firstSource;
 							sG[0] += g0; sG[1] += g1; sG[2] += g2;
-							sG2[0] += g0*g0; sG2[1] += g1*g1; sG2[2] += g2*g2;
-							nDone++; lenSum += (unsigned)walkLength;
+							nDone++;
+							if (STATS) { sTot2 += total*total; sG2[0] += g0*g0; sG2[1] += g1*g1; sG2[2] += g2*g2; lenSum += (unsigned)walkLength; }
 							pendTot += total; pendCnt += 1.0f; pendFirst += firstSource;
 						}
 						state = kNeedPair;
@@ -341,12 +369,13 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		}
 
 		// ---- reduce the per-lane sums and write the point's estimate -------------------------------------
-		float tot = warpSum(sTot), tot2 = warpSum(sTot2), first = warpSum(sFirst);
+		float tot = warpSum(sTot), first = warpSum(sFirst);
 		float g0 = warpSum(sG[0]), g1 = warpSum(sG[1]), g2 = warpSum(sG[2]);
 		unsigned cnt = warpSumU(nDone);
 		cCompleted += lane == 0 ? cnt : 0u;
 		float inv = 1.0f/(float)(cnt > 0u ? cnt : 1u);
-		if (stats12) {
+		if (STATS && stats12) {
+			float tot2 = warpSum(sTot2);
 			float q0 = warpSum(sG2[0]), q1 = warpSum(sG2[1]), q2 = warpSum(sG2[2]);
 			unsigned len = warpSumU(lenSum);
 			if (lane == 0) {
@@ -380,12 +409,40 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	}
 }
 
+#if defined(NMC_BESSEL_TAB)
+// uploads the Bessel table to the current device once and points cBesselTab at it
+static cudaError_t ensureBesselTable() {
+	static std::mutex mu;
+	static const float4* ptr[64] = {};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	std::lock_guard<std::mutex> lock(mu);
+	if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+	if (ptr[dev]) return cudaSuccess;
+	const BesselTable& T = besselTable();
+	float4* d = nullptr;
+	e = cudaMalloc((void**)&d, T.coef.size()*sizeof(float));
+	if (e != cudaSuccess) return e;
+	e = cudaMemcpy(d, T.coef.data(), T.coef.size()*sizeof(float), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cudaFree(d); return e; }
+	BesselTabView v; v.c = d; v.t0 = T.t0; v.perOctave = (float)T.perOctave; v.n = T.n;
+	e = cudaMemcpyToSymbol(cBesselTab, &v, sizeof(v));
+	if (e != cudaSuccess) { cudaFree(d); return e; }
+	ptr[dev] = d;
+	return cudaSuccess;
+}
+#endif
+
 cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d_pts, long long n,
 					   unsigned long long indexOffset, float* d_p, float* d_g, unsigned int* d_workCounter,
 					   Counters* d_counters, float* d_stats12, int smCount, int maxDepth, cudaStream_t stream, FastLaunchInfo* info) {
 	if (n <= 0) return cudaSuccess;
 	if (n >= (1ll << 32) - 65536) return cudaErrorInvalidValue;
 	const int dim = S.dim;
+#if defined(NMC_BESSEL_TAB)
+	if (dim == 2) { cudaError_t eb = ensureBesselTable(); if (eb != cudaSuccess) return eb; }
+#endif
 	// small scenes are scanned flat (no per-step tree traversal); the flat kernels stage every table in shared memory
 	// unconditionally, so a scene whose tables do not fit the 48 KB stage falls back to the tree kernels
 	bool flat = S.nPrims <= 128 && S.nSilU <= 128; // <= 43 KB of tables (asserted by tests/test_host_logic.py)
@@ -405,9 +462,15 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (!smemStack) stackSlots = 0; // LocalStack: the first-ball chunks sit right behind the staged scene
 	size_t smem = (stageQuads ? bytes : 0) + (size_t)stackSlots*kBlock*8 + (size_t)kWarps*kFbFields*32*sizeof(float);
 	void (*kern)(SceneView, SolverParams, const float*, long long, unsigned long long, float*, float*, unsigned int*, Counters*, float*, int, int);
-	if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true> : fastKernel<3, StridedStack, true>;
-	else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false> : fastKernel<2, LocalStack, false>;
-	else kern = smemStack ? fastKernel<3, StridedStack, false> : fastKernel<3, LocalStack, false>;
+	if (d_stats12) {
+		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true, true> : fastKernel<3, StridedStack, true, true>;
+		else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false, true> : fastKernel<2, LocalStack, false, true>;
+		else kern = smemStack ? fastKernel<3, StridedStack, false, true> : fastKernel<3, LocalStack, false, true>;
+	} else {
+		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true, false> : fastKernel<3, StridedStack, true, false>;
+		else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false, false> : fastKernel<2, LocalStack, false, false>;
+		else kern = smemStack ? fastKernel<3, StridedStack, false, false> : fastKernel<3, LocalStack, false, false>;
+	}
 	if (flat && (!smemStack || stageQuads == 0)) return cudaErrorInvalidConfiguration; // cannot happen: <= 128 primitives give a shallow tree, and see above
 	int perSM = 0;
 	cudaError_t e = cudaSuccess;

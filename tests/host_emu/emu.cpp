@@ -134,6 +134,26 @@ extern "C" void emu_rays(void* h, const float* o, const float* d, const float* t
 	}
 }
 
+// the same with the walk's on-boundary convention: origin offset against the normal (wost_fast.cu phase 1 /
+// intersectNeumann); out additionally carries the hit point
+extern "C" void emu_rays_onb(void* h, const float* o, const float* nrm, const float* d, const float* tmax, int n, float* outFlat, float* outTree) {
+	EmuScene* s = (EmuScene*)h;
+	FlatTab F = flatTab(s);
+	const int D = s->v.dim;
+	for (int i = 0; i < n; i++) {
+		V3 pt = mk(o[D*i], o[D*i + 1], D == 3 ? o[D*i + 2] : 0.0f), dir = mk(d[D*i], d[D*i + 1], D == 3 ? d[D*i + 2] : 0.0f);
+		V3 nn = mk(nrm[D*i], nrm[D*i + 1], D == 3 ? nrm[D*i + 2] : 0.0f);
+		Hit a; a.d = kMaxF; a.p = mk(0, 0, 0); a.n = mk(0, 0, 0);
+		Hit b = a;
+		V3 ro = D == 2 ? offsetPoint<2>(pt, neg(nn)) : offsetPoint<3>(pt, neg(nn));
+		bool ha = D == 2 ? flatRay<2>(F, ro, dir, tmax[i], a) : flatRay<3>(F, ro, dir, tmax[i], a);
+		bool hb = D == 2 ? intersectNeumann<2>(s->v, pt, nn, dir, tmax[i], true, b) : intersectNeumann<3>(s->v, pt, nn, dir, tmax[i], true, b);
+		float* x = outFlat + 8*i; float* y = outTree + 8*i;
+		x[0] = ha; x[1] = ha ? a.d : 0.0f; x[2] = a.n.x; x[3] = a.n.y; x[4] = a.n.z; x[5] = a.p.x; x[6] = a.p.y; x[7] = a.p.z;
+		y[0] = hb; y[1] = hb ? b.d : 0.0f; y[2] = b.n.x; y[3] = b.n.y; y[4] = b.n.z; y[5] = b.p.x; y[6] = b.p.y; y[7] = b.p.z;
+	}
+}
+
 extern "C" void emu_dist_neumann(void* h, const float* pts, int n, int signedDist, float* out) {
 	EmuScene* s = (EmuScene*)h;
 	const int D = s->v.dim;

@@ -160,17 +160,25 @@ def test_fused_envelope_matches_reference_query_velocity(siren, shape):
     assert (ytc - yr).abs().max().item() <= 1e-4*scale
 
 
-@pytest.mark.parametrize("scenario", ["karman", "smoke_obs"])
+@pytest.mark.parametrize("scenario", ["karman", "smoke_obs", "karman3d", "smoke"])
 def test_general_envelope_matches_reference_query_velocity(siren, scenario):
-    """The karman (base.py:169-181) and smoke_obs (3d base.py:224-244) branches of query_velocity inside the kernels:
+    """The karman (base.py:169-181), smoke_obs (3d base.py:224-244), karman3d (3d base.py:257-275, cylinder of 3d
+    main.py:92-98) and smoke (3d base.py:197-222, per-step inlet noise) branches of query_velocity inside the kernels:
     region override, obstacle weight (NOT detached: its gradient reaches x), wall weights; forward on both kernels
     and backward against stock autograd on the torch transcription of the reference (siren.envelope_reference)."""
     if scenario == "karman":
         shape, size, eps = (2, 128, 2, 2), (-1.0, 1.0, -0.4, 0.4), 0.15
         env = siren.karman_envelope(size, eps, centre=(-0.3, 0.05), radius=0.12, karman_vel=0.5)
-    else:
+    elif scenario == "smoke_obs":
         shape, size, eps = (3, 64, 5, 3), (-1.0, 1.0)*3, 0.2
         env = siren.smoke_obs_envelope(size, eps, centre=(0.1, 0.0, 0.2), radius=0.25, inlet_centre=(0.0, 0.0, -0.6), inlet_radius=0.3)
+    elif scenario == "karman3d":
+        shape, size, eps = (3, 128, 2, 3), (-1.0, 1.0)*3, 0.2
+        env = siren.karman3d_envelope(size, eps, centre_xz=(0.1, -0.3), radius=0.25, karman_vel=0.5)
+    else:
+        shape, size, eps = (3, 64, 5, 3), (-1.0, 1.0)*3, 0.2
+        seed = torch.tensor([17], dtype=torch.int32, device="cuda")
+        env = siren.smoke_envelope(size, eps, seed, inlet_radius=0.45)
     dim = shape[0]
     net = _net(siren, shape, seed=41)
     lo = torch.tensor(size[0::2], device="cuda"); hi = torch.tensor(size[1::2], device="cuda")
@@ -184,17 +192,31 @@ def test_general_envelope_matches_reference_query_velocity(siren, scenario):
     grads_r = torch.autograd.grad((yr*w).sum() + (yr**2).sum(), [xr] + list(net.parameters()))
     scale = yr.abs().max().item()
     # every part of the envelope is exercised by the sample set
-    dist = torch.linalg.norm(x.detach() - torch.tensor([env.sphere_c[i] for i in range(dim)], device="cuda"), dim=-1) - env.sphere_r
-    assert ((dist > 0) & (dist < eps)).sum() > 100 and (dist < 0).sum() > 20
+    if scenario == "smoke":
+        inlet = torch.linalg.norm(x.detach() - torch.tensor([0.0, 0.0, -0.6], device="cuda"), dim=-1) < 0.45
+        assert inlet.sum() > 100
+        interior = inlet & (x.detach().abs() < 1 - eps).all(dim=-1)   # wall weights are 1 there: u = 0.1 * noise
+        un = yr.detach()[interior, 0]/0.1
+        assert interior.sum() > 100 and un.min() < -0.9 and un.max() > 0.9 and abs(un.mean().item()) < 0.2   # uniform in [-1, 1)
+        assert torch.allclose(yr.detach()[interior, 2], 0.2 + 0.1*un, atol=1e-6)
+        seed.fill_(18)   # the next time step draws new noise (the kernels read the seed from device memory)
+        y2 = net(x.detach(), envelope=env)
+        assert (y2[inlet] - y.detach()[inlet]).abs().max().item() > 0.05 and torch.equal(y2[~inlet], y.detach()[~inlet])
+        seed.fill_(17)
+    else:
+        sel = torch.tensor([float(((env.sphere_axes or 7) >> i) & 1) for i in range(dim)], device="cuda")
+        dist = torch.linalg.norm((x.detach() - torch.tensor([env.sphere_c[i] for i in range(dim)], device="cuda"))*sel, dim=-1) - env.sphere_r
+        assert ((dist > 0) & (dist < eps)).sum() > 100 and (dist < 0).sum() > 20
     assert (y - yr).abs().max().item() <= 3e-5*scale
     gx, gxr = grads[0], grads_r[0]
     assert (gx - gxr).abs().max().item() <= 5e-4*gxr.abs().max().item() + 1e-9
     for a, b in zip(grads[1:], grads_r[1:]):
         assert (a - b).abs().max().item() <= 5e-4*b.abs().max().item() + 1e-9
     # the obstacle weight contributes to dL/dx: without it the input gradient would be off by far more than the tolerance
-    yd = siren.envelope_reference(env, xr, net.forward_reference(xr).detach())
-    gobs = torch.autograd.grad((yd*w).sum() + (yd**2).sum(), xr)[0]
-    assert gobs.abs().max().item() > 50*5e-4*gxr.abs().max().item()
+    if scenario != "smoke":
+        yd = siren.envelope_reference(env, xr, net.forward_reference(xr).detach())
+        gobs = torch.autograd.grad((yd*w).sum() + (yd**2).sum(), xr)[0]
+        assert gobs.abs().max().item() > 50*5e-4*gxr.abs().max().item()
     with torch.no_grad():
         net.tensor_cores = True
         ytc = net(x.detach(), envelope=env)

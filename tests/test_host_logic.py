@@ -509,3 +509,25 @@ def test_default_mode_tree_queries_equal_the_oracle(emu_fast, oracle_lib, tmp_pa
         if both.any():
             assert (np.abs(out[both, 1] - ray[both, 1]) <= 2e-5*np.abs(ray[both, 1]) + 1e-6).all(), name
         emu_fast.emuf_scene_destroy(h); osc.close()
+
+
+def test_bessel_lookup_table_against_scipy():
+    """The default mode's table of i0e, i1e, k0e, k1e (cubic pieces in log2 x, csrc/bessel_table.cpp) against scipy's
+    exponentially scaled Bessel functions in double: relative error below 1e-6 (float evaluation of log2 x included) over the whole range a walk can reach
+    (x = r sqrt(lambda) from rClamp*sqrt(lambda) to beyond the reference's float overflow at 91.9)."""
+    from scipy import special
+    coef, t0, per_octave = util.package().capi.bessel_table()
+    n = coef.shape[0]
+    rng = np.random.default_rng(3)
+    t = t0 + rng.random(200000)*(n/per_octave)
+    x = np.exp2(t)
+    u = (np.log2(x.astype(np.float32)).astype(np.float32) - np.float32(t0))*np.float32(per_octave)   # the device's arithmetic
+    i = np.clip(u.astype(np.int32), 0, n - 1)
+    f = (u - i).astype(np.float32)
+    want = [special.ive(0, x), special.ive(1, x), special.kve(0, x), special.kve(1, x)]
+    for k in range(4):
+        c = coef[i, k]
+        got = ((c[:, 3]*f + c[:, 2])*f + c[:, 1])*f + c[:, 0]
+        rel = np.abs(got - want[k])/np.abs(want[k])
+        assert rel.max() < 1e-6, (k, rel.max(), x[rel.argmax()])
+    assert 2.0**t0 <= 1e-4*np.sqrt(350.0)/8 and 2.0**(t0 + n/per_octave) > 165.0   # rClamp*mu .. the Taylor-Green box
