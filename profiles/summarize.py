@@ -28,3 +28,27 @@ for r in rows[2:]:
     st = [(float(r[i] or 0), h) for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
     for v, h in sorted(st, reverse=True)[:8]:
         print("    %-40s %.3f" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
+
+
+def write_profile_json(report, workload, walks_per_launch, capture_name, path="profiles/walk_kernel_profile.json"):
+    """Adds the per-build figures bench.py quotes (roofline.traffic, roofline_issue) for the walk kernel in `report`."""
+    import json
+    import os
+    import re
+    m = re.search(r"fastKernel<(\d)", rows[2][hdr.index("Kernel Name")])
+    r = rows[2]
+    val = lambda k: float(r[hdr.index(k)].replace(",", ""))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = sum(val(k)*scale[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    prof = json.load(open(path)) if os.path.exists(path) else {}
+    prof["fastKernel<%s>" % m.group(1)] = {
+        "capture": capture_name, "workload": workload, "walks_per_launch": walks_per_launch,
+        "dram_bytes_per_launch": dram, "warp_inst_per_walk": val("smsp__inst_executed.sum")/walks_per_launch,
+        "active_lanes_per_inst": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "kernel_ms_under_ncu": val("gpu__time_duration.sum")*{"ms": 1.0, "us": 1e-3, "s": 1e3}[units[hdr.index("gpu__time_duration.sum")]]}
+    json.dump(prof, open(path, "w"), indent=1, sort_keys=True)
+
+
+if len(sys.argv) >= 5:  # summarize.py report.ncu-rep WORKLOAD WALKS_PER_LAUNCH CAPTURE_NAME  -> updates walk_kernel_profile.json
+    write_profile_json(sys.argv[1], sys.argv[2], float(sys.argv[3]), sys.argv[4])
