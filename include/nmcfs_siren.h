@@ -81,6 +81,18 @@ int nmc_siren_weight_grads(const nmc_siren_shape* shape, const float* x, int64_t
 int nmc_siren_forward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
 						 int64_t n, float* y, float* z_saved, const nmc_siren_envelope* env, void* stream);
 
+/* Tensor-core (tcgen05, 3xTF32) backward of a fit iteration, two launches with the contracts of the fp32 pair above:
+ * nmc_siren_backward_tc writes dZ (layout of nmc_siren_backward, including the out_dim rows of grad_y'); it does not
+ * produce A or grad_x (the weight-gradient kernel recomputes A = sin(w0 z) from z_saved while staging its operands).
+ * nmc_siren_weight_grads_tc accumulates every weight / bias gradient into the zero-filled gW / gb: hidden layers as
+ * H x H x batch tcgen05 GEMMs, first / last layer and bias sums on the FMA pipe.  n must be a multiple of 4; dZ, z_saved
+ * and the hidden layers' gW must be 16-byte aligned.  Errors (never another path) on unsupported shapes. */
+int nmc_siren_backward_tc(const nmc_siren_shape* shape, const float* const* W, const float* const* b, const float* x,
+						  int64_t n, const float* z_saved, const float* grad_y, float* dZ,
+						  const nmc_siren_envelope* env, void* stream);
+int nmc_siren_weight_grads_tc(const nmc_siren_shape* shape, const float* x, int64_t n, const float* dZ, const float* z_saved,
+							  float* const* gW, float* const* gb, void* stream);
+
 /* MSE loss of a fit iteration in one launch: diff = y - target, grad_y = dL/dy = diff * 2/count, *loss = mean(diff^2)
  * (count = n * out_dim floats; base.py:83-96 with the loss of model_split.py:113). */
 int nmc_mse_grad(const float* y, const float* target, int64_t count, float* diff, float* grad_y, float* loss, void* stream);

@@ -37,6 +37,15 @@ __device__ __forceinline__ float sinReduced(float x) {
 
 constexpr int kTile = 128;
 constexpr int kMaxLayers = 18;
+
+// -DNMC_TC_TRACE: CTA 0 / thread 0 stamps clock64() at the phase boundaries of its first tile (profiles/tools/tc_trace.py)
+#ifdef NMC_TC_TRACE
+__device__ long long g_trace[256];
+__device__ int g_traceN;
+#define TRACE(tag) do { if (blockIdx.x == 0 && tid == 0 && tile == blockIdx.x && tn < 127) { g_trace[2*tn] = (tag); g_trace[2*tn + 1] = clock64(); tn++; g_traceN = tn; } } while (0)
+#else
+#define TRACE(tag) do {} while (0)
+#endif
 constexpr int kNChunk = 64;   // output neurons per MMA group (UMMA N)
 
 struct Params {
@@ -138,9 +147,13 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 	};
 	if (nHidden >= 1 && (long long)blockIdx.x*kTile < n) loadW(1, 0);
 
+#ifdef NMC_TC_TRACE
+	int tn = 0;
+#endif
 	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
 		const long long s = tile*kTile + row;
 		const bool live = s < n;
+		TRACE(1);
 		{ // first layer on the FMA pipe, written straight into the A operand
 			float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
 			if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
@@ -164,11 +177,14 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
+				TRACE(2);
 				storeW();
+				TRACE(3);
 				// generic-proxy writes (A from the previous epilogue, B from above) -> visible to the tensor core
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncthreads();
+				TRACE(4);
 				if (tid == 0) {
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t d = tmemBase + (uint32_t)(nc*kNChunk);
@@ -185,15 +201,18 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 					// arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
 					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barAddr) : "memory");
 				}
+				TRACE(5);
 				{ // fetch the chunk that follows (this layer, the next layer, or the first one of the next tile) during the MMAs
 					int ln = l, ncn = nc + 1;
 					if (ncn == H/kNChunk) { ncn = 0; ln = l + 1; }
 					if (ln <= nHidden) loadW(ln, ncn);
 					else if ((tile + gridDim.x)*kTile < n) loadW(1, 0);
 				}
+				TRACE(6);
 				mbarWait(barAddr, phase);
 				phase ^= 1u;
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				TRACE(7);
 			}
 			// epilogue: this thread's row of the accumulator -> bias, sin, next layer's operand
 			for (int c0 = cBeg; c0 < cEnd; c0 += 16) {
@@ -229,6 +248,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 				}
 			}
 		}
+		TRACE(8);
 		if (half == 1) { ypart[0][row] = y0; ypart[1][row] = y1; ypart[2][row] = y2; } // the other half of this row's last-layer dot product
 		__syncthreads();
 		if (live && half == 0) {
@@ -245,6 +265,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		// the next tile's first layer overwrites A: every thread is past its last use (MMAs completed via the mbarrier)
 		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 		__syncthreads();
+		TRACE(9);
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
@@ -255,6 +276,16 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 
 extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* const* W, const float* const* b, const float* x,
 									int64_t n, float* y, float* z_saved, const nmc_siren_envelope* envp, void* stream);
+#ifdef NMC_TC_TRACE
+extern "C" int nmc_siren_trace_read(long long* out, int cap) { // (tag, clock) pairs of the last traced launch
+	int n = 0;
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(&n, g_traceN, sizeof(int));
+	if (n > cap) n = cap;
+	cudaMemcpyFromSymbol(out, g_trace, sizeof(long long)*2*n);
+	return n;
+}
+#endif
 
 namespace nmc_siren_detail { void setError(const char* m); }
 

@@ -9,6 +9,7 @@ first_layer_sine_init).  `forward` runs ONE CUDA kernel (csrc/siren.cu) instead 
 tensor-core kernel (csrc/siren_tc.cu) with `tensor_cores=True`.  CUDA tensors only: there is no CPU path.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -183,6 +184,8 @@ def _lib():
         L.nmc_siren_backward.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp,
                                          vp, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_weight_grads.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
+        L.nmc_siren_backward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, vp, C.POINTER(Envelope), vp]
+        L.nmc_siren_weight_grads_tc.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         L.nmc_adam_step_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
         L.nmc_mse_grad.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
@@ -443,6 +446,11 @@ class DirectFit:
         self.out = (take((H, self.sh.in_dim)), take((H,)), take((Lh, H, H)), take((Lh, H)), take((self.sh.out_dim, H)), take((self.sh.out_dim,)))
         assert off[0] == g.numel()
         self.z = torch.empty((Lh + 1)*H*max_batch, device=g.device)
+        # tensor-core backward (delta chain + weight gradients): on with the network's tensor_cores flag; NMC_SIREN_TC_BWD=0
+        # selects the fp32 kernels for A/B measurements
+        self.tc_backward = self.tensor_cores and os.environ.get("NMC_SIREN_TC_BWD", "1") != "0"
+        self.tc_backward_min = int(os.environ.get("NMC_SIREN_TC_BWD_MIN", "4096"))
+        self.dz = torch.empty(((Lh + 1)*H + self.sh.out_dim)*max_batch, device=g.device) if self.tc_backward else None
         self.max_batch = max_batch
         self.loss = torch.zeros((), device=g.device)  # mean squared error of the last iterate() call
 
@@ -461,9 +469,20 @@ class DirectFit:
         tgt = target.contiguous()
         with torch.cuda.device(x.device):  # diff, dL/dy and the loss in one launch
             _check(_lib().nmc_mse_grad(y.data_ptr(), tgt.data_ptr(), y.numel(), diff.data_ptr(), gy.data_ptr(), self.loss.data_ptr(), _stream()))
-        dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)
         self.opt.g.zero_()
-        _param_grads(sh, x, n, dZ, A, out=self.out)
+        if self.tc_backward and n >= self.tc_backward_min and n % 4 == 0 and sh.n_hidden_layers >= 1:
+            # tcgen05 delta chain + weight gradients (csrc/siren_tc_bwd.cu); the activations are recomputed from z
+            dZ = self.dz[: ((sh.n_hidden_layers + 1)*sh.hidden + sh.out_dim)*n]
+            gW0, gb0, gWh, gbh, gWl, gbl = self.out
+            gW = [gW0] + [gWh[i] for i in range(sh.n_hidden_layers)] + [gWl]
+            gb = [gb0] + [gbh[i] for i in range(sh.n_hidden_layers)] + [gbl]
+            with torch.cuda.device(x.device):
+                _check(_lib().nmc_siren_backward_tc(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
+                                                    dZ.data_ptr(), self.env, _stream()))
+                _check(_lib().nmc_siren_weight_grads_tc(C.byref(sh), x.data_ptr(), n, dZ.data_ptr(), z.data_ptr(), _ptrs(gW), _ptrs(gb), _stream()))
+        else:
+            dZ, A = _backward_chain(sh, self.W, self.b, x, n, z, gy, None, self.env)
+            _param_grads(sh, x, n, dZ, A, out=self.out)
         if self.world > 1:  # mean over the global batch = mean over ranks of the local means (equal shard sizes)
             import torch.distributed as dist
             dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG, group=self.group)
@@ -473,6 +492,7 @@ class DirectFit:
     def close(self):
         """Releases the scratch buffers; the network keeps its (flat-backed) parameters."""
         self.z = None
+        self.dz = None
         self.out = None
 
     def sync_parameters(self, src=0):

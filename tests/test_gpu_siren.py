@@ -304,3 +304,84 @@ def test_tensor_core_training_forward_equals_fp32_path(siren, shape):
     for p, q, r in zip(a.parameters(), b.parameters(), start):
         moved = (q - r).abs().max().item()
         assert (p - q).abs().max().item() <= 0.02*moved + 1e-8
+
+
+def _raw_backward(siren, net, x, gy, env, tc):
+    """dZ of the delta chain and the flat weight / bias gradients, through the C ABI, fp32 kernels or tcgen05 kernels."""
+    import ctypes as C
+    L = siren._lib()
+    lin = net._linears()
+    W = [m.weight.detach().contiguous() for m in lin]; b = [m.bias.detach().contiguous() for m in lin]
+    sh = siren._shape_of(W, 30.0)
+    n = x.shape[0]
+    H, Lh = sh.hidden, sh.n_hidden_layers
+    y = torch.empty((n, sh.out_dim), device=x.device)
+    z = torch.empty(((Lh + 1)*H, n), device=x.device)
+    siren._check(L.nmc_siren_forward(C.byref(sh), siren._ptrs(W), siren._ptrs(b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), env, siren._stream()))
+    dZ = torch.zeros(((Lh + 1)*H + sh.out_dim, n), device=x.device)
+    gW = [torch.zeros_like(w) for w in W]; gb = [torch.zeros_like(v) for v in b]
+    if tc:
+        siren._check(L.nmc_siren_backward_tc(C.byref(sh), siren._ptrs(W), siren._ptrs(b), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
+                                             dZ.data_ptr(), env, siren._stream()))
+        siren._check(L.nmc_siren_weight_grads_tc(C.byref(sh), x.data_ptr(), n, dZ.data_ptr(), z.data_ptr(), siren._ptrs(gW), siren._ptrs(gb), siren._stream()))
+    else:
+        A = torch.empty(((Lh + 1)*H, n), device=x.device)
+        siren._check(L.nmc_siren_backward(C.byref(sh), siren._ptrs(W), siren._ptrs(b), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
+                                          dZ.data_ptr(), A.data_ptr(), None, env, siren._stream()))
+        siren._check(L.nmc_siren_weight_grads(C.byref(sh), x.data_ptr(), n, dZ.data_ptr(), A.data_ptr(), siren._ptrs(gW), siren._ptrs(gb), siren._stream()))
+    torch.cuda.synchronize()
+    return dZ, gW, gb
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("n", [4096, 16384, 128*9 + 52, 60])
+@pytest.mark.parametrize("with_env", [False, True])
+def test_tensor_core_backward_matches_fp32_kernels_and_autograd(siren, shape, n, with_env):
+    """tcgen05 delta chain + weight gradients (csrc/siren_tc_bwd.cu, 3xTF32) vs the exact-fp32 kernels (every delta,
+    every gradient entry) and vs torch autograd through the reference's stock-op network (base.py:83-96)."""
+    if with_env and n not in (4096, 60):
+        pytest.skip("envelope covered at two batch sizes")
+    net = _net(siren, shape, seed=71)
+    x = _coords(n, shape[0], seed=72)
+    env = siren.wall_envelope((-1.0, 1.0)*shape[0], 0.1) if with_env else None
+    target = torch.sin(3*x[:, :1]).expand(-1, shape[3]).contiguous()
+    with torch.no_grad():
+        y = net(x, envelope=env)
+    gy = ((y - target)*(2.0/y.numel())).contiguous()
+    dZ32, gW32, gb32 = _raw_backward(siren, net, x, gy, env, tc=False)
+    dZtc, gWtc, gbtc = _raw_backward(siren, net, x, gy, env, tc=True)
+    H, Lh = shape[1], shape[2]
+    for l in range(Lh + 1):
+        a, b = dZtc[l*H:(l + 1)*H], dZ32[l*H:(l + 1)*H]
+        assert (a - b).abs().max().item() <= 2e-5*b.abs().max().item() + 1e-12, ("dZ", l, (a - b).abs().max().item(), b.abs().max().item())
+    assert torch.equal(dZtc[(Lh + 1)*H:], dZ32[(Lh + 1)*H:])
+    for l, (a, b) in enumerate(zip(gWtc, gW32)):
+        assert (a - b).abs().max().item() <= 3e-5*b.abs().max().item() + 1e-12, ("gW", l, (a - b).abs().max().item(), b.abs().max().item())
+    for l, (a, b) in enumerate(zip(gbtc, gb32)):
+        assert (a - b).abs().max().item() <= 3e-5*b.abs().max().item() + 1e-12, ("gb", l, (a - b).abs().max().item(), b.abs().max().item())
+    # torch autograd through stock ops
+    ref_out = siren.envelope_reference(env, x, net.forward_reference(x))
+    loss = ((ref_out - target)**2).mean()
+    lin = net._linears()
+    gr = torch.autograd.grad(loss, [m.weight for m in lin] + [m.bias for m in lin])
+    for a, r in zip(gWtc + gbtc, gr):
+        assert (a - r).abs().max().item() <= 2e-4*r.abs().max().item() + 1e-9, (tuple(a.shape), (a - r).abs().max().item(), r.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 6, 2), (3, 128, 2, 3)])
+def test_tensor_core_backward_in_direct_fit(siren, shape):
+    """DirectFit with the tcgen05 backward (default for tensor_cores networks) follows the fp32-kernel fit step for step."""
+    a = _net(siren, shape, seed=81, tensor_cores=True)
+    b = _net(siren, shape, seed=81, tensor_cores=False)
+    start = [p.detach().clone() for p in a.parameters()]
+    n = 4096
+    x = _coords(n, shape[0], seed=82)
+    target = torch.cos(x[:, :1]*2.0).repeat(1, shape[3])
+    fa = siren.DirectFit(a, 1e-4, None, max_batch=n)
+    fb = siren.DirectFit(b, 1e-4, None, max_batch=n)
+    assert fa.tc_backward and not fb.tc_backward
+    for _ in range(8):
+        fa.iterate(x, target); fb.iterate(x, target)
+    for p, q, r in zip(a.parameters(), b.parameters(), start):
+        moved = (q - r).abs().max().item()
+        assert (p - q).abs().max().item() <= 0.02*moved + 1e-8
