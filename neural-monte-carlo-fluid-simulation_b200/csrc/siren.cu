@@ -562,25 +562,59 @@ sirenWeightGrad(Params P, int inDim, int outDim, int nHidden, const float* __res
 	if (tid < RP) atomicAdd(&P.gb[l][tid], bsum);
 }
 
-// MSE loss of a fit iteration in one pass: diff = y - target, grad_y = diff * 2/count, loss = mean(diff^2).
-// One CTA (the fit batches hold at most a few 10^5 floats): no atomics, the loss needs no zero-fill.
-__global__ void __launch_bounds__(1024) mseGrad(const float* __restrict__ y, const float* __restrict__ target, long long count,
-												 float* __restrict__ diff, float* __restrict__ gy, float* __restrict__ loss) {
+// MSE loss of a fit iteration in one launch: diff = y - target, grad_y = diff * 2/count, loss = mean(diff^2).
+// A few CTAs (one SM moves ~100 bytes per clock: a single CTA took 10 us for 49152 floats), 16-byte accesses; every CTA
+// leaves its partial sum in a scratch slot, the last one to finish adds the slots in index order (deterministic) and
+// writes the loss, so nothing needs a zero-fill.  The scratch is per device context: calls are stream-ordered by the
+// callers (one fit at a time), not re-entrant across streams.
+constexpr int kMseBlocks = 32;
+__device__ float g_msePart[kMseBlocks];
+__device__ unsigned g_mseDone;
+__global__ void __launch_bounds__(512) mseGrad(const float* __restrict__ y, const float* __restrict__ target, long long count,
+												float* __restrict__ diff, float* __restrict__ gy, float* __restrict__ loss, int vec) {
 	const float scale = 2.0f/(float)count;
+	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x, nth = (long long)gridDim.x*blockDim.x;
 	float acc = 0.0f;
-	for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+	long long done = 0;
+	if (vec) {
+		const long long c4 = count >> 2;
+		const float4* y4 = reinterpret_cast<const float4*>(y); const float4* t4 = reinterpret_cast<const float4*>(target);
+		float4* d4 = reinterpret_cast<float4*>(diff); float4* g4 = reinterpret_cast<float4*>(gy);
+#pragma unroll 2
+		for (long long i = tid; i < c4; i += nth) {
+			const float4 a = y4[i], b = t4[i];
+			const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+			d4[i] = d; g4[i] = make_float4(d.x*scale, d.y*scale, d.z*scale, d.w*scale);
+			acc += (d.x*d.x + d.y*d.y) + (d.z*d.z + d.w*d.w);
+		}
+		done = c4 << 2;
+	}
+	for (long long i = done + tid; i < count; i += nth) {
 		const float d = y[i] - target[i];
 		diff[i] = d; gy[i] = d*scale;
 		acc += d*d;
 	}
 	for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
 	__shared__ float part[32];
+	__shared__ bool isLast;
 	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
 	__syncthreads();
 	if (threadIdx.x < 32) {
 		float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0f;
 		for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-		if (threadIdx.x == 0) *loss = v/(float)count;
+		if (threadIdx.x == 0) {
+			g_msePart[blockIdx.x] = v;
+			__threadfence();
+			isLast = atomicAdd(&g_mseDone, 1u) == gridDim.x - 1;
+		}
+	}
+	__syncthreads();
+	if (isLast && threadIdx.x == 0) {
+		__threadfence();
+		float v = 0.0f;
+		for (unsigned b = 0; b < gridDim.x; b++) v += *(volatile float*)&g_msePart[b];
+		*loss = v/(float)count;
+		g_mseDone = 0;
 	}
 }
 
@@ -762,7 +796,10 @@ extern "C" int nmc_siren_weight_grads(const nmc_siren_shape* sh, const float* x,
 extern "C" int nmc_mse_grad(const float* y, const float* target, int64_t count, float* diff, float* grad_y, float* loss, void* stream) {
 	if (count <= 0) return 0;
 	if (!y || !target || !diff || !grad_y || !loss) return fail("null buffer");
-	mseGrad<<<1, 1024, 0, (cudaStream_t)stream>>>(y, target, count, diff, grad_y, loss);
+	const int vec = (((uintptr_t)y | (uintptr_t)target | (uintptr_t)diff | (uintptr_t)grad_y) & 15) == 0;
+	int blocks = (int)((count/4 + 511)/512);
+	blocks = blocks < 1 ? 1 : (blocks > kMseBlocks ? kMseBlocks : blocks);
+	mseGrad<<<blocks, 512, 0, (cudaStream_t)stream>>>(y, target, count, diff, grad_y, loss, vec);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

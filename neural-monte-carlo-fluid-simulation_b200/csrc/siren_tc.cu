@@ -18,22 +18,11 @@
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
+#include "siren_tc.cuh"
 
 namespace {
 
-// sin/cos of the SIREN pre-activation w0*z.  |w0 z| stays below a few hundred, so one explicit reduction to
-// [-pi, pi] (t = x/2pi - rint(x/2pi), exact subtraction) followed by the SFU sine/cosine is accurate to
-// ~5e-7 absolute -- the same size as the fp32 rounding of the argument itself (ulp(100) = 7.6e-6) -- and costs
-// 4 instructions instead of the ~40 of sinf's generic range reduction.  -DNMC_SIREN_LIBM_SIN restores sinf/cosf.
-__device__ __forceinline__ float sinReduced(float x) {
-#ifdef NMC_SIREN_LIBM_SIN
-	return sinf(x);
-#else
-	float t = x*0.15915494309189535f;
-	t -= rintf(t);
-	return __sinf(6.283185307179586f*t);
-#endif
-}
+using nmc_siren_tc::sinReduced;
 
 constexpr int kTile = 128;
 constexpr int kMaxLayers = 18;
@@ -89,8 +78,15 @@ __device__ __forceinline__ void splitTf32(float v, float& hi, float& lo) {
 // the weight operand, so the serial part between two MMA batches is half as long.
 constexpr int kThreads = 2*kTile;
 
-template <int H>
-__global__ void __launch_bounds__(kThreads)
+// Everything that is not a GEMM operand -- every bias, the first layer's weights (H x in), the last layer's (out x H) and
+// its bias -- is staged once per CTA in shared memory and read as warp-wide broadcasts: the epilogues used to fetch
+// them with one dependent global load per element (phase trace: 5500 of the 8400 cycles of a hidden layer).
+__host__ __device__ inline int smallParamFloats(int H, int nHidden, int inDim, int outDim) {
+	return (nHidden + 1)*H + 4*H + outDim*H + outDim + 0*inDim;
+}
+
+template <int H, bool SAVEZ>
+__global__ void __launch_bounds__(kThreads, H == 64 ? 2 : 1)
 sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y,
 			   float* __restrict__ zSaved) {
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -98,11 +94,17 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 	unsigned char* Alo = Ahi + kTile*H*4;
 	unsigned char* Bhi = Alo + kTile*H*4;
 	unsigned char* Blo = Bhi + kNChunk*H*4;
+	float* sBias = reinterpret_cast<float*>(Blo + kNChunk*H*4);   // [nHidden + 1][H]
+	float4* sW0 = reinterpret_cast<float4*>(sBias + (nHidden + 1)*H); // [H] (w_0, w_1, w_2, bias) of the first layer: one 16-byte broadcast per neuron
+	float* sWL = reinterpret_cast<float*>(sW0 + H);                // [outDim][H]
+	float* sbL = sWL + outDim*H;                                   // [outDim]
 	__shared__ __align__(8) unsigned long long mbar;
 	__shared__ uint32_t tmemBaseSh;
 	__shared__ float ypart[3][kTile];
 	const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), half = tid >> 7;
-	const int cBeg = half*(H/2), cEnd = cBeg + H/2;
+	const int cBeg = half*(H/2);
+	constexpr int HC = H/2;
+	const int last = nHidden + 1;
 
 	if (warp == 0) { // TMEM: H fp32 columns x 128 lanes
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemAddr(&tmemBaseSh)), "r"((uint32_t)H) : "memory");
@@ -112,6 +114,11 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smemAddr(&mbar)) : "memory");
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	for (int l = 0; l <= nHidden; l++) for (int i = tid; i < H; i += kThreads) sBias[l*H + i] = __ldg(&P.b[l][i]);
+	for (int i = tid; i < H; i += kThreads)
+		sW0[i] = make_float4(__ldg(&P.W[0][i*inDim]), inDim > 1 ? __ldg(&P.W[0][i*inDim + 1]) : 0.0f, inDim > 2 ? __ldg(&P.W[0][i*inDim + 2]) : 0.0f, __ldg(&P.b[0][i]));
+	for (int i = tid; i < outDim*H; i += kThreads) sWL[i] = __ldg(&P.W[last][i]);
+	if (tid < outDim) sbL[tid] = __ldg(&P.b[last][tid]);
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -121,7 +128,6 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 	// D = F32, A = B = TF32, both K-major, N = 64, M = 128
 	const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNChunk >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 	uint32_t phase = 0;
-	const int last = nHidden + 1;
 	// Weight operand pipeline: the next 64-row chunk of W is fetched from L2 into registers while the tensor core works
 	// on the current one (the single B buffer can only be rewritten once those MMAs have completed), so the
 	// global-load latency no longer sits between two MMA batches.
@@ -154,26 +160,44 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		const long long s = tile*kTile + row;
 		const bool live = s < n;
 		TRACE(1);
-		{ // first layer on the FMA pipe, written straight into the A operand
-			float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
-			if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
-			for (int c = cBeg; c < cEnd; c += 4) {
-				float hi[4], lo[4];
+		float* zrow = SAVEZ ? zSaved + s : nullptr;
+		float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f;
+		// activation of this thread's columns c .. c + 3 of layer l from the pre-activations z: optional save, sine, the last
+		// layer's dot products (when l is the last hidden layer) or the hi/lo operand words of the next GEMM
+		auto emit4 = [&](int l, int c, const float (&z)[4], bool lastHidden) {
+			float hi[4], lo[4];
 #pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const float* w = &P.W[0][(c + q)*inDim];
-					float z = __ldg(&P.b[0][c + q]) + __ldg(w)*x0;
-					if (inDim > 1) z += __ldg(w + 1)*x1;
-					if (inDim > 2) z += __ldg(w + 2)*x2;
-					if (zSaved && live) zSaved[(size_t)(c + q)*n + s] = z;   // a warp writes 32 consecutive samples of one neuron
-					splitTf32(live ? sinReduced(w0*z) : 0.0f, hi[q], lo[q]);
+			for (int q = 0; q < 4; q++) {
+				if (SAVEZ) { if (live) zrow[((size_t)l*H + c + q)*n] = z[q]; } // a warp writes 32 consecutive samples of one neuron
+				float a = sinReduced(w0*z[q]);
+				if (!live) a = 0.0f;
+				if (lastHidden) {
+					y0 += sWL[c + q]*a;
+					if (outDim > 1) y1 += sWL[H + c + q]*a;
+					if (outDim > 2) y2 += sWL[2*H + c + q]*a;
 				}
-				int off = coreOffsetBytes<H>(row, c);
+				splitTf32(a, hi[q], lo[q]);
+			}
+			if (!lastHidden) {
+				const int off = coreOffsetBytes<H>(row, c);
 				*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
 				*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 			}
+		};
+		{ // first layer on the FMA pipe, written straight into the A operand
+			float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+			if (live) { x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2]; }
+#pragma unroll 4
+			for (int c4 = 0; c4 < HC; c4 += 4) {
+				float z[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const float4 w = sW0[cBeg + c4 + q];
+					z[q] = fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w))); // absent inputs carry zero weights
+				}
+				emit4(0, cBeg + c4, z, nHidden == 0);
+			}
 		}
-		float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f;
 		for (int l = 1; l <= nHidden; l++) {
 			for (int nc = 0; nc < H/kNChunk; nc++) {
 				// stage one 64-row chunk of W_l (rows = output neurons, K-major) as hi/lo TF32 operands
@@ -185,29 +209,30 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncthreads();
 				TRACE(4);
-				if (tid == 0) {
-					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					const uint32_t d = tmemBase + (uint32_t)(nc*kNChunk);
-					const uint32_t aH = smemAddr(Ahi), aL = smemAddr(Alo), bH = smemAddr(Bhi), bL = smemAddr(Blo);
-					const uint32_t sbo = H*32;
-#pragma unroll 1
-					for (int ks = 0; ks < H/8; ks++) { // UMMA K = 8 tf32 = two 16-byte core-matrix columns = 256 bytes
-						uint64_t dAh = smemDesc(aH + ks*256, 128, sbo), dAl = smemDesc(aL + ks*256, 128, sbo);
-						uint64_t dBh = smemDesc(bH + ks*256, 128, sbo), dBl = smemDesc(bL + ks*256, 128, sbo);
-						mmaTf32(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
-						mmaTf32(d, dAh, dBl, idesc, 1u);
-						mmaTf32(d, dAl, dBh, idesc, 1u);
-					}
-					// arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
-					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barAddr) : "memory");
-				}
-				TRACE(5);
-				{ // fetch the chunk that follows (this layer, the next layer, or the first one of the next tile) during the MMAs
+				{ // fetch the chunk that follows (this layer, the next layer, or the first one of the next tile) during the MMAs;
+				  // requested before the MMA issue so that thread 0's share is not late
 					int ln = l, ncn = nc + 1;
 					if (ncn == H/kNChunk) { ncn = 0; ln = l + 1; }
 					if (ln <= nHidden) loadW(ln, ncn);
 					else if ((tile + gridDim.x)*kTile < n) loadW(1, 0);
 				}
+				if (tid == 0) {
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t d = tmemBase + (uint32_t)(nc*kNChunk);
+					const uint32_t aH = smemAddr(Ahi), aL = smemAddr(Alo), bH = smemAddr(Bhi), bL = smemAddr(Blo);
+					const uint32_t sbo = H*32;
+					const uint64_t dAh = smemDesc(aH, 128, sbo), dAl = smemDesc(aL, 128, sbo);
+					const uint64_t dBh = smemDesc(bH, 128, sbo), dBl = smemDesc(bL, 128, sbo);
+#pragma unroll
+					for (int ks = 0; ks < H/8; ks++) { // UMMA K = 8 tf32 = two 16-byte core-matrix columns = 256 bytes (16 in descriptor units)
+						mmaTf32(d, dAh + 16*ks, dBh + 16*ks, idesc, ks > 0 ? 1u : 0u);
+						mmaTf32(d, dAh + 16*ks, dBl + 16*ks, idesc, 1u);
+						mmaTf32(d, dAl + 16*ks, dBh + 16*ks, idesc, 1u);
+					}
+					// arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
+					asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barAddr) : "memory");
+				}
+				TRACE(5);
 				TRACE(6);
 				mbarWait(barAddr, phase);
 				phase ^= 1u;
@@ -215,9 +240,12 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 				TRACE(7);
 			}
 			// epilogue: this thread's row of the accumulator -> bias, sin, next layer's operand
-			for (int c0 = cBeg; c0 < cEnd; c0 += 16) {
+			const float* bl = sBias + l*H;
+			const bool lastHidden = l == nHidden;
+#pragma unroll
+			for (int c0 = 0; c0 < HC; c0 += 16) {
 				uint32_t v[16];
-				uint32_t taddr = tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)c0;
+				uint32_t taddr = tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0);
 				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
 							 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
 							   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
@@ -225,26 +253,11 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
 				for (int q4 = 0; q4 < 16; q4 += 4) {
-					float hi[4], lo[4];
-#pragma unroll
-					for (int q = 0; q < 4; q++) {
-						int c = c0 + q4 + q;
-						const float z = __uint_as_float(v[q4 + q]) + __ldg(&P.b[l][c]);
-						if (zSaved && live) zSaved[((size_t)l*H + c)*n + s] = z;
-						float a = sinReduced(w0*z);
-						if (!live) a = 0.0f;
-						if (l == nHidden) {
-							y0 += __ldg(&P.W[last][c])*a;
-							if (outDim > 1) y1 += __ldg(&P.W[last][H + c])*a;
-							if (outDim > 2) y2 += __ldg(&P.W[last][2*H + c])*a;
-						}
-						splitTf32(a, hi[q], lo[q]);
-					}
-					if (l < nHidden) {
-						int off = coreOffsetBytes<H>(row, c0 + q4);
-						*reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-						*reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-					}
+					const int c = cBeg + c0 + q4;
+					const float4 bv = *reinterpret_cast<const float4*>(bl + c);
+					const float z[4] = {__uint_as_float(v[q4]) + bv.x, __uint_as_float(v[q4 + 1]) + bv.y, __uint_as_float(v[q4 + 2]) + bv.z, __uint_as_float(v[q4 + 3]) + bv.w};
+					if (lastHidden) emit4(l, c, z, true);
+					else emit4(l, c, z, false);
 				}
 			}
 		}
@@ -253,7 +266,7 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 		__syncthreads();
 		if (live && half == 0) {
 			y0 += ypart[0][row]; y1 += ypart[1][row]; y2 += ypart[2][row];
-			float yo[3] = {y0 + __ldg(&P.b[last][0]), outDim > 1 ? y1 + __ldg(&P.b[last][1]) : 0.0f, outDim > 2 ? y2 + __ldg(&P.b[last][2]) : 0.0f};
+			float yo[3] = {y0 + sbL[0], outDim > 1 ? y1 + sbL[1] : 0.0f, outDim > 2 ? y2 + sbL[2] : 0.0f};
 			if (env.active) {
 				const float xs[3] = {x[s*inDim], inDim > 1 ? x[s*inDim + 1] : 0.0f, inDim > 2 ? x[s*inDim + 2] : 0.0f};
 				nmc_siren_detail::envForward(env, inDim, outDim, xs, yo);
@@ -304,7 +317,7 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	Env env;
 	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) { nmc_siren_detail::setError(bad); return 1; }
 	const int H = sh->hidden;
-	size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4;
+	size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4 + (size_t)smallParamFloats(H, sh->n_hidden_layers, sh->in_dim, sh->out_dim)*4;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -313,13 +326,13 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	int grid = (int)(tiles < (long long)perSM*sms ? tiles : (long long)perSM*sms);
 	cudaStream_t st = (cudaStream_t)stream;
 	cudaError_t e;
-	if (H == 64) {
-		e = cudaFuncSetAttribute(sirenForwardTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<64><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
-	} else {
-		e = cudaFuncSetAttribute(sirenForwardTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenForwardTc<128><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
-	}
+#define NMC_LAUNCH_FWD(HH, SZ) do { \
+		e = cudaFuncSetAttribute(sirenForwardTc<HH, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+		if (!e) sirenForwardTc<HH, SZ><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved); \
+	} while (0)
+	if (H == 64) { if (z_saved) NMC_LAUNCH_FWD(64, true); else NMC_LAUNCH_FWD(64, false); }
+	else { if (z_saved) NMC_LAUNCH_FWD(128, true); else NMC_LAUNCH_FWD(128, false); }
+#undef NMC_LAUNCH_FWD
 	if (!e) e = cudaGetLastError();
 	if (e) { nmc_siren_detail::setError(cudaGetErrorString(e)); return 1; }
 	return 0;

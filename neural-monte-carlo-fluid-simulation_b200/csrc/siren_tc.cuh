@@ -11,22 +11,25 @@ namespace nmc_siren_tc {
 // [-pi, pi] (t = x/2pi - rint(x/2pi), exact subtraction) followed by the SFU sine/cosine is accurate to
 // ~5e-7 absolute -- the same size as the fp32 rounding of the argument itself (ulp(100) = 7.6e-6) -- and costs
 // 4 instructions instead of the ~40 of sinf's generic range reduction.  -DNMC_SIREN_LIBM_SIN restores sinf/cosf.
+// The rounding t - rint(t) is done with the 1.5 * 2^23 magic constant (two FADDs, exact for |t| < 2^22, the same
+// round-to-nearest-even result as rintf) instead of FRND, which shares the 16-lane XU pipe with the sine itself.
+__device__ __forceinline__ float turnsReduced(float x) {
+	const float t = x*0.15915494309189535f;
+	const float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
+	return t - r;
+}
 __device__ __forceinline__ float sinReduced(float x) {
 #ifdef NMC_SIREN_LIBM_SIN
 	return sinf(x);
 #else
-	float t = x*0.15915494309189535f;
-	t -= rintf(t);
-	return __sinf(6.283185307179586f*t);
+	return __sinf(6.283185307179586f*turnsReduced(x));
 #endif
 }
 __device__ __forceinline__ float cosReduced(float x) {
 #ifdef NMC_SIREN_LIBM_SIN
 	return cosf(x);
 #else
-	float t = x*0.15915494309189535f;
-	t -= rintf(t);
-	return __cosf(6.283185307179586f*t);
+	return __cosf(6.283185307179586f*turnsReduced(x));
 #endif
 }
 

@@ -19,6 +19,7 @@
 // the bias sums are not GEMM-shaped and run on the FMA pipe in the same launch.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
 #include "siren_tc.cuh"
@@ -42,6 +43,16 @@ struct Params {
 	float* gb[kMaxLayers];
 };
 
+// -DNMC_TC_TRACE: thread 0 of the first CTA of layer 0 (FMA path, slot 0) and of layer 1 (tensor-core path, slot 1), and of the delta chain (slot 2), stamps
+// clock64() at its phase boundaries (profiles/tools/tc_trace.py)
+#ifdef NMC_TC_TRACE
+__device__ long long g_traceW[3][256];
+__device__ int g_traceWN[3];
+#define TRACEW(slot, tag) do { if (blockIdx.x == 0 && tid == 0 && tn < 127) { g_traceW[slot][2*tn] = (tag); g_traceW[slot][2*tn + 1] = clock64(); tn++; g_traceWN[slot] = tn; } } while (0)
+#else
+#define TRACEW(slot, tag) do {} while (0)
+#endif
+
 // ---- delta chain ---------------------------------------------------------------------------------------------------------
 template <int H>
 __global__ void __launch_bounds__(kThreads, H == 64 ? 2 : 1)
@@ -52,6 +63,7 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 	unsigned char* Dlo = Dhi + kTile*H*4;
 	unsigned char* Bhi = Dlo + kTile*H*4;            // W_l^T chunk [64 input neurons x H output neurons], K-major
 	unsigned char* Blo = Bhi + kNChunk*H*4;
+	float* sWL = reinterpret_cast<float*>(Blo + kNChunk*H*4);   // last layer's weights [outDim][H]: warp-wide broadcasts
 	__shared__ __align__(8) unsigned long long mbar;
 	__shared__ uint32_t tmemBaseSh;
 	const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), half = tid >> 7;
@@ -60,6 +72,7 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 
 	if (warp == 0) tmemAlloc(&tmemBaseSh, (uint32_t)H);
 	if (tid == 0) mbarInit(smemAddr(&mbar), 1);
+	for (int i = tid; i < outDim*H; i += kThreads) sWL[i] = __ldg(&P.W[nHidden + 1][i]);
 	fenceBeforeSync();
 	__syncthreads();
 	fenceAfterSync();
@@ -67,7 +80,6 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 	const uint32_t barAddr = smemAddr(&mbar);
 	const uint32_t idesc = instrDescTf32(kTile, kNChunk);
 	uint32_t phase = 0;
-	const int last = nHidden + 1;
 
 	// B operand of dA = dZ_l W_l:  B(nrow = input neuron, k = output neuron) = W_l[k][nrow]; a thread gathers four
 	// consecutive k of one input neuron (lanes walk the input neurons: coalesced rows of W_l) into one 16-byte word
@@ -94,9 +106,17 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 	};
 	if (nHidden >= 1 && (long long)blockIdx.x*kTile < n) loadW(nHidden, 0);
 
+#ifdef NMC_TC_TRACE
+	int tn = 0;
+#endif
 	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x) {
 		const long long s = tile*kTile + row;
 		const bool live = s < n;
+		// rows past the end read the last sample (always in bounds, no per-element branch); their results are zeroed / not stored
+		const long long sc = live ? s : n - 1;
+		const float* zrow = zSaved + sc + (size_t)cBeg*n;   // + layer*H*n: this thread's first column, stride n per column
+		float* drow = dZ + sc + (size_t)cBeg*n;
+		TRACEW(2, 1);
 		float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
 		if (live) {
 			g0 = gy[s*outDim]; if (outDim > 1) g1 = gy[s*outDim + 1]; if (outDim > 2) g2 = gy[s*outDim + 2];
@@ -115,19 +135,25 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 		}
 		float zreg[HC];
 		{ // dZ_L = (W_last^T gy') * w0 cos(w0 z_L) on the FMA pipe, written straight into the A operand
+			{
+				const float* zp = zrow + (size_t)nHidden*H*n;
 #pragma unroll
-			for (int q = 0; q < HC; q++) zreg[q] = live ? zSaved[((size_t)nHidden*H + cBeg + q)*n + s] : 0.0f;
+				for (int q = 0; q < HC; q++) { zreg[q] = __ldg(zp); zp += n; }
+			}
+			float* dp = drow + (size_t)nHidden*H*n;
+			if (!live) { g0 = 0.0f; g1 = 0.0f; g2 = 0.0f; }
 #pragma unroll
 			for (int q4 = 0; q4 < HC; q4 += 4) {
 				float d[4];
 #pragma unroll
 				for (int q = 0; q < 4; q++) {
 					const int c = cBeg + q4 + q;
-					float a = __ldg(&P.W[last][c])*g0;
-					if (outDim > 1) a += __ldg(&P.W[last][H + c])*g1;
-					if (outDim > 2) a += __ldg(&P.W[last][2*H + c])*g2;
-					a = live ? a*w0*cosReduced(w0*zreg[q4 + q]) : 0.0f;
-					if (live) dZ[((size_t)nHidden*H + c)*n + s] = a;
+					float a = sWL[c]*g0;
+					if (outDim > 1) a += sWL[H + c]*g1;
+					if (outDim > 2) a += sWL[2*H + c]*g2;
+					a = a*w0*cosReduced(w0*zreg[q4 + q]);
+					if (live) *dp = a;
+					dp += n;
 					d[q] = a;
 				}
 				float4 h, o;
@@ -139,39 +165,50 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 		}
 		for (int l = nHidden; l >= 1; l--) {
 			// pre-activations of layer l - 1 for this thread's columns: in flight during the MMAs
+			{
+				const float* zp = zrow + (size_t)(l - 1)*H*n;
 #pragma unroll
-			for (int q = 0; q < HC; q++) zreg[q] = live ? zSaved[((size_t)(l - 1)*H + cBeg + q)*n + s] : 0.0f;
+				for (int q = 0; q < HC; q++) { zreg[q] = __ldg(zp); zp += n; }
+			}
 			for (int nc = 0; nc < H/kNChunk; nc++) {
+				TRACEW(2, 2);
 				storeW();
+				TRACEW(2, 3);
 				fenceProxyAsync();
 				fenceBeforeSync();
 				__syncthreads();
-				if (tid == 0) {
-					fenceAfterSync();
-					const uint32_t d = tmemBase + (uint32_t)(nc*kNChunk);
-					const uint32_t aH = smemAddr(Dhi), aL = smemAddr(Dlo), bH = smemAddr(Bhi), bL = smemAddr(Blo);
-					const uint32_t sbo = H*32;
-#pragma unroll 1
-					for (int ks = 0; ks < H/8; ks++) {
-						const uint64_t dAh = smemDesc(aH + ks*256, 128, sbo), dAl = smemDesc(aL + ks*256, 128, sbo);
-						const uint64_t dBh = smemDesc(bH + ks*256, 128, sbo), dBl = smemDesc(bL + ks*256, 128, sbo);
-						mmaTf32(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
-						mmaTf32(d, dAh, dBl, idesc, 1u);
-						mmaTf32(d, dAl, dBh, idesc, 1u);
-					}
-					mmaCommit(barAddr);
-				}
-				{ // the chunk that follows: this layer, the layer below, or the first one of the next tile
+				TRACEW(2, 4);
+				{ // the chunk that follows: this layer, the layer below, or the first one of the next tile (requested before the
+				  // MMA issue so that thread 0's share is not late)
 					int ln = l, ncn = nc + 1;
 					if (ncn == H/kNChunk) { ncn = 0; ln = l - 1; }
 					if (ln >= 1) loadW(ln, ncn);
 					else if ((tile + gridDim.x)*kTile < n) loadW(nHidden, 0);
 				}
+				if (tid == 0) {
+					fenceAfterSync();
+					const uint32_t d = tmemBase + (uint32_t)(nc*kNChunk);
+					const uint32_t aH = smemAddr(Dhi), aL = smemAddr(Dlo), bH = smemAddr(Bhi), bL = smemAddr(Blo);
+					const uint32_t sbo = H*32;
+					const uint64_t dAh = smemDesc(aH, 128, sbo), dAl = smemDesc(aL, 128, sbo);
+					const uint64_t dBh = smemDesc(bH, 128, sbo), dBl = smemDesc(bL, 128, sbo);
+#pragma unroll
+					for (int ks = 0; ks < H/8; ks++) { // one K step = 256 bytes = 16 descriptor address units
+						mmaTf32(d, dAh + 16*ks, dBh + 16*ks, idesc, ks > 0 ? 1u : 0u);
+						mmaTf32(d, dAh + 16*ks, dBl + 16*ks, idesc, 1u);
+						mmaTf32(d, dAl + 16*ks, dBh + 16*ks, idesc, 1u);
+					}
+					mmaCommit(barAddr);
+				}
+				TRACEW(2, 5);
 				mbarWait(barAddr, phase);
 				phase ^= 1u;
 				fenceAfterSync();
+				TRACEW(2, 6);
 			}
 			// epilogue: dZ_{l-1} = dA_{l-1} * w0 cos(w0 z_{l-1}) -> global (weight gradients) and the next A operand
+			float* dp = drow + (size_t)(l - 1)*H*n;
+			const float w0l = live ? w0 : 0.0f;   // dead rows: zero deltas
 #pragma unroll
 			for (int c0 = 0; c0 < HC; c0 += 16) {
 				uint32_t v[16];
@@ -181,10 +218,9 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 					float d[4];
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
-						const int c = cBeg + c0 + q4 + q;
-						float a = __uint_as_float(v[q4 + q])*w0*cosReduced(w0*zreg[c0 + q4 + q]);
-						if (!live) a = 0.0f;
-						else dZ[((size_t)(l - 1)*H + c)*n + s] = a;
+						const float a = __uint_as_float(v[q4 + q])*w0l*cosReduced(w0*zreg[c0 + q4 + q]);
+						if (live) *dp = a;
+						dp += n;
 						d[q] = a;
 					}
 					if (l > 1) {
@@ -197,6 +233,7 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 				}
 			}
 		}
+		TRACEW(2, 7);
 		// the next tile's first deltas overwrite D: every thread is past its last use (MMAs completed via the mbarrier)
 		fenceBeforeSync();
 		__syncthreads();
@@ -207,21 +244,28 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 }
 
 // ---- weight gradients ----------------------------------------------------------------------------------------------------
+
 constexpr int kKS = 64;           // samples per MMA batch (K of one staged operand tile)
 constexpr int kGS = 32;           // samples per staged tile of the FMA path (first / last layer)
 
 template <int H>
 __global__ void __launch_bounds__(kThreads)
 sirenWeightGradTc(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
-				  const float* __restrict__ dZ, const float* __restrict__ zSaved, int chunk) {
+				  const float* __restrict__ dZ, const float* __restrict__ zSaved, int chunkTc, int chunkFma) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) unsigned long long mbar;
 	__shared__ uint32_t tmemBaseSh;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int l = blockIdx.y;                 // 0 .. nHidden + 1
 	const int last = nHidden + 1;
+	// the grid's x extent covers the finer of the two partitions; the CTAs beyond a layer's own chunk count leave at once
+	const int chunk = (l == 0 || l == last) ? chunkFma : chunkTc;
 	const long long s0 = (long long)blockIdx.x*chunk;
+	if (s0 >= n) return;
 	const long long s1 = s0 + chunk < n ? s0 + chunk : n;
+#ifdef NMC_TC_TRACE
+	int tn = 0;
+#endif
 
 	if (l == 0 || l == last) { // ---- FMA path: C[i][j] = sum_s P[i][s] Q[j][s] with 2-3 rows on one side; bias sums
 		constexpr int LDS = H + 4;
@@ -237,6 +281,7 @@ sirenWeightGradTc(Params P, int inDim, int outDim, int nHidden, float w0, const 
 		float bsum = 0.0f;
 		for (long long sb = s0; sb < s1; sb += kGS) {
 			const int ns = (int)(s1 - sb < kGS ? s1 - sb : kGS);
+			if (l == 0) TRACEW(0, 1);
 			__syncthreads();
 			for (int idx = tid; idx < RP*kGS; idx += kThreads) { int r = idx/kGS, c = idx - r*kGS; Ps[c][r] = c < ns ? Pg[(size_t)r*n + sb + c] : 0.0f; }
 			if (l == 0) { for (int idx = tid; idx < kGS*inDim; idx += kThreads) { int c = idx/inDim, r = idx - c*inDim; Qs[c][r] = c < ns ? x[(sb + c)*inDim + r] : 0.0f; } }
@@ -252,8 +297,10 @@ sirenWeightGradTc(Params P, int inDim, int outDim, int nHidden, float w0, const 
 			if (tid < RP) { float a = 0.0f; for (int c = 0; c < kGS; c++) a += Ps[c][tid]; bsum += a; }
 		}
 		int q = 0;
+		if (l == 0) TRACEW(0, 2);
 		for (int o = tid; o < RP*RQ; o += kThreads, q++) atomicAdd(&P.gW[l][o], small[q]);
 		if (tid < RP) atomicAdd(&P.gb[l][tid], bsum);
+		if (l == 0) TRACEW(0, 3);
 		return;
 	}
 
@@ -315,35 +362,43 @@ sirenWeightGradTc(Params P, int inDim, int outDim, int nHidden, float w0, const 
 	};
 	uint32_t phase = 0;
 	int stage = 0;
+	if (l == 1) TRACEW(1, 1);
 	loadStage(s0);
 	for (long long sb = s0; sb < s1; sb += kKS, stage++) {
+		if (l == 1) TRACEW(1, 2);
 		if (stage > 0) { // the MMAs of the previous batch have finished reading the operand tiles
 			mbarWait(barAddr, phase);
 			phase ^= 1u;
 			fenceAfterSync();
 		}
+		if (l == 1) TRACEW(1, 3);
 		storeStage();
+		if (l == 1) TRACEW(1, 4);
 		fenceProxyAsync();
 		fenceBeforeSync();
 		__syncthreads();
+		if (l == 1) TRACEW(1, 5);
+		if (sb + kKS < s1) loadStage(sb + kKS); // in flight during the MMAs (requested before the issue: thread 0's share is not late)
 		if (tid == 0) {
 			fenceAfterSync();
 			const uint32_t pH = smemAddr(Phi), pL = smemAddr(Plo), qH = smemAddr(Qhi), qL = smemAddr(Qlo);
 			const uint32_t sbo = kKS*32;
-#pragma unroll 1
-			for (int ks = 0; ks < kKS/8; ks++) {
-				const uint64_t dPh = smemDesc(pH + ks*256, 128, sbo), dPl = smemDesc(pL + ks*256, 128, sbo);
-				const uint64_t dQh = smemDesc(qH + ks*256, 128, sbo), dQl = smemDesc(qL + ks*256, 128, sbo);
-				mmaTf32(tmemBase, dPh, dQh, idesc, (stage > 0 || ks > 0) ? 1u : 0u);
-				mmaTf32(tmemBase, dPh, dQl, idesc, 1u);
-				mmaTf32(tmemBase, dPl, dQh, idesc, 1u);
+			const uint64_t dPh = smemDesc(pH, 128, sbo), dPl = smemDesc(pL, 128, sbo);
+			const uint64_t dQh = smemDesc(qH, 128, sbo), dQl = smemDesc(qL, 128, sbo);
+#pragma unroll
+			for (int ks = 0; ks < kKS/8; ks++) { // one K step = 256 bytes = 16 descriptor address units
+				mmaTf32(tmemBase, dPh + 16*ks, dQh + 16*ks, idesc, (stage > 0 || ks > 0) ? 1u : 0u);
+				mmaTf32(tmemBase, dPh + 16*ks, dQl + 16*ks, idesc, 1u);
+				mmaTf32(tmemBase, dPl + 16*ks, dQh + 16*ks, idesc, 1u);
 			}
 			mmaCommit(barAddr);
 		}
-		if (sb + kKS < s1) loadStage(sb + kKS); // in flight during the MMAs
+		if (l == 1) TRACEW(1, 6);
 	}
+	if (l == 1) TRACEW(1, 7);
 	mbarWait(barAddr, phase);
 	fenceAfterSync();
+	if (l == 1) TRACEW(1, 8);
 	{ // accumulator tile -> gradient buffer.  M = 128: row i in TMEM lane i; M = 64: row i in lane (i % 16) + 32 (i / 16)
 		const int sp = warp & 3, ch = warp >> 2;  // TMEM sub-partition of this warp, column half
 		const int i = H == 128 ? sp*32 + lane : sp*16 + (lane & 15);
@@ -368,6 +423,7 @@ sirenWeightGradTc(Params P, int inDim, int outDim, int nHidden, float w0, const 
 			if (lane < 8) atomicAdd(&P.gb[l][itemRow(i)], b);
 		}
 	}
+	if (l == 1) TRACEW(1, 9);
 	fenceBeforeSync();
 	__syncthreads();
 	if (warp == 0) tmemFree(tmemBase, (uint32_t)H);
@@ -398,7 +454,7 @@ extern "C" int nmc_siren_backward_tc(const nmc_siren_shape* sh, const float* con
 	Env env;
 	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
 	const int H = sh->hidden;
-	const size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4;
+	const size_t smem = (size_t)(2*kTile*H + 2*kNChunk*H)*4 + (size_t)sh->out_dim*H*4;
 	const long long tiles = (n + kTile - 1)/kTile;
 	const int perSM = H == 64 ? 2 : 1;
 	const int grid = (int)(tiles < (long long)perSM*smCount() ? tiles : (long long)perSM*smCount());
@@ -431,20 +487,39 @@ extern "C" int nmc_siren_weight_grads_tc(const nmc_siren_shape* sh, const float*
 	if (((uintptr_t)dZ & 15) || ((uintptr_t)z_saved & 15)) return fail("tensor-core weight gradients: dZ and z_saved must be 16-byte aligned");
 	const int H = sh->hidden;
 	// samples per CTA: as large as possible (fewer reductions into the gradient buffer) while the hidden layers' CTAs cover the SMs
+	// (measured, batch 16384: H = 64 (64 KB per CTA, three resident per SM, which hide each other's load -> stage -> MMA
+	// round trips) is fastest with ~2 CTAs per SM; H = 128 (128 KB per CTA, one per SM) with a single wave)
 	int chunk = 1024;
-	while (chunk > kKS && ((n + chunk - 1)/chunk)*sh->n_hidden_layers < smCount()) chunk >>= 1;
-	dim3 grid((unsigned)((n + chunk - 1)/chunk), (unsigned)(sh->n_hidden_layers + 2));
+	const long long want = H == 64 ? 2ll*smCount() : (3ll*smCount())/4;
+	while (chunk > 2*kKS && ((n + chunk - 1)/chunk)*sh->n_hidden_layers < want) chunk >>= 1;
+	if (const char* ov = getenv("NMC_WGRAD_CHUNK")) { const int v = atoi(ov); if (v >= kKS && v % kKS == 0) chunk = v; } // A/B measurements
+	// first / last layer (FMA path, 32-sample tiles with a full load -> barrier -> compute round trip each): short chunks,
+	// so that these CTAs finish with the tensor-core ones (phase trace: 3000 cycles per tile)
+	const int chunkFma = chunk < 128 ? chunk : 128;
+	dim3 grid((unsigned)((n + chunkFma - 1)/chunkFma), (unsigned)(sh->n_hidden_layers + 2));
 	const size_t smemTc = (size_t)4*H*kKS*4, smemFma = (size_t)2*kGS*(H + 4)*4;
 	const size_t smem = smemTc > smemFma ? smemTc : smemFma;
 	cudaStream_t st = (cudaStream_t)stream;
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenWeightGradTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenWeightGradTc<64><<<grid, kThreads, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, dZ, z_saved, chunk);
+		if (!e) sirenWeightGradTc<64><<<grid, kThreads, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, dZ, z_saved, chunk, chunkFma);
 	} else {
 		e = cudaFuncSetAttribute(sirenWeightGradTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenWeightGradTc<128><<<grid, kThreads, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, dZ, z_saved, chunk);
+		if (!e) sirenWeightGradTc<128><<<grid, kThreads, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, dZ, z_saved, chunk, chunkFma);
 	}
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
+
+#ifdef NMC_TC_TRACE
+extern "C" int nmc_siren_trace_read_wgrad(int slot, long long* out, int cap) { // (tag, clock) pairs of the last traced launch
+	int n[3] = {0, 0, 0};
+	if (slot < 0 || slot > 2) return 0;
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(n, g_traceWN, sizeof(n));
+	int k = n[slot] > cap ? cap : n[slot];
+	cudaMemcpyFromSymbol(out, g_traceW, sizeof(long long)*2*k, sizeof(long long)*256*slot);
+	return k;
+}
+#endif

@@ -450,21 +450,34 @@ class DirectFit:
         # selects the fp32 kernels for A/B measurements
         self.tc_backward = self.tensor_cores and os.environ.get("NMC_SIREN_TC_BWD", "1") != "0"
         self.tc_backward_min = int(os.environ.get("NMC_SIREN_TC_BWD_MIN", "4096"))
+        self.tc_forward_min = int(os.environ.get("NMC_SIREN_TC_FWD_MIN", "16384"))
         self.dz = torch.empty(((Lh + 1)*H + self.sh.out_dim)*max_batch, device=g.device) if self.tc_backward else None
         self.max_batch = max_batch
         self.loss = torch.zeros((), device=g.device)  # mean squared error of the last iterate() call
 
     def iterate(self, x, target):
+        return self.finish(x, self.forward(x), target)
+
+    def forward(self, x):
+        """First half of an iteration: the training forward (saves the pre-activations).  Independent of the target, so a
+        caller may compute the target on another stream meanwhile (stepper.py)."""
         n = x.shape[0]
         assert n <= self.max_batch and x.is_contiguous()
         sh = self.sh
         y = torch.empty((n, sh.out_dim), device=x.device)
         z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]  # [layer*H + neuron][sample], stride n
         with torch.cuda.device(x.device):
-            if self.tensor_cores and n >= 16384 and sh.n_hidden_layers >= 1:  # tcgen05 forward that also writes the pre-activations
+            if self.tensor_cores and n >= self.tc_forward_min and sh.n_hidden_layers >= 1:  # tcgen05 forward that also writes the pre-activations
                 _check(_lib().nmc_siren_forward_tc(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
             else:
                 _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
+        return y
+
+    def finish(self, x, y, target):
+        """Second half: loss, dL/dy, delta chain, weight gradients, (all_reduce,) Adam.  Returns y - target."""
+        n = x.shape[0]
+        sh = self.sh
+        z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]
         diff = torch.empty_like(y); gy = torch.empty_like(y)
         tgt = target.contiguous()
         with torch.cuda.device(x.device):  # diff, dL/dy and the loss in one launch

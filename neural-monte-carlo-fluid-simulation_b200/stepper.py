@@ -18,6 +18,8 @@ every iteration, base.py:142 -- the early-stop test here runs every `check_every
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import capi, zombie, fields
@@ -102,6 +104,8 @@ class SplitStepper:
         self.sample_resolution, self.wost_resolution, self.grid_resolution = sample_resolution, wost_resolution, grid_resolution
         self.max_n_iters, self.early_stop, self.check_every = max_n_iters, early_stop, check_every
         self.boundary, self.use_graph = boundary, use_cuda_graph
+        # fit target on a second stream, parallel to the training forward (NMC_OVERLAP_TARGETS=0: one stream, for A/B runs)
+        self.overlap_targets = os.environ.get("NMC_OVERLAP_TARGETS", "1") != "0"
         torch.manual_seed(seed)
         self.dim = dim = len(self.size)//2
         if dim not in (2, 3):
@@ -217,9 +221,24 @@ class SplitStepper:
         else:
             loss_buf = fit.loss  # mean squared error, written by the iteration itself
 
+            side2 = torch.cuda.Stream(device=self.dev) if self.overlap_targets else None
+
             def one():
-                samples, target = iteration()
-                fit.iterate(samples, target)
+                # `iteration()` returns the samples and a function that computes the fit target from them.  The target
+                # (one or two evaluations of the previous network) does not depend on the training forward, so the two run
+                # on different streams -- inside the captured graph they become parallel branches.
+                samples, make_target = iteration()
+                if side2 is None:
+                    target = make_target(samples)
+                    fit.iterate(samples, target)
+                    return
+                main = torch.cuda.current_stream()
+                side2.wait_stream(main)
+                with torch.cuda.stream(side2):
+                    target = make_target(samples)
+                y = fit.forward(samples)
+                main.wait_stream(side2)
+                fit.finish(samples, y, target)
 
             graph = None
             if self.use_graph:
@@ -279,13 +298,14 @@ class SplitStepper:
         n = self.sample_resolution**2//self.world
         s = self.size
 
-        def iteration():
-            samples = self.sample_random(n)
+        def make_target(samples):
             with torch.no_grad():
                 prev_u = self.query_velocity(samples, use_prev=True)
                 back = fields.backtrace(samples, prev_u, self.dt, self.size[0::2], self.size[1::2])
-                advected = self.query_velocity(back, use_prev=True)
-            return samples, advected
+                return self.query_velocity(back, use_prev=True)
+
+        def iteration():
+            return self.sample_random(n), make_target
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect")
 
     def divergence_grid(self):
@@ -347,18 +367,20 @@ class SplitStepper:
                 # uniform index in [0, big - 2] (the reference's randint(0, big - 1) excludes the last point, :274);
                 # the bound is a device scalar so the captured graph serves every step's sample count
                 idx = torch.clamp((torch.rand(n, device=self.dev)*pc).long(), max=cap_idx)
-                samples = ps[idx]
-                with torch.no_grad():
-                    target = self.query_velocity(samples, use_prev=True) - pg[idx]
-                return samples, target
+
+                def make_target(samples):
+                    with torch.no_grad():
+                        return self.query_velocity(samples, use_prev=True) - pg[idx]
+                return ps[idx], make_target
             cap_idx = ps.shape[0] - 1
         else:
             def iteration():
                 idx = torch.randint(0, big - 1 if self.dim == 2 else big, (n,), device=self.dev)  # 2D excludes the last point (:274)
-                samples = samples_all[idx]
-                with torch.no_grad():
-                    target = self.query_velocity(samples, use_prev=True) - grad_p[idx]
-                return samples, target
+
+                def make_target(samples):
+                    with torch.no_grad():
+                        return self.query_velocity(samples, use_prev=True) - grad_p[idx]
+                return samples_all[idx], make_target
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="project")
 
     def _sync_prev(self):

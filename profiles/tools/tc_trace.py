@@ -33,3 +33,20 @@ for i in range(k):
     tag, t = buf[2*i], buf[2*i + 1]
     print("%-18s +%6d cycles  (total %7d)" % (names.get(tag, str(tag)), t - prev, t - t0))
     prev = t
+
+# one fit iteration: the weight-gradient kernel's FMA-path CTA (slot 0: 1 tile start, 2 tiles done, 3 atomics done) and
+# tensor-core CTA (slot 1: 1 start, 2 stage start, 3 previous MMAs done, 4 operands staged, 5 fence + barrier, 6 MMAs issued,
+# 7 loop end, 8 MMAs complete, 9 reductions done)
+fit = S.DirectFit(net, 1e-4, None, max_batch=n)
+target = torch.sin(x)
+for _ in range(3):
+    fit.iterate(x, target)
+torch.cuda.synchronize()
+for slot in (0, 1, 2):  # 2 = delta chain: 1 tile start, 2 chunk start, 3 weights staged, 4 fence + barrier, 5 MMAs issued, 6 MMAs complete, 7 tile end
+    k = L.nmc_siren_trace_read_wgrad(slot, buf, 127)
+    print("weight-gradient kernel, slot %d: %d stamps" % (slot, k))
+    t0 = prev = buf[1]
+    for i in range(k):
+        tag, t = buf[2*i], buf[2*i + 1]
+        print("  tag %d  +%6d cycles  (total %7d)" % (tag, t - prev, t - t0))
+        prev = t
