@@ -382,6 +382,7 @@ def main():
         except Exception as e:
             pe2e = {"error": "%s: %s" % (type(e).__name__, e)}
     issue_peak = pkg.capi.measure_peaks(X.local) if X.rank == 0 else None
+    dispatch = pkg.capi.measure_issue_peak(X.local) if X.rank == 0 else None
 
     if X.rank != 0:
         if world > 1:
@@ -417,12 +418,13 @@ def main():
             "gpu_launches": R["launches"], "clocks": R["clocks"], "finite": R["finite"]}
     if issue_peak:
         rate = walks_per_launch/(k_ms*1e-3)  # walks/s of this GPU inside the kernel
-        ri = {"bound": "issue", "peak": issue_peak[0], "unit": "warp-inst/s", "peak_source": "measured live (nmc_measure_peaks: fp32 FMA chains, 1 warp instruction / scheduler / clock)",
-              "mufu_peak": issue_peak[1], "fp64_fma_peak": issue_peak[2], "per": "GPU"}
+        ri = {"bound": "issue", "peak": dispatch[0], "unit": "warp-inst/s",
+              "peak_source": "measured live (nmc_measure_issue_peak): 4 dispatch slots per SM x SMs x the SM clock under load (clock64 vs globaltimer)",
+              "sm_clock_hz": dispatch[1], "fma_pipe_peak": issue_peak[0], "mufu_peak": issue_peak[1], "fp64_fma_peak": issue_peak[2], "per": "GPU"}
         if prof is not None and prof.get("warp_inst_per_walk"):
-            ri.update(achieved=rate*prof["warp_inst_per_walk"], frac=rate*prof["warp_inst_per_walk"]/issue_peak[0],
+            ri.update(achieved=rate*prof["warp_inst_per_walk"], frac=rate*prof["warp_inst_per_walk"]/dispatch[0],
                       warp_inst_per_walk=prof["warp_inst_per_walk"], active_lanes_per_inst=prof.get("active_lanes_per_inst"),
-                      lane_issue_frac=rate*prof["warp_inst_per_walk"]*prof.get("active_lanes_per_inst", 32.0)/32.0/issue_peak[0],
+                      lane_issue_frac=rate*prof["warp_inst_per_walk"]*prof.get("active_lanes_per_inst", 32.0)/32.0/dispatch[0],
                       profile=prof.get("capture"), profile_workload=prof.get("workload"))
         line["roofline_issue"] = ri
     if not args.no_cpu_baseline and world == 1:

@@ -119,6 +119,41 @@ int nmc_wost_solve_stats(nmc_scene* scene, const nmc_solver_opts* opts, const fl
 						 uint64_t index_offset, float* p_out, float* grad_out, float* stats12,
 						 nmc_solve_stats* stats);
 
+/* EstimationQuantity::Solution (walk_on_stars.h:354-461) at caller-given sample points, deterministic replay: the
+ * estimator boundary value caching runs at its cache points.  HOST buffers.  normals n x dim (may be NULL), types per
+ * point 0 = in the domain, 2 = ON the reflecting boundary (zombie::SampleType; NULL = all 0), aligned = the point's
+ * estimateBoundaryNormalAligned flag (double-sided scenes; NULL = all 0).  Stream of point i: nmc_point_seed(opts->seed,
+ * index_offset + i), not re-seeded between walks.  stats4_out (may be NULL): variance, number of averaged walks, mean walk
+ * length, first sphere radius per point. */
+int nmc_estimate_solution(nmc_scene* scene, const nmc_solver_opts* opts, const float* pts, const float* normals,
+						  const int* types, const int* aligned, int64_t n, int n_walks, uint64_t index_offset,
+						  float* solution_out, float* stats4_out);
+
+/* Boundary value caching, bvc(scene, solverConfig, outputConfig) of the 2D bindings (demo.cpp:265-363): the solver options
+ * it reads beyond nmc_solver_opts. */
+typedef struct {
+	int boundaryCacheSize;                        /* 1024 */
+	int domainCacheSize;                          /* 1024 */
+	int nWalksForCachedSolutionEstimates;         /* 128 */
+	int nWalksForCachedGradientEstimates;         /* 640; unused: there are no Dirichlet cache points in the bindings */
+	int gridRes;                                  /* outputConfig["gridRes"] */
+	float normalOffsetForCachedDirichletSamples;  /* 5 * epsilonShell */
+	float radiusClampForKernels;                  /* 1e-3 */
+	float regularizationForKernels;               /* 0 */
+} nmc_bvc_opts;
+/* Runs the whole pipeline on the scene's device and returns the masked evaluation grid: grid_out[i * gridRes + j] is the
+ * value at point (i, j) of createEvaluationGrid (demo/grid.h:352-368) after saveEvaluationGrid's masking (:388-411);
+ * writing the image files is left to the binding layer.  cache_out (may be NULL): up to cache_cap boundary cache points x 6
+ * floats (x, y, nx, ny, estimated solution, pdf).  2D scenes only. */
+int nmc_bvc_solve(nmc_scene* scene, const nmc_solver_opts* opts, const nmc_bvc_opts* bvc, float* grid_out,
+				  float* cache_out, int cache_cap, int* n_cache_out, int* n_domain_out);
+/* The splat stage alone (Splatter::splat, splatter.h:53-116, 203-290), HOST buffers: cache8 = n_cache records of 8 floats
+ * (x, y, nx, ny, value, normal derivative, pdf, kind: 0 boundary, 2 boundary normal-aligned, 1 source); out[i] receives the
+ * sum of the three groups' means for every evaluation point whose Dirichlet distance is >= the cut-off. */
+int nmc_bvc_splat(int dim, float absorption, const float* eval_pts, const float* eval_dirichlet_dist, int64_t n_eval,
+				  const float* cache8, int n_cache, float radius_clamp, float regularization, float dirichlet_dist_cutoff,
+				  float* out);
+
 /* Seeding rule of the deterministic mode (splitmix64 finaliser of seed + golden*(index+1)). */
 uint64_t nmc_point_seed(uint64_t seed, uint64_t index);
 
@@ -145,10 +180,14 @@ int nmc_probe(nmc_scene* scene, int kind, int64_t n, const float* pts, const flo
  * number of intervals and copies up to capacity_floats coefficients.  For the tests. */
 int nmc_bessel_table(float* out, int capacity_floats, float* t0, int* per_octave);
 
-/* Instruction-throughput peaks of `device`, measured by micro-benchmarks (csrc/peaks.cu), in warp-instructions per
- * second: out3[0] fp32 FMA (= the issue limit, one instruction per scheduler per clock), out3[1] MUFU (ex2),
- * out3[2] fp64 FMA.  Denominators of the issue-bound roofline bench.py reports for the walk kernels. */
+/* Pipe-throughput peaks of `device`, measured by micro-benchmarks (csrc/peaks.cu), in warp-instructions per
+ * second: out3[0] fp32 FMA (FMA pipe; ~2/3 of the dispatch limit on B200), out3[1] MUFU (ex2), out3[2] fp64 FMA. */
 int nmc_measure_peaks(int device, float* out3);
+
+/* Issue (dispatch) limit of `device`: one warp instruction per SM sub-partition per clock.  out2[0] = 4 x SMs x the SM
+ * clock measured under load (clock64 against globaltimer) in warp-instructions per second, out2[1] = that clock in Hz.
+ * Denominator of the issue-bound roofline bench.py reports for the walk kernels. */
+int nmc_measure_issue_peak(int device, float* out2);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,14 @@ class SolverOpts(C.Structure):
                 ("boundaryDistanceMask", C.c_float), ("mode", C.c_int), ("seed", C.c_uint64)]
 
 
+class BvcOpts(C.Structure):
+    """nmc_bvc_opts: the solver options of bvc() beyond SolverOpts (demo.cpp:274-292)."""
+    _fields_ = [("boundaryCacheSize", C.c_int), ("domainCacheSize", C.c_int), ("nWalksForCachedSolutionEstimates", C.c_int),
+                ("nWalksForCachedGradientEstimates", C.c_int), ("gridRes", C.c_int),
+                ("normalOffsetForCachedDirichletSamples", C.c_float), ("radiusClampForKernels", C.c_float),
+                ("regularizationForKernels", C.c_float)]
+
+
 class SolveStats(C.Structure):
     _fields_ = [("walks_started", C.c_uint64), ("walks_completed", C.c_uint64), ("walk_steps", C.c_uint64),
                 ("active_points", C.c_uint64), ("kernel_ms", C.c_float), ("total_ms", C.c_float),
@@ -45,7 +53,7 @@ class SolveStats(C.Structure):
 EXPORTS = ["nmc_last_error", "nmc_device_count", "nmc_scene_create", "nmc_scene_destroy", "nmc_scene_set_source",
            "nmc_scene_dim", "nmc_scene_bbox", "nmc_scene_num_nodes", "nmc_scene_nodes", "nmc_wost_solve",
            "nmc_wost_solve_device", "nmc_wost_solve_stats", "nmc_point_seed", "nmc_probe", "nmc_scene_set_source_async",
-           "nmc_measure_peaks", "nmc_bessel_table"]
+           "nmc_measure_peaks", "nmc_measure_issue_peak", "nmc_bessel_table", "nmc_estimate_solution", "nmc_bvc_solve", "nmc_bvc_splat"]
 SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_siren_backward_tc", "nmc_siren_weight_grads_tc", "nmc_adam_step", "nmc_adam_step_device", "nmc_mse_grad"]
 
 _lib = None
@@ -67,6 +75,7 @@ def lib():
         L.nmc_scene_set_source.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.nmc_scene_set_source_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.nmc_measure_peaks.argtypes = [C.c_int, _fp]
+        L.nmc_measure_issue_peak.argtypes = [C.c_int, _fp]
         L.nmc_scene_dim.argtypes = [C.c_void_p]
         L.nmc_scene_bbox.argtypes = [C.c_void_p, _fp]
         L.nmc_scene_num_nodes.argtypes = [C.c_void_p]
@@ -81,6 +90,12 @@ def lib():
         L.nmc_point_seed.argtypes = [C.c_uint64, C.c_uint64]
         L.nmc_probe.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nmc_estimate_solution.argtypes = [C.c_void_p, C.POINTER(SolverOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.nmc_bvc_solve.argtypes = [C.c_void_p, C.POINTER(SolverOpts), C.POINTER(BvcOpts), C.c_void_p, C.c_void_p, C.c_int,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.nmc_bvc_splat.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                    C.c_float, C.c_void_p]
         _lib = L
     return _lib
 
@@ -99,10 +114,17 @@ def device_count():
 
 
 def measure_peaks(device=0):
-    """Instruction-throughput peaks of the device in warp-instructions/s: (fp32 FMA = issue limit, MUFU, fp64 FMA)."""
+    """Pipe-throughput peaks of the device in warp-instructions/s: (fp32 FMA, MUFU, fp64 FMA)."""
     out = (C.c_float*3)()
     check(lib().nmc_measure_peaks(int(device), out))
     return float(out[0]), float(out[1]), float(out[2])
+
+
+def measure_issue_peak(device=0):
+    """(dispatch limit in warp-instructions/s = 4 x SMs x SM clock under load, that clock in Hz)."""
+    out = (C.c_float*2)()
+    check(lib().nmc_measure_issue_peak(int(device), out))
+    return float(out[0]), float(out[1])
 
 
 def bessel_table():
@@ -201,6 +223,29 @@ class SceneHandle:
         check(lib().nmc_wost_solve_device(self._h, C.byref(opts), C.c_void_p(pts_ptr), n, C.c_uint64(index_offset),
                                           C.c_void_p(p_ptr), C.c_void_p(g_ptr), C.c_void_p(stream),
                                           C.byref(stats) if stats is not None else None))
+
+    def estimate_solution(self, opts, pts, n_walks, normals=None, types=None, aligned=None, index_offset=0):
+        """EstimationQuantity::Solution at the given points (deterministic replay); types: 0 in the domain, 2 on the
+        reflecting boundary.  Returns (solution[N], stats[N, 4] = variance, averaged walks, mean walk length, first radius)."""
+        pts = _f32(pts).reshape(-1, self.dim)
+        n = len(pts)
+        nr = None if normals is None else _f32(normals).reshape(n, self.dim)
+        ty = None if types is None else np.ascontiguousarray(types, dtype=np.int32)
+        al = None if aligned is None else np.ascontiguousarray(aligned, dtype=np.int32)
+        sol = np.zeros(n, np.float32); st = np.zeros((n, 4), np.float32)
+        check(lib().nmc_estimate_solution(self._h, C.byref(opts), _ptr(pts), _ptr(nr), _ptr(ty), _ptr(al), n, int(n_walks),
+                                          C.c_uint64(index_offset), _ptr(sol), _ptr(st)))
+        return sol, st
+
+    def bvc_solve(self, opts, bvc_opts, cache_cap=1 << 16):
+        """Boundary value caching on the device.  Returns (grid[res, res] indexed [i][j] as createEvaluationGrid,
+        cache[n, 6] = x, y, nx, ny, estimated solution, pdf, number of domain cache points)."""
+        res = int(bvc_opts.gridRes)
+        grid = np.zeros((res, res), np.float32)
+        cache = np.zeros((cache_cap, 6), np.float32)
+        nb, nd = C.c_int(0), C.c_int(0)
+        check(lib().nmc_bvc_solve(self._h, C.byref(opts), C.byref(bvc_opts), _ptr(grid), _ptr(cache), cache_cap, C.byref(nb), C.byref(nd)))
+        return grid, cache[: min(nb.value, cache_cap)].copy(), nd.value
 
     def probe(self, kind, n, pts=None, aux0=None, aux1=None, aux2=None, aux3=None, params=None):
         width = {PROBE_RAY: 2 + 2 * self.dim, PROBE_GREENS: 10, PROBE_GREENS_FAST: 10, PROBE_SAMPLE_VOLUME: 3,

@@ -13,26 +13,11 @@
 using namespace nmc;
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int nmcFail(int code, const std::string& msg) { g_err = msg; return code; }
+static int fail(int code, const std::string& msg) { return nmcFail(code, msg); }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(NMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
-struct nmc_scene {
-	int device = 0, smCount = 148;
-	FlatScene flat;
-	SceneView view;
-	float4 *d_nodes = nullptr, *d_prims = nullptr, *d_primN = nullptr, *d_nrmV = nullptr, *d_sils = nullptr, *d_silsU = nullptr, *d_grpP = nullptr, *d_grpS = nullptr, *d_rayP = nullptr, *d_rayN = nullptr;
-	float* d_src = nullptr; size_t srcCap = 0;
-	// grow-only work buffers
-	float* d_work = nullptr; size_t workCap = 0;      // points + outputs for the host-buffer entry point
-	float* d_lhs = nullptr; size_t lhsCap = 0;        // deterministic-mode Latin-hypercube scratch
-	Counters* d_counters = nullptr;
-	unsigned int* d_workCounter = nullptr;
-	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	// the work buffers, counters and events above are per-scene mutable state: calls on one scene are serialised
-	// (the reference serialises them by holding the GIL, demo.cpp:119; the bindings here release it)
-	std::mutex mu;
-};
-typedef std::lock_guard<std::mutex> Lock;
+#include "capi_scene.h"
 
 extern "C" const char* nmc_last_error(void) { return g_err.c_str(); }
 
@@ -100,6 +85,8 @@ extern "C" nmc_scene* nmc_scene_create(int dim, const float* verts, int nV, cons
 	s->device = device;
 	cudaDeviceGetAttribute(&s->smCount, cudaDevAttrMultiProcessorCount, device);
 	buildFlatScene(dim, verts, nV, prims, nP, opts->isDoubleSided != 0, s->flat);
+	s->verts.assign(verts, verts + (size_t)nV*dim);
+	s->prims.assign(prims, prims + (size_t)nP*dim);
 	SceneView& v = s->view;
 	memset(&v, 0, sizeof(v));
 	v.dim = dim; v.nNodes = s->flat.nNodes; v.nPrims = s->flat.nPrims; v.nSilRefs = s->flat.nSilRefs;
@@ -161,7 +148,9 @@ extern "C" int nmc_scene_nodes(const nmc_scene* s, float* out) {
 	return NMC_OK;
 }
 
-static int toParams(const nmc_solver_opts* o, SolverParams& p) {
+int nmcToParams(const nmc_solver_opts* o, SolverParams& p);
+static int toParams(const nmc_solver_opts* o, SolverParams& p) { return nmcToParams(o, p); }
+int nmcToParams(const nmc_solver_opts* o, SolverParams& p) {
 	if (!o) return fail(NMC_ERR_INVALID, "null solver options");
 	if (o->useCosineSamplingForDerivatives) return fail(NMC_ERR_UNSUPPORTED, "useCosineSamplingForDirectionalDerivatives is not supported");
 	if (o->nWalks < 0 || o->maxWalkLength < 0) return fail(NMC_ERR_INVALID, "negative nWalks / maxWalkLength");
@@ -288,11 +277,17 @@ extern "C" int nmc_wost_solve(nmc_scene* s, const nmc_solver_opts* opts, const f
 	return nmc_wost_solve_stats(s, opts, pts, n, index_offset, p_out, grad_out, nullptr, stats);
 }
 
+int nmcProbeUnlocked(nmc_scene* s, int kind, int64_t n, const float* pts, const float* aux0, const float* aux1,
+						 const float* aux2, const float* aux3, const float* params, float* out);
 extern "C" int nmc_probe(nmc_scene* s, int kind, int64_t n, const float* pts, const float* aux0, const float* aux1,
 						 const float* aux2, const float* aux3, const float* params, float* out) {
 	if (!s || !out || n < 0) return fail(NMC_ERR_INVALID, "bad arguments");
 	if (n == 0) return NMC_OK;
 	Lock lock(s->mu);
+	return nmcProbeUnlocked(s, kind, n, pts, aux0, aux1, aux2, aux3, params, out);
+}
+int nmcProbeUnlocked(nmc_scene* s, int kind, int64_t n, const float* pts, const float* aux0, const float* aux1,
+						 const float* aux2, const float* aux3, const float* params, float* out) {
 	CK(cudaSetDevice(s->device));
 	const int dim = s->flat.dim;
 	int W = probeWidth(dim, kind);

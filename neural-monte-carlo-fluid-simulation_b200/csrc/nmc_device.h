@@ -16,6 +16,9 @@ size_t deterministicScratchFloats(int dim, const SolverParams& o, long long n);
 cudaError_t launchProbe(const SceneView& S, int kind, long long n, const float* d_pts, const float* a0, const float* a1,
 						const float* a2, const float* a3, const float* params, float* d_out, cudaStream_t stream);
 int probeWidth(int dim, int kind);
+cudaError_t launchSolutionEstimator(const SceneView& S, const SolverParams& o, const float* d_pts, const float* d_normals,
+									const int* d_types, const int* d_aligned, long long n, int nWalks, unsigned long long indexOffset,
+									float* d_sol, float* d_stats4, Counters* d_counters, cudaStream_t stream);
 
 // wost_fast.cu
 struct FastLaunchInfo { int grid, block, smemBytes; };

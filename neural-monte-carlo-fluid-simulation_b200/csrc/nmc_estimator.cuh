@@ -45,23 +45,29 @@ NMC_HD void welford(float est, float& mean, float& M2, int N) { // :863-868
 	M2 += delta*delta2;
 }
 
-// walk() :135-329 (firstSphereRadius == 0 on this path, :580)
+// walk() :135-329.  firstSphereRadius == 0 on the solution-and-gradient path (:580); estimateSolution passes the radius it
+// precomputed for the sample point (:405-425), which replaces the first step's star radius (:148-149).
 template <int DIM>
 NMC_HD int detWalk(const SceneView& S, const SolverParams& o, float dirichletDist, Pcg32& rng,
-				   BallExact<DIM>& g, WalkState& st, unsigned& steps) {
+				   BallExact<DIM>& g, WalkState& st, unsigned& steps, float firstSphereRadius = 0.0f) {
 	typedef ExactMath M;
+	bool firstStep = true;
 	while (dirichletDist > o.epsilonShell) {
 		steps++;
 		float starR;
-		bool flipOrient = false;
-		if (S.doubleSided && st.onNeumann) { // :154-160
-			if (st.prevDist > 0.0f && dot(st.prevDir, st.normal) < 0.0f) { st.normal = st.normal*-1.0f; flipOrient = true; }
-		}
-		if (o.stepsBeforeUsingMaximalSpheres <= st.walkLength) starR = dirichletDist;
+		if (firstStep && firstSphereRadius > 0.0f) starR = firstSphereRadius;
 		else {
-			starR = starRadius<DIM, M>(S, st.pt, o.minStarRadius, dirichletDist, o.silhouettePrecision, flipOrient);
-			if (o.minStarRadius <= dirichletDist) starR = maxS(kShrink*starR, o.minStarRadius);
+			bool flipOrient = false;
+			if (S.doubleSided && st.onNeumann) { // :154-160
+				if (st.prevDist > 0.0f && dot(st.prevDir, st.normal) < 0.0f) { st.normal = st.normal*-1.0f; flipOrient = true; }
+			}
+			if (o.stepsBeforeUsingMaximalSpheres <= st.walkLength) starR = dirichletDist;
+			else {
+				starR = starRadius<DIM, M>(S, st.pt, o.minStarRadius, dirichletDist, o.silhouettePrecision, flipOrient);
+				if (o.minStarRadius <= dirichletDist) starR = maxS(kShrink*starR, o.minStarRadius);
+			}
 		}
+		firstStep = false;
 		g.update(st.pt, starR);
 
 		float u0 = rng.nextFloat();
@@ -226,6 +232,47 @@ NMC_HD void detEstimatePoint(const SceneView& S, const SolverParams& o, V3 x, ui
 	out.meanFirstSource = totalFirstSource/(nSol > 1 ? nSol : 1);
 	out.nSol = nSol; out.totalWalkLength = totalWalkLength; out.active = active ? 1 : 0;
 	out.walksStarted = walksStarted; out.steps = steps;
+}
+
+// estimateSolution (walk_on_stars.h:354-461): EstimationQuantity::Solution at one sample point that lies in the domain
+// (type 0) or ON the reflecting boundary (type 2 = SampleType::OnNeumannBoundary, with its unit normal) -- the estimator
+// boundary value caching runs at its cache points (boundary_sampler.h:148-185).  The bindings have no Dirichlet geometry,
+// so SampleType::OnDirichletBoundary cannot occur.  One pcg32 stream per point, not re-seeded between walks.
+// out4: mean, M2, number of estimates, summed walk length; *firstR receives firstSphereRadius.
+template <int DIM>
+NMC_HD void detEstimateSolution(const SceneView& S, const SolverParams& o, V3 x, V3 nrm, int type, bool normalAligned,
+								int nWalks, uint64_t globalIndex, float* out4, float* firstR, unsigned& walksStarted, unsigned& steps) {
+	typedef ExactMath M;
+	const float dDist = distDirichlet<DIM>(S, x);
+	if (dDist <= o.epsilonShell) nWalks = 1; // :382-385
+	V3 currentNormal = nrm, prevDir = nrm;
+	bool flip = false;
+	if (S.doubleSided && type == 2 && normalAligned) { currentNormal = nrm*-1.0f; prevDir = nrm*-1.0f; flip = true; } // :395-401
+	float firstSphereRadius;
+	if (dDist > o.epsilonShell && o.stepsBeforeUsingMaximalSpheres != 0) { // :405-425
+		float starR = starRadius<DIM, M>(S, x, o.minStarRadius, dDist, o.silhouettePrecision, flip);
+		if (o.minStarRadius <= dDist) starR = maxS(kShrink*starR, o.minStarRadius);
+		firstSphereRadius = starR;
+	} else firstSphereRadius = dDist;
+	float mean = 0.0f, M2 = 0.0f;
+	int nSol = 0, totalLen = 0;
+	Pcg32 rng; rng.seed(pointSeed(o.seed, globalIndex), 1);
+	for (int w = 0; w < nWalks; w++) {
+		BallExact<DIM> g; g.init(S.absorption > 0.0f && o.stepsBeforeApplyingTikhonov == 0, S.absorption);
+		WalkState st;
+		st.pt = x; st.normal = currentNormal; st.prevDir = prevDir; st.srcGradDir = st.bdyGradDir = mk(0, 0, 0);
+		st.prevDist = kMaxF; st.throughput = 1.0f; st.onNeumann = type == 2;
+		st.totalNeumann = st.totalSource = st.firstSource = 0.0f; st.walkLength = 0;
+		walksStarted++;
+		int code = detWalk<DIM>(S, o, dDist, rng, g, st, steps, firstSphereRadius);
+		if (code == kReachedDirichlet || code == kRussianRoulette) { // :446-458; terminal value 0 (pde.dirichlet == 0, initVal == 0)
+			float total = st.throughput*0.0f + st.totalNeumann + st.totalSource;
+			nSol += 1; welford(total, mean, M2, nSol);
+			totalLen += st.walkLength;
+		}
+	}
+	out4[0] = mean; out4[1] = M2; out4[2] = (float)nSol; out4[3] = (float)totalLen;
+	if (firstR) *firstR = firstSphereRadius;
 }
 
 } // namespace nmc

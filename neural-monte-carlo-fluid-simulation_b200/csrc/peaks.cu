@@ -60,6 +60,30 @@ __global__ void __launch_bounds__(256) dfmaPeak(float* out, double a, double b) 
 	if (s == 12345.678) out[0] = (float)s;
 }
 
+// SM clock under load: cycles (clock64) per nanosecond (globaltimer) over a busy window, on every SM's first CTA.
+__global__ void __launch_bounds__(256) clockProbe(unsigned long long* out, float a, float b) {
+	unsigned long long t0 = 0, c0 = 0;
+	if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); c0 = clock64(); }
+	float v[kChains];
+#pragma unroll
+	for (int k = 0; k < kChains; k++) v[k] = a + (float)(threadIdx.x + k);
+#pragma unroll 1
+	for (int i = 0; i < 4*kIters; i++) {
+#pragma unroll
+		for (int k = 0; k < kChains; k++) v[k] = fmaf(v[k], a, b);
+	}
+	float s = 0.0f;
+#pragma unroll
+	for (int k = 0; k < kChains; k++) s += v[k];
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long t1, c1 = clock64();
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		out[2*blockIdx.x] = c1 - c0; out[2*blockIdx.x + 1] = t1 - t0;
+	}
+	if (s == 12345.678f) out[0] = (unsigned long long)s;
+}
+
 template <class F>
 cudaError_t timeKernel(F launch, double warpInstPerLaunch, float* rate) {
 	cudaEvent_t e0, e1;
@@ -100,4 +124,37 @@ extern "C" int nmc_measure_peaks(int device, float* out3) {
 	if (e == cudaSuccess) e = timeKernel([&] { dfmaPeak<<<grid, block>>>(d, 0.999, 1e-3); }, warps*(kIters/16)*kChains, &out3[2]);
 	cudaFree(d);
 	return e == cudaSuccess ? NMC_OK : NMC_ERR_CUDA;
+}
+
+// Issue limit of the device: every SM sub-partition (4 per SM) dispatches at most one warp instruction per clock, so
+//   out2[0] = 4 x SMs x (SM clock measured under load)   [warp instructions / s],   out2[1] = that clock in Hz.
+// (A pure FFMA stream reaches ~2/3 of it on B200 -- nmc_measure_peaks()[0] -- because the FMA pipe, not dispatch, limits it;
+// a kernel that mixes FMA, ALU, XU and LSU instructions, like the walk kernel, can exceed the FFMA rate.)
+extern "C" int nmc_measure_issue_peak(int device, float* out2) {
+	if (!out2) return NMC_ERR_INVALID;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return NMC_ERR_NO_DEVICE; }
+	if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return NMC_ERR_CUDA; }
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	const int grid = sms*8;
+	unsigned long long* d = nullptr;
+	if (cudaMalloc((void**)&d, sizeof(unsigned long long)*2*grid) != cudaSuccess) return NMC_ERR_CUDA;
+	unsigned long long* hbuf = new unsigned long long[2*grid];
+	double best = 0.0;
+	cudaError_t e = cudaSuccess;
+	for (int rep = 0; rep < 3 && e == cudaSuccess; rep++) {
+		clockProbe<<<grid, 256>>>(d, 0.999f, 1e-3f);
+		e = cudaMemcpy(hbuf, d, sizeof(unsigned long long)*2*grid, cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) break;
+		double cyc = 0.0, ns = 0.0;
+		for (int i = 0; i < grid; i++) { cyc += (double)hbuf[2*i]; ns += (double)hbuf[2*i + 1]; }
+		if (rep > 0 && ns > 0.0 && cyc/ns > best) best = cyc/ns; // GHz
+	}
+	delete[] hbuf;
+	cudaFree(d);
+	if (e != cudaSuccess) { cudaGetLastError(); return NMC_ERR_CUDA; }
+	out2[1] = (float)(best*1e9);
+	out2[0] = (float)(4.0*sms*best*1e9);
+	return NMC_OK;
 }

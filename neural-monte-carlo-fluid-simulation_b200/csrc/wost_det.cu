@@ -63,6 +63,51 @@ cudaError_t launchDeterministic(const SceneView& S, const SolverParams& o, const
 	return cudaGetLastError();
 }
 
+// ---- solution-only estimator at caller-given sample points (boundary value caching's cache points) ----------------------
+template <int DIM>
+__global__ void __launch_bounds__(128)
+detSolutionKernel(SceneView S, SolverParams o, const float* __restrict__ pts, const float* __restrict__ normals,
+				  const int* __restrict__ types, const int* __restrict__ aligned, long long n, int nWalks,
+				  unsigned long long indexOffset, float* __restrict__ sol, float* __restrict__ stats4, Counters* __restrict__ counters) {
+	long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	unsigned started = 0, completed = 0, steps = 0;
+	if (i < n) {
+		V3 x = mk(pts[i*DIM], pts[i*DIM + 1], DIM == 3 ? pts[i*DIM + 2] : 0.0f);
+		V3 nr = normals ? mk(normals[i*DIM], normals[i*DIM + 1], DIM == 3 ? normals[i*DIM + 2] : 0.0f) : mk(0, 0, 0);
+		float r4[4], firstR = 0.0f;
+		detEstimateSolution<DIM>(S, o, x, nr, types ? types[i] : 0, aligned ? aligned[i] != 0 : false, nWalks,
+								 indexOffset + (unsigned long long)i, r4, &firstR, started, steps);
+		sol[i] = r4[0];
+		completed = (unsigned)r4[2];
+		if (stats4) { // layout of oracle/ref_harness.cpp ref_estimate_solution: variance, count, mean walk length, first sphere radius
+			const int nSol = (int)r4[2];
+			stats4[i*4] = r4[1]/(nSol - 1 > 1 ? nSol - 1 : 1); stats4[i*4 + 1] = r4[2];
+			stats4[i*4 + 2] = r4[3]/(nSol > 1 ? nSol : 1); stats4[i*4 + 3] = firstR;
+		}
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		started += __shfl_down_sync(0xffffffffu, started, off);
+		completed += __shfl_down_sync(0xffffffffu, completed, off);
+		steps += __shfl_down_sync(0xffffffffu, steps, off);
+	}
+	if ((threadIdx.x & 31) == 0 && counters) {
+		atomicAdd(&counters->walksStarted, (unsigned long long)started);
+		atomicAdd(&counters->walksCompleted, (unsigned long long)completed);
+		atomicAdd(&counters->steps, (unsigned long long)steps);
+	}
+}
+
+cudaError_t launchSolutionEstimator(const SceneView& S, const SolverParams& o, const float* d_pts, const float* d_normals,
+									const int* d_types, const int* d_aligned, long long n, int nWalks, unsigned long long indexOffset,
+									float* d_sol, float* d_stats4, Counters* d_counters, cudaStream_t stream) {
+	if (n <= 0) return cudaSuccess;
+	const int block = 128;
+	unsigned grid = (unsigned)((n + block - 1)/block);
+	if (S.dim == 2) detSolutionKernel<2><<<grid, block, 0, stream>>>(S, o, d_pts, d_normals, d_types, d_aligned, n, nWalks, indexOffset, d_sol, d_stats4, d_counters);
+	else detSolutionKernel<3><<<grid, block, 0, stream>>>(S, o, d_pts, d_normals, d_types, d_aligned, n, nWalks, indexOffset, d_sol, d_stats4, d_counters);
+	return cudaGetLastError();
+}
+
 // ---- probes ---------------------------------------------------------------------------------------
 int probeWidth(int dim, int kind) {
 	switch (kind) {

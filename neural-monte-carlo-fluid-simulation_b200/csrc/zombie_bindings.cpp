@@ -21,6 +21,8 @@
 #include <vector>
 
 #include "../../include/nmcfs.h"
+#include "image_io.h"
+#include <filesystem>
 
 #ifndef NMC_BIND_DIM
 #define NMC_BIND_DIM 2
@@ -81,11 +83,29 @@ public:
 
 	Scene(const py::dict& config, py::array_t<float, py::array::c_style | py::array::forcecast> source) {
 		if (source.ndim() != DIM) throw py::type_error("sourceValue must be a " + std::to_string(DIM) + "-dimensional array");
-		isWatertight = optional<bool>(config, "isWatertight", false);
+		const int shape[3] = {(int)source.shape(0), (int)source.shape(1), DIM == 3 ? (int)source.shape(2) : 1};
+		init(config, source.data(), shape, false, false);
+	}
+	// Scene(config) of the 2D module (scene.h:22-52): the source grid comes from the image file config["sourceValue"];
+	// isWatertight and flipOrientation default to TRUE here (false in the two-argument form).  PFM files only.
+	Scene(const py::dict& config) {
+		if (DIM != 2) throw std::runtime_error("Scene(config) exists in the 2D module only");
+		const std::string file = required<std::string>(config, "sourceValue");
+		if (!nmc_io::hasExtension(file, "pfm")) throw std::runtime_error("Scene(config): only PFM source images are supported (" + file + ")");
+		int h = 0, w = 0;
+		std::vector<float> grid;
+		nmc_io::readPfmGrey(file, h, w, grid);
+		const int shape[3] = {h, w, 1};
+		init(config, grid.data(), shape, true, true);
+	}
+
+private:
+	void init(const py::dict& config, const float* source, const int* shape, bool watertightDefault, bool flipDefault) {
+		isWatertight = optional<bool>(config, "isWatertight", watertightDefault);
 		isDoubleSided = optional<bool>(config, "isDoubleSided", false);
 		const std::string boundary = required<std::string>(config, "boundary");
 		const bool normalize = DIM == 2 ? optional<bool>(config, "normalizeDomain", false) : false; // zombie3d ignores both
-		const bool flip = DIM == 2 ? optional<bool>(config, "flipOrientation", false) : false;
+		const bool flip = DIM == 2 ? optional<bool>(config, "flipOrientation", flipDefault) : false;
 		std::vector<float> verts; std::vector<int> prims;
 		loadObj(boundary, flip, verts, prims);
 		const int nV = (int)verts.size()/DIM, nP = (int)prims.size()/DIM;
@@ -106,15 +126,11 @@ public:
 		int device = 0;
 		if (const char* lr = std::getenv("LOCAL_RANK")) { if (nmc_device_count() > 1) device = std::atoi(lr); }
 		if (config.contains("device")) device = config["device"].cast<int>();
-		handle = nmc_scene_create(DIM, verts.data(), nV, prims.data(), nP, source.data(), (int)source.shape(0), (int)source.shape(1),
-								  DIM == 3 ? (int)source.shape(2) : 1, &so, device);
+		handle = nmc_scene_create(DIM, verts.data(), nV, prims.data(), nP, source, shape[0], shape[1], shape[2], &so, device);
 		if (!handle) throw std::runtime_error(std::string("zombie_bindings.Scene: ") + nmc_last_error());
 	}
-	Scene(const py::dict&) {
-		// 1-argument constructor of the 2D module loads the source from an image file (scene.h:22-52);
-		// src/2d never calls it
-		throw std::runtime_error("Scene(config): image-file sources are not provided; use Scene(config, sourceValue)");
-	}
+
+public:
 	~Scene() { nmc_scene_destroy(handle); }
 	Scene(const Scene&) = delete;
 	Scene& operator=(const Scene&) = delete;
@@ -189,13 +205,61 @@ static py::tuple wostArray(const Scene& scene, const py::dict& solver, const py:
 	return py::make_tuple(ap, ag);
 }
 
+#if NMC_BIND_DIM == 2
+// bvc(scene, solverConfig, outputConfig) -> None: runBoundaryValueCaching (demo.cpp:265-363); writes outputConfig["solutionFile"]
+// (default "solution.pfm") and, unless saveColormapped is false, <stem>_color<ext> (demo/grid.h:9-33, 370-415).
+static py::array_t<float> bvcGrid(const Scene& scene, const py::dict& solver, const py::dict& output) {
+	nmc_solver_opts o = solverOpts(solver, output);
+	o.mode = NMC_MODE_DETERMINISTIC; // the cache-point estimator is the deterministic replay (its seed comes from set_seed() or the OS)
+	nmc_bvc_opts b;
+	b.boundaryCacheSize = optional<int>(solver, "boundaryCacheSize", 1024);
+	b.domainCacheSize = optional<int>(solver, "domainCacheSize", 1024);
+	b.nWalksForCachedSolutionEstimates = optional<int>(solver, "nWalksForCachedSolutionEstimates", 128);
+	b.nWalksForCachedGradientEstimates = optional<int>(solver, "nWalksForCachedGradientEstimates", 640);
+	b.gridRes = required<int>(output, "gridRes");
+	b.normalOffsetForCachedDirichletSamples = optional<float>(solver, "normalOffsetForCachedDirichletSamples", 5.0f*o.epsilonShell);
+	b.radiusClampForKernels = optional<float>(solver, "radiusClampForKernels", 1e-3f);
+	b.regularizationForKernels = optional<float>(solver, "regularizationForKernels", 0.0f);
+	if (b.gridRes <= 0) throw py::value_error("gridRes must be positive");
+	py::array_t<float> grid({(int64_t)b.gridRes, (int64_t)b.gridRes});
+	int rc;
+	{
+		py::gil_scoped_release nogil;
+		rc = nmc_bvc_solve(scene.handle, &o, &b, grid.mutable_data(), nullptr, 0, nullptr, nullptr);
+	}
+	if (rc != NMC_OK) throw std::runtime_error(std::string("zombie_bindings.bvc: ") + nmc_last_error());
+	return grid;
+}
+
+static void bvc(const Scene& scene, const py::dict& solver, const py::dict& output) {
+	py::array_t<float> grid = bvcGrid(scene, solver, output);
+	const int res = (int)grid.shape(0);
+	const std::string solutionFile = optional<std::string>(output, "solutionFile", "solution.pfm");
+	const bool saveColormapped = optional<bool>(output, "saveColormapped", true);
+	const std::string colormap = optional<std::string>(output, "colormap", "");
+	const float lo = optional<float>(output, "colormapMinVal", 0.0f), hi = optional<float>(output, "colormapMaxVal", 1.0f);
+	// solution->get(j, i) = value of point (i, j): image row <-> y index, column <-> x index (grid.h:388-411)
+	std::vector<float> img((size_t)3*res*res), col((size_t)3*res*res);
+	const float* g = grid.data();
+	for (int i = 0; i < res; i++) for (int j = 0; j < res; j++) {
+		const float v = g[(size_t)i*res + j];
+		float* px = &img[(size_t)3*((size_t)j*res + i)];
+		px[0] = px[1] = px[2] = v;
+		nmc_io::applyColormap(std::min(std::max((v - lo)/(hi - lo), 0.0f), 1.0f), colormap, &col[(size_t)3*((size_t)j*res + i)]);
+	}
+	std::filesystem::path path(solutionFile);
+	if (!path.parent_path().empty()) std::filesystem::create_directories(path.parent_path());
+	nmc_io::writeImage3(solutionFile, res, res, img);
+	if (saveColormapped) nmc_io::writeImage3((path.parent_path()/path.stem()).string() + "_color" + path.extension().string(), res, res, col);
+}
+#endif
+
 PYBIND11_MODULE(zombie_bindings, m) {
 	m.doc() = "pybind11 WoSt"; // as the reference
 	m.def("wost", &wost);
 #if NMC_BIND_DIM == 2
-	m.def("bvc", [](const Scene&, const py::dict&, const py::dict&) {
-		throw std::runtime_error("bvc (boundary value caching, demo.cpp:265-363) is outside the pressure-projection path and not provided");
-	});
+	m.def("bvc", &bvc);
+	m.def("bvc_grid", &bvcGrid, "additive: the masked evaluation grid of bvc() as a numpy array [i][j] instead of image files");
 #endif
 	auto cls = py::class_<Scene>(m, "Scene");
 #if NMC_BIND_DIM == 2

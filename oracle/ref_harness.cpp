@@ -265,6 +265,153 @@ int ref_wost(void* h, const char* solver_json, const char* output_json,
 	return 0;
 }
 
+// ---- solution-only estimator (walk_on_stars.h:354-461, EstimationQuantity::Solution) at caller-given points -------------
+// types: 0 = InDomain, 2 = OnNeumannBoundary (zombie::SampleType); normals: n x DIM (used by boundary starts);
+// aligned: estimateBoundaryNormalAligned per point (may be null).  stats (may be null): per point 4 floats
+// [0] variance [1] number of estimates [2] mean walk length [3] firstSphereRadius
+static zombie::WalkSettings<float> walk_settings_from(const json& solverConfig, bool solveDoubleSided) {
+	const bool disableGradientControlVariates = getOptional<bool>(solverConfig, "disableGradientControlVariates", false);
+	const bool disableGradientAntitheticVariates = getOptional<bool>(solverConfig, "disableGradientAntitheticVariates", false);
+	const bool useCosineSamplingForDirectionalDerivatives = getOptional<bool>(solverConfig, "useCosineSamplingForDirectionalDerivatives", false);
+	const bool ignoreDirichlet = getOptional<bool>(solverConfig, "ignoreDirichlet", false);
+	const bool ignoreNeumann = getOptional<bool>(solverConfig, "ignoreNeumann", false);
+	const bool ignoreSource = getOptional<bool>(solverConfig, "ignoreSource", false);
+	const int maxWalkLength = getOptional<int>(solverConfig, "maxWalkLength", 1024);
+	const int stepsBeforeApplyingTikhonov = getOptional<int>(solverConfig, "setpsBeforeApplyingTikhonov", maxWalkLength);
+	const int stepsBeforeUsingMaximalSpheres = getOptional<int>(solverConfig, "setpsBeforeUsingMaximalSpheres", maxWalkLength);
+	const float epsilonShell = getOptional<float>(solverConfig, "epsilonShell", 1e-3f);
+	const float minStarRadius = getOptional<float>(solverConfig, "minStarRadius", 1e-3f);
+	const float silhouettePrecision = getOptional<float>(solverConfig, "silhouettePrecision", 1e-3f);
+	const float russianRouletteThreshold = getOptional<float>(solverConfig, "russianRouletteThreshold", 0.0f);
+	return zombie::WalkSettings<float>(0.0f, epsilonShell, minStarRadius, silhouettePrecision, russianRouletteThreshold,
+									   maxWalkLength, stepsBeforeApplyingTikhonov, stepsBeforeUsingMaximalSpheres, solveDoubleSided,
+									   !disableGradientControlVariates, !disableGradientAntitheticVariates,
+									   useCosineSamplingForDirectionalDerivatives, ignoreDirichlet, ignoreNeumann, ignoreSource, false);
+}
+
+int ref_estimate_solution(void* h, const char* solver_json, const float* pts, const float* normals, const int* types,
+						  const int* aligned, int n, int nWalks, uint64_t seed, uint64_t index_offset, int nthreads,
+						  float* sol_out, float* stats) {
+	Scene& scene = *((RefScene*)h)->scene;
+	json solverConfig = json::parse(solver_json);
+	const zombie::GeometricQueries<REF_DIM>& queries = scene.queries;
+	const zombie::PDE<float, REF_DIM>& pde = scene.pde;
+	zombie::WalkSettings<float> walkSettings = walk_settings_from(solverConfig, scene.isDoubleSided);
+	zombie::WalkOnStars<float, REF_DIM> walkOnStars(queries);
+	std::vector<zombie::SamplePoint<float, REF_DIM>> samplePts;
+	samplePts.reserve(n);
+	for (int i = 0; i < n; i++) {
+		VecD pt, nr = VecD::Zero();
+		for (int k = 0; k < DIM; k++) { pt[k] = pts[(size_t)i*DIM + k]; if (normals) nr[k] = normals[(size_t)i*DIM + k]; }
+		zombie::SampleType ty = types && types[i] == 2 ? zombie::SampleType::OnNeumannBoundary : zombie::SampleType::InDomain;
+		float dDist = queries.computeDistToDirichlet(pt, false);
+		float nDist = queries.computeDistToNeumann(pt, false);
+		samplePts.emplace_back(zombie::SamplePoint<float, REF_DIM>(pt, nr, ty, 1.0f, dDist, nDist, 0.0f));
+		if (aligned && aligned[i]) samplePts.back().estimateBoundaryNormalAligned = true;
+	}
+	zombie::SampleEstimationData<REF_DIM> est(nWalks, zombie::EstimationQuantity::Solution);
+	parallel_points(n, nthreads, [&](int i) {
+		samplePts[i].sampler.seed(nmc_point_seed(seed, index_offset + (uint64_t)i), 1);
+		nmc_shim::current_sampler = &samplePts[i].sampler;
+		walkOnStars.solve(pde, walkSettings, est, samplePts[i]);
+		nmc_shim::current_sampler = nullptr;
+	});
+	for (int i = 0; i < n; i++) {
+		auto& st = *samplePts[i].statistics;
+		sol_out[i] = st.getEstimatedSolution();
+		if (stats) {
+			stats[(size_t)i*4 + 0] = st.getEstimatedSolutionVariance();
+			stats[(size_t)i*4 + 1] = (float)st.getSolutionEstimateCount();
+			stats[(size_t)i*4 + 2] = st.getMeanWalkLength();
+			stats[(size_t)i*4 + 3] = samplePts[i].firstSphereRadius;
+		}
+	}
+	return 0;
+}
+
+#if REF_DIM == 2
+// ---- boundary value caching: mirrors demo.cpp runBoundaryValueCaching (:265-363) up to saveEvaluationGrid's masking (grid.h:388-411)
+// grid_out: gridRes*gridRes masked solution values, index i*gridRes + j <-> point (i, j) of createEvaluationGrid (grid.h:352-368).
+// cache_out (may be null): up to cache_cap boundary samples x 6 floats (x, y, nx, ny, estimated solution, pdf); *n_cache = their number.
+// The samplers' wall-clock seeds (boundary_sampler.h:103, domain_sampler.h:26, every SamplePoint) come from one pcg32 seeded with `seed`.
+int ref_bvc(void* h, const char* solver_json, const char* output_json, uint64_t seed, int nthreads,
+			float* grid_out, float* cache_out, int cache_cap, int* n_cache, int* n_domain) {
+	Scene& scene = *((RefScene*)h)->scene;
+	json solverConfig = json::parse(solver_json);
+	json outputConfig = json::parse(output_json);
+	const bool useFiniteDifferencesForBoundaryDerivatives = getOptional<bool>(solverConfig, "useFiniteDifferencesForBoundaryDerivatives", false);
+	const bool ignoreSource = getOptional<bool>(solverConfig, "ignoreSource", false);
+	const int nWalksForCachedSolutionEstimates = getOptional<int>(solverConfig, "nWalksForCachedSolutionEstimates", 128);
+	const int nWalksForCachedGradientEstimates = getOptional<int>(solverConfig, "nWalksForCachedGradientEstimates", 640);
+	const int boundaryCacheSize = getOptional<int>(solverConfig, "boundaryCacheSize", 1024);
+	const int domainCacheSize = getOptional<int>(solverConfig, "domainCacheSize", 1024);
+	const int gridRes = getRequired<int>(outputConfig, "gridRes");
+	const float epsilonShell = getOptional<float>(solverConfig, "epsilonShell", 1e-3f);
+	const float normalOffsetForCachedDirichletSamples = getOptional<float>(solverConfig, "normalOffsetForCachedDirichletSamples", 5.0f*epsilonShell);
+	const float radiusClampForKernels = getOptional<float>(solverConfig, "radiusClampForKernels", 1e-3f);
+	const float regularizationForKernels = getOptional<float>(solverConfig, "regularizationForKernels", 0.0f);
+	const float boundaryDistanceMask = getOptional<float>(outputConfig, "boundaryDistanceMask", 0.0);
+
+	fcpw::BoundingBox<2> bbox = scene.bbox;
+	const zombie::GeometricQueries<2>& queries = scene.queries;
+	const zombie::PDE<float, 2>& pde = scene.pde;
+	bool solveDoubleSided = scene.isDoubleSided;
+	std::function<bool(const Vector2&)> insideSolveRegionBoundarySampler = [&queries](const Vector2& x) -> bool { return !queries.outsideBoundingDomain(x); };
+	std::function<bool(const Vector2&)> insideSolveRegionDomainSampler = [&queries, solveDoubleSided](const Vector2& x) -> bool {
+		return solveDoubleSided ? !queries.outsideBoundingDomain(x) : queries.insideDomain(x);
+	};
+	std::function<bool(const Vector2&)> onNeumannBoundary = [&scene](const Vector2 &x) -> bool { return scene.onNeumannBoundary(x); };
+
+	pcg32 master(seed, 1);
+	nmc_shim::current_sampler = &master; // every clock read below draws from `master` (single-threaded set-up)
+	std::vector<zombie::SamplePoint<float, 2>> boundaryCache, boundaryCacheNormalAligned, domainCache;
+	std::vector<zombie::EvaluationPoint<float, 2>> evalPts;
+	createEvaluationGrid(evalPts, queries, bbox.pMin, bbox.pMax, gridRes);
+	zombie::WalkOnStars<float, 2> walkOnStars(queries);
+	zombie::BoundarySampler<float, 2> boundarySampler(scene.vertices, scene.segments, queries, walkOnStars,
+													  insideSolveRegionBoundarySampler, onNeumannBoundary);
+	zombie::DomainSampler<float, 2> domainSampler(queries, insideSolveRegionDomainSampler, bbox.pMin, bbox.pMax, scene.getSolveRegionVolume());
+	boundarySampler.initialize(normalOffsetForCachedDirichletSamples, solveDoubleSided);
+	boundarySampler.generateSamples(boundaryCacheSize, normalOffsetForCachedDirichletSamples, solveDoubleSided, 0.0f,
+									boundaryCache, boundaryCacheNormalAligned);
+	if (!ignoreSource) domainSampler.generateSamples(pde, domainCacheSize, domainCache);
+	nmc_shim::current_sampler = nullptr;
+
+	zombie::WalkSettings<float> walkSettings = walk_settings_from(solverConfig, solveDoubleSided);
+	// computeEstimates (boundary_sampler.h:148-226) uses tbb::parallel_for inside solve(); the per-point samplers were seeded
+	// from `master` at construction, so the estimates do not depend on the thread schedule
+	boundarySampler.computeEstimates(pde, walkSettings, nWalksForCachedSolutionEstimates, nWalksForCachedGradientEstimates,
+									 boundaryCache, useFiniteDifferencesForBoundaryDerivatives, nthreads <= 1);
+	boundarySampler.computeEstimates(pde, walkSettings, nWalksForCachedSolutionEstimates, nWalksForCachedGradientEstimates,
+									 boundaryCacheNormalAligned, useFiniteDifferencesForBoundaryDerivatives, nthreads <= 1);
+	zombie::Splatter<float, 2> splatter(queries, walkOnStars);
+	splatter.splat(pde, boundaryCache, radiusClampForKernels, regularizationForKernels, normalOffsetForCachedDirichletSamples, evalPts);
+	splatter.splat(pde, boundaryCacheNormalAligned, radiusClampForKernels, regularizationForKernels, normalOffsetForCachedDirichletSamples, evalPts);
+	splatter.splat(pde, domainCache, radiusClampForKernels, regularizationForKernels, normalOffsetForCachedDirichletSamples, evalPts);
+	splatter.estimatePointwiseNearDirichletBoundary(pde, walkSettings, normalOffsetForCachedDirichletSamples,
+													nWalksForCachedSolutionEstimates, evalPts, nthreads <= 1);
+	for (int i = 0; i < gridRes; i++) for (int j = 0; j < gridRes; j++) {
+		int idx = i*gridRes + j;
+		float inDomain = queries.insideDomain(evalPts[idx].pt) ? 1 : 0;
+		float value = evalPts[idx].getEstimatedSolution();
+		bool maskOutValue = (!inDomain && !solveDoubleSided) ||
+							std::min(std::abs(evalPts[idx].dirichletDist), std::abs(evalPts[idx].neumannDist)) < boundaryDistanceMask;
+		grid_out[idx] = maskOutValue ? 0.0f : value;
+	}
+	int nb = 0;
+	for (auto* cache : {&boundaryCache, &boundaryCacheNormalAligned}) for (auto& sp : *cache) {
+		if (cache_out && nb < cache_cap) {
+			float* c = cache_out + (size_t)nb*6;
+			c[0] = sp.pt[0]; c[1] = sp.pt[1]; c[2] = sp.normal[0]; c[3] = sp.normal[1]; c[4] = sp.solution; c[5] = sp.pdf;
+		}
+		nb++;
+	}
+	if (n_cache) *n_cache = nb;
+	if (n_domain) *n_domain = (int)domainCache.size();
+	return 0;
+}
+#endif
+
 // ---- probes: RNG (deps/pcg32/pcg32.h:40-112) ------------------------------------------------
 void ref_pcg32_uint(uint64_t initstate, uint64_t initseq, int n, uint32_t* out) {
 	pcg32 s(initstate, initseq);

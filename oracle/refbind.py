@@ -87,6 +87,31 @@ class RefScene:
                         _fp(st) if want_stats else None)
         return p, g, st
 
+    def estimate_solution(self, solver, pts, n_walks, normals=None, types=None, aligned=None, seed=0, index_offset=0, nthreads=1):
+        """EstimationQuantity::Solution (walk_on_stars.h:354-461) at the given points; types: 0 InDomain, 2 OnNeumannBoundary.
+        Returns (solution[N], stats[N, 4] = variance, number of estimates, mean walk length, first sphere radius)."""
+        pts = self._pts(pts)
+        n = len(pts)
+        nr = np.ascontiguousarray(normals, dtype=_f32).reshape(n, self.dim) if normals is not None else None
+        ty = np.ascontiguousarray(types, dtype=np.int32) if types is not None else None
+        al = np.ascontiguousarray(aligned, dtype=np.int32) if aligned is not None else None
+        sol = np.zeros(n, _f32); st = np.zeros((n, 4), _f32)
+        self.L.ref_estimate_solution(C.c_void_p(self.h), json.dumps(solver).encode(), _fp(pts), _fp(nr) if nr is not None else None,
+                                     _ip(ty) if ty is not None else None, _ip(al) if al is not None else None, n, int(n_walks),
+                                     C.c_uint64(seed), C.c_uint64(index_offset), nthreads, _fp(sol), _fp(st))
+        return sol, st
+
+    def bvc(self, solver, output, seed=0, nthreads=1, cache_cap=1 << 16):
+        """runBoundaryValueCaching (demo.cpp:265-363) up to the masked evaluation grid (2D only).  Returns
+        (grid[gridRes, gridRes] indexed [i][j] as createEvaluationGrid, cache[n, 6] = x, y, nx, ny, solution, pdf, n_domain)."""
+        res = int(output["gridRes"])
+        grid = np.zeros((res, res), _f32)
+        cache = np.zeros((cache_cap, 6), _f32)
+        nb = C.c_int(0); nd = C.c_int(0)
+        self.L.ref_bvc(C.c_void_p(self.h), json.dumps(solver).encode(), json.dumps(output).encode(), C.c_uint64(seed), nthreads,
+                       _fp(grid), _fp(cache), cache_cap, C.byref(nb), C.byref(nd))
+        return grid, cache[: min(nb.value, cache_cap)].copy(), nd.value
+
     # ---- probes -----------------------------------------------------------------------------
     def _pts(self, pts):
         return np.ascontiguousarray(pts, dtype=_f32).reshape(-1, self.dim)

@@ -37,8 +37,12 @@ bad = dict(cfg["scene"]); del bad["boundary"]
 assert raises(KeyError, lambda: zb.Scene(bad, src))
 assert raises(RuntimeError, lambda: zb.Scene(dict(cfg["scene"], boundary="/nonexistent.obj"), src))
 assert raises(TypeError, lambda: zb.Scene(cfg["scene"], np.zeros((3,)*(dim + 1), np.float32)))
-if dim == 2:
-    assert raises(RuntimeError, lambda: zb.Scene(cfg["scene"]))          # image-file source: not provided
+if dim == 2:  # Scene(config) (scene.h:22-52): the source grid comes from the image file config["sourceValue"]
+    assert raises(KeyError, lambda: zb.Scene(cfg["scene"]))                                        # no "sourceValue"
+    assert raises(RuntimeError, lambda: zb.Scene(dict(cfg["scene"], sourceValue="/nonexistent.pfm")))
+    assert raises(RuntimeError, lambda: zb.Scene(dict(cfg["scene"], sourceValue="/tmp/source.png")))  # PFM only
+else:
+    assert raises(TypeError, lambda: zb.Scene(cfg["scene"]))                                       # zombie3d has no such overload
 if where == "cpu":
     # no GPU here: creating a scene must fail loudly (no CPU fallback)
     assert raises(RuntimeError, lambda: zb.Scene(cfg["scene"], src))
@@ -47,7 +51,32 @@ if where == "cpu":
 
 scene = zb.Scene(cfg["scene"], src.tolist())                # nested lists, as src/*/models/model_split.py passes them
 if dim == 2:
-    assert raises(RuntimeError, lambda: zb.bvc(scene, cfg["solver"], cfg["output"]))
+    # Scene(config): the same grid read back from a PFM file gives the same estimates as Scene(config, grid);
+    # its defaults differ (isWatertight / flipOrientation true), so pass the two-argument form's explicitly
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    pfm = os.path.join(tmp, "source.pfm")
+    with open(pfm, "wb") as f:
+        f.write(b"Pf\n%d %d\n-1\n" % (src.shape[1], src.shape[0])); f.write(np.ascontiguousarray(src, "<f4").tobytes())
+    scene1 = zb.Scene(dict(cfg["scene"], sourceValue=pfm, isWatertight=cfg["scene"].get("isWatertight", False),
+                           flipOrientation=cfg["scene"].get("flipOrientation", False)))
+    q = util.random_points(np.array([-1.0, -0.5], np.float32), np.array([1.8, 0.5], np.float32), 64, seed=4)
+    zb.set_mode("deterministic"); zb.set_seed(3)
+    pa1, _ = zb.wost_array(scene1, cfg["solver"], cfg["output"], q)
+    pa2, _ = zb.wost_array(scene, cfg["solver"], cfg["output"], q)
+    assert np.allclose(pa1, pa2, rtol=1e-5, atol=1e-9) and np.abs(pa2).max() > 0     # the grey conversion rounds 0.299 + 0.587 + 0.114
+    # bvc(scene, solverConfig, outputConfig) -> None, writes the solution image and its colour-mapped copy (demo.cpp:265-363)
+    bsolver = dict(cfg["solver"], boundaryCacheSize=512, domainCacheSize=512, nWalksForCachedSolutionEstimates=16)
+    bout = dict(cfg["output"], gridRes=32, solutionFile=os.path.join(tmp, "out", "bvc.pfm"), colormap="turbo", colormapMinVal=-1e-3, colormapMaxVal=1e-3)
+    assert zb.bvc(scene, bsolver, bout) is None
+    assert os.path.getsize(os.path.join(tmp, "out", "bvc.pfm")) == len(b"PF\n32 32\n-1\n") + 32*32*3*4
+    assert os.path.exists(os.path.join(tmp, "out", "bvc_color.pfm"))
+    assert zb.bvc(scene, bsolver, dict(bout, solutionFile=os.path.join(tmp, "bvc.png"))) is None
+    with open(os.path.join(tmp, "bvc_color.png"), "rb") as f:
+        assert f.read(8) == b"\x89PNG\r\n\x1a\n"
+    grid = zb.bvc_grid(scene, bsolver, bout)
+    assert grid.shape == (32, 32) and np.isfinite(grid).all() and np.abs(grid).max() > 0
+    zb.set_seed(11)
 no_grid = dict(cfg["output"]); del no_grid["gridRes"]
 pts = util.random_points(*[np.asarray(v, np.float32) for v in ((-0.9,)*dim, (0.9,)*dim)], 300, seed=3) if dim == 3 else \
     util.random_points(np.array([-1.0, -0.5], np.float32), np.array([1.8, 0.5], np.float32), 300, seed=3)

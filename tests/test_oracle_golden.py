@@ -160,3 +160,22 @@ def test_oracle_against_live_reference_on_random_meshes(oracle_lib, tmp_path):
         b = o.wost(cfg["solver"], cfg["output"], pts, seed=3, index_offset=0, nthreads=8, want_stats=True)
         assert all(np.array_equal(x, y) for x, y in zip(a, b)), name
         r.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["karman", "karman_doublesided"])
+def test_live_reference_reproduces_the_bvc_vectors(name):
+    """tests/golden/vectors/bvc.npz (solution-only estimator in the domain and on the boundary; make_bvc_vectors.py) is
+    what the reference build in oracle/_ref produces today: the fixture the GPU suite compares against is pinned."""
+    from oracle import refbind
+    if not refbind.available(2):
+        pytest.skip("oracle/_ref is not built (needs /root/reference)")
+    vec = np.load(os.path.join(util.GOLDEN, "vectors", "bvc.npz"))
+    cfg = util.load_case("karman")
+    if name == "karman_doublesided":
+        cfg["scene"]["isDoubleSided"] = True
+    sc = refbind.RefScene(2, cfg["scene"], util.source_grid(2))
+    k = name + "/"
+    sol, st = sc.estimate_solution(cfg["solver"], vec[k + "pts"], 48, normals=vec[k + "normals"], types=vec[k + "types"],
+                                   aligned=vec[k + "aligned"], seed=17, nthreads=4)
+    sc.close()
+    assert np.array_equal(sol, vec[k + "solution"]) and np.array_equal(st, vec[k + "stats"])
