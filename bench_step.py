@@ -34,9 +34,9 @@ def build(args, pkg, st):
     dd = dict(device=getattr(args, "device", 0), distributed=getattr(args, "distributed", False))
     if args.case == "taylorgreen":
         cfg = util.load_case("taylorgreen_shipped" if args.watertight else "taylorgreen_active")
-        size = (0.0, 2*math.pi, 0.0, 2*math.pi)
+        size = util.scene_size_from_obj(cfg["scene"]["boundary"])  # main.py:36-45: the samples live in the OBJ's box, not in [0, 2 pi]
         s = st.SplitStepper(cfg, scene_size=size, max_n_iters=args.iters, early_stop=False, use_cuda_graph=not args.no_graph, seed=1, **dd)
-        tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
+        tg = util.taylor_green_initial(size)
         return s, cfg, tg, (6, 64), "taylorgreen step (SIREN 6x64, batch 64^2, dt 1e-3), 512^2 pressure samples x 500 walks, 1002^2 divergence grid"
     if args.case in ("smoke3d", "karman3d"):
         # examples/smoke3d/run.sh (--src smoke): SIREN 5x64; examples/karman3d/run.sh: SIREN 2x128, karman_vel 0.5;

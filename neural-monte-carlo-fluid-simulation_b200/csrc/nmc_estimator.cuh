@@ -15,7 +15,7 @@ namespace nmc {
 struct SolverParams {
 	int nWalks, maxWalkLength, stepsBeforeApplyingTikhonov, stepsBeforeUsingMaximalSpheres;
 	float epsilonShell, minStarRadius, silhouettePrecision, russianRouletteThreshold;
-	int useGradientControlVariates, useGradientAntitheticVariates;
+	int useGradientControlVariates, useGradientAntitheticVariates, useCosineSampling;
 	int ignoreDirichlet, ignoreNeumann, ignoreSource;
 	float boundaryDistanceMask;
 	uint64_t seed;
@@ -187,8 +187,18 @@ NMC_HD void detEstimatePoint(const SceneView& S, const SolverParams& o, V3 x, ui
 					st.srcGradDir = g.gradient()/(sourcePdf*gn);
 				}
 				if (a == 0) { // :547-567
-					V3 bd = sphereDir<DIM, M>(lhs.at(D*(2*w + 1)), DIM == 3 ? lhs.at(D*(2*w + 1) + D - 1) : 0.0f);
-					boundaryPdf = pdfSphere<DIM>(1.0f);
+					const float ub0 = lhs.at(D*(2*w + 1)), ub1 = DIM == 3 ? lhs.at(D*(2*w + 1) + D - 1) : 0.0f;
+					V3 bd;
+					if (o.useCosineSampling) { // :550-554: cosine lobe around +/- directionForDerivative = e_x (SampleEstimationData's default, :680-683)
+						bd = cosineHemisphere<DIM, M>(ub0, ub1);
+						float* last = DIM == 2 ? &bd.y : &bd.z;
+						if (rng.nextFloat() < 0.5f) *last *= -1.0f;
+						boundaryPdf = 0.5f*pdfCosineHemisphere<DIM>(fabsf(*last));
+						bd = toFrame<DIM>(mk(1.0f, 0.0f, 0.0f), bd);
+					} else {
+						bd = sphereDir<DIM, M>(ub0, ub1);
+						boundaryPdf = pdfSphere<DIM>(1.0f);
+					}
 					g.ySurf = g.c + g.R*bd;
 					boundaryPt = g.ySurf;
 				} else {

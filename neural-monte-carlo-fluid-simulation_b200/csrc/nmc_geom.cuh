@@ -35,6 +35,7 @@ struct SceneView {
 	const float4* sils;
 	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
 	const float4* grpP; const float4* grpS; // (lo, hi) per group (8 in 2D, 4 in 3D) of ray primitives / silhouettes
+	const float4* supP; const float4* supS; // (lo, hi) per 32 groups: second level of the flat scans on large meshes
 	const float4* rayP; const float4* rayN; int nRay; // ray-scan primitives as (origin, edge vectors); 2D: collinear chains merged; padded to whole groups
 	float bboxLo[3], bboxHi[3];
 	const float* src; int n0, n1, n2;
@@ -477,6 +478,7 @@ template <int DIM> struct FlatGroup { static constexpr int n = DIM == 2 ? 8 : 4;
 struct FlatTab {
 	const float4 *silsU, *grpS; int nSilU;   // distinct silhouettes, (lo, hi) per group
 	const float4 *rayP, *rayN, *grpP; int nRay; // ray primitives as (origin, edge vectors), unit normals, (lo, hi) per group
+	const float4 *supS, *supP;               // SUPER scans (large meshes, tables in global memory): (lo, hi) per 32 groups
 };
 template <int DIM>
 NMC_HD float boxSqDistMin(float4 lo, float4 hi, V3 p) {
@@ -497,7 +499,9 @@ NMC_HD int lowestBit(unsigned m) {
 // bounded with d <= sqrt(r2)); stage 2 runs SilhouetteVertex/Edge::findClosestSilhouettePoint
 // (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143) on the marked records only.  Every lane walks
 // its own candidate list, so a warp pays for the longest list, not for the union of the lanes' candidates.
-template <int DIM>
+// SUPER: two-level scan for meshes of hundreds to thousands of primitives (tables in global memory, L1/L2-resident):
+// a block of 32 groups whose common box is out of reach is skipped as a whole.
+template <int DIM, bool SUPER = false>
 NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
 	if (sqMinR >= r2) return false;
 	constexpr int G = FlatGroup<DIM>::n;
@@ -505,6 +509,7 @@ NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, f
 	const bool cull = F.nSilU > 4*G; // a handful of records (a box): testing them costs less than culling
 	bool found = false;
 	for (int g0 = 0, gi = 0; g0 < F.nSilU; g0 += G, gi += 2) {
+		if (SUPER && (gi & 63) == 0 && boxSqDistMin<DIM>(F.supS[gi >> 5], F.supS[(gi >> 5) + 1], x) > r2) { g0 += 31*G; gi += 62; continue; }
 		// every lane of the warp sits near the same query point, so this cull is nearly warp-coherent
 		if (cull && boxSqDistMin<DIM>(F.grpS[gi], F.grpS[gi + 1], x) > r2) continue;
 		unsigned cand = 0u;
@@ -552,7 +557,7 @@ NMC_HD bool flatClosestSilhouette(const FlatTab& F, V3 x, float r2, bool flip, f
 #ifndef NMC_RAY_UNROLL
 #define NMC_RAY_UNROLL 1
 #endif
-template <int DIM>
+template <int DIM, bool SUPER = false>
 NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 	constexpr int G = FlatGroup<DIM>::n;
 	constexpr int kRayUnroll = DIM == 3 ? NMC_RAY_UNROLL : 1; // 3D: the plane-form test is branch-free, unrolling buys instruction-level parallelism
@@ -562,8 +567,7 @@ NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 	// list, so a warp pays for the longest list and not for the union of the lanes' groups.
 	const float ix = 1.0f/dir.x, iy = 1.0f/dir.y, iz = DIM == 3 ? 1.0f/dir.z : 0.0f;
 	const float ox = -o.x*ix, oy = -o.y*iy, oz = DIM == 3 ? -o.z*iz : 0.0f;
-	auto reach = [&](int gi, float tm) {
-		const float4 lo = F.grpP[gi], hi = F.grpP[gi + 1];
+	auto reachBox = [&](const float4 lo, const float4 hi, float tm) {
 		const float a0 = fmaf(lo.x, ix, ox), a1 = fmaf(hi.x, ix, ox), b0 = fmaf(lo.y, iy, oy), b1 = fmaf(hi.y, iy, oy);
 		float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), 0.0f), tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tm);
 		if (DIM == 3) {
@@ -572,16 +576,21 @@ NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 		}
 		return tn <= tf*1.0001f + 1e-6f; // boxes are exact bounds of the records: leave a rounding margin
 	};
-	const int nG = (F.nRay + G - 1)/G; // <= 32
+	auto reach = [&](int gi, float tm) { return reachBox(F.grpP[gi], F.grpP[gi + 1], tm); };
+	const int nGAll = (F.nRay + G - 1)/G; // <= 32 unless SUPER
 	const bool cull = F.nRay > 4*G;    // a handful of primitives (a box): testing them costs less than culling
+#pragma unroll 1
+	for (int sg0 = 0; sg0 < (SUPER ? nGAll : 1); sg0 += 32) {
+	if (SUPER && !reachBox(F.supP[sg0 >> 4], F.supP[(sg0 >> 4) + 1], tMax)) continue;
+	const int nG = SUPER ? (nGAll - sg0 < 32 ? nGAll - sg0 : 32) : nGAll;
 	unsigned todo = nG >= 32 ? 0xffffffffu : (1u << nG) - 1u;
 	if (cull) {
 		todo = 0u;
 #pragma unroll 1
-		for (int g = 0; g < nG; g++) todo |= (reach(2*g, tMax) ? 1u : 0u) << g;
+		for (int g = 0; g < nG; g++) todo |= (reach(2*(sg0 + g), tMax) ? 1u : 0u) << g;
 	}
 	while (todo) {
-		const int g = lowestBit(todo), g0 = g*G;
+		const int g = sg0 + lowestBit(todo), g0 = g*G;
 		todo &= todo - 1u;
 		if (cull && best >= 0 && !reach(2*g, tMax)) continue; // the ray got shorter since the list was made
 #pragma unroll kRayUnroll
@@ -610,6 +619,7 @@ NMC_HD bool flatRay(const FlatTab& F, V3 o, V3 dir, float tMax, Hit& out) {
 				tMax = ok ? t : tMax; best = ok ? i : best;
 			}
 		}
+	}
 	}
 	if (best < 0) return false;
 	out.d = tMax; out.ref = best; out.n = xyz(F.rayN[best]);

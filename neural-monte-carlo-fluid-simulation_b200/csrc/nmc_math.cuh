@@ -198,4 +198,36 @@ NMC_HD float pdfSphere(float r) {
 	return DIM == 2 ? (float)(1.0f/(2.0f*kPi*r)) : (float)(1.0f/(4.0f*kPi*r*r));
 }
 
+// sampleUnitHemisphereCosine<DIM>(float* u) (sampling.h:113-154): 2D (2u - 1, sqrt(1 - .^2)); 3D the concentric disk map
+// lifted to the hemisphere around +z.  The reference evaluates the disk angle in double (float * M_PI) and narrows it once.
+template <int DIM, class M>
+NMC_HD V3 cosineHemisphere(float u0, float u1) {
+	if (DIM == 2) {
+		float a = 2.0f*u0 - 1.0f;
+		return mk(a, sqrtf(maxS(0.0f, 1.0f - a*a)), 0.0f);
+	}
+	float a = 2.0f*u0 - 1.0f, b = 2.0f*u1 - 1.0f;
+	float dx = 0.0f, dy = 0.0f;
+	if (!(a == 0.0f && b == 0.0f)) {
+		float r, theta;
+		if (fabsf(a) > fabsf(b)) { r = a; theta = (float)(0.25f*kPi*(b/a)); }
+		else { r = b; theta = (float)(0.5f*kPi*(1.0f - 0.5f*(a/b))); }
+		dx = r*M::cos_(theta); dy = r*M::sin_(theta);
+	}
+	return mk(dx, dy, sqrtf(maxS(0.0f, 1.0f - (dx*dx + dy*dy))));
+}
+// pdfSampleUnitHemisphereCosine<DIM>(cosTheta) (sampling.h:163-173)
+template <int DIM>
+NMC_HD float pdfCosineHemisphere(float c) { return DIM == 2 ? c/2.0f : (float)(c/kPi); }
+// transformCoordinates<DIM>(n, d) (sampling.h:181-204): the local frame's last axis becomes n
+template <int DIM>
+NMC_HD V3 toFrame(V3 n, V3 d) {
+	if (DIM == 2) return mk(d.x*n.y + d.y*n.x, d.x*(-n.x) + d.y*n.y, 0.0f);
+	const float sign = copysignf(1.0f, n.z);
+	const float a = -1.0f/(sign + n.z);
+	const float b = n.x*n.y*a;
+	const V3 b1 = mk(1.0f + sign*n.x*n.x*a, sign*b, -sign*n.x), b2 = mk(b, sign + n.y*n.y*a, -n.y);
+	return mk(d.x*b1.x + d.y*b2.x + d.z*n.x, d.x*b1.y + d.y*b2.y + d.z*n.y, d.x*b1.z + d.y*b2.z + d.z*n.z);
+}
+
 } // namespace nmc

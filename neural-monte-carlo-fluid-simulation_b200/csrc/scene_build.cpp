@@ -414,6 +414,20 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 	};
 	groupBoxes(out.rayP, dim == 2 ? 1 : 3, out.nRay, dim == 2 ? 1 : 3, out.grpP);
 	groupBoxes(out.silsU, dim == 2 ? 2 : 4, out.nSilU, dim == 2 ? 1 : 2, out.grpS); // 2D: the vertex; 3D: both edge end points
+	auto superBoxes = [&](const std::vector<Q4>& grp, std::vector<Q4>& outBoxes) { // bounds of 32 consecutive group boxes
+		const size_t nG = grp.size()/2;
+		for (size_t s0 = 0; s0 < nG; s0 += 32) {
+			Q4 lo = grp[2*s0], hi = grp[2*s0 + 1];
+			for (size_t g = s0 + 1; g < std::min(nG, s0 + 32); g++) {
+				const Q4 &a = grp[2*g], &b = grp[2*g + 1];
+				lo.x = std::min(lo.x, a.x); lo.y = std::min(lo.y, a.y); lo.z = std::min(lo.z, a.z);
+				hi.x = std::max(hi.x, b.x); hi.y = std::max(hi.y, b.y); hi.z = std::max(hi.z, b.z);
+			}
+			outBoxes.push_back(lo); outBoxes.push_back(hi);
+		}
+	};
+	superBoxes(out.grpP, out.supP);
+	superBoxes(out.grpS, out.supS);
 
 	// scan-friendly records (after the boxes, which need the end points):
 	//  * ray primitives: 2D (origin, edge vector) = (pa.xy, pb - pa); 3D plane form (N, d0)(A, d1)(B, d2), see below;

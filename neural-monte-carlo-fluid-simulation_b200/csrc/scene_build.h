@@ -20,6 +20,8 @@ struct FlatScene {
 	int nSilU = 0;
 	// flat-scan culling boxes: one (lo, hi) pair per group of 8 consecutive primitives / distinct silhouettes
 	std::vector<Q4> grpP, grpS;
+	// second level for meshes beyond the shared-memory flat scan: one (lo, hi) pair per 32 consecutive groups
+	std::vector<Q4> supP, supS;
 	// ray-scan primitives of the default mode: in 2D, chains of connected collinear segments are merged into one
 	// segment (a subdivided straight wall is one ray target); in 3D a copy of `prims`.  rayN: unit normals.
 	std::vector<Q4> rayP, rayN;

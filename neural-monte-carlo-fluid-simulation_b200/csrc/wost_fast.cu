@@ -31,6 +31,7 @@
 #include "nmc_device.h"
 #include "bessel_table.h"
 #include "../../include/nmcfs.h"
+#include <cstdlib>
 #include <mutex>
 
 namespace nmc {
@@ -50,7 +51,7 @@ __device__ __forceinline__ unsigned warpSumU(unsigned v) {
 
 enum LaneState { kNeedPair = 0, kWalking = 2, kIdle = 3 };
 // first-ball record per pair: d0.xyz, e0.xyz, firstSource (walk 0), firstSource (twin), sfr, the pair's control variates (bcv, scv)
-static constexpr int kFbFields = 11;
+static constexpr int kFbFields = 12; // + the first boundary sample's pdf weight (cosine sampling for derivatives)
 
 // resident CTAs per SM the compiler must allow for: 2D 6 (80 registers/thread: the Bessel code spills less), 3D 7
 // (72 registers) -- measured on B200 against 8 (64 registers): profiles/README.md, r02 A/B table
@@ -71,7 +72,9 @@ __device__ __forceinline__ void stackInit(LocalStack&, int*, int) {}
 
 // STATS: the per-point statistics record of the parity tests (variances, mean walk length) costs five more
 // accumulators per lane; the product path (stats12 == nullptr) runs the instantiation without them.
-template <int DIM, class STACK, bool FLAT, bool STATS>
+// FLAT: 0 = tree traversals per step, 1 = flat scans over tables staged in shared memory (<= 128 primitives),
+// 2 = two-level flat scans over tables in global memory (larger meshes; the tree is still walked once per point)
+template <int DIM, class STACK, int FLAT, bool STATS>
 __global__ void __launch_bounds__(kBlock, DIM == 2 ? NMC_MINB2 : NMC_MINB3)
 fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
 		   float* __restrict__ pOut, float* __restrict__ gOut, unsigned int* __restrict__ workCounter,
@@ -90,10 +93,14 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	FlatTab F = {};
 	constexpr int G = FlatGroup<DIM>::n; // the flat-scan lists are padded to whole groups (scene_build.cpp)
 	const int nSilP = (Sg.nSilU + G - 1)/G*G, nRayP = (Sg.nRay + G - 1)/G*G;
-	if (FLAT || stageQuads > 0) { // FLAT scenes always fit (launchFast)
-		// FLAT: the de-duplicated silhouette list replaces the per-leaf references (the tree is only walked once per point)
-		const float4* silSrc = FLAT ? Sg.silsU : Sg.sils;
-		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*(FLAT ? nSilP : Sg.nSilRefs);
+	if (FLAT == 2) { // large mesh: the scan tables stay in global memory (L1 / L2), two-level culling
+		F.silsU = Sg.silsU; F.nSilU = Sg.nSilU; F.grpS = Sg.grpS; F.supS = Sg.supS;
+		F.rayP = Sg.rayP; F.rayN = Sg.rayN; F.nRay = Sg.nRay; F.grpP = Sg.grpP; F.supP = Sg.supP;
+	}
+	if (FLAT == 1 || stageQuads > 0) { // FLAT == 1 scenes always fit (launchFast)
+		// FLAT == 1: the de-duplicated silhouette list replaces the per-leaf references (the tree is only walked once per point)
+		const float4* silSrc = FLAT == 1 ? Sg.silsU : Sg.sils;
+		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*(FLAT == 1 ? nSilP : Sg.nSilRefs);
 #pragma unroll 1
 		for (int i = threadIdx.x; i < qN; i += kBlock) stage[i] = Sg.nodes[i];
 #pragma unroll 1
@@ -103,7 +110,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 #pragma unroll 1
 		for (int i = threadIdx.x; i < qS; i += kBlock) stage[qN + qP + qF + i] = silSrc[i];
 		S.nodes = stage; S.prims = stage + qN; S.primN = stage + qN + qP;
-		if (FLAT) {
+		if (FLAT == 1) {
 			const int qGP = 2*(nRayP/G), qGS = 2*(nSilP/G), qRP = (DIM == 2 ? 1 : 3)*nRayP;
 			const int oG = qN + qP + qF + qS, oR = oG + qGP + qGS;
 #pragma unroll 1
@@ -189,6 +196,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 					const int lastNeeded = nAnti == 2 ? (lastW + 1) >> 1 : lastW;                      // pairs, exclusive
 					const bool want = state == kNeedPair && mineW < nWalksPt;
 					bool fetched = false;
+					float pdfWeight = 1.0f; // first boundary sample: uniform pdf / pdf used (cosine sampling only)
 					// Control variates = running means over the walks finished so far (walk_on_stars.h:501-506), fixed ONCE per
 					// pair as in the reference: the lane that takes a pair's first walk parks them next to the pair's first-ball
 					// samples and the twin reads them, so a twin handed out in a later refill does not see a mean that already
@@ -199,6 +207,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						d0 = mk(fbuf[sl_], fbuf[32 + sl_], DIM == 3 ? fbuf[64 + sl_] : 0.0f); \
 						e0 = mk(fbuf[96 + sl_], fbuf[128 + sl_], DIM == 3 ? fbuf[160 + sl_] : 0.0f); \
 						firstSource = fbuf[(myAnti ? 224 : 192) + sl_]; sfr = fbuf[256 + sl_]; \
+						if (o.useCosineSampling) pdfWeight = fbuf[352 + sl_]; \
 						if (myAnti == 0) { fbuf[288 + sl_] = bcvNow; fbuf[320 + sl_] = scvNow; } fetched = true; } while (0)
 					if (want && mine < chunkEnd) NMC_FETCH_FIRST_BALL(mine - chunkBase);
 					bool cvTaken = false;
@@ -223,7 +232,17 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 								ub1 = ((float)permute(2u*cp + 1u, nStrata, permKey1) + r0.nextFloat())*invStrata;
 							}
 							const V3 sdir = sphereDir<DIM, M>(fminf(us0, 1.0f - kEps), fminf(us1, 1.0f - kEps));
-							const V3 be = firstR*sphereDir<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
+							V3 bdir;
+							if (o.useCosineSampling) { // walk_on_stars.h:550-554: cosine lobe around +/- directionForDerivative = e_x
+								bdir = cosineHemisphere<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
+								float last = DIM == 2 ? bdir.y : bdir.z;
+								if (r0.nextFloat() < 0.5f) last = -last;
+								if (DIM == 2) bdir.y = last; else bdir.z = last;
+								// throughput = poissonKernel / pdf: relative to the uniform pdf the default path assumes
+								fbuf[352 + lane] = pdfSphere<DIM>(1.0f)/(0.5f*pdfCosineHemisphere<DIM>(fabsf(last)));
+								bdir = toFrame<DIM>(mk(1.0f, 0.0f, 0.0f), bdir);
+							} else bdir = sphereDir<DIM, M>(fminf(ub0, 1.0f - kEps), fminf(ub1, 1.0f - kEps));
+							const V3 be = firstR*bdir;
 							const float uA = r0.nextFloat(), uB = r0.nextFloat();
 							float rs = 0.0f, fsrc = 0.0f, fsrc1 = 0.0f, sf = 0.0f;
 							if (!o.ignoreSource) {
@@ -254,7 +273,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 							walkSeed = splitmix64(key ^ (0xD1B54A32D192ED03ull*(unsigned long long)(pair + 1)));
 							// start from the boundary sample, mirrored for the antithetic twin (:564-567), same walk stream (:579)
 							pt = x0 + (anti ? neg(e0) : e0); normal = mk(0, 0, 0); onNeumann = false; flipNext = false; walkLength = 0;
-							throughput = exitT; totalSource = firstSource;
+							throughput = exitT*pdfWeight; totalSource = firstSource;
 							rng.state = walkSeed; rng.inc = 1;
 							bl = fb;
 							state = kWalking; cStarted++;
@@ -285,7 +304,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 								if (o.minStarRadius <= dirichletDist) {
 									float dsil;
 									float r2max = dirichletDist < kMaxF ? dirichletDist*dirichletDist : kMaxF;
-									bool f = flatClosestSilhouette<DIM>(F, pt, r2max, !flipOrient, o.minStarRadius*o.minStarRadius, o.silhouettePrecision, dsil);
+									bool f = flatClosestSilhouette<DIM, FLAT == 2>(F, pt, r2max, !flipOrient, o.minStarRadius*o.minStarRadius, o.silhouettePrecision, dsil);
 									starR = f ? fmaxf(dsil, o.minStarRadius) : fmaxf(dirichletDist, o.minStarRadius);
 								}
 							} else
@@ -300,7 +319,7 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 						Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
 						if (FLAT) {
 							V3 ro = onNeumann ? offsetPoint<DIM>(pt, neg(normal)) : pt;
-							hit = flatRay<DIM>(F, ro, dir, starR, h);
+							hit = flatRay<DIM, FLAT == 2>(F, ro, dir, starR, h);
 						} else
 						hit = intersectNeumann<DIM>(S, stack, pt, normal, dir, starR, onNeumann, h);
 						if (hit) { ipt = h.p; inrm = h.n; idist = h.d; }
@@ -462,15 +481,17 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (!smemStack) stackSlots = 0; // LocalStack: the first-ball chunks sit right behind the staged scene
 	size_t smem = (stageQuads ? bytes : 0) + (size_t)stackSlots*kBlock*8 + (size_t)kWarps*kFbFields*32*sizeof(float);
 	void (*kern)(SceneView, SolverParams, const float*, long long, unsigned long long, float*, float*, unsigned int*, Counters*, float*, int, int);
-	if (d_stats12) {
-		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true, true> : fastKernel<3, StridedStack, true, true>;
-		else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false, true> : fastKernel<2, LocalStack, false, true>;
-		else kern = smemStack ? fastKernel<3, StridedStack, false, true> : fastKernel<3, LocalStack, false, true>;
-	} else {
-		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, true, false> : fastKernel<3, StridedStack, true, false>;
-		else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, false, false> : fastKernel<2, LocalStack, false, false>;
-		else kern = smemStack ? fastKernel<3, StridedStack, false, false> : fastKernel<3, LocalStack, false, false>;
-	}
+	// meshes beyond the shared-memory flat scan: two-level flat scans over the global tables (NMC_BIG_MESH=tree selects the
+	// per-lane tree traversals instead, for A/B measurements)
+	static const bool bigFlat = [] { const char* e = getenv("NMC_BIG_MESH"); return !(e && e[0] == 't'); }();
+	const bool flat2 = !flat && bigFlat && smemStack && S.supP && S.supS;
+#define NMC_PICK(ST) do { \
+		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, 1, ST> : fastKernel<3, StridedStack, 1, ST>; \
+		else if (flat2) kern = dim == 2 ? fastKernel<2, StridedStack, 2, ST> : fastKernel<3, StridedStack, 2, ST>; \
+		else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, 0, ST> : fastKernel<2, LocalStack, 0, ST>; \
+		else kern = smemStack ? fastKernel<3, StridedStack, 0, ST> : fastKernel<3, LocalStack, 0, ST>; } while (0)
+	if (d_stats12) NMC_PICK(true); else NMC_PICK(false);
+#undef NMC_PICK
 	if (flat && (!smemStack || stageQuads == 0)) return cudaErrorInvalidConfiguration; // cannot happen: <= 128 primitives give a shallow tree, and see above
 	int perSM = 0;
 	cudaError_t e = cudaSuccess;

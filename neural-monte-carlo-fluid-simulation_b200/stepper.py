@@ -260,7 +260,10 @@ class SplitStepper:
             else:
                 one()
             it += 1
-            if self.early_stop and it % self.check_every == 0 and self._stop_now(loss_buf):
+            # the reference tests the loss after every iteration (base.py:148); here after the first one (a fit whose target is
+            # the network itself -- the projection with a zero pressure gradient -- stops at once, as it does there) and then
+            # every `check_every` iterations, each test being a host synchronisation
+            if self.early_stop and (it == 1 or it % self.check_every == 0) and self._stop_now(loss_buf):
                 break
         return it, loss_buf
 

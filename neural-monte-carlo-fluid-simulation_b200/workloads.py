@@ -64,6 +64,37 @@ def walks_per_point(solver):
     return nw if solver.get("disableGradientAntitheticVariates", False) else 2*max(1, nw//2)
 
 
+def scene_size_from_obj(path, dim=2):
+    """cfg.scene_size the way the reference's drivers derive it (src/2d/main.py:36-45, src/3d: the same with z): the
+    bounding box of the OBJ's vertices, (x0, x1, y0, y1[, z0, z1]).  The training / pressure samples are drawn in THIS box:
+    the Taylor-Green square spans [0.000447, 6.279553], not [0, 2 pi], and a sample outside the boundary mesh starts
+    walks outside the domain."""
+    v = []
+    for line in open(path):
+        t = line.split()
+        if t and t[0] == "v":
+            v.append([float(c) for c in t[1:1 + dim]])
+    v = np.array(v)
+    lo, hi = v.min(0), v.max(0)
+    out = []
+    for k in range(dim):
+        out += [float(lo[k]), float(hi[k])]
+    return tuple(out)
+
+
+def taylor_green_initial(scene_size):
+    """taylorgreen_velocity (src/2d/sources.py:19-31): the samples are rescaled from the scene box to (0, 2 pi)."""
+    import math
+
+    import torch
+
+    def fn(x):
+        a = (x[:, 0] - scene_size[0])/(scene_size[1] - scene_size[0])*(2*math.pi)
+        b = (x[:, 1] - scene_size[2])/(scene_size[3] - scene_size[2])*(2*math.pi)
+        return torch.stack([torch.sin(a)*torch.cos(b), -torch.cos(a)*torch.sin(b)], dim=-1)
+    return fn
+
+
 def karman_obstacle(mask=1e-3):
     """Centre and radius of the cylinder of the karman fixture the way src/2d/main.py:36-57,90-102 derives them:
     the vertices strictly inside the bounding box, mean centre, mean radius + output.boundaryDistanceMask.

@@ -120,6 +120,41 @@ void nmo_sphere_dir(int dim, const float* u, int n, float* out) {
 		for (int k = 0; k < dim; k++) out[(size_t)i*dim + k] = d[k];
 	}
 }
+/* sampleUnitHemisphereCosine<DIM>(float* u), sampling.h:113-154 (concentric disk map :122-146) */
+static void cosine_hemisphere(int dim, const float* u, float* d) {
+	if (dim == 2) {
+		float u1 = 2.0f*u[0] - 1.0f;
+		d[0] = u1; d[1] = sqrtf(fmax_std(0.0f, 1.0f - u1*u1)); d[2] = 0.0f;
+		return;
+	}
+	float u1 = 2.0f*u[0] - 1.0f, u2 = 2.0f*u[1] - 1.0f;
+	float dx = 0.0f, dy = 0.0f;
+	if (!(u1 == 0 && u2 == 0)) {
+		float theta, r;
+		if (fabsf(u1) > fabsf(u2)) { r = u1; theta = 0.25f*M_PI*(u2/u1); }
+		else { r = u2; theta = 0.5f*M_PI*(1.0f - 0.5f*(u1/u2)); }
+		dx = r*cosf(theta); dy = r*sinf(theta);
+	}
+	d[0] = dx; d[1] = dy; d[2] = sqrtf(fmax_std(0.0f, 1.0f - (dx*dx + dy*dy)));
+}
+/* pdfSampleUnitHemisphereCosine<DIM>(cosTheta), sampling.h:163-173 */
+static inline float pdf_cosine_hemisphere(int dim, float c) { return dim == 2 ? c/2.0f : (float)(c/M_PI); }
+/* transformCoordinates<DIM>(n, d), sampling.h:181-204 */
+static void transform_coordinates(int dim, const float* n, float* d) {
+	if (dim == 2) {
+		float sx = n[1], sy = -n[0];
+		float x = d[0]*sx + d[1]*n[0], y = d[0]*sy + d[1]*n[1];
+		d[0] = x; d[1] = y;
+		return;
+	}
+	float sign = copysignf(1.0f, n[2]);
+	const float a = -1.0f/(sign + n[2]);
+	const float b = n[0]*n[1]*a;
+	float b1[3] = {1.0f + sign*n[0]*n[0]*a, sign*b, -sign*n[0]}, b2[3] = {b, sign + n[1]*n[1]*a, -n[1]};
+	float r[3];
+	for (int k = 0; k < 3; k++) r[k] = d[0]*b1[k] + d[1]*b2[k] + d[2]*n[k];
+	d[0] = r[0]; d[1] = r[1]; d[2] = r[2];
+}
 /* pdfSampleSphereUniform<DIM>(r), sampling.h:55-65 */
 static inline float pdf_sphere(int dim, float r) {
 	return dim == 2 ? (float)(1.0f/(2.0f*M_PI*r)) : (float)(1.0f/(4.0f*M_PI*r*r));
@@ -1477,8 +1512,16 @@ static void estimate_point(const nmo_scene* s, const nmo_solver_opts* o, const f
 				for (int k = 0; k < 3; k++) st.srcGradDir[k] = gr[k]/den;
 			}
 			if (a == 0) {
-				v3 bd; sphere_dir(s->dim, &scratch[D*(2*w + 1)], bd);
-				boundaryPdf = pdf_sphere(s->dim, 1.0f);
+				v3 bd;
+				if (o->useCosineSamplingForDerivatives) { /* :550-554 */
+					cosine_hemisphere(s->dim, &scratch[D*(2*w + 1)], bd);
+					if (nmo_pcg32_float(rng) < 0.5f) bd[s->dim - 1] *= -1.0f;
+					boundaryPdf = 0.5f*pdf_cosine_hemisphere(s->dim, fabsf(bd[s->dim - 1]));
+					transform_coordinates(s->dim, dirForDeriv, bd);
+				} else {
+					sphere_dir(s->dim, &scratch[D*(2*w + 1)], bd);
+					boundaryPdf = pdf_sphere(s->dim, 1.0f);
+				}
 				for (int k = 0; k < 3; k++) g.ySurf[k] = g.c[k] + g.R*bd[k];
 				memcpy(boundaryPt, g.ySurf, sizeof(v3));
 			} else {
@@ -1572,7 +1615,6 @@ static void* worker(void* arg) {
 int nmo_wost(const nmo_scene* s, const nmo_solver_opts* o, const float* pts, int n,
 			 uint64_t seed, uint64_t index_offset, int nthreads,
 			 float* p_out, float* grad_out, float* stats) {
-	if (o->useCosineSamplingForDerivatives) return -1; /* not restated */
 	volatile int next = 0;
 	job_t J = {s, o, pts, n, seed, index_offset, p_out, grad_out, stats, &next, o->nWalks > 1 ? o->nWalks : 1};
 	if (nthreads <= 1) { worker(&J); return 0; }

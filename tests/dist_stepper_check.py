@@ -27,7 +27,7 @@ def main():
     st = import_module(pkg.__name__ + ".stepper")
     S = pkg.load_siren()
     cfg = util.load_case("taylorgreen_active")
-    kw = dict(scene_size=(0.0, 2*math.pi, 0.0, 2*math.pi), grid_resolution=120, wost_resolution=64, sample_resolution=32, max_n_iters=30,
+    kw = dict(scene_size=pkg.workloads.scene_size_from_obj(cfg["scene"]["boundary"]), grid_resolution=120, wost_resolution=64, sample_resolution=32, max_n_iters=30,
               check_every=10, lr=1e-4, seed=3, device=local, reset_wts=True)
     tg = lambda x: torch.stack([torch.sin(x[:, 0])*torch.cos(x[:, 1]), -torch.cos(x[:, 0])*torch.sin(x[:, 1])], dim=-1)  # noqa: E731
 

@@ -277,8 +277,8 @@ def test_edge_cases(pkg):
     # the public list-based API returns nested lists like the pybind module
     pts, sol, grad = pkg.wost(sc, cfg["solver"], cfg["output"], [[0.1, 0.2], [0.3, 0.1]])
     assert isinstance(sol, list) and isinstance(grad[0], list) and len(grad[0]) == 2 and pts[1][0] == pytest.approx(0.3)
-    with pytest.raises(RuntimeError, match="not supported"):
-        pkg.zombie.wost_array(sc, dict(cfg["solver"], useCosineSamplingForDirectionalDerivatives=True), cfg["output"], mid)
+    with pytest.raises(RuntimeError, match="unknown mode"):
+        pkg.zombie.wost_array(sc, cfg["solver"], cfg["output"], mid, mode=7)
 
 
 def test_full_size_3d_properties_one_million_points(pkg):

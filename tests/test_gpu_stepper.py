@@ -17,7 +17,7 @@ def _stepper(**kw):
     pkg = util.package()
     st = import_module(pkg.__name__ + ".stepper")
     cfg = util.load_case("taylorgreen_active")
-    args = dict(scene_size=(0.0, 2*math.pi, 0.0, 2*math.pi), grid_resolution=200, wost_resolution=64, sample_resolution=32,
+    args = dict(scene_size=pkg.workloads.scene_size_from_obj(cfg["scene"]["boundary"]), grid_resolution=200, wost_resolution=64, sample_resolution=32,
                 max_n_iters=40, check_every=10, seed=3, device=0)
     args.update(kw)
     return pkg, st.SplitStepper(cfg, **args)

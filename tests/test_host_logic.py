@@ -151,7 +151,7 @@ def test_early_stop_is_a_collective_decision_world_size_2_gloo(tmp_path):
 class _EmuParams(C.Structure):
     _fields_ = [("nWalks", C.c_int), ("maxWalkLength", C.c_int), ("sT", C.c_int), ("sM", C.c_int),
                 ("eps", C.c_float), ("minR", C.c_float), ("prec", C.c_float), ("rr", C.c_float),
-                ("cv", C.c_int), ("anti", C.c_int), ("iD", C.c_int), ("iN", C.c_int), ("iS", C.c_int),
+                ("cv", C.c_int), ("anti", C.c_int), ("cosine", C.c_int), ("iD", C.c_int), ("iN", C.c_int), ("iS", C.c_int),
                 ("mask", C.c_float), ("seed", C.c_uint64)]
 
 
@@ -205,7 +205,7 @@ def test_host_compiled_device_code_matches_oracle(emu, oracle_lib, case):
     o = oracle_lib.solver_opts(solver, cfg["output"])
     ep = _EmuParams(o.nWalks, o.maxWalkLength, o.stepsBeforeApplyingTikhonov, o.stepsBeforeUsingMaximalSpheres, o.epsilonShell,
                     o.minStarRadius, o.silhouettePrecision, o.russianRouletteThreshold, o.useGradientControlVariates,
-                    o.useGradientAntitheticVariates, o.ignoreDirichlet, o.ignoreNeumann, o.ignoreSource, o.boundaryDistanceMask, 3)
+                    o.useGradientAntitheticVariates, o.useCosineSamplingForDerivatives, o.ignoreDirichlet, o.ignoreNeumann, o.ignoreSource, o.boundaryDistanceMask, 3)
     p = np.zeros(len(pts), np.float32); g = np.zeros((len(pts), dim), np.float32); st = np.zeros((len(pts), 12), np.float32)
     emu.emu_wost(h, C.byref(ep), _fp(pts), len(pts), C.c_uint64(0), _fp(p), _fp(g), _fp(st))
     rp, rg, rst = osc.wost(solver, cfg["output"], pts, seed=3, nthreads=4, want_stats=True)

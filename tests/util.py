@@ -78,6 +78,7 @@ OPTION_VARIANTS = {
     "no_rr": ({}, {"russianRouletteThreshold": 0.0, "maxWalkLength": 256}),      # nothing stops a walk: all exceed the length and are discarded
     "maxsph": ({}, {"setpsBeforeUsingMaximalSpheres": 1}),
     "ignore_source": ({}, {"ignoreSource": True}),
+    "cosine": ({}, {"useCosineSamplingForDirectionalDerivatives": True}),    # first boundary sample from a cosine lobe around +/- e_x (:550-554)
 }
 OPTION_CASES = ("karman", "karman3d")
 
