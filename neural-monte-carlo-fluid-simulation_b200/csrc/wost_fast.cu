@@ -93,11 +93,12 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 	FlatTab F = {};
 	constexpr int G = FlatGroup<DIM>::n; // the flat-scan lists are padded to whole groups (scene_build.cpp)
 	const int nSilP = (Sg.nSilU + G - 1)/G*G, nRayP = (Sg.nRay + G - 1)/G*G;
-	if (FLAT == 2) { // large mesh: the scan tables stay in global memory (L1 / L2), two-level culling
+	if (FLAT == 2) { // large mesh: records and culling boxes stay in global memory (L1 / L2); staging the boxes in shared memory
+		// was measured slower (1.9e8 against 2.6e8 walks/s on box_sphere: the 48 KB stage costs resident CTAs)
 		F.silsU = Sg.silsU; F.nSilU = Sg.nSilU; F.grpS = Sg.grpS; F.supS = Sg.supS;
 		F.rayP = Sg.rayP; F.rayN = Sg.rayN; F.nRay = Sg.nRay; F.grpP = Sg.grpP; F.supP = Sg.supP;
 	}
-	if (FLAT == 1 || stageQuads > 0) { // FLAT == 1 scenes always fit (launchFast)
+	if (FLAT == 1 || (FLAT == 0 && stageQuads > 0)) { // FLAT == 1 scenes always fit (launchFast)
 		// FLAT == 1: the de-duplicated silhouette list replaces the per-leaf references (the tree is only walked once per point)
 		const float4* silSrc = FLAT == 1 ? Sg.silsU : Sg.sils;
 		const int qN = 4*Sg.nNodes, qP = (DIM == 2 ? 1 : 3)*Sg.nPrims, qF = Sg.nPrims, qS = (DIM == 2 ? 2 : 4)*(FLAT == 1 ? nSilP : Sg.nSilRefs);
@@ -473,6 +474,14 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	};
 	if (flat && stageQuadsFor(true)*sizeof(float4) > 48*1024) flat = false;
 	size_t quads = stageQuadsFor(flat);
+	// meshes beyond the shared-memory flat scan: two-level flat scans over the global tables (NMC_BIG_MESH=tree selects the
+	// per-lane tree traversals instead, for A/B measurements).
+	// 3D only: on box_sphere (1292 triangles) the two-level scan runs 2.6e8 walks/s against 4.7e7 for the per-lane tree
+	// traversal; in 2D (channel_circle, 1184 segments) the tree is the faster of the two (8.7e8 against 4.1e8: long merged
+	// wall segments make poor group boxes) and stays the default
+	static const bool bigFlat = [] { const char* e = getenv("NMC_BIG_MESH"); return !(e && e[0] == 't'); }();
+	const bool flat2 = !flat && bigFlat && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
+	if (flat2) quads = 0; // FLAT == 2 stages nothing (see the kernel)
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
@@ -481,10 +490,6 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (!smemStack) stackSlots = 0; // LocalStack: the first-ball chunks sit right behind the staged scene
 	size_t smem = (stageQuads ? bytes : 0) + (size_t)stackSlots*kBlock*8 + (size_t)kWarps*kFbFields*32*sizeof(float);
 	void (*kern)(SceneView, SolverParams, const float*, long long, unsigned long long, float*, float*, unsigned int*, Counters*, float*, int, int);
-	// meshes beyond the shared-memory flat scan: two-level flat scans over the global tables (NMC_BIG_MESH=tree selects the
-	// per-lane tree traversals instead, for A/B measurements)
-	static const bool bigFlat = [] { const char* e = getenv("NMC_BIG_MESH"); return !(e && e[0] == 't'); }();
-	const bool flat2 = !flat && bigFlat && smemStack && S.supP && S.supS;
 #define NMC_PICK(ST) do { \
 		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, 1, ST> : fastKernel<3, StridedStack, 1, ST>; \
 		else if (flat2) kern = dim == 2 ? fastKernel<2, StridedStack, 2, ST> : fastKernel<3, StridedStack, 2, ST>; \
