@@ -303,8 +303,8 @@ def sim_steps(X, example, iters_list=(1000, 10000), steps=(2, 1)):
         out["K%d" % iters] = {"value": nst/dt, "unit": "steps/s", "ms_per_step": 1e3*dt/nst, "steps_timed": nst,
                               "pressure_ms": s.last.get("pressure_ms"), "walks_per_step": int(s.last.get("walks", 0))}
     out["config"] = what
-    out["parallelism"] = ("data-parallel fits (one gradient all_reduce per iteration), pressure samples sharded + all_gather"
-                          if X.world > 1 else "single GPU")
+    out["parallelism"] = ("fits replicated on every rank (identical samples, weights re-broadcast after each fit), pressure samples sharded + all_gather; "
+                          "data-parallel fits (SplitStepper(fit_parallel='data')) are slower while an iteration is latency-bound" if X.world > 1 else "single GPU")
     s.close()
     return out
 

@@ -31,7 +31,7 @@ def _leave():
 
 def build(args, pkg, st):
     """(stepper, initial-velocity function, network shape, description) for the chosen example configuration."""
-    dd = dict(device=getattr(args, "device", 0), distributed=getattr(args, "distributed", False))
+    dd = dict(device=getattr(args, "device", 0), distributed=getattr(args, "distributed", False), fit_parallel=getattr(args, "fit_parallel", "replicated"))
     if args.case == "taylorgreen":
         cfg = util.load_case("taylorgreen_shipped" if args.watertight else "taylorgreen_active")
         size = util.scene_size_from_obj(cfg["scene"]["boundary"])  # main.py:36-45: the samples live in the OBJ's box, not in [0, 2 pi]
@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--watertight", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--fit-parallel", dest="fit_parallel", default="replicated", choices=["replicated", "data"], help="multi-GPU fits: every rank the whole fit (default) or data-parallel with a gradient all_reduce per iteration")
     ap.add_argument("--gpus", type=int, default=1, help="under torchrun: data-parallel fits + sharded pressure solve")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

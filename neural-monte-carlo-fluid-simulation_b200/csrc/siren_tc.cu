@@ -242,23 +242,18 @@ sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, 
 			// epilogue: this thread's row of the accumulator -> bias, sin, next layer's operand
 			const float* bl = sBias + l*H;
 			const bool lastHidden = l == nHidden;
+			uint32_t v[HC]; // the whole half row in flight, one wait (two round trips per 32 columns before: the epilogue is latency-bound at 8 warps per SM)
 #pragma unroll
-			for (int c0 = 0; c0 < HC; c0 += 16) {
-				uint32_t v[16];
-				uint32_t taddr = tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0);
-				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-							 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-							   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-							 : "r"(taddr) : "memory");
-				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+			for (int c0 = 0; c0 < HC; c0 += 16)
+				nmc_siren_tc::tmemLoad16Async(tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0), &v[c0]);
+			nmc_siren_tc::tmemLoadWait();
 #pragma unroll
-				for (int q4 = 0; q4 < 16; q4 += 4) {
-					const int c = cBeg + c0 + q4;
-					const float4 bv = *reinterpret_cast<const float4*>(bl + c);
-					const float z[4] = {__uint_as_float(v[q4]) + bv.x, __uint_as_float(v[q4 + 1]) + bv.y, __uint_as_float(v[q4 + 2]) + bv.z, __uint_as_float(v[q4 + 3]) + bv.w};
-					if (lastHidden) emit4(l, c, z, true);
-					else emit4(l, c, z, false);
-				}
+			for (int c0 = 0; c0 < HC; c0 += 4) {
+				const int c = cBeg + c0;
+				const float4 bv = *reinterpret_cast<const float4*>(bl + c);
+				const float z[4] = {__uint_as_float(v[c0]) + bv.x, __uint_as_float(v[c0 + 1]) + bv.y, __uint_as_float(v[c0 + 2]) + bv.z, __uint_as_float(v[c0 + 3]) + bv.w};
+				if (lastHidden) emit4(l, c, z, true);
+				else emit4(l, c, z, false);
 			}
 		}
 		TRACE(8);

@@ -88,6 +88,14 @@ __device__ __forceinline__ void tmemLoad16(uint32_t taddr, uint32_t (&v)[16]) {
 				 : "r"(taddr) : "memory");
 	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same without the wait: several loads can be in flight before one tmemLoadWait()
+__device__ __forceinline__ void tmemLoad16Async(uint32_t taddr, uint32_t* v) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+				 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+				   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+				 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void splitTf32(float v, float& hi, float& lo) {
 	hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); // the 10 mantissa bits the tensor core keeps
 	lo = v - hi;

@@ -209,27 +209,26 @@ sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0,
 			// epilogue: dZ_{l-1} = dA_{l-1} * w0 cos(w0 z_{l-1}) -> global (weight gradients) and the next A operand
 			float* dp = drow + (size_t)(l - 1)*H*n;
 			const float w0l = live ? w0 : 0.0f;   // dead rows: zero deltas
+			uint32_t v[HC]; // the whole half row in flight, one wait
 #pragma unroll
-			for (int c0 = 0; c0 < HC; c0 += 16) {
-				uint32_t v[16];
-				tmemLoad16(tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0), v);
+			for (int c0 = 0; c0 < HC; c0 += 16) tmemLoad16Async(tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0), &v[c0]);
+			tmemLoadWait();
 #pragma unroll
-				for (int q4 = 0; q4 < 16; q4 += 4) {
-					float d[4];
+			for (int c0 = 0; c0 < HC; c0 += 4) {
+				float d[4];
 #pragma unroll
-					for (int q = 0; q < 4; q++) {
-						const float a = __uint_as_float(v[q4 + q])*w0l*cosReduced(w0*zreg[c0 + q4 + q]);
-						if (live) *dp = a;
-						dp += n;
-						d[q] = a;
-					}
-					if (l > 1) {
-						float4 h, o;
-						splitTf32(make_float4(d[0], d[1], d[2], d[3]), h, o);
-						const int off = coreOffsetBytes<H>(row, cBeg + c0 + q4);
-						*reinterpret_cast<float4*>(Dhi + off) = h;
-						*reinterpret_cast<float4*>(Dlo + off) = o;
-					}
+				for (int q = 0; q < 4; q++) {
+					const float a = __uint_as_float(v[c0 + q])*w0l*cosReduced(w0*zreg[c0 + q]);
+					if (live) *dp = a;
+					dp += n;
+					d[q] = a;
+				}
+				if (l > 1) {
+					float4 h, o;
+					splitTf32(make_float4(d[0], d[1], d[2], d[3]), h, o);
+					const int off = coreOffsetBytes<H>(row, cBeg + c0);
+					*reinterpret_cast<float4*>(Dhi + off) = h;
+					*reinterpret_cast<float4*>(Dlo + off) = o;
 				}
 			}
 		}

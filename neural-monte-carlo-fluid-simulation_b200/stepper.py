@@ -88,7 +88,7 @@ class SplitStepper:
                  sample_resolution=64, wost_resolution=512, grid_resolution=1000, bdry_eps=1e-3, max_n_iters=10000,
                  early_stop=True, check_every=100, boundary="taylorgreen", mode=capi.MODE_FAST, seed=0, device=0,
                  use_cuda_graph=True, tensor_cores=True, init_velocity=None, init_iters=0, obstacle=None, karman_vel=0.5,
-                 reset_wts=False, distributed=False):
+                 reset_wts=False, distributed=False, fit_parallel="data"):
         """distributed: one process per GPU under torch.distributed (NCCL).  The fits are data-parallel (each rank
         draws 1/world of every batch, one gradient all_reduce per iteration), the pressure samples are drawn and
         solved per rank and all-gathered (points, p, grad p), the divergence grid and the networks are replicated.
@@ -98,6 +98,14 @@ class SplitStepper:
         if distributed:
             import torch.distributed as dist
             self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        # fit_parallel (distributed runs): "data" = data-parallel fits, every rank 1/world of each batch and one gradient
+        # all_reduce per iteration; "replicated" = every rank runs the whole fit on identical samples (the same random
+        # streams on all ranks) and only the pressure solve is sharded -- the better choice while a fit iteration is
+        # latency-bound (measured at 2 GPUs, smoke3d, K = 1000: 2.9 steps/s data-parallel against 4.2 on one GPU).  The
+        # weights are re-broadcast from rank 0 after every fit (the gradient reductions use atomics: last-bit differences).
+        if fit_parallel not in ("data", "replicated"):
+            raise ValueError("fit_parallel must be 'data' or 'replicated'")
+        self.fit_world = self.world if fit_parallel == "data" else 1
         self.cfg = wost_config
         self.size = tuple(float(v) for v in scene_size)
         self.dt, self.lr, self.eps = dt, lr, bdry_eps
@@ -123,8 +131,8 @@ class SplitStepper:
         self.timestep, self.seed = 0, seed
         self.last = {}
         self._fit, self._graphs, self._proj = None, {}, None
-        if self.world > 1:  # identical initial weights (same seed above), different training samples per rank from here on
-            torch.manual_seed(seed*7919 + 1 + self.rank)
+        if self.world > 1:  # identical initial weights (same seed above); data-parallel fits: different training samples per rank from here on
+            torch.manual_seed(seed*7919 + 1 + (self.rank if self.fit_world > 1 else 0))
         self.obstacle, self.karman_vel, self.reset_wts = obstacle, float(karman_vel), bool(reset_wts)
         if boundary in ("taylorgreen", "walls"):
             self.env = wall_envelope(self.size, bdry_eps)
@@ -208,7 +216,7 @@ class SplitStepper:
         later time step: its inputs live in buffers that persist across steps, and Adam's step counter is on the
         device.  (Capturing per fit costs a synchronise + allocator flush per phase, i.e. tens to hundreds of ms.)"""
         if self._fit is None:
-            self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2, distributed=self.world > 1)
+            self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2, distributed=self.fit_world > 1)
         fit = self._fit
         fit.opt.reset()
         if self.reset_wts:
@@ -271,7 +279,7 @@ class SplitStepper:
         """Early-stop test of _training_loop (base.py:148).  Data-parallel fits: `loss_buf` is this rank's shard MSE, so
         the decision is taken on the mean over ranks -- every rank issues this all_reduce at the same iteration and
         reaches the same verdict (a rank that stopped alone would leave the others waiting in the gradient all_reduce)."""
-        return collective_stop(loss_buf, self.world)
+        return collective_stop(loss_buf, self.fit_world)
 
     def close(self):
         """Drops the captured CUDA graphs (they hold the NCCL gradient all_reduce of the data-parallel fits: while they
@@ -298,7 +306,7 @@ class SplitStepper:
         return False
 
     def advect_velocity(self, n_iters=None):
-        n = self.sample_resolution**2//self.world
+        n = self.sample_resolution**2//self.fit_world
         s = self.size
 
         def make_target(samples):
@@ -321,14 +329,14 @@ class SplitStepper:
             div = div + torch.autograd.grad(u[:, i], x, torch.ones_like(u[:, i]), retain_graph=(i < self.dim - 1))[0][:, i]
         return (-div).reshape(self.grid_shape).contiguous()
 
-    def pressure_solve(self, samples):
+    def pressure_solve(self, samples, index_offset=None):
         div = self.divergence_grid()
         stream = torch.cuda.current_stream().cuda_stream  # the grid's producer, the copy and the solve share one stream
         self.scene.handle.set_source_device(div.data_ptr(), div.shape, stream=stream)
         n = samples.shape[0]
         p = torch.empty(n, device=self.dev); g = torch.empty((n, self.dim), device=self.dev)
         st = capi.SolveStats()
-        self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=self.rank*(self.wost_resolution**2),
+        self.scene.handle.solve_device(self.opts, samples.data_ptr(), n, p.data_ptr(), g.data_ptr(), index_offset=self.rank*(self.wost_resolution**2) if index_offset is None else index_offset,
                                        stream=stream, stats=st)
         self.last.update(walks=st.walks_started, wost_ms=st.kernel_ms, div=div)
         return p, g
@@ -347,17 +355,41 @@ class SplitStepper:
         full = torch.cat(parts, dim=0)
         return full[:, :self.dim].contiguous(), full[:, self.dim].contiguous(), full[:, self.dim + 1:].contiguous()
 
+    def _solve_shard_of_common_samples(self, samples_all):
+        """Replicated fits: every rank holds the same pressure samples, solves its contiguous block and the blocks are
+        all-gathered (equal padded blocks, one collective for p and grad p)."""
+        import torch.distributed as dist
+        from .sharding import shard_bounds
+        N = samples_all.shape[0]
+        b0, b1 = shard_bounds(N, self.rank, self.world)
+        m = -(-N//self.world)
+        p, g = self.pressure_solve(samples_all[b0:b1].contiguous(), index_offset=b0)
+        loc = torch.zeros(m, self.dim + 1, device=self.dev)
+        loc[: b1 - b0, 0] = p; loc[: b1 - b0, 1:] = g
+        full = torch.empty(m*self.world, self.dim + 1, device=self.dev)
+        dist.all_gather_into_tensor(full, loc)
+        parts = []
+        for r in range(self.world):
+            a0, a1 = shard_bounds(N, r, self.world)
+            parts.append(full[r*m: r*m + (a1 - a0)])
+        full = torch.cat(parts, dim=0)
+        return full[:, 0].contiguous(), full[:, 1:].contiguous()
+
     def project_velocity(self, n_iters=None):
-        samples_all = self.sample_random(self.wost_resolution**2//self.world, keep_shape=False).contiguous()
+        replicated = self.world > 1 and self.fit_world == 1
+        samples_all = self.sample_random(self.wost_resolution**2//(1 if replicated else self.world), keep_shape=False).contiguous()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        p, grad_p = self.pressure_solve(samples_all)
-        if self.world > 1:
-            samples_all, p, grad_p = self._gather_pressure(samples_all, p, grad_p)
+        if replicated:
+            p, grad_p = self._solve_shard_of_common_samples(samples_all)
+        else:
+            p, grad_p = self.pressure_solve(samples_all)
+            if self.world > 1:
+                samples_all, p, grad_p = self._gather_pressure(samples_all, p, grad_p)
         e1.record(); e1.synchronize()
         self.last["pressure_ms"] = e0.elapsed_time(e1)
         self.last.update(p=p, grad_p=grad_p, pressure_samples=samples_all)
-        n, big = self.sample_resolution**2//self.world, samples_all.shape[0]
+        n, big = self.sample_resolution**2//self.fit_world, samples_all.shape[0]
         if self.use_graph:  # persistent inputs of the captured iteration: samples, gradients and their count
             if self._proj is None:
                 cap = self.wost_resolution**2
@@ -395,12 +427,21 @@ class SplitStepper:
             self._noise_seed.fill_(self.timestep)
         self._sync_prev()
         it_a, loss_a = self.advect_velocity(n_iters)
+        self._rebroadcast_weights()
         self._sync_prev()
         it_p, loss_p = self.project_velocity(n_iters)
+        self._rebroadcast_weights()
         self._sync_prev()
         self.timestep += 1
         self.opts.seed = (self.seed + self.timestep) & 0xFFFFFFFFFFFFFFFF
         return {"advect_iters": it_a, "advect_loss": loss_a, "project_iters": it_p, "project_loss": loss_p}
+
+    def _rebroadcast_weights(self):
+        """Replicated fits: the ranks' weights agree up to the last bits (atomic gradient reductions) and the ranks may stop
+        a fit at different iterations; continue from rank 0's."""
+        if self.world > 1 and self.fit_world == 1 and self._fit is not None:
+            import torch.distributed as dist
+            dist.broadcast(self._fit.opt.flat, src=0)
 
     def karman_initial_velocity(self, samples):
         """karman_vortex_velocity (sources.py:34-43): (karman_vel, 0) times the obstacle weight."""

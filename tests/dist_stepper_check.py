@@ -74,6 +74,21 @@ def main():
         assert s._stop_now(mine) is False
         assert s._stop_now(torch.tensor(1e-12, device="cuda")) is True
         s.close()   # drops the graphs that captured the gradient all_reduce
+    # 3. replicated fits (fit_parallel="replicated"): every rank runs the whole fit on identical samples, only the
+    #    pressure solve is sharded; identical weights (re-broadcast) and identical full pressure sets on every rank
+    s = st.SplitStepper(cfg, use_cuda_graph=True, distributed=True, fit_parallel="replicated", **kw)
+    s.fit_initial(tg, 50, lr=1e-3)
+    for _ in range(2):
+        out = s.step()
+    assert math.isfinite(out["advect_loss"].item()) and math.isfinite(out["project_loss"].item())
+    assert s.last["pressure_samples"].shape[0] == 64*64 and s.last["grad_p"].shape == (64*64, 2)
+    for t in (torch.cat([p.detach().reshape(-1) for p in s.velocity_field.parameters()]), s.last["pressure_samples"], s.last["grad_p"]):
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(t, ref), "replicated fits: rank %d differs from rank 0" % rank
+    assert s.last["grad_p"].abs().sum().item() > 0
+    s.close()
+    say(rank, 'replicated fits ok')
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
