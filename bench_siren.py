@@ -71,13 +71,33 @@ def main():
             opt_r.zero_grad(); loss.backward(); opt_r.step()
         t_it_f = timeit(it_fused, 50)
         t_it_r = timeit(it_ref, 50)
+        # the same iteration the way the time-stepper runs it (stepper.py): DirectFit (no autograd; tcgen05 forward /
+        # delta chain / weight gradients, fused MSE and Adam), captured once in a CUDA graph and replayed
+        net_g = S.FusedSiren(i, o, l, h, nonlinearity="sine", tensor_cores=True).cuda()
+        fit = S.DirectFit(net_g, 1e-5, None, max_batch=batch)
+
+        def it_direct():
+            with torch.no_grad():
+                pu = prev(xb); back = (xb - pu[:, :i]*0.05).clamp(-1, 1); adv = prev(back)
+            fit.iterate(xb, adv)
+        prev.tensor_cores = True
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                it_direct()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            it_direct()
+        t_it_g = timeit(graph.replay, 200)
+        del graph
         tf = lambda ms: args.grid*flops/(ms*1e-3)/1e12  # noqa: E731
         print(json.dumps({"shape": name, "net": {"in": i, "hidden": h, "hidden_layers": l, "out": o}, "grid_points": args.grid,
                           "forward_ms": {"torch_fp32": t_ref, "fused_fp32": t_f32, "fused_tcgen05_3xtf32": t_tc},
                           "forward_tflops_algorithmic": {"torch_fp32": tf(t_ref), "fused_fp32": tf(t_f32), "fused_tcgen05_3xtf32": tf(t_tc)},
                           "tensor_roofline": {"achieved_tflops_issued": 3*tf(t_tc), "peak_bf16_tflops": peaks["bf16_tflops"],
                                               "note": "3 TF32 MMAs per algorithmic product; TF32 peak is half the bf16 figure"},
-                          "fit_iteration_ms": {"batch": batch, "torch": t_it_r, "fused": t_it_f}}), flush=True)
+                          "fit_iteration_ms": {"batch": batch, "torch": t_it_r, "fused_autograd_eager": t_it_f, "direct_fit_graph_replay": t_it_g}}), flush=True)
 
 
 if __name__ == "__main__":
