@@ -93,6 +93,13 @@ int nmc_siren_backward_tc(const nmc_siren_shape* shape, const float* const* W, c
 int nmc_siren_weight_grads_tc(const nmc_siren_shape* shape, const float* x, int64_t n, const float* dZ, const float* z_saved,
 							  float* const* gW, float* const* gb, void* stream);
 
+/* The same backward pass in ONE launch for hidden = 64 networks with at most 6 hidden layers (csrc/siren_tc_fused_bwd.cu):
+ * delta chain and every weight / bias gradient, deltas and activations kept in shared memory, gradient tiles accumulated in
+ * TMEM and added to the zero-filled gW / gb at the end.  Nothing but gW / gb is written (no dZ).  Errors on other shapes. */
+int nmc_siren_backward_fused_tc(const nmc_siren_shape* shape, const float* const* W, const float* x, int64_t n,
+								const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
+								const nmc_siren_envelope* env, void* stream);
+
 /* MSE loss of a fit iteration in one launch: diff = y - target, grad_y = dL/dy = diff * 2/count, *loss = mean(diff^2)
  * (count = n * out_dim floats; base.py:83-96 with the loss of model_split.py:113). */
 int nmc_mse_grad(const float* y, const float* target, int64_t count, float* diff, float* grad_y, float* loss, void* stream);
@@ -106,6 +113,33 @@ int nmc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
  * to capture in a CUDA graph: a replayed nmc_adam_step would keep the corrections of its capture-time step. */
 int nmc_adam_step_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
 						 float eps, long long* step, void* stream);
+
+/* ---- per-iteration glue of the fit loops, for CUDA-graph replay (csrc/fit_glue.cu) ------------------------------------------
+ * The random draws of an iteration are keyed by (seed, *epoch, *step, element): `step` is Adam's device-side counter (the
+ * iteration index within a fit), `epoch` a device int64 the host bumps once per fit, so a captured iteration draws fresh
+ * numbers at every replay without a host-side generator.  24-bit uniforms in [0, 1) like torch.rand. */
+
+/* sample_in_training with the 'random' pattern (src/2d/models/base.py:225-241, utils/model_utils.py:22-31): n points uniform in
+ * the box [lo, hi) (host arrays of `dim` floats).  obstacle = {centre[dim], radius} (host) or NULL: a point inside the ball is
+ * redrawn once so that the batch keeps its shape (the reference drops it). */
+int nmc_fit_sample_uniform(int dim, const float* lo, const float* hi, int64_t n, float* out, const long long* step,
+						   const long long* epoch, uint64_t seed, const float* obstacle, void* stream);
+
+/* The projection fit's batch (src/2d/models/model_split.py:272-277): idx = min(floor(u * *count), cap - 1) per element,
+ * out_x[i] = src_x[idx], out_g[i] = src_g[idx] (rows of `dim` floats; *count is a device float). */
+int nmc_fit_gather(int dim, int64_t n, const float* src_x, const float* src_g, const float* count, int64_t cap, float* out_x,
+				   float* out_g, const long long* step, const long long* epoch, uint64_t seed, void* stream);
+
+/* nmc_mse_grad with the rest of an iteration's bookkeeping in the same launch: the target is target - sub when sub != NULL
+ * (u_prev - grad p of the projection fit), `zero` (zero_count floats: the flat gradient buffer) is cleared, and *step_advance
+ * (Adam's device-side counter) is incremented -- every kernel that reads the counter as the iteration index was launched
+ * earlier on the stream, nmc_adam_update_device later. */
+int nmc_mse_grad_fit(const float* y, const float* target, const float* sub, int64_t count, float* diff, float* grad_y, float* loss,
+					 float* zero, int64_t zero_count, long long* step_advance, void* stream);
+
+/* nmc_adam_step_device without the increment (the counter was advanced by nmc_mse_grad_fit). */
+int nmc_adam_update_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+						   float eps, const long long* step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -186,9 +186,15 @@ def _lib():
         L.nmc_siren_weight_grads.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
         L.nmc_siren_backward_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp, vp, vp, C.POINTER(Envelope), vp]
         L.nmc_siren_weight_grads_tc.argtypes = [C.POINTER(Shape), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
+        L.nmc_siren_backward_fused_tc.argtypes = [C.POINTER(Shape), C.POINTER(vp), vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Envelope), vp]
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         L.nmc_adam_step_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
         L.nmc_mse_grad.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
+        L.nmc_mse_grad_fit.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int64, vp, vp]
+        L.nmc_adam_update_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+        f3 = C.POINTER(C.c_float)
+        L.nmc_fit_sample_uniform.argtypes = [C.c_int, f3, f3, C.c_int64, vp, vp, vp, C.c_uint64, f3, vp]
+        L.nmc_fit_gather.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_uint64, vp]
         _configured = True
     return L
 
@@ -398,6 +404,13 @@ class FusedAdam:
             _check(_lib().nmc_adam_step_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
                                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
 
+    def update_flat(self):
+        """step_flat without the increment: the counter was advanced by nmc_mse_grad_fit earlier in the iteration."""
+        self.step_count += 1
+        with torch.cuda.device(self.flat.device):
+            _check(_lib().nmc_adam_update_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                                 self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
+
     def step(self):
         self.step_count += 1
         off = 0
@@ -411,6 +424,36 @@ class FusedAdam:
         with torch.cuda.device(self.flat.device):
             _check(_lib().nmc_adam_step_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
                                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
+
+
+def fit_sample_uniform(n, lo, hi, step_dev, epoch_dev, seed, obstacle=None, out=None):
+    """One launch: n points uniform in the box [lo, hi) (sample_in_training 'random', base.py:225-241); obstacle = (centre, radius):
+    a point inside the ball is redrawn once.  The draw is keyed by (seed, epoch, step) read from device memory at run time, so the
+    call can be captured in a CUDA graph (csrc/fit_glue.cu)."""
+    dim = len(lo)
+    dev = step_dev.device
+    if out is None:
+        out = torch.empty((n, dim), device=dev)
+    f = C.c_float*dim
+    obs = None
+    if obstacle is not None:
+        obs = (C.c_float*(dim + 1))(*[float(v) for v in obstacle[0]], float(obstacle[1]))
+    with torch.cuda.device(dev):
+        _check(_lib().nmc_fit_sample_uniform(dim, f(*[float(v) for v in lo]), f(*[float(v) for v in hi]), n, out.data_ptr(), step_dev.data_ptr(),
+                                             epoch_dev.data_ptr(), int(seed) & (2**64 - 1), obs, _stream()))
+    return out
+
+
+def fit_gather(n, src_x, src_g, count_dev, step_dev, epoch_dev, seed):
+    """One launch: the projection fit's batch, rows idx = floor(u * count) of the pressure samples and of grad p
+    (model_split.py:272-277)."""
+    dim = src_x.shape[1]
+    assert src_x.is_contiguous() and src_g.is_contiguous() and src_g.shape == src_x.shape and count_dev.dtype == torch.float32
+    out_x = torch.empty((n, dim), device=src_x.device); out_g = torch.empty((n, dim), device=src_x.device)
+    with torch.cuda.device(src_x.device):
+        _check(_lib().nmc_fit_gather(dim, n, src_x.data_ptr(), src_g.data_ptr(), count_dev.data_ptr(), src_x.shape[0], out_x.data_ptr(), out_g.data_ptr(),
+                                     step_dev.data_ptr(), epoch_dev.data_ptr(), int(seed) & (2**64 - 1), _stream()))
+    return out_x, out_g
 
 
 class DirectFit:
@@ -450,13 +493,14 @@ class DirectFit:
         # selects the fp32 kernels for A/B measurements
         self.tc_backward = self.tensor_cores and os.environ.get("NMC_SIREN_TC_BWD", "1") != "0"
         self.tc_backward_min = int(os.environ.get("NMC_SIREN_TC_BWD_MIN", "4096"))
+        self.fused_backward = os.environ.get("NMC_SIREN_FUSED_BWD", "0") != "0"  # hidden = 64: the one-kernel backward (experimental)
         self.tc_forward_min = int(os.environ.get("NMC_SIREN_TC_FWD_MIN", "16384"))
         self.dz = torch.empty(((Lh + 1)*H + self.sh.out_dim)*max_batch, device=g.device) if self.tc_backward else None
         self.max_batch = max_batch
         self.loss = torch.zeros((), device=g.device)  # mean squared error of the last iterate() call
 
-    def iterate(self, x, target):
-        return self.finish(x, self.forward(x), target)
+    def iterate(self, x, target, sub=None):
+        return self.finish(x, self.forward(x), target, sub)
 
     def forward(self, x):
         """First half of an iteration: the training forward (saves the pre-activations).  Independent of the target, so a
@@ -473,22 +517,32 @@ class DirectFit:
                 _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
         return y
 
-    def finish(self, x, y, target):
-        """Second half: loss, dL/dy, delta chain, weight gradients, (all_reduce,) Adam.  Returns y - target."""
+    def finish(self, x, y, target, sub=None):
+        """Second half: loss, dL/dy, delta chain, weight gradients, (all_reduce,) Adam.  Returns y - target.
+        The fit target is target - sub when `sub` is given (the projection fit's u_prev - grad p)."""
         n = x.shape[0]
         sh = self.sh
         z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]
         diff = torch.empty_like(y); gy = torch.empty_like(y)
         tgt = target.contiguous()
-        with torch.cuda.device(x.device):  # diff, dL/dy and the loss in one launch
-            _check(_lib().nmc_mse_grad(y.data_ptr(), tgt.data_ptr(), y.numel(), diff.data_ptr(), gy.data_ptr(), self.loss.data_ptr(), _stream()))
-        self.opt.g.zero_()
+        if sub is not None:
+            sub = sub.contiguous()
+            assert sub.shape == tgt.shape
+        with torch.cuda.device(x.device):  # diff, dL/dy, the loss, the zero-fill of the gradient buffer and Adam's t += 1 in one launch
+            _check(_lib().nmc_mse_grad_fit(y.data_ptr(), tgt.data_ptr(), sub.data_ptr() if sub is not None else None, y.numel(), diff.data_ptr(),
+                                           gy.data_ptr(), self.loss.data_ptr(), self.opt.g.data_ptr(), self.opt.g.numel(), self.opt.step_dev.data_ptr(), _stream()))
         if self.tc_backward and n >= self.tc_backward_min and n % 4 == 0 and sh.n_hidden_layers >= 1:
-            # tcgen05 delta chain + weight gradients (csrc/siren_tc_bwd.cu); the activations are recomputed from z
-            dZ = self.dz[: ((sh.n_hidden_layers + 1)*sh.hidden + sh.out_dim)*n]
             gW0, gb0, gWh, gbh, gWl, gbl = self.out
             gW = [gW0] + [gWh[i] for i in range(sh.n_hidden_layers)] + [gWl]
             gb = [gb0] + [gbh[i] for i in range(sh.n_hidden_layers)] + [gbl]
+        if self.tc_backward and self.fused_backward and n >= self.tc_backward_min and sh.hidden == 64 and 1 <= sh.n_hidden_layers <= 6:
+            # one kernel: delta chain and all gradients, deltas / activations in shared memory (csrc/siren_tc_fused_bwd.cu)
+            with torch.cuda.device(x.device):
+                _check(_lib().nmc_siren_backward_fused_tc(C.byref(sh), _ptrs(self.W), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
+                                                          _ptrs(gW), _ptrs(gb), self.env, _stream()))
+        elif self.tc_backward and n >= self.tc_backward_min and n % 4 == 0 and sh.n_hidden_layers >= 1:
+            # tcgen05 delta chain + weight gradients (csrc/siren_tc_bwd.cu); the activations are recomputed from z
+            dZ = self.dz[: ((sh.n_hidden_layers + 1)*sh.hidden + sh.out_dim)*n]
             with torch.cuda.device(x.device):
                 _check(_lib().nmc_siren_backward_tc(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
                                                     dZ.data_ptr(), self.env, _stream()))
@@ -499,7 +553,7 @@ class DirectFit:
         if self.world > 1:  # mean over the global batch = mean over ranks of the local means (equal shard sizes)
             import torch.distributed as dist
             dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG, group=self.group)
-        self.opt.step_flat()
+        self.opt.update_flat()
         return diff
 
     def close(self):

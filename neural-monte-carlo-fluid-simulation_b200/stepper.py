@@ -23,7 +23,7 @@ import os
 import torch
 
 from . import capi, zombie, fields
-from .siren import (FusedSiren, DirectFit, wall_envelope, karman_envelope, smoke_obs_envelope, karman3d_envelope, smoke_envelope,
+from .siren import (FusedSiren, DirectFit, fit_sample_uniform, fit_gather, wall_envelope, karman_envelope, smoke_obs_envelope, karman3d_envelope, smoke_envelope,
                     envelope_reference)
 
 
@@ -114,6 +114,9 @@ class SplitStepper:
         self.boundary, self.use_graph = boundary, use_cuda_graph
         # fit target on a second stream, parallel to the training forward (NMC_OVERLAP_TARGETS=0: one stream, for A/B runs)
         self.overlap_targets = os.environ.get("NMC_OVERLAP_TARGETS", "1") != "0"
+        # captured iterations draw their batches with one launch keyed by device-side counters (csrc/fit_glue.cu) instead of
+        # three to eight torch launches; without CUDA graphs the batches come from torch's generator (NMC_FIT_GLUE=0: always)
+        self.fused_glue = bool(use_cuda_graph) and os.environ.get("NMC_FIT_GLUE", "1") != "0"
         torch.manual_seed(seed)
         self.dim = dim = len(self.size)//2
         if dim not in (2, 3):
@@ -131,6 +134,7 @@ class SplitStepper:
         self.timestep, self.seed = 0, seed
         self.last = {}
         self._fit, self._graphs, self._proj = None, {}, None
+        self._epoch = torch.zeros((), dtype=torch.int64, device=self.dev)  # fits started so far: part of the key of the captured draws
         if self.world > 1:  # identical initial weights (same seed above); data-parallel fits: different training samples per rank from here on
             torch.manual_seed(seed*7919 + 1 + (self.rank if self.fit_world > 1 else 0))
         self.obstacle, self.karman_vel, self.reset_wts = obstacle, float(karman_vel), bool(reset_wts)
@@ -186,11 +190,16 @@ class SplitStepper:
         """circle_obstable_functions (main.py:101-104): signed distance to the cylinder."""
         return torch.linalg.norm(samples - self._obs_c, dim=-1) - self.obstacle[1]
 
-    def sample_random(self, n, keep_shape=True):
+    def sample_random(self, n, keep_shape=True, fused=False):
         """sample_in_training with the 'random' pattern (base.py:225-241, utils/model_utils.py:22-31).  With an
         obstacle the reference drops the samples inside it (a batch a fraction of a percent smaller); here a sample
         inside is redrawn once so that the batch keeps its shape (CUDA-graph replay), or, with keep_shape=False,
         dropped exactly like the reference."""
+        if fused and keep_shape:  # inside a captured fit iteration only: the key is the fit's (epoch, iteration) pair
+            # data-parallel fits: every rank its own stream; replicated fits: the same samples on every rank
+            seed = self.seed*0x9E3779B1 + 0x632BE5AB*(self.rank if self.fit_world > 1 else 0)
+            return fit_sample_uniform(n, self.size[0::2], self.size[1::2], self._fit.opt.step_dev, self._epoch, seed,
+                                      obstacle=self.obstacle if self.boundary == "karman" else None)
         x = torch.rand(n, self.dim, device=self.dev)*(self._hi - self._lo) + self._lo
         if self.boundary == "karman":
             if keep_shape:
@@ -219,6 +228,7 @@ class SplitStepper:
             self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2, distributed=self.fit_world > 1)
         fit = self._fit
         fit.opt.reset()
+        self._epoch += 1
         if self.reset_wts:
             self._reset_weights()
             fit.sync_parameters()  # the re-initialisation draws from per-rank random streams
@@ -238,7 +248,7 @@ class SplitStepper:
                 samples, make_target = iteration()
                 if side2 is None:
                     target = make_target(samples)
-                    fit.iterate(samples, target)
+                    fit.iterate(samples, *target) if isinstance(target, tuple) else fit.iterate(samples, target)
                     return
                 main = torch.cuda.current_stream()
                 side2.wait_stream(main)
@@ -246,7 +256,7 @@ class SplitStepper:
                     target = make_target(samples)
                 y = fit.forward(samples)
                 main.wait_stream(side2)
-                fit.finish(samples, y, target)
+                fit.finish(samples, y, *target) if isinstance(target, tuple) else fit.finish(samples, y, target)
 
             graph = None
             if self.use_graph:
@@ -316,7 +326,7 @@ class SplitStepper:
                 return self.query_velocity(back, use_prev=True)
 
         def iteration():
-            return self.sample_random(n), make_target
+            return self.sample_random(n, fused=self.fused_glue), make_target
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect")
 
     def divergence_grid(self):
@@ -398,6 +408,16 @@ class SplitStepper:
             # 2D: randint(0, N - 1) excludes the last point (2d model_split.py:274); 3D: randint(0, N) (3d model_split.py:295)
             ps[:big].copy_(samples_all); pg[:big].copy_(grad_p); pc.fill_(float(big - 1 if self.dim == 2 else big))
 
+            def iteration_fused():
+                # the same draw and both gathers in one launch; the target is (u_prev(samples), grad p): the subtraction happens in the loss kernel
+                seed = self.seed*0x9E3779B1 + 0x632BE5AB*(self.rank if self.fit_world > 1 else 0) + 0x1B873593
+                xs, gs = fit_gather(n, ps, pg, pc, self._fit.opt.step_dev, self._epoch, seed)
+
+                def make_target(samples):
+                    with torch.no_grad():
+                        return self.query_velocity(samples, use_prev=True), gs
+                return xs, make_target
+
             def iteration():
                 # uniform index in [0, big - 2] (the reference's randint(0, big - 1) excludes the last point, :274);
                 # the bound is a device scalar so the captured graph serves every step's sample count
@@ -416,6 +436,8 @@ class SplitStepper:
                     with torch.no_grad():
                         return self.query_velocity(samples, use_prev=True) - grad_p[idx]
                 return samples_all[idx], make_target
+        if self.use_graph and self.fused_glue:
+            iteration = iteration_fused
         return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="project")
 
     def _sync_prev(self):

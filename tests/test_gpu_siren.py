@@ -393,3 +393,155 @@ def test_tensor_core_backward_in_direct_fit(siren, shape):
     for _ in range(8):
         fa.iterate(x, target); fb.iterate(x, target)
     _assert_same_trajectory(a, b, start)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 6, 2), (3, 64, 5, 3), (2, 64, 1, 2)])
+@pytest.mark.parametrize("n", [4096, 16384, 128*150 + 52, 60])
+@pytest.mark.parametrize("with_env", [False, True])
+def test_fused_tensor_core_backward_matches_fp32_kernels_and_autograd(siren, shape, n, with_env):
+    """The one-kernel backward of the hidden = 64 networks (csrc/siren_tc_fused_bwd.cu: delta chain and every gradient, the
+    delta / activation buffers read K-major for the chain and MN-major for the gradients, bias gradients from a column of ones,
+    gradient tiles accumulated in TMEM across a CTA's tiles) vs the exact-fp32 kernels and torch autograd."""
+    import ctypes as C
+    if with_env and n not in (4096, 60):
+        pytest.skip("envelope covered at two batch sizes")
+    net = _net(siren, shape, seed=91)
+    x = _coords(n, shape[0], seed=92)
+    env = siren.wall_envelope((-1.0, 1.0)*shape[0], 0.1) if with_env else None
+    target = torch.sin(3*x[:, :1]).expand(-1, shape[3]).contiguous()
+    with torch.no_grad():
+        y = net(x, envelope=env)
+    gy = ((y - target)*(2.0/y.numel())).contiguous()
+    _, gW32, gb32 = _raw_backward(siren, net, x, gy, env, tc=False)
+    L = siren._lib()
+    lin = net._linears()
+    W = [m.weight.detach().contiguous() for m in lin]; b = [m.bias.detach().contiguous() for m in lin]
+    sh = siren._shape_of(W, 30.0)
+    z = torch.empty(((sh.n_hidden_layers + 1)*sh.hidden, n), device=x.device)
+    yy = torch.empty((n, sh.out_dim), device=x.device)
+    siren._check(L.nmc_siren_forward(C.byref(sh), siren._ptrs(W), siren._ptrs(b), x.data_ptr(), n, yy.data_ptr(), z.data_ptr(), env, siren._stream()))
+    gW = [torch.zeros_like(w) for w in W]; gb = [torch.zeros_like(v) for v in b]
+    siren._check(L.nmc_siren_backward_fused_tc(C.byref(sh), siren._ptrs(W), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
+                                               siren._ptrs(gW), siren._ptrs(gb), env, siren._stream()))
+    torch.cuda.synchronize()
+    for l, (a, r) in enumerate(zip(gW, gW32)):
+        assert (a - r).abs().max().item() <= 3e-5*r.abs().max().item() + 1e-12, ("gW", l, (a - r).abs().max().item(), r.abs().max().item())
+    for l, (a, r) in enumerate(zip(gb, gb32)):
+        assert (a - r).abs().max().item() <= 3e-5*r.abs().max().item() + 1e-12, ("gb", l, (a - r).abs().max().item(), r.abs().max().item())
+    ref_out = siren.envelope_reference(env, x, net.forward_reference(x))
+    loss = ((ref_out - target)**2).mean()
+    gr = torch.autograd.grad(loss, [m.weight for m in lin] + [m.bias for m in lin])
+    for a, r in zip(gW + gb, gr):
+        assert (a - r).abs().max().item() <= 2e-4*r.abs().max().item() + 1e-9
+
+
+def _counters(step, epoch):
+    return (torch.full((), step, dtype=torch.int64, device="cuda"), torch.full((), epoch, dtype=torch.int64, device="cuda"))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_fit_sample_uniform_kernel(siren, dim):
+    """One-launch batch draw of a captured fit iteration (csrc/fit_glue.cu; sample_in_training 'random', base.py:225-241):
+    inside the box, uniform, a new draw for every (epoch, step) read from device memory, reproducible for the same key,
+    and -- with an obstacle -- redrawn once when inside the ball."""
+    lo, hi = [-1.0, 0.5, 2.0][:dim], [3.0, 1.5, 2.5][:dim]
+    n = 200000
+    st, ep = _counters(3, 7)
+    a = siren.fit_sample_uniform(n, lo, hi, st, ep, seed=11)
+    assert a.shape == (n, dim)
+    for k in range(dim):
+        assert a[:, k].min().item() >= lo[k] and a[:, k].max().item() < hi[k]
+        u = (a[:, k] - lo[k])/(hi[k] - lo[k])
+        assert abs(u.mean().item() - 0.5) < 4/np.sqrt(12*n) and abs(u.var().item() - 1/12) < 1e-3
+        hist = torch.histc(u, bins=64, min=0, max=1)
+        assert (hist - n/64).abs().max().item() < 5*np.sqrt(n/64)
+    if dim > 1:  # the coordinates are independent
+        c = torch.corrcoef(a.t())
+        assert (c - torch.eye(dim, device="cuda")).abs().max().item() < 0.01
+    assert torch.equal(a, siren.fit_sample_uniform(n, lo, hi, st, ep, seed=11))
+    st2, ep2 = _counters(4, 7)
+    b = siren.fit_sample_uniform(n, lo, hi, st2, ep2, seed=11)
+    assert (a == b).float().mean().item() < 1e-3
+    st3, ep3 = _counters(3, 8)
+    assert (a == siren.fit_sample_uniform(n, lo, hi, st3, ep3, seed=11)).float().mean().item() < 1e-3
+    assert (a == siren.fit_sample_uniform(n, lo, hi, st, ep, seed=12)).float().mean().item() < 1e-3
+    # graph replay: the counters are read at run time
+    out = torch.empty((n, dim), device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        siren.fit_sample_uniform(n, lo, hi, st, ep, seed=11, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        siren.fit_sample_uniform(n, lo, hi, st, ep, seed=11, out=out)
+    st.fill_(4)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, b)
+    # obstacle: a ball covering ~20 % of the box (2D) -- after one redraw ~4 % of the points are still inside
+    c, r = [0.5*(l + h) for l, h in zip(lo, hi)], 0.25
+    st.fill_(3)
+    o = siren.fit_sample_uniform(n, lo, hi, st, ep, seed=11, obstacle=(c, r))
+    inside = ((o - torch.tensor(c, device="cuda")).norm(dim=1) <= r).float().mean().item()
+    frac = ((a - torch.tensor(c, device="cuda")).norm(dim=1) <= r).float().mean().item()
+    assert frac > 0 and abs(inside - frac*frac) < 4*np.sqrt(frac*frac/n) + 1e-4
+    keep = (a - torch.tensor(c, device="cuda")).norm(dim=1) > r
+    assert torch.equal(o[keep], a[keep])   # points outside the obstacle are the first draw
+
+
+def test_fit_gather_kernel(siren):
+    """The projection fit's batch in one launch (model_split.py:272-277): rows floor(u count) of the samples and of grad p."""
+    cap, n, dim = 5000, 100000, 3
+    src_x = torch.arange(cap*dim, device="cuda", dtype=torch.float32).reshape(cap, dim).contiguous()
+    src_g = -src_x
+    count = torch.tensor(3000.0, device="cuda")
+    st, ep = _counters(9, 2)
+    x, g = siren.fit_gather(n, src_x, src_g, count, st, ep, seed=5)
+    idx = (x[:, 0]/dim).long()
+    assert torch.equal(x, src_x[idx]) and torch.equal(g, src_g[idx])
+    assert idx.min().item() >= 0 and idx.max().item() <= 2999
+    hist = torch.bincount(idx, minlength=3000).float()
+    assert (hist > 0).float().mean().item() > 0.99 and abs(idx.float().mean().item() - 1499.5) < 4*3000/np.sqrt(12*n)
+    st.fill_(10)
+    x2, _ = siren.fit_gather(n, src_x, src_g, count, st, ep, seed=5)
+    assert (x2[:, 0] == x[:, 0]).float().mean().item() < 0.01
+    count.fill_(1.0e9)   # the clamp to the buffer
+    x3, _ = siren.fit_gather(n, src_x, src_g, count, st, ep, seed=5)
+    assert (x3[:, 0]/dim).long().max().item() == cap - 1
+
+
+@pytest.mark.parametrize("count", [3*4096, 2*1000 + 1])
+def test_mse_grad_fit_kernel(siren, count):
+    """nmc_mse_grad_fit: the loss kernel that also subtracts grad p from the target, clears the flat gradient buffer and advances
+    Adam's device-side step; nmc_adam_update_device then equals torch.optim.Adam for the advanced step."""
+    import ctypes as C
+    L = siren._lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    y, t, s = (torch.randn(count, generator=g, device="cuda") for _ in range(3))
+    diff, gy = torch.empty_like(y), torch.empty_like(y)
+    loss = torch.zeros((), device="cuda")
+    zero = torch.ones(21123, device="cuda")
+    step = torch.full((), 4, dtype=torch.int64, device="cuda")
+    siren._check(L.nmc_mse_grad_fit(y.data_ptr(), t.data_ptr(), s.data_ptr(), count, diff.data_ptr(), gy.data_ptr(), loss.data_ptr(),
+                                    zero.data_ptr(), zero.numel(), step.data_ptr(), siren._stream()))
+    ref = y - (t - s)
+    assert torch.equal(diff, ref) and torch.allclose(gy, ref*(2.0/count), rtol=1e-6, atol=0)
+    assert loss.item() == pytest.approx((ref.double()**2).mean().item(), rel=1e-5)
+    assert zero.abs().max().item() == 0.0 and step.item() == 5
+    siren._check(L.nmc_mse_grad_fit(y.data_ptr(), t.data_ptr(), None, count, diff.data_ptr(), gy.data_ptr(), loss.data_ptr(),
+                                    None, 0, None, siren._stream()))
+    assert torch.equal(diff, y - t) and step.item() == 5
+    # Adam with the device-side counter, not advanced by the update itself
+    p = torch.randn(1000, generator=g, device="cuda"); grad = torch.randn(1000, generator=g, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step.fill_(0)
+    for it in range(3):
+        pr.grad = grad.clone(); opt.step()
+        step += 1
+        siren._check(L.nmc_adam_update_device(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
+                                              step.data_ptr(), siren._stream()))
+        assert step.item() == it + 1
+    assert torch.allclose(p, pr.detach(), rtol=1e-5, atol=1e-7)
