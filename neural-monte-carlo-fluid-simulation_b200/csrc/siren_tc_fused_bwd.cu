@@ -3,18 +3,21 @@
 // src/2d/models/networks.py:47-57).  The two-kernel form (siren_tc_bwd.cu) writes every delta to global memory and reads it
 // back, with the activations, in a second launch whose MMA batches wait on those loads; here a CTA keeps the deltas dZ_l and
 // the activations A_{l-1} of its 128 samples in shared memory and uses the SAME buffers twice:
-//   dA_{l-1} = dZ_l W_l            A operand: dZ_l [sample x neuron], K-major (K = neurons)                      M 128, N 64
-//   dW_l    += dZ_l^T [A_{l-1} 1]  A operand: the dZ_l buffer read MN-major (M = neurons, K = samples);          M 64, N 72
-//                                  B operand: the A_{l-1} buffer read MN-major, with a column of ones appended,
-//                                  so that column 64 of the product is the bias gradient sum_s dZ_l[s][.]
-// In the un-swizzled canonical layout the element (r, c) of a [rows x K] K-major operand sits at
-// (r/8)(32 K) + (c/4) 128 + (r%8) 16 + (c%4) 4; read MN-major with MN = c and K = r the same bytes are a canonical operand
-// with SBO = 128 (16-byte chunks of four neurons) and LBO = 32 K (groups of eight samples) -- cute::UMMA make_umma_desc<Major::MN>,
-// mma_traits_sm100.hpp:238-270 -- and one K step (8 samples) advances the start address by LBO.
-// First layer: dW_0 | db_0 = dZ_0^T [x 1] (N = 8); last layer: dW_last^T = A_L^T gy' (N = 8); both as M = 64 MMAs over small
-// [128 x 8] operands.  All products are 3xTF32 (hi.hi + hi.lo + lo.hi).  The gradient tiles accumulate in TMEM across the
-// CTA's tiles (512 columns: 64 for the chain, 72 per hidden layer, 16 for the small layers: up to 6 hidden layers) and are added
-// to the gradient buffer once, with 16-byte vector reductions.
+//   dA_{l-1} = dZ_l W_l            A operand: dZ_l [sample x neuron], K-major (K = neurons), no swizzle            M 128, N 64
+//   dW_l    += dZ_l^T A_{l-1}      A operand: dZ_l read MN-major (M = neurons, K = samples);                       M 64, N 64
+//                                  B operand: A_{l-1} read MN-major
+//   db_l    += dZ_l^T 1            the same A operand against a constant tile of ones (N = 8; column 0 is the sum)
+// tcgen05.mma.kind::tf32 reads an MN-major operand ONLY in the 128-byte-swizzle / 32-byte-base layout (descriptor layout type
+// 1, cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B): with no swizzle or the 32 / 64 / 128-byte swizzles the instruction runs
+// and multiplies zeros (profiles/tools/umma_mn_probe.cu reads the addresses back through one-hot operands).  That layout is
+// rows of 32 MN elements (128 bytes) per K index, four K rows per 512-byte atom, the 32-byte chunk index XORed with k % 4;
+// SBO = stride between atoms along K, LBO = stride between groups of 32 along MN.  A K-major read of the same bytes does not
+// exist (layout type 1 faults for K-major operands, the 128-byte K-major swizzle permutes 16-byte chunks by row % 8), so the
+// deltas are written twice: K-major for the chain, MN-major for the gradients; the activations only MN-major.
+// First layer: dW_0 | db_0 = dZ_0^T [x 1] (N = 8); last layer: dW_last^T = A_L^T gy' (N = 8): the small operand [8 x 128] is
+// K-major (K = samples).  All products are 3xTF32 (hi.hi + hi.lo + lo.hi).  The gradient tiles accumulate in TMEM across the
+// CTA's tiles (512 columns: 64 for the chain, 64 + 8 per hidden layer, 16 for the small layers: up to 6 hidden layers) and are
+// added to the gradient buffer once, with 16-byte vector reductions.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
@@ -30,17 +33,24 @@ using nmc_siren_detail::Env;
 
 constexpr int H = 64;
 constexpr int kTile = 128, kThreads = 256, kMaxLayers = 18, kMaxHidden = 6;
-constexpr int KA = H + 8;        // columns of the activation buffer: 64 activations, a one, seven zeros
-constexpr int HC = H/2;          // columns per thread (two threads per sample row)
+constexpr int HC = H/2;          // columns per thread (two threads per sample row) = one MN group of 32 neurons
+constexpr int kMnGroup = kTile*128;   // bytes of one [128 samples x 32 neurons] block of an MN-major buffer
+constexpr uint32_t kTransA = 1u << 15, kTransB = 1u << 16;   // instruction descriptor: operand is MN-major
+constexpr uint64_t kLayoutMn = 1ull << 61;                   // shared-memory descriptor: 128-byte swizzle, 32-byte base
+
+// MN-major operand (MN = neurons, K = samples): byte offset of the 32-byte chunk holding neurons 8j .. 8j+7 (j = 0..3 within
+// the thread's group of 32) of sample r
+__device__ __forceinline__ int mnChunkOffset(int group, int r, int j) {
+	return group*kMnGroup + (r >> 2)*512 + (r & 3)*128 + ((j ^ (r & 3)) << 5);
+}
+// small K-major operand [8 x 128 samples]: element (n, sample r)
+__device__ __forceinline__ int smallOffset(int n, int r) { return (r >> 2)*128 + n*16 + (r & 3)*4; }
 
 struct Params {
 	const float* W[kMaxLayers];
 	float* gW[kMaxLayers];
 	float* gb[kMaxLayers];
 };
-
-// instruction descriptor with both operands MN-major (bits 15 / 16 of cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t instrDescTf32MN(int M, int N) { return instrDescTf32(M, N) | (1u << 15) | (1u << 16); }
 
 __device__ __forceinline__ void tmemLoad8(uint32_t taddr, uint32_t (&v)[8]) {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -51,18 +61,23 @@ __device__ __forceinline__ void tmemLoad8(uint32_t taddr, uint32_t (&v)[8]) {
 __global__ void __launch_bounds__(kThreads, 1)
 sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 					 const float* __restrict__ zSaved, const float* __restrict__ gy) {
-	extern __shared__ __align__(128) unsigned char smem[];
-	unsigned char* Dhi = smem;                        // dZ_l [128 x 64]
+	extern __shared__ __align__(1024) unsigned char smem[];
+	unsigned char* Dhi = smem;                        // dZ_l [128 x 64], K-major (chain operand)
 	unsigned char* Dlo = Dhi + kTile*H*4;
-	unsigned char* Ahi = Dlo + kTile*H*4;             // [A_{l-1} | 1 | 0..] [128 x 72]
-	unsigned char* Alo = Ahi + kTile*KA*4;
-	unsigned char* Bhi = Alo + kTile*KA*4;            // W_l^T [64 x 64]
+	unsigned char* Mhi = Dlo + kTile*H*4;             // dZ_l, MN-major (gradient operand)
+	unsigned char* Mlo = Mhi + kTile*H*4;
+	unsigned char* Ahi = Mlo + kTile*H*4;             // A_{l-1}, MN-major
+	unsigned char* Alo = Ahi + kTile*H*4;
+	unsigned char* Bhi = Alo + kTile*H*4;             // W_l^T [64 x 64]
 	unsigned char* Blo = Bhi + H*H*4;
-	unsigned char* Shi = Blo + H*H*4;                 // small operand [128 x 8]: gy' (last layer), then [x 1] (first layer)
-	unsigned char* Slo = Shi + kTile*8*4;
-	float* sWL = reinterpret_cast<float*>(Slo + kTile*8*4);   // last layer's weights [outDim][H]
-	__shared__ __align__(8) unsigned long long mbar;
-	__shared__ uint32_t tmemBaseSh;
+	// the small operand [8 x 128] (gy' for the last layer, then [x 1] for the first) lives in the weight buffer: it is written
+	// and read while no chain batch is in flight (before the first storeW of a tile / after the last chain batch)
+	unsigned char* Shi = Bhi;
+	unsigned char* Slo = Blo;
+	unsigned char* ones = Blo + H*H*4;                // [8 x 8] K-major tile of ones (bias gradients)
+	float* sWL = reinterpret_cast<float*>(ones + 256);   // last layer's weights [outDim][H]
+	unsigned long long& mbar = *reinterpret_cast<unsigned long long*>(ones + 256 + 3*H*4);   // after sWL (room for three output rows)
+	uint32_t& tmemBaseSh = *reinterpret_cast<uint32_t*>(ones + 256 + 3*H*4 + 8);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & (kTile - 1), half = tid >> 7;
 	const int cBeg = half*HC;
 	const int last = nHidden + 1;
@@ -77,15 +92,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	const uint32_t barAddr = smemAddr(&mbar);
 	// TMEM columns: [0, 64) chain accumulator; hidden layer l: [64 + 72 (l - 1), + 72); small layers: 16 columns at the end
 	const uint32_t colSmall = 64u + 72u*(uint32_t)nHidden;   // +0: dW_0 | db_0 (8 columns), +8: dW_last^T (8 columns)
-#if defined(NMC_DBG_VARIANT) && NMC_DBG_VARIANT == 1
-	const uint32_t idChain = instrDescTf32(kTile, H), idGrad = instrDescTf32(H, KA), idSmall = instrDescTf32MN(H, 8);
-#elif defined(NMC_DBG_VARIANT) && NMC_DBG_VARIANT == 2
-	const uint32_t idChain = instrDescTf32(kTile, H), idGrad = instrDescTf32MN(H, 64), idSmall = instrDescTf32MN(H, 8);
-#elif defined(NMC_DBG_VARIANT) && NMC_DBG_VARIANT == 3
-	const uint32_t idChain = instrDescTf32(kTile, H), idGrad = instrDescTf32(H, 64) | (1u << 16), idSmall = instrDescTf32MN(H, 8);
-#else
-	const uint32_t idChain = instrDescTf32(kTile, H), idGrad = instrDescTf32MN(H, KA), idSmall = instrDescTf32MN(H, 8);
-#endif
+	const uint32_t idChain = instrDescTf32(kTile, H), idGrad = instrDescTf32(H, H) | kTransA | kTransB, idSmall = instrDescTf32(H, 8) | kTransA;
 	uint32_t phase = 0;
 
 	constexpr int RW = H*H/4/kThreads; // 4
@@ -121,18 +128,13 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	// descriptors (start address in 16-byte units in the low bits: adding to the 64-bit value moves the operand)
 	const uint64_t dD_K_h = smemDesc(smemAddr(Dhi), 128, H*32), dD_K_l = smemDesc(smemAddr(Dlo), 128, H*32);          // chain A: K-major, K = neurons
 	const uint64_t dB_K_h = smemDesc(smemAddr(Bhi), 128, H*32), dB_K_l = smemDesc(smemAddr(Blo), 128, H*32);          // chain B: K-major
-	const uint64_t dD_MN_h = smemDesc(smemAddr(Dhi), H*32, 128), dD_MN_l = smemDesc(smemAddr(Dlo), H*32, 128);        // gradient A: MN-major (LBO = sample groups, SBO = neuron chunks)
-	const uint64_t dA_MN_h = smemDesc(smemAddr(Ahi), KA*32, 128), dA_MN_l = smemDesc(smemAddr(Alo), KA*32, 128);      // gradient B / last-layer A
-	const uint64_t dS_MN_h = smemDesc(smemAddr(Shi), 8*32, 128), dS_MN_l = smemDesc(smemAddr(Slo), 8*32, 128);        // small B
+	const uint64_t dD_MN_h = smemDesc(smemAddr(Mhi), kMnGroup, 512) | kLayoutMn, dD_MN_l = smemDesc(smemAddr(Mlo), kMnGroup, 512) | kLayoutMn;   // gradient A
+	const uint64_t dA_MN_h = smemDesc(smemAddr(Ahi), kMnGroup, 512) | kLayoutMn, dA_MN_l = smemDesc(smemAddr(Alo), kMnGroup, 512) | kLayoutMn;   // gradient B / last-layer A
+	const uint64_t dS_K_h = smemDesc(smemAddr(Shi), 128, 256), dS_K_l = smemDesc(smemAddr(Slo), 128, 256);            // small B [8 x 128], K-major
+	const uint64_t dOnes = smemDesc(smemAddr(ones), 128, 256);
+	constexpr uint32_t kMnStep = 1024/16, kSmallStep = 256/16;   // one K step = 8 samples
 
-	// the ones column of the activation buffer (and its zero padding) never changes
-	if (half == 1) {
-		const int off = coreOffsetBytes<KA>(row, H);
-		*reinterpret_cast<float4*>(Ahi + off) = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
-		*reinterpret_cast<float4*>(Ahi + off + 128) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		*reinterpret_cast<float4*>(Alo + off) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		*reinterpret_cast<float4*>(Alo + off + 128) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	}
+	if (tid < 64) reinterpret_cast<float*>(ones)[tid] = 1.0f;
 	if ((long long)blockIdx.x*kTile < n) loadW(nHidden);
 
 	int tilesDone = 0;
@@ -156,12 +158,13 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 		}
 		if (half == 0) { // small operand: gy' padded to eight columns
 			bl0 += g0; bl1 += g1; bl2 += g2;
-			float4 h, o;
-			splitTf32(make_float4(g0, g1, g2, 0.0f), h, o);
-			const int off = coreOffsetBytes<8>(row, 0);
-			*reinterpret_cast<float4*>(Shi + off) = h; *reinterpret_cast<float4*>(Slo + off) = o;
-			*reinterpret_cast<float4*>(Shi + off + 128) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-			*reinterpret_cast<float4*>(Slo + off + 128) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			const float gs[8] = {g0, g1, g2, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				float h, o;
+				splitTf32(gs[q], h, o);
+				*reinterpret_cast<float*>(Shi + smallOffset(q, row)) = h; *reinterpret_cast<float*>(Slo + smallOffset(q, row)) = o;
+			}
 		}
 		float zreg[HC];
 		{
@@ -184,11 +187,12 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 				d[q] = v*w0*__cosf(t);
 			}
 			float4 h, o;
-			splitTf32(make_float4(d[0], d[1], d[2], d[3]), h, o);
+			splitTf32(make_float4(live ? d[0] : 0.0f, live ? d[1] : 0.0f, live ? d[2] : 0.0f, live ? d[3] : 0.0f), h, o);
 			int off = coreOffsetBytes<H>(row, cBeg + q4);
 			*reinterpret_cast<float4*>(Dhi + off) = h; *reinterpret_cast<float4*>(Dlo + off) = o;
+			off = mnChunkOffset(half, row, q4 >> 3) + (q4 & 4)*4;
+			*reinterpret_cast<float4*>(Mhi + off) = h; *reinterpret_cast<float4*>(Mlo + off) = o;
 			splitTf32(make_float4(a[0], a[1], a[2], a[3]), h, o);
-			off = coreOffsetBytes<KA>(row, cBeg + q4);
 			*reinterpret_cast<float4*>(Ahi + off) = h; *reinterpret_cast<float4*>(Alo + off) = o;
 		}
 		fenceProxyAsync();
@@ -196,7 +200,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 		__syncthreads();
 		if (tid == 0) { // dW_last^T [64 x 8] += A_L^T gy'
 			fenceAfterSync();
-			issue(tmemBase + colSmall + 8u, dA_MN_h, dA_MN_l, dS_MN_h, dS_MN_l, KA*2, 16, kTile/8, idSmall, acc);
+			issue(tmemBase + colSmall + 8u, dA_MN_h, dA_MN_l, dS_K_h, dS_K_l, kMnStep, kSmallStep, kTile/8, idSmall, acc);
 			mmaCommit(barAddr);
 		}
 		for (int l = nHidden; l >= 1; l--) {
@@ -224,7 +228,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 				}
 				float4 h, o;
 				splitTf32(make_float4(a[0], a[1], a[2], a[3]), h, o);
-				const int off = coreOffsetBytes<KA>(row, cBeg + q4);
+				const int off = mnChunkOffset(half, row, q4 >> 3) + (q4 & 4)*4;
 				*reinterpret_cast<float4*>(Ahi + off) = h; *reinterpret_cast<float4*>(Alo + off) = o;
 			}
 			fenceProxyAsync();
@@ -235,7 +239,13 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 			if (tid == 0) {
 				fenceAfterSync();
 				issue(tmemBase, dD_K_h, dD_K_l, dB_K_h, dB_K_l, 16, 16, H/8, idChain, false);                                   // dA_{l-1}
-				issue(tmemBase + 64u + 72u*(uint32_t)(l - 1), dD_MN_h, dD_MN_l, dA_MN_h, dA_MN_l, H*2, KA*2, kTile/8, idGrad, acc); // dW_l | db_l
+				const uint32_t colL = tmemBase + 64u + 72u*(uint32_t)(l - 1);
+				issue(colL, dD_MN_h, dD_MN_l, dA_MN_h, dA_MN_l, kMnStep, kMnStep, kTile/8, idGrad, acc);                        // dW_l
+#pragma unroll 1
+				for (int ks = 0; ks < kTile/8; ks++) {                                                                           // db_l
+					mmaTf32(colL + 64u, dD_MN_h + (uint64_t)(kMnStep*ks), dOnes, idSmall, (acc || ks > 0) ? 1u : 0u);
+					mmaTf32(colL + 64u, dD_MN_l + (uint64_t)(kMnStep*ks), dOnes, idSmall, 1u);
+				}
 				mmaCommit(barAddr);
 			}
 			mbarWait(barAddr, phase);
@@ -250,23 +260,28 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 			for (int c0 = 0; c0 < HC; c0 += 4) {
 				float4 h, o;
 				splitTf32(make_float4(__uint_as_float(v[c0])*cs[c0], __uint_as_float(v[c0 + 1])*cs[c0 + 1], __uint_as_float(v[c0 + 2])*cs[c0 + 2], __uint_as_float(v[c0 + 3])*cs[c0 + 3]), h, o);
-				const int off = coreOffsetBytes<H>(row, cBeg + c0);
+				int off = coreOffsetBytes<H>(row, cBeg + c0);
 				*reinterpret_cast<float4*>(Dhi + off) = h; *reinterpret_cast<float4*>(Dlo + off) = o;
+				off = mnChunkOffset(half, row, c0 >> 3) + (c0 & 4)*4;
+				*reinterpret_cast<float4*>(Mhi + off) = h; *reinterpret_cast<float4*>(Mlo + off) = o;
 			}
 		}
 		// first layer: dW_0 | db_0 = dZ_0^T [x 1]
 		if (half == 0) {
-			float4 h, o;
-			splitTf32(make_float4(x0, x1, x2, 1.0f), h, o);
-			const int off = coreOffsetBytes<8>(row, 0);
-			*reinterpret_cast<float4*>(Shi + off) = h; *reinterpret_cast<float4*>(Slo + off) = o; // columns 4..7 stay zero
+			const float xs4[4] = {x0, x1, x2, 1.0f};   // rows 4..7 of the operand stay zero
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				float h = 0.0f, o = 0.0f;
+				if (q < 4) splitTf32(xs4[q], h, o);
+				*reinterpret_cast<float*>(Shi + smallOffset(q, row)) = h; *reinterpret_cast<float*>(Slo + smallOffset(q, row)) = o;
+			}
 		}
 		fenceProxyAsync();
 		fenceBeforeSync();
 		__syncthreads();
 		if (tid == 0) {
 			fenceAfterSync();
-			issue(tmemBase + colSmall, dD_MN_h, dD_MN_l, dS_MN_h, dS_MN_l, H*2, 16, kTile/8, idSmall, acc);
+			issue(tmemBase + colSmall, dD_MN_h, dD_MN_l, dS_K_h, dS_K_l, kMnStep, kSmallStep, kTile/8, idSmall, acc);
 			mmaCommit(barAddr);
 		}
 		mbarWait(barAddr, phase); // D and the small operand are rewritten by the next tile
@@ -275,19 +290,6 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	}
 
 	// ---- gradient tiles -> gradient buffer.  M = 64 accumulators: row i in TMEM lane (i % 16) + 32 (i / 16) -------------------
-#ifdef NMC_FUSED_DEBUG
-	if (tilesDone > 0 && blockIdx.x == 0 && warp < 4) { // raw dump: TMEM lane (warp*32 + lane), 32 columns of hidden layer 1's region and 16 of the chain's
-		uint32_t v[16];
-		for (int c0 = 0; c0 < 32; c0 += 16) {
-			tmemLoad16(tmemBase + ((uint32_t)(warp*32) << 16) + 64u + (uint32_t)c0, v);
-			for (int q = 0; q < 16; q++) P.gW[1][(warp*32 + lane)*32 + c0 + q] = __uint_as_float(v[q]);
-		}
-	}
-	fenceBeforeSync();
-	__syncthreads();
-	if (warp == 0) tmemFree(tmemBase, 512u);
-	return;
-#endif
 	if (tilesDone > 0) {
 		const int sp = warp & 3, ch = warp >> 2;
 		const int i = sp*16 + (lane & 15);
@@ -361,7 +363,7 @@ extern "C" int nmc_siren_backward_fused_tc(const nmc_siren_shape* sh, const floa
 	}
 	Env env;
 	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
-	const size_t smem = (size_t)(2*kTile*H + 2*kTile*KA + 2*H*H + 2*kTile*8)*4 + (size_t)sh->out_dim*H*4;
+	const size_t smem = (size_t)(6*kTile*H + 2*H*H)*4 + 256 + (size_t)3*H*4 + 16;
 	const long long tiles = (n + kTile - 1)/kTile;
 	const int grid = (int)(tiles < smCount() ? tiles : smCount());
 	cudaError_t e = cudaFuncSetAttribute(sirenBackwardFusedTc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

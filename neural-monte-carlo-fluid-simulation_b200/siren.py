@@ -493,7 +493,9 @@ class DirectFit:
         # selects the fp32 kernels for A/B measurements
         self.tc_backward = self.tensor_cores and os.environ.get("NMC_SIREN_TC_BWD", "1") != "0"
         self.tc_backward_min = int(os.environ.get("NMC_SIREN_TC_BWD_MIN", "4096"))
-        self.fused_backward = os.environ.get("NMC_SIREN_FUSED_BWD", "0") != "0"  # hidden = 64: the one-kernel backward (experimental)
+        self.fused_backward = os.environ.get("NMC_SIREN_FUSED_BWD", "1") != "0"  # hidden = 64: the one-kernel backward (NMC_SIREN_FUSED_BWD=0: two kernels)
+        # one tile chain per CTA: pays once the batch fills the GPU (>= 128 tiles); below, the weight-gradient kernel's layer-parallel grid wins
+        self.fused_backward_min = int(os.environ.get("NMC_SIREN_FUSED_BWD_MIN", "16384"))
         self.tc_forward_min = int(os.environ.get("NMC_SIREN_TC_FWD_MIN", "16384"))
         self.dz = torch.empty(((Lh + 1)*H + self.sh.out_dim)*max_batch, device=g.device) if self.tc_backward else None
         self.max_batch = max_batch
@@ -535,7 +537,7 @@ class DirectFit:
             gW0, gb0, gWh, gbh, gWl, gbl = self.out
             gW = [gW0] + [gWh[i] for i in range(sh.n_hidden_layers)] + [gWl]
             gb = [gb0] + [gbh[i] for i in range(sh.n_hidden_layers)] + [gbl]
-        if self.tc_backward and self.fused_backward and n >= self.tc_backward_min and sh.hidden == 64 and 1 <= sh.n_hidden_layers <= 6:
+        if self.tc_backward and self.fused_backward and n >= self.fused_backward_min and sh.hidden == 64 and 1 <= sh.n_hidden_layers <= 6:
             # one kernel: delta chain and all gradients, deltas / activations in shared memory (csrc/siren_tc_fused_bwd.cu)
             with torch.cuda.device(x.device):
                 _check(_lib().nmc_siren_backward_fused_tc(C.byref(sh), _ptrs(self.W), x.data_ptr(), n, z.data_ptr(), gy.data_ptr(),
