@@ -6,7 +6,6 @@
 //   dA_{l-1} = dZ_l W_l            A operand: dZ_l [sample x neuron], K-major (K = neurons), no swizzle            M 128, N 64
 //   dW_l    += dZ_l^T A_{l-1}      A operand: dZ_l read MN-major (M = neurons, K = samples);                       M 64, N 64
 //                                  B operand: A_{l-1} read MN-major
-//   db_l    += dZ_l^T 1            the same A operand against a constant tile of ones (N = 8; column 0 is the sum)
 // tcgen05.mma.kind::tf32 reads an MN-major operand ONLY in the 128-byte-swizzle / 32-byte-base layout (descriptor layout type
 // 1, cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B): with no swizzle or the 32 / 64 / 128-byte swizzles the instruction runs
 // and multiplies zeros (profiles/tools/umma_mn_probe.cu reads the addresses back through one-hot operands).  That layout is
@@ -16,8 +15,12 @@
 // deltas are written twice: K-major for the chain, MN-major for the gradients; the activations only MN-major.
 // First layer: dW_0 | db_0 = dZ_0^T [x 1] (N = 8); last layer: dW_last^T = A_L^T gy' (N = 8): the small operand [8 x 128] is
 // K-major (K = samples).  All products are 3xTF32 (hi.hi + hi.lo + lo.hi).  The gradient tiles accumulate in TMEM across the
-// CTA's tiles (512 columns: 64 for the chain, 64 + 8 per hidden layer, 16 for the small layers: up to 6 hidden layers) and are
-// added to the gradient buffer once, with 16-byte vector reductions.
+// CTA's tiles (512 columns: 64 for the chain, 72 per hidden layer, 16 for the small layers: up to 6 hidden layers) and are
+// added to the gradient buffer once, with 16-byte vector reductions.  The bias gradients (column sums of the deltas) are
+// reduced with warp shuffles in the epilogues and shared-memory atomics.
+// Per layer the chain batch and the gradient batch are committed to two mbarriers: the epilogue (TMEM load, cosine factor,
+// K-major store of the next delta, sine / cosine of the next layer's pre-activations) only waits for the chain and overlaps
+// the gradient MMAs; the MN-major stores wait for the gradient batch that still reads those buffers.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
@@ -32,7 +35,7 @@ using namespace nmc_siren_tc;
 using nmc_siren_detail::Env;
 
 constexpr int H = 64;
-constexpr int kTile = 128, kThreads = 256, kMaxLayers = 18, kMaxHidden = 6;
+constexpr int kTile = 128, kWorkers = 256, kThreads = kWorkers + 128, kMaxLayers = 18, kMaxHidden = 6;   // warps 0..7: operands and epilogues; warps 8..11: MMA issue (one thread)
 constexpr int HC = H/2;          // columns per thread (two threads per sample row) = one MN group of 32 neurons
 constexpr int kMnGroup = kTile*128;   // bytes of one [128 samples x 32 neurons] block of an MN-major buffer
 constexpr uint32_t kTransA = 1u << 15, kTransB = 1u << 16;   // instruction descriptor: operand is MN-major
@@ -46,17 +49,27 @@ __device__ __forceinline__ int mnChunkOffset(int group, int r, int j) {
 // small K-major operand [8 x 128 samples]: element (n, sample r)
 __device__ __forceinline__ int smallOffset(int n, int r) { return (r >> 2)*128 + n*16 + (r & 3)*4; }
 
+// -DNMC_TC_TRACE: CTA 0, threads 256 (the MMA issuer) and 64 stamp clock64() at the phase boundaries of the first tile
+// (profiles/tools/fused_bwd_trace.py)
+#ifdef NMC_TC_TRACE
+__device__ long long g_ftrace[2][256];
+__device__ int g_ftraceN[2];
+#define FTRACE(tag) do { if (blockIdx.x == 0 && (tid == 256 || tid == 64) && tilesDone == 0 && tn < 127) { const int sl = tid == 256 ? 0 : 1; g_ftrace[sl][2*tn] = (tag); g_ftrace[sl][2*tn + 1] = clock64(); tn++; g_ftraceN[sl] = tn; } } while (0)
+#else
+#define FTRACE(tag) do {} while (0)
+#endif
+
+// warp specialisation: the issuing warpgroup hands its registers to the two working warpgroups (168 per thread at launch for 384
+// threads; 256 x 240 + 128 x 24 = 64512 afterwards).  The roles meet at a named barrier (every thread of the CTA arrives).
+__device__ __forceinline__ void regsInc240() { asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory"); }
+__device__ __forceinline__ void regsDec24() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory"); }
+__device__ __forceinline__ void ctaBarrier() { asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory"); }
+
 struct Params {
 	const float* W[kMaxLayers];
 	float* gW[kMaxLayers];
 	float* gb[kMaxLayers];
 };
-
-__device__ __forceinline__ void tmemLoad8(uint32_t taddr, uint32_t (&v)[8]) {
-	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-				 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
@@ -74,33 +87,37 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	// and read while no chain batch is in flight (before the first storeW of a tile / after the last chain batch)
 	unsigned char* Shi = Bhi;
 	unsigned char* Slo = Blo;
-	unsigned char* ones = Blo + H*H*4;                // [8 x 8] K-major tile of ones (bias gradients)
-	float* sWL = reinterpret_cast<float*>(ones + 256);   // last layer's weights [outDim][H]
-	unsigned long long& mbar = *reinterpret_cast<unsigned long long*>(ones + 256 + 3*H*4);   // after sWL (room for three output rows)
-	uint32_t& tmemBaseSh = *reinterpret_cast<uint32_t*>(ones + 256 + 3*H*4 + 8);
+	float* sWL = reinterpret_cast<float*>(Blo + H*H*4);             // last layer's weights [3][H]
+	float* sBias = sWL + 3*H;                                       // bias-gradient sums [nHidden + 1][H]
+	unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBias + (kMaxHidden + 1)*H);   // [0] gradient batches, [1] chain batches
+	uint32_t& tmemBaseSh = *reinterpret_cast<uint32_t*>(mbar + 2);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & (kTile - 1), half = tid >> 7;
 	const int cBeg = half*HC;
 	const int last = nHidden + 1;
+	const bool worker = tid < kWorkers;        // thread 256 only issues the MMAs: issuing the 72 MMAs of a layer takes ~5000 cycles, which a
+	const bool issuer = tid == kWorkers;       // working warp would add to its own epilogue (and to everybody's barrier wait)
 
 	if (warp == 0) tmemAlloc(&tmemBaseSh, 512u);
-	if (tid == 0) mbarInit(smemAddr(&mbar), 1);
+	if (tid == 0) { mbarInit(smemAddr(&mbar[0]), 1); mbarInit(smemAddr(&mbar[1]), 1); }
+	for (int i = tid; i < (kMaxHidden + 1)*H; i += kThreads) sBias[i] = 0.0f;
 	for (int i = tid; i < outDim*H; i += kThreads) sWL[i] = __ldg(&P.W[last][i]);
 	fenceBeforeSync();
 	__syncthreads();
 	fenceAfterSync();
 	const uint32_t tmemBase = tmemBaseSh;
-	const uint32_t barAddr = smemAddr(&mbar);
+	const uint32_t barG = smemAddr(&mbar[0]), barC = smemAddr(&mbar[1]);
 	// TMEM columns: [0, 64) chain accumulator; hidden layer l: [64 + 72 (l - 1), + 72); small layers: 16 columns at the end
 	const uint32_t colSmall = 64u + 72u*(uint32_t)nHidden;   // +0: dW_0 | db_0 (8 columns), +8: dW_last^T (8 columns)
 	const uint32_t idChain = instrDescTf32(kTile, H), idGrad = instrDescTf32(H, H) | kTransA | kTransB, idSmall = instrDescTf32(H, 8) | kTransA;
-	uint32_t phase = 0;
+	uint32_t phaseG = 0, phaseC = 0;
+	bool liveRow = false;
 
-	constexpr int RW = H*H/4/kThreads; // 4
+	constexpr int RW = H*H/4/kWorkers; // 4
 	float4 wreg[RW];
 	auto loadW = [&](int l) { // B(n = input neuron, k = output neuron) = W_l[k][n]: four consecutive k of one n per 16-byte word
 #pragma unroll
 		for (int i = 0; i < RW; i++) {
-			const int idx = tid + i*kThreads, k4 = idx/H, r = idx - k4*H;
+			const int idx = tid + i*kWorkers, k4 = idx/H, r = idx - k4*H;
 			const float* w = &P.W[l][(size_t)(4*k4)*H + r];
 			wreg[i] = make_float4(__ldg(w), __ldg(w + H), __ldg(w + 2*H), __ldg(w + 3*H));
 		}
@@ -108,7 +125,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	auto storeW = [&]() {
 #pragma unroll
 		for (int i = 0; i < RW; i++) {
-			const int idx = tid + i*kThreads, k4 = idx/H, r = idx - k4*H;
+			const int idx = tid + i*kWorkers, k4 = idx/H, r = idx - k4*H;
 			float4 h, o;
 			splitTf32(wreg[i], h, o);
 			const int off = coreOffsetBytes<H>(r, 4*k4);
@@ -131,144 +148,216 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	const uint64_t dD_MN_h = smemDesc(smemAddr(Mhi), kMnGroup, 512) | kLayoutMn, dD_MN_l = smemDesc(smemAddr(Mlo), kMnGroup, 512) | kLayoutMn;   // gradient A
 	const uint64_t dA_MN_h = smemDesc(smemAddr(Ahi), kMnGroup, 512) | kLayoutMn, dA_MN_l = smemDesc(smemAddr(Alo), kMnGroup, 512) | kLayoutMn;   // gradient B / last-layer A
 	const uint64_t dS_K_h = smemDesc(smemAddr(Shi), 128, 256), dS_K_l = smemDesc(smemAddr(Slo), 128, 256);            // small B [8 x 128], K-major
-	const uint64_t dOnes = smemDesc(smemAddr(ones), 128, 256);
 	constexpr uint32_t kMnStep = 1024/16, kSmallStep = 256/16;   // one K step = 8 samples
 
-	if (tid < 64) reinterpret_cast<float*>(ones)[tid] = 1.0f;
-	if ((long long)blockIdx.x*kTile < n) loadW(nHidden);
+	if (worker && (long long)blockIdx.x*kTile < n) loadW(nHidden);
 
-	int tilesDone = 0;
-	float bl0 = 0.0f, bl1 = 0.0f, bl2 = 0.0f; // last layer's bias gradient: sum of gy' over this thread's samples (half 0 only)
-	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x, tilesDone++) {
-		const bool acc = tilesDone > 0;
-		const long long s = tile*kTile + row;
-		const bool live = s < n;
-		const long long sc = live ? s : n - 1;   // rows past the end read the last sample; their deltas are zeroed
-		const float* zrow = zSaved + sc + (size_t)cBeg*n;
-		float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
-		if (live) {
-			g0 = gy[s*outDim]; if (outDim > 1) g1 = gy[s*outDim + 1]; if (outDim > 2) g2 = gy[s*outDim + 2];
-			x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2];
-			if (env.active) { // dL/d(network output) = dL/d(enveloped output) x (detached) envelope weights
-				const float xs[3] = {x0, x1, x2};
-				float gys[3] = {g0, g1, g2};
-				nmc_siren_detail::envBackward(env, inDim, outDim, xs, nullptr, gys, nullptr);
-				g0 = gys[0]; g1 = gys[1]; g2 = gys[2];
-			}
-		}
-		if (half == 0) { // small operand: gy' padded to eight columns
-			bl0 += g0; bl1 += g1; bl2 += g2;
-			const float gs[8] = {g0, g1, g2, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-			for (int q = 0; q < 8; q++) {
-				float h, o;
-				splitTf32(gs[q], h, o);
-				*reinterpret_cast<float*>(Shi + smallOffset(q, row)) = h; *reinterpret_cast<float*>(Slo + smallOffset(q, row)) = o;
-			}
-		}
-		float zreg[HC];
-		{
-			const float* zp = zrow + (size_t)nHidden*H*n;
-#pragma unroll
-			for (int q = 0; q < HC; q++) { zreg[q] = __ldg(zp); zp += n; }
-		}
-		// layer L: A_L = sin(w0 z_L) (for dW_last) and dZ_L = (W_last^T gy') w0 cos(w0 z_L)
+	// this thread's 32 values of a row (sample `row`, neurons cBeg .. cBeg + 31) -> the operand buffers, split into TF32 hi / lo
+	auto storeKMajor = [&](const float (&val)[HC]) {
 #pragma unroll
 		for (int q4 = 0; q4 < HC; q4 += 4) {
-			float d[4], a[4];
+			float4 h, o;
+			splitTf32(make_float4(val[q4], val[q4 + 1], val[q4 + 2], val[q4 + 3]), h, o);
+			const int off = coreOffsetBytes<H>(row, cBeg + q4);
+			*reinterpret_cast<float4*>(Dhi + off) = h; *reinterpret_cast<float4*>(Dlo + off) = o;
+		}
+	};
+	// MN-major rows are 128 bytes per sample with the 32-byte chunks rotated by r % 4: lanes r and r + 4 of a quarter warp would
+	// hit the same 16 bytes' banks, so lanes with bit 2 set write the two halves of a chunk in the opposite order
+	const bool swapHalves = (row & 4) != 0;
+	auto storeMnMajor = [&](unsigned char* hi, unsigned char* lo, const float (&val)[HC]) {
 #pragma unroll
-			for (int q = 0; q < 4; q++) {
-				const int c = cBeg + q4 + q;
+		for (int q8 = 0; q8 < HC; q8 += 8) {
+			float4 h0, o0, h1, o1;
+			splitTf32(make_float4(val[q8], val[q8 + 1], val[q8 + 2], val[q8 + 3]), h0, o0);
+			splitTf32(make_float4(val[q8 + 4], val[q8 + 5], val[q8 + 6], val[q8 + 7]), h1, o1);
+			const int off = mnChunkOffset(half, row, q8 >> 3);
+			const int offA = off + (swapHalves ? 16 : 0), offB = off + (swapHalves ? 0 : 16);
+			*reinterpret_cast<float4*>(hi + offA) = swapHalves ? h1 : h0; *reinterpret_cast<float4*>(lo + offA) = swapHalves ? o1 : o0;
+			*reinterpret_cast<float4*>(hi + offB) = swapHalves ? h0 : h1; *reinterpret_cast<float4*>(lo + offB) = swapHalves ? o0 : o1;
+		}
+	};
+	auto loadZ = [&](float (&z)[HC], const float* zrow, int layer) {
+		const float* zp = zrow + (size_t)layer*H*n;
+#pragma unroll
+		for (int q = 0; q < HC; q++) { z[q] = __ldg(zp); zp += n; }
+	};
+	// bias gradients db_l = sum over samples of dZ_l: transposed butterfly over the warp's 32 rows (lane j ends with the sum of
+	// column cBeg + j), then one shared-memory atomic per lane; the sums leave with the gradient tiles
+	auto biasSum = [&](const float (&val)[HC], int layer) {
+		float t[HC];
+#pragma unroll
+		for (int q = 0; q < HC; q++) t[q] = val[q];
+#pragma unroll
+		for (int off = 16; off >= 1; off >>= 1) {
+			const bool upper = (lane & off) != 0;
+#pragma unroll
+			for (int q = 0; q < off; q++) {
+				const float send = upper ? t[q] : t[q + off];
+				const float keep = upper ? t[q + off] : t[q];
+				t[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+			}
+		}
+		atomicAdd(&sBias[layer*H + cBeg + lane], t[0]);
+	};
+	auto activations = [&](const float (&z)[HC], float (&av)[HC], float (&cv)[HC]) {
+#pragma unroll
+		for (int q = 0; q < HC; q++) {
+			const float t = 6.283185307179586f*turnsReduced(w0*z[q]);
+			av[q] = liveRow ? __sinf(t) : 0.0f;
+			cv[q] = liveRow ? w0*__cosf(t) : 0.0f;
+		}
+	};
+
+	int tilesDone = 0;
+#ifdef NMC_TC_TRACE
+	int tn = 0;
+#endif
+	float bl0 = 0.0f, bl1 = 0.0f, bl2 = 0.0f; // last layer's bias gradient: sum of gy' over this thread's samples (half 0 only)
+	if (!worker) {
+		// ---- issuing warpgroup: the same barrier sequence as the workers, one thread issues after each -------------------------
+		regsDec24();
+		for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x, tilesDone++) {
+			const bool acc = tilesDone > 0;
+			FTRACE(1);
+			ctaBarrier();
+			if (issuer) { // dW_last^T [64 x 8] += A_L^T gy'
+				fenceAfterSync();
+				issue(tmemBase + colSmall + 8u, dA_MN_h, dA_MN_l, dS_K_h, dS_K_l, kMnStep, kSmallStep, kTile/8, idSmall, acc);
+				mmaCommit(barG);
+			}
+			FTRACE(4);
+			for (int l = nHidden; l >= 1; l--) {
+				ctaBarrier();
+				FTRACE(13);
+				if (issuer) {
+					fenceAfterSync();
+					issue(tmemBase, dD_K_h, dD_K_l, dB_K_h, dB_K_l, 16, 16, H/8, idChain, false);                                   // dA_{l-1}
+					mmaCommit(barC);
+					issue(tmemBase + 64u + 72u*(uint32_t)(l - 1), dD_MN_h, dD_MN_l, dA_MN_h, dA_MN_l, kMnStep, kMnStep, kTile/8, idGrad, acc);   // dW_l
+					mmaCommit(barG);
+				}
+				FTRACE(14);
+			}
+			ctaBarrier();
+			if (issuer) { // dW_0 += dZ_0^T x
+				fenceAfterSync();
+				issue(tmemBase + colSmall, dD_MN_h, dD_MN_l, dS_K_h, dS_K_l, kMnStep, kSmallStep, kTile/8, idSmall, acc);
+				mmaCommit(barG);
+			}
+			FTRACE(21);
+		}
+	} else {
+	regsInc240();
+	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x, tilesDone++) {
+		const long long s = tile*kTile + row;
+		const bool live = s < n;
+		liveRow = live;
+		FTRACE(1);
+		const long long sc = live ? s : n - 1;   // rows past the end read the last sample; their deltas are zeroed
+		const float* zrow = zSaved + sc + (size_t)cBeg*n;
+		float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+		float zreg[HC];
+		float d[HC];    // dZ of the layer the loop is about to process (this thread's half row)
+		float a[HC];    // A_{l-1} = sin(w0 z_{l-1})
+		float cs[HC];   // w0 cos(w0 z_{l-1})
+		{
+			float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+			loadZ(zreg, zrow, nHidden);
+			if (live) {
+				g0 = gy[s*outDim]; if (outDim > 1) g1 = gy[s*outDim + 1]; if (outDim > 2) g2 = gy[s*outDim + 2];
+				x0 = x[s*inDim]; if (inDim > 1) x1 = x[s*inDim + 1]; if (inDim > 2) x2 = x[s*inDim + 2];
+				if (env.active) { // dL/d(network output) = dL/d(enveloped output) x (detached) envelope weights
+					const float xs[3] = {x0, x1, x2};
+					float gys[3] = {g0, g1, g2};
+					nmc_siren_detail::envBackward(env, inDim, outDim, xs, nullptr, gys, nullptr);
+					g0 = gys[0]; g1 = gys[1]; g2 = gys[2];
+				}
+			}
+			if (half == 0) { // small operand: gy' padded to eight rows
+				bl0 += g0; bl1 += g1; bl2 += g2;
+				const float gs[8] = {g0, g1, g2, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					float h, o;
+					splitTf32(gs[q], h, o);
+					*reinterpret_cast<float*>(Shi + smallOffset(q, row)) = h; *reinterpret_cast<float*>(Slo + smallOffset(q, row)) = o;
+				}
+			}
+			// layer L: A_L = sin(w0 z_L) (for dW_last) and dZ_L = (W_last^T gy') w0 cos(w0 z_L)
+#pragma unroll
+			for (int q = 0; q < HC; q++) {
+				const int c = cBeg + q;
 				float v = sWL[c]*g0;
 				if (outDim > 1) v += sWL[H + c]*g1;
 				if (outDim > 2) v += sWL[2*H + c]*g2;
-				const float t = 6.283185307179586f*turnsReduced(w0*zreg[q4 + q]);
+				const float t = 6.283185307179586f*turnsReduced(w0*zreg[q]);
 				a[q] = live ? __sinf(t) : 0.0f;
-				d[q] = v*w0*__cosf(t);
+				d[q] = live ? v*w0*__cosf(t) : 0.0f;
 			}
-			float4 h, o;
-			splitTf32(make_float4(live ? d[0] : 0.0f, live ? d[1] : 0.0f, live ? d[2] : 0.0f, live ? d[3] : 0.0f), h, o);
-			int off = coreOffsetBytes<H>(row, cBeg + q4);
-			*reinterpret_cast<float4*>(Dhi + off) = h; *reinterpret_cast<float4*>(Dlo + off) = o;
-			off = mnChunkOffset(half, row, q4 >> 3) + (q4 & 4)*4;
-			*reinterpret_cast<float4*>(Mhi + off) = h; *reinterpret_cast<float4*>(Mlo + off) = o;
-			splitTf32(make_float4(a[0], a[1], a[2], a[3]), h, o);
-			*reinterpret_cast<float4*>(Ahi + off) = h; *reinterpret_cast<float4*>(Alo + off) = o;
 		}
+		FTRACE(2);
+		storeKMajor(d);
+		storeMnMajor(Mhi, Mlo, d);
+		storeMnMajor(Ahi, Alo, a);
+		biasSum(d, nHidden);
+		FTRACE(3);
 		fenceProxyAsync();
 		fenceBeforeSync();
-		__syncthreads();
-		if (tid == 0) { // dW_last^T [64 x 8] += A_L^T gy'
-			fenceAfterSync();
-			issue(tmemBase + colSmall + 8u, dA_MN_h, dA_MN_l, dS_K_h, dS_K_l, kMnStep, kSmallStep, kTile/8, idSmall, acc);
-			mmaCommit(barAddr);
-		}
+		ctaBarrier();               // -> the last layer's batch
+		FTRACE(4);
+		loadZ(zreg, zrow, nHidden - 1);
+		activations(zreg, a, cs);
 		for (int l = nHidden; l >= 1; l--) {
-			// pre-activations of layer l - 1 (in flight during the wait below)
-			{
-				const float* zp = zrow + (size_t)(l - 1)*H*n;
-#pragma unroll
-				for (int q = 0; q < HC; q++) { zreg[q] = __ldg(zp); zp += n; }
-			}
-			if (l == nHidden) { // the last-layer batch has finished reading the activation and small operands
-				mbarWait(barAddr, phase);
-				phase ^= 1u;
-				fenceAfterSync();
-			}
+			// here: Dk holds dZ_l; d[] = dZ_l (not yet in Dm when l < nHidden); a[], cs[] belong to layer l - 1; a gradient batch
+			// reading Am, Dm (and, for l = nHidden, the small operand in the weight buffer) may still be in flight
+			FTRACE(10);
+			mbarWait(barG, phaseG);
+			phaseG ^= 1u;
+			fenceAfterSync();
+			FTRACE(11);
+			if (l < nHidden) storeMnMajor(Mhi, Mlo, d);
 			storeW();
-			float cs[HC];
-#pragma unroll
-			for (int q4 = 0; q4 < HC; q4 += 4) { // A_{l-1} = sin(w0 z_{l-1}) -> operand; cos kept for the epilogue
-				float a[4];
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const float t = 6.283185307179586f*turnsReduced(w0*zreg[q4 + q]);
-					a[q] = live ? __sinf(t) : 0.0f;
-					cs[q4 + q] = live ? w0*__cosf(t) : 0.0f;
-				}
-				float4 h, o;
-				splitTf32(make_float4(a[0], a[1], a[2], a[3]), h, o);
-				const int off = mnChunkOffset(half, row, q4 >> 3) + (q4 & 4)*4;
-				*reinterpret_cast<float4*>(Ahi + off) = h; *reinterpret_cast<float4*>(Alo + off) = o;
-			}
+			storeMnMajor(Ahi, Alo, a);
 			fenceProxyAsync();
 			fenceBeforeSync();
-			__syncthreads();
-			if (l > 1) loadW(l - 1);
-			else if ((tile + gridDim.x)*kTile < n) loadW(nHidden);
-			if (tid == 0) {
-				fenceAfterSync();
-				issue(tmemBase, dD_K_h, dD_K_l, dB_K_h, dB_K_l, 16, 16, H/8, idChain, false);                                   // dA_{l-1}
-				const uint32_t colL = tmemBase + 64u + 72u*(uint32_t)(l - 1);
-				issue(colL, dD_MN_h, dD_MN_l, dA_MN_h, dA_MN_l, kMnStep, kMnStep, kTile/8, idGrad, acc);                        // dW_l
-#pragma unroll 1
-				for (int ks = 0; ks < kTile/8; ks++) {                                                                           // db_l
-					mmaTf32(colL + 64u, dD_MN_h + (uint64_t)(kMnStep*ks), dOnes, idSmall, (acc || ks > 0) ? 1u : 0u);
-					mmaTf32(colL + 64u, dD_MN_l + (uint64_t)(kMnStep*ks), dOnes, idSmall, 1u);
-				}
-				mmaCommit(barAddr);
-			}
-			mbarWait(barAddr, phase);
-			phase ^= 1u;
+			FTRACE(12);
+			ctaBarrier();           // -> chain batch (barC), gradient batch (barG)
+			FTRACE(13);
+			float csn[HC];
+			if (l > 1) { // the next layer's activations while the chain batch runs (a[] is in the operand buffer by now)
+				loadW(l - 1);
+				loadZ(zreg, zrow, l - 2);
+				activations(zreg, a, csn);
+			} else if ((tile + gridDim.x)*kTile < n) loadW(nHidden);
+			FTRACE(14);
+			mbarWait(barC, phaseC);
+			phaseC ^= 1u;
 			fenceAfterSync();
-			// epilogue: dZ_{l-1} = dA_{l-1} w0 cos(w0 z_{l-1}) -> the D operand of the next layer (and of dW_{l-1})
-			uint32_t v[HC];
+			FTRACE(15);
+			// epilogue: dZ_{l-1} = dA_{l-1} w0 cos(w0 z_{l-1}); the chain batch has finished reading Dk, the gradient batch still reads Dm
+			{
+				uint32_t v[HC];
 #pragma unroll
-			for (int c0 = 0; c0 < HC; c0 += 16) tmemLoad16Async(tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0), &v[c0]);
-			tmemLoadWait();
+				for (int c0 = 0; c0 < HC; c0 += 16) tmemLoad16Async(tmemBase + ((uint32_t)((warp & 3)*32) << 16) + (uint32_t)(cBeg + c0), &v[c0]);
+				tmemLoadWait();
 #pragma unroll
-			for (int c0 = 0; c0 < HC; c0 += 4) {
-				float4 h, o;
-				splitTf32(make_float4(__uint_as_float(v[c0])*cs[c0], __uint_as_float(v[c0 + 1])*cs[c0 + 1], __uint_as_float(v[c0 + 2])*cs[c0 + 2], __uint_as_float(v[c0 + 3])*cs[c0 + 3]), h, o);
-				int off = coreOffsetBytes<H>(row, cBeg + c0);
-				*reinterpret_cast<float4*>(Dhi + off) = h; *reinterpret_cast<float4*>(Dlo + off) = o;
-				off = mnChunkOffset(half, row, c0 >> 3) + (c0 & 4)*4;
-				*reinterpret_cast<float4*>(Mhi + off) = h; *reinterpret_cast<float4*>(Mlo + off) = o;
+				for (int q = 0; q < HC; q++) { d[q] = __uint_as_float(v[q])*cs[q]; cs[q] = csn[q]; }
 			}
+			FTRACE(16);
+			if (l > 1) storeKMajor(d);
+			FTRACE(17);
+			biasSum(d, l - 1);
+			FTRACE(18);
 		}
-		// first layer: dW_0 | db_0 = dZ_0^T [x 1]
+		FTRACE(20);
+		// first layer: dW_0 = dZ_0^T x
+		mbarWait(barG, phaseG);
+		phaseG ^= 1u;
+		fenceAfterSync();
+		storeMnMajor(Mhi, Mlo, d);
 		if (half == 0) {
-			const float xs4[4] = {x0, x1, x2, 1.0f};   // rows 4..7 of the operand stay zero
+			const float xs4[4] = {x0, x1, x2, 0.0f};   // rows 3..7 of the operand stay zero
 #pragma unroll
 			for (int q = 0; q < 8; q++) {
 				float h = 0.0f, o = 0.0f;
@@ -278,27 +367,28 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 		}
 		fenceProxyAsync();
 		fenceBeforeSync();
-		__syncthreads();
-		if (tid == 0) {
-			fenceAfterSync();
-			issue(tmemBase + colSmall, dD_MN_h, dD_MN_l, dS_K_h, dS_K_l, kMnStep, kSmallStep, kTile/8, idSmall, acc);
-			mmaCommit(barAddr);
-		}
-		mbarWait(barAddr, phase); // D and the small operand are rewritten by the next tile
-		phase ^= 1u;
+		ctaBarrier();               // -> the first layer's batch
+		mbarWait(barG, phaseG);     // Dm, Am and the small operand are rewritten by the next tile
+		phaseG ^= 1u;
 		fenceAfterSync();
+		FTRACE(21);
+	}
 	}
 
 	// ---- gradient tiles -> gradient buffer.  M = 64 accumulators: row i in TMEM lane (i % 16) + 32 (i / 16) -------------------
-	if (tilesDone > 0) {
+	if (tilesDone > 0 && worker) {
 		const int sp = warp & 3, ch = warp >> 2;
 		const int i = sp*16 + (lane & 15);
 		const bool valid = lane < 16;
 		const uint32_t laneBase = tmemBase + ((uint32_t)(sp*32) << 16);
-		for (int l = 1; l <= nHidden; l++) {
+		// every CTA adds to the same 20 k addresses: the order is rotated by the CTA index, or the reductions of all CTAs queue
+		// up at the same L2 slices at the same time (25 k cycles for 5 layers against 14 k rotated)
+		for (int li = 0; li < nHidden; li++) {
+			const int l = 1 + (li + (int)blockIdx.x) % nHidden;
 			const uint32_t col = 64u + 72u*(uint32_t)(l - 1);
 			float* gw = P.gW[l] + (size_t)i*H;
-			for (int c0 = ch*32; c0 < ch*32 + 32; c0 += 16) {
+			for (int cc = 0; cc < 2; cc++) {
+				const int c0 = ch*32 + 16*((cc + (int)blockIdx.x/nHidden) & 1);
 				uint32_t v[16];
 				tmemLoad16(laneBase + col + (uint32_t)c0, v);
 				if (valid) {
@@ -306,11 +396,6 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 					for (int q = 0; q < 16; q += 4)
 						redAdd4(gw + c0 + q, __uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
 				}
-			}
-			if (ch == 1) { // column 64: the bias gradient
-				uint32_t v[8];
-				tmemLoad8(laneBase + col + 64u, v);
-				if (valid) atomicAdd(&P.gb[l][i], __uint_as_float(v[0]));
 			}
 		}
 		if (ch == 0) {
@@ -322,6 +407,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 				for (int j = 0; j < outDim; j++) atomicAdd(&P.gW[last][j*H + i], __uint_as_float(v[8 + j]));
 			}
 		}
+		for (int o = tid; o < (nHidden + 1)*H; o += kWorkers) atomicAdd(&P.gb[o/H][o % H], sBias[o]);   // complete: every biasSum precedes the tile's last __syncthreads
 		if (half == 0) { // last layer's bias gradient
 			for (int off = 16; off > 0; off >>= 1) {
 				bl0 += __shfl_xor_sync(0xffffffffu, bl0, off); bl1 += __shfl_xor_sync(0xffffffffu, bl1, off); bl2 += __shfl_xor_sync(0xffffffffu, bl2, off);
@@ -335,6 +421,10 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	}
 	fenceBeforeSync();
 	__syncthreads();
+#ifdef NMC_TC_TRACE
+	tilesDone = 0;
+	FTRACE(22);
+#endif
 	if (warp == 0) tmemFree(tmemBase, 512u);
 }
 
@@ -346,6 +436,17 @@ int smCount() {
 int fail(const char* m) { nmc_siren_detail::setError(m); return 1; }
 
 } // namespace
+
+#ifdef NMC_TC_TRACE
+extern "C" int nmc_siren_trace_read_fused(int slot, long long* out, int cap) { // (tag, clock) pairs of the last traced launch
+	int n = 0;
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(&n, g_ftraceN, sizeof(int), sizeof(int)*slot);
+	if (n > cap) n = cap;
+	cudaMemcpyFromSymbol(out, g_ftrace, sizeof(long long)*2*n, sizeof(long long)*256*slot);
+	return n;
+}
+#endif
 
 extern "C" int nmc_siren_backward_fused_tc(const nmc_siren_shape* sh, const float* const* W, const float* x, int64_t n,
 										   const float* z_saved, const float* grad_y, float* const* gW, float* const* gb,
@@ -363,7 +464,7 @@ extern "C" int nmc_siren_backward_fused_tc(const nmc_siren_shape* sh, const floa
 	}
 	Env env;
 	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
-	const size_t smem = (size_t)(6*kTile*H + 2*H*H)*4 + 256 + (size_t)3*H*4 + 16;
+	const size_t smem = (size_t)(6*kTile*H + 2*H*H)*4 + (size_t)(3 + kMaxHidden + 1)*H*4 + 32;
 	const long long tiles = (n + kTile - 1)/kTile;
 	const int grid = (int)(tiles < smCount() ? tiles : smCount());
 	cudaError_t e = cudaFuncSetAttribute(sirenBackwardFusedTc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
