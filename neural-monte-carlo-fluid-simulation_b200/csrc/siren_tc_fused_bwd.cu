@@ -23,6 +23,7 @@
 // the gradient MMAs; the MN-major stores wait for the gradient batch that still reads those buffers.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
 #include "siren_tc.cuh"
@@ -54,7 +55,7 @@ __device__ __forceinline__ int smallOffset(int n, int r) { return (r >> 2)*128 +
 #ifdef NMC_TC_TRACE
 __device__ long long g_ftrace[2][256];
 __device__ int g_ftraceN[2];
-#define FTRACE(tag) do { if (blockIdx.x == 0 && (tid == 256 || tid == 64) && tilesDone == 0 && tn < 127) { const int sl = tid == 256 ? 0 : 1; g_ftrace[sl][2*tn] = (tag); g_ftrace[sl][2*tn + 1] = clock64(); tn++; g_ftraceN[sl] = tn; } } while (0)
+#define FTRACE(tag) do { if (blockIdx.x == 0 && (tid == 256 || tid == 64) && (tilesDone == 0 || (tag) >= 22) && tn < 127) { const int sl = tid == 256 ? 0 : 1; g_ftrace[sl][2*tn] = (tag); g_ftrace[sl][2*tn + 1] = clock64(); tn++; g_ftraceN[sl] = tn; } } while (0)
 #else
 #define FTRACE(tag) do {} while (0)
 #endif
@@ -63,6 +64,19 @@ __device__ int g_ftraceN[2];
 // threads; 256 x 240 + 128 x 24 = 64512 afterwards).  The roles meet at a named barrier (every thread of the CTA arrives).
 __device__ __forceinline__ void regsInc240() { asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory"); }
 __device__ __forceinline__ void regsDec24() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory"); }
+// thread-block cluster: barrier over every thread of every CTA, and a 16-byte load from a peer CTA's shared memory
+__device__ __forceinline__ void clusterSync() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t clusterRank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ float4 loadPeer16(uint32_t localAddr, uint32_t rank) {
+	uint32_t remote;
+	float4 v;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(localAddr), "r"(rank));
+	asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+	return v;
+}
 __device__ __forceinline__ void ctaBarrier() { asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory"); }
 
 struct Params {
@@ -73,7 +87,7 @@ struct Params {
 
 __global__ void __launch_bounds__(kThreads, 1)
 sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
-					 const float* __restrict__ zSaved, const float* __restrict__ gy) {
+					 const float* __restrict__ zSaved, const float* __restrict__ gy, int cluster) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	unsigned char* Dhi = smem;                        // dZ_l [128 x 64], K-major (chain operand)
 	unsigned char* Dlo = Dhi + kTile*H*4;
@@ -89,7 +103,8 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 	unsigned char* Slo = Blo;
 	float* sWL = reinterpret_cast<float*>(Blo + H*H*4);             // last layer's weights [3][H]
 	float* sBias = sWL + 3*H;                                       // bias-gradient sums [nHidden + 1][H]
-	unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBias + (kMaxHidden + 1)*H);   // [0] gradient batches, [1] chain batches
+	float* sBl = sBias + (kMaxHidden + 1)*H;                        // last layer's bias gradient (cluster reduction), 16 bytes
+	unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sBl + 4);   // [0] gradient batches, [1] chain batches
 	uint32_t& tmemBaseSh = *reinterpret_cast<uint32_t*>(mbar + 2);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & (kTile - 1), half = tid >> 7;
 	const int cBeg = half*HC;
@@ -99,7 +114,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 
 	if (warp == 0) tmemAlloc(&tmemBaseSh, 512u);
 	if (tid == 0) { mbarInit(smemAddr(&mbar[0]), 1); mbarInit(smemAddr(&mbar[1]), 1); }
-	for (int i = tid; i < (kMaxHidden + 1)*H; i += kThreads) sBias[i] = 0.0f;
+	for (int i = tid; i < (kMaxHidden + 1)*H + 4; i += kThreads) sBias[i] = 0.0f;   // and sBl
 	for (int i = tid; i < outDim*H; i += kThreads) sWL[i] = __ldg(&P.W[last][i]);
 	fenceBeforeSync();
 	__syncthreads();
@@ -247,6 +262,7 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 			}
 			FTRACE(21);
 		}
+		if (cluster > 1) { clusterSync(); clusterSync(); }   // the working warpgroups' gradient reduction
 	} else {
 	regsInc240();
 	for (long long tile = blockIdx.x; tile*kTile < n; tile += gridDim.x, tilesDone++) {
@@ -373,16 +389,16 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 		fenceAfterSync();
 		FTRACE(21);
 	}
-	}
-
+	// the gradients leave from the working warpgroups' branch: after the roles merge the code is compiled for the issuing
+	// warpgroup's 24 registers (the read-out spilled everything and took 15-19 k cycles there)
 	// ---- gradient tiles -> gradient buffer.  M = 64 accumulators: row i in TMEM lane (i % 16) + 32 (i / 16) -------------------
-	if (tilesDone > 0 && worker) {
+	if (tilesDone > 0 && cluster <= 1) {
 		const int sp = warp & 3, ch = warp >> 2;
 		const int i = sp*16 + (lane & 15);
 		const bool valid = lane < 16;
 		const uint32_t laneBase = tmemBase + ((uint32_t)(sp*32) << 16);
 		// every CTA adds to the same 20 k addresses: the order is rotated by the CTA index, or the reductions of all CTAs queue
-		// up at the same L2 slices at the same time (25 k cycles for 5 layers against 14 k rotated)
+		// up at the same L2 slices at the same time (25 k cycles for 5 layers against 19 k rotated)
 		for (int li = 0; li < nHidden; li++) {
 			const int l = 1 + (li + (int)blockIdx.x) % nHidden;
 			const uint32_t col = 64u + 72u*(uint32_t)(l - 1);
@@ -403,7 +419,6 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 			tmemLoad16(laneBase + colSmall, v);
 			if (valid) {
 				for (int j = 0; j < inDim; j++) atomicAdd(&P.gW[0][i*inDim + j], __uint_as_float(v[j]));
-				atomicAdd(&P.gb[0][i], __uint_as_float(v[3]));
 				for (int j = 0; j < outDim; j++) atomicAdd(&P.gW[last][j*H + i], __uint_as_float(v[8 + j]));
 			}
 		}
@@ -419,12 +434,94 @@ sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, floa
 			}
 		}
 	}
+	FTRACE(23);
+	if (cluster > 1) {
+		// ---- every gradient reduced over the cluster first: a CTA leaves its tiles in its own shared memory (the operand buffers
+		// are idle), CTA r of the cluster sums slice r of all peers through distributed shared memory and issues the global
+		// reductions for that slice only: `cluster` times fewer L2 atomics on the same 21 k addresses (they were a quarter of
+		// the kernel, the 128-deep same-address queues of the small layers and biases half of that)
+		float4* stage4 = reinterpret_cast<float4*>(smem);   // [nHidden][64][16] hidden tiles, [64] dW_0 rows, [64] dW_last columns
+		const int T4 = nHidden*H*H/4, B4 = (nHidden + 1)*H/4;
+		{
+			const int sp = warp & 3, ch = warp >> 2;
+			const int i = sp*16 + (lane & 15);
+			const uint32_t laneBase = tmemBase + ((uint32_t)(sp*32) << 16);
+			for (int l = 1; l <= nHidden; l++) {
+				uint32_t v[32];
+#pragma unroll
+				for (int q = 0; q < 32; q++) v[q] = 0u;
+				if (tilesDone > 0) {
+					tmemLoad16Async(laneBase + 64u + 72u*(uint32_t)(l - 1) + (uint32_t)(ch*32), &v[0]);
+					tmemLoad16Async(laneBase + 64u + 72u*(uint32_t)(l - 1) + (uint32_t)(ch*32 + 16), &v[16]);
+					tmemLoadWait();
+				}
+				if (lane < 16) { // a row is 16 float4: slot (column chunk ^ row % 16), or the 16 lanes of a warp would write one bank group
+					float4* dst = stage4 + (size_t)(l - 1)*H*H/4 + i*(H/4);
+#pragma unroll
+					for (int q = 0; q < 32; q += 4) dst[(ch*8 + (q >> 2)) ^ (i & 15)] = make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+				}
+			}
+			if (ch == 0) {
+				uint32_t v[16];
+#pragma unroll
+				for (int q = 0; q < 16; q++) v[q] = 0u;
+				if (tilesDone > 0) tmemLoad16(laneBase + colSmall, v);
+				if (lane < 16) {
+					stage4[T4 + i] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), 0.0f);
+					stage4[T4 + H + i] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), 0.0f);
+				}
+			}
+			if (half == 0) { // last layer's bias gradient
+				for (int off = 16; off > 0; off >>= 1) {
+					bl0 += __shfl_xor_sync(0xffffffffu, bl0, off); bl1 += __shfl_xor_sync(0xffffffffu, bl1, off); bl2 += __shfl_xor_sync(0xffffffffu, bl2, off);
+				}
+				if (lane == 0) { atomicAdd(&sBl[0], bl0); atomicAdd(&sBl[1], bl1); atomicAdd(&sBl[2], bl2); }
+			}
+		}
+		FTRACE(24);
+		clusterSync();
+		FTRACE(25);
+		{
+			const int total = T4 + 2*H + B4 + 1, per = (total + cluster - 1)/cluster;
+			const int beg = (int)clusterRank()*per, end = beg + per < total ? beg + per : total;
+			const uint32_t stageAddr = smemAddr(stage4), biasAddr = smemAddr(sBias), blAddr = smemAddr(sBl);
+#pragma unroll 2
+			for (int idx = beg + tid; idx < end; idx += kWorkers) {
+				const uint32_t addr = idx < T4 + 2*H ? stageAddr + (uint32_t)idx*16u : (idx < T4 + 2*H + B4 ? biasAddr + (uint32_t)(idx - T4 - 2*H)*16u : blAddr);
+				float4 part[8];
+#pragma unroll
+				for (int p = 0; p < 8; p++) part[p] = p < cluster ? loadPeer16(addr, (uint32_t)p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				float4 sum = part[0];
+#pragma unroll
+				for (int p = 1; p < 8; p++) { sum.x += part[p].x; sum.y += part[p].y; sum.z += part[p].z; sum.w += part[p].w; }
+				if (idx < T4) {
+					const int l = idx/(H*H/4), w = idx - l*(H*H/4), i = w >> 4, c4 = (w & 15) ^ (i & 15);
+					redAdd4(P.gW[l + 1] + i*H + 4*c4, sum.x, sum.y, sum.z, sum.w);
+				} else if (idx < T4 + H) {
+					const int i = idx - T4;
+					const float sv[3] = {sum.x, sum.y, sum.z};
+					for (int j = 0; j < inDim; j++) atomicAdd(&P.gW[0][i*inDim + j], sv[j]);
+				} else if (idx < T4 + 2*H) {
+					const int i = idx - T4 - H;
+					const float sv[3] = {sum.x, sum.y, sum.z};
+					for (int j = 0; j < outDim; j++) atomicAdd(&P.gW[last][j*H + i], sv[j]);
+				} else if (idx < T4 + 2*H + B4) {
+					const int o = 4*(idx - T4 - 2*H), l = o/H, c = o - l*H;
+					atomicAdd(&P.gb[l][c], sum.x); atomicAdd(&P.gb[l][c + 1], sum.y); atomicAdd(&P.gb[l][c + 2], sum.z); atomicAdd(&P.gb[l][c + 3], sum.w);
+				} else {
+					const float sv[3] = {sum.x, sum.y, sum.z};
+					for (int j = 0; j < outDim; j++) atomicAdd(&P.gb[last][j], sv[j]);
+				}
+			}
+		}
+		FTRACE(26);
+		clusterSync();   // no CTA leaves while a peer still reads its shared memory
+	}
+	}
+
 	fenceBeforeSync();
 	__syncthreads();
-#ifdef NMC_TC_TRACE
-	tilesDone = 0;
 	FTRACE(22);
-#endif
 	if (warp == 0) tmemFree(tmemBase, 512u);
 }
 
@@ -464,11 +561,37 @@ extern "C" int nmc_siren_backward_fused_tc(const nmc_siren_shape* sh, const floa
 	}
 	Env env;
 	if (const char* bad = nmc_siren_detail::toEnv(envp, env)) return fail(bad);
-	const size_t smem = (size_t)(6*kTile*H + 2*H*H)*4 + (size_t)(3 + kMaxHidden + 1)*H*4 + 32;
+	const size_t smem = (size_t)(6*kTile*H + 2*H*H)*4 + (size_t)(3 + kMaxHidden + 1)*H*4 + 48;
 	const long long tiles = (n + kTile - 1)/kTile;
-	const int grid = (int)(tiles < smCount() ? tiles : smCount());
 	cudaError_t e = cudaFuncSetAttribute(sirenBackwardFusedTc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (!e) sirenBackwardFusedTc<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y);
+	if (e) return fail(cudaGetErrorString(e));
+	// thread-block clusters for the gradient reduction (batches that fill the GPU): the largest size the device can co-schedule
+	static int clusterMax = -1;
+	if (clusterMax < 0) {
+		clusterMax = 1;
+		const char* envc = getenv("NMC_FUSED_BWD_CLUSTER");
+		const int want = envc ? atoi(envc) : 4;   // 8: the 128 CTAs of a 16384 batch no longer fit in one wave (82 us against 44)
+		for (int c = want; c > 1; c >>= 1) {
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3((unsigned)(smCount()/c*c)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+			cfg.attrs = at; cfg.numAttrs = 1;
+			int nc = 0;
+			if (cudaOccupancyMaxActiveClusters(&nc, sirenBackwardFusedTc, &cfg) == cudaSuccess && nc*c >= 96) { clusterMax = c; break; }
+			cudaGetLastError();
+		}
+	}
+	int cluster = tiles >= 64 ? clusterMax : 1;
+	long long cap = cluster > 1 ? (long long)(smCount()/cluster)*cluster : smCount();
+	long long want = cluster > 1 ? (tiles + cluster - 1)/cluster*cluster : tiles;
+	const int grid = (int)(want < cap ? want : cap);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+	cfg.attrs = at; cfg.numAttrs = 1;
+	e = cudaLaunchKernelEx(&cfg, sirenBackwardFusedTc, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, z_saved, grad_y, cluster);
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
