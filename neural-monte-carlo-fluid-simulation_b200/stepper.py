@@ -117,6 +117,8 @@ class SplitStepper:
         # captured iterations draw their batches with one launch keyed by device-side counters (csrc/fit_glue.cu) instead of
         # three to eight torch launches; without CUDA graphs the batches come from torch's generator (NMC_FIT_GLUE=0: always)
         self.fused_glue = bool(use_cuda_graph) and os.environ.get("NMC_FIT_GLUE", "1") != "0"
+        # advection fit: the next iteration's target computed during the current iteration (NMC_PIPELINE_TARGETS=0: same iteration)
+        self.pipeline_targets = os.environ.get("NMC_PIPELINE_TARGETS", "1") != "0"
         torch.manual_seed(seed)
         self.dim = dim = len(self.size)//2
         if dim not in (2, 3):
@@ -134,6 +136,7 @@ class SplitStepper:
         self.timestep, self.seed = 0, seed
         self.last = {}
         self._fit, self._graphs, self._proj = None, {}, None
+        self._pipes = {}
         self._epoch = torch.zeros((), dtype=torch.int64, device=self.dev)  # fits started so far: part of the key of the captured draws
         if self.world > 1:  # identical initial weights (same seed above); data-parallel fits: different training samples per rank from here on
             torch.manual_seed(seed*7919 + 1 + (self.rank if self.fit_world > 1 else 0))
@@ -190,16 +193,16 @@ class SplitStepper:
         """circle_obstable_functions (main.py:101-104): signed distance to the cylinder."""
         return torch.linalg.norm(samples - self._obs_c, dim=-1) - self.obstacle[1]
 
-    def sample_random(self, n, keep_shape=True, fused=False):
+    def sample_random(self, n, keep_shape=True, fused=False, seed_xor=0, out=None):
         """sample_in_training with the 'random' pattern (base.py:225-241, utils/model_utils.py:22-31).  With an
         obstacle the reference drops the samples inside it (a batch a fraction of a percent smaller); here a sample
         inside is redrawn once so that the batch keeps its shape (CUDA-graph replay), or, with keep_shape=False,
         dropped exactly like the reference."""
         if fused and keep_shape:  # inside a captured fit iteration only: the key is the fit's (epoch, iteration) pair
             # data-parallel fits: every rank its own stream; replicated fits: the same samples on every rank
-            seed = self.seed*0x9E3779B1 + 0x632BE5AB*(self.rank if self.fit_world > 1 else 0)
+            seed = (self.seed*0x9E3779B1 + 0x632BE5AB*(self.rank if self.fit_world > 1 else 0)) ^ seed_xor
             return fit_sample_uniform(n, self.size[0::2], self.size[1::2], self._fit.opt.step_dev, self._epoch, seed,
-                                      obstacle=self.obstacle if self.boundary == "karman" else None)
+                                      obstacle=self.obstacle if self.boundary == "karman" else None, out=out)
         x = torch.rand(n, self.dim, device=self.dev)*(self._hi - self._lo) + self._lo
         if self.boundary == "karman":
             if keep_shape:
@@ -217,7 +220,7 @@ class SplitStepper:
             if net.first_layer_init is not None:
                 net.net[0].apply(net.first_layer_init)
 
-    def _loop(self, iteration, n_iters, key=None):
+    def _loop(self, iteration, n_iters, key=None, pipeline=None):
         """_training_loop (base.py:129-152) without autograd and without a host sync per iteration:
         `iteration()` returns (samples, target); the MSE fit step is DirectFit.iterate.  One DirectFit (one flat
         parameter / Adam buffer) serves every fit and is reset where the reference creates a new optimizer
@@ -234,12 +237,44 @@ class SplitStepper:
             fit.sync_parameters()  # the re-initialisation draws from per-rank random streams
         cached = self._graphs.get(key) if (self.use_graph and key is not None) else None
         it = 0
+        # Software-pipelined targets (`pipeline` = (draw, make_target), graph mode): the target of iteration k + 1 depends only on
+        # the frozen previous network and on the batch, so it is computed on a second stream DURING iteration k (its forward,
+        # backward and Adam step) and handed over through a device buffer.  The advection target -- two network evaluations and
+        # a back-trace, twice the training forward -- leaves the critical path of small batches (taylorgreen: 97 -> 66 us).
+        pipe = None
+        # (not with the one-kernel backward of the hidden = 64 networks at batch >= 16384: its CTAs take a whole SM each and the
+        # target kernels queue behind them -- smoke3d measured 91 us per iteration without, 94 us with the pipeline)
+        crowded = fit.fused_backward and fit.tc_backward and fit.sh.hidden == 64 and self.sample_resolution**2//self.fit_world >= fit.fused_backward_min
+        if (pipeline is not None and self.use_graph and self.fused_glue and self.overlap_targets and self.pipeline_targets and key is not None
+                and not crowded):
+            draw, make_target_p = pipeline
+            pipe = self._pipes.get(key)
+            if pipe is None:
+                n_b = self.sample_resolution**2//self.fit_world
+                pipe = self._pipes[key] = (torch.empty(2, n_b, self.dim, device=self.dev), torch.empty(2, n_b, self.dim, device=self.dev))
+            cur, nxt = pipe
+            draw(0x7F4A7C15, out=cur[0])          # batch and target of the first iteration
+            cur[1].copy_(make_target_p(cur[0]))
         if cached is not None:
             graph, loss_buf = cached
         else:
             loss_buf = fit.loss  # mean squared error, written by the iteration itself
 
             side2 = torch.cuda.Stream(device=self.dev) if self.overlap_targets else None
+
+            def one_pipelined():
+                cur, nxt = pipe
+                main = torch.cuda.current_stream()
+                side2.wait_stream(main)
+                with torch.cuda.stream(side2):
+                    draw(0, out=nxt[0])            # keyed by (epoch, Adam's step): read before this iteration's loss kernel advances it
+                    drawn = torch.cuda.Event(); drawn.record(side2)
+                    nxt[1].copy_(make_target_p(nxt[0]))
+                y = fit.forward(cur[0])
+                main.wait_event(drawn)
+                fit.finish(cur[0], y, cur[1])
+                main.wait_stream(side2)
+                cur.copy_(nxt)
 
             def one():
                 # `iteration()` returns the samples and a function that computes the fit target from them.  The target
@@ -258,6 +293,8 @@ class SplitStepper:
                 main.wait_stream(side2)
                 fit.finish(samples, y, *target) if isinstance(target, tuple) else fit.finish(samples, y, target)
 
+            if pipe is not None:
+                one = one_pipelined
             graph = None
             if self.use_graph:
                 side = torch.cuda.Stream(device=self.dev)
@@ -299,6 +336,7 @@ class SplitStepper:
             graph, _ = self._graphs.pop(key)
             graph.reset()
         self._graphs = {}
+        self._pipes = {}
         self._proj = None
         if self._fit is not None:
             self._fit.close()
@@ -327,7 +365,10 @@ class SplitStepper:
 
         def iteration():
             return self.sample_random(n, fused=self.fused_glue), make_target
-        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect")
+
+        def draw(seed_xor, out):
+            return self.sample_random(n, fused=True, seed_xor=seed_xor, out=out)
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect", pipeline=(draw, make_target))
 
     def divergence_grid(self):
         """-div u_prev on the grid with boundary samples, as the source array the scene expects: 2D [rows(y)][cols(x)]
