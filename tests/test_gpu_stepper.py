@@ -161,6 +161,45 @@ def test_taylor_green_velocity_error_tracks_the_reference_arrangement(oracle_lib
     assert 0.5*ref[-1] <= fast[-1] <= 2.0*ref[-1], (fast, ref)
 
 
+def test_pipelined_advection_targets_hand_over_consistent_batches():
+    """Graph mode: the advection fit computes the target of iteration k + 1 on a second stream during iteration k and hands it
+    over through device buffers (stepper._loop, pipeline=...).  After any number of replays the hand-over buffer holds a batch
+    inside the domain together with the target of exactly that batch, the batches differ from iteration to iteration and from
+    fit to fit, and the fit converges like the un-pipelined one (NMC_PIPELINE_TARGETS=0 arrangement)."""
+    kw = dict(max_n_iters=40, lr=1e-4, dt=0.01, grid_resolution=120, wost_resolution=48, sample_resolution=64, early_stop=False, seed=3)
+    pkg, s = _stepper(use_cuda_graph=True, **kw)
+    s.fit_initial(_tg, 300, lr=3e-4)
+    F = pkg.load_fields()
+
+    def expected_target(x):
+        with torch.no_grad():
+            pu = s.query_velocity(x, use_prev=True)
+            return s.query_velocity(F.backtrace(x, pu, s.dt, s.size[0::2], s.size[1::2]), use_prev=True)
+    seen = []
+    for n_it in (7, 12):
+        s._sync_prev()
+        it, loss = s.advect_velocity(n_it)
+        torch.cuda.synchronize()
+        assert it == n_it and math.isfinite(loss.item())
+        cur, nxt = s._pipes["advect"]
+        x, t = cur[0].clone(), cur[1].clone()
+        lo = torch.tensor(s.size[0::2], device=x.device); hi = torch.tensor(s.size[1::2], device=x.device)
+        assert (x >= lo).all() and (x < hi).all()
+        assert (t - expected_target(x)).abs().max().item() <= 1e-5
+        assert torch.equal(cur, nxt)                       # the hand-over copy closes every iteration
+        seen.append(x)
+    assert (seen[0] == seen[1]).float().mean().item() < 1e-3
+    # same fit with and without the pipeline: different batches (the draws are keyed differently), same loss level
+    assert s._fit.opt.step_dev.item() == 12
+    s2_pkg, s2 = _stepper(use_cuda_graph=True, **kw)
+    s2.pipeline_targets = False
+    s2.velocity_field.load_state_dict(s.velocity_field_prev.state_dict()); s2._sync_prev()
+    s.velocity_field.load_state_dict(s.velocity_field_prev.state_dict())
+    _, la = s.advect_velocity(40); _, lb = s2.advect_velocity(40)
+    assert "advect" not in s2._pipes
+    assert 0.5 <= la.item()/lb.item() <= 2.0, (la.item(), lb.item())
+
+
 def _karman_stepper(**kw):
     pkg = util.package()
     st = import_module(pkg.__name__ + ".stepper")
