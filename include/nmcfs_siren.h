@@ -130,6 +130,12 @@ int nmc_fit_sample_uniform(int dim, const float* lo, const float* hi, int64_t n,
 int nmc_fit_gather(int dim, int64_t n, const float* src_x, const float* src_g, const float* count, int64_t cap, float* out_x,
 				   float* out_g, const long long* step, const long long* epoch, uint64_t seed, void* stream);
 
+/* Targets computed ahead of time, a chunk of iterations per launch (the fit target depends only on the frozen previous network
+ * and on the batch): ring_x / ring_t / ring_s (optional) hold `slots` batches of `count` floats each; the captured iteration
+ * copies slot (*step % slots) -- Adam's device-side counter = the iteration index -- into the fixed buffers it reads. */
+int nmc_fit_fetch(int64_t count, int slots, const float* ring_x, const float* ring_t, const float* ring_s, const long long* step,
+				  float* out_x, float* out_t, float* out_s, void* stream);
+
 /* nmc_mse_grad with the rest of an iteration's bookkeeping in the same launch: the target is target - sub when sub != NULL
  * (u_prev - grad p of the projection fit), `zero` (zero_count floats: the flat gradient buffer) is cleared, and *step_advance
  * (Adam's device-side counter) is incremented -- every kernel that reads the counter as the iteration index was launched

@@ -60,6 +60,26 @@ __global__ void fitGather(int dim, long long n, const float* __restrict__ srcX, 
 	}
 }
 
+// one slot of the target ring -> the fixed buffers a captured iteration reads; the slot is Adam's device-side step modulo `slots`
+__global__ void fitFetch(long long count, int slots, const float* __restrict__ ringX, const float* __restrict__ ringT, const float* __restrict__ ringS,
+						 const long long* __restrict__ step, float* __restrict__ outX, float* __restrict__ outT, float* __restrict__ outS, int vec) {
+	const long long base = (*step % slots)*count;
+	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x, nth = (long long)gridDim.x*blockDim.x;
+	if (vec) {
+		const float4* x4 = reinterpret_cast<const float4*>(ringX + base); const float4* t4 = reinterpret_cast<const float4*>(ringT + base);
+		const float4* s4 = ringS ? reinterpret_cast<const float4*>(ringS + base) : nullptr;
+		for (long long i = tid; i < (count >> 2); i += nth) {
+			reinterpret_cast<float4*>(outX)[i] = x4[i]; reinterpret_cast<float4*>(outT)[i] = t4[i];
+			if (s4) reinterpret_cast<float4*>(outS)[i] = s4[i];
+		}
+	} else {
+		for (long long i = tid; i < count; i += nth) {
+			outX[i] = ringX[base + i]; outT[i] = ringT[base + i];
+			if (ringS) outS[i] = ringS[base + i];
+		}
+	}
+}
+
 unsigned gridFor(long long n) { long long b = (n + 255)/256; return (unsigned)(b < 1 ? 1 : (b > 1184 ? 1184 : b)); }
 
 } // namespace
@@ -83,6 +103,16 @@ extern "C" int nmc_fit_gather(int dim, int64_t n, const float* src_x, const floa
 	if (n <= 0) return 0;
 	if (!src_x || !src_g || !count || !out_x || !out_g || !step || !epoch || cap < 1) return fail("bad arguments");
 	fitGather<<<gridFor(n), 256, 0, (cudaStream_t)stream>>>(dim, n, src_x, src_g, count, cap, out_x, out_g, step, epoch, seed);
+	cudaError_t e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_fit_fetch(int64_t count, int slots, const float* ring_x, const float* ring_t, const float* ring_s, const long long* step,
+							 float* out_x, float* out_t, float* out_s, void* stream) {
+	if (count <= 0) return 0;
+	if (slots < 1 || !ring_x || !ring_t || !step || !out_x || !out_t || (ring_s && !out_s)) return fail("bad arguments");
+	const int vec = (count % 4 == 0) && ((((uintptr_t)ring_x | (uintptr_t)ring_t | (uintptr_t)ring_s | (uintptr_t)out_x | (uintptr_t)out_t | (uintptr_t)out_s) & 15) == 0);
+	fitFetch<<<gridFor(vec ? count/4 : count), 256, 0, (cudaStream_t)stream>>>(count, slots, ring_x, ring_t, ring_s, step, out_x, out_t, out_s, vec);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

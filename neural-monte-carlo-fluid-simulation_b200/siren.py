@@ -195,6 +195,7 @@ def _lib():
         f3 = C.POINTER(C.c_float)
         L.nmc_fit_sample_uniform.argtypes = [C.c_int, f3, f3, C.c_int64, vp, vp, vp, C.c_uint64, f3, vp]
         L.nmc_fit_gather.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_uint64, vp]
+        L.nmc_fit_fetch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         _configured = True
     return L
 
@@ -454,6 +455,16 @@ def fit_gather(n, src_x, src_g, count_dev, step_dev, epoch_dev, seed):
         _check(_lib().nmc_fit_gather(dim, n, src_x.data_ptr(), src_g.data_ptr(), count_dev.data_ptr(), src_x.shape[0], out_x.data_ptr(), out_g.data_ptr(),
                                      step_dev.data_ptr(), epoch_dev.data_ptr(), int(seed) & (2**64 - 1), _stream()))
     return out_x, out_g
+
+
+def fit_fetch(ring_x, ring_t, ring_s, step_dev, out_x, out_t, out_s):
+    """One launch: slot (step % slots) of the target ring ([slots, n, dim] each) -> the fixed buffers of a captured iteration."""
+    slots = ring_x.shape[0]
+    count = out_x.numel()
+    assert ring_x.is_contiguous() and ring_t.is_contiguous() and ring_x.numel() == slots*count and ring_t.shape == ring_x.shape
+    with torch.cuda.device(out_x.device):
+        _check(_lib().nmc_fit_fetch(count, slots, ring_x.data_ptr(), ring_t.data_ptr(), ring_s.data_ptr() if ring_s is not None else None,
+                                    step_dev.data_ptr(), out_x.data_ptr(), out_t.data_ptr(), out_s.data_ptr() if ring_s is not None else None, _stream()))
 
 
 class DirectFit:

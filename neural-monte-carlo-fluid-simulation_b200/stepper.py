@@ -23,7 +23,7 @@ import os
 import torch
 
 from . import capi, zombie, fields
-from .siren import (FusedSiren, DirectFit, fit_sample_uniform, fit_gather, wall_envelope, karman_envelope, smoke_obs_envelope, karman3d_envelope, smoke_envelope,
+from .siren import (FusedSiren, DirectFit, fit_sample_uniform, fit_gather, fit_fetch, wall_envelope, karman_envelope, smoke_obs_envelope, karman3d_envelope, smoke_envelope,
                     envelope_reference)
 
 
@@ -117,8 +117,8 @@ class SplitStepper:
         # captured iterations draw their batches with one launch keyed by device-side counters (csrc/fit_glue.cu) instead of
         # three to eight torch launches; without CUDA graphs the batches come from torch's generator (NMC_FIT_GLUE=0: always)
         self.fused_glue = bool(use_cuda_graph) and os.environ.get("NMC_FIT_GLUE", "1") != "0"
-        # advection fit: the next iteration's target computed during the current iteration (NMC_PIPELINE_TARGETS=0: same iteration)
-        self.pipeline_targets = os.environ.get("NMC_PIPELINE_TARGETS", "1") != "0"
+        # fit targets of the next `target_chunk` iterations computed in one pass on a second stream (NMC_TARGET_CHUNK=0: inside the iteration)
+        self.target_chunk = int(os.environ.get("NMC_TARGET_CHUNK", "32"))
         torch.manual_seed(seed)
         self.dim = dim = len(self.size)//2
         if dim not in (2, 3):
@@ -136,7 +136,7 @@ class SplitStepper:
         self.timestep, self.seed = 0, seed
         self.last = {}
         self._fit, self._graphs, self._proj = None, {}, None
-        self._pipes = {}
+        self._rings = {}
         self._epoch = torch.zeros((), dtype=torch.int64, device=self.dev)  # fits started so far: part of the key of the captured draws
         if self.world > 1:  # identical initial weights (same seed above); data-parallel fits: different training samples per rank from here on
             torch.manual_seed(seed*7919 + 1 + (self.rank if self.fit_world > 1 else 0))
@@ -220,7 +220,7 @@ class SplitStepper:
             if net.first_layer_init is not None:
                 net.net[0].apply(net.first_layer_init)
 
-    def _loop(self, iteration, n_iters, key=None, pipeline=None):
+    def _loop(self, iteration, n_iters, key=None, chunked=None):
         """_training_loop (base.py:129-152) without autograd and without a host sync per iteration:
         `iteration()` returns (samples, target); the MSE fit step is DirectFit.iterate.  One DirectFit (one flat
         parameter / Adam buffer) serves every fit and is reset where the reference creates a new optimizer
@@ -237,24 +237,44 @@ class SplitStepper:
             fit.sync_parameters()  # the re-initialisation draws from per-rank random streams
         cached = self._graphs.get(key) if (self.use_graph and key is not None) else None
         it = 0
-        # Software-pipelined targets (`pipeline` = (draw, make_target), graph mode): the target of iteration k + 1 depends only on
-        # the frozen previous network and on the batch, so it is computed on a second stream DURING iteration k (its forward,
-        # backward and Adam step) and handed over through a device buffer.  The advection target -- two network evaluations and
-        # a back-trace, twice the training forward -- leaves the critical path of small batches (taylorgreen: 97 -> 66 us).
-        pipe = None
-        # (not with the one-kernel backward of the hidden = 64 networks at batch >= 16384: its CTAs take a whole SM each and the
-        # target kernels queue behind them -- smoke3d measured 91 us per iteration without, 94 us with the pipeline)
-        crowded = fit.fused_backward and fit.tc_backward and fit.sh.hidden == 64 and self.sample_resolution**2//self.fit_world >= fit.fused_backward_min
-        if (pipeline is not None and self.use_graph and self.fused_glue and self.overlap_targets and self.pipeline_targets and key is not None
-                and not crowded):
-            draw, make_target_p = pipeline
-            pipe = self._pipes.get(key)
-            if pipe is None:
-                n_b = self.sample_resolution**2//self.fit_world
-                pipe = self._pipes[key] = (torch.empty(2, n_b, self.dim, device=self.dev), torch.empty(2, n_b, self.dim, device=self.dev))
-            cur, nxt = pipe
-            draw(0x7F4A7C15, out=cur[0])          # batch and target of the first iteration
-            cur[1].copy_(make_target_p(cur[0]))
+        # Targets ahead of time (`chunked` = gen(chunk id, m) -> (samples, target, sub or None), graph mode): the target of an
+        # iteration depends only on the frozen previous network and on the batch, so the batches and targets of the next
+        # `target_chunk` iterations are computed in ONE pass on a second stream -- at 32 x 4096 samples the tcgen05 forward runs at its
+        # large-batch rate (2.3 us per 4096 samples against 18.7 us for a launch of its own) -- into a ring of two chunks; the
+        # captured iteration fetches its slot (Adam's device-side step modulo the ring size) and is one stream: forward, loss,
+        # backward, Adam.  taylorgreen advect: 97 us per iteration with the target inside the iteration, 83 us with the next
+        # iteration's target overlapped, see profiles/ for the chunked figure.
+        ring = None
+        C = self.target_chunk
+        if chunked is not None and self.use_graph and self.fused_glue and C >= 4 and key is not None:
+            n_b = self.sample_resolution**2//self.fit_world
+            ring = self._rings.get(key)
+            if ring is None:
+                mk = lambda *shape: torch.empty(*shape, device=self.dev)  # noqa: E731
+                ring = self._rings[key] = dict(X=mk(2*C, n_b, self.dim), T=mk(2*C, n_b, self.dim), S=None, x=mk(n_b, self.dim), t=mk(n_b, self.dim), s=None,
+                                               ids=torch.arange(1 << 16, dtype=torch.int64, device=self.dev), gen=torch.cuda.Stream(device=self.dev),
+                                               done=[torch.cuda.Event(), torch.cuda.Event()], used=[torch.cuda.Event(), torch.cuda.Event()])
+            main = torch.cuda.current_stream()
+            ring["gen"].wait_stream(main)   # the previous network, the epoch counter and (projection) the pressure samples are in place
+
+            def generate(c):
+                half = c % 2
+                with torch.cuda.stream(ring["gen"]):
+                    if c >= 2:
+                        ring["gen"].wait_event(ring["used"][half])   # the iterations of chunk c - 2 have read this half
+                    X, T, S = chunked(ring["ids"][c % ring["ids"].numel()], C*n_b)
+                    ring["X"][half*C:(half + 1)*C].view(-1, self.dim).copy_(X)
+                    ring["T"][half*C:(half + 1)*C].view(-1, self.dim).copy_(T)
+                    if S is not None:
+                        if ring["S"] is None:
+                            ring["S"] = torch.empty_like(ring["X"]); ring["s"] = torch.empty_like(ring["x"])
+                        ring["S"][half*C:(half + 1)*C].view(-1, self.dim).copy_(S)
+                    ring["done"][half].record(ring["gen"])
+            generate(0)
+            main.wait_event(ring["done"][0])
+            if n_iters > C:
+                generate(1)
+            chunk_now = 0
         if cached is not None:
             graph, loss_buf = cached
         else:
@@ -262,19 +282,10 @@ class SplitStepper:
 
             side2 = torch.cuda.Stream(device=self.dev) if self.overlap_targets else None
 
-            def one_pipelined():
-                cur, nxt = pipe
-                main = torch.cuda.current_stream()
-                side2.wait_stream(main)
-                with torch.cuda.stream(side2):
-                    draw(0, out=nxt[0])            # keyed by (epoch, Adam's step): read before this iteration's loss kernel advances it
-                    drawn = torch.cuda.Event(); drawn.record(side2)
-                    nxt[1].copy_(make_target_p(nxt[0]))
-                y = fit.forward(cur[0])
-                main.wait_event(drawn)
-                fit.finish(cur[0], y, cur[1])
-                main.wait_stream(side2)
-                cur.copy_(nxt)
+            def one_chunked():
+                fit_fetch(ring["X"], ring["T"], ring["S"], fit.opt.step_dev, ring["x"], ring["t"], ring["s"])
+                y = fit.forward(ring["x"])
+                fit.finish(ring["x"], y, ring["t"], ring["s"])
 
             def one():
                 # `iteration()` returns the samples and a function that computes the fit target from them.  The target
@@ -293,8 +304,8 @@ class SplitStepper:
                 main.wait_stream(side2)
                 fit.finish(samples, y, *target) if isinstance(target, tuple) else fit.finish(samples, y, target)
 
-            if pipe is not None:
-                one = one_pipelined
+            if ring is not None:
+                one = one_chunked
             graph = None
             if self.use_graph:
                 side = torch.cuda.Stream(device=self.dev)
@@ -310,6 +321,12 @@ class SplitStepper:
                 if key is not None:
                     self._graphs[key] = (graph, loss_buf)
         while it < n_iters:
+            if ring is not None and it//C != chunk_now:   # first iteration of the next chunk: wait for it, start the one after
+                ring["used"][chunk_now % 2].record(torch.cuda.current_stream())
+                chunk_now = it//C
+                torch.cuda.current_stream().wait_event(ring["done"][chunk_now % 2])
+                if (chunk_now + 1)*C < n_iters:
+                    generate(chunk_now + 1)
             if graph is not None:
                 graph.replay()
             else:
@@ -320,6 +337,8 @@ class SplitStepper:
             # every `check_every` iterations, each test being a host synchronisation
             if self.early_stop and (it == 1 or it % self.check_every == 0) and self._stop_now(loss_buf):
                 break
+        if ring is not None:  # a chunk generated ahead of an early stop must not overlap the next fit's set-up
+            torch.cuda.current_stream().wait_stream(ring["gen"])
         return it, loss_buf
 
     def _stop_now(self, loss_buf):
@@ -336,7 +355,7 @@ class SplitStepper:
             graph, _ = self._graphs.pop(key)
             graph.reset()
         self._graphs = {}
-        self._pipes = {}
+        self._rings = {}
         self._proj = None
         if self._fit is not None:
             self._fit.close()
@@ -366,9 +385,12 @@ class SplitStepper:
         def iteration():
             return self.sample_random(n, fused=self.fused_glue), make_target
 
-        def draw(seed_xor, out):
-            return self.sample_random(n, fused=True, seed_xor=seed_xor, out=out)
-        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect", pipeline=(draw, make_target))
+        def chunked(chunk_id, m):
+            seed = self.seed*0x9E3779B1 + 0x632BE5AB*(self.rank if self.fit_world > 1 else 0)
+            x = fit_sample_uniform(m, self.size[0::2], self.size[1::2], chunk_id, self._epoch, seed,
+                                   obstacle=self.obstacle if self.boundary == "karman" else None)
+            return x, make_target(x), None
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="advect", chunked=chunked)
 
     def divergence_grid(self):
         """-div u_prev on the grid with boundary samples, as the source array the scene expects: 2D [rows(y)][cols(x)]
@@ -477,9 +499,16 @@ class SplitStepper:
                     with torch.no_grad():
                         return self.query_velocity(samples, use_prev=True) - grad_p[idx]
                 return samples_all[idx], make_target
+        chunked = None
         if self.use_graph and self.fused_glue:
             iteration = iteration_fused
-        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="project")
+
+            def chunked(chunk_id, m):
+                seed = self.seed*0x9E3779B1 + 0x632BE5AB*(self.rank if self.fit_world > 1 else 0) + 0x1B873593
+                xs, gs = fit_gather(m, ps, pg, pc, chunk_id, self._epoch, seed)
+                with torch.no_grad():
+                    return xs, self.query_velocity(xs, use_prev=True), gs
+        return self._loop(iteration, self.max_n_iters if n_iters is None else n_iters, key="project", chunked=chunked)
 
     def _sync_prev(self):
         self.velocity_field_prev.load_state_dict(self.velocity_field.state_dict())

@@ -161,42 +161,58 @@ def test_taylor_green_velocity_error_tracks_the_reference_arrangement(oracle_lib
     assert 0.5*ref[-1] <= fast[-1] <= 2.0*ref[-1], (fast, ref)
 
 
-def test_pipelined_advection_targets_hand_over_consistent_batches():
-    """Graph mode: the advection fit computes the target of iteration k + 1 on a second stream during iteration k and hands it
-    over through device buffers (stepper._loop, pipeline=...).  After any number of replays the hand-over buffer holds a batch
-    inside the domain together with the target of exactly that batch, the batches differ from iteration to iteration and from
-    fit to fit, and the fit converges like the un-pipelined one (NMC_PIPELINE_TARGETS=0 arrangement)."""
+def test_chunked_fit_targets_are_the_targets_of_their_batches():
+    """Graph mode: batches and targets of the next `target_chunk` iterations are computed in one pass on a second stream into a
+    ring of two chunks and fetched by the captured iteration (stepper._loop, chunked=...).  Every ring slot holds a batch
+    inside the domain together with the target of exactly that batch, slots differ from each other and from fit to fit, the
+    iteration reads the slot of its index, and the fit reaches the loss level of the fit that computes its targets inside
+    the iteration (NMC_TARGET_CHUNK=0 arrangement)."""
     kw = dict(max_n_iters=40, lr=1e-4, dt=0.01, grid_resolution=120, wost_resolution=48, sample_resolution=64, early_stop=False, seed=3)
     pkg, s = _stepper(use_cuda_graph=True, **kw)
+    s.target_chunk = 8
     s.fit_initial(_tg, 300, lr=3e-4)
     F = pkg.load_fields()
+    lo = torch.tensor(s.size[0::2], device="cuda"); hi = torch.tensor(s.size[1::2], device="cuda")
 
     def expected_target(x):
         with torch.no_grad():
             pu = s.query_velocity(x, use_prev=True)
             return s.query_velocity(F.backtrace(x, pu, s.dt, s.size[0::2], s.size[1::2]), use_prev=True)
     seen = []
-    for n_it in (7, 12):
+    for n_it in (7, 21):   # within one chunk; three chunks through both halves of the ring
         s._sync_prev()
         it, loss = s.advect_velocity(n_it)
         torch.cuda.synchronize()
-        assert it == n_it and math.isfinite(loss.item())
-        cur, nxt = s._pipes["advect"]
-        x, t = cur[0].clone(), cur[1].clone()
-        lo = torch.tensor(s.size[0::2], device=x.device); hi = torch.tensor(s.size[1::2], device=x.device)
-        assert (x >= lo).all() and (x < hi).all()
-        assert (t - expected_target(x)).abs().max().item() <= 1e-5
-        assert torch.equal(cur, nxt)                       # the hand-over copy closes every iteration
-        seen.append(x)
+        assert it == n_it and math.isfinite(loss.item()) and s._fit.opt.step_dev.item() == n_it
+        ring = s._rings["advect"]
+        last = n_it - 1
+        assert torch.equal(ring["x"], ring["X"][last % 16]) and torch.equal(ring["t"], ring["T"][last % 16])   # the slot of the last iteration
+        for k in range(8*(last//8), last + 1):                       # the chunk in use
+            x, t = ring["X"][k % 16], ring["T"][k % 16]
+            assert (x >= lo).all() and (x < hi).all()
+            assert (t - expected_target(x)).abs().max().item() <= 1e-5
+        assert (ring["X"][last % 16] == ring["X"][(last - 1) % 16]).float().mean().item() < 1e-3
+        seen.append(ring["x"].clone())
     assert (seen[0] == seen[1]).float().mean().item() < 1e-3
-    # same fit with and without the pipeline: different batches (the draws are keyed differently), same loss level
-    assert s._fit.opt.step_dev.item() == 12
+    # projection fit: the target is (u_prev(x), grad p) with x, grad p rows of the pressure samples
+    s._sync_prev()
+    it, loss = s.project_velocity(12)
+    torch.cuda.synchronize()
+    ring = s._rings["project"]
+    ps, pg = s.last["pressure_samples"], s.last["grad_p"]
+    x, t, g = ring["X"][3], ring["T"][3], ring["S"][3]
+    with torch.no_grad():
+        assert (t - s.query_velocity(x, use_prev=True)).abs().max().item() <= 1e-5
+    match = (x[:64, None, :] == ps[None, :, :]).all(dim=2)             # every fetched sample is one of the pressure samples, with its gradient
+    assert match.any(dim=1).all()
+    assert torch.equal(g[:64], pg[match.float().argmax(dim=1)])
+    # same fit with the targets computed inside the iteration: different batches, same loss level
     s2_pkg, s2 = _stepper(use_cuda_graph=True, **kw)
-    s2.pipeline_targets = False
+    s2.target_chunk = 0
     s2.velocity_field.load_state_dict(s.velocity_field_prev.state_dict()); s2._sync_prev()
     s.velocity_field.load_state_dict(s.velocity_field_prev.state_dict())
     _, la = s.advect_velocity(40); _, lb = s2.advect_velocity(40)
-    assert "advect" not in s2._pipes
+    assert "advect" not in s2._rings
     assert 0.5 <= la.item()/lb.item() <= 2.0, (la.item(), lb.item())
 
 
