@@ -636,10 +636,10 @@ __global__ void adamAdvance(long long* step) { *step += 1; }
 __global__ void adamKernelDev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
 							  long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step) {
 	__shared__ float bc[2];
-	if (threadIdx.x == 0) {
-		const double t = (double)*step;
-		bc[0] = (float)(1.0 - pow((double)b1, t));
-		bc[1] = sqrtf((float)(1.0 - pow((double)b2, t)));
+	if (threadIdx.x == 0) { // 1 - beta^t = -expm1(t log1p(-(1 - beta))): fp32 throughout (1 - beta is exact), ~2e-7 relative; the double-precision
+		const float t = (float)*step;   // pow it replaces took ~1.5 of the kernel's 3.6 us on the fp64 pipe
+		bc[0] = -expm1f(t*log1pf(-(1.0f - b1)));
+		bc[1] = sqrtf(-expm1f(t*log1pf(-(1.0f - b2))));
 	}
 	__syncthreads();
 	long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;

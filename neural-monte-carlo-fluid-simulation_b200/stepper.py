@@ -118,7 +118,10 @@ class SplitStepper:
         # three to eight torch launches; without CUDA graphs the batches come from torch's generator (NMC_FIT_GLUE=0: always)
         self.fused_glue = bool(use_cuda_graph) and os.environ.get("NMC_FIT_GLUE", "1") != "0"
         # fit targets of the next `target_chunk` iterations computed in one pass on a second stream (NMC_TARGET_CHUNK=0: inside the iteration)
-        self.target_chunk = int(os.environ.get("NMC_TARGET_CHUNK", "32"))
+        self.target_chunk = int(os.environ.get("NMC_TARGET_CHUNK", "40"))
+        # with chunked targets an iteration is one stream of six kernels; `graph_unroll` of them are captured in a second graph, which
+        # removes the ~4 us between two graph launches (taylorgreen: 68 -> 64 us per iteration).  Must divide the chunk and check_every.
+        self.graph_unroll = int(os.environ.get("NMC_GRAPH_UNROLL", "20"))
         torch.manual_seed(seed)
         self.dim = dim = len(self.size)//2
         if dim not in (2, 3):
@@ -275,8 +278,9 @@ class SplitStepper:
             if n_iters > C:
                 generate(1)
             chunk_now = 0
+        graph_u = None
         if cached is not None:
-            graph, loss_buf = cached
+            graph, loss_buf, graph_u = cached
         else:
             loss_buf = fit.loss  # mean squared error, written by the iteration itself
 
@@ -318,8 +322,14 @@ class SplitStepper:
                 with torch.cuda.graph(graph):
                     one()
                 it = 3
+                U = self.graph_unroll
+                if ring is not None and U > 1 and C % U == 0 and self.check_every % U == 0:
+                    graph_u = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph_u):
+                        for _ in range(U):
+                            one()
                 if key is not None:
-                    self._graphs[key] = (graph, loss_buf)
+                    self._graphs[key] = (graph, loss_buf, graph_u)
         while it < n_iters:
             if ring is not None and it//C != chunk_now:   # first iteration of the next chunk: wait for it, start the one after
                 ring["used"][chunk_now % 2].record(torch.cuda.current_stream())
@@ -327,11 +337,15 @@ class SplitStepper:
                 torch.cuda.current_stream().wait_event(ring["done"][chunk_now % 2])
                 if (chunk_now + 1)*C < n_iters:
                     generate(chunk_now + 1)
-            if graph is not None:
+            if graph_u is not None and it % self.graph_unroll == 0 and it + self.graph_unroll <= n_iters:
+                graph_u.replay()   # neither a chunk boundary nor an early-stop test falls inside: both are multiples of the unroll
+                it += self.graph_unroll
+            elif graph is not None:
                 graph.replay()
+                it += 1
             else:
                 one()
-            it += 1
+                it += 1
             # the reference tests the loss after every iteration (base.py:148); here after the first one (a fit whose target is
             # the network itself -- the projection with a zero pressure gradient -- stops at once, as it does there) and then
             # every `check_every` iterations, each test being a host synchronisation
@@ -352,8 +366,10 @@ class SplitStepper:
         are alive torch.distributed.destroy_process_group() blocks), the fit buffers and the scene."""
         torch.cuda.synchronize(self.dev)
         for key in list(self._graphs):
-            graph, _ = self._graphs.pop(key)
+            graph, _, graph_u = self._graphs.pop(key)
             graph.reset()
+            if graph_u is not None:
+                graph_u.reset()
         self._graphs = {}
         self._rings = {}
         self._proj = None
