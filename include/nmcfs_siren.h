@@ -139,13 +139,17 @@ int nmc_fit_fetch(int64_t count, int slots, const float* ring_x, const float* ri
 /* nmc_mse_grad with the rest of an iteration's bookkeeping in the same launch: the target is target - sub when sub != NULL
  * (u_prev - grad p of the projection fit), `zero` (zero_count floats: the flat gradient buffer) is cleared, and *step_advance
  * (Adam's device-side counter) is incremented -- every kernel that reads the counter as the iteration index was launched
- * earlier on the stream, nmc_adam_update_device later. */
+ * earlier on the stream, nmc_adam_update_device later.  Early stop without a host round trip (base.py:148 leaves the loop at the
+ * first iteration whose loss is <= 1.1e-10): when stop_flag != NULL and the loss is <= stop_threshold, *stop_flag (device int,
+ * cleared by the caller at the start of a fit) is set and stays set. */
 int nmc_mse_grad_fit(const float* y, const float* target, const float* sub, int64_t count, float* diff, float* grad_y, float* loss,
-					 float* zero, int64_t zero_count, long long* step_advance, void* stream);
+					 float* zero, int64_t zero_count, long long* step_advance, float stop_threshold, int* stop_flag, void* stream);
 
-/* nmc_adam_step_device without the increment (the counter was advanced by nmc_mse_grad_fit). */
+/* nmc_adam_step_device without the increment (the counter was advanced by nmc_mse_grad_fit).  With stop_flag != NULL and
+ * *stop_flag != 0 the parameters are left alone: iterations replayed between the loss reaching the threshold and the host's
+ * next test of the flag do not move a fit the reference has already ended. */
 int nmc_adam_update_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-						   float eps, const long long* step, void* stream);
+						   float eps, const long long* step, const int* stop_flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -574,7 +574,8 @@ __device__ unsigned g_mseDone;
 // step counter is advanced in the same launch (three 2 us launches less per iteration).
 __global__ void __launch_bounds__(512) mseGrad(const float* __restrict__ y, const float* __restrict__ target, const float* __restrict__ sub,
 												long long count, float* __restrict__ diff, float* __restrict__ gy, float* __restrict__ loss, int vec,
-												float* __restrict__ zero, long long zeroCount, long long* __restrict__ stepAdvance) {
+												float* __restrict__ zero, long long zeroCount, long long* __restrict__ stepAdvance,
+												float stopThreshold, int* __restrict__ stopFlag) {
 	const float scale = 2.0f/(float)count;
 	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x, nth = (long long)gridDim.x*blockDim.x;
 	if (stepAdvance && tid == 0) *stepAdvance += 1;
@@ -626,6 +627,7 @@ __global__ void __launch_bounds__(512) mseGrad(const float* __restrict__ y, cons
 		float v = 0.0f;
 		for (unsigned b = 0; b < gridDim.x; b++) v += *(volatile float*)&g_msePart[b];
 		*loss = v/(float)count;
+		if (stopFlag && v/(float)count <= stopThreshold) *stopFlag = 1;   // sticky until the next fit: the Adam update checks it
 		g_mseDone = 0;
 	}
 }
@@ -634,7 +636,8 @@ __global__ void __launch_bounds__(512) mseGrad(const float* __restrict__ y, cons
 // corrections at their capture-time values, so the counter is advanced by a one-thread kernel and read by the update.
 __global__ void adamAdvance(long long* step) { *step += 1; }
 __global__ void adamKernelDev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-							  long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step) {
+							  long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step, const int* __restrict__ stopFlag) {
+	if (stopFlag && *stopFlag) return;   // the fit has reached the early-stop threshold (base.py:148): the reference has left the loop
 	__shared__ float bc[2];
 	if (threadIdx.x == 0) { // 1 - beta^t = -expm1(t log1p(-(1 - beta))): fp32 throughout (1 - beta is exact), ~2e-7 relative; the double-precision
 		const float t = (float)*step;   // pow it replaces took ~1.5 of the kernel's 3.6 us on the fp64 pipe
@@ -806,27 +809,27 @@ extern "C" int nmc_siren_weight_grads(const nmc_siren_shape* sh, const float* x,
 }
 
 extern "C" int nmc_mse_grad_fit(const float* y, const float* target, const float* sub, int64_t count, float* diff, float* grad_y, float* loss,
-								float* zero, int64_t zero_count, long long* step_advance, void* stream) {
+								float* zero, int64_t zero_count, long long* step_advance, float stop_threshold, int* stop_flag, void* stream) {
 	if (count <= 0) return 0;
 	if (!y || !target || !diff || !grad_y || !loss) return fail("null buffer");
 	if (zero && (((uintptr_t)zero & 15) || zero_count < 0)) return fail("the buffer to clear must be 16-byte aligned");
 	const int vec = (((uintptr_t)y | (uintptr_t)target | (uintptr_t)diff | (uintptr_t)grad_y | (uintptr_t)sub) & 15) == 0;
 	int blocks = (int)((count/4 + 511)/512);
 	blocks = blocks < 1 ? 1 : (blocks > kMseBlocks ? kMseBlocks : blocks);
-	mseGrad<<<blocks, 512, 0, (cudaStream_t)stream>>>(y, target, sub, count, diff, grad_y, loss, vec, zero_count > 0 ? zero : nullptr, zero_count, step_advance);
+	mseGrad<<<blocks, 512, 0, (cudaStream_t)stream>>>(y, target, sub, count, diff, grad_y, loss, vec, zero_count > 0 ? zero : nullptr, zero_count, step_advance, stop_threshold, stop_flag);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
 
 extern "C" int nmc_mse_grad(const float* y, const float* target, int64_t count, float* diff, float* grad_y, float* loss, void* stream) {
-	return nmc_mse_grad_fit(y, target, nullptr, count, diff, grad_y, loss, nullptr, 0, nullptr, stream);
+	return nmc_mse_grad_fit(y, target, nullptr, count, diff, grad_y, loss, nullptr, 0, nullptr, 0.0f, nullptr, stream);
 }
 
 extern "C" int nmc_adam_update_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-									  float eps, const long long* step, void* stream) {
+									  float eps, const long long* step, const int* stop_flag, void* stream) {
 	if (n <= 0) return 0;
 	if (!p || !g || !m || !v || !step) return fail("bad arguments");
-	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step);
+	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, stop_flag);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
@@ -836,7 +839,7 @@ extern "C" int nmc_adam_step_device(float* p, const float* g, float* m, float* v
 	if (n <= 0) return 0;
 	if (!p || !g || !m || !v || !step) return fail("bad arguments");
 	adamAdvance<<<1, 1, 0, (cudaStream_t)stream>>>(step);
-	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step);
+	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, nullptr);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

@@ -190,8 +190,8 @@ def _lib():
         L.nmc_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]
         L.nmc_adam_step_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
         L.nmc_mse_grad.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
-        L.nmc_mse_grad_fit.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int64, vp, vp]
-        L.nmc_adam_update_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+        L.nmc_mse_grad_fit.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int64, vp, C.c_float, vp, vp]
+        L.nmc_adam_update_device.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
         f3 = C.POINTER(C.c_float)
         L.nmc_fit_sample_uniform.argtypes = [C.c_int, f3, f3, C.c_int64, vp, vp, vp, C.c_uint64, f3, vp]
         L.nmc_fit_gather.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_uint64, vp]
@@ -373,6 +373,7 @@ class FusedAdam:
         self.flat = torch.zeros(n, device=dev); self.m = torch.zeros(n, device=dev); self.v = torch.zeros(n, device=dev)
         self.g = torch.zeros(n, device=dev)
         self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)  # Adam's t lives on the device (CUDA-graph replay)
+        self.stop_flag = torch.zeros((), dtype=torch.int32, device=dev)  # set by the loss kernel at the early-stop threshold (DirectFit.stop_threshold)
         with torch.no_grad():  # re-home the parameters as views into one flat buffer
             off = 0
             for p in self.params:
@@ -394,7 +395,7 @@ class FusedAdam:
 
     def reset(self):
         """A fresh optimizer on the same parameters (create_optimizer() at the top of every fit, base.py:133)."""
-        self.m.zero_(); self.v.zero_(); self.step_dev.zero_()
+        self.m.zero_(); self.v.zero_(); self.step_dev.zero_(); self.stop_flag.zero_()
         self.step_count = 0
 
     def step_flat(self):
@@ -405,12 +406,14 @@ class FusedAdam:
             _check(_lib().nmc_adam_step_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
                                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
 
-    def update_flat(self):
-        """step_flat without the increment: the counter was advanced by nmc_mse_grad_fit earlier in the iteration."""
+    def update_flat(self, gated=False):
+        """step_flat without the increment: the counter was advanced by nmc_mse_grad_fit earlier in the iteration.
+        gated: no update once the loss kernel has set `stop_flag` (the fit reached the early-stop threshold)."""
         self.step_count += 1
         with torch.cuda.device(self.flat.device):
             _check(_lib().nmc_adam_update_device(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
-                                                 self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), _stream()))
+                                                 self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(),
+                                                 self.stop_flag.data_ptr() if gated else None, _stream()))
 
     def step(self):
         self.step_count += 1
@@ -511,6 +514,9 @@ class DirectFit:
         self.dz = torch.empty(((Lh + 1)*H + self.sh.out_dim)*max_batch, device=g.device) if self.tc_backward else None
         self.max_batch = max_batch
         self.loss = torch.zeros((), device=g.device)  # mean squared error of the last iterate() call
+        # > 0: the reference's early stop (base.py:148, loss <= 1.1e-10) decided on the device -- the loss kernel sets opt.stop_flag,
+        # later updates are skipped until opt.reset(); the host reads the flag whenever it likes (stepper._stop_now)
+        self.stop_threshold = 0.0
 
     def iterate(self, x, target, sub=None):
         return self.finish(x, self.forward(x), target, sub)
@@ -538,12 +544,14 @@ class DirectFit:
         z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]
         diff = torch.empty_like(y); gy = torch.empty_like(y)
         tgt = target.contiguous()
+        gated = self.stop_threshold > 0 and self.world == 1   # data-parallel fits: the decision is collective (stepper.collective_stop)
         if sub is not None:
             sub = sub.contiguous()
             assert sub.shape == tgt.shape
         with torch.cuda.device(x.device):  # diff, dL/dy, the loss, the zero-fill of the gradient buffer and Adam's t += 1 in one launch
             _check(_lib().nmc_mse_grad_fit(y.data_ptr(), tgt.data_ptr(), sub.data_ptr() if sub is not None else None, y.numel(), diff.data_ptr(),
-                                           gy.data_ptr(), self.loss.data_ptr(), self.opt.g.data_ptr(), self.opt.g.numel(), self.opt.step_dev.data_ptr(), _stream()))
+                                           gy.data_ptr(), self.loss.data_ptr(), self.opt.g.data_ptr(), self.opt.g.numel(), self.opt.step_dev.data_ptr(),
+                                           float(self.stop_threshold), self.opt.stop_flag.data_ptr() if gated else None, _stream()))
         if self.tc_backward and n >= self.tc_backward_min and n % 4 == 0 and sh.n_hidden_layers >= 1:
             gW0, gb0, gWh, gbh, gWl, gbl = self.out
             gW = [gW0] + [gWh[i] for i in range(sh.n_hidden_layers)] + [gWl]
@@ -566,7 +574,7 @@ class DirectFit:
         if self.world > 1:  # mean over the global batch = mean over ranks of the local means (equal shard sizes)
             import torch.distributed as dist
             dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG, group=self.group)
-        self.opt.update_flat()
+        self.opt.update_flat(gated)
         return diff
 
     def close(self):

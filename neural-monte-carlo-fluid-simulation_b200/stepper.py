@@ -233,6 +233,7 @@ class SplitStepper:
         if self._fit is None:
             self._fit = DirectFit(self.velocity_field, self.lr, self.env, max_batch=self.sample_resolution**2, distributed=self.fit_world > 1)
         fit = self._fit
+        fit.stop_threshold = 1.1e-10 if (self.early_stop and self.fit_world == 1) else 0.0
         fit.opt.reset()
         self._epoch += 1
         if self.reset_wts:
@@ -273,6 +274,8 @@ class SplitStepper:
                             ring["S"] = torch.empty_like(ring["X"]); ring["s"] = torch.empty_like(ring["x"])
                         ring["S"][half*C:(half + 1)*C].view(-1, self.dim).copy_(S)
                     ring["done"][half].record(ring["gen"])
+                if os.environ.get("NMC_CHUNK_SERIAL", "0") == "1":   # experiment: no overlap of generation and training
+                    torch.cuda.current_stream().wait_event(ring["done"][half])
             generate(0)
             main.wait_event(ring["done"][0])
             if n_iters > C:
@@ -337,7 +340,7 @@ class SplitStepper:
                 torch.cuda.current_stream().wait_event(ring["done"][chunk_now % 2])
                 if (chunk_now + 1)*C < n_iters:
                     generate(chunk_now + 1)
-            if graph_u is not None and it % self.graph_unroll == 0 and it + self.graph_unroll <= n_iters:
+            if graph_u is not None and it >= self.graph_unroll and it % self.graph_unroll == 0 and it + self.graph_unroll <= n_iters:
                 graph_u.replay()   # neither a chunk boundary nor an early-stop test falls inside: both are multiples of the unroll
                 it += self.graph_unroll
             elif graph is not None:
@@ -359,6 +362,8 @@ class SplitStepper:
         """Early-stop test of _training_loop (base.py:148).  Data-parallel fits: `loss_buf` is this rank's shard MSE, so
         the decision is taken on the mean over ranks -- every rank issues this all_reduce at the same iteration and
         reaches the same verdict (a rank that stopped alone would leave the others waiting in the gradient all_reduce)."""
+        if self._fit is not None and self._fit.stop_threshold > 0 and self.fit_world == 1:
+            return bool(self._fit.opt.stop_flag.item() != 0) or loss_buf.item() <= self._fit.stop_threshold
         return collective_stop(loss_buf, self.fit_world)
 
     def close(self):

@@ -16,3 +16,11 @@ for _ in range(3):
     fit.iterate(xb, tb)
 torch.cuda.synchronize()
 print("done")
+# hidden = 64 at batch 16384: the one-kernel backward (sirenBackwardFusedTc) and the large-batch inference forward
+net64 = S.FusedSiren(3, 3, 5, 64, nonlinearity="sine", tensor_cores=True).cuda()
+fit64 = S.DirectFit(net64, 1e-5, None, max_batch=16384)
+x64 = torch.rand(16384, 3, device="cuda"); t64 = torch.rand(16384, 3, device="cuda")
+for _ in range(3):
+    fit64.iterate(x64, t64)
+torch.cuda.synchronize()
+print("done 64")

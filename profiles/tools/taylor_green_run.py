@@ -29,6 +29,8 @@ F = pkg.load_fields()
 torch.manual_seed(0)
 s, cfg, init_fn, _, what = bench_step.build(SimpleNamespace(case="taylorgreen", iters=10000, watertight=variant == "shipped", no_graph=os.environ.get("NMC_NO_GRAPH", "0") == "1"), pkg, st)
 s.early_stop = True
+if os.environ.get("NMC_PREV_FP32", "0") == "1":   # experiment: the frozen network evaluated by the fp32 kernels at every batch size
+    s.velocity_field_prev.tensor_cores = False
 t0 = time.time()
 s.fit_initial(init_fn, init_iters, lr=1e-5)  # add_source (base.py:330-335): 10000 iterations at the run's learning rate
 size = s.size

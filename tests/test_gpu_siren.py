@@ -523,15 +523,24 @@ def test_mse_grad_fit_kernel(siren, count):
     loss = torch.zeros((), device="cuda")
     zero = torch.ones(21123, device="cuda")
     step = torch.full((), 4, dtype=torch.int64, device="cuda")
+    flag = torch.zeros((), dtype=torch.int32, device="cuda")
     siren._check(L.nmc_mse_grad_fit(y.data_ptr(), t.data_ptr(), s.data_ptr(), count, diff.data_ptr(), gy.data_ptr(), loss.data_ptr(),
-                                    zero.data_ptr(), zero.numel(), step.data_ptr(), siren._stream()))
+                                    zero.data_ptr(), zero.numel(), step.data_ptr(), 1.1e-10, flag.data_ptr(), siren._stream()))
+    assert flag.item() == 0   # the loss is far above the early-stop threshold
     ref = y - (t - s)
     assert torch.equal(diff, ref) and torch.allclose(gy, ref*(2.0/count), rtol=1e-6, atol=0)
     assert loss.item() == pytest.approx((ref.double()**2).mean().item(), rel=1e-5)
     assert zero.abs().max().item() == 0.0 and step.item() == 5
     siren._check(L.nmc_mse_grad_fit(y.data_ptr(), t.data_ptr(), None, count, diff.data_ptr(), gy.data_ptr(), loss.data_ptr(),
-                                    None, 0, None, siren._stream()))
+                                    None, 0, None, 0.0, None, siren._stream()))
     assert torch.equal(diff, y - t) and step.item() == 5
+    # early stop decided on the device: the flag is set at the threshold and stays set
+    siren._check(L.nmc_mse_grad_fit(y.data_ptr(), y.data_ptr(), None, count, diff.data_ptr(), gy.data_ptr(), loss.data_ptr(),
+                                    None, 0, None, 1.1e-10, flag.data_ptr(), siren._stream()))
+    assert loss.item() == 0.0 and flag.item() == 1
+    siren._check(L.nmc_mse_grad_fit(y.data_ptr(), t.data_ptr(), None, count, diff.data_ptr(), gy.data_ptr(), loss.data_ptr(),
+                                    None, 0, None, 1.1e-10, flag.data_ptr(), siren._stream()))
+    assert loss.item() > 1.0e-3 and flag.item() == 1
     # Adam with the device-side counter, not advanced by the update itself
     p = torch.randn(1000, generator=g, device="cuda"); grad = torch.randn(1000, generator=g, device="cuda")
     pr = p.clone().requires_grad_(True)
@@ -542,6 +551,38 @@ def test_mse_grad_fit_kernel(siren, count):
         pr.grad = grad.clone(); opt.step()
         step += 1
         siren._check(L.nmc_adam_update_device(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
-                                              step.data_ptr(), siren._stream()))
+                                              step.data_ptr(), None, siren._stream()))
         assert step.item() == it + 1
     assert torch.allclose(p, pr.detach(), rtol=1e-5, atol=1e-7)
+    before = p.clone()   # a set flag freezes the parameters, a clear one does not
+    siren._check(L.nmc_adam_update_device(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
+                                          step.data_ptr(), flag.data_ptr(), siren._stream()))
+    assert torch.equal(p, before)
+    flag.zero_()
+    siren._check(L.nmc_adam_update_device(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
+                                          step.data_ptr(), flag.data_ptr(), siren._stream()))
+    assert not torch.equal(p, before)
+
+
+def test_direct_fit_stops_moving_at_the_early_stop_threshold(siren):
+    """base.py:148 leaves the fit at the first iteration with loss <= 1.1e-10.  DirectFit takes that decision on the device (no host
+    round trip per iteration): a fit whose target is the network's own output -- the projection of examples/taylorgreen as
+    shipped, evaluated by ANOTHER kernel (tcgen05 at the chunk size, fp32 at the batch size), i.e. a loss of ~1e-13 and a
+    tiny non-zero gradient that Adam would normalise to full-size steps -- leaves the parameters exactly where they were."""
+    net = _net(siren, (2, 64, 6, 2), seed=5, tensor_cores=True)
+    x = _coords(4096, 2, seed=6)
+    big = _coords(32768, 2, seed=7); big[:4096] = x
+    with torch.no_grad():
+        target = net(big)[:4096].contiguous()      # 32768 samples: the tcgen05 forward; the training forward at 4096 is the fp32 kernel
+    fit = siren.DirectFit(net, 1e-5, None, max_batch=4096)
+    start = [p.detach().clone() for p in net.parameters()]
+    fit.stop_threshold = 1.1e-10
+    for _ in range(5):
+        fit.iterate(x, target)
+    assert 0.0 <= fit.loss.item() <= 1.1e-10 and fit.opt.stop_flag.item() == 1
+    assert all(torch.equal(a, b) for a, b in zip(start, net.parameters()))
+    fit.opt.reset(); fit.stop_threshold = 0.0       # without the gate Adam walks away at lr per step
+    for _ in range(5):
+        fit.iterate(x, target)
+    if fit.loss.item() > 0.0:
+        assert max((a - b).abs().max().item() for a, b in zip(start, net.parameters())) > 1e-5
