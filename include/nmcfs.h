@@ -171,6 +171,10 @@ uint64_t nmc_point_seed(uint64_t seed, uint64_t index);
 #define NMC_PROBE_SAMPLE_VOLUME 8       /* aux0 = R[n], aux1 = seeds as 2 x uint32 per entry; params: lambda  out: r, pdf, draws */
 #define NMC_PROBE_GREENS_FAST 9         /* fast-mode fp32 ball functions: aux0 = R[n], aux1 = r[n]  out: 10 floats */
 #define NMC_PROBE_SAMPLE_RADIUS_FAST 10 /* fast-mode inverse-CDF radial sampler: aux0 = R[n], aux1 = u[n]  out: r, pdf */
+/* the default mode's warp-packet tree queries (csrc/nmc_packet.cuh): 32 consecutive inputs form one packet */
+#define NMC_PROBE_STAR_RADIUS_PACKET 11 /* inputs and output of NMC_PROBE_STAR_RADIUS */
+#define NMC_PROBE_RAY_PACKET 12         /* inputs and output of NMC_PROBE_RAY */
+#define NMC_PROBE_CLOSEST_PACKET 13     /* in: pts            out: 2 floats: unsigned distance, signed distance */
 int nmc_probe(nmc_scene* scene, int kind, int64_t n, const float* pts, const float* aux0, const float* aux1,
 			  const float* aux2, const float* aux3, const float* params, float* out);
 

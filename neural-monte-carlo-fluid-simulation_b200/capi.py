@@ -15,6 +15,7 @@ MODE_DETERMINISTIC = 1
 PROBE_DIST_NEUMANN, PROBE_SIGNED_DIST_NEUMANN, PROBE_DIST_DIRICHLET, PROBE_INSIDE_DOMAIN = 0, 1, 2, 3
 PROBE_STAR_RADIUS, PROBE_RAY, PROBE_SOURCE, PROBE_GREENS, PROBE_SAMPLE_VOLUME = 4, 5, 6, 7, 8
 PROBE_GREENS_FAST, PROBE_SAMPLE_RADIUS_FAST = 9, 10
+PROBE_STAR_RADIUS_PACKET, PROBE_RAY_PACKET, PROBE_CLOSEST_PACKET = 11, 12, 13
 
 
 class SceneOpts(C.Structure):
@@ -248,8 +249,8 @@ class SceneHandle:
         return grid, cache[: min(nb.value, cache_cap)].copy(), nd.value
 
     def probe(self, kind, n, pts=None, aux0=None, aux1=None, aux2=None, aux3=None, params=None):
-        width = {PROBE_RAY: 2 + 2 * self.dim, PROBE_GREENS: 10, PROBE_GREENS_FAST: 10, PROBE_SAMPLE_VOLUME: 3,
-                 PROBE_SAMPLE_RADIUS_FAST: 2}.get(kind, 1)
+        width = {PROBE_RAY: 2 + 2 * self.dim, PROBE_RAY_PACKET: 2 + 2 * self.dim, PROBE_CLOSEST_PACKET: 2, PROBE_GREENS: 10,
+                 PROBE_GREENS_FAST: 10, PROBE_SAMPLE_VOLUME: 3, PROBE_SAMPLE_RADIUS_FAST: 2}.get(kind, 1)
         arrs = [None if a is None else _f32(a) for a in (pts, aux0, aux1, aux2, aux3)]
         par = _f32(list(params or []) + [0.0] * (4 - len(params or [])))
         out = np.zeros((n, width), np.float32)

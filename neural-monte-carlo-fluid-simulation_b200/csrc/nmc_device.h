@@ -27,5 +27,7 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 					   Counters* d_counters, float* d_stats12, int smCount, int maxDepth, cudaStream_t stream, FastLaunchInfo* info);
 cudaError_t launchProbeFast(const SceneView& S, int kind, long long n, const float* a0, const float* a1,
 							const float* params, float* d_out, cudaStream_t stream);
+cudaError_t launchProbePacket(const SceneView& S, int kind, long long n, const float* pts, const float* a0, const float* a1,
+							  const float* a2, const float* a3, const float* params, float* d_out, cudaStream_t stream);
 
 } // namespace nmc

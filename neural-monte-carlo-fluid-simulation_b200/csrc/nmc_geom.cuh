@@ -29,6 +29,7 @@ namespace nmc {
 struct SceneView {
 	int dim, nNodes, nPrims, nSilRefs;
 	const float4* nodes;
+	const float4* coneF;   // default mode: own normal cone per node (axis, cos halfAngle; scene_build.cpp conesFast)
 	const float4* prims;
 	const float4* primN;
 	const float4* nrmV;
@@ -113,8 +114,12 @@ NMC_HD bool coneOverlap(V3 axis, float halfAngle, V3 o, V3 lo, V3 hi, float dist
 //   inRange(pi/2, a - h, a + h), a = acos(c)  <=>  |asin c| <= h  <=>  |c| <= sin h      (h < pi/2)
 // and for the widened test  |c| <= sin(h + v) = sin h cos v + cos h sin v, "h + v >= pi/2" <=> cos(h + v) <= 0,
 // where (sin v, cos v) = (r/l, sqrt(1 - r^2/l^2)) or (d, s)/sqrt(d^2 + s^2).  cosH = cos(halfAngle) is stored per node.
-NMC_HD bool coneOverlapFast(V3 axis, float cosH, V3 o, V3 lo, V3 hi, float distToBox) {
-	if (cosH <= 0.0f || distToBox < kEps) return true;
+// slack (a small multiple of the silhouette precision) keeps the records the leaf test accepts through its precision band:
+// |dot(view, n)| <= precision counts as "on the face plane" there (isSilhouette), which an exact cone bound would cut off.
+NMC_HD bool coneOverlapFast(V3 axis, float w, V3 o, V3 lo, V3 hi, float distToBox, float ownSlack) {
+	if (w <= 0.0f || distToBox < kEps) return true;
+	const bool own = w > 3.0f; // scene_build.cpp conesFast: the reference's cone as cos, the default mode's own cone as 4 + cos
+	const float cosH = own ? w - 4.0f : w, slack = own ? ownSlack : 0.0f;
 	float sinH = sqrtf(fmaxf(0.0f, 1.0f - cosH*cosH));
 	V3 c = (lo + hi)*0.5f;
 	V3 vca = c - o;
@@ -122,7 +127,7 @@ NMC_HD bool coneOverlapFast(V3 axis, float cosH, V3 o, V3 lo, V3 hi, float distT
 	float il = rsqrtf(l2);
 	vca = vca*il;
 	float ca = fabsf(fminf(1.0f, fmaxf(-1.0f, dot(axis, vca))));
-	if (ca <= sinH) return true;
+	if (ca <= sinH + slack) return true;
 	V3 e = hi - c;
 	float r2 = dot(e, e);
 	float sv, cv;
@@ -136,8 +141,8 @@ NMC_HD bool coneOverlapFast(V3 axis, float cosH, V3 o, V3 lo, V3 hi, float distT
 		float ih = rsqrtf(d*d + sgap*sgap);
 		sv = d*ih; cv = sgap*ih;
 	}
-	if (cosH*cv - sinH*sv <= 0.0f) return true;
-	return ca <= sinH*cv + cosH*sv;
+	if (cosH*cv - sinH*sv <= slack) return true;
+	return ca <= sinH*cv + cosH*sv + slack;
 }
 
 // findClosestPointLineSegment (line_segments.inl:184-209)
@@ -440,7 +445,8 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 				V3 lo = xyz(S.nodes[4*c0]), hi = xyz(S.nodes[4*c0 + 1]);
 				boxSqDist(lo, hi, x, b0, tmp);
 #if defined(NMC_FAST_GEOM)
-				hit0 = b0 <= r2 && coneOverlapFast(xyz(k0), S.nodes[4*c0 + 3].w, x, lo, hi, b0);
+				const float4 f0 = S.coneF[c0];
+				hit0 = b0 <= r2 && coneOverlapFast(xyz(f0), f0.w, x, lo, hi, b0, 2.0f*precision);
 #else
 				hit0 = b0 <= r2 && coneOverlap<M>(xyz(k0), k0.w, x, lo, hi, b0);
 #endif
@@ -450,7 +456,8 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 				V3 lo = xyz(S.nodes[4*c1]), hi = xyz(S.nodes[4*c1 + 1]);
 				boxSqDist(lo, hi, x, b1, tmp);
 #if defined(NMC_FAST_GEOM)
-				hit1 = b1 <= r2 && coneOverlapFast(xyz(k1), S.nodes[4*c1 + 3].w, x, lo, hi, b1);
+				const float4 f1 = S.coneF[c1];
+				hit1 = b1 <= r2 && coneOverlapFast(xyz(f1), f1.w, x, lo, hi, b1, 2.0f*precision);
 #else
 				hit1 = b1 <= r2 && coneOverlap<M>(xyz(k1), k1.w, x, lo, hi, b1);
 #endif

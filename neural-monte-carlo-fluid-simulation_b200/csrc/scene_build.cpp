@@ -177,6 +177,45 @@ struct Builder {
 			cones(refs, refN, refFN, start + node.second, end);
 		}
 	}
+
+	// The default mode's own cones.  The reference takes the axis from the silhouettes' own normals (edge / vertex normals) and
+	// the half-angle from the face normals; on a closed triangle mesh seen from outside the two can point to opposite sides
+	// (half-angles near pi: nothing is ever culled and a closest-silhouette query visits a third of the tree -- measured on
+	// box_sphere).  Here the axis is the mean of the very face normals the silhouette test multiplies with the view direction
+	// (refFN, the records' n0 / n1), so a cone of half-angle < pi/2 around it is a valid bound for
+	// dot(view, n0)*dot(view, n1) < 0.  Only culling changes; the deterministic mode keeps the reference's cones.
+	void conesFast(const std::vector<int>& refs, const std::vector<std::array<P3, 2>>& refFN, int start, int end, std::vector<Q4>& out) {
+		const BuildNode& node = nodes[start];
+		P3 axis{0, 0, 0}; bool any = false, two = true;
+		for (int i = start; i < end; i++) for (int j = 0; j < nodes[i].nSil; j++) {
+			int r = nodes[i].silOffset + j;
+			axis = axis + refFN[r][0] + refFN[r][1];
+			two = two && silHasFace(sil[refs[r]], 0) && silHasFace(sil[refs[r]], 1);
+			any = true;
+		}
+		float cosH = any ? -1.0f : 2.0f;
+		if (any && two) {
+			float an = std::sqrt(dot(axis, axis));
+			if (an > FLT_EPSILON) {
+				axis = {axis.x/an, axis.y/an, axis.z/an};
+				cosH = 1.0f;
+				for (int i = start; i < end; i++) for (int j = 0; j < nodes[i].nSil; j++) {
+					int r = nodes[i].silOffset + j;
+					for (int k = 0; k < 2; k++) cosH = mn(cosH, dot(axis, refFN[r][k]));
+				}
+			}
+		}
+		// Where the reference's cone does cull (half-angle below pi/2: the 2D meshes) it is kept as it is, so that the default mode
+		// drops exactly what the reference drops -- its exact bound also cuts off records the leaf test would accept through its
+		// precision band, e.g. the nearly collinear vertices of a finely subdivided circle.  The own cone (stored as 4 + cos) is
+		// evaluated with a slack of two precisions and keeps them, as the reference's non-culling cone does.
+		if (node.halfAngle >= 0.0f && node.halfAngle < (float)M_PI_2) out[start] = {node.axis.x, node.axis.y, node.axis.z, std::cos(node.halfAngle)};
+		else out[start] = {axis.x, axis.y, axis.z, cosH > 0.0f && cosH <= 1.0f ? 4.0f + cosH : cosH};
+		if (node.nRefs == 0) {
+			conesFast(refs, refFN, start + 1, start + node.second, out);
+			conesFast(refs, refFN, start + node.second, end, out);
+		}
+	}
 };
 
 } // namespace
@@ -308,6 +347,8 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 		node.nSil = (int)refs.size() - node.silOffset;
 	}
 	B.cones(refs, refN, refFN, 0, (int)B.nodes.size());
+	out.coneF.assign(B.nodes.size(), Q4{0, 0, 0, 2.0f});
+	if (!B.nodes.empty()) B.conesFast(refs, refFN, 0, (int)B.nodes.size(), out.coneF);
 
 	// flatten
 	out.nNodes = (int)B.nodes.size(); out.nPrims = nP; out.nSilRefs = (int)refs.size(); out.maxDepth = B.maxDepth;

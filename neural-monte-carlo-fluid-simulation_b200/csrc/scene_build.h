@@ -12,6 +12,8 @@ struct FlatScene {
 	int dim = 0;
 	int nNodes = 0, nPrims = 0, nSilRefs = 0, maxDepth = 0;
 	std::vector<Q4> nodes;  // 4 per node
+	std::vector<Q4> coneF;  // 1 per node: the default mode's own normal cone (axis, w); w = 2: no silhouettes below, w <= 0: no culling,
+	                        // 0 < w <= 1: the reference's cone, w = cos(halfAngle); w > 4: own cone, w = 4 + cos(halfAngle) (scene_build.cpp conesFast)
 	std::vector<Q4> prims;  // 1 (2D) / 3 (3D) per primitive
 	std::vector<Q4> primN;  // 1 per primitive
 	std::vector<Q4> nrmV;   // 2 (2D) / 6 (3D) per primitive

@@ -111,7 +111,8 @@ cudaError_t launchSolutionEstimator(const SceneView& S, const SolverParams& o, c
 // ---- probes ---------------------------------------------------------------------------------------
 int probeWidth(int dim, int kind) {
 	switch (kind) {
-		case NMC_PROBE_RAY: return 2 + 2*dim;
+		case NMC_PROBE_RAY: case NMC_PROBE_RAY_PACKET: return 2 + 2*dim;
+		case NMC_PROBE_CLOSEST_PACKET: return 2;
 		case NMC_PROBE_GREENS: case NMC_PROBE_GREENS_FAST: return 10;
 		case NMC_PROBE_SAMPLE_VOLUME: return 3;
 		case NMC_PROBE_SAMPLE_RADIUS_FAST: return 2;

@@ -29,6 +29,7 @@
 #define NMC_BESSEL_TAB 1
 #endif
 #include "nmc_device.h"
+#include "nmc_packet.cuh"
 #include "bessel_table.h"
 #include "../../include/nmcfs.h"
 #include <cstdlib>
@@ -73,7 +74,8 @@ __device__ __forceinline__ void stackInit(LocalStack&, int*, int) {}
 // STATS: the per-point statistics record of the parity tests (variances, mean walk length) costs five more
 // accumulators per lane; the product path (stats12 == nullptr) runs the instantiation without them.
 // FLAT: 0 = tree traversals per step, 1 = flat scans over tables staged in shared memory (<= 128 primitives),
-// 2 = two-level flat scans over tables in global memory (larger meshes; the tree is still walked once per point)
+// 2 = two-level flat scans over tables in global memory (larger meshes; the tree is still walked once per point),
+// 3 = warp-packet tree traversals (nmc_packet.cuh): the default beyond the flat-scan limit
 template <int DIM, class STACK, int FLAT, bool STATS>
 __global__ void __launch_bounds__(kBlock, DIM == 2 ? NMC_MINB2 : NMC_MINB3)
 fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
@@ -150,8 +152,19 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 		// ---- per-point set-up (uniform across the warp): createSolutionGrid + estimationQuantity --------
 		const V3 x0 = mk(pts[(size_t)pi*DIM], pts[(size_t)pi*DIM + 1], DIM == 3 ? pts[(size_t)pi*DIM + 2] : 0.0f);
 		const float dDist = distDirichlet<DIM>(S, x0);
-		const float nDist = distNeumann<DIM>(S, stack, x0, false);
-		const bool inside = S.watertight ? insideDomain<DIM>(S, stack, x0) : true; // pseudo-normals (nrmV) stay in global memory
+		float nDist; bool inside = true;
+		if (FLAT == 3) { // one packet traversal (all lanes ask for x0) gives the distance and the pseudo-normal of the inside test
+			Hit h0; h0.d = kMaxF; h0.p = x0; h0.n = mk(0, 0, 0);
+			const bool f0 = S.nPrims > 0 && packetClosestPoint<DIM, WarpOps>(S, x0, kMaxF, S.watertight != 0, h0);
+			nDist = f0 ? h0.d : kMaxF;
+			if (S.watertight) { // insideDomain (fcpw_scene_loader.h:642-648)
+				const float d2s = (f0 && dot(x0 - h0.p, h0.n) > 0.0f ? 1.0f : -1.0f)*nDist;
+				inside = fabsf(dDist) < fabsf(d2s) ? dDist < 0.0f : d2s < 0.0f;
+			}
+		} else {
+			nDist = distNeumann<DIM>(S, stack, x0, false);
+			inside = S.watertight ? insideDomain<DIM>(S, stack, x0) : true; // pseudo-normals (nrmV) stay in global memory
+		}
 		// points inside the boundary mask are zeroed on output (demo/grid.h:174,227); do not walk them
 		const bool masked = fabsf(nDist) < o.boundaryDistanceMask;
 		const bool active = (inside || S.doubleSided) && !masked && nDist > 0.0f;
@@ -290,6 +303,46 @@ fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long lon
 				V3 dir = mk(0, 0, 0), ipt = pt, inrm = mk(0, 0, 0);
 				float idist = 0.0f, uRad = 0.0f, uRad2 = 0.0f, uRR = 1.0f;
 				bool hit = false, sliceActive = false, terminated = false, completed = false;
+				if (FLAT == 3) {
+					// packet traversals: the per-lane parts of the step run under the lane's own predicate, the two tree queries are
+					// made by the whole warp (lanes without a query pass a negative radius / ray length)
+					bool stepLive = false, flipOrient = false, needSil = false;
+					float dirichletDist = 0.0f, starR = 0.0f, dsil = 0.0f;
+					if (state == kWalking) {
+						cSteps++;
+						dirichletDist = distDirichlet<DIM>(S, pt);
+						if (!(dirichletDist > o.epsilonShell)) { terminated = true; completed = true; }
+						else {
+							stepLive = true;
+							if (S.doubleSided && onNeumann && flipNext) { normal = normal*-1.0f; flipOrient = true; } // :154-160
+							starR = dirichletDist;
+							needSil = o.stepsBeforeUsingMaximalSpheres > walkLength && o.minStarRadius <= dirichletDist && S.nPrims > 0;
+						}
+					}
+					const bool fsil = packetClosestSilhouette<DIM, WarpOps>(S, pt, needSil ? (dirichletDist < kMaxF ? dirichletDist*dirichletDist : kMaxF) : -1.0f,
+						!flipOrient, o.minStarRadius*o.minStarRadius, o.silhouettePrecision, dsil);
+					V3 ro = pt;
+					if (stepLive) {
+						if (o.stepsBeforeUsingMaximalSpheres > walkLength && o.minStarRadius <= dirichletDist) { // starRadius(), fcpw_scene_loader.h:621-641
+							starR = fsil ? fmaxf(dsil, o.minStarRadius) : fmaxf(dirichletDist, o.minStarRadius);
+							starR = fmaxf(kShrink*starR, o.minStarRadius);
+						}
+						bl.update(starR);
+						float u0 = rng.nextFloat(), u1 = rng.nextFloat();
+						uRad = rng.nextFloat(); uRad2 = rng.nextFloat(); uRR = rng.nextFloat();
+						dir = sphereDir<DIM, M>(u0, u1);
+						if (onNeumann && dot(normal, dir) > 0.0f) dir = dir*-1.0f;
+						if (onNeumann) ro = offsetPoint<DIM>(pt, neg(normal));
+						if (DIM == 2) { ro.z = 0.0f; dir.z = 0.0f; }
+					}
+					Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
+					hit = packetRay<DIM, WarpOps>(S, ro, dir, stepLive && S.nPrims > 0 ? starR : -1.0f, h);
+					if (stepLive) {
+						if (hit) { ipt = h.p; inrm = h.n; idist = h.d; }
+						else { ipt = ro + starR*dir; idist = starR; }
+						sliceActive = !o.ignoreSource;
+					}
+				} else
 				if (state == kWalking) {
 					cSteps++;
 					float dirichletDist = distDirichlet<DIM>(S, pt);
@@ -479,13 +532,16 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	// 3D only: on box_sphere (1292 triangles) the two-level scan runs 2.6e8 walks/s against 4.7e7 for the per-lane tree
 	// traversal; in 2D (channel_circle, 1184 segments) the tree is the faster of the two (8.7e8 against 4.1e8: long merged
 	// wall segments make poor group boxes) and stays the default
-	static const bool bigFlat = [] { const char* e = getenv("NMC_BIG_MESH"); return !(e && e[0] == 't'); }();
-	const bool flat2 = !flat && bigFlat && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
-	if (flat2) quads = 0; // FLAT == 2 stages nothing (see the kernel)
+	// Default: warp-packet traversals of the tree (FLAT == 3, nmc_packet.cuh): one traversal per warp with warp-uniform node loads
+	// and a register stack; NMC_BIG_MESH=flat2 / tree select the two older paths.
+	static const int bigMode = [] { const char* e = getenv("NMC_BIG_MESH"); return !e ? 3 : e[0] == 't' ? 0 : e[0] == 'f' ? 2 : 3; }();
+	const bool packet = !flat && bigMode == 3 && maxDepth + 2 <= NMC_STACK;
+	const bool flat2 = !flat && bigMode == 2 && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
+	if (flat2 || packet) quads = 0; // FLAT == 2 / 3 stage nothing (see the kernel)
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
 	// traversal stacks: depth of the tree + 2 entries per thread in shared memory when that is small
-	int stackSlots = maxDepth + 3;
+	int stackSlots = packet ? 0 : maxDepth + 3; // the packet stack lives in registers
 	bool smemStack = stackSlots <= 24;
 	if (!smemStack) stackSlots = 0; // LocalStack: the first-ball chunks sit right behind the staged scene
 	size_t smem = (stageQuads ? bytes : 0) + (size_t)stackSlots*kBlock*8 + (size_t)kWarps*kFbFields*32*sizeof(float);
@@ -493,6 +549,7 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 #define NMC_PICK(ST) do { \
 		if (flat) kern = dim == 2 ? fastKernel<2, StridedStack, 1, ST> : fastKernel<3, StridedStack, 1, ST>; \
 		else if (flat2) kern = dim == 2 ? fastKernel<2, StridedStack, 2, ST> : fastKernel<3, StridedStack, 2, ST>; \
+		else if (packet) kern = dim == 2 ? fastKernel<2, StridedStack, 3, ST> : fastKernel<3, StridedStack, 3, ST>; \
 		else if (dim == 2) kern = smemStack ? fastKernel<2, StridedStack, 0, ST> : fastKernel<2, LocalStack, 0, ST>; \
 		else kern = smemStack ? fastKernel<3, StridedStack, 0, ST> : fastKernel<3, LocalStack, 0, ST>; } while (0)
 	if (d_stats12) NMC_PICK(true); else NMC_PICK(false);
@@ -541,6 +598,49 @@ cudaError_t launchProbeFast(const SceneView& S, int kind, long long n, const flo
 	unsigned grid = (unsigned)((n + 127)/128);
 	if (S.dim == 2) probeFastKernel<2><<<grid, 128, 0, stream>>>(kind, n, a0, a1, params, d_out);
 	else probeFastKernel<3><<<grid, 128, 0, stream>>>(kind, n, a0, a1, params, d_out);
+	return cudaGetLastError();
+}
+
+// ---- packet probes: the FLAT == 3 kernel's tree queries, 32 consecutive inputs per warp -----------------------------
+template <int DIM>
+__global__ void probePacketKernel(SceneView S, int kind, long long n, const float* __restrict__ pts, const float* __restrict__ a0,
+								  const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ a3,
+								  const float* __restrict__ params, float* __restrict__ out) {
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	const bool on = i < n; // lanes past the end take part in the traversal without a query
+	const V3 x = on ? mk(pts[i*DIM], pts[i*DIM + 1], DIM == 3 ? pts[i*DIM + 2] : 0.0f) : mk(0, 0, 0);
+	if (kind == NMC_PROBE_STAR_RADIUS_PACKET) { // starRadius(), nmc_geom.cuh
+		const float minR = params[0], prec = params[1]; const bool flipOrient = params[2] != 0.0f;
+		const float maxR = on ? a0[i] : 0.0f;
+		const bool ask = on && !(minR > maxR) && S.nPrims > 0;
+		float d = 0.0f;
+		const bool f = packetClosestSilhouette<DIM, WarpOps>(S, x, ask ? (maxR < kMaxF ? maxR*maxR : kMaxF) : -1.0f, !flipOrient, minR*minR, prec, d);
+		if (on) out[i] = minR > maxR ? maxR : f ? fmaxf(d, minR) : fmaxf(maxR, minR);
+	} else if (kind == NMC_PROBE_RAY_PACKET) { // intersectNeumann(), nmc_geom.cuh
+		V3 nn = mk(0, 0, 0), d = mk(0, 0, 0);
+		if (on) { nn = mk(a0[i*DIM], a0[i*DIM + 1], DIM == 3 ? a0[i*DIM + 2] : 0.0f); d = mk(a1[i*DIM], a1[i*DIM + 1], DIM == 3 ? a1[i*DIM + 2] : 0.0f); }
+		V3 o = on && a3[i] != 0.0f ? offsetPoint<DIM>(x, neg(nn)) : x;
+		if (DIM == 2) { o.z = 0.0f; d.z = 0.0f; }
+		Hit h; h.d = kMaxF; h.p = mk(0, 0, 0); h.n = mk(0, 0, 0);
+		const bool hit = packetRay<DIM, WarpOps>(S, o, d, on && S.nPrims > 0 ? a2[i] : -1.0f, h);
+		if (on) {
+			float* r = out + i*(2 + 2*DIM);
+			r[0] = hit ? 1.0f : 0.0f; r[1] = h.d;
+			r[2] = h.p.x; r[3] = h.p.y; if (DIM == 3) r[4] = h.p.z;
+			r[2 + DIM] = h.n.x; r[3 + DIM] = h.n.y; if (DIM == 3) r[4 + DIM] = h.n.z;
+		}
+	} else {
+		Hit h; h.d = kMaxF; h.p = x; h.n = mk(0, 0, 0);
+		const bool f = packetClosestPoint<DIM, WarpOps>(S, x, on && S.nPrims > 0 ? kMaxF : -1.0f, true, h);
+		if (on) { out[2*i] = f ? h.d : kMaxF; out[2*i + 1] = f ? (dot(x - h.p, h.n) > 0.0f ? 1.0f : -1.0f)*h.d : kMaxF; }
+	}
+}
+cudaError_t launchProbePacket(const SceneView& S, int kind, long long n, const float* pts, const float* a0, const float* a1,
+							  const float* a2, const float* a3, const float* params, float* d_out, cudaStream_t stream) {
+	if (n <= 0) return cudaSuccess;
+	unsigned grid = (unsigned)((n + 127)/128);
+	if (S.dim == 2) probePacketKernel<2><<<grid, 128, 0, stream>>>(S, kind, n, pts, a0, a1, a2, a3, params, d_out);
+	else probePacketKernel<3><<<grid, 128, 0, stream>>>(S, kind, n, pts, a0, a1, a2, a3, params, d_out);
 	return cudaGetLastError();
 }
 

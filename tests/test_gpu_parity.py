@@ -224,8 +224,8 @@ def test_size_independent_properties_at_scale(pkg, mode):
 
 @pytest.mark.parametrize("n_circle", [24, 128, 400])
 def test_mesh_size_regimes_of_the_default_mode(pkg, oracle_lib, tmp_path, n_circle):
-    """The default mode picks its data path by mesh size: flat tables in shared memory (<= 128 primitives),
-    tree + staged records + stacks in shared memory (here > 48 KB, the opt-in range), tree through L1/L2.
+    """The default mode picks its data path by mesh size: flat tables in shared memory (<= 128 primitives), beyond that
+    warp-packet traversals of the tree through L1/L2 (csrc/nmc_packet.cuh).
     Each regime is checked against the oracle: bit-exact star radii and statistically equal estimates."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("mss", os.path.join(util.GOLDEN, "make_synthetic_scenes.py"))
@@ -255,6 +255,52 @@ def test_mesh_size_regimes_of_the_default_mode(pkg, oracle_lib, tmp_path, n_circ
     for d in range(2):
         zg = (s[both, 2 + d] - ref[both, 2 + d])/np.sqrt(s[both, 5 + d]/nf + ref[both, 5 + d]/nr + 1e-30)
         assert (np.abs(zg) < 3).mean() >= 0.97 and abs(zg.mean()) < 0.4
+
+
+@pytest.mark.parametrize("case", ["channel_circle", "box_sphere", "karman", "karman3d"])
+def test_warp_packet_tree_queries_on_the_device(pkg, case):
+    """The default mode's big-mesh path (csrc/nmc_packet.cuh: one tree traversal per warp, per-lane radii) through the packet
+    probes: every lane must get what the deterministic kernel's private traversal gets, on coherent packets (32 queries in one
+    small ball, the walk kernel's situation) and incoherent ones (32 queries anywhere), with idle lanes at the end.  The fast
+    file is compiled with -use_fast_math (approximate divisions), hence 1e-5 relative instead of bits."""
+    cfg = util.load_case(case)
+    dim = cfg["dim"]
+    sc = _scene(pkg, cfg)
+    lo, hi = sc.bbox()
+    ext = float((hi - lo).max())
+    rng = np.random.default_rng(31)
+    far = util.random_points(lo, hi, 4096, seed=5)
+    centres = util.random_points(lo, hi, 128, seed=6)
+    near = (np.repeat(centres, 32, 0) + (rng.random((4096, dim), dtype=np.float32) - 0.5)*0.06*ext).astype(np.float32)
+    q = np.ascontiguousarray(np.concatenate([far, near])[:-13])
+    n = len(q)
+    max_r = (rng.random(n, dtype=np.float32)*ext).astype(np.float32); max_r[::7] = np.float32(3.0e38)
+    for flip in (0.0, 1.0):
+        want = sc.handle.probe(pkg.capi.PROBE_STAR_RADIUS, n, q, aux0=max_r, params=[1e-3, 1e-3, flip])
+        got = sc.handle.probe(pkg.capi.PROBE_STAR_RADIUS_PACKET, n, q, aux0=max_r, params=[1e-3, 1e-3, flip])
+        rel = np.abs(got - want)/np.maximum(np.abs(want), 1e-6)
+        assert (rel < 1e-5).mean() >= 0.999, (case, flip, (rel < 1e-5).mean(), rel.max())
+    u = rng.random((n, 2), dtype=np.float32)
+    if dim == 2:
+        a = 2*np.pi*u[:, 0]; d = np.stack([np.cos(a), np.sin(a)], 1).astype(np.float32)
+    else:
+        z = 1 - 2*u[:, 0]; r = np.sqrt(np.maximum(0, 1 - z*z)); a = 2*np.pi*u[:, 1]
+        d = np.stack([r*np.cos(a), r*np.sin(a), z], 1).astype(np.float32)
+    tmax = (rng.random(n, dtype=np.float32)*ext).astype(np.float32)
+    nrm = np.zeros_like(q); onb = np.zeros(n, np.float32)
+    want = sc.handle.probe(pkg.capi.PROBE_RAY, n, q, aux0=nrm, aux1=d, aux2=tmax, aux3=onb)
+    got = sc.handle.probe(pkg.capi.PROBE_RAY_PACKET, n, q, aux0=nrm, aux1=d, aux2=tmax, aux3=onb)
+    assert want[:, 0].sum() > 100
+    assert (got[:, 0] == want[:, 0]).mean() >= 0.9995, case
+    both = (got[:, 0] > 0) & (want[:, 0] > 0)
+    assert (np.abs(got[both, 1] - want[both, 1]) <= 2e-5*np.abs(want[both, 1]) + 1e-6).all(), case
+    assert (np.abs(got[both, 2:2 + dim] - want[both, 2:2 + dim]) <= 1e-4*ext).all(), case
+    assert (np.abs(got[both, 2 + dim:] - want[both, 2 + dim:]).max(1) < 1e-5).mean() >= 0.999, case   # equidistant hits may pick the neighbour
+    cl = sc.handle.probe(pkg.capi.PROBE_CLOSEST_PACKET, n, q)
+    dn = sc.handle.probe(pkg.capi.PROBE_DIST_NEUMANN, n, q)
+    sd = sc.handle.probe(pkg.capi.PROBE_SIGNED_DIST_NEUMANN, n, q)
+    assert (np.abs(cl[:, 0] - dn) <= 1e-5*np.abs(dn) + 1e-7).mean() >= 0.9999, case
+    assert (np.sign(cl[:, 1]) == np.sign(sd)).mean() >= 0.999, case
 
 
 def test_edge_cases(pkg):

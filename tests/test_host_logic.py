@@ -463,7 +463,7 @@ def emu_fast():
     srcs = [os.path.join(d, "emu_fast.cpp"), os.path.join(PKG_DIR, "csrc", "scene_build.cpp")]
     deps = srcs + [os.path.join(PKG_DIR, "csrc", f) for f in os.listdir(os.path.join(PKG_DIR, "csrc")) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so] + srcs)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-o", so] + srcs)
     L = C.CDLL(so)
     L.emuf_scene_create.restype = C.c_void_p
     return L
@@ -508,6 +508,66 @@ def test_default_mode_tree_queries_equal_the_oracle(emu_fast, oracle_lib, tmp_pa
         both = (out[:, 0] > 0) & (ray[:, 0] > 0)
         if both.any():
             assert (np.abs(out[both, 1] - ray[both, 1]) <= 2e-5*np.abs(ray[both, 1]) + 1e-6).all(), name
+        emu_fast.emuf_scene_destroy(h); osc.close()
+
+
+def _sphere_dirs(rng, n, dim):
+    u = rng.random((n, 2), dtype=np.float32)
+    if dim == 2:
+        a = 2*np.pi*u[:, 0]
+        return np.stack([np.cos(a), np.sin(a)], 1).astype(np.float32)
+    z = 1 - 2*u[:, 0]; r = np.sqrt(np.maximum(0, 1 - z*z)); a = 2*np.pi*u[:, 1]
+    return np.stack([r*np.cos(a), r*np.sin(a), z], 1).astype(np.float32)
+
+
+@pytest.mark.timeout(600)
+def test_warp_packet_traversals_equal_the_private_ones(emu_fast, oracle_lib, tmp_path):
+    """csrc/nmc_packet.cuh (the default mode's tree queries on meshes beyond the flat-scan limit) compiled for the host, as
+    packets of one query and as packets of 32 queries run by 32 lockstep threads (ballots and the lane-distributed stack
+    behave as on the device): every lane must get what its private traversal (nmc_geom.cuh) gets -- star radius, closest hit,
+    distance and pseudo-normal side -- on coherent packets (32 queries inside one small ball: the kernel's situation) and on
+    incoherent ones (32 queries anywhere in the box: the children vote is split, lanes idle)."""
+    rng = np.random.default_rng(11)
+    names = ("channel_circle", "box_sphere", "karman", "karman3d")
+    scenes = [(c, util.load_case(c)) for c in names] + [(n, cfg) for n, _, cfg in util.random_meshes(tmp_path)][:4]
+    for name, cfg in scenes:
+        dim, sc = cfg["dim"], cfg["scene"]
+        v, p = oracle_lib.load_obj(sc["boundary"], dim, False)
+        src = util.source_grid(dim); shp = list(src.shape) + [1]*(3 - dim)
+        h = C.c_void_p(emu_fast.emuf_scene_create(dim, _fp(v), len(v), p.ctypes.data_as(C.POINTER(C.c_int)), len(p), _fp(src), shp[0], shp[1], shp[2],
+                                                  C.c_float(sc.get("absorptionCoeff", 0.0)), int(sc.get("isWatertight", False)), int(sc.get("isDoubleSided", False))))
+        lo = np.array([v[:, k].min() for k in range(dim)], np.float32); hi = np.array([v[:, k].max() for k in range(dim)], np.float32)
+        ext = float((hi - lo).max())
+        # 20 incoherent packets + 20 coherent ones (a centre and 31 points within 3 % of the box of it); 13 queries short of a whole packet
+        far = util.random_points(lo, hi, 640, seed=5, margin=0.05)
+        centres = util.random_points(lo, hi, 20, seed=6, margin=0.05)
+        near = (np.repeat(centres, 32, 0) + (rng.random((640, dim), dtype=np.float32) - 0.5)*0.06*ext).astype(np.float32)
+        q = np.ascontiguousarray(np.concatenate([far, near])[:-13])
+        n = len(q)
+        max_r = (rng.random(n, dtype=np.float32)*ext).astype(np.float32); max_r[::7] = np.float32(3.0e38)
+        for flip in (0, 1):
+            want = np.zeros(n, np.float32); one = np.zeros(n, np.float32); warp = np.zeros(n, np.float32)
+            emu_fast.emuf_star_radius(h, _fp(q), n, C.c_float(1e-3), _fp(max_r), C.c_float(1e-3), flip, _fp(want))
+            emu_fast.emuf_star_radius_packet(h, _fp(q), n, C.c_float(1e-3), _fp(max_r), C.c_float(1e-3), flip, _fp(one))
+            emu_fast.emuf_star_radius_warp(h, _fp(q), n, C.c_float(1e-3), _fp(max_r), C.c_float(1e-3), flip, _fp(warp))
+            assert np.array_equal(one, want), (name, flip, np.abs(one - want).max())
+            assert np.array_equal(warp, want), (name, flip, np.abs(warp - want).max())
+        d = _sphere_dirs(rng, n, dim)
+        tmax = (rng.random(n, dtype=np.float32)*ext).astype(np.float32)
+        want = np.zeros((n, 2), np.float32); one = np.zeros((n, 2), np.float32); warp = np.zeros((n, 2), np.float32)
+        emu_fast.emuf_rays(h, _fp(q), _fp(d), _fp(tmax), n, _fp(want))
+        emu_fast.emuf_rays_packet(h, _fp(q), _fp(d), _fp(tmax), n, _fp(one))
+        emu_fast.emuf_rays_warp(h, _fp(q), _fp(d), _fp(tmax), n, _fp(warp))
+        assert want[:, 0].sum() > 20, name
+        assert np.array_equal(one, want) and np.array_equal(warp, want), name
+        one = np.zeros((n, 2), np.float32); warp = np.zeros((n, 2), np.float32)
+        emu_fast.emuf_closest_packet(h, _fp(q), n, _fp(one))
+        emu_fast.emuf_closest_warp(h, _fp(q), n, _fp(warp))
+        osc = oracle_lib.OracleScene(dim, sc, src)
+        assert np.array_equal(one[:, 0], osc.dist_neumann(q)), name
+        sd = osc.dist_neumann(q, signed=True)
+        assert (one[:, 1] == sd).mean() >= 0.999, name      # an equidistant pair of primitives may resolve to the other pseudo-normal
+        assert np.array_equal(warp[:, 0], one[:, 0]) and (warp[:, 1] == one[:, 1]).mean() >= 0.999, name
         emu_fast.emuf_scene_destroy(h); osc.close()
 
 
