@@ -382,6 +382,15 @@ NMC_HD bool isSilhouette(float concavity, V3 n0, V3 n1, V3 viewDir, float d, boo
 	if (fabsf(dot1) <= precision) return sign*dot0 > precision;
 	return dot0*dot1 < 0.0f;
 }
+// Cheap necessary condition for isSilhouette() on an edge with two faces (default mode): the face normals are perpendicular
+// to the edge, so n.(x - pa) = d*dot(view, n) for the closest point's view direction whatever that point is.  The edge can only
+// pass if x sees the two face planes from opposite sides, or sits within the precision band of one of them
+// (|dot| <= precision and d <= sqrt(r2)), or within `precision` of the edge itself (|s| <= d <= precision).  On a smooth
+// obstacle almost every record of the visited leaves fails this before the closest point (a division, a square root) is computed.
+NMC_HD bool silhouetteCandidate(V3 n0, V3 n1, V3 rel, float precision, float r2) {
+	const float s0 = dot(n0, rel), s1 = dot(n1, rel);
+	return s0*s1 < 0.0f || fminf(fabsf(s0), fabsf(s1)) <= precision*fmaxf(1.0f, sqrtf(r2));
+}
 // closest silhouette point: Sbvh::findClosestSilhouettePointFromNode (sbvh.inl:1093-1255) with
 // SilhouetteVertex/Edge::findClosestSilhouettePoint (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143)
 template <int DIM, class M, class Stack>
@@ -421,11 +430,14 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 					flags = asInt(s0.w); id = asInt(s1.w);
 					if (id == lastId) continue;
 					if (sqMinR >= r2) continue;
+					float4 s2 = S.sils[4*ri + 2];
+					n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.sils[4*ri + 3]);
+#if defined(NMC_FAST_GEOM)
+					if ((flags & 3) == 3 && !silhouetteCandidate(n0, n1, x - xyz(s0), precision, r2)) continue;
+#endif
 					V3 pt; float t;
 					d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
 					viewDir = x - pt;
-					float4 s2 = S.sils[4*ri + 2];
-					n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.sils[4*ri + 3]);
 				}
 				if (d*d > r2) continue;
 				bool isSil = (flags & 3) != 3;

@@ -3,10 +3,10 @@
 // The lanes of a warp work on walks of ONE query point (wost_fast.cu), so their queries sit within a ball or two of each
 // other.  Instead of 32 private traversals (32 stacks, 32 divergent node fetches per trip, leaf and inner-node code
 // serialised) the warp walks the tree once: a node is entered when ANY lane can still improve inside it, every node record is
-// fetched with one warp-uniform load (a single L1 transaction, broadcast), the stack holds node indices only and lives in
-// registers spread over the lanes (entry i in lane i & 31, read back with a shuffle), and the two children are ordered by a
-// vote of the lanes that reach both.  Every lane keeps its own search radius / ray length, so each lane gets exactly the
-// result of its private traversal (Sbvh::findClosestSilhouettePointFromNode sbvh.inl:1093-1255, intersectFromNode :538-683,
+// fetched with one warp-uniform load (a single L1 transaction, broadcast), the stack (node index + the lanes that asked for
+// the node) lives in registers spread over the lanes (entry i in lane i & 31, read back with a shuffle), and the two children
+// are ordered by a vote of the lanes that reach both.  Every lane keeps its own search radius / ray length and only works on
+// nodes its own tests selected, so each lane gets exactly the result of its private traversal (Sbvh::findClosestSilhouettePointFromNode sbvh.inl:1093-1255, intersectFromNode :538-683,
 // findClosestPointFromNode :948-1074) -- only ties between equidistant records may resolve differently.
 // The reference's own wide traversal (mbvh.inl:702-818, 1661-1810) vectorises over the four children of one query; here the
 // vector lanes are the queries.
@@ -21,15 +21,20 @@ namespace nmc {
 
 #if defined(__CUDACC__)
 struct WarpOps {
-	int s0 = 0, s1 = 0; // stack entries sp & 31 of the first / second 32 slots (NMC_STACK = 64 bounds the tree depth)
+	// stack entry sp (node index + the lanes that asked for it) lives in lane sp & 31: first / second 32 slots (NMC_STACK = 64 bounds the depth)
+	int s0 = 0, s1 = 0; unsigned q0 = 0, q1 = 0;
 	__device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 	__device__ __forceinline__ static unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 	__device__ __forceinline__ static int popc(unsigned m) { return __popc(m); }
-	__device__ __forceinline__ void put(int sp, int node) {
-		const bool mine = (int)(threadIdx.x & 31) == (sp & 31);
-		if (sp < 32) s0 = mine ? node : s0; else s1 = mine ? node : s1;
+	__device__ __forceinline__ static bool mine(unsigned m) { return (m >> (threadIdx.x & 31)) & 1u; }
+	__device__ __forceinline__ void put(int sp, int node, unsigned lanes) {
+		const bool here = (int)(threadIdx.x & 31) == (sp & 31);
+		if (sp < 32) { s0 = here ? node : s0; q0 = here ? lanes : q0; } else { s1 = here ? node : s1; q1 = here ? lanes : q1; }
 	}
-	__device__ __forceinline__ int get(int sp) const { return __shfl_sync(0xffffffffu, sp < 32 ? s0 : s1, sp & 31); }
+	__device__ __forceinline__ int get(int sp, unsigned& lanes) const {
+		lanes = __shfl_sync(0xffffffffu, sp < 32 ? q0 : q1, sp & 31);
+		return __shfl_sync(0xffffffffu, sp < 32 ? s0 : s1, sp & 31);
+	}
 };
 #define NMC_PK __device__ __forceinline__
 #define NMC_PKI __device__ __forceinline__
@@ -38,15 +43,18 @@ struct WarpOps {
 #define NMC_PKI inline
 #endif
 struct HostLane {
-	int st[NMC_STACK + 2];
+	int st[NMC_STACK + 2]; unsigned q[NMC_STACK + 2];
 	static bool any(bool p) { return p; }
 	static unsigned ballot(bool p) { return p ? 1u : 0u; }
 	static int popc(unsigned m) { return (int)(m & 1u); }
-	void put(int sp, int node) { st[sp] = node; }
-	int get(int sp) const { return st[sp]; }
+	static bool mine(unsigned m) { return m & 1u; }
+	void put(int sp, int node, unsigned lanes) { st[sp] = node; q[sp] = lanes; }
+	int get(int sp, unsigned& lanes) const { lanes = q[sp]; return st[sp]; }
 };
 
-// pushes the children the packet still needs, the one most lanes prefer on top
+// pushes the children the packet still needs, the one most lanes prefer on top.  Every entry carries the lanes that asked for
+// it: a lane works on a node only if its OWN tests led there, exactly as in its private traversal -- it matters for the
+// silhouette query, where the cone test also drops records the leaf test would accept through its precision band.
 template <class W>
 NMC_PKI void packetPush(W& w, int& sp, int c0, int c1, bool hit0, bool hit1, bool prefer1) {
 	const unsigned m0 = W::ballot(hit0), m1 = W::ballot(hit1);
@@ -54,10 +62,10 @@ NMC_PKI void packetPush(W& w, int& sp, int c0, int c1, bool hit0, bool hit1, boo
 		// lanes that reach one child only vote for it
 		const unsigned v1 = W::ballot(hit1 && (!hit0 || prefer1));
 		const bool first1 = 2*W::popc(v1) > W::popc(m0 | m1);
-		w.put(++sp, first1 ? c0 : c1);
-		w.put(++sp, first1 ? c1 : c0);
-	} else if (m0) w.put(++sp, c0);
-	else if (m1) w.put(++sp, c1);
+		w.put(++sp, first1 ? c0 : c1, first1 ? m0 : m1);
+		w.put(++sp, first1 ? c1 : c0, first1 ? m1 : m0);
+	} else if (m0) w.put(++sp, c0, m0);
+	else if (m1) w.put(++sp, c1, m1);
 }
 
 // closest silhouette point within sqrt(r2) of x; false when there is none (dOut untouched)
@@ -70,12 +78,14 @@ NMC_PK bool packetClosestSilhouette(const SceneView& S, V3 x, float r2, bool fli
 	float b0, b1, tmp;
 	bool found = false; int lastId = -1;
 	int sp = 0;
-	w.put(0, 0);
+	w.put(0, 0, 0xffffffffu);
 	while (sp >= 0) {
-		const int ni = w.get(sp); sp--;
+		unsigned asked;
+		const int ni = w.get(sp, asked); sp--;
 		const float4 na = S.nodes[4*ni], nb = S.nodes[4*ni + 1];
 		boxSqDist(xyz(na), xyz(nb), x, b0, tmp);
-		if (!W::any(live && b0 <= r2)) continue; // radii shrank since the node was pushed
+		const bool here = W::mine(asked) && live && b0 <= r2; // the radius may have shrunk since the node was pushed
+		if (!W::any(here)) continue;
 		const int nRefs = asInt(na.w);
 		if (nRefs > 0) {
 			const float4 nd = S.nodes[4*ni + 3];
@@ -87,18 +97,19 @@ NMC_PK bool packetClosestSilhouette(const SceneView& S, V3 x, float r2, bool fli
 					const float4 s0 = S.sils[2*ri], s1 = S.sils[2*ri + 1];
 					flags = asInt(s0.z); id = asInt(s0.w);
 					viewDir = x - mk(s0.x, s0.y, 0.0f);
-					if (!live || id == lastId || dot(viewDir, viewDir) > r2) continue; // reject on the squared distance before paying for the sqrt
+					if (!here || !live || id == lastId || dot(viewDir, viewDir) > r2) continue; // reject on the squared distance before paying for the sqrt
 					d = norm(viewDir);
 					n0 = mk(s1.x, s1.y, 0.0f); n1 = mk(s1.z, s1.w, 0.0f);
 					concavity = n0.x*n1.y - n1.x*n0.y;
 				} else {
 					const float4 s0 = S.sils[4*ri], s1 = S.sils[4*ri + 1], s2 = S.sils[4*ri + 2];
 					flags = asInt(s0.w); id = asInt(s1.w);
+					n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.sils[4*ri + 3]);
+					if (!here || !live || id == lastId) continue;
+					if ((flags & 3) == 3 && !silhouetteCandidate(n0, n1, x - xyz(s0), precision, r2)) continue;
 					V3 pt; float t;
 					d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
 					viewDir = x - pt;
-					n0 = xyz(s2); concavity = s2.w; n1 = xyz(S.sils[4*ri + 3]);
-					if (!live || id == lastId) continue;
 				}
 				if (d*d > r2) continue;
 				bool isSil = (flags & 3) != 3;
@@ -118,13 +129,13 @@ NMC_PK bool packetClosestSilhouette(const SceneView& S, V3 x, float r2, bool fli
 			if (k0.w != 2.0f) { // the subtree holds silhouettes
 				const V3 lo = xyz(S.nodes[4*c0]), hi = xyz(S.nodes[4*c0 + 1]);
 				boxSqDist(lo, hi, x, b0, tmp);
-				hit0 = live && b0 <= r2 && coneOverlapFast(xyz(k0), k0.w, x, lo, hi, b0, 2.0f*precision);
+				hit0 = here && live && b0 <= r2 && coneOverlapFast(xyz(k0), k0.w, x, lo, hi, b0, 2.0f*precision);
 			}
 			const float4 k1 = S.coneF[c1];
 			if (k1.w != 2.0f) {
 				const V3 lo = xyz(S.nodes[4*c1]), hi = xyz(S.nodes[4*c1 + 1]);
 				boxSqDist(lo, hi, x, b1, tmp);
-				hit1 = live && b1 <= r2 && coneOverlapFast(xyz(k1), k1.w, x, lo, hi, b1, 2.0f*precision);
+				hit1 = here && live && b1 <= r2 && coneOverlapFast(xyz(k1), k1.w, x, lo, hi, b1, 2.0f*precision);
 			}
 			packetPush(w, sp, c0, c1, hit0, hit1, b1 < b0);
 		}
@@ -141,11 +152,12 @@ NMC_PK bool packetRay(const SceneView& S, V3 o, V3 dir, float tMax, Hit& out) {
 	float b0, b1, b2, b3;
 	bool hitAny = false;
 	int sp = 0;
-	w.put(0, 0);
+	w.put(0, 0, 0xffffffffu);
 	while (sp >= 0) {
-		const int ni = w.get(sp); sp--;
+		unsigned asked;
+		const int ni = w.get(sp, asked); sp--;
 		const float4 na = S.nodes[4*ni], nb = S.nodes[4*ni + 1];
-		const bool reach = tMax >= 0.0f && boxRay(xyz(na), xyz(nb), o, invD, tMax, b0, b1);
+		const bool reach = W::mine(asked) && tMax >= 0.0f && boxRay(xyz(na), xyz(nb), o, invD, tMax, b0, b1);
 		if (!W::any(reach)) continue;
 		const int nRefs = asInt(na.w);
 		if (nRefs > 0) {
@@ -182,12 +194,13 @@ NMC_PK bool packetClosestPoint(const SceneView& S, V3 x, float r2, bool wantNorm
 		if (r2 >= 0.0f && b0 <= r2) r2 = minS(r2, b1);
 	}
 	int sp = 0;
-	w.put(0, 0);
+	w.put(0, 0, 0xffffffffu);
 	while (sp >= 0) {
-		const int ni = w.get(sp); sp--;
+		unsigned asked;
+		const int ni = w.get(sp, asked); sp--;
 		const float4 na = S.nodes[4*ni], nb = S.nodes[4*ni + 1];
 		boxSqDist(xyz(na), xyz(nb), x, b0, b1);
-		const bool reach = b0 <= r2; // r2 < 0: never
+		const bool reach = W::mine(asked) && b0 <= r2; // r2 < 0: never
 		if (!W::any(reach)) continue;
 		const int nRefs = asInt(na.w);
 		if (nRefs > 0) {

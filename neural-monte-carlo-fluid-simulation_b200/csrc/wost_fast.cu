@@ -75,7 +75,7 @@ __device__ __forceinline__ void stackInit(LocalStack&, int*, int) {}
 // accumulators per lane; the product path (stats12 == nullptr) runs the instantiation without them.
 // FLAT: 0 = tree traversals per step, 1 = flat scans over tables staged in shared memory (<= 128 primitives),
 // 2 = two-level flat scans over tables in global memory (larger meshes; the tree is still walked once per point),
-// 3 = warp-packet tree traversals (nmc_packet.cuh): the default beyond the flat-scan limit
+// 3 = warp-packet tree traversals (nmc_packet.cuh), selectable with NMC_BIG_MESH=packet
 template <int DIM, class STACK, int FLAT, bool STATS>
 __global__ void __launch_bounds__(kBlock, DIM == 2 ? NMC_MINB2 : NMC_MINB3)
 fastKernel(SceneView Sg, SolverParams o, const float* __restrict__ pts, long long n, unsigned long long indexOffset,
@@ -527,16 +527,15 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	};
 	if (flat && stageQuadsFor(true)*sizeof(float4) > 48*1024) flat = false;
 	size_t quads = stageQuadsFor(flat);
-	// meshes beyond the shared-memory flat scan: two-level flat scans over the global tables (NMC_BIG_MESH=tree selects the
-	// per-lane tree traversals instead, for A/B measurements).
-	// 3D only: on box_sphere (1292 triangles) the two-level scan runs 2.6e8 walks/s against 4.7e7 for the per-lane tree
-	// traversal; in 2D (channel_circle, 1184 segments) the tree is the faster of the two (8.7e8 against 4.1e8: long merged
-	// wall segments make poor group boxes) and stays the default
-	// Default: warp-packet traversals of the tree (FLAT == 3, nmc_packet.cuh): one traversal per warp with warp-uniform node loads
-	// and a register stack; NMC_BIG_MESH=flat2 / tree select the two older paths.
-	static const int bigMode = [] { const char* e = getenv("NMC_BIG_MESH"); return !e ? 3 : e[0] == 't' ? 0 : e[0] == 'f' ? 2 : 3; }();
+	// Beyond the flat-scan limit, by measurement (profiles/r02_mbvh.jsonl, B200, 1e3 .. 1.3e5 primitives): 2D per-lane tree
+	// traversals; 3D the two-level flat scan up to 8192 triangles (1292: 2.0e8 walks/s against 1.6e8 packet / 7e7 tree), per-lane
+	// tree traversals above (82 k: 5.1e6 against 3.9e6 packet).  The warp-packet traversals (FLAT == 3, nmc_packet.cuh: one traversal
+	// per warp, warp-uniform node loads, register stack) are kept selectable: they win only between ~1e4 and ~3e4 triangles
+	// (+14 % at 20 k) and lose in 2D (the union of 32 lanes' search regions is several times one lane's).
+	// NMC_BIG_MESH = packet | tree | flat2 forces one path (A/B measurements, tests).
+	static const int bigMode = [] { const char* e = getenv("NMC_BIG_MESH"); return !e ? -1 : e[0] == 't' ? 0 : e[0] == 'f' ? 2 : e[0] == 'p' ? 3 : -1; }();
 	const bool packet = !flat && bigMode == 3 && maxDepth + 2 <= NMC_STACK;
-	const bool flat2 = !flat && bigMode == 2 && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
+	const bool flat2 = !flat && (bigMode == 2 || (bigMode == -1 && S.nPrims <= 8192)) && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
 	if (flat2 || packet) quads = 0; // FLAT == 2 / 3 stage nothing (see the kernel)
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2

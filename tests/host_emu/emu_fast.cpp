@@ -19,7 +19,7 @@ using namespace nmc;
 
 // A warp of 32 host threads in lockstep at every cross-lane operation: ballots meet at a barrier, the stack entry sp lives
 // with lane sp & 31 as on the device (WarpOps), reading it back is a synchronising shuffle.
-struct HostWarpCtx { pthread_barrier_t bar; std::atomic<unsigned> acc{0}; int s0[32], s1[32]; };
+struct HostWarpCtx { pthread_barrier_t bar; std::atomic<unsigned> acc{0}; int s0[32], s1[32]; unsigned q0[32], q1[32]; };
 static thread_local HostWarpCtx* tlCtx = nullptr;
 static thread_local int tlLane = 0;
 struct HostWarp {
@@ -35,11 +35,15 @@ struct HostWarp {
 	}
 	static bool any(bool p) { return ballot(p) != 0; }
 	static int popc(unsigned m) { return __builtin_popcount(m); }
-	void put(int sp, int node) { if (tlLane == (sp & 31)) (sp < 32 ? tlCtx->s0 : tlCtx->s1)[sp & 31] = node; }
-	int get(int sp) const {
+	static bool mine(unsigned m) { return (m >> tlLane) & 1u; }
+	void put(int sp, int node, unsigned lanes) {
+		if (tlLane == (sp & 31)) { (sp < 32 ? tlCtx->s0 : tlCtx->s1)[sp & 31] = node; (sp < 32 ? tlCtx->q0 : tlCtx->q1)[sp & 31] = lanes; }
+	}
+	int get(int sp, unsigned& lanes) const {
 		HostWarpCtx& c = *tlCtx;
 		pthread_barrier_wait(&c.bar);
 		int v = (sp < 32 ? c.s0 : c.s1)[sp & 31];
+		lanes = (sp < 32 ? c.q0 : c.q1)[sp & 31];
 		pthread_barrier_wait(&c.bar);
 		return v;
 	}

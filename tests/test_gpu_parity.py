@@ -258,7 +258,7 @@ def test_mesh_size_regimes_of_the_default_mode(pkg, oracle_lib, tmp_path, n_circ
 
 
 @pytest.mark.parametrize("case", ["channel_circle", "box_sphere", "karman", "karman3d"])
-def test_warp_packet_tree_queries_on_the_device(pkg, case):
+def test_warp_packet_tree_queries_on_the_device(pkg, oracle_lib, case):
     """The default mode's big-mesh path (csrc/nmc_packet.cuh: one tree traversal per warp, per-lane radii) through the packet
     probes: every lane must get what the deterministic kernel's private traversal gets, on coherent packets (32 queries in one
     small ball, the walk kernel's situation) and incoherent ones (32 queries anywhere), with idle lanes at the end.  The fast
@@ -272,14 +272,21 @@ def test_warp_packet_tree_queries_on_the_device(pkg, case):
     far = util.random_points(lo, hi, 4096, seed=5)
     centres = util.random_points(lo, hi, 128, seed=6)
     near = (np.repeat(centres, 32, 0) + (rng.random((4096, dim), dtype=np.float32) - 0.5)*0.06*ext).astype(np.float32)
-    q = np.ascontiguousarray(np.concatenate([far, near])[:-13])
+    # packets ON the boundary (where a walk continues after a reflection) with every other lane moved off it: on the fine
+    # circle a lane that worked on a leaf its own cone test had dropped would accept vertices inside the precision band
+    v, pr = oracle_lib.load_obj(cfg["scene"]["boundary"], dim, False)
+    first = rng.integers(0, max(1, len(pr) - 32), 128)
+    idx = np.minimum((first[:, None] + np.arange(32)[None, :]).reshape(-1), len(pr) - 1)
+    mixed = v[pr[idx]].mean(1).astype(np.float32)[:, :dim]
+    mixed[1::2] += ((rng.random((len(mixed)//2, dim), dtype=np.float32) - 0.5)*0.03*ext).astype(np.float32)
+    q = np.ascontiguousarray(np.concatenate([far, mixed, near])[:-13])
     n = len(q)
-    max_r = (rng.random(n, dtype=np.float32)*ext).astype(np.float32); max_r[::7] = np.float32(3.0e38)
+    max_r = (rng.random(n, dtype=np.float32)*ext).astype(np.float32); max_r[::7] = np.float32(3.0e38); max_r[4096:8192] = np.float32(3.0e38)
     for flip in (0.0, 1.0):
         want = sc.handle.probe(pkg.capi.PROBE_STAR_RADIUS, n, q, aux0=max_r, params=[1e-3, 1e-3, flip])
         got = sc.handle.probe(pkg.capi.PROBE_STAR_RADIUS_PACKET, n, q, aux0=max_r, params=[1e-3, 1e-3, flip])
         rel = np.abs(got - want)/np.maximum(np.abs(want), 1e-6)
-        assert (rel < 1e-5).mean() >= 0.999, (case, flip, (rel < 1e-5).mean(), rel.max())
+        assert (rel < 1e-5).mean() >= 0.9995, (case, flip, (rel < 1e-5).mean(), rel.max())
     u = rng.random((n, 2), dtype=np.float32)
     if dim == 2:
         a = 2*np.pi*u[:, 0]; d = np.stack([np.cos(a), np.sin(a)], 1).astype(np.float32)

@@ -529,7 +529,7 @@ def test_warp_packet_traversals_equal_the_private_ones(emu_fast, oracle_lib, tmp
     incoherent ones (32 queries anywhere in the box: the children vote is split, lanes idle)."""
     rng = np.random.default_rng(11)
     names = ("channel_circle", "box_sphere", "karman", "karman3d")
-    scenes = [(c, util.load_case(c)) for c in names] + [(n, cfg) for n, _, cfg in util.random_meshes(tmp_path)][:4]
+    scenes = [(c, util.load_case(c)) for c in names] + [(n, cfg) for n, _, cfg in util.random_meshes(tmp_path)][:2]
     for name, cfg in scenes:
         dim, sc = cfg["dim"], cfg["scene"]
         v, p = oracle_lib.load_obj(sc["boundary"], dim, False)
@@ -538,11 +538,20 @@ def test_warp_packet_traversals_equal_the_private_ones(emu_fast, oracle_lib, tmp
                                                   C.c_float(sc.get("absorptionCoeff", 0.0)), int(sc.get("isWatertight", False)), int(sc.get("isDoubleSided", False))))
         lo = np.array([v[:, k].min() for k in range(dim)], np.float32); hi = np.array([v[:, k].max() for k in range(dim)], np.float32)
         ext = float((hi - lo).max())
-        # 20 incoherent packets + 20 coherent ones (a centre and 31 points within 3 % of the box of it); 13 queries short of a whole packet
-        far = util.random_points(lo, hi, 640, seed=5, margin=0.05)
-        centres = util.random_points(lo, hi, 20, seed=6, margin=0.05)
-        near = (np.repeat(centres, 32, 0) + (rng.random((640, dim), dtype=np.float32) - 0.5)*0.06*ext).astype(np.float32)
-        q = np.ascontiguousarray(np.concatenate([far, near])[:-13])
+        # 10 incoherent packets + 10 coherent ones (a centre and 31 points within 3 % of the box of it); 13 queries short of a whole packet
+        far = util.random_points(lo, hi, 320, seed=5, margin=0.05)
+        centres = util.random_points(lo, hi, 10, seed=6, margin=0.05)
+        near = (np.repeat(centres, 32, 0) + (rng.random((320, dim), dtype=np.float32) - 0.5)*0.06*ext).astype(np.float32)
+        # 10 packets ON the boundary, where a walk continues after a reflection: centroids of 32 consecutive primitives each (at a
+        # point on a finely subdivided circle the neighbouring vertices sit inside the silhouette test's precision band -- a lane
+        # that worked on a leaf its own cone test had dropped would accept them and shrink its star to a segment length)
+        n_onb = 60 if name == "channel_circle" else 10   # the fine circle is where ignoring the per-lane masks shows (a few lanes per 20 packets)
+        first = rng.integers(0, max(1, len(p) - 32), n_onb)
+        idx = np.minimum((first[:, None] + np.arange(32)[None, :]).reshape(-1), len(p) - 1)
+        onb = v[p[idx]].mean(1).astype(np.float32)[:, :dim]
+        mixed = onb.copy()   # the same packets with every other lane moved off the boundary by up to 1.5 % of the box
+        mixed[1::2] += ((rng.random((len(onb)//2, dim), dtype=np.float32) - 0.5)*0.03*ext).astype(np.float32)
+        q = np.ascontiguousarray(np.concatenate([far, onb, mixed, near])[:-13])
         n = len(q)
         max_r = (rng.random(n, dtype=np.float32)*ext).astype(np.float32); max_r[::7] = np.float32(3.0e38)
         for flip in (0, 1):
