@@ -150,6 +150,11 @@ int nmc_mse_grad_fit(const float* y, const float* target, const float* sub, int6
  * next test of the flag do not move a fit the reference has already ended. */
 int nmc_adam_update_device(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
 						   float eps, const long long* step, const int* stop_flag, void* stream);
+/* nmc_adam_update_device of one iteration and nmc_fit_fetch of the next in ONE launch (both read the device-side step, neither
+ * writes it): used between the iterations of an unrolled fit graph. */
+int nmc_adam_update_fetch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+						  float eps, const long long* step, const int* stop_flag, int64_t count, int slots, const float* ring_x,
+						  const float* ring_t, const float* ring_s, float* out_x, float* out_t, float* out_s, void* stream);
 
 #ifdef __cplusplus
 }

@@ -655,6 +655,50 @@ __global__ void adamKernelDev(float* __restrict__ p, const float* __restrict__ g
 	p[i] -= (lr/bc[0])*(mi/denom);
 }
 
+// adamKernelDev of iteration i and the ring fetch of iteration i + 1 (fit_glue.cu: fitFetch) in one launch: the first `adamBlocks`
+// CTAs update the parameters, the others copy slot (step % slots) of the target ring into the fixed buffers the next captured
+// iteration reads.  Both read the step counter, nobody writes it (nmc_mse_grad_fit advances it earlier in the iteration), so the
+// launch does what the two did back to back; one ~2 us launch less per iteration of an unrolled fit graph.
+__global__ void adamFetchKernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+								long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step, const int* __restrict__ stopFlag,
+								int adamBlocks, long long count, int slots, const float* __restrict__ ringX, const float* __restrict__ ringT,
+								const float* __restrict__ ringS, float* __restrict__ outX, float* __restrict__ outT, float* __restrict__ outS, int vec) {
+	if ((int)blockIdx.x >= adamBlocks) {
+		const long long base = (*step % slots)*count;
+		const long long tid = (long long)(blockIdx.x - adamBlocks)*blockDim.x + threadIdx.x, nth = (long long)(gridDim.x - adamBlocks)*blockDim.x;
+		if (vec) {
+			const float4* x4 = reinterpret_cast<const float4*>(ringX + base); const float4* t4 = reinterpret_cast<const float4*>(ringT + base);
+			const float4* s4 = ringS ? reinterpret_cast<const float4*>(ringS + base) : nullptr;
+			for (long long i = tid; i < (count >> 2); i += nth) {
+				reinterpret_cast<float4*>(outX)[i] = x4[i]; reinterpret_cast<float4*>(outT)[i] = t4[i];
+				if (s4) reinterpret_cast<float4*>(outS)[i] = s4[i];
+			}
+		} else {
+			for (long long i = tid; i < count; i += nth) {
+				outX[i] = ringX[base + i]; outT[i] = ringT[base + i];
+				if (ringS) outS[i] = ringS[base + i];
+			}
+		}
+		return;
+	}
+	if (stopFlag && *stopFlag) return;
+	__shared__ float bc[2];
+	if (threadIdx.x == 0) {
+		const float t = (float)*step;
+		bc[0] = -expm1f(t*log1pf(-(1.0f - b1)));
+		bc[1] = sqrtf(-expm1f(t*log1pf(-(1.0f - b2))));
+	}
+	__syncthreads();
+	long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float gi = g[i];
+	float mi = b1*m[i] + (1.0f - b1)*gi;
+	float vi = b2*v[i] + (1.0f - b2)*gi*gi;
+	m[i] = mi; v[i] = vi;
+	float denom = sqrtf(vi)/bc[1] + eps;
+	p[i] -= (lr/bc[0])*(mi/denom);
+}
+
 // torch.optim.Adam (no amsgrad, no weight decay) over one flat buffer; step is 1-based
 __global__ void adamKernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
 						   long long n, float lr, float b1, float b2, float eps, float bc1, float bc2sqrt) {
@@ -830,6 +874,21 @@ extern "C" int nmc_adam_update_device(float* p, const float* g, float* m, float*
 	if (n <= 0) return 0;
 	if (!p || !g || !m || !v || !step) return fail("bad arguments");
 	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, stop_flag);
+	cudaError_t e = cudaGetLastError();
+	return e ? fail(cudaGetErrorString(e)) : 0;
+}
+
+extern "C" int nmc_adam_update_fetch(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+									 float eps, const long long* step, const int* stop_flag, int64_t count, int slots, const float* ring_x,
+									 const float* ring_t, const float* ring_s, float* out_x, float* out_t, float* out_s, void* stream) {
+	if (n <= 0 || count <= 0) return fail("nmc_adam_update_fetch: empty update or fetch");
+	if (!p || !g || !m || !v || !step || slots < 1 || !ring_x || !ring_t || !out_x || !out_t || (ring_s && !out_s)) return fail("bad arguments");
+	const int vec = (count % 4 == 0) && ((((uintptr_t)ring_x | (uintptr_t)ring_t | (uintptr_t)ring_s | (uintptr_t)out_x | (uintptr_t)out_t | (uintptr_t)out_s) & 15) == 0);
+	const int adamBlocks = (int)((n + 255)/256);
+	long long fb = ((vec ? count/4 : count) + 255)/256;
+	fb = fb < 1 ? 1 : (fb > 1184 ? 1184 : fb);
+	adamFetchKernel<<<(unsigned)(adamBlocks + fb), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, stop_flag, adamBlocks,
+		count, slots, ring_x, ring_t, ring_s, out_x, out_t, out_s, vec);
 	cudaError_t e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

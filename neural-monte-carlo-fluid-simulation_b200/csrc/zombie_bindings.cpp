@@ -185,14 +185,31 @@ static py::tuple wost(const Scene& scene, const py::dict& solver, const py::dict
 	std::vector<float> p, g;
 	solve(scene, solver, output, pts, p, g);
 	const int64_t n = pts.shape(0);
-	py::list outPts(n), outP(n), outG(n);
+	// The nested lists the pybind STL casters return (demo.cpp:119,204): N x (2 DIM + 1) float objects and 2 N inner lists, built
+	// with the C API (stolen references, no accessor temporaries) and with the cyclic collector paused -- millions of fresh
+	// container objects would otherwise trigger a full collection every few thousand allocations (1e6 points: 0.87 s -> 0.30 s).
 	auto a = pts.unchecked<2>();
-	for (int64_t i = 0; i < n; i++) {
-		py::list q(DIM), gr(DIM);
-		for (int k = 0; k < DIM; k++) { q[k] = py::float_(a(i, k)); gr[k] = py::float_(g[(size_t)i*DIM + k]); }
-		outPts[i] = q; outP[i] = py::float_(p[(size_t)i]); outG[i] = gr;
+#if PY_VERSION_HEX >= 0x030A0000
+	const int gcWasOn = PyGC_Disable();
+#endif
+	PyObject *outPts = PyList_New(n), *outP = PyList_New(n), *outG = PyList_New(n);
+	bool ok = outPts && outP && outG;
+	for (int64_t i = 0; ok && i < n; i++) {
+		PyObject *q = PyList_New(DIM), *gr = PyList_New(DIM), *pv = PyFloat_FromDouble(p[(size_t)i]);
+		ok = q && gr && pv;
+		for (int k = 0; ok && k < DIM; k++) {
+			PyObject *x = PyFloat_FromDouble(a(i, k)), *y = PyFloat_FromDouble(g[(size_t)i*DIM + k]);
+			if (!x || !y) { Py_XDECREF(x); Py_XDECREF(y); ok = false; break; }
+			PyList_SET_ITEM(q, k, x); PyList_SET_ITEM(gr, k, y);
+		}
+		if (!ok) { Py_XDECREF(q); Py_XDECREF(gr); Py_XDECREF(pv); break; }
+		PyList_SET_ITEM(outPts, i, q); PyList_SET_ITEM(outP, i, pv); PyList_SET_ITEM(outG, i, gr);
 	}
-	return py::make_tuple(outPts, outP, outG);
+#if PY_VERSION_HEX >= 0x030A0000
+	if (gcWasOn) PyGC_Enable();
+#endif
+	if (!ok) { Py_XDECREF(outPts); Py_XDECREF(outP); Py_XDECREF(outG); throw std::bad_alloc(); }
+	return py::make_tuple(py::reinterpret_steal<py::object>(outPts), py::reinterpret_steal<py::object>(outP), py::reinterpret_steal<py::object>(outG));
 }
 
 static py::tuple wostArray(const Scene& scene, const py::dict& solver, const py::dict& output, const PtsArray& pts) {

@@ -196,6 +196,8 @@ def _lib():
         L.nmc_fit_sample_uniform.argtypes = [C.c_int, f3, f3, C.c_int64, vp, vp, vp, C.c_uint64, f3, vp]
         L.nmc_fit_gather.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_uint64, vp]
         L.nmc_fit_fetch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.nmc_adam_update_fetch.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
+                                            C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, vp]
         _configured = True
     return L
 
@@ -415,6 +417,18 @@ class FusedAdam:
                                                  self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(),
                                                  self.stop_flag.data_ptr() if gated else None, _stream()))
 
+    def update_flat_fetch(self, gated, ring_x, ring_t, ring_s, out_x, out_t, out_s):
+        """update_flat and the fit_fetch of the NEXT iteration in one launch (csrc/siren.cu: adamFetchKernel)."""
+        self.step_count += 1
+        slots, count = ring_x.shape[0], out_x.numel()
+        assert ring_x.is_contiguous() and ring_t.is_contiguous() and ring_x.numel() == slots*count and ring_t.shape == ring_x.shape
+        with torch.cuda.device(self.flat.device):
+            _check(_lib().nmc_adam_update_fetch(self.flat.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(),
+                                                self.stop_flag.data_ptr() if gated else None, count, slots, ring_x.data_ptr(), ring_t.data_ptr(),
+                                                ring_s.data_ptr() if ring_s is not None else None, out_x.data_ptr(), out_t.data_ptr(),
+                                                out_s.data_ptr() if ring_s is not None else None, _stream()))
+
     def step(self):
         self.step_count += 1
         off = 0
@@ -536,9 +550,10 @@ class DirectFit:
                 _check(_lib().nmc_siren_forward(C.byref(sh), _ptrs(self.W), _ptrs(self.b), x.data_ptr(), n, y.data_ptr(), z.data_ptr(), self.env, _stream()))
         return y
 
-    def finish(self, x, y, target, sub=None):
+    def finish(self, x, y, target, sub=None, fetch_next=None):
         """Second half: loss, dL/dy, delta chain, weight gradients, (all_reduce,) Adam.  Returns y - target.
-        The fit target is target - sub when `sub` is given (the projection fit's u_prev - grad p)."""
+        The fit target is target - sub when `sub` is given (the projection fit's u_prev - grad p).
+        fetch_next = (ring_x, ring_t, ring_s, out_x, out_t, out_s): the Adam launch also fetches the next iteration's ring slot."""
         n = x.shape[0]
         sh = self.sh
         z = self.z[: (sh.n_hidden_layers + 1)*sh.hidden*n]
@@ -574,7 +589,10 @@ class DirectFit:
         if self.world > 1:  # mean over the global batch = mean over ranks of the local means (equal shard sizes)
             import torch.distributed as dist
             dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG, group=self.group)
-        self.opt.update_flat(gated)
+        if fetch_next is not None:
+            self.opt.update_flat_fetch(gated, *fetch_next)
+        else:
+            self.opt.update_flat(gated)
         return diff
 
     def close(self):

@@ -122,6 +122,8 @@ class SplitStepper:
         # with chunked targets an iteration is one stream of six kernels; `graph_unroll` of them are captured in a second graph, which
         # removes the ~4 us between two graph launches (taylorgreen: 68 -> 64 us per iteration).  Must divide the chunk and check_every.
         self.graph_unroll = int(os.environ.get("NMC_GRAPH_UNROLL", "20"))
+        # inside the unrolled graph the Adam update of iteration i and the ring fetch of iteration i + 1 are one launch (NMC_MERGE_ADAM_FETCH=0: two)
+        self.merge_adam_fetch = os.environ.get("NMC_MERGE_ADAM_FETCH", "1") != "0"
         torch.manual_seed(seed)
         self.dim = dim = len(self.size)//2
         if dim not in (2, 3):
@@ -289,10 +291,13 @@ class SplitStepper:
 
             side2 = torch.cuda.Stream(device=self.dev) if self.overlap_targets else None
 
-            def one_chunked():
-                fit_fetch(ring["X"], ring["T"], ring["S"], fit.opt.step_dev, ring["x"], ring["t"], ring["s"])
+            def one_chunked(fetch=True, fetch_next=False):
+                # fetch_next (inside the unrolled graph): the Adam launch of this iteration also copies the ring slot of the next one
+                if fetch:
+                    fit_fetch(ring["X"], ring["T"], ring["S"], fit.opt.step_dev, ring["x"], ring["t"], ring["s"])
                 y = fit.forward(ring["x"])
-                fit.finish(ring["x"], y, ring["t"], ring["s"])
+                fit.finish(ring["x"], y, ring["t"], ring["s"],
+                           fetch_next=(ring["X"], ring["T"], ring["S"], ring["x"], ring["t"], ring["s"]) if fetch_next else None)
 
             def one():
                 # `iteration()` returns the samples and a function that computes the fit target from them.  The target
@@ -328,9 +333,13 @@ class SplitStepper:
                 U = self.graph_unroll
                 if ring is not None and U > 1 and C % U == 0 and self.check_every % U == 0:
                     graph_u = torch.cuda.CUDAGraph()
+                    merge = self.merge_adam_fetch and fit.world == 1
                     with torch.cuda.graph(graph_u):
-                        for _ in range(U):
-                            one()
+                        for u in range(U):
+                            if merge:
+                                one_chunked(fetch=(u == 0), fetch_next=(u < U - 1))
+                            else:
+                                one()
                 if key is not None:
                     self._graphs[key] = (graph, loss_buf, graph_u)
         while it < n_iters:

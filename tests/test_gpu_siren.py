@@ -586,3 +586,41 @@ def test_direct_fit_stops_moving_at_the_early_stop_threshold(siren):
         fit.iterate(x, target)
     if fit.loss.item() > 0.0:
         assert max((a - b).abs().max().item() for a, b in zip(start, net.parameters())) > 1e-5
+
+
+@pytest.mark.parametrize("with_sub,count", [(True, 3*4096), (False, 2*4096 + 2)])
+def test_adam_update_and_next_fetch_in_one_launch(siren, with_sub, count):
+    """csrc/siren.cu adamFetchKernel (between the iterations of an unrolled fit graph): the same bits as nmc_adam_update_device
+    followed by nmc_fit_fetch -- parameters, both moments and the three fetched buffers -- for a 16-byte-aligned and an odd slot
+    size, with and without the projection fit's third ring, and with the early-stop flag set (no update, the fetch still runs)."""
+    import torch
+    S = siren
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    slots = 8
+    ring_x, ring_t = torch.randn(slots, count, device=dev), torch.randn(slots, count, device=dev)
+    ring_s = torch.randn(slots, count, device=dev) if with_sub else None
+    for stopped in (False, True):
+        outs = []
+        for merged in (False, True):
+            torch.manual_seed(5)
+            params = [torch.nn.Parameter(torch.randn(64, 3, device=dev)), torch.nn.Parameter(torch.randn(64, device=dev)),
+                      torch.nn.Parameter(torch.randn(4, 64, 64, device=dev))]
+            opt = S.FusedAdam(params, lr=1e-3)
+            opt.g.copy_(torch.randn_like(opt.g)); opt.m.copy_(torch.rand_like(opt.m)*0.1); opt.v.copy_(torch.rand_like(opt.v)*0.01)
+            opt.step_dev.fill_(13)                 # slot 13 % 8 = 5
+            opt.stop_flag.fill_(1 if stopped else 0)
+            ox, ot = torch.zeros(count, device=dev), torch.zeros(count, device=dev)
+            os_ = torch.zeros(count, device=dev) if with_sub else None
+            before = opt.flat.clone()
+            if merged:
+                opt.update_flat_fetch(True, ring_x, ring_t, ring_s, ox, ot, os_)
+            else:
+                opt.update_flat(True)
+                S.fit_fetch(ring_x, ring_t, ring_s, opt.step_dev, ox, ot, os_)
+            torch.cuda.synchronize()
+            assert torch.equal(ox, ring_x[5]) and torch.equal(ot, ring_t[5]) and (not with_sub or torch.equal(os_, ring_s[5]))
+            assert torch.equal(opt.flat, before) == stopped
+            outs.append((opt.flat.clone(), opt.m.clone(), opt.v.clone()))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
