@@ -308,7 +308,7 @@ def test_warp_packet_tree_queries_on_the_device(pkg, oracle_lib, case):
     dn = sc.handle.probe(pkg.capi.PROBE_DIST_NEUMANN, n, q)
     sd = sc.handle.probe(pkg.capi.PROBE_SIGNED_DIST_NEUMANN, n, q)
     assert (np.abs(cl[:, 0] - dn) <= 1e-5*np.abs(dn) + 1e-7).mean() >= 0.9999, case
-    assert (np.sign(cl[:, 1]) == np.sign(sd)).mean() >= 0.999, case
+    assert (np.sign(cl[off, 1]) == np.sign(sd[off])).mean() >= 0.999, case      # ON a primitive the side is decided by rounding
 
 
 def test_edge_cases(pkg):
