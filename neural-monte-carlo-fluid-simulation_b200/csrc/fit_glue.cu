@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
+#include "pdl.cuh"
 
 namespace nmc_siren_detail { void setError(const char* m); }
 
@@ -63,6 +64,7 @@ __global__ void fitGather(int dim, long long n, const float* __restrict__ srcX, 
 // one slot of the target ring -> the fixed buffers a captured iteration reads; the slot is Adam's device-side step modulo `slots`
 __global__ void fitFetch(long long count, int slots, const float* __restrict__ ringX, const float* __restrict__ ringT, const float* __restrict__ ringS,
 						 const long long* __restrict__ step, float* __restrict__ outX, float* __restrict__ outT, float* __restrict__ outS, int vec) {
+	nmc_pdl::gridEnter();
 	const long long base = (*step % slots)*count;
 	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x, nth = (long long)gridDim.x*blockDim.x;
 	if (vec) {
@@ -112,7 +114,7 @@ extern "C" int nmc_fit_fetch(int64_t count, int slots, const float* ring_x, cons
 	if (count <= 0) return 0;
 	if (slots < 1 || !ring_x || !ring_t || !step || !out_x || !out_t || (ring_s && !out_s)) return fail("bad arguments");
 	const int vec = (count % 4 == 0) && ((((uintptr_t)ring_x | (uintptr_t)ring_t | (uintptr_t)ring_s | (uintptr_t)out_x | (uintptr_t)out_t | (uintptr_t)out_s) & 15) == 0);
-	fitFetch<<<gridFor(vec ? count/4 : count), 256, 0, (cudaStream_t)stream>>>(count, slots, ring_x, ring_t, ring_s, step, out_x, out_t, out_s, vec);
-	cudaError_t e = cudaGetLastError();
+	cudaError_t e = nmc_pdl::launch(fitFetch, dim3(gridFor(vec ? count/4 : count)), dim3(256), 0, (cudaStream_t)stream, (long long)count, slots, ring_x, ring_t, ring_s, step, out_x, out_t, out_s, vec);
+	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }

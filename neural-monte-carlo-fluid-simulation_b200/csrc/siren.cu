@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
+#include "pdl.cuh"
 
 namespace {
 
@@ -241,6 +242,7 @@ template <int H, int NPT>
 __global__ void __launch_bounds__(32*(H/NPT), H == 128 ? 2 : 4)
 sirenForwardSplit(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 				  float* __restrict__ y, float* __restrict__ zSaved) {
+	nmc_pdl::gridEnter();
 	extern __shared__ float smem[];
 	constexpr int LD = H + 4, NG = H/NPT, NT = 32*NG;
 	// H = 64: two weight buffers, the next layer's weights stream in with cp.async while this layer is computed
@@ -576,6 +578,7 @@ __global__ void __launch_bounds__(512) mseGrad(const float* __restrict__ y, cons
 												long long count, float* __restrict__ diff, float* __restrict__ gy, float* __restrict__ loss, int vec,
 												float* __restrict__ zero, long long zeroCount, long long* __restrict__ stepAdvance,
 												float stopThreshold, int* __restrict__ stopFlag) {
+	nmc_pdl::gridEnter();
 	const float scale = 2.0f/(float)count;
 	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x, nth = (long long)gridDim.x*blockDim.x;
 	if (stepAdvance && tid == 0) *stepAdvance += 1;
@@ -637,6 +640,7 @@ __global__ void __launch_bounds__(512) mseGrad(const float* __restrict__ y, cons
 __global__ void adamAdvance(long long* step) { *step += 1; }
 __global__ void adamKernelDev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
 							  long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step, const int* __restrict__ stopFlag) {
+	nmc_pdl::gridEnter();
 	if (stopFlag && *stopFlag) return;   // the fit has reached the early-stop threshold (base.py:148): the reference has left the loop
 	__shared__ float bc[2];
 	if (threadIdx.x == 0) { // 1 - beta^t = -expm1(t log1p(-(1 - beta))): fp32 throughout (1 - beta is exact), ~2e-7 relative; the double-precision
@@ -663,6 +667,7 @@ __global__ void adamFetchKernel(float* __restrict__ p, const float* __restrict__
 								long long n, float lr, float b1, float b2, float eps, const long long* __restrict__ step, const int* __restrict__ stopFlag,
 								int adamBlocks, long long count, int slots, const float* __restrict__ ringX, const float* __restrict__ ringT,
 								const float* __restrict__ ringS, float* __restrict__ outX, float* __restrict__ outT, float* __restrict__ outS, int vec) {
+	nmc_pdl::gridEnter();
 	if ((int)blockIdx.x >= adamBlocks) {
 		const long long base = (*step % slots)*count;
 		const long long tid = (long long)(blockIdx.x - adamBlocks)*blockDim.x + threadIdx.x, nth = (long long)(gridDim.x - adamBlocks)*blockDim.x;
@@ -768,10 +773,10 @@ extern "C" int nmc_siren_forward(const nmc_siren_shape* sh, const float* const* 
 		int gridS = (int)(tilesS < 8ll*smCount() ? tilesS : 8ll*smCount());
 		if (H == 64) {
 			e = cudaFuncSetAttribute(sirenForwardSplit<64, kNpt64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-			if (!e) sirenForwardSplit<64, kNpt64><<<gridS, 32*(64/kNpt64), smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+			if (!e) e = nmc_pdl::launch(sirenForwardSplit<64, kNpt64>, dim3(gridS), dim3(32*(64/kNpt64)), smemS, st, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, y, z_saved);
 		} else {
 			e = cudaFuncSetAttribute(sirenForwardSplit<128, kNpt128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-			if (!e) sirenForwardSplit<128, kNpt128><<<gridS, 32*(128/kNpt128), smemS, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved);
+			if (!e) e = nmc_pdl::launch(sirenForwardSplit<128, kNpt128>, dim3(gridS), dim3(32*(128/kNpt128)), smemS, st, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, y, z_saved);
 		}
 		if (!e) e = cudaGetLastError();
 		return e ? fail(cudaGetErrorString(e)) : 0;
@@ -860,8 +865,9 @@ extern "C" int nmc_mse_grad_fit(const float* y, const float* target, const float
 	const int vec = (((uintptr_t)y | (uintptr_t)target | (uintptr_t)diff | (uintptr_t)grad_y | (uintptr_t)sub) & 15) == 0;
 	int blocks = (int)((count/4 + 511)/512);
 	blocks = blocks < 1 ? 1 : (blocks > kMseBlocks ? kMseBlocks : blocks);
-	mseGrad<<<blocks, 512, 0, (cudaStream_t)stream>>>(y, target, sub, count, diff, grad_y, loss, vec, zero_count > 0 ? zero : nullptr, zero_count, step_advance, stop_threshold, stop_flag);
-	cudaError_t e = cudaGetLastError();
+	cudaError_t e = nmc_pdl::launch(mseGrad, dim3(blocks), dim3(512), 0, (cudaStream_t)stream, y, target, sub, (long long)count, diff, grad_y, loss, vec,
+									zero_count > 0 ? zero : (float*)nullptr, (long long)zero_count, step_advance, stop_threshold, stop_flag);
+	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
 
@@ -873,8 +879,8 @@ extern "C" int nmc_adam_update_device(float* p, const float* g, float* m, float*
 									  float eps, const long long* step, const int* stop_flag, void* stream) {
 	if (n <= 0) return 0;
 	if (!p || !g || !m || !v || !step) return fail("bad arguments");
-	adamKernelDev<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, stop_flag);
-	cudaError_t e = cudaGetLastError();
+	cudaError_t e = nmc_pdl::launch(adamKernelDev, dim3((unsigned)((n + 255)/256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (long long)n, lr, beta1, beta2, eps, step, stop_flag);
+	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
 
@@ -887,9 +893,9 @@ extern "C" int nmc_adam_update_fetch(float* p, const float* g, float* m, float* 
 	const int adamBlocks = (int)((n + 255)/256);
 	long long fb = ((vec ? count/4 : count) + 255)/256;
 	fb = fb < 1 ? 1 : (fb > 1184 ? 1184 : fb);
-	adamFetchKernel<<<(unsigned)(adamBlocks + fb), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, stop_flag, adamBlocks,
-		count, slots, ring_x, ring_t, ring_s, out_x, out_t, out_s, vec);
-	cudaError_t e = cudaGetLastError();
+	cudaError_t e = nmc_pdl::launch(adamFetchKernel, dim3((unsigned)(adamBlocks + fb)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (long long)n, lr, beta1, beta2,
+									eps, step, stop_flag, adamBlocks, (long long)count, slots, ring_x, ring_t, ring_s, out_x, out_t, out_s, vec);
+	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
 }
 

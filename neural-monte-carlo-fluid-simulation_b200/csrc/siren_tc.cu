@@ -19,6 +19,7 @@
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
 #include "siren_tc.cuh"
+#include "pdl.cuh"
 
 namespace {
 
@@ -89,6 +90,7 @@ template <int H, bool SAVEZ>
 __global__ void __launch_bounds__(kThreads, H == 64 ? 2 : 1)
 sirenForwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n, float* __restrict__ y,
 			   float* __restrict__ zSaved) {
+	nmc_pdl::gridEnter();
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned char* Ahi = smem;
 	unsigned char* Alo = Ahi + kTile*H*4;
@@ -323,7 +325,7 @@ extern "C" int nmc_siren_forward_tc(const nmc_siren_shape* sh, const float* cons
 	cudaError_t e;
 #define NMC_LAUNCH_FWD(HH, SZ) do { \
 		e = cudaFuncSetAttribute(sirenForwardTc<HH, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-		if (!e) sirenForwardTc<HH, SZ><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, y, z_saved); \
+		if (!e) e = nmc_pdl::launch(sirenForwardTc<HH, SZ>, dim3(grid), dim3(kThreads), smem, st, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, y, z_saved); \
 	} while (0)
 	if (H == 64) { if (z_saved) NMC_LAUNCH_FWD(64, true); else NMC_LAUNCH_FWD(64, false); }
 	else { if (z_saved) NMC_LAUNCH_FWD(128, true); else NMC_LAUNCH_FWD(128, false); }

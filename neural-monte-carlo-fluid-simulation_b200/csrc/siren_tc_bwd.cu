@@ -23,6 +23,7 @@
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
 #include "siren_tc.cuh"
+#include "pdl.cuh"
 
 namespace nmc_siren_detail { void setError(const char* m); }
 
@@ -58,6 +59,7 @@ template <int H>
 __global__ void __launch_bounds__(kThreads, H == 64 ? 2 : 1)
 sirenBackwardTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 				const float* __restrict__ zSaved, const float* __restrict__ gy, float* __restrict__ dZ) {
+	nmc_pdl::gridEnter();
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned char* Dhi = smem;                       // dZ_l [128 samples x H neurons], K-major (K = neurons of layer l)
 	unsigned char* Dlo = Dhi + kTile*H*4;
@@ -251,6 +253,7 @@ template <int H>
 __global__ void __launch_bounds__(kThreads)
 sirenWeightGradTc(Params P, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 				  const float* __restrict__ dZ, const float* __restrict__ zSaved, int chunkTc, int chunkFma) {
+	nmc_pdl::gridEnter();
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) unsigned long long mbar;
 	__shared__ uint32_t tmemBaseSh;
@@ -461,10 +464,10 @@ extern "C" int nmc_siren_backward_tc(const nmc_siren_shape* sh, const float* con
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenBackwardTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenBackwardTc<64><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, dZ);
+		if (!e) e = nmc_pdl::launch(sirenBackwardTc<64>, dim3(grid), dim3(kThreads), smem, st, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, z_saved, grad_y, dZ);
 	} else {
 		e = cudaFuncSetAttribute(sirenBackwardTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenBackwardTc<128><<<grid, kThreads, smem, st>>>(P, env, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, z_saved, grad_y, dZ);
+		if (!e) e = nmc_pdl::launch(sirenBackwardTc<128>, dim3(grid), dim3(kThreads), smem, st, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, z_saved, grad_y, dZ);
 	}
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
@@ -502,10 +505,10 @@ extern "C" int nmc_siren_weight_grads_tc(const nmc_siren_shape* sh, const float*
 	cudaError_t e;
 	if (H == 64) {
 		e = cudaFuncSetAttribute(sirenWeightGradTc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenWeightGradTc<64><<<grid, kThreads, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, dZ, z_saved, chunk, chunkFma);
+		if (!e) e = nmc_pdl::launch(sirenWeightGradTc<64>, grid, dim3(kThreads), smem, st, P, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, dZ, z_saved, chunk, chunkFma);
 	} else {
 		e = cudaFuncSetAttribute(sirenWeightGradTc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (!e) sirenWeightGradTc<128><<<grid, kThreads, smem, st>>>(P, sh->in_dim, sh->out_dim, sh->n_hidden_layers, sh->w0, x, n, dZ, z_saved, chunk, chunkFma);
+		if (!e) e = nmc_pdl::launch(sirenWeightGradTc<128>, grid, dim3(kThreads), smem, st, P, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, dZ, z_saved, chunk, chunkFma);
 	}
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;

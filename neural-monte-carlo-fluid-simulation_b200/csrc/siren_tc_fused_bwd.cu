@@ -27,6 +27,7 @@
 #include "../../include/nmcfs_siren.h"
 #include "siren_env.cuh"
 #include "siren_tc.cuh"
+#include "pdl.cuh"
 
 namespace nmc_siren_detail { void setError(const char* m); }
 
@@ -88,6 +89,7 @@ struct Params {
 __global__ void __launch_bounds__(kThreads, 1)
 sirenBackwardFusedTc(Params P, Env env, int inDim, int outDim, int nHidden, float w0, const float* __restrict__ x, long long n,
 					 const float* __restrict__ zSaved, const float* __restrict__ gy, int cluster) {
+	nmc_pdl::gridEnter();
 	extern __shared__ __align__(1024) unsigned char smem[];
 	unsigned char* Dhi = smem;                        // dZ_l [128 x 64], K-major (chain operand)
 	unsigned char* Dlo = Dhi + kTile*H*4;
@@ -588,9 +590,10 @@ extern "C" int nmc_siren_backward_fused_tc(const nmc_siren_shape* sh, const floa
 	const int grid = (int)(want < cap ? want : cap);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-	cudaLaunchAttribute at[1];
+	cudaLaunchAttribute at[2];
 	at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-	cfg.attrs = at; cfg.numAttrs = 1;
+	at[1] = nmc_pdl::attribute();
+	cfg.attrs = at; cfg.numAttrs = nmc_pdl::enabled() ? 2 : 1;
 	e = cudaLaunchKernelEx(&cfg, sirenBackwardFusedTc, P, env, (int)sh->in_dim, (int)sh->out_dim, (int)sh->n_hidden_layers, (float)sh->w0, x, (long long)n, z_saved, grad_y, cluster);
 	if (!e) e = cudaGetLastError();
 	return e ? fail(cudaGetErrorString(e)) : 0;
