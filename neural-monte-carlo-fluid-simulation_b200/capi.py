@@ -55,7 +55,7 @@ EXPORTS = ["nmc_last_error", "nmc_device_count", "nmc_scene_create", "nmc_scene_
            "nmc_scene_dim", "nmc_scene_bbox", "nmc_scene_num_nodes", "nmc_scene_nodes", "nmc_wost_solve",
            "nmc_wost_solve_device", "nmc_wost_solve_stats", "nmc_point_seed", "nmc_probe", "nmc_scene_set_source_async",
            "nmc_measure_peaks", "nmc_measure_issue_peak", "nmc_bessel_table", "nmc_estimate_solution", "nmc_bvc_solve", "nmc_bvc_splat"]
-SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_siren_backward_tc", "nmc_siren_weight_grads_tc", "nmc_siren_backward_fused_tc", "nmc_fit_sample_uniform", "nmc_fit_gather", "nmc_fit_fetch", "nmc_mse_grad_fit", "nmc_adam_update_device", "nmc_adam_step", "nmc_adam_step_device", "nmc_mse_grad"]
+SIREN_EXPORTS = ["nmc_siren_last_error", "nmc_siren_forward", "nmc_siren_backward", "nmc_siren_forward_tc", "nmc_siren_weight_grads", "nmc_siren_backward_tc", "nmc_siren_weight_grads_tc", "nmc_siren_backward_fused_tc", "nmc_fit_sample_uniform", "nmc_fit_gather", "nmc_fit_fetch", "nmc_mse_grad_fit", "nmc_adam_update_device", "nmc_adam_update_fetch", "nmc_adam_step", "nmc_adam_step_device", "nmc_mse_grad"]
 
 _lib = None
 _fp = C.POINTER(C.c_float)
