@@ -28,7 +28,7 @@ prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
 # last iterations: find the Adam kernels
-adam = [i for i, e in enumerate(ev) if "adamKernelDev" in e["name"]]
+adam = [i for i, e in enumerate(ev) if "adamKernelDev" in e["name"] or "adamFetchKernel" in e["name"]]   # the Adam launch closes an iteration
 lo = adam[-4] + 1 if len(adam) >= 4 else 0
 t0 = ev[lo]["ts"]
 last_end = {}
