@@ -330,7 +330,12 @@ NMC_HD bool primRay(const SceneView& S, int ri, V3 o, V3 dir, float tMax, bool o
 	}
 	return false;
 }
-#if defined(NMC_FAST_GEOM)
+// NMC_WHILE_WHILE: `if` = one node per trip (a leaf is processed right after it is popped); `while` (-DNMC_TRAV_WHILE_WHILE) = a lane
+// walks inner nodes until it holds a leaf, then the lanes work on their leaves together.  The second form was tried because ncu showed
+// the 3D record loop running with 7 of 32 lanes on a 20 k-triangle obstacle; measured on the B200 it LOSES (16.5 k segments 1.84e8 ->
+// 1.28e8 walks/s, 131 k 5.4e7 -> 3.3e7, 20 k triangles 1.29e7 -> 1.16e7: lanes holding a leaf wait for the slowest inner-node walk), so
+// it is off; profiles/experiments/r02_while_while_mbvh.jsonl.
+#if defined(NMC_FAST_GEOM) && defined(NMC_TRAV_WHILE_WHILE)
 #define NMC_WHILE_WHILE while
 #else
 #define NMC_WHILE_WHILE if
@@ -345,7 +350,7 @@ NMC_TRAV bool rayIntersect(const SceneView& S, Stack& stack, V3 o, V3 dir, float
 	if (!boxRay(xyz(S.nodes[0]), xyz(S.nodes[1]), o, invD, tMax, b0, b1)) return false;
 	stack.put(0, 0, b0);
 	int sp = 0;
-	int refOffset = 0, nLeaf = 0; // default mode: inner nodes until the lane holds a leaf, then the leaves together (see closestSilhouette)
+	int refOffset = 0, nLeaf = 0; // see NMC_WHILE_WHILE
 	while (sp >= 0 || nLeaf > 0) {
 		NMC_WHILE_WHILE (sp >= 0 && nLeaf == 0) {
 			int ni = stack.node(sp); float cd = stack.dist(sp); sp--;
@@ -411,9 +416,7 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 	if (!(b0 <= r2)) return false;
 	stack.put(0, 0, b0);
 	int sp = 0;
-	// Default mode ("while-while"): a lane first walks inner nodes until it holds a leaf, then the lanes work on their leaves
-	// together -- ncu on a 20 k-triangle obstacle showed the record loop running with 7 of 32 lanes (the others were between
-	// leaves) and waiting on its loads for half of all samples.  Each lane still visits its nodes in the same order.
+	// one node per trip, or (NMC_WHILE_WHILE = while) inner nodes until the lane holds a leaf; the nodes are visited in the same order
 	int silOffset = 0, nSil = 0;
 	while (sp >= 0 || nSil > 0) {
 		NMC_WHILE_WHILE (sp >= 0 && nSil == 0) {
