@@ -27,7 +27,7 @@ mss = importlib.util.module_from_spec(spec); spec.loader.exec_module(mss)
 n_pts = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 sizes2d = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 and sys.argv[2] else [1024, 16384, 131072]
 levels3d = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 and sys.argv[3] else [3, 5, 6]
-mode = os.environ.get("NMC_BIG_MESH", "packet")
+mode = os.environ.get("NMC_BIG_MESH", "default")
 tmp = tempfile.mkdtemp(prefix="mbvh_")
 
 
