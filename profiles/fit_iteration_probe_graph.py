@@ -9,10 +9,10 @@ import torch, util, __graft_entry__ as ge
 pkg = ge.load_package()
 st = import_module(pkg.__name__ + ".stepper")
 s = st.SplitStepper(util.load_case("taylorgreen_active"), scene_size=(0.0, 2*math.pi, 0.0, 2*math.pi), grid_resolution=200,
-                    wost_resolution=64, max_n_iters=8, early_stop=False, use_cuda_graph=True, seed=1)
+                    wost_resolution=64, max_n_iters=40, early_stop=False, use_cuda_graph=True, seed=1)
 s._sync_prev()
-s.advect_velocity(8)
+s.advect_velocity(40)   # 3 warm-up + 17 single-iteration replays + one replay of the 20-iteration graph
 s._sync_prev()
-s.project_velocity(8)
+s.project_velocity(40)
 torch.cuda.synchronize()
 print("done")
