@@ -180,4 +180,13 @@ void emuf_closest_warp(void* h, const float* pts, int n, float* out) {
 		if (i < n) { out[2*i] = f ? b.d : kMaxF; out[2*i + 1] = f ? (dot(x - b.p, b.n) > 0.0f ? 1.0f : -1.0f)*b.d : kMaxF; }
 	});
 }
+// builder tables for the cone test: nodes (16 floats each), the default mode's cones (4 floats per node), silhouette records
+int emuf_num_nodes(void* h) { return ((FastScene*)h)->flat.nNodes; }
+int emuf_num_sil_refs(void* h) { return ((FastScene*)h)->flat.nSilRefs; }
+void emuf_tables(void* h, float* nodes, float* cones, float* sils) {
+	FastScene* s = (FastScene*)h;
+	memcpy(nodes, s->flat.nodes.data(), s->flat.nodes.size()*sizeof(Q4));
+	memcpy(cones, s->flat.coneF.data(), s->flat.coneF.size()*sizeof(Q4));
+	memcpy(sils, s->flat.sils.data(), s->flat.sils.size()*sizeof(Q4));
+}
 }

@@ -580,6 +580,63 @@ def test_warp_packet_traversals_equal_the_private_ones(emu_fast, oracle_lib, tmp
         emu_fast.emuf_scene_destroy(h); osc.close()
 
 
+def test_default_mode_normal_cones(emu_fast, oracle_lib):
+    """scene_build.cpp conesFast: every node's cone of the default mode bounds the face normals of all silhouette records below it
+    (so `dot(view, n0) dot(view, n1) < 0` cannot hold where the cone test says no); where the reference's cone culls (half-angle
+    below pi/2) it is kept as it is; on the closed 3D mesh the reference's cones are useless (half-angles near pi) and the own
+    ones are narrow."""
+    for name, want_own in (("box_sphere", True), ("channel_circle", False), ("karman3d", True), ("karman", False)):
+        cfg = util.load_case(name)
+        dim, sc = cfg["dim"], cfg["scene"]
+        v, p = oracle_lib.load_obj(sc["boundary"], dim, False)
+        src = util.source_grid(dim); shp = list(src.shape) + [1]*(3 - dim)
+        h = C.c_void_p(emu_fast.emuf_scene_create(dim, _fp(v), len(v), p.ctypes.data_as(C.POINTER(C.c_int)), len(p), _fp(src), shp[0], shp[1], shp[2],
+                                                  C.c_float(sc.get("absorptionCoeff", 0.0)), int(sc.get("isWatertight", False)), int(sc.get("isDoubleSided", False))))
+        n, nref = emu_fast.emuf_num_nodes(h), emu_fast.emuf_num_sil_refs(h)
+        per = 2 if dim == 2 else 4
+        nodes, cones, sils = np.zeros((n, 16), np.float32), np.zeros((n, 4), np.float32), np.zeros((max(nref, 1), per, 4), np.float32)
+        emu_fast.emuf_tables(h, _fp(nodes), _fp(cones), _fp(sils))
+        n_refs = nodes[:, 3].view(np.int32); second = nodes[:, 7].view(np.int32)
+        ref_half = nodes[:, 11]; sil_off = nodes[:, 13].view(np.int32); n_sil = nodes[:, 14].view(np.int32)
+        w = cones[:, 3]
+        assert np.array_equal(w == 2.0, ref_half < 0)                       # "no silhouettes below" agrees with the reference's marker
+        keep = (ref_half >= 0) & (ref_half < np.pi/2)
+        assert np.allclose(w[keep], np.cos(ref_half[keep]), atol=1e-6) and np.allclose(cones[keep, :3], nodes[keep, 8:11])
+        own = w > 3.0
+        assert not (own & keep).any()
+        if want_own and dim == 3 and name == "box_sphere":
+            leaf = n_refs > 0
+            assert (ref_half[leaf & (ref_half >= 0)] > 3.0).mean() > 0.9         # the reference's leaf cones: half-angles near pi
+            assert (w[leaf & own] - 4.0 > 0.9).mean() > 0.9                      # the own leaf cones: a few degrees
+        if not want_own:
+            assert keep.sum() > 0.5*(w != 2.0).sum()
+
+        # subtree ranges in the depth-first layout: node i covers [i, end_i)
+        end = np.zeros(n, np.int64)
+
+        def span(i):
+            if n_refs[i] > 0:
+                end[i] = i + 1
+            else:
+                span(i + 1); span(i + second[i]); end[i] = end[i + second[i]]
+            return end[i]
+        import sys
+        sys.setrecursionlimit(10000)
+        span(0)
+        checked = 0
+        for i in np.flatnonzero(own)[:400]:
+            axis, cos_h = cones[i, :3].astype(np.float64), float(w[i]) - 4.0
+            leaves = [j for j in range(i, int(end[i])) if n_refs[j] > 0]
+            for j in leaves:
+                for r in range(sil_off[j], sil_off[j] + n_sil[j]):
+                    n0, n1 = (sils[r, 1, :2], sils[r, 1, 2:4]) if dim == 2 else (sils[r, 2, :3], sils[r, 3, :3])
+                    for nn in (n0, n1):
+                        assert float(np.dot(axis[:len(nn)], nn)) >= cos_h - 1e-5, (name, int(i), r)
+                        checked += 1
+        assert checked > 0 or not own.any()
+        emu_fast.emuf_scene_destroy(h)
+
+
 def test_bessel_lookup_table_against_scipy():
     """The default mode's table of i0e, i1e, k0e, k1e (cubic pieces in log2 x, csrc/bessel_table.cpp) against scipy's
     exponentially scaled Bessel functions in double: relative error below 1e-6 (float evaluation of log2 x included) over the whole range a walk can reach
