@@ -34,6 +34,7 @@ struct SceneView {
 	const float4* primN;
 	const float4* nrmV;
 	const float4* sils;
+	const float4* silsF;   // 3D default mode: the two face planes of every silhouette reference (prefilter, scene_build.cpp)
 	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
 	const float4* grpP; const float4* grpS; // (lo, hi) per group (8 in 2D, 4 in 3D) of ray primitives / silhouettes
 	const float4* supP; const float4* supS; // (lo, hi) per 32 groups: second level of the flat scans on large meshes
@@ -404,6 +405,39 @@ NMC_HD bool silhouetteCandidate(V3 n0, V3 n1, V3 rel, float precision, float r2)
 	const float s0 = dot(n0, rel), s1 = dot(n1, rel);
 	return s0*s1 < 0.0f || fminf(fabsf(s0), fabsf(s1)) <= precision*fmaxf(1.0f, sqrtf(r2));
 }
+#if defined(NMC_FAST_GEOM)
+// One record of a 3D leaf after the prefilter (default mode): the tests of the generic loop below, in the same order.
+NMC_HD void silhouetteRecord3(const SceneView& S, int ri, V3 x, bool flip, float sqMinR, float precision, float& r2, bool& found, int& lastId, float& dOut) {
+	const float4 s0 = S.sils[4*ri], s1 = S.sils[4*ri + 1], s2 = S.sils[4*ri + 2], s3 = S.sils[4*ri + 3];
+	const int flags = asInt(s0.w), id = asInt(s1.w);
+	if (id == lastId || sqMinR >= r2) return;
+	V3 pt; float t;
+	const float d = closestOnSegment(xyz(s0), xyz(s1), x, pt, t);
+	if (d*d > r2) return;
+	bool isSil = (flags & 3) != 3;
+	if (!isSil) isSil = isSilhouette(s2.w, xyz(s2), xyz(s3), x - pt, d, flip, precision);
+	if (isSil) { found = true; r2 = minS(r2, d*d); dOut = d; lastId = id; }
+}
+// The records of a 3D leaf, two at a time: the plane pairs of both (32 bytes each, SceneView::silsF) are requested together, so a
+// leaf of seven records costs four load round trips instead of seven (the loop is latency-bound: ncu), and
+// the full record (64 bytes) is only read for the few that pass.
+NMC_HD void silhouetteLeaf3(const SceneView& S, int silOffset, int nSil, V3 x, bool flip, float sqMinR, float precision, float& r2, bool& found, int& lastId, float& dOut) {
+	for (int p = 0; p < nSil; p += 2) {
+		const int ri = silOffset + p;
+		const bool two = p + 1 < nSil;
+		const float4 a0 = S.silsF[2*ri], a1 = S.silsF[2*ri + 1];
+		const float4 b0 = S.silsF[2*(two ? ri + 1 : ri)], b1 = S.silsF[2*(two ? ri + 1 : ri) + 1];
+		const float band = precision*fmaxf(1.0f, sqrtf(r2));
+		const float sa0 = fmaf(a0.x, x.x, fmaf(a0.y, x.y, fmaf(a0.z, x.z, a0.w))), sa1 = fmaf(a1.x, x.x, fmaf(a1.y, x.y, fmaf(a1.z, x.z, a1.w)));
+		const float sb0 = fmaf(b0.x, x.x, fmaf(b0.y, x.y, fmaf(b0.z, x.z, b0.w))), sb1 = fmaf(b1.x, x.x, fmaf(b1.y, x.y, fmaf(b1.z, x.z, b1.w)));
+		const bool ca = sa0*sa1 < 0.0f || fminf(fabsf(sa0), fabsf(sa1)) <= band;
+		const bool cb = two && (sb0*sb1 < 0.0f || fminf(fabsf(sb0), fabsf(sb1)) <= band);
+		if (ca) silhouetteRecord3(S, ri, x, flip, sqMinR, precision, r2, found, lastId, dOut);
+		if (cb) silhouetteRecord3(S, ri + 1, x, flip, sqMinR, precision, r2, found, lastId, dOut);
+		if (sqMinR >= r2) break;
+	}
+}
+#endif
 // closest silhouette point: Sbvh::findClosestSilhouettePointFromNode (sbvh.inl:1093-1255) with
 // SilhouetteVertex/Edge::findClosestSilhouettePoint (vertex_silhouettes.inl:89-118, edge_silhouettes.inl:112-143)
 template <int DIM, class M, class Stack>
@@ -460,6 +494,9 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 				else if (hit1) { sp++; stack.put(sp, c1, b1); }
 			}
 		}
+#if defined(NMC_FAST_GEOM)
+		if (DIM == 3) { silhouetteLeaf3(S, silOffset, nSil, x, flip, sqMinR, precision, r2, found, lastId, dOut); nSil = 0; }
+#endif
 		{
 			for (int p = 0; p < nSil; p++) {
 				int ri = silOffset + p;

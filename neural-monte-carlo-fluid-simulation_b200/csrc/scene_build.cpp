@@ -378,6 +378,7 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 		}
 	}
 	out.sils.resize((size_t)(dim == 2 ? 2 : 4)*refs.size());
+	out.silsF.assign(dim == 3 ? 2*refs.size() : 0, Q4{0, 0, 0, 0});
 	std::vector<char> emitted(B.sil.size(), 0);
 	for (size_t r = 0; r < refs.size(); r++) {
 		const Sil& s = B.sil[refs[r]];
@@ -395,6 +396,12 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 			out.sils[4*r + 1] = {pb.x, pb.y, pb.z, bits(s.id)};
 			out.sils[4*r + 2] = {n0.x, n0.y, n0.z, refAngle[r]};
 			out.sils[4*r + 3] = {n1.x, n1.y, n1.z, 0.0f};
+			// plane form of the prefilter (nmc_geom.cuh silhouetteCandidate): s = n.x + d = n.(x - pa); a record with fewer than two
+			// faces is always a silhouette candidate (zeros pass the band test)
+			if (flags == 3) {
+				out.silsF[2*r + 0] = {n0.x, n0.y, n0.z, -dot(n0, pa)};
+				out.silsF[2*r + 1] = {n1.x, n1.y, n1.z, -dot(n1, pa)};
+			}
 		}
 		if (!emitted[refs[r]]) { // de-duplicated copy: a silhouette shared by several leaves appears once
 			emitted[refs[r]] = 1;
