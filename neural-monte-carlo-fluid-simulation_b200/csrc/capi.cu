@@ -94,13 +94,13 @@ extern "C" nmc_scene* nmc_scene_create(int dim, const float* verts, int nV, cons
 	v.absorption = opts->absorptionCoeff; v.watertight = opts->isWatertight != 0; v.doubleSided = opts->isDoubleSided != 0;
 	bool ok = upload(s->d_nodes, s->flat.nodes) == cudaSuccess && upload(s->d_prims, s->flat.prims) == cudaSuccess &&
 			  upload(s->d_primN, s->flat.primN) == cudaSuccess && upload(s->d_nrmV, s->flat.nrmV) == cudaSuccess &&
-			  upload(s->d_sils, s->flat.sils) == cudaSuccess && upload(s->d_silsU, s->flat.silsU) == cudaSuccess && upload(s->d_grpP, s->flat.grpP) == cudaSuccess && upload(s->d_grpS, s->flat.grpS) == cudaSuccess && upload(s->d_rayP, s->flat.rayP) == cudaSuccess && upload(s->d_rayN, s->flat.rayN) == cudaSuccess && upload(s->d_supP, s->flat.supP) == cudaSuccess && upload(s->d_supS, s->flat.supS) == cudaSuccess && upload(s->d_coneF, s->flat.coneF) == cudaSuccess && upload(s->d_silsF, s->flat.silsF) == cudaSuccess &&
+			  upload(s->d_sils, s->flat.sils) == cudaSuccess && upload(s->d_silsU, s->flat.silsU) == cudaSuccess && upload(s->d_grpP, s->flat.grpP) == cudaSuccess && upload(s->d_grpS, s->flat.grpS) == cudaSuccess && upload(s->d_rayP, s->flat.rayP) == cudaSuccess && upload(s->d_rayN, s->flat.rayN) == cudaSuccess && upload(s->d_supP, s->flat.supP) == cudaSuccess && upload(s->d_supS, s->flat.supS) == cudaSuccess && upload(s->d_coneF, s->flat.coneF) == cudaSuccess && upload(s->d_silsF, s->flat.silsF) == cudaSuccess && upload(s->d_treeF, s->flat.treeF) == cudaSuccess &&
 			  cudaMalloc((void**)&s->d_counters, sizeof(Counters)) == cudaSuccess &&
 			  cudaMalloc((void**)&s->d_workCounter, sizeof(unsigned int)) == cudaSuccess;
 	for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&s->ev[i]) == cudaSuccess;
 	if (!ok) { fail(NMC_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError())); nmc_scene_destroy(s); return nullptr; }
 	v.nodes = s->d_nodes; v.prims = s->d_prims; v.primN = s->d_primN; v.nrmV = s->d_nrmV; v.sils = s->d_sils;
-	v.silsU = s->d_silsU; v.nSilU = s->flat.nSilU; v.grpP = s->d_grpP; v.grpS = s->d_grpS; v.rayP = s->d_rayP; v.rayN = s->d_rayN; v.nRay = s->flat.nRay; v.supP = s->d_supP; v.supS = s->d_supS; v.coneF = s->d_coneF; v.silsF = s->d_silsF;
+	v.silsU = s->d_silsU; v.nSilU = s->flat.nSilU; v.grpP = s->d_grpP; v.grpS = s->d_grpS; v.rayP = s->d_rayP; v.rayN = s->d_rayN; v.nRay = s->flat.nRay; v.supP = s->d_supP; v.supS = s->d_supS; v.coneF = s->d_coneF; v.silsF = s->d_silsF; v.treeF = s->d_treeF;
 	if (setSource(s, src, n0, n1, n2, 0) != NMC_OK) { nmc_scene_destroy(s); return nullptr; }
 	return s;
 }
@@ -108,7 +108,7 @@ extern "C" nmc_scene* nmc_scene_create(int dim, const float* verts, int nV, cons
 extern "C" void nmc_scene_destroy(nmc_scene* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
-	cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_primN); cudaFree(s->d_nrmV); cudaFree(s->d_sils); cudaFree(s->d_silsU); cudaFree(s->d_grpP); cudaFree(s->d_grpS); cudaFree(s->d_rayP); cudaFree(s->d_rayN); cudaFree(s->d_supP); cudaFree(s->d_supS); cudaFree(s->d_coneF); cudaFree(s->d_silsF);
+	cudaFree(s->d_nodes); cudaFree(s->d_prims); cudaFree(s->d_primN); cudaFree(s->d_nrmV); cudaFree(s->d_sils); cudaFree(s->d_silsU); cudaFree(s->d_grpP); cudaFree(s->d_grpS); cudaFree(s->d_rayP); cudaFree(s->d_rayN); cudaFree(s->d_supP); cudaFree(s->d_supS); cudaFree(s->d_coneF); cudaFree(s->d_silsF); cudaFree(s->d_treeF);
 	cudaFree(s->d_src); cudaFree(s->d_work); cudaFree(s->d_lhs); cudaFree(s->d_counters); cudaFree(s->d_workCounter);
 	for (int i = 0; i < 4; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	cudaGetLastError();

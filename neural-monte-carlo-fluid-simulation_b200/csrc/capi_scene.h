@@ -13,7 +13,7 @@ struct nmc_scene {
 	std::vector<float> verts;   // the mesh as passed to nmc_scene_create (boundary value caching samples its primitives)
 	std::vector<int> prims;
 	nmc::SceneView view;
-	float4 *d_nodes = nullptr, *d_prims = nullptr, *d_primN = nullptr, *d_nrmV = nullptr, *d_sils = nullptr, *d_silsU = nullptr, *d_grpP = nullptr, *d_grpS = nullptr, *d_rayP = nullptr, *d_rayN = nullptr, *d_supP = nullptr, *d_supS = nullptr, *d_coneF = nullptr, *d_silsF = nullptr;
+	float4 *d_nodes = nullptr, *d_prims = nullptr, *d_primN = nullptr, *d_nrmV = nullptr, *d_sils = nullptr, *d_silsU = nullptr, *d_grpP = nullptr, *d_grpS = nullptr, *d_rayP = nullptr, *d_rayN = nullptr, *d_supP = nullptr, *d_supS = nullptr, *d_coneF = nullptr, *d_silsF = nullptr, *d_treeF = nullptr;
 	float* d_src = nullptr; size_t srcCap = 0;
 	// grow-only work buffers
 	float* d_work = nullptr; size_t workCap = 0;      // points + outputs for the host-buffer entry point

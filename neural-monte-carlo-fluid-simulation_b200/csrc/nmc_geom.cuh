@@ -34,6 +34,7 @@ struct SceneView {
 	const float4* primN;
 	const float4* nrmV;
 	const float4* sils;
+	const float4* treeF;   // default mode: 6 words per inner node, both children's boxes / cone codes / cone axes (scene_build.cpp)
 	const float4* silsF;   // 3D default mode: the two face planes of every silhouette reference (prefilter, scene_build.cpp)
 	const float4* silsU; int nSilU;   // distinct silhouettes (flat scan)
 	const float4* grpP; const float4* grpS; // (lo, hi) per group (8 in 2D, 4 in 3D) of ray primitives / silhouettes
@@ -542,6 +543,75 @@ NMC_TRAV bool closestSilhouette(const SceneView& S, Stack& stack, V3 x, float r2
 	return found;
 }
 
+#if defined(NMC_FAST_GEOM)
+// closestSilhouette() of the default mode over the per-node child blocks (SceneView::treeF): the same tests in the same order,
+// but an inner-node visit is ONE round trip of six independent 16-byte loads (the generic form reads the node's child offset
+// first and then eight words of the two children plus their cones: two dependent trips, ten scattered words), and a leaf is
+// recognised from the sign of its stack entry.  ncu on the big-mesh kernels: dependent-load latency is what bounds them.
+template <int DIM, class Stack>
+NMC_TRAV bool closestSilhouetteFast(const SceneView& S, Stack& stack, V3 x, float r2, bool flip, float sqMinR, float precision, float& dOut) {
+	if (S.nNodes == 0) return false;
+	if (sqMinR >= r2) return false;
+	float b0, b1, tmp;
+	bool found = false; int lastId = -1;
+	boxSqDist(xyz(S.nodes[0]), xyz(S.nodes[1]), x, b0, tmp);
+	if (!(b0 <= r2)) return false;
+	stack.put(0, asInt(S.nodes[0].w) > 0 ? ~0 : 0, b0);
+	int sp = 0;
+	while (sp >= 0) {
+		const int e = stack.node(sp); const float cd = stack.dist(sp); sp--;
+		if (cd > r2) continue;
+		if (e < 0) { // leaf
+			const float4 nd = S.nodes[4*(~e) + 3];
+			const int silOffset = asInt(nd.y), nSil = asInt(nd.z);
+			if (DIM == 3) silhouetteLeaf3(S, silOffset, nSil, x, flip, sqMinR, precision, r2, found, lastId, dOut);
+			else for (int p = 0; p < nSil; p++) { // SilhouetteVertex::findClosestSilhouettePoint, as in closestSilhouette()
+				const int ri = silOffset + p;
+				const float4 s0 = S.sils[2*ri], s1 = S.sils[2*ri + 1];
+				const int flags = asInt(s0.z), id = asInt(s0.w);
+				if (id == lastId) continue;
+				if (sqMinR >= r2) continue;
+				const V3 viewDir = x - mk(s0.x, s0.y, 0.0f);
+				if (dot(viewDir, viewDir) > r2) continue;
+				const float d = norm(viewDir);
+				const V3 n0 = mk(s1.x, s1.y, 0.0f), n1 = mk(s1.z, s1.w, 0.0f);
+				if (d*d > r2) continue;
+				bool isSil = (flags & 3) != 3;
+				if (!isSil) isSil = isSilhouette(n0.x*n1.y - n1.x*n0.y, n0, n1, viewDir, d, flip, precision);
+				if (isSil && d*d <= r2) {
+					found = true;
+					r2 = minS(r2, d*d);
+					dOut = d; lastId = id;
+					if (sqMinR >= r2) break;
+				}
+			}
+			continue;
+		}
+		const float4* q = S.treeF + 6*(size_t)e;
+		const float4 l0 = q[0], h0 = q[1], a0 = q[2], l1 = q[3], h1 = q[4], a1 = q[5];
+		const int c0 = e + 1, c1 = e + asInt(h1.w);
+		bool hit0 = false, hit1 = false;
+		if (l0.w != 2.0f) { // the subtree holds silhouettes
+			boxSqDist(xyz(l0), xyz(h0), x, b0, tmp);
+			hit0 = b0 <= r2 && coneOverlapFast(xyz(a0), l0.w, x, xyz(l0), xyz(h0), b0, 2.0f*precision);
+		}
+		if (l1.w != 2.0f) {
+			boxSqDist(xyz(l1), xyz(h1), x, b1, tmp);
+			hit1 = b1 <= r2 && coneOverlapFast(xyz(a1), l1.w, x, xyz(l1), xyz(h1), b1, 2.0f*precision);
+		}
+		const int e0 = asInt(a0.w) > 0 ? ~c0 : c0, e1 = asInt(a1.w) > 0 ? ~c1 : c1;
+		if (hit0 && hit1) {
+			int closer = e0, other = e1;
+			if (b1 < b0) { float t = b0; b0 = b1; b1 = t; closer = e1; other = e0; }
+			sp++; stack.put(sp, other, b1);
+			sp++; stack.put(sp, closer, b0);
+		} else if (hit0) { sp++; stack.put(sp, e0, b0); }
+		else if (hit1) { sp++; stack.put(sp, e1, b1); }
+	}
+	return found;
+}
+#endif
+
 // ---- flat scans for small scenes (default mode only) ------------------------------------------------------
 // With a few dozen primitives the tree bookkeeping (stack traffic, box sorting, cone tests) costs more than it
 // saves, and it makes the lanes of a warp diverge.  These scans visit the records group by group (8 in 2D, 4 in
@@ -757,7 +827,11 @@ NMC_HD float starRadius(const SceneView& S, Stack& stack, V3 x, float minR, floa
 		bool flip = !flipOrient; // FCPW's convention needs flipped normals (:629)
 		float r2 = maxR < kMaxF ? maxR*maxR : kMaxF;
 		float d;
+#if defined(NMC_FAST_GEOM) && !defined(NMC_NO_TREE_BLOCKS)
+		if (closestSilhouetteFast<DIM>(S, stack, x, r2, flip, minR*minR, prec, d)) return maxS(d, minR);
+#else
 		if (closestSilhouette<DIM, M>(S, stack, x, r2, flip, minR*minR, prec, d)) return maxS(d, minR);
+#endif
 	}
 	return maxS(maxR, minR);
 }

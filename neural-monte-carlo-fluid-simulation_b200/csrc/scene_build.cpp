@@ -350,6 +350,22 @@ void buildFlatScene(int dim, const float* verts, int nV, const int* prims, int n
 	out.coneF.assign(B.nodes.size(), Q4{0, 0, 0, 2.0f});
 	if (!B.nodes.empty()) B.conesFast(refs, refFN, 0, (int)B.nodes.size(), out.coneF);
 
+	// silhouette-traversal blocks of the default mode (nmc_geom.cuh closestSilhouetteFast): everything an inner-node visit needs about
+	// its two children in 96 contiguous bytes -- one round trip instead of two dependent ones over ten scattered words
+	out.treeF.assign((size_t)6*B.nodes.size(), Q4{0, 0, 0, 0});
+	for (size_t i = 0; i < B.nodes.size(); i++) {
+		const BuildNode& n = B.nodes[i];
+		if (n.nRefs > 0) continue;
+		const size_t c[2] = {i + 1, i + (size_t)n.second};
+		for (int k = 0; k < 2; k++) {
+			const BuildNode& ch = B.nodes[c[k]];
+			const Q4& cone = out.coneF[c[k]];
+			out.treeF[6*i + 3*k + 0] = {ch.box.lo.x, ch.box.lo.y, ch.box.lo.z, cone.w};
+			out.treeF[6*i + 3*k + 1] = {ch.box.hi.x, ch.box.hi.y, ch.box.hi.z, bits(k == 1 ? n.second : 1)};
+			out.treeF[6*i + 3*k + 2] = {cone.x, cone.y, cone.z, bits(ch.nRefs)};
+		}
+	}
+
 	// flatten
 	out.nNodes = (int)B.nodes.size(); out.nPrims = nP; out.nSilRefs = (int)refs.size(); out.maxDepth = B.maxDepth;
 	out.nodes.resize((size_t)4*out.nNodes);

@@ -18,6 +18,7 @@ struct FlatScene {
 	std::vector<Q4> primN;  // 1 per primitive
 	std::vector<Q4> nrmV;   // 2 (2D) / 6 (3D) per primitive
 	std::vector<Q4> sils;   // 2 (2D) / 4 (3D) per silhouette reference
+	std::vector<Q4> treeF;  // default mode: 6 per node -- an inner node's two children as (lo, cone code), (hi, -), (cone axis, nRefs of the child) each
 	std::vector<Q4> silsF;  // 3D, default mode: 2 per silhouette reference, the two face planes (n, -n.pa) of the plane-side prefilter (zeros: always a candidate)
 	std::vector<Q4> silsU;  // the same records, one per distinct silhouette (flat scan of small scenes)
 	int nSilU = 0;

@@ -68,7 +68,7 @@ void* emuf_scene_create(int dim, const float* verts, int nV, const int* prims, i
 	s->src.assign(src, src + cnt);
 	SceneView& v = s->v; memset(&v, 0, sizeof(v));
 	v.dim = dim; v.nNodes = s->flat.nNodes; v.nPrims = s->flat.nPrims; v.nSilRefs = s->flat.nSilRefs;
-	v.nodes = (const float4*)s->flat.nodes.data(); v.coneF = (const float4*)s->flat.coneF.data(); v.silsF = (const float4*)s->flat.silsF.data(); v.prims = (const float4*)s->flat.prims.data();
+	v.nodes = (const float4*)s->flat.nodes.data(); v.coneF = (const float4*)s->flat.coneF.data(); v.silsF = (const float4*)s->flat.silsF.data(); v.treeF = (const float4*)s->flat.treeF.data(); v.prims = (const float4*)s->flat.prims.data();
 	v.primN = (const float4*)s->flat.primN.data(); v.nrmV = (const float4*)s->flat.nrmV.data(); v.sils = (const float4*)s->flat.sils.data();
 	for (int k = 0; k < 3; k++) { v.bboxLo[k] = s->flat.bboxLo[k]; v.bboxHi[k] = s->flat.bboxHi[k]; }
 	v.src = s->src.data(); v.n0 = n0; v.n1 = n1; v.n2 = dim == 3 ? n2 : 1;
