@@ -528,14 +528,15 @@ cudaError_t launchFast(const SceneView& S, const SolverParams& o, const float* d
 	if (flat && stageQuadsFor(true)*sizeof(float4) > 48*1024) flat = false;
 	size_t quads = stageQuadsFor(flat);
 	// Beyond the flat-scan limit, by measurement (profiles/r02_mbvh.jsonl, B200, 1e3 .. 1.3e5 primitives): 2D per-lane tree
-	// traversals; 3D the two-level flat scan up to 8192 triangles (1292: 2.0e8 walks/s against 1.6e8 packet / 7e7 tree), per-lane
-	// tree traversals above (82 k: 5.1e6 against 3.9e6 packet).  The warp-packet traversals (FLAT == 3, nmc_packet.cuh: one traversal
-	// per warp, warp-uniform node loads, register stack) are kept selectable: they win only between ~1e4 and ~3e4 triangles
-	// (+14 % at 20 k) and lose in 2D (the union of 32 lanes' search regions is several times one lane's).
+	// traversals; 3D the two-level flat scan for small meshes (1292 triangles: 1.9e8 walks/s against 1.2e8 tree / 1.5e8 packet), per-lane
+	// tree traversals for large ones (20 k: 2.1e7 against 9.6e6 flat2; 82 k: 8.3e6).  The flat scan falls like 1/N, the tree like
+	// N^-0.6: the two measured end points cross near 4700 triangles, hence the switch at 4096.  The warp-packet traversals
+	// (FLAT == 3, nmc_packet.cuh: one traversal per warp, warp-uniform node loads, register stack) are kept selectable: they never beat
+	// the better of the two by much and lose in 2D (the union of 32 lanes' search regions is several times one lane's).
 	// NMC_BIG_MESH = packet | tree | flat2 forces one path (A/B measurements, tests).
 	static const int bigMode = [] { const char* e = getenv("NMC_BIG_MESH"); return !e ? -1 : e[0] == 't' ? 0 : e[0] == 'f' ? 2 : e[0] == 'p' ? 3 : -1; }();
 	const bool packet = !flat && bigMode == 3 && maxDepth + 2 <= NMC_STACK;
-	const bool flat2 = !flat && (bigMode == 2 || (bigMode == -1 && S.nPrims <= 8192)) && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
+	const bool flat2 = !flat && (bigMode == 2 || (bigMode == -1 && S.nPrims <= 4096)) && dim == 3 && maxDepth + 3 <= 24 && S.supP && S.supS;
 	if (flat2 || packet) quads = 0; // FLAT == 2 / 3 stage nothing (see the kernel)
 	size_t bytes = quads*sizeof(float4);
 	int stageQuads = bytes <= 48*1024 ? (int)quads : 0; // larger structures are read through L1/L2
